@@ -1,0 +1,189 @@
+/* ntf_b200.h -- C ABI of libntf_b200.so: the B200 (sm_100a) kernels behind OpeNTF's Fnn/Bnn hot path.
+ *
+ * The reference (fani-lab/OpeNTF) is pure Python: it has no FFI / operator registry; its "operators" for this
+ * path are ATen calls made from src/mdl/fnn.py.  Each entry point below replaces one group of those call
+ * sites (cited as file:line under /root/reference) and is what a ctypes/cffi binding inside the reference
+ * would call (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer.
+ *   - the caller owns every buffer (parameters, optimiser state, CSR, outputs, workspace); the library
+ *     allocates nothing that outlives a call.  `*_workspace_bytes` tells how much scratch a call needs.
+ *   - every call is asynchronous and ordered on `stream` (a cudaStream_t passed as void*).
+ *   - return value: NTF_OK or a negative ntf_status; ntf_last_error() gives the message of the calling
+ *     thread's last failure.  No C++ exception crosses this boundary.  There is no CPU fallback: a
+ *     device that is not sm_100 makes ntf_create fail.
+ *   - matrices are row-major fp32.  A batch is B consecutive rows of a CSR: `indptr` points at the batch's
+ *     first row (B+1 entries, ABSOLUTE offsets into `indices`), so a batch of the epoch-permuted CSR built
+ *     by ntf_csr_gather is addressed by pointer arithmetic only.
+ *   - precision: NTF_FP32 = CUDA-core fp32 FMA chains (bit-stable, the parity mode);
+ *                NTF_TF32 = tcgen05 kind::tf32 MMA with fp32 accumulation in TMEM (the fast mode).
+ */
+#ifndef NTF_B200_H
+#define NTF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTF_ABI_VERSION 1
+
+typedef enum {
+  NTF_OK = 0,
+  NTF_ERR_BAD_ARG = -1,      /* null pointer, negative size, misaligned buffer ...            */
+  NTF_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels are built for                   */
+  NTF_ERR_CUDA = -3,         /* a CUDA runtime / driver call failed (message has the string)   */
+  NTF_ERR_WORKSPACE = -4,    /* workspace smaller than *_workspace_bytes says                  */
+  NTF_ERR_DEVICE = -5        /* not an sm_100 device                                           */
+} ntf_status;
+
+typedef enum { NTF_FP32 = 0, NTF_TF32 = 1 } ntf_precision;
+typedef enum { NTF_NS_NONE = 0, NTF_NS_UNIFORM = 1, NTF_NS_UNIGRAM = 2, NTF_NS_UNIGRAM_B = 3 } ntf_nsd;
+
+typedef struct ntf_ctx ntf_ctx; /* opaque per-device handle (device properties + TMA encoder entry point) */
+
+int ntf_version(void);
+int ntf_last_error(char* buf, size_t n);
+/* one handle per device; the reference keeps the equivalent state in torch's globals (ntf.py:12-14) */
+int ntf_create(int device, ntf_ctx** out);
+int ntf_destroy(ntf_ctx* ctx);
+int ntf_sm_count(const ntf_ctx* ctx);
+
+/* ---- batching: replaces DataLoader(shuffle) + NtfDataset.__getitem__ (fnn.py:95-97, ntf.py:17-25) ------------
+ * dst row i = src row rows[i] (rows == NULL: identity).  dst_indptr gets n+1 offsets (exclusive scan of the
+ * row lengths), dst_ent_row[p] (nullable) = destination row of entry p.  One call per epoch with the epoch's
+ * permutation builds the CSR every batch of the epoch is a slice of. */
+size_t ntf_csr_gather_workspace_bytes(int n);
+int ntf_csr_gather(ntf_ctx* ctx, void* stream, const int32_t* rows, int n, const int32_t* src_indptr,
+                   const int32_t* src_indices, int32_t* dst_indptr, int32_t* dst_indices, int32_t* dst_ent_row,
+                   void* workspace, size_t workspace_bytes);
+
+/* ---- input layer: multi-hot skills --------------------------------------------------------------------------
+ * replaces ntf.py:23 (row -> dense float), fnn.py:120 (H2D of dense X) and layer 0 of fnn.py:25
+ * (aten::linear over a 99.97%-zero X, + leaky_relu):
+ *   A[n,:] = lrelu( b0 + sum_{s in skills(n)} W0T[s,:] ),  W0T is [S,h] (a skill's vector is contiguous). */
+int ntf_csr_bag_fwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
+                    const float* W0T, const float* b0, int S, int h, float* A);
+/* replaces autograd's addmm backward for layer 0 (fnn.py:137):
+ *   dW0T[s,:] = sum_{n: s in skills(n)} dZ[n,:]  for EVERY s in [0,S) (zeros for skills absent from the batch).
+ * Atomic-free and run-to-run deterministic (a skill row is owned by one warp, summed in entry order).
+ * ent_row[p] - row_base = batch row of CSR entry p (from ntf_csr_gather). */
+int ntf_csr_bag_bwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
+                    const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T);
+
+/* ---- hidden layers / dense (embedded) skill input: fnn.py:25 layers i>=1, ntf.py:24 ----------------------------
+ * Y = act(A W^T + b), A [B,in], W [out,in] (torch layout); act 0 = identity, 1 = leaky_relu, 2 = sigmoid(leaky_relu). */
+int ntf_dense_fwd(ntf_ctx* ctx, void* stream, const float* A, const float* W, const float* b, int B, int in,
+                  int out, int act, float* Y);
+/* dZ = dY * lrelu'(Y) (act=1; the sign is taken from the stored activation), db = colsum(dZ); dZ may be NULL. */
+size_t ntf_act_bwd_workspace_bytes(int B, int h);
+int ntf_act_bwd(ntf_ctx* ctx, void* stream, const float* dY, const float* Y, int B, int h, int act, float* dZ,
+                float* db, void* workspace, size_t workspace_bytes);
+/* dW[out,in] = dZ^T A ;  dA[B,in] = dZ W  (dA may be NULL). */
+size_t ntf_dense_bwd_workspace_bytes(int B, int in, int out);
+int ntf_dense_bwd(ntf_ctx* ctx, void* stream, const float* A, const float* W, const float* dZ, int B, int in,
+                  int out, float* dW, float* dA, void* workspace, size_t workspace_bytes);
+
+/* ---- negative sampling: fnn.py:48-76 -----------------------------------------------------------------------------
+ * counts[j] = number of batch teams having expert j (fnn.py:75 `y.sum(0)` as an exact integer; for the global
+ * unigram of fnn.py:82 pass all teams once); cdf = inclusive prefix sum. */
+size_t ntf_expert_cdf_workspace_bytes(int E);
+int ntf_expert_cdf(ntf_ctx* ctx, void* stream, int B, const int32_t* m_indptr, const int32_t* m_indices, int E,
+                   uint32_t* counts, uint32_t* cdf, void* workspace, size_t workspace_bytes);
+/* neg[n, 0..ns) = distinct experts that are not members of team n, drawn without replacement with probability
+ * proportional to counts (unigram, unigram_b) or uniformly (uniform): the distribution of the reference's
+ * torch.multinomial(replacement=False) / top-ns-of-iid-keys.  Counter RNG: Philox4x32-10 keyed by seed, counter =
+ * (row0+n, draw, step); restated on the CPU in oracle/sampler_oracle.py.  A row whose candidates carry no mass
+ * falls back to uniform over ALL experts (fnn.py:67-69).  Unfilled slots are -1. */
+int ntf_neg_sample(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed, uint64_t step, int row0, int B,
+                   const int32_t* m_indptr, const int32_t* m_indices, int E, int ns, const uint32_t* cdf,
+                   int32_t* neg);
+/* special[n, j/32] bit j%32 = 1 iff j is a member of team n or j is in neg[n,:]: the reference's `condition` tensor
+ * (fnn.py:33-43), bit-packed.  op 1 sets the bits, op 0 clears the same words again (no full memset per step). */
+int ntf_special_bits(ntf_ctx* ctx, void* stream, int op, int B, const int32_t* m_indptr, const int32_t* m_indices,
+                     const int32_t* neg, int ns, int E, uint32_t* special, int pitch_words);
+
+/* ---- output layer, training: last layer of fnn.py:25 + fnn.py:32-46,135 + its autograd (fnn.py:137) -----------------
+ * z = A W^T + b ; x = lrelu(z) ; w = special ? tpw : tnw ; y = [j is a member of team n]
+ * loss_out[0] = loss_scale * sum_{n,j} w*((1-y)x + softplus(-x))          (loss_scale = 1/B of the GLOBAL batch)
+ * dz = w*(sigmoid(x)-y)*loss_scale*lrelu'(z) ;  dW = dz^T A ; db = colsum(dz) ; dA = dz W
+ * A validation step passes dW = db = dA = NULL (loss only, fnn.py:144-151).
+ * Flipout (W_delta != NULL; A_s = A*sign_in): z += (A_s W_delta^T + b_delta)*s_out, and the extra gradients
+ * dW_delta = (dz*s_out)^T A_s, db_delta = colsum(dz*s_out), dA_s = (dz*s_out) W_delta are produced. */
+typedef struct {
+  const float* A;              /* [B,h] last hidden activation                                      */
+  const float* W;              /* [E,h] (mu for Bnn)                                                 */
+  const float* b;              /* [E]                                                                */
+  const uint32_t* special;     /* [B,pitch_words] bit plane (NULL: every weight is tnw)              */
+  int pitch_words;
+  const int32_t* m_indptr;     /* member CSR of the batch (B+1 absolute offsets)                     */
+  const int32_t* m_indices;
+  int B, h, E;
+  float tpw, tnw, loss_scale;
+  float* dW;                   /* [E,h] or NULL                                                      */
+  float* db;                   /* [E]   or NULL                                                      */
+  float* dA;                   /* [B,h] or NULL                                                      */
+  float* loss_out;             /* [1]                                                                */
+  /* Flipout extras (all NULL for Fnn) */
+  const float* A_s;            /* [B,h]  A * sign_in                                                 */
+  const float* W_delta;        /* [E,h]  softplus(rho_W) * eps_W                                     */
+  const float* b_delta;        /* [E]                                                                */
+  const uint32_t* sign_out;    /* [B,pitch_words] bit=1 -> -1                                        */
+  float* dW_delta;             /* [E,h]                                                              */
+  float* db_delta;             /* [E]                                                                */
+  float* dA_s;                 /* [B,h]                                                              */
+} ntf_out_train_args;
+size_t ntf_out_train_workspace_bytes(const ntf_ctx* ctx, int precision, int B, int h, int E, int flipout);
+int ntf_out_train(ntf_ctx* ctx, void* stream, int precision, const ntf_out_train_args* args, void* workspace,
+                  size_t workspace_bytes);
+
+/* ---- optimiser: torch.optim.Adam (fnn.py:104,139), dense, one launch over the flat parameter arena; step is 1-based */
+int ntf_adam_step(ntf_ctx* ctx, void* stream, float* p, const float* g, float* m, float* v, size_t n, double lr,
+                  double beta1, double beta2, double eps, int64_t step);
+
+/* ---- test time: fnn.py:200-213 + pkgmgr.py:125-134 (+ the ranking of evl/metric.py:17-28) ---------------------------
+ * P[n,j] = sigmoid(lrelu(A W^T + b)) (Flipout extras as above, may be NULL).  accumulate != 0 adds into P. */
+size_t ntf_infer_scores_workspace_bytes(int B, int E, int flipout);
+int ntf_infer_scores(ntf_ctx* ctx, void* stream, int precision, const float* A, const float* W, const float* b,
+                     int B, int h, int E, const float* A_s, const float* W_delta, const float* b_delta,
+                     const uint32_t* sign_out, int pitch_words, int accumulate, float* P, void* workspace,
+                     size_t workspace_bytes);
+/* per row: the K largest of scale*P[n,:] in rank order (value descending, ties -> lower expert id first); K <= 2048 */
+int ntf_topk_select(ntf_ctx* ctx, void* stream, const float* P, int B, int E, int K, float scale, float* vals,
+                    int32_t* idx);
+/* merge G per-shard candidate lists [G][B][K] (idx = global expert ids, -1 = empty) into the global top-K per row:
+ * the merge step of the expert-sharded output layer. */
+int ntf_topk_merge(ntf_ctx* ctx, void* stream, const float* vals_in, const int32_t* idx_in, int G, int B, int K,
+                   float* vals, int32_t* idx);
+/* Bnn test-time uncertainty (fnn.py:206-208): out[n] (+)= -sum_j q log(q+1e-15), q = scale*P[n,j] */
+int ntf_row_entropy(ntf_ctx* ctx, void* stream, const float* P, int B, int E, float scale, int accumulate, float* out);
+int ntf_axpy(ntf_ctx* ctx, void* stream, size_t n, float a, const float* x, float* y); /* y += a*x (MC mean, fnn.py:209) */
+
+/* ---- Bnn / Flipout parameter pass (bayesian-torch 0.5.0 LinearFlipout + get_kl_loss; bnn.py:19-25, fnn.py:136) ---------
+ * delta = softplus(rho)*eps ;  kl_out[0] += kl_scale * sum(-log sigma + (sigma^2 + mu^2)/2 - 1/2)   (kl_scale = 1/numel:
+ * the reference takes a MEAN per tensor, prior N(0,1)) */
+size_t ntf_flipout_prepare_workspace_bytes(const ntf_ctx* ctx);
+int ntf_flipout_prepare(ntf_ctx* ctx, void* stream, const float* mu, const float* rho, const float* eps, size_t n,
+                        float kl_scale, float* delta, float* kl_out, void* workspace, size_t workspace_bytes);
+/* g_mu += kl_gscale*mu ; g_rho = (g_delta*eps + kl_gscale*(sigma - 1/sigma)) * sigmoid(rho)   (kl_gscale = 1/(numel*B)) */
+int ntf_flipout_grads(ntf_ctx* ctx, void* stream, const float* mu, const float* rho, const float* eps,
+                      const float* g_delta, size_t n, float kl_gscale, float* g_mu, float* g_rho);
+/* eps ~ N(0,1): Philox(seed; counter = (i/4, stream_id, step)) + Box-Muller */
+int ntf_fill_normal(ntf_ctx* ctx, void* stream, uint64_t seed, uint64_t step, uint32_t stream_id, size_t n, float* out);
+/* bit planes of iid fair signs (bit=1 -> -1): Philox(seed; counter = (word/4, stream_id, step)) */
+int ntf_fill_sign_bits(ntf_ctx* ctx, void* stream, uint64_t seed, uint64_t step, uint32_t stream_id, size_t n_words,
+                       uint32_t* bits);
+/* As[n,c] = A[n,c] * (bit(n,c) ? -1 : +1) */
+int ntf_apply_sign(ntf_ctx* ctx, void* stream, const float* A, const uint32_t* bits, int pitch_words, int B, int h,
+                   float* As);
+
+/* out[i] = sum_k parts[k*part_stride + i] in a fixed order (deterministic split reductions) */
+int ntf_sum_parts(ntf_ctx* ctx, void* stream, const float* parts, int nparts, size_t n, size_t part_stride, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTF_B200_H */

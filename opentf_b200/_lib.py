@@ -1,0 +1,106 @@
+"""ctypes binding of libntf_b200.so (the C ABI declared in include/ntf_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, an exception is raised.  The library
+is built in-tree by `python -m opentf_b200.csrc.build` (or `__graft_entry__.build()`).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libntf_b200.so')
+
+NTF_FP32, NTF_TF32 = 0, 1
+NSD = {None: 0, '': 0, 'none': 0, 'None': 0, 'uniform': 1, 'unigram': 2, 'unigram_b': 3}
+PRECISION = {'fp32': NTF_FP32, 'tf32': NTF_TF32}
+
+vp, i32, i64, u32, u64, f32, f64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_double, C.c_size_t
+
+
+class OutTrainArgs(C.Structure):
+    """mirror of ntf_out_train_args"""
+    _fields_ = [('A', vp), ('W', vp), ('b', vp), ('special', vp), ('pitch_words', i32), ('m_indptr', vp), ('m_indices', vp),
+                ('B', i32), ('h', i32), ('E', i32), ('tpw', f32), ('tnw', f32), ('loss_scale', f32),
+                ('dW', vp), ('db', vp), ('dA', vp), ('loss_out', vp),
+                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp)]
+
+
+# name -> (restype, argtypes); must list every symbol of include/ntf_b200.h (tests/test_abi.py checks it)
+SIGNATURES = {
+    'ntf_version': (i32, []),
+    'ntf_last_error': (i32, [C.c_char_p, sz]),
+    'ntf_create': (i32, [i32, C.POINTER(vp)]),
+    'ntf_destroy': (i32, [vp]),
+    'ntf_sm_count': (i32, [vp]),
+    'ntf_csr_gather_workspace_bytes': (sz, [i32]),
+    'ntf_csr_gather': (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz]),
+    'ntf_csr_bag_fwd': (i32, [vp, vp, i32, vp, vp, vp, vp, i32, i32, vp]),
+    'ntf_csr_bag_bwd': (i32, [vp, vp, i32, vp, vp, vp, i32, vp, i32, i32, vp]),
+    'ntf_dense_fwd': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    'ntf_act_bwd_workspace_bytes': (sz, [i32, i32]),
+    'ntf_act_bwd': (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, sz]),
+    'ntf_dense_bwd_workspace_bytes': (sz, [i32, i32, i32]),
+    'ntf_dense_bwd': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, sz]),
+    'ntf_expert_cdf_workspace_bytes': (sz, [i32]),
+    'ntf_expert_cdf': (i32, [vp, vp, i32, vp, vp, i32, vp, vp, vp, sz]),
+    'ntf_neg_sample': (i32, [vp, vp, i32, u64, u64, i32, i32, vp, vp, i32, i32, vp, vp]),
+    'ntf_special_bits': (i32, [vp, vp, i32, i32, vp, vp, vp, i32, i32, vp, i32]),
+    'ntf_out_train_workspace_bytes': (sz, [vp, i32, i32, i32, i32, i32]),
+    'ntf_out_train': (i32, [vp, vp, i32, C.POINTER(OutTrainArgs), vp, sz]),
+    'ntf_adam_step': (i32, [vp, vp, vp, vp, vp, vp, sz, f64, f64, f64, f64, i64]),
+    'ntf_infer_scores_workspace_bytes': (sz, [i32, i32, i32]),
+    'ntf_infer_scores': (i32, [vp, vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, sz]),
+    'ntf_topk_select': (i32, [vp, vp, vp, i32, i32, i32, f32, vp, vp]),
+    'ntf_topk_merge': (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),
+    'ntf_row_entropy': (i32, [vp, vp, vp, i32, i32, f32, i32, vp]),
+    'ntf_axpy': (i32, [vp, vp, sz, f32, vp, vp]),
+    'ntf_flipout_prepare_workspace_bytes': (sz, [vp]),
+    'ntf_flipout_prepare': (i32, [vp, vp, vp, vp, vp, sz, f32, vp, vp, vp, sz]),
+    'ntf_flipout_grads': (i32, [vp, vp, vp, vp, vp, vp, sz, f32, vp, vp]),
+    'ntf_fill_normal': (i32, [vp, vp, u64, u64, u32, sz, vp]),
+    'ntf_fill_sign_bits': (i32, [vp, vp, u64, u64, u32, sz, vp]),
+    'ntf_apply_sign': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    'ntf_sum_parts': (i32, [vp, vp, vp, i32, sz, sz, vp]),
+}
+
+_lib = None
+
+
+class NtfError(RuntimeError):
+    pass
+
+
+def lib():
+    """load (once) and type the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NtfError(f'{LIB_PATH} is missing: build it with `python -m opentf_b200.csrc.build` (there is no CPU fallback)')
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def last_error():
+    buf = C.create_string_buffer(512)
+    lib().ntf_last_error(buf, 512)
+    return buf.value.decode(errors='replace')
+
+
+def check(rc, what=''):
+    if rc != 0:
+        raise NtfError(f'{what} failed with status {rc}: {last_error()}')
+
+
+_ctx = {}
+
+
+def ctx(device_index):
+    """one ntf_ctx per CUDA device (fails loudly on anything that is not sm_100)."""
+    if device_index not in _ctx:
+        h = vp()
+        check(lib().ntf_create(int(device_index), C.byref(h)), 'ntf_create')
+        _ctx[device_index] = h
+    return _ctx[device_index]

@@ -1,0 +1,47 @@
+// adam.cu -- K6: torch.optim.Adam(betas=(.9,.999), eps=1e-8, weight_decay=0, amsgrad=False) (fnn.py:104,139) as ONE
+// launch over the flat parameter arena.  HBM-bound: 28 bytes per parameter per step (read p,g,m,v; write p,m,v).
+// Operation order follows torch's single-tensor path: m.lerp_(g,1-b1); v.mul_(b2).addcmul_(g,g,1-b2);
+// denom = sqrt(v)/sqrt(bc2) + eps; p.addcdiv_(m, denom, -lr/bc1).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+struct AdamK { float one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, neg_step; };
+
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamK& k) {
+  m = m + k.one_minus_b1 * (g - m);
+  v = v * k.b2;
+  v = v + (k.one_minus_b2 * g) * g;
+  const float denom = sqrtf(v) / k.bc2_sqrt + k.eps;
+  p = p + k.neg_step * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, size_t n4, size_t n, AdamK k) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    const float4 G = __ldg(reinterpret_cast<const float4*>(g) + i);
+    adam1(P.x, G.x, M.x, V.x, k); adam1(P.y, G.y, M.y, V.y, k); adam1(P.z, G.z, M.z, V.z, k); adam1(P.w, G.w, M.w, V.w, k);
+    reinterpret_cast<float4*>(p)[i] = P; reinterpret_cast<float4*>(m)[i] = M; reinterpret_cast<float4*>(v)[i] = V;
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) adam1(p[i], g[i], m[i], v[i], k);
+}
+}  // namespace
+
+extern "C" int ntf_adam_step(ntf_ctx* ctx, void* stream, float* p, const float* g, float* m, float* v, size_t n, double lr,
+                             double beta1, double beta2, double eps, int64_t step) {
+  NTF_REQUIRE(ctx && p && g && m && v, NTF_ERR_BAD_ARG, "adam_step: null pointer");
+  NTF_REQUIRE(step >= 1, NTF_ERR_BAD_ARG, "adam_step: step=%lld (1-based)", (long long)step);
+  if (n == 0) return NTF_OK;
+  const bool aligned = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0;
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  AdamK k{(float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)sqrt(bc2), (float)eps, (float)(-(lr / bc1))};
+  const size_t n4 = aligned ? n / 4 : 0;
+  const size_t work = n4 ? n4 : n;
+  const int blocks = (int)((work + 255) / 256 < (size_t)ctx->sm_count * 16 ? (work + 255) / 256 : (size_t)ctx->sm_count * 16);
+  adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n4, n, k);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}

@@ -1,0 +1,118 @@
+// common.cuh -- shared helpers for libntf_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ntf_b200.h"
+
+struct ntf_ctx {
+  int device;
+  int sm_count;
+  int cc_major, cc_minor;
+  size_t smem_optin;
+  void* encode_tiled;  // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
+};
+
+// ---- error plumbing -------------------------------------------------------------------------------------
+void ntf_set_error(const char* fmt, ...);
+
+#define NTF_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      ntf_set_error(__VA_ARGS__);     \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+#define NTF_CUDA(call)                                                                            \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      ntf_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return NTF_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+#define NTF_LAUNCH_CHECK() NTF_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- device helpers -------------------------------------------------------------------------------------
+#define NTF_LRELU_SLOPE 0.01f
+
+__device__ __forceinline__ float lrelu(float z) { return z > 0.f ? z : NTF_LRELU_SLOPE * z; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Weighted BCE-with-logits on x = lrelu(z), and its gradient wrt z.
+//   loss = w*((1-y)*x + max(-x,0) + log1p(exp(-|x|)))      d/dz = w*(sigmoid(x)-y)*scale*(z>0 ? 1 : 0.01)
+// FAST=false: libm-accurate expf/log1pf (the fp32 parity mode).  FAST=true: MUFU ex2/lg2/rcp.
+template <bool FAST>
+__device__ __forceinline__ void bce_elem(float z, bool y, float w, float scale, float& loss, float& dz) {
+  const float x = lrelu(z);
+  const float ax = fabsf(x);
+  float e, l1p, r;
+  if (FAST) {
+    e = __expf(-ax);
+    l1p = __logf(1.f + e);
+    r = __frcp_rn(1.f + e);
+  } else {
+    e = expf(-ax);
+    l1p = log1pf(e);
+    r = 1.f / (1.f + e);
+  }
+  const float sig = x >= 0.f ? r : e * r;
+  const float yf = y ? 1.f : 0.f;
+  loss = w * ((1.f - yf) * x + fmaxf(-x, 0.f) + l1p);
+  dz = w * (sig - yf) * scale * (z > 0.f ? 1.f : NTF_LRELU_SLOPE);
+}
+
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_lrelu(float z) {
+  const float x = lrelu(z);
+  if (FAST) {
+    const float e = __expf(-fabsf(x));
+    const float r = __frcp_rn(1.f + e);
+    return x >= 0.f ? r : e * r;
+  }
+  return 1.f / (1.f + expf(-x));  // torch.sigmoid's fp32 formula
+}
+
+// is expert j a member of team `row`?  (member rows are short: 2-10 entries, sorted)
+__device__ __forceinline__ bool is_member(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                          int row, int j) {
+  const int b = indptr[row], e = indptr[row + 1];
+  for (int p = b; p < e; ++p)
+    if (indices[p] == j) return true;
+  return false;
+}
+
+// ---- Philox4x32-10 (Salmon et al. 2011), the counter RNG restated in oracle/sampler_oracle.py -------------
+struct Philox4 {
+  uint32_t v[4];
+};
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                         uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  Philox4 o;
+  o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+  return o;
+}

@@ -1,0 +1,343 @@
+// csr_bag.cu -- the sparse multi-hot input layer (K1/K2 of SURVEY.md) and CSR staging.
+//
+//   ntf_scan_u32      : device-wide inclusive/exclusive prefix sum (two-level, deterministic)
+//   ntf_csr_gather    : permuted/compacted copy of CSR rows (the DataLoader shuffle, fnn.py:95-97, on device)
+//   ntf_csr_bag_fwd   : A = lrelu(b0 + sum_s W0T[s,:])                    -- HBM-bound gather-sum
+//   ntf_csr_bag_bwd   : dW0T[s,:] = sum_{n: s in skills(n)} dZ[n,:]       -- atomic-free, owner-computes
+//   ntf_act_bwd       : dZ = dY*lrelu'(Y), db = colsum(dZ)
+#include "common.cuh"
+
+// =========================================================================================================
+// prefix sum: block-local scan + one-block scan of the block totals + offset add
+// =========================================================================================================
+namespace {
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  // returns the exclusive prefix of v over the block; *total (all threads) = block sum
+  __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t t = lane < SCAN_THREADS / 32 ? warp_tot[lane] : 0u, ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += u;
+    }
+    if (lane < SCAN_THREADS / 32) warp_tot[lane] = ti - t;  // exclusive warp offsets
+    if (lane == SCAN_THREADS / 32 - 1) *total = ti;
+  }
+  __syncthreads();
+  const uint32_t r = warp_tot[w] + inc - v;
+  __syncthreads();
+  return r;
+}
+
+// pass 1: per-tile totals.  in may be a length array or (if from_indptr) derived as indptr[rows[i]+1]-indptr[rows[i]]
+__global__ void scan_tile_totals(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ tile_tot) {
+  __shared__ uint32_t tot;
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE;
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    const size_t k = base + (size_t)i * SCAN_THREADS + threadIdx.x;
+    if (k < n) s += in[k];
+  }
+  (void)block_exclusive_scan(s, &tot);
+  if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
+}
+
+// pass 2: one block turns tile totals into exclusive tile offsets (serial over chunks of SCAN_THREADS)
+__global__ void scan_tile_offsets(uint32_t* __restrict__ tile_tot, int ntiles) {
+  __shared__ uint32_t tot;
+  uint32_t carry = 0;
+  for (int base = 0; base < ntiles; base += SCAN_THREADS) {
+    const int k = base + threadIdx.x;
+    const uint32_t v = k < ntiles ? tile_tot[k] : 0u;
+    const uint32_t ex = block_exclusive_scan(v, &tot);
+    if (k < ntiles) tile_tot[k] = carry + ex;
+    carry += tot;
+    __syncthreads();
+  }
+}
+
+// pass 3: scan inside each tile (thread owns SCAN_ITEMS consecutive items) + tile offset
+__global__ void scan_apply(const uint32_t* __restrict__ in, size_t n, const uint32_t* __restrict__ tile_off,
+                           uint32_t* __restrict__ out, int inclusive, uint32_t* __restrict__ grand_total) {
+  __shared__ uint32_t tot;
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    v[i] = base + i < n ? in[base + i] : 0u;
+    s += v[i];
+  }
+  uint32_t run = block_exclusive_scan(s, &tot) + tile_off[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < n) out[base + i] = inclusive ? run + v[i] : run;
+    run += v[i];
+  }
+  if (grand_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) *grand_total = run;
+}
+}  // namespace
+
+size_t ntf_scan_workspace_bytes(size_t n) { return align_up(((n + SCAN_TILE - 1) / SCAN_TILE + 1) * sizeof(uint32_t), 256); }
+
+// out may alias in.  grand_total (device, nullable) receives the sum of all items.
+int ntf_scan_u32_impl(cudaStream_t st, const uint32_t* in, size_t n, uint32_t* out, int inclusive, uint32_t* grand_total,
+                      void* ws, size_t ws_bytes) {
+  if (n == 0) {
+    if (grand_total) NTF_CUDA(cudaMemsetAsync(grand_total, 0, sizeof(uint32_t), st));
+    return NTF_OK;
+  }
+  NTF_REQUIRE(ws_bytes >= ntf_scan_workspace_bytes(n), NTF_ERR_WORKSPACE, "scan: workspace %zu < %zu", ws_bytes,
+              ntf_scan_workspace_bytes(n));
+  const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+  uint32_t* tile = (uint32_t*)ws;
+  scan_tile_totals<<<ntiles, SCAN_THREADS, 0, st>>>(in, n, tile);
+  scan_tile_offsets<<<1, SCAN_THREADS, 0, st>>>(tile, ntiles);
+  scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(in, n, tile, out, inclusive, grand_total);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
+
+// =========================================================================================================
+// CSR gather: dst row i = src row rows[i]
+// =========================================================================================================
+namespace {
+__global__ void csr_row_lengths(const int32_t* __restrict__ rows, int n, const int32_t* __restrict__ indptr,
+                                uint32_t* __restrict__ len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int r = rows ? rows[i] : i;
+    len[i] = (uint32_t)(indptr[r + 1] - indptr[r]);
+  }
+}
+
+// one warp per destination row; also records the destination row of every entry (ent_row)
+__global__ void csr_copy_rows(const int32_t* __restrict__ rows, int n, const int32_t* __restrict__ src_indptr,
+                              const int32_t* __restrict__ src_indices, int32_t* __restrict__ dst_indptr,
+                              int32_t* __restrict__ dst_indices, int32_t* __restrict__ dst_ent_row) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const int r = rows ? rows[warp] : warp;
+  const int sb = src_indptr[r], len = src_indptr[r + 1] - sb;
+  const int db = dst_indptr[warp];
+  for (int k = lane; k < len; k += 32) {
+    dst_indices[db + k] = src_indices[sb + k];
+    if (dst_ent_row) dst_ent_row[db + k] = warp;
+  }
+  if (warp == n - 1 && lane == 0) dst_indptr[n] = db + len;
+}
+}  // namespace
+
+extern "C" size_t ntf_csr_gather_workspace_bytes(int n) { return ntf_scan_workspace_bytes((size_t)n); }
+
+extern "C" int ntf_csr_gather(ntf_ctx* ctx, void* stream, const int32_t* rows, int n, const int32_t* src_indptr,
+                              const int32_t* src_indices, int32_t* dst_indptr, int32_t* dst_indices,
+                              int32_t* dst_ent_row, void* workspace, size_t workspace_bytes) {
+  NTF_REQUIRE(ctx && src_indptr && src_indices && dst_indptr && dst_indices, NTF_ERR_BAD_ARG, "csr_gather: null pointer");
+  NTF_REQUIRE(n >= 0, NTF_ERR_BAD_ARG, "csr_gather: n=%d", n);
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) {
+    NTF_CUDA(cudaMemsetAsync(dst_indptr, 0, sizeof(int32_t), st));
+    return NTF_OK;
+  }
+  // lengths are staged in dst_indptr[0..n) and scanned in place (exclusive)
+  csr_row_lengths<<<cdiv(n, 256), 256, 0, st>>>(rows, n, src_indptr, (uint32_t*)dst_indptr);
+  int rc = ntf_scan_u32_impl(st, (const uint32_t*)dst_indptr, (size_t)n, (uint32_t*)dst_indptr, 0, nullptr, workspace,
+                             workspace_bytes);
+  if (rc) return rc;
+  csr_copy_rows<<<cdiv(n * 32, 256), 256, 0, st>>>(rows, n, src_indptr, src_indices, dst_indptr, dst_indices, dst_ent_row);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
+
+// =========================================================================================================
+// K1: embedding-bag forward.  One warp per team; a lane owns float4 slices of the h-vector.
+// Algorithmic bytes per team: n_s*(4h+4) + 8 + 4h   
+// =========================================================================================================
+namespace {
+template <bool VEC4>
+__global__ void __launch_bounds__(256) csr_bag_fwd_kernel(int B, const int32_t* __restrict__ indptr,
+                                                          const int32_t* __restrict__ indices,
+                                                          const float* __restrict__ W0T, const float* __restrict__ b0,
+                                                          int h, float* __restrict__ A) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < B; n += warps) {
+    const int beg = indptr[n], end = indptr[n + 1];
+    if (VEC4) {
+      const int h4 = h >> 2;
+      for (int c = lane; c < h4; c += 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int p = beg;
+        for (; p + 4 <= end; p += 4) {  // 4 independent 16-byte loads in flight, summed in CSR order
+          const int s0 = indices[p], s1 = indices[p + 1], s2 = indices[p + 2], s3 = indices[p + 3];
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(W0T + (size_t)s0 * h) + c);
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(W0T + (size_t)s1 * h) + c);
+          const float4 v2 = __ldg(reinterpret_cast<const float4*>(W0T + (size_t)s2 * h) + c);
+          const float4 v3 = __ldg(reinterpret_cast<const float4*>(W0T + (size_t)s3 * h) + c);
+          acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+          acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+          acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+          acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+        }
+        for (; p < end; ++p) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(W0T + (size_t)indices[p] * h) + c);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b0) + c);
+        float4 o;
+        o.x = lrelu(acc.x + bb.x); o.y = lrelu(acc.y + bb.y); o.z = lrelu(acc.z + bb.z); o.w = lrelu(acc.w + bb.w);
+        reinterpret_cast<float4*>(A + (size_t)n * h)[c] = o;
+      }
+    } else {
+      for (int c = lane; c < h; c += 32) {
+        float acc = 0.f;
+        for (int p = beg; p < end; ++p) acc += __ldg(W0T + (size_t)indices[p] * h + c);
+        A[(size_t)n * h + c] = lrelu(acc + b0[c]);
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" int ntf_csr_bag_fwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
+                               const float* W0T, const float* b0, int S, int h, float* A) {
+  NTF_REQUIRE(ctx && indptr && indices && W0T && b0 && A, NTF_ERR_BAD_ARG, "csr_bag_fwd: null pointer");
+  NTF_REQUIRE(B >= 0 && S > 0 && h > 0, NTF_ERR_BAD_ARG, "csr_bag_fwd: B=%d S=%d h=%d", B, S, h);
+  if (B == 0) return NTF_OK;
+  const int blocks = min(cdiv(B, 8), ctx->sm_count * 8);
+  const bool vec = (h % 4 == 0) && (((uintptr_t)W0T | (uintptr_t)b0 | (uintptr_t)A) % 16 == 0);
+  if (vec) csr_bag_fwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(B, indptr, indices, W0T, b0, h, A);
+  else csr_bag_fwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(B, indptr, indices, W0T, b0, h, A);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
+
+// =========================================================================================================
+// K2: embedding-bag backward, atomic-free.  The skill axis is cut into chunks of SKW skills; a warp owns one
+// chunk, keeps SKW x h accumulators in shared memory, streams over the batch's flat (skill id, team) entry
+// list with coalesced loads, and adds dZ[team,:] for the entries that fall in its chunk -- in entry order, so
+// the sum order depends on the data only (run-to-run deterministic).  Every dW0T row is written exactly once
+// (zeros for skills absent from the batch: Adam is dense, SURVEY.md "Hard parts").
+// Algorithmic bytes per team: n_s*(4h+4) + 4h read, 4h*S/B written.
+// =========================================================================================================
+namespace {
+constexpr int BWD_WARPS = 8;
+
+__global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_kernel(int B, const int32_t* __restrict__ indptr,
+                                                                      const int32_t* __restrict__ indices,
+                                                                      const int32_t* __restrict__ ent_row, int row_base,
+                                                                      const float* __restrict__ dZ, int S, int h, int skw,
+                                                                      float* __restrict__ dW0T) {
+  extern __shared__ float acc_all[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* acc = acc_all + (size_t)w * skw * h;
+  const int nchunks = (S + skw - 1) / skw;
+  const int p_beg = indptr[0], p_end = indptr[B];
+  for (int chunk = blockIdx.x * BWD_WARPS + w; chunk < nchunks; chunk += gridDim.x * BWD_WARPS) {
+    const int s0 = chunk * skw, s1 = min(S, s0 + skw);
+    for (int k = lane; k < skw * h; k += 32) acc[k] = 0.f;
+    __syncwarp();
+    for (int base = p_beg; base < p_end; base += 32) {
+      const int p = base + lane;
+      int s = -1, n = 0;
+      if (p < p_end) {
+        s = __ldg(indices + p);
+        if (s >= s0 && s < s1) n = __ldg(ent_row + p) - row_base; else s = -1;
+      }
+      unsigned hits = __ballot_sync(0xffffffffu, s >= 0);
+      while (hits) {
+        const int L = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int sl = __shfl_sync(0xffffffffu, s, L) - s0;
+        const int nn = __shfl_sync(0xffffffffu, n, L);
+        const float* src = dZ + (size_t)nn * h;
+        float* dst = acc + (size_t)sl * h;
+        for (int c = lane; c < h; c += 32) dst[c] += __ldg(src + c);
+      }
+    }
+    __syncwarp();
+    for (int k = lane; k < (s1 - s0) * h; k += 32) dW0T[(size_t)s0 * h + k] = acc[k];
+    __syncwarp();
+  }
+}
+}  // namespace
+
+extern "C" int ntf_csr_bag_bwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
+                               const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T) {
+  NTF_REQUIRE(ctx && indptr && indices && ent_row && dZ && dW0T, NTF_ERR_BAD_ARG, "csr_bag_bwd: null pointer");
+  NTF_REQUIRE(B > 0 && S > 0 && h > 0, NTF_ERR_BAD_ARG, "csr_bag_bwd: B=%d S=%d h=%d", B, S, h);
+  NTF_REQUIRE(h <= 2048, NTF_ERR_UNSUPPORTED, "csr_bag_bwd: first hidden width %d > 2048", h);
+  int skw = 2048 / h;  // 8 KB of accumulators per warp
+  if (skw < 1) skw = 1;
+  if (skw > 32) skw = 32;
+  const size_t smem = (size_t)BWD_WARPS * skw * h * sizeof(float);
+  NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nchunks = cdiv(S, skw);
+  const int blocks = min(cdiv(nchunks, BWD_WARPS), ctx->sm_count * 3);
+  csr_bag_bwd_kernel<<<blocks, BWD_WARPS * 32, smem, as_stream(stream)>>>(B, indptr, indices, ent_row, row_base, dZ, S, h,
+                                                                         skw, dW0T);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
+
+// =========================================================================================================
+// dZ = dY * lrelu'(Y) ; db = colsum(dZ).  Column sums are taken by one thread per column over a fixed row
+// order inside a block of rows, then across row-blocks by a second fixed-order pass: deterministic.
+// =========================================================================================================
+namespace {
+constexpr int ACT_ROWS = 64;  // rows per block
+
+__global__ void act_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, int B, int h, int act,
+                               float* __restrict__ dZ, float* __restrict__ part) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= h) return;
+  const int r0 = blockIdx.y * ACT_ROWS, r1 = min(B, r0 + ACT_ROWS);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const size_t k = (size_t)r * h + c;
+    float g = dY[k];
+    if (act) g *= (Y[k] > 0.f ? 1.f : NTF_LRELU_SLOPE);
+    if (dZ) dZ[k] = g;
+    s += g;
+  }
+  part[(size_t)blockIdx.y * h + c] = s;
+}
+
+__global__ void colsum_parts_kernel(const float* __restrict__ part, int nparts, int h, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= h) return;
+  float s = 0.f;
+  for (int k = 0; k < nparts; ++k) s += part[(size_t)k * h + c];
+  out[c] = s;
+}
+}  // namespace
+
+extern "C" size_t ntf_act_bwd_workspace_bytes(int B, int h) { return align_up((size_t)cdiv(B, ACT_ROWS) * h * sizeof(float), 256); }
+
+extern "C" int ntf_act_bwd(ntf_ctx* ctx, void* stream, const float* dY, const float* Y, int B, int h, int act, float* dZ,
+                           float* db, void* workspace, size_t workspace_bytes) {
+  NTF_REQUIRE(ctx && dY && db && workspace && (!act || Y), NTF_ERR_BAD_ARG, "act_bwd: null pointer");
+  NTF_REQUIRE(B > 0 && h > 0, NTF_ERR_BAD_ARG, "act_bwd: B=%d h=%d", B, h);
+  NTF_REQUIRE(workspace_bytes >= ntf_act_bwd_workspace_bytes(B, h), NTF_ERR_WORKSPACE, "act_bwd: workspace too small");
+  const int nparts = cdiv(B, ACT_ROWS);
+  dim3 grid(cdiv(h, 128), nparts);
+  act_bwd_kernel<<<grid, 128, 0, as_stream(stream)>>>(dY, Y, B, h, act, dZ, (float*)workspace);
+  colsum_parts_kernel<<<cdiv(h, 128), 128, 0, as_stream(stream)>>>((const float*)workspace, nparts, h, db);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}

@@ -1,0 +1,135 @@
+// sampler.cu -- negative sampling (K4) and the bit-packed `condition` plane of fnn.py:33-43.
+//
+// The reference draws B x E random keys per step and keeps the top-ns per row (uniform: fnn.py:48-56; unigram /
+// unigram_b: torch.multinomial without replacement == top-ns of p_j/Exp(1), fnn.py:58-76).  Both are "ns draws
+// without replacement from the row's negatives, with probability proportional to p_j".  Here that distribution
+// is sampled directly: successive draws from the integer CDF of the expert counts (p_j = count_j / B exactly),
+// rejecting the row's own members and experts already drawn -- O(ns log E) per team instead of O(E), all in
+// integer arithmetic so that oracle/sampler_oracle.py reproduces every index bit for bit.
+#include "common.cuh"
+
+int ntf_scan_u32_impl(cudaStream_t st, const uint32_t* in, size_t n, uint32_t* out, int inclusive, uint32_t* grand_total,
+                      void* ws, size_t ws_bytes);
+size_t ntf_scan_workspace_bytes(size_t n);
+
+namespace {
+constexpr uint32_t PURPOSE_NEG = 0x6e656730u;  // key1 ^= this for the negative sampler stream
+
+__global__ void count_members_kernel(int B, const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_indices,
+                                     uint32_t* __restrict__ counts) {
+  const int p0 = m_indptr[0], p1 = m_indptr[B];
+  for (int p = p0 + blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += gridDim.x * blockDim.x)
+    atomicAdd(counts + m_indices[p], 1u);  // integer adds: the result does not depend on the order
+}
+
+__device__ __forceinline__ uint64_t draw64(uint64_t seed, uint32_t row, uint32_t t, uint64_t step) {
+  const Philox4 r = philox4x32_10(row, t, (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)seed,
+                                  (uint32_t)(seed >> 32) ^ PURPOSE_NEG);
+  return ((uint64_t)r.v[1] << 32) | r.v[0];
+}
+
+// smallest j with cdf[j] > x
+__device__ __forceinline__ int upper_bound_u32(const uint32_t* __restrict__ cdf, int E, uint32_t x) {
+  int lo = 0, hi = E;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(cdf + mid) > x) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+constexpr int NS_MAX = 64;
+
+__global__ void neg_sample_kernel(int nsd, uint64_t seed, uint64_t step, int row0, int B,
+                                  const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_indices, int E, int ns,
+                                  const uint32_t* __restrict__ cdf, int32_t* __restrict__ neg) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= B) return;
+  const int pb = m_indptr[n], pe = m_indptr[n + 1], npos = pe - pb;
+  int32_t* out = neg + (size_t)n * ns;
+  int got = 0;
+  uint32_t t = 0;
+  auto is_pos = [&](int j) { for (int p = pb; p < pe; ++p) if (m_indices[p] == j) return true; return false; };
+  auto is_dup = [&](int j) { for (int q = 0; q < got; ++q) if (out[q] == j) return true; return false; };
+  const int max_tries = 32 * ns + 64;
+
+  bool weighted = (nsd == NTF_NS_UNIGRAM || nsd == NTF_NS_UNIGRAM_B);
+  bool all_experts = false;  // fnn.py:67-69 fallback: uniform over ALL experts, members included
+  uint32_t T = 0;
+  if (weighted) {
+    T = cdf[E - 1];
+    uint32_t pos_mass = 0;
+    for (int p = pb; p < pe; ++p) { const int j = m_indices[p]; pos_mass += cdf[j] - (j ? cdf[j - 1] : 0u); }
+    if (T == pos_mass) { weighted = false; all_experts = true; }
+  }
+  if (weighted) {
+    for (int tries = 0; got < ns && tries < max_tries; ++tries, ++t) {
+      const uint32_t x = (uint32_t)__umul64hi(draw64(seed, (uint32_t)(row0 + n), t, step), (uint64_t)T);
+      const int j = upper_bound_u32(cdf, E, x);
+      if (!is_pos(j) && !is_dup(j)) out[got++] = j;
+    }
+  }
+  // uniform mode, the all-expert fallback, and the top-up when fewer than ns weighted candidates exist
+  const int avail = all_experts ? E : E - npos;
+  const int want = min(ns, avail);
+  for (int tries = 0; got < want && tries < max_tries; ++tries, ++t) {
+    const int j = (int)__umul64hi(draw64(seed, (uint32_t)(row0 + n), t, step), (uint64_t)E);
+    if ((all_experts || !is_pos(j)) && !is_dup(j)) out[got++] = j;
+  }
+  for (int j = 0; got < want && j < E; ++j)  // pathological rows (E - npos barely >= ns): deterministic sweep
+    if ((all_experts || !is_pos(j)) && !is_dup(j)) out[got++] = j;
+  for (; got < ns; ++got) out[got] = -1;
+}
+
+__global__ void special_bits_kernel(int op, int B, const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_indices,
+                                    const int32_t* __restrict__ neg, int ns, int E, uint32_t* __restrict__ special, int pitch) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= B) return;
+  uint32_t* row = special + (size_t)n * pitch;
+  // one thread owns the whole row of the plane, so plain read-modify-write is race free
+  for (int p = m_indptr[n]; p < m_indptr[n + 1]; ++p) {
+    const int j = m_indices[p];
+    if (op) row[j >> 5] |= 1u << (j & 31); else row[j >> 5] = 0u;
+  }
+  if (neg)
+    for (int q = 0; q < ns; ++q) {
+      const int j = neg[(size_t)n * ns + q];
+      if (j < 0 || j >= E) continue;
+      if (op) row[j >> 5] |= 1u << (j & 31); else row[j >> 5] = 0u;
+    }
+}
+}  // namespace
+
+extern "C" size_t ntf_expert_cdf_workspace_bytes(int E) { return ntf_scan_workspace_bytes((size_t)E); }
+
+extern "C" int ntf_expert_cdf(ntf_ctx* ctx, void* stream, int B, const int32_t* m_indptr, const int32_t* m_indices, int E,
+                              uint32_t* counts, uint32_t* cdf, void* workspace, size_t workspace_bytes) {
+  NTF_REQUIRE(ctx && m_indptr && m_indices && counts && cdf, NTF_ERR_BAD_ARG, "expert_cdf: null pointer");
+  NTF_REQUIRE(B > 0 && E > 0, NTF_ERR_BAD_ARG, "expert_cdf: B=%d E=%d", B, E);
+  cudaStream_t st = as_stream(stream);
+  NTF_CUDA(cudaMemsetAsync(counts, 0, (size_t)E * sizeof(uint32_t), st));
+  count_members_kernel<<<min(cdiv(B * 4, 256), ctx->sm_count * 8), 256, 0, st>>>(B, m_indptr, m_indices, counts);
+  NTF_LAUNCH_CHECK();
+  return ntf_scan_u32_impl(st, counts, (size_t)E, cdf, 1, nullptr, workspace, workspace_bytes);
+}
+
+extern "C" int ntf_neg_sample(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed, uint64_t step, int row0, int B,
+                              const int32_t* m_indptr, const int32_t* m_indices, int E, int ns, const uint32_t* cdf,
+                              int32_t* neg) {
+  NTF_REQUIRE(ctx && m_indptr && m_indices && neg, NTF_ERR_BAD_ARG, "neg_sample: null pointer");
+  NTF_REQUIRE(nsd >= NTF_NS_UNIFORM && nsd <= NTF_NS_UNIGRAM_B, NTF_ERR_BAD_ARG, "neg_sample: nsd=%d", nsd);
+  NTF_REQUIRE(nsd == NTF_NS_UNIFORM || cdf, NTF_ERR_BAD_ARG, "neg_sample: unigram modes need a cdf");
+  NTF_REQUIRE(B > 0 && E > 0 && ns > 0 && ns <= NS_MAX, NTF_ERR_UNSUPPORTED, "neg_sample: B=%d E=%d ns=%d (ns<=%d)", B, E, ns, NS_MAX);
+  neg_sample_kernel<<<cdiv(B, 128), 128, 0, as_stream(stream)>>>(nsd, seed, step, row0, B, m_indptr, m_indices, E, ns, cdf, neg);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
+
+extern "C" int ntf_special_bits(ntf_ctx* ctx, void* stream, int op, int B, const int32_t* m_indptr, const int32_t* m_indices,
+                                const int32_t* neg, int ns, int E, uint32_t* special, int pitch_words) {
+  NTF_REQUIRE(ctx && m_indptr && m_indices && special, NTF_ERR_BAD_ARG, "special_bits: null pointer");
+  NTF_REQUIRE(B > 0 && E > 0 && pitch_words * 32 >= E, NTF_ERR_BAD_ARG, "special_bits: B=%d E=%d pitch=%d", B, E, pitch_words);
+  special_bits_kernel<<<cdiv(B, 128), 128, 0, as_stream(stream)>>>(op, B, m_indptr, m_indices, neg, ns, E, special, pitch_words);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}

@@ -1,0 +1,282 @@
+"""Device-resident training / inference engine behind `opentf_b200.fnn.Fnn` and `opentf_b200.bnn.Bnn`.
+
+Everything numeric is a kernel of libntf_b200.so called through `ops`; this module owns the memory
+(parameter arena, Adam state, activations, CSR staging) and the order of launches of one step.
+
+Data layout in HBM:
+  * one flat fp32 arena holds every parameter, 128-byte aligned segments; `grads`, `adam_m`, `adam_v` mirror it,
+    so Adam (and the data-parallel gradient all-reduce) is one launch / one collective over a flat buffer.
+    Layer 0's weight is stored TRANSPOSED ([S,h0]: a skill's vector is one contiguous 4*h0-byte row) -- the
+    state_dict exporter/importer transposes to/from torch's [out,in].
+  * the teamsvecs CSR (int32 indptr / indices; data is all ones, team.py:20-27) is staged once; a split is a
+    gathered copy in batch order (`SplitData`), re-gathered per epoch with that epoch's permutation, so batch b
+    is the row range [b*B, (b+1)*B) of it and kernels address it by pointer offset.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import NSD, PRECISION, OutTrainArgs
+
+ALIGN = 32  # floats (128 bytes)
+
+
+def _round_up(n, a):
+    return (n + a - 1) // a * a
+
+
+def to_csr(mat):
+    """accept scipy lil/csr/coo (the reference hands lil uint8, team.py:154) -> (indptr int32, indices int32, shape)."""
+    c = mat.tocsr()
+    c.sort_indices()
+    if c.nnz >= 2 ** 31: raise ValueError('CSR with >= 2^31 entries is not supported')
+    return np.ascontiguousarray(c.indptr, dtype=np.int32), np.ascontiguousarray(c.indices, dtype=np.int32), c.shape
+
+
+class DeviceCSR:
+    """all teams of one teamsvecs matrix on the device"""
+
+    def __init__(self, mat, device):
+        indptr, indices, self.shape = to_csr(mat)
+        self.host_indptr = indptr
+        self.indptr = torch.from_numpy(indptr).to(device)
+        self.indices = torch.from_numpy(indices).to(device) if len(indices) else torch.zeros(1, dtype=torch.int32, device=device)
+        self.nnz = int(len(indices))
+
+    def nnz_of(self, rows):
+        rows = np.asarray(rows, dtype=np.int64)
+        return int((self.host_indptr[rows + 1] - self.host_indptr[rows]).sum())
+
+
+class SplitData:
+    """teams `rows` (in that order) of the skill and member CSR, gathered on the device.  `regather(order)`
+    rebuilds the copy for a new order of the same teams (the per-epoch shuffle of fnn.py:95)."""
+
+    def __init__(self, eng, rows):
+        self.eng = eng
+        self.rows_host = np.ascontiguousarray(np.asarray(rows), dtype=np.int32)
+        self.n = len(self.rows_host)
+        dev = eng.device
+        self.nnz_s, self.nnz_m = eng.skill.nnz_of(self.rows_host), eng.member.nnz_of(self.rows_host)
+        self.s_indptr = torch.empty(self.n + 1, dtype=torch.int32, device=dev)
+        self.s_indices = torch.empty(max(1, self.nnz_s), dtype=torch.int32, device=dev)
+        self.s_ent_row = torch.empty(max(1, self.nnz_s), dtype=torch.int32, device=dev)
+        self.m_indptr = torch.empty(self.n + 1, dtype=torch.int32, device=dev)
+        self.m_indices = torch.empty(max(1, self.nnz_m), dtype=torch.int32, device=dev)
+        self.rows_dev = torch.empty(max(1, self.n), dtype=torch.int32, device=dev)
+        self.regather(None)
+
+    def regather(self, order):
+        """order: positions into the split's rows (None = as given)."""
+        rows = self.rows_host if order is None else self.rows_host[np.asarray(order)]
+        self.rows_now = rows
+        if self.n == 0: return
+        self.rows_dev.copy_(torch.from_numpy(np.ascontiguousarray(rows)), non_blocking=False)
+        e = self.eng
+        ops.csr_gather(self.rows_dev, self.n, e.skill.indptr, e.skill.indices, self.s_indptr, self.s_indices, self.s_ent_row, e.ws)
+        ops.csr_gather(self.rows_dev, self.n, e.member.indptr, e.member.indices, self.m_indptr, self.m_indices, None, e.ws)
+
+
+class Engine:
+    def __init__(self, S, hidden, E, device, bayesian=False, precision='tf32', tpw=10.0, tnw=1.0, nsd='uniform', ns=5,
+                 seed=0, max_batch=1000):
+        if not torch.cuda.is_available():
+            raise _lib.NtfError('opentf_b200 needs a CUDA device: the kernels are sm_100a only and there is no CPU fallback')
+        self.device = torch.device(device)
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.ctx(self.dev_index)  # fails loudly if this is not a B200-class device
+        self.S, self.hidden, self.E = int(S), [int(x) for x in hidden], int(E)
+        self.bayesian, self.precision = bool(bayesian), PRECISION[precision]
+        self.tpw, self.tnw, self.nsd, self.ns, self.seed = float(tpw), float(tnw), NSD[nsd], int(ns), int(seed)
+        self.Bmax = int(max_batch)
+        self.sizes = [self.S] + self.hidden + [self.E]
+        self.L = len(self.sizes) - 1  # number of linear layers
+        self.ws = ops.Workspace(self.device)
+        self.skill = self.member = None
+        self._layout()
+        self._buffers()
+        self.adam_t = 0
+        self.global_step = 0  # counts train AND valid steps: the sampler's Philox counter (fnn.py:148 samples in valid too)
+        self.world, self.rank = 1, 0
+
+    # ------------------------------------------------------------------ memory
+    def _layout(self):
+        """name -> (offset, stored shape).  Fnn: layers.i.weight/bias.  Bnn: layers.i.{mu,rho}_{weight,bias}."""
+        self.views, off = {}, 0
+        kinds = ['mu_', 'rho_'] if self.bayesian else ['']
+        for i in range(self.L):
+            fin, fout = self.sizes[i], self.sizes[i + 1]
+            wshape = (fin, fout) if i == 0 else (fout, fin)  # layer 0 stored transposed
+            for k in kinds:
+                self.views[f'layers.{i}.{k}weight'] = (off, wshape); off += _round_up(fin * fout, ALIGN)
+            for k in kinds:
+                self.views[f'layers.{i}.{k}bias'] = (off, (fout,)); off += _round_up(fout, ALIGN)
+        self.n_params = off
+        if self.bayesian:  # per-step noise / perturbation buffers share one layout (one slot per (weight|bias) tensor)
+            self.nviews, off = {}, 0
+            for i in range(self.L):
+                fin, fout = self.sizes[i], self.sizes[i + 1]
+                self.nviews[f'{i}.weight'] = (off, (fin, fout) if i == 0 else (fout, fin)); off += _round_up(fin * fout, ALIGN)
+                self.nviews[f'{i}.bias'] = (off, (fout,)); off += _round_up(fout, ALIGN)
+            self.n_noise = off
+
+    def _buffers(self):
+        dev, f32 = self.device, torch.float32
+        self.params = torch.zeros(self.n_params, dtype=f32, device=dev)
+        self.grads = torch.zeros(self.n_params, dtype=f32, device=dev)
+        self.adam_m = torch.zeros(self.n_params, dtype=f32, device=dev)
+        self.adam_v = torch.zeros(self.n_params, dtype=f32, device=dev)
+        B = self.Bmax
+        self.act = [torch.empty(B, h, dtype=f32, device=dev) for h in self.hidden]
+        self.dact = [torch.empty(B, h, dtype=f32, device=dev) for h in self.hidden]
+        self.dz = [torch.empty(B, h, dtype=f32, device=dev) for h in self.hidden]
+        self.pitch = _round_up(self.E, 32) // 32
+        self.special = torch.zeros(B, self.pitch, dtype=torch.int32, device=dev)
+        self.neg = torch.full((B, max(1, self.ns)), -1, dtype=torch.int32, device=dev)
+        self.counts = torch.zeros(self.E, dtype=torch.int32, device=dev)
+        self.cdf = torch.zeros(self.E, dtype=torch.int32, device=dev)
+        self.loss_buf = torch.zeros(4096, dtype=f32, device=dev)
+        if self.bayesian:
+            self.eps = torch.zeros(self.n_noise, dtype=f32, device=dev)
+            self.delta = torch.zeros(self.n_noise, dtype=f32, device=dev)
+            self.gdelta = torch.zeros(self.n_noise, dtype=f32, device=dev)
+            self.kl = torch.zeros(1, dtype=f32, device=dev)
+            self.act_s = [torch.empty(B, h, dtype=f32, device=dev) for h in self.hidden]
+            self.dact_s = [torch.empty(B, h, dtype=f32, device=dev) for h in self.hidden]
+            self.dzs = [torch.empty(B, h, dtype=f32, device=dev) for h in self.hidden]
+            self.sign_in = [None] + [torch.zeros(B, _round_up(h, 32) // 32, dtype=torch.int32, device=dev) for h in self.hidden]
+            self.sign_out = [torch.zeros(B, _round_up(o, 32) // 32, dtype=torch.int32, device=dev) for o in self.sizes[1:]]
+
+    def view(self, name, buf=None):
+        off, shape = self.views[name]
+        return (self.params if buf is None else buf)[off:off + int(np.prod(shape))].view(*shape)
+
+    def nview(self, buf, key):
+        off, shape = self.nviews[key]
+        return buf[off:off + int(np.prod(shape))].view(*shape)
+
+    # ------------------------------------------------------------------ parameters
+    def load_state_dict(self, sd):
+        """torch-layout state dict (Fnn: layers.i.weight/bias; Bnn: layers.i.{mu,rho}_{weight,bias}) -> arena."""
+        missing = [k for k in self.views if k not in sd]
+        if missing: raise KeyError(f'state_dict is missing {missing}')
+        for name in self.views:
+            t = torch.as_tensor(sd[name]).detach().to(torch.float32)
+            if name.startswith('layers.0.') and name.endswith('weight'): t = t.t()
+            v = self.view(name)
+            if tuple(t.shape) != tuple(v.shape): raise ValueError(f'{name}: shape {tuple(t.shape)} does not fit {tuple(v.shape)}')
+            v.copy_(t.contiguous())
+
+    def state_dict(self):
+        out = {}
+        for name in self.views:
+            t = self.view(name).detach().cpu().clone()
+            if name.startswith('layers.0.') and name.endswith('weight'): t = t.t().contiguous()
+            out[name] = t
+        return out
+
+    def reset_optimizer(self):
+        self.adam_m.zero_(); self.adam_v.zero_(); self.adam_t = 0
+
+    # ------------------------------------------------------------------ data
+    def stage(self, skill_mat, member_mat):
+        self.skill, self.member = DeviceCSR(skill_mat, self.device), DeviceCSR(member_mat, self.device)
+        assert self.skill.shape[1] == self.S and self.member.shape[1] == self.E
+        return self
+
+    def split(self, rows):
+        return SplitData(self, rows)
+
+    def set_global_unigram(self):
+        """fnn.py:82: expert frequency over ALL teams -> integer counts + CDF (nsd == 'unigram')."""
+        N = self.member.shape[0]
+        ops.expert_cdf(N, self.member.indptr.data_ptr(), self.member.indices, self.E, self.counts, self.cdf, self.ws)
+
+    # ------------------------------------------------------------------ one step
+    def _forward_hidden(self, sp, b0, B):
+        ops.csr_bag_fwd(B, sp.s_indptr.data_ptr() + 4 * b0, sp.s_indices, self.view('layers.0.weight'), self.view('layers.0.bias'),
+                        self.S, self.hidden[0], self.act[0])
+        for i in range(1, self.L - 1):
+            ops.dense_fwd(self.act[i - 1], self.view(f'layers.{i}.weight'), self.view(f'layers.{i}.bias'), B, self.hidden[i - 1],
+                          self.hidden[i], 1, self.act[i])
+
+    def _sample(self, sp, b0, B, neg_host, gbatch=None):
+        """fills self.neg for this batch (or takes host-supplied indices: the parity-test contract).  `gbatch` =
+        (first row, size) of the GLOBAL batch this slice belongs to: unigram_b counts experts over all of it
+        (every rank holds the whole CSR, so no collective is needed for the histogram)."""
+        if self.nsd == 0 and neg_host is None: return None
+        if neg_host is not None:
+            t = torch.as_tensor(np.ascontiguousarray(neg_host), dtype=torch.int32)
+            assert t.shape[0] == B
+            neg = self.neg[:B, :t.shape[1]] if t.shape[1] == self.neg.shape[1] else torch.empty(B, t.shape[1], dtype=torch.int32, device=self.device)
+            neg.copy_(t)
+            return neg.contiguous()
+        mptr = sp.m_indptr.data_ptr() + 4 * b0
+        if self.nsd == NSD['unigram_b']:
+            g0, gB = (b0, B) if gbatch is None else gbatch
+            ops.expert_cdf(gB, sp.m_indptr.data_ptr() + 4 * g0, sp.m_indices, self.E, self.counts, self.cdf, self.ws)
+        ops.neg_sample(self.nsd, self.seed, self.global_step, b0, B, mptr, sp.m_indices, self.E, self.ns,
+                       self.cdf if self.nsd != NSD['uniform'] else None, self.neg)
+        return self.neg
+
+    def step(self, sp, b0, B, train, lr=None, loss_slot=0, neg_host=None, loss_scale=None, gbatch=None):
+        """one batch = rows [b0, b0+B) of split `sp`: forward + loss (+ backward + Adam when train).
+        The loss lands in self.loss_buf[loss_slot] (device); nothing is synchronised here."""
+        assert 0 < B <= self.Bmax and b0 + B <= sp.n
+        if self.bayesian: return self._step_bayes(sp, b0, B, train, lr, loss_slot, neg_host, loss_scale, gbatch)
+        h_last = self.hidden[-1]
+        Lo = self.L - 1
+        self._forward_hidden(sp, b0, B)
+        neg = self._sample(sp, b0, B, neg_host, gbatch)
+        mptr = sp.m_indptr.data_ptr() + 4 * b0
+        ns = 0 if neg is None else neg.shape[1]
+        ops.special_bits(1, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
+        a = OutTrainArgs()
+        a.A, a.W, a.b = self.act[-1].data_ptr(), self.view(f'layers.{Lo}.weight').data_ptr(), self.view(f'layers.{Lo}.bias').data_ptr()
+        a.special, a.pitch_words = self.special.data_ptr(), self.pitch
+        a.m_indptr, a.m_indices = mptr, sp.m_indices.data_ptr()
+        a.B, a.h, a.E = B, h_last, self.E
+        a.tpw, a.tnw, a.loss_scale = self.tpw, self.tnw, (1.0 / B if loss_scale is None else loss_scale)
+        a.loss_out = self.loss_buf.data_ptr() + 4 * loss_slot
+        if train:
+            a.dW, a.db = self.view(f'layers.{Lo}.weight', self.grads).data_ptr(), self.view(f'layers.{Lo}.bias', self.grads).data_ptr()
+            a.dA = self.dact[-1].data_ptr()
+        ops.out_train(self.dev_index, self.precision, a, self.ws)
+        ops.special_bits(0, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
+        self.global_step += 1
+        if not train: return
+        for i in range(self.L - 2, 0, -1):  # hidden dense layers
+            ops.act_bwd(self.dact[i], self.act[i], B, self.hidden[i], 1, self.dz[i], self.view(f'layers.{i}.bias', self.grads), self.ws)
+            ops.dense_bwd(self.act[i - 1], self.view(f'layers.{i}.weight'), self.dz[i], B, self.hidden[i - 1], self.hidden[i],
+                          self.view(f'layers.{i}.weight', self.grads), self.dact[i - 1], self.ws)
+        ops.act_bwd(self.dact[0], self.act[0], B, self.hidden[0], 1, self.dz[0], self.view('layers.0.bias', self.grads), self.ws)
+        ops.csr_bag_bwd(B, sp.s_indptr.data_ptr() + 4 * b0, sp.s_indices, sp.s_ent_row, b0, self.dz[0], self.S, self.hidden[0],
+                        self.view('layers.0.weight', self.grads))
+        self.optimizer_step(lr)
+
+    def optimizer_step(self, lr):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grads)  # sum over ranks; every rank scaled its loss by 1/B_global
+        self.adam_t += 1
+        ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, self.n_params, lr, 0.9, 0.999, 1e-8, self.adam_t)
+
+    def _step_bayes(self, sp, b0, B, train, lr, loss_slot, neg_host, loss_scale, gbatch):
+        raise NotImplementedError('Bnn engine lands in bnn_engine.py')
+
+    # ------------------------------------------------------------------ inference
+    def scores(self, sp, b0, B, out):
+        """out[:B] = sigmoid(model(X)) for rows [b0,b0+B) (fnn.py:211), dense [B,E] on the device."""
+        self._forward_hidden(sp, b0, B)
+        Lo = self.L - 1
+        ops.infer_scores(self.precision, self.act[-1], self.view(f'layers.{Lo}.weight'), self.view(f'layers.{Lo}.bias'), B, self.hidden[-1],
+                         self.E, out, self.ws)
+        return out
+
+    def topk(self, sp, b0, B, K, scores_buf, vals, idx):
+        """the K best experts per team in rank order; only [B,K] leaves the GPU (fnn.py:213-218 keeps [N,E] on the host)."""
+        self.scores(sp, b0, B, scores_buf)
+        ops.topk_select(scores_buf, B, self.E, K, 1.0, vals, idx)
+        return vals, idx

@@ -1,0 +1,101 @@
+"""Ranking metrics for *.pred files: the consumer side of the hot path (reference: src/evl/metric.py).
+
+`calculate_metrics` gives the same numbers as the reference's pytrec_eval call (metric.py:5-35) for the measure
+families OpeNTF asks for -- P_k, recall_k, ndcg_cut_k, map_cut_k, success_k (src/__config__.yaml:91) -- computed
+directly from the trec_eval definitions, so pytrec_eval is not needed.  Ranking follows trec_eval: score
+descending, ties by document id string descending.  Pinned by the reference's committed eval CSVs
+(tests/test_metric.py).
+"""
+import numpy as np
+import scipy.sparse as sp
+
+FAMILIES = ('P', 'recall', 'ndcg_cut', 'map_cut', 'success')
+
+
+def parse_metrics(metrics):
+    """['P_2,5,10', 'recall_2,5,10', ...] -> [(family, [k...])]"""
+    out = []
+    for m in metrics:
+        fam, _, ks = m.rpartition('_')
+        if fam not in FAMILIES: raise ValueError(f'unsupported trec measure {m!r} (supported: {FAMILIES})')
+        out.append((fam, [int(k) for k in ks.split(',')]))
+    return out
+
+
+def _ranked_hits(cols, vals, rel, depth):
+    """relevance (0/1) of the first `depth` documents in trec_eval order."""
+    if len(vals) > depth:  # metric.py:19-21: first-stage cut by value
+        cut = np.partition(vals, len(vals) - depth)[len(vals) - depth]
+        keep = np.nonzero(vals >= cut)[0]
+        cols, vals = cols[keep], vals[keep]
+    order = sorted(range(len(vals)), key=lambda i: (float(vals[i]), 'd' + str(int(cols[i]))), reverse=True)[:depth]
+    return np.fromiter((cols[i] in rel for i in order), dtype=np.float64, count=len(order))
+
+
+def calculate_metrics(Y, Y_, topK=None, per_instance=False, metrics=('P_2,5,10', 'recall_2,5,10', 'ndcg_cut_2,5,10')):
+    import pandas as pd
+    assert Y.shape == Y_.shape, f'Shape mismatch between truth Y {Y.shape} vs preds Y_ {Y_.shape}!'
+    fams = parse_metrics(metrics)
+    kmax = max(k for _, ks in fams for k in ks)
+    N, E = Y.shape
+    Yc = sp.csr_matrix(Y)
+    Yr = sp.csr_matrix(Y_) if sp.issparse(Y_) else None
+    first_stage = min(topK, E) if topK else E
+    names = [f'{f}_{k}' for f, ks in fams for k in ks]
+    res = {n: np.zeros(N) for n in names}
+    disc = 1.0 / np.log2(np.arange(2, kmax + 2))
+    for i in range(N):
+        rel = set(Yc.indices[Yc.indptr[i]:Yc.indptr[i + 1]].tolist())
+        if Yr is not None: cols, vals = Yr.indices[Yr.indptr[i]:Yr.indptr[i + 1]], Yr.data[Yr.indptr[i]:Yr.indptr[i + 1]]
+        else: cols, vals = np.arange(E), np.asarray(Y_[i])
+        if len(vals) > first_stage:  # keep the first_stage best by value (metric.py:19-28), then rank
+            keep = np.argsort(-vals, kind='stable')[:first_stage]
+            cols, vals = cols[keep], vals[keep]
+        hits = _ranked_hits(cols, vals, rel, kmax)
+        R = len(rel)
+        csum = np.cumsum(hits)
+        for f, ks in fams:
+            for k in ks:
+                h = hits[:k]
+                if f == 'P': v = h.sum() / k
+                elif f == 'recall': v = h.sum() / R if R else 0.0
+                elif f == 'success': v = float(h.sum() > 0)
+                elif f == 'ndcg_cut': v = (h * disc[:len(h)]).sum() / disc[:min(R, k)].sum() if R else 0.0
+                else: v = ((csum[:len(h)] / np.arange(1, len(h) + 1)) * h).sum() / R if R else 0.0  # map_cut
+                res[f'{f}_{k}'][i] = v
+    df = pd.DataFrame(res)
+    df_mean = df.mean().to_frame('mean').rename_axis('metrics')
+    return (df if per_instance else None), df_mean
+
+
+def calculate_auc_roc(Y, Y_, curve=False):
+    """metric.py:37-42 (micro-averaged; densifies like the reference)."""
+    from sklearn import metrics as skm
+    assert Y.shape == Y_.shape
+    yt = np.asarray(Y.todense()) if sp.issparse(Y) else np.asarray(Y)
+    yp = np.asarray(Y_.todense()) if sp.issparse(Y_) else np.asarray(Y_)
+    auc = skm.roc_auc_score(yt, yp, average='micro', multi_class='ovr')
+    if curve:
+        fpr, tpr, _ = skm.roc_curve(yt.ravel(), yp.ravel())
+        return auc, (fpr, tpr)
+    return auc, None
+
+
+def calculate_skill_coverage(X, Y_, expertskillvecs, per_instance=False, topks='2,5,10'):
+    """metric.py:44-73: fraction of a team's required skills held by the union of its top-k recommended experts."""
+    import pandas as pd
+    assert X.shape[0] == Y_.shape[0]
+    ks = [int(k) for k in topks.split(',')]
+    Xc, Sk = sp.csr_matrix(X), sp.csr_matrix(expertskillvecs)
+    teams = Y_.shape[0]
+    cov = {k: np.zeros(teams) for k in ks}
+    Yr = sp.csr_matrix(Y_) if sp.issparse(Y_) else None
+    for t in range(teams):
+        row = np.asarray(Yr.getrow(t).todense()).ravel() if Yr is not None else np.asarray(Y_[t])
+        ranked = np.argsort(row)[::-1]
+        need = Xc.indices[Xc.indptr[t]:Xc.indptr[t + 1]]
+        for k in ks:
+            have = np.unique(Sk[ranked[:k]].indices)
+            cov[k][t] = np.intersect1d(need, have).size / len(need)
+    df = pd.DataFrame({f'skill_coverage_{k}': cov[k] for k in ks})
+    return df, df.mean().to_frame('mean').rename_axis('metrics')

@@ -1,0 +1,171 @@
+"""Typed Python entry points over the C ABI: torch tensors in, kernels launched on torch's current stream.
+
+torch is used for device memory and streams only (every tensor handed in is a caller-owned device buffer);
+all arithmetic happens in libntf_b200.so.  Nothing here falls back to torch ops.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import OutTrainArgs, check, lib
+
+F32, I32 = torch.float32, torch.int32
+
+
+def _dev(t):
+    assert t.is_cuda, 'libntf_b200 works on CUDA buffers only (no CPU fallback)'
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _p(t, dtype=None):
+    if t is None: return None
+    assert t.is_cuda and t.is_contiguous(), 'device-resident contiguous tensor required'
+    if dtype is not None: assert t.dtype == dtype, f'expected {dtype}, got {t.dtype}'
+    return t.data_ptr()
+
+
+class Workspace:
+    """a grow-only scratch buffer owned by the caller side (the library never allocates)."""
+
+    def __init__(self, device):
+        self.device, self.buf = device, None
+
+    def get(self, nbytes):
+        if nbytes <= 0: return None, 0
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self.buf.data_ptr(), self.buf.numel()
+
+
+def csr_gather(rows, n, src_indptr, src_indices, dst_indptr, dst_indices, dst_ent_row, ws):
+    d = _dev(src_indptr)
+    p, nb = ws.get(lib().ntf_csr_gather_workspace_bytes(n))
+    check(lib().ntf_csr_gather(_lib.ctx(d), _stream(d), _p(rows, I32), n, _p(src_indptr, I32), _p(src_indices, I32),
+                               _p(dst_indptr, I32), _p(dst_indices, I32), _p(dst_ent_row, I32), p, nb), 'ntf_csr_gather')
+
+
+def csr_bag_fwd(B, indptr_ptr, indices, W0T, b0, S, h, A):
+    d = _dev(W0T)
+    check(lib().ntf_csr_bag_fwd(_lib.ctx(d), _stream(d), B, indptr_ptr, _p(indices, I32), _p(W0T, F32), _p(b0, F32), S, h, _p(A, F32)),
+          'ntf_csr_bag_fwd')
+
+
+def csr_bag_bwd(B, indptr_ptr, indices, ent_row, row_base, dZ, S, h, dW0T):
+    d = _dev(dZ)
+    check(lib().ntf_csr_bag_bwd(_lib.ctx(d), _stream(d), B, indptr_ptr, _p(indices, I32), _p(ent_row, I32), row_base, _p(dZ, F32), S, h,
+                                _p(dW0T, F32)), 'ntf_csr_bag_bwd')
+
+
+def dense_fwd(A, W, b, B, inn, out, act, Y):
+    d = _dev(A)
+    check(lib().ntf_dense_fwd(_lib.ctx(d), _stream(d), _p(A, F32), _p(W, F32), _p(b, F32), B, inn, out, act, _p(Y, F32)), 'ntf_dense_fwd')
+
+
+def act_bwd(dY, Y, B, h, act, dZ, db, ws):
+    d = _dev(dY)
+    p, nb = ws.get(lib().ntf_act_bwd_workspace_bytes(B, h))
+    check(lib().ntf_act_bwd(_lib.ctx(d), _stream(d), _p(dY, F32), _p(Y, F32), B, h, act, _p(dZ, F32), _p(db, F32), p, nb), 'ntf_act_bwd')
+
+
+def dense_bwd(A, W, dZ, B, inn, out, dW, dA, ws):
+    d = _dev(A)
+    p, nb = ws.get(lib().ntf_dense_bwd_workspace_bytes(B, inn, out))
+    check(lib().ntf_dense_bwd(_lib.ctx(d), _stream(d), _p(A, F32), _p(W, F32), _p(dZ, F32), B, inn, out, _p(dW, F32), _p(dA, F32), p, nb),
+          'ntf_dense_bwd')
+
+
+def expert_cdf(B, m_indptr_ptr, m_indices, E, counts, cdf, ws):
+    d = _dev(m_indices)
+    p, nb = ws.get(lib().ntf_expert_cdf_workspace_bytes(E))
+    check(lib().ntf_expert_cdf(_lib.ctx(d), _stream(d), B, m_indptr_ptr, _p(m_indices, I32), E, _p(counts), _p(cdf), p, nb), 'ntf_expert_cdf')
+
+
+def neg_sample(nsd, seed, step, row0, B, m_indptr_ptr, m_indices, E, ns, cdf, neg):
+    d = _dev(m_indices)
+    check(lib().ntf_neg_sample(_lib.ctx(d), _stream(d), nsd, seed, step, row0, B, m_indptr_ptr, _p(m_indices, I32), E, ns, _p(cdf),
+                               _p(neg, I32)), 'ntf_neg_sample')
+
+
+def special_bits(op, B, m_indptr_ptr, m_indices, neg, ns, E, special, pitch):
+    d = _dev(m_indices)
+    check(lib().ntf_special_bits(_lib.ctx(d), _stream(d), op, B, m_indptr_ptr, _p(m_indices, I32), _p(neg, I32), ns, E, _p(special), pitch),
+          'ntf_special_bits')
+
+
+def out_train_workspace_bytes(dev, precision, B, h, E, flipout):
+    return lib().ntf_out_train_workspace_bytes(_lib.ctx(dev), precision, B, h, E, int(flipout))
+
+
+def out_train(dev, precision, args, ws):
+    p, nb = ws.get(out_train_workspace_bytes(dev, precision, args.B, args.h, args.E, bool(args.W_delta)))
+    check(lib().ntf_out_train(_lib.ctx(dev), _stream(dev), precision, C.byref(args), p, nb), 'ntf_out_train')
+
+
+def adam_step(p, g, m, v, n, lr, b1, b2, eps, step):
+    d = _dev(p)
+    check(lib().ntf_adam_step(_lib.ctx(d), _stream(d), _p(p, F32), _p(g, F32), _p(m, F32), _p(v, F32), n, lr, b1, b2, eps, step), 'ntf_adam_step')
+
+
+def infer_scores(precision, A, W, b, B, h, E, P, ws, accumulate=0, A_s=None, W_delta=None, b_delta=None, sign_out=None, pitch=0):
+    d = _dev(A)
+    p, nb = ws.get(lib().ntf_infer_scores_workspace_bytes(B, E, int(W_delta is not None)))
+    check(lib().ntf_infer_scores(_lib.ctx(d), _stream(d), precision, _p(A, F32), _p(W, F32), _p(b, F32), B, h, E, _p(A_s, F32), _p(W_delta, F32),
+                                 _p(b_delta, F32), _p(sign_out), pitch, accumulate, _p(P, F32), p, nb), 'ntf_infer_scores')
+
+
+def topk_select(P, B, E, K, scale, vals, idx):
+    d = _dev(P)
+    check(lib().ntf_topk_select(_lib.ctx(d), _stream(d), _p(P, F32), B, E, K, scale, _p(vals, F32), _p(idx, I32)), 'ntf_topk_select')
+
+
+def topk_merge(vals_in, idx_in, G, B, K, vals, idx):
+    d = _dev(vals_in)
+    check(lib().ntf_topk_merge(_lib.ctx(d), _stream(d), _p(vals_in, F32), _p(idx_in, I32), G, B, K, _p(vals, F32), _p(idx, I32)), 'ntf_topk_merge')
+
+
+def row_entropy(P, B, E, scale, accumulate, out):
+    d = _dev(P)
+    check(lib().ntf_row_entropy(_lib.ctx(d), _stream(d), _p(P, F32), B, E, scale, accumulate, _p(out, F32)), 'ntf_row_entropy')
+
+
+def axpy(n, a, x, y):
+    d = _dev(x)
+    check(lib().ntf_axpy(_lib.ctx(d), _stream(d), n, a, _p(x, F32), _p(y, F32)), 'ntf_axpy')
+
+
+def flipout_prepare(mu, rho, eps, n, kl_scale, delta, kl_out, ws):
+    d = _dev(mu)
+    p, nb = ws.get(lib().ntf_flipout_prepare_workspace_bytes(_lib.ctx(d)))
+    check(lib().ntf_flipout_prepare(_lib.ctx(d), _stream(d), _p(mu, F32), _p(rho, F32), _p(eps, F32), n, kl_scale, _p(delta, F32), _p(kl_out, F32), p, nb),
+          'ntf_flipout_prepare')
+
+
+def flipout_grads(mu, rho, eps, g_delta, n, kl_gscale, g_mu, g_rho):
+    d = _dev(mu)
+    check(lib().ntf_flipout_grads(_lib.ctx(d), _stream(d), _p(mu, F32), _p(rho, F32), _p(eps, F32), _p(g_delta, F32), n, kl_gscale, _p(g_mu, F32),
+                                  _p(g_rho, F32)), 'ntf_flipout_grads')
+
+
+def fill_normal(seed, step, stream_id, n, out):
+    d = _dev(out)
+    check(lib().ntf_fill_normal(_lib.ctx(d), _stream(d), seed, step, stream_id, n, _p(out, F32)), 'ntf_fill_normal')
+
+
+def fill_sign_bits(seed, step, stream_id, n_words, bits):
+    d = _dev(bits)
+    check(lib().ntf_fill_sign_bits(_lib.ctx(d), _stream(d), seed, step, stream_id, n_words, _p(bits)), 'ntf_fill_sign_bits')
+
+
+def apply_sign(A, bits, pitch, B, h, As):
+    d = _dev(A)
+    check(lib().ntf_apply_sign(_lib.ctx(d), _stream(d), _p(A, F32), _p(bits), pitch, B, h, _p(As, F32)), 'ntf_apply_sign')
+
+
+def sum_parts(parts, nparts, n, stride, out):
+    d = _dev(parts)
+    check(lib().ntf_sum_parts(_lib.ctx(d), _stream(d), _p(parts, F32), nparts, n, stride, _p(out, F32)), 'ntf_sum_parts')
