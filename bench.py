@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- train teams/s of the Fnn hot path on a synthetic DBLP-v12-shaped workload (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload dblp] [--batch 1000] [--precision tf32]
+
+A step = one training batch: input layer, negative sampling, output layer forward + weighted BCE + backward, input
+layer backward, Adam.  `value` times K steps with every input resident in HBM (CUDA events, max over ranks);
+`e2e` times the same steps through the streaming entry point with HOST batches (pinned H2D of the batch CSR and a
+D2H read of the loss inside the timed region).  Under torchrun each rank works on its own slice of a global
+batch of N x --batch teams (weak scaling), gradients are all-reduced over NCCL.
+`--impl reference` times the reference's own CPU implementation of the same step (the oracle port of
+src/mdl/fnn.py, torch CPU, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path: sys.path.insert(0, ROOT)
+
+METRIC, UNIT = 'train teams/s (Fnn, unigram_b, fwd+bwd+Adam)', 'teams/s'
+SEEDS = {'dblp': 12, 'imdb': 3, 'uspt': 4, 'toy': 1}
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument('--gpus', type=int, default=1)
+    p.add_argument('--steps', type=int, default=50)
+    p.add_argument('--warmup', type=int, default=5)
+    p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    p.add_argument('--workload', default='dblp', choices=list(SEEDS))
+    p.add_argument('--batch', type=int, default=1000, help='teams per GPU per step (reference default b=1000)')
+    p.add_argument('--precision', default='tf32', choices=['tf32', 'fp32'])
+    p.add_argument('--nsd', default='unigram_b')
+    p.add_argument('--cpu-baseline-seconds', type=float, default=15.0)
+    p.add_argument('--no-cpu-baseline', action='store_true')
+    p.add_argument('--infer-k', type=int, default=10)
+    return p.parse_args()
+
+
+def workload(name):
+    """the synthetic teamsvecs + splits (cached as npz under /tmp: every rank and both arms see the same data)."""
+    import scipy.sparse as sp
+    from opentf_b200 import synth
+    path = f'/tmp/ntf_b200_synth_{name}_{SEEDS[name]}.npz'
+    if not os.path.exists(path):
+        tv = synth.make_teamsvecs(name, seed=SEEDS[name])
+        tmp = f'{path}.{os.getpid()}.npz'
+        np.savez(tmp, s_ptr=tv['skill'].indptr, s_idx=tv['skill'].indices, s_shape=tv['skill'].shape, m_ptr=tv['member'].indptr,
+                 m_idx=tv['member'].indices, m_shape=tv['member'].shape)
+        os.replace(tmp, path)
+    z = np.load(path)
+    mk = lambda p: sp.csr_matrix((np.ones(len(z[f'{p}_idx']), dtype=np.uint8), z[f'{p}_idx'], z[f'{p}_ptr']), shape=tuple(z[f'{p}_shape']))
+    tv = {'skill': mk('s'), 'member': mk('m')}
+    return tv, synth.make_splits(tv['skill'].shape[0], seed=SEEDS[name])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100', '-i', str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.rows.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try: self.proc.wait(2)
+            except Exception: self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for l in self.rows:
+            f = [x.strip() for x in l.split(',')]
+            if len(f) < 8: continue
+            try: sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError: continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if v.lower().startswith('active'): reasons.add(name)
+        if not sm: return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p)); d['_source'] = 'measured'
+        return d
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, '_source': 'fallback'}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_reference_steps(tv, splits, batch, nsd, max_seconds, min_steps=1, warmup=1, max_steps=10 ** 9):
+    """the reference's CPU implementation of one step (oracle port of fnn.py:118-140, incl. its per-row densification),
+    on fold-0 train batches of the same workload.  Returns (teams/s, steps timed, seconds, threads)."""
+    import torch
+    from oracle import fnn_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    S, E = tv['skill'].shape[1], tv['member'].shape[1]
+    rows_all = np.asarray(splits['folds'][0]['train'])
+    torch.manual_seed(0)
+    layers = O.init_params(S, [128], E)
+    flat = [t for Wb in layers for t in Wb]
+    opt = O.Adam(flat, 1e-3)
+    skill_lil, member_lil = tv['skill'].tolil(), tv['member'].tolil()  # what the reference is handed (team.py:154)
+
+    def one(bi):
+        rows = rows_all[(bi * batch) % (len(rows_all) - batch):][:batch]
+        # ntf.py:23: one lil row at a time -> csr -> dense -> float, then the default collate stacks them
+        X = torch.stack([torch.as_tensor(skill_lil[int(r)].tocsr().toarray()).float() for r in rows]).squeeze(1)
+        y = torch.stack([torch.as_tensor(member_lil[int(r)].tocsr().toarray()).float() for r in rows]).squeeze(1)
+        logits, acts, pre = O.forward(layers, X)
+        neg = O.sample_negatives(y, nsd, 5, None)
+        w = O.loss_weights(y, neg, 10, 1)
+        loss = O.bce_with_logits(logits, y, w).sum(dim=1).mean()
+        opt.step([g for Wb in O.backward(layers, acts, pre, y, w) for g in Wb])
+        return loss.item()
+
+    for i in range(warmup): one(i)
+    t0, n = time.perf_counter(), 0
+    while n < max_steps and (n < min_steps or time.perf_counter() - t0 < max_seconds):
+        one(warmup + n); n += 1
+    dt = time.perf_counter() - t0
+    return n * batch / dt, n, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0: return  # rank 0 alone runs the CPU arm
+    tv, splits = workload(args.workload)
+    steps = max(1, min(args.steps, 20))
+    v, n, dt, threads = cpu_reference_steps(tv, splits, args.batch, args.nsd, 1e9, min_steps=steps, warmup=min(args.warmup, 2), max_steps=steps)
+    sample = f'{n} steps of b={args.batch} on fold-0 train rows of the {args.workload}-shaped workload (oracle port of fnn.py:118-140 incl. per-row densification)'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': n, 'warmup': min(args.warmup, 2),
+        'ms_per_step': 1e3 * dt / n, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': config_of(args, tv), 'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
+
+
+def config_of(args, tv):
+    N, S = tv['skill'].shape; E = tv['member'].shape[1]
+    return {'workload': f'{args.workload}-shaped synthetic teamsvecs (BASELINE configs[1]): N={N} S={S} E={E}, Fnn h=[128], nsd={args.nsd}, ns=5, tpw=10, tnw=1',
+            'batch_per_gpu': args.batch, 'global_batch': args.batch * args.gpus, 'parallelism': f'dp{args.gpus}', 'precision': args.precision,
+            'l2_policy': 'no flush: one step touches params+grads+Adam state (>140 MB) and the [B,E] work set, larger than the 126 MB L2'}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from opentf_b200 import _lib, ops
+    from opentf_b200.engine import Engine, to_csr
+
+    world, rank, local = int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device(f'cuda:{local}')
+    if world > 1: dist.init_process_group('nccl', device_id=dev)
+    tv, splits = workload(args.workload)
+    N, S = tv['skill'].shape; E = tv['member'].shape[1]
+    b, G = args.batch, world
+    eng = Engine(S, [128], E, dev, precision=args.precision, tpw=10, tnw=1, nsd=args.nsd, ns=5, seed=0, max_batch=b)
+    eng.world, eng.rank = world, rank
+    eng.stage(tv['skill'], tv['member'])
+    torch.manual_seed(0)
+    lin = [torch.nn.Linear(S, 128), torch.nn.Linear(128, E)]
+    for m in lin: torch.nn.init.xavier_uniform_(m.weight)
+    eng.load_state_dict({f'layers.{i}.{n}': getattr(m, n).detach() for i, m in enumerate(lin) for n in ('weight', 'bias')})
+    train_rows = np.asarray(splits['folds'][0]['train'])
+    sp = eng.split(train_rows[np.random.default_rng(0).permutation(len(train_rows))])
+    gB = b * G
+    nb = sp.n // gB
+    assert nb >= 1, 'workload smaller than one global batch'
+    precision_used = 'tf32' if eng.precision == _lib.NTF_TF32 else 'fp32'
+
+    def device_step(i):
+        g0 = (i % nb) * gB
+        eng.step(sp, g0 + rank * b, b, True, lr=1e-3, loss_slot=i % 1024, loss_scale=1.0 / gB, gbatch=(g0, gB))
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-resident timing: `value` ----
+    for i in range(args.warmup): device_step(i)
+    sync()
+    _lib.lib().ntf_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the dominant kernel group (output layer: forward + loss + backward) timed live with events on the launching stream
+    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    orig_out_train = ops.out_train
+    cur = {'i': 0}
+
+    def timed_out_train(*a, **k):
+        k0[cur['i']].record(); orig_out_train(*a, **k); k1[cur['i']].record()
+    ops.out_train = timed_out_train
+    with ClockSampler(local) as clk:
+        sync()
+        ev0.record()
+        for i in range(args.steps):
+            cur['i'] = i
+            device_step(args.warmup + i)
+        ev1.record()
+        sync()
+    ops.out_train = orig_out_train
+    launches = int(_lib.lib().ntf_launch_count(0))
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = args.steps * gB / (ms * 1e-3)
+    k_ms = float(np.mean([a.elapsed_time(c) for a, c in zip(k0, k1)]))
+
+    # ---- end to end through the streaming entry point: host batches in, loss out ----
+    host = HostBatches(tv, train_rows, b, rank, G)
+    for i in list(range(min(3, args.warmup))) + [100 + i for i in range(args.steps)]: host.batch(i)  # pinned host inputs exist before timing
+    for i in range(min(3, args.warmup)): host.step(eng, i)
+    sync()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps): host.step(eng, 100 + i)
+    e1.record()
+    sync()
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = args.steps * gB / (float(t.item()) * 1e-3)
+
+    # ---- top-K inference teams/s (second half of BASELINE's metric), device resident ----
+    test_sp = eng.split(np.asarray(splits['test']))
+    ib = min(b, test_sp.n)
+    scores = torch.empty(ib, E, device=dev)
+    vals, idx = torch.empty(ib, args.infer_k, device=dev), torch.empty(ib, args.infer_k, dtype=torch.int32, device=dev)
+    for _ in range(3): eng.topk(test_sp, 0, ib, args.infer_k, scores, vals, idx)
+    sync()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    i0.record()
+    for r in range(reps): eng.topk(test_sp, (r * ib) % max(1, test_sp.n - ib + 1), ib, args.infer_k, scores, vals, idx)
+    i1.record()
+    sync()
+    infer_value = reps * ib * G / (i0.elapsed_time(i1) * 1e-3)
+
+    if rank != 0:
+        if world > 1: dist.destroy_process_group()
+        return
+    pk = peaks()
+    flops = 6.0 * 128 * E * b  # K3 flops/team (Fnn train) = 6*h_L*E, per launch of b teams
+    tensor_peak = pk['bf16_tflops_sustained'] / 2 if precision_used == 'tf32' else None  # tf32 runs at half the bf16 MMA rate
+    roof = {'bound': 'tensor', 'kernel': f'ntf_out_train[{precision_used}] (output layer fwd + weighted BCE + bwd)', 'achieved': flops / (k_ms * 1e-3) / 1e12,
+            'peak': tensor_peak if tensor_peak else 0.5 * pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'traffic': None,
+            'peak_source': f"{pk['_source']} bf16 sustained {pk['bf16_tflops_sustained']} TF/s / 2 (kind::tf32 is half the bf16 rate)",
+            'avg_launch_ms': k_ms, 'share_of_step': k_ms * args.steps / ms}
+    roof['frac'] = roof['achieved'] / roof['peak']
+    out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': G, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if precision_used == 'fp32' else 'tf32 (fp32 accumulate)',
+           'data': 'synthetic', 'config': config_of(args, tv), 'clocks': clk.summary(),
+           'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': host.h2d_bytes, 'd2h_bytes_per_step': 4,
+                   'api': 'Engine.step_host: pinned batch CSR -> H2D -> step -> loss.item()'},
+           'gpu_launches': launches, 'roofline': roof, 'infer_topk': {'k': args.infer_k, 'value': infer_value, 'unit': 'teams/s', 'batch': ib}}
+    if not args.no_cpu_baseline:
+        v, n, dt, threads = cpu_reference_steps(tv, splits, b, args.nsd, args.cpu_baseline_seconds)
+        out['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                               'sample': f'{n} steps of b={b} ({dt:.1f} s) of the same workload, oracle port of fnn.py:118-140 incl. per-row densification'}
+    print(json.dumps(out))
+    if world > 1: dist.destroy_process_group()
+
+
+class HostBatches:
+    """batches as the host holds them (pinned CSR slices of teamsvecs) for the end-to-end leg."""
+
+    def __init__(self, tv, train_rows, b, rank, G):
+        import torch
+        from opentf_b200.engine import to_csr
+        self.b, self.rank, self.G = b, rank, G
+        self.s = to_csr(tv['skill']); self.m = to_csr(tv['member'])
+        self.rows = train_rows
+        self.h2d_bytes = 0
+        self.pin = {}
+
+    def batch(self, i):
+        """pinned compact CSR of global batch i (built once, outside any timed region)"""
+        import torch
+        if i in self.pin: return self.pin[i]
+        gB = self.b * self.G
+        g0 = (i * gB) % (len(self.rows) - gB)
+        rows = self.rows[g0:g0 + gB]
+        out = []
+        for k, (ptr, idx, _) in enumerate((self.s, self.m)):
+            lens = ptr[rows + 1] - ptr[rows]
+            p = np.zeros(len(rows) + 1, dtype=np.int32); np.cumsum(lens, out=p[1:])
+            ind = np.concatenate([idx[ptr[r]:ptr[r + 1]] for r in rows]).astype(np.int32)
+            out += [torch.from_numpy(p).pin_memory(), torch.from_numpy(ind).pin_memory()]
+            if k == 0: out.append(torch.from_numpy(np.repeat(np.arange(len(rows), dtype=np.int32), lens)).pin_memory())
+        self.pin[i] = out
+        return out
+
+    def step(self, eng, i):
+        s_ptr, s_idx, s_row, m_ptr, m_idx = self.batch(i)
+        self.h2d_bytes = sum(t.numel() * 4 for t in (s_ptr, s_idx, s_row, m_ptr, m_idx))
+        return eng.step_host(s_ptr, s_idx, s_row, m_ptr, m_idx, self.rank, self.G, lr=1e-3)
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference': run_reference(a)
+    else: run_ours(a)

@@ -51,6 +51,8 @@ int ntf_last_error(char* buf, size_t n);
 int ntf_create(int device, ntf_ctx** out);
 int ntf_destroy(ntf_ctx* ctx);
 int ntf_sm_count(const ntf_ctx* ctx);
+/* number of kernels this library has launched in this process (reset != 0 clears it): launch accounting for bench.py */
+unsigned long long ntf_launch_count(int reset);
 
 /* ---- batching: replaces DataLoader(shuffle) + NtfDataset.__getitem__ (fnn.py:95-97, ntf.py:17-25) ------------
  * dst row i = src row rows[i] (rows == NULL: identity).  dst_indptr gets n+1 offsets (exclusive scan of the
@@ -136,6 +138,8 @@ typedef struct {
   float* db_delta;             /* [E]                                                                */
   float* dA_s;                 /* [B,h]                                                              */
 } ntf_out_train_args;
+/* 1 if NTF_TF32 has a tcgen05 kernel for this shape (else callers use NTF_FP32; ntf_out_train(NTF_TF32) refuses it) */
+int ntf_tc_supported(int B, int h, int E, int flipout);
 size_t ntf_out_train_workspace_bytes(const ntf_ctx* ctx, int precision, int B, int h, int E, int flipout);
 int ntf_out_train(ntf_ctx* ctx, void* stream, int precision, const ntf_out_train_args* args, void* workspace,
                   size_t workspace_bytes);

@@ -31,6 +31,7 @@ SIGNATURES = {
     'ntf_create': (i32, [i32, C.POINTER(vp)]),
     'ntf_destroy': (i32, [vp]),
     'ntf_sm_count': (i32, [vp]),
+    'ntf_launch_count': (C.c_ulonglong, [i32]),
     'ntf_csr_gather_workspace_bytes': (sz, [i32]),
     'ntf_csr_gather': (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz]),
     'ntf_csr_bag_fwd': (i32, [vp, vp, i32, vp, vp, vp, vp, i32, i32, vp]),
@@ -44,6 +45,7 @@ SIGNATURES = {
     'ntf_expert_cdf': (i32, [vp, vp, i32, vp, vp, i32, vp, vp, vp, sz]),
     'ntf_neg_sample': (i32, [vp, vp, i32, u64, u64, i32, i32, vp, vp, i32, i32, vp, vp]),
     'ntf_special_bits': (i32, [vp, vp, i32, i32, vp, vp, vp, i32, i32, vp, i32]),
+    'ntf_tc_supported': (i32, [i32, i32, i32, i32]),
     'ntf_out_train_workspace_bytes': (sz, [vp, i32, i32, i32, i32, i32]),
     'ntf_out_train': (i32, [vp, vp, i32, C.POINTER(OutTrainArgs), vp, sz]),
     'ntf_adam_step': (i32, [vp, vp, vp, vp, vp, vp, sz, f64, f64, f64, f64, i64]),

@@ -41,7 +41,7 @@ extern "C" int ntf_adam_step(ntf_ctx* ctx, void* stream, float* p, const float* 
   const size_t n4 = aligned ? n / 4 : 0;
   const size_t work = n4 ? n4 : n;
   const int blocks = (int)((work + 255) / 256 < (size_t)ctx->sm_count * 16 ? (work + 255) / 256 : (size_t)ctx->sm_count * 16);
-  adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n4, n, k);
+  NTF_COUNT_LAUNCH; adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n4, n, k);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

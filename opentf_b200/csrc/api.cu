@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
+unsigned long long g_ntf_launches = 0;
 
 void ntf_set_error(const char* fmt, ...) {
   va_list ap;
@@ -54,3 +55,9 @@ extern "C" int ntf_destroy(ntf_ctx* ctx) {
 }
 
 extern "C" int ntf_sm_count(const ntf_ctx* ctx) { return ctx ? ctx->sm_count : NTF_ERR_BAD_ARG; }
+
+extern "C" unsigned long long ntf_launch_count(int reset) {
+  const unsigned long long v = g_ntf_launches;
+  if (reset) g_ntf_launches = 0;
+  return v;
+}

@@ -15,6 +15,10 @@ struct ntf_ctx {
   void* encode_tiled;  // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
 };
 
+// ---- launch accounting (bench.py reports how many of OUR kernels ran in the timed region) ----------------
+extern unsigned long long g_ntf_launches;
+#define NTF_COUNT_LAUNCH (++g_ntf_launches)
+
 // ---- error plumbing -------------------------------------------------------------------------------------
 void ntf_set_error(const char* fmt, ...);
 

@@ -105,9 +105,9 @@ int ntf_scan_u32_impl(cudaStream_t st, const uint32_t* in, size_t n, uint32_t* o
               ntf_scan_workspace_bytes(n));
   const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
   uint32_t* tile = (uint32_t*)ws;
-  scan_tile_totals<<<ntiles, SCAN_THREADS, 0, st>>>(in, n, tile);
-  scan_tile_offsets<<<1, SCAN_THREADS, 0, st>>>(tile, ntiles);
-  scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(in, n, tile, out, inclusive, grand_total);
+  NTF_COUNT_LAUNCH; scan_tile_totals<<<ntiles, SCAN_THREADS, 0, st>>>(in, n, tile);
+  NTF_COUNT_LAUNCH; scan_tile_offsets<<<1, SCAN_THREADS, 0, st>>>(tile, ntiles);
+  NTF_COUNT_LAUNCH; scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(in, n, tile, out, inclusive, grand_total);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
@@ -155,11 +155,11 @@ extern "C" int ntf_csr_gather(ntf_ctx* ctx, void* stream, const int32_t* rows, i
     return NTF_OK;
   }
   // lengths are staged in dst_indptr[0..n) and scanned in place (exclusive)
-  csr_row_lengths<<<cdiv(n, 256), 256, 0, st>>>(rows, n, src_indptr, (uint32_t*)dst_indptr);
+  NTF_COUNT_LAUNCH; csr_row_lengths<<<cdiv(n, 256), 256, 0, st>>>(rows, n, src_indptr, (uint32_t*)dst_indptr);
   int rc = ntf_scan_u32_impl(st, (const uint32_t*)dst_indptr, (size_t)n, (uint32_t*)dst_indptr, 0, nullptr, workspace,
                              workspace_bytes);
   if (rc) return rc;
-  csr_copy_rows<<<cdiv(n * 32, 256), 256, 0, st>>>(rows, n, src_indptr, src_indices, dst_indptr, dst_indices, dst_ent_row);
+  NTF_COUNT_LAUNCH; csr_copy_rows<<<cdiv(n * 32, 256), 256, 0, st>>>(rows, n, src_indptr, src_indices, dst_indptr, dst_indices, dst_ent_row);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
@@ -221,6 +221,7 @@ extern "C" int ntf_csr_bag_fwd(ntf_ctx* ctx, void* stream, int B, const int32_t*
   if (B == 0) return NTF_OK;
   const int blocks = min(cdiv(B, 8), ctx->sm_count * 8);
   const bool vec = (h % 4 == 0) && (((uintptr_t)W0T | (uintptr_t)b0 | (uintptr_t)A) % 16 == 0);
+  NTF_COUNT_LAUNCH;
   if (vec) csr_bag_fwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(B, indptr, indices, W0T, b0, h, A);
   else csr_bag_fwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(B, indptr, indices, W0T, b0, h, A);
   NTF_LAUNCH_CHECK();
@@ -289,7 +290,7 @@ extern "C" int ntf_csr_bag_bwd(ntf_ctx* ctx, void* stream, int B, const int32_t*
   NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nchunks = cdiv(S, skw);
   const int blocks = min(cdiv(nchunks, BWD_WARPS), ctx->sm_count * 3);
-  csr_bag_bwd_kernel<<<blocks, BWD_WARPS * 32, smem, as_stream(stream)>>>(B, indptr, indices, ent_row, row_base, dZ, S, h,
+  NTF_COUNT_LAUNCH; csr_bag_bwd_kernel<<<blocks, BWD_WARPS * 32, smem, as_stream(stream)>>>(B, indptr, indices, ent_row, row_base, dZ, S, h,
                                                                          skw, dW0T);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
@@ -336,8 +337,8 @@ extern "C" int ntf_act_bwd(ntf_ctx* ctx, void* stream, const float* dY, const fl
   NTF_REQUIRE(workspace_bytes >= ntf_act_bwd_workspace_bytes(B, h), NTF_ERR_WORKSPACE, "act_bwd: workspace too small");
   const int nparts = cdiv(B, ACT_ROWS);
   dim3 grid(cdiv(h, 128), nparts);
-  act_bwd_kernel<<<grid, 128, 0, as_stream(stream)>>>(dY, Y, B, h, act, dZ, (float*)workspace);
-  colsum_parts_kernel<<<cdiv(h, 128), 128, 0, as_stream(stream)>>>((const float*)workspace, nparts, h, db);
+  NTF_COUNT_LAUNCH; act_bwd_kernel<<<grid, 128, 0, as_stream(stream)>>>(dY, Y, B, h, act, dZ, (float*)workspace);
+  NTF_COUNT_LAUNCH; colsum_parts_kernel<<<cdiv(h, 128), 128, 0, as_stream(stream)>>>((const float*)workspace, nparts, h, db);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

@@ -161,7 +161,7 @@ template <class Epi>
 int launch_gemm(cudaStream_t st, const GemmArgs& g, const Epi& epi, int nsplit = 1) {
   dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), nsplit);
   NTF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, NTF_ERR_UNSUPPORTED, "gemm grid too large (%u,%u,%u)", grid.x, grid.y, grid.z);
-  sgemm_kernel<Epi><<<grid, 256, 0, st>>>(g, epi);
+  NTF_COUNT_LAUNCH; sgemm_kernel<Epi><<<grid, 256, 0, st>>>(g, epi);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
@@ -202,20 +202,20 @@ __global__ void colsum_pass1(const float* __restrict__ X, int R, int C, float* _
 }  // namespace
 
 int ntf_sum_parts_impl(cudaStream_t st, const float* parts, int nparts, size_t n, size_t stride, float* out) {
-  sum_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(parts, nparts, n, stride, out);
+  NTF_COUNT_LAUNCH; sum_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(parts, nparts, n, stride, out);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
 int ntf_loss_reduce_impl(cudaStream_t st, const float* part, int n, float* loss_out) {
-  loss_reduce_kernel<<<1, 256, 0, st>>>(part, n, loss_out);
+  NTF_COUNT_LAUNCH; loss_reduce_kernel<<<1, 256, 0, st>>>(part, n, loss_out);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
 int ntf_colsum_impl(cudaStream_t st, const float* X, int R, int C, float* out, float* part_ws) {
   const int np = cdiv(R, CS_ROWS);
   NTF_REQUIRE(np <= 65535, NTF_ERR_UNSUPPORTED, "colsum: too many rows %d", R);
-  colsum_pass1<<<dim3(cdiv(C, 128), np), 128, 0, st>>>(X, R, C, part_ws);
-  sum_parts_kernel<<<cdiv(C, 256), 256, 0, st>>>(part_ws, np, (size_t)C, (size_t)C, out);
+  NTF_COUNT_LAUNCH; colsum_pass1<<<dim3(cdiv(C, 128), np), 128, 0, st>>>(X, R, C, part_ws);
+  NTF_COUNT_LAUNCH; sum_parts_kernel<<<cdiv(C, 256), 256, 0, st>>>(part_ws, np, (size_t)C, (size_t)C, out);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

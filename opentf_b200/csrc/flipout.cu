@@ -99,7 +99,7 @@ static int grid_for(const ntf_ctx* ctx, size_t n) {
 extern "C" int ntf_fill_normal(ntf_ctx* ctx, void* stream, uint64_t seed, uint64_t step, uint32_t stream_id, size_t n, float* out) {
   NTF_REQUIRE(ctx && out, NTF_ERR_BAD_ARG, "fill_normal: null pointer");
   if (!n) return NTF_OK;
-  fill_normal_kernel<<<grid_for(ctx, (n + 3) / 4), 256, 0, as_stream(stream)>>>(seed, step, stream_id, n, out);
+  NTF_COUNT_LAUNCH; fill_normal_kernel<<<grid_for(ctx, (n + 3) / 4), 256, 0, as_stream(stream)>>>(seed, step, stream_id, n, out);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
@@ -108,7 +108,7 @@ extern "C" int ntf_fill_sign_bits(ntf_ctx* ctx, void* stream, uint64_t seed, uin
                                   uint32_t* bits) {
   NTF_REQUIRE(ctx && bits, NTF_ERR_BAD_ARG, "fill_sign_bits: null pointer");
   if (!n_words) return NTF_OK;
-  fill_sign_bits_kernel<<<grid_for(ctx, (n_words + 3) / 4), 256, 0, as_stream(stream)>>>(seed, step, stream_id, n_words, bits);
+  NTF_COUNT_LAUNCH; fill_sign_bits_kernel<<<grid_for(ctx, (n_words + 3) / 4), 256, 0, as_stream(stream)>>>(seed, step, stream_id, n_words, bits);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
@@ -116,7 +116,7 @@ extern "C" int ntf_fill_sign_bits(ntf_ctx* ctx, void* stream, uint64_t seed, uin
 extern "C" int ntf_apply_sign(ntf_ctx* ctx, void* stream, const float* A, const uint32_t* bits, int pitch_words, int B, int h, float* As) {
   NTF_REQUIRE(ctx && A && bits && As, NTF_ERR_BAD_ARG, "apply_sign: null pointer");
   NTF_REQUIRE(B > 0 && h > 0 && pitch_words * 32 >= h, NTF_ERR_BAD_ARG, "apply_sign: B=%d h=%d pitch=%d", B, h, pitch_words);
-  apply_sign_kernel<<<(unsigned)(((size_t)B * h + 255) / 256), 256, 0, as_stream(stream)>>>(A, bits, pitch_words, B, h, As);
+  NTF_COUNT_LAUNCH; apply_sign_kernel<<<(unsigned)(((size_t)B * h + 255) / 256), 256, 0, as_stream(stream)>>>(A, bits, pitch_words, B, h, As);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
@@ -129,8 +129,8 @@ extern "C" int ntf_flipout_prepare(ntf_ctx* ctx, void* stream, const float* mu, 
   NTF_REQUIRE(workspace_bytes >= ntf_flipout_prepare_workspace_bytes(ctx), NTF_ERR_WORKSPACE, "flipout_prepare: workspace too small");
   if (!n) return NTF_OK;
   const int blocks = grid_for(ctx, n);
-  flipout_prepare_kernel<<<blocks, 256, 0, as_stream(stream)>>>(mu, rho, eps, n, delta, (float*)workspace);
-  kl_finish_kernel<<<1, 256, 0, as_stream(stream)>>>((const float*)workspace, blocks, kl_scale, kl_out);
+  NTF_COUNT_LAUNCH; flipout_prepare_kernel<<<blocks, 256, 0, as_stream(stream)>>>(mu, rho, eps, n, delta, (float*)workspace);
+  NTF_COUNT_LAUNCH; kl_finish_kernel<<<1, 256, 0, as_stream(stream)>>>((const float*)workspace, blocks, kl_scale, kl_out);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
@@ -139,7 +139,7 @@ extern "C" int ntf_flipout_grads(ntf_ctx* ctx, void* stream, const float* mu, co
                                  const float* g_delta, size_t n, float kl_gscale, float* g_mu, float* g_rho) {
   NTF_REQUIRE(ctx && mu && rho && eps && g_delta && g_mu && g_rho, NTF_ERR_BAD_ARG, "flipout_grads: null pointer");
   if (!n) return NTF_OK;
-  flipout_grads_kernel<<<grid_for(ctx, n), 256, 0, as_stream(stream)>>>(mu, rho, eps, g_delta, n, kl_gscale, g_mu, g_rho);
+  NTF_COUNT_LAUNCH; flipout_grads_kernel<<<grid_for(ctx, n), 256, 0, as_stream(stream)>>>(mu, rho, eps, g_delta, n, kl_gscale, g_mu, g_rho);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

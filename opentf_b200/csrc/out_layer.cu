@@ -12,6 +12,8 @@ int ntf_out_train_tc(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a,
 int ntf_out_tc_supported(int B, int h, int E, int flipout);
 int ntf_infer_scores_tc(ntf_ctx* ctx, cudaStream_t st, const float* A, const float* W, const float* b, int B, int h, int E, float* P);
 
+extern "C" int ntf_tc_supported(int B, int h, int E, int flipout) { return ntf_out_tc_supported(B, h, E, flipout); }
+
 extern "C" size_t ntf_out_train_workspace_bytes(const ntf_ctx* ctx, int precision, int B, int h, int E, int flipout) {
   if (precision == NTF_TF32) return ntf_out_train_tc_workspace_bytes(ctx, B, h, E, flipout);
   return ntf_out_train_fp32_workspace_bytes(B, h, E, flipout);
@@ -73,7 +75,7 @@ extern "C" int ntf_axpy(ntf_ctx* ctx, void* stream, size_t n, float a, const flo
   NTF_REQUIRE(ctx && x && y, NTF_ERR_BAD_ARG, "axpy: null pointer");
   if (!n) return NTF_OK;
   size_t b = (n + 255) / 256, cap = (size_t)ctx->sm_count * 16;
-  axpy_kernel<<<(unsigned)(b < cap ? b : cap), 256, 0, as_stream(stream)>>>(n, a, x, y);
+  NTF_COUNT_LAUNCH; axpy_kernel<<<(unsigned)(b < cap ? b : cap), 256, 0, as_stream(stream)>>>(n, a, x, y);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

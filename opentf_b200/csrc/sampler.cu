@@ -108,7 +108,7 @@ extern "C" int ntf_expert_cdf(ntf_ctx* ctx, void* stream, int B, const int32_t* 
   NTF_REQUIRE(B > 0 && E > 0, NTF_ERR_BAD_ARG, "expert_cdf: B=%d E=%d", B, E);
   cudaStream_t st = as_stream(stream);
   NTF_CUDA(cudaMemsetAsync(counts, 0, (size_t)E * sizeof(uint32_t), st));
-  count_members_kernel<<<min(cdiv(B * 4, 256), ctx->sm_count * 8), 256, 0, st>>>(B, m_indptr, m_indices, counts);
+  NTF_COUNT_LAUNCH; count_members_kernel<<<min(cdiv(B * 4, 256), ctx->sm_count * 8), 256, 0, st>>>(B, m_indptr, m_indices, counts);
   NTF_LAUNCH_CHECK();
   return ntf_scan_u32_impl(st, counts, (size_t)E, cdf, 1, nullptr, workspace, workspace_bytes);
 }
@@ -120,7 +120,7 @@ extern "C" int ntf_neg_sample(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed
   NTF_REQUIRE(nsd >= NTF_NS_UNIFORM && nsd <= NTF_NS_UNIGRAM_B, NTF_ERR_BAD_ARG, "neg_sample: nsd=%d", nsd);
   NTF_REQUIRE(nsd == NTF_NS_UNIFORM || cdf, NTF_ERR_BAD_ARG, "neg_sample: unigram modes need a cdf");
   NTF_REQUIRE(B > 0 && E > 0 && ns > 0 && ns <= NS_MAX, NTF_ERR_UNSUPPORTED, "neg_sample: B=%d E=%d ns=%d (ns<=%d)", B, E, ns, NS_MAX);
-  neg_sample_kernel<<<cdiv(B, 128), 128, 0, as_stream(stream)>>>(nsd, seed, step, row0, B, m_indptr, m_indices, E, ns, cdf, neg);
+  NTF_COUNT_LAUNCH; neg_sample_kernel<<<cdiv(B, 128), 128, 0, as_stream(stream)>>>(nsd, seed, step, row0, B, m_indptr, m_indices, E, ns, cdf, neg);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
@@ -129,7 +129,7 @@ extern "C" int ntf_special_bits(ntf_ctx* ctx, void* stream, int op, int B, const
                                 const int32_t* neg, int ns, int E, uint32_t* special, int pitch_words) {
   NTF_REQUIRE(ctx && m_indptr && m_indices && special, NTF_ERR_BAD_ARG, "special_bits: null pointer");
   NTF_REQUIRE(B > 0 && E > 0 && pitch_words * 32 >= E, NTF_ERR_BAD_ARG, "special_bits: B=%d E=%d pitch=%d", B, E, pitch_words);
-  special_bits_kernel<<<cdiv(B, 128), 128, 0, as_stream(stream)>>>(op, B, m_indptr, m_indices, neg, ns, E, special, pitch_words);
+  NTF_COUNT_LAUNCH; special_bits_kernel<<<cdiv(B, 128), 128, 0, as_stream(stream)>>>(op, B, m_indptr, m_indices, neg, ns, E, special, pitch_words);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

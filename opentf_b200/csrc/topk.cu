@@ -165,7 +165,7 @@ extern "C" int ntf_topk_select(ntf_ctx* ctx, void* stream, const float* P, int B
   NTF_REQUIRE(K <= TK_KMAX, NTF_ERR_UNSUPPORTED, "topk_select: K=%d > %d", K, TK_KMAX);
   NTF_REQUIRE(scale > 0.f, NTF_ERR_BAD_ARG, "topk_select: scale must be positive");
   const int Kpad = next_pow2(K);
-  topk_select_kernel<<<B, TK_THREADS, (size_t)Kpad * 8, as_stream(stream)>>>(P, E, K, Kpad, scale, vals, idx);
+  NTF_COUNT_LAUNCH; topk_select_kernel<<<B, TK_THREADS, (size_t)Kpad * 8, as_stream(stream)>>>(P, E, K, Kpad, scale, vals, idx);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
@@ -178,7 +178,7 @@ extern "C" int ntf_topk_merge(ntf_ctx* ctx, void* stream, const float* vals_in, 
   NTF_REQUIRE(npad <= 16384, NTF_ERR_UNSUPPORTED, "topk_merge: G*K=%d > 16384", G * K);
   const size_t smem = (size_t)npad * 8;
   NTF_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  topk_merge_kernel<<<B, TK_THREADS, smem, as_stream(stream)>>>(vals_in, idx_in, G, B, K, npad, vals, idx);
+  NTF_COUNT_LAUNCH; topk_merge_kernel<<<B, TK_THREADS, smem, as_stream(stream)>>>(vals_in, idx_in, G, B, K, npad, vals, idx);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
@@ -186,7 +186,7 @@ extern "C" int ntf_topk_merge(ntf_ctx* ctx, void* stream, const float* vals_in, 
 extern "C" int ntf_row_entropy(ntf_ctx* ctx, void* stream, const float* P, int B, int E, float scale, int accumulate, float* out) {
   NTF_REQUIRE(ctx && P && out, NTF_ERR_BAD_ARG, "row_entropy: null pointer");
   NTF_REQUIRE(B > 0 && E > 0, NTF_ERR_BAD_ARG, "row_entropy: B=%d E=%d", B, E);
-  row_entropy_kernel<<<B, 256, 0, as_stream(stream)>>>(P, E, scale, accumulate, out);
+  NTF_COUNT_LAUNCH; row_entropy_kernel<<<B, 256, 0, as_stream(stream)>>>(P, E, scale, accumulate, out);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

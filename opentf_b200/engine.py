@@ -80,6 +80,17 @@ class SplitData:
         ops.csr_gather(self.rows_dev, self.n, e.member.indptr, e.member.indices, self.m_indptr, self.m_indices, None, e.ws)
 
 
+class _HostStage:
+    """device landing buffers of one host batch (same attributes `Engine.step` reads from a SplitData)"""
+
+    def __init__(self, device, n, nnz_s, nnz_m):
+        i32 = torch.int32
+        self.cap, self.n = (n, nnz_s, nnz_m), 0
+        self.s_indptr = torch.zeros(n + 1, dtype=i32, device=device); self.m_indptr = torch.zeros(n + 1, dtype=i32, device=device)
+        self.s_indices = torch.zeros(nnz_s, dtype=i32, device=device); self.s_ent_row = torch.zeros(nnz_s, dtype=i32, device=device)
+        self.m_indices = torch.zeros(nnz_m, dtype=i32, device=device)
+
+
 class Engine:
     def __init__(self, S, hidden, E, device, bayesian=False, precision='tf32', tpw=10.0, tnw=1.0, nsd='uniform', ns=5,
                  seed=0, max_batch=1000):
@@ -90,6 +101,10 @@ class Engine:
         _lib.ctx(self.dev_index)  # fails loudly if this is not a B200-class device
         self.S, self.hidden, self.E = int(S), [int(x) for x in hidden], int(E)
         self.bayesian, self.precision = bool(bayesian), PRECISION[precision]
+        # 'tf32' selects the tcgen05 kernels where they exist for the shape; other shapes (toy sizes, odd widths) run the
+        # CUDA-core fp32 kernels of the same library -- both are sm_100a code, neither is a fallback to another backend.
+        if self.precision == _lib.NTF_TF32 and not _lib.lib().ntf_tc_supported(int(max_batch), int(hidden[-1]), int(E), int(bool(bayesian))):
+            self.precision = _lib.NTF_FP32
         self.tpw, self.tnw, self.nsd, self.ns, self.seed = float(tpw), float(tnw), NSD[nsd], int(ns), int(seed)
         self.Bmax = int(max_batch)
         self.sizes = [self.S] + self.hidden + [self.E]
@@ -265,6 +280,25 @@ class Engine:
 
     def _step_bayes(self, sp, b0, B, train, lr, loss_slot, neg_host, loss_scale, gbatch):
         raise NotImplementedError('Bnn engine lands in bnn_engine.py')
+
+    # ------------------------------------------------------------------ streaming entry point (host batches)
+    def step_host(self, s_ptr, s_idx, s_row, m_ptr, m_idx, rank=0, G=1, lr=1e-3, train=True):
+        """one step on a batch the HOST holds: compact CSR of the global batch (pinned int32 tensors: skill indptr / indices /
+        entry->row, member indptr / indices) is copied to the device, this rank trains on its slice, and the loss comes
+        back to the host (one sync) -- the per-step shape of the reference's loop (fnn.py:118-140: H2D of the batch, .item())."""
+        n, nnz_s, nnz_m = s_ptr.numel() - 1, s_idx.numel(), m_idx.numel()
+        st = getattr(self, '_hstage', None)
+        if st is None or st.cap[0] < n or st.cap[1] < nnz_s or st.cap[2] < nnz_m:
+            st = _HostStage(self.device, max(n, self.Bmax), 2 * nnz_s + 64, 2 * nnz_m + 64)
+            self._hstage = st
+        st.n = n
+        st.s_indptr[:n + 1].copy_(s_ptr, non_blocking=True); st.s_indices[:nnz_s].copy_(s_idx, non_blocking=True)
+        st.s_ent_row[:nnz_s].copy_(s_row, non_blocking=True)
+        st.m_indptr[:n + 1].copy_(m_ptr, non_blocking=True); st.m_indices[:nnz_m].copy_(m_idx, non_blocking=True)
+        b = -(-n // G)
+        lo, hi = min(n, rank * b), min(n, (rank + 1) * b)
+        self.step(st, lo, hi - lo, train, lr=lr, loss_slot=0, loss_scale=1.0 / n, gbatch=(0, n))
+        return float(self.loss_buf[0].item())
 
     # ------------------------------------------------------------------ inference
     def scores(self, sp, b0, B, out):

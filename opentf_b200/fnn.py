@@ -75,7 +75,10 @@ class Fnn(Ntf):
     def __init__(self, output, device, seed, cfg):
         super().__init__(output, device, seed, cfg)
         self.engine = None
-        self.neg_provider = None  # tests: callable(phase, team_rows ndarray) -> [B,ns] int array of host-supplied negatives
+        # parity tests replay a recorded reference run through this class: an object with
+        #   init(fold) -> state dict | None, order(fold, epoch, phase, n) -> positions | None, neg(fold, epoch, phase, batch, team_rows) -> [B,ns] | None
+        # replaces the host RNG draws (initial weights, shuffles) and supplies the negatives (SURVEY.md 9.3 "host-supplied indices").
+        self.replay = None
         self.last_history = {}
 
     # ---- helpers --------------------------------------------------------------------------------------------
@@ -149,6 +152,7 @@ class Fnn(Ntf):
                 if nsd == 'unigram': eng.set_global_unigram()  # fnn.py:82
                 first = False
             if prev_model: self.model.load_state_dict(self._load_ckpt(prev_model[foldidx]))  # fnn.py:101
+            if self.replay is not None and self.replay.init(foldidx) is not None: self.model.load_state_dict(self.replay.init(foldidx))
             train_sp = eng.split(splits['folds'][foldidx]['train'])
             valid_sp = eng.split(splits['folds'][foldidx]['valid'])
             nb_t, nb_v = -(-train_sp.n // b), -(-valid_sp.n // b)
@@ -161,13 +165,16 @@ class Fnn(Ntf):
                 eng.loss_buf.zero_()
                 for phase, sp, nb, slot0 in (('train', train_sp, nb_t, 0), ('valid', valid_sp, nb_v, nb_t)):
                     order = loader_order(torch, sp.n, phase == 'train')
+                    if self.replay is not None: order = self.replay.order(foldidx, e, phase, sp.n)
                     if order is not None: sp.regather(order)
                     for bi in range(nb):
                         b0, B = bi * b, min(b, sp.n - bi * b)
                         lo, hi = self._rank_slice(B)
                         if hi <= lo: continue
                         neg = None
-                        if self.neg_provider is not None: neg = np.asarray(self.neg_provider(phase, sp.rows_now[b0:b0 + B]))[lo:hi]
+                        if self.replay is not None:
+                            neg = self.replay.neg(foldidx, e, phase, bi, sp.rows_now[b0:b0 + B])
+                            if neg is not None: neg = np.asarray(neg)[lo:hi]
                         eng.step(sp, b0 + lo, hi - lo, phase == 'train', lr=lr, loss_slot=slot0 + bi, neg_host=neg, loss_scale=1.0 / B, gbatch=(b0, B))
                 losses = eng.loss_buf[:nb_t + nb_v]
                 if eng.world > 1: torch.distributed.all_reduce(losses)
