@@ -71,10 +71,13 @@ int ntf_csr_bag_fwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, co
                     const float* W0T, const float* b0, int S, int h, float* A);
 /* replaces autograd's addmm backward for layer 0 (fnn.py:137):
  *   dW0T[s,:] = sum_{n: s in skills(n)} dZ[n,:]  for EVERY s in [0,S) (zeros for skills absent from the batch).
- * Atomic-free and run-to-run deterministic (a skill row is owned by one warp, summed in entry order).
+ * No floating-point atomics, run-to-run deterministic: a skill row is owned by one warp (or, for the few skills that sit
+ * in most teams, by one CTA with a fixed-order combine) and summed in entry order.
  * ent_row[p] - row_base = batch row of CSR entry p (from ntf_csr_gather). */
+size_t ntf_csr_bag_bwd_workspace_bytes(int S);
 int ntf_csr_bag_bwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
-                    const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T);
+                    const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T,
+                    void* workspace, size_t workspace_bytes);
 
 /* ---- hidden layers / dense (embedded) skill input: fnn.py:25 layers i>=1, ntf.py:24 ----------------------------
  * Y = act(A W^T + b), A [B,in], W [out,in] (torch layout); act 0 = identity, 1 = leaky_relu, 2 = sigmoid(leaky_relu). */

@@ -229,21 +229,38 @@ extern "C" int ntf_csr_bag_fwd(ntf_ctx* ctx, void* stream, int B, const int32_t*
 }
 
 // =========================================================================================================
-// K2: embedding-bag backward, atomic-free.  The skill axis is cut into chunks of SKW skills; a warp owns one
-// chunk, keeps SKW x h accumulators in shared memory, streams over the batch's flat (skill id, team) entry
-// list with coalesced loads, and adds dZ[team,:] for the entries that fall in its chunk -- in entry order, so
-// the sum order depends on the data only (run-to-run deterministic).  Every dW0T row is written exactly once
-// (zeros for skills absent from the batch: Adam is dense, SURVEY.md "Hard parts").
-// Algorithmic bytes per team: n_s*(4h+4) + 4h read, 4h*S/B written.
+// K2: embedding-bag backward, atomic-free and run-to-run deterministic.
+//   dW0T[s,:] = sum over the batch entries (s, n) of dZ[n,:], written exactly once for EVERY s (zeros for skills
+//   absent from the batch: Adam is dense, SURVEY.md "Hard parts").
+// Skill popularity is heavy-tailed (a few skills sit in most teams), so the work is split by a per-batch histogram:
+//   cold skills (<= HOT entries): the skill axis is cut into chunks of SKW skills, a warp owns a chunk, keeps SKW x h
+//     accumulators in shared memory and streams over the batch's flat entry list with coalesced loads, adding dZ rows
+//     for the entries that fall in its chunk, 4 rows in flight at a time, in entry order;
+//   hot skills (> HOT entries): one CTA per skill compacts that skill's entries in entry order, its 8 warps sum
+//     fixed slices of the list and the 8 partials are combined in a fixed order.
+// The summation order depends on the data only.  Algorithmic bytes per team: n_s*(4h+4) + 4h read, 4h*S/B written.
 // =========================================================================================================
 namespace {
 constexpr int BWD_WARPS = 8;
+constexpr int HOT = 48;
+constexpr int HCAP = 4096;
 
-__global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_kernel(int B, const int32_t* __restrict__ indptr,
-                                                                      const int32_t* __restrict__ indices,
-                                                                      const int32_t* __restrict__ ent_row, int row_base,
-                                                                      const float* __restrict__ dZ, int S, int h, int skw,
-                                                                      float* __restrict__ dW0T) {
+__global__ void skill_count_kernel(int B, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                   uint32_t* __restrict__ cnt) {
+  const int p0 = indptr[0], p1 = indptr[B];
+  for (int p = p0 + blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += gridDim.x * blockDim.x) atomicAdd(cnt + indices[p], 1u);
+}
+
+__global__ void hot_list_kernel(int S, const uint32_t* __restrict__ cnt, int32_t* __restrict__ hot, uint32_t* __restrict__ nhot) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < S && cnt[s] > HOT) hot[atomicAdd(nhot, 1u)] = s;  // list order is irrelevant: every hot skill is reduced on its own
+}
+
+__global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_cold_kernel(int B, const int32_t* __restrict__ indptr,
+                                                                           const int32_t* __restrict__ indices,
+                                                                           const int32_t* __restrict__ ent_row, int row_base,
+                                                                           const float* __restrict__ dZ, int S, int h, int skw,
+                                                                           const uint32_t* __restrict__ cnt, float* __restrict__ dW0T) {
   extern __shared__ float acc_all[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* acc = acc_all + (size_t)w * skw * h;
@@ -258,40 +275,127 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_kernel(int B, cons
       int s = -1, n = 0;
       if (p < p_end) {
         s = __ldg(indices + p);
-        if (s >= s0 && s < s1) n = __ldg(ent_row + p) - row_base; else s = -1;
+        if (s >= s0 && s < s1 && __ldg(cnt + s) <= HOT) n = __ldg(ent_row + p) - row_base; else s = -1;
       }
       unsigned hits = __ballot_sync(0xffffffffu, s >= 0);
       while (hits) {
-        const int L = __ffs(hits) - 1;
-        hits &= hits - 1;
-        const int sl = __shfl_sync(0xffffffffu, s, L) - s0;
-        const int nn = __shfl_sync(0xffffffffu, n, L);
-        const float* src = dZ + (size_t)nn * h;
-        float* dst = acc + (size_t)sl * h;
-        for (int c = lane; c < h; c += 32) dst[c] += __ldg(src + c);
+        int sl[4], nn[4], g = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (hits) {
+            const int L = __ffs(hits) - 1;
+            hits &= hits - 1;
+            sl[q] = __shfl_sync(0xffffffffu, s, L) - s0;
+            nn[q] = __shfl_sync(0xffffffffu, n, L);
+            g = q + 1;
+          } else { sl[q] = 0; nn[q] = 0; }
+        }
+        for (int c = lane; c < h; c += 32) {
+          float v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = q < g ? __ldg(dZ + (size_t)nn[q] * h + c) : 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (q < g) acc[(size_t)sl[q] * h + c] += v[q];  // in entry order
+        }
       }
     }
     __syncwarp();
-    for (int k = lane; k < (s1 - s0) * h; k += 32) dW0T[(size_t)s0 * h + k] = acc[k];
+    for (int k = lane; k < (s1 - s0) * h; k += 32)
+      if (__ldg(cnt + s0 + k / h) <= HOT) dW0T[(size_t)s0 * h + k] = acc[k];
     __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_hot_kernel(int B, const int32_t* __restrict__ indptr,
+                                                                          const int32_t* __restrict__ indices,
+                                                                          const int32_t* __restrict__ ent_row, int row_base,
+                                                                          const float* __restrict__ dZ, int h,
+                                                                          const int32_t* __restrict__ hot,
+                                                                          const uint32_t* __restrict__ nhot_p, float* __restrict__ dW0T) {
+  extern __shared__ float sm[];
+  float* total = sm;                        // [h]
+  float* partial = sm + h;                  // [BWD_WARPS][h]
+  int* hits = (int*)(sm + (size_t)(1 + BWD_WARPS) * h);  // [HCAP]
+  __shared__ uint32_t warp_cnt[BWD_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int p_beg = indptr[0], p_end = indptr[B];
+  const int nhot = (int)*nhot_p;
+  for (int hi = blockIdx.x; hi < nhot; hi += gridDim.x) {
+    const int s = hot[hi];
+    for (int c = tid; c < h; c += blockDim.x) total[c] = 0.f;
+    int filled = 0;
+    __syncthreads();
+    for (int base = p_beg; base < p_end; base += BWD_WARPS * 32) {
+      const int p = base + tid;
+      const bool flag = p < p_end && __ldg(indices + p) == s;
+      const unsigned bal = __ballot_sync(0xffffffffu, flag);
+      if (lane == 0) warp_cnt[w] = __popc(bal);
+      __syncthreads();
+      int off = 0, tot = 0;
+#pragma unroll
+      for (int q = 0; q < BWD_WARPS; ++q) { if (q < w) off += warp_cnt[q]; tot += warp_cnt[q]; }
+      if (flag) hits[filled + off + __popc(bal & ((1u << lane) - 1u))] = __ldg(ent_row + p) - row_base;
+      filled += tot;
+      __syncthreads();
+      const bool last = base + BWD_WARPS * 32 >= p_end;
+      if (filled > HCAP - BWD_WARPS * 32 || last) {  // reduce this segment of the entry list
+        const int per = (filled + BWD_WARPS - 1) / BWD_WARPS;
+        const int i0 = min(filled, w * per), i1 = min(filled, (w + 1) * per);
+        for (int c = lane; c < h; c += 32) {
+          float a = 0.f;
+          int i = i0;
+          for (; i + 4 <= i1; i += 4) {
+            const float v0 = __ldg(dZ + (size_t)hits[i] * h + c), v1 = __ldg(dZ + (size_t)hits[i + 1] * h + c);
+            const float v2 = __ldg(dZ + (size_t)hits[i + 2] * h + c), v3 = __ldg(dZ + (size_t)hits[i + 3] * h + c);
+            a += v0; a += v1; a += v2; a += v3;
+          }
+          for (; i < i1; ++i) a += __ldg(dZ + (size_t)hits[i] * h + c);
+          partial[(size_t)w * h + c] = a;
+        }
+        __syncthreads();
+        for (int c = tid; c < h; c += blockDim.x) {
+          float t = total[c];
+#pragma unroll
+          for (int q = 0; q < BWD_WARPS; ++q) t += partial[(size_t)q * h + c];
+          total[c] = t;
+        }
+        filled = 0;
+        __syncthreads();
+      }
+    }
+    for (int c = tid; c < h; c += blockDim.x) dW0T[(size_t)s * h + c] = total[c];
+    __syncthreads();
   }
 }
 }  // namespace
 
+extern "C" size_t ntf_csr_bag_bwd_workspace_bytes(int S) { return align_up((size_t)(2 * S + 64) * sizeof(uint32_t), 256); }
+
 extern "C" int ntf_csr_bag_bwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
-                               const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T) {
-  NTF_REQUIRE(ctx && indptr && indices && ent_row && dZ && dW0T, NTF_ERR_BAD_ARG, "csr_bag_bwd: null pointer");
+                               const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T,
+                               void* workspace, size_t workspace_bytes) {
+  NTF_REQUIRE(ctx && indptr && indices && ent_row && dZ && dW0T && workspace, NTF_ERR_BAD_ARG, "csr_bag_bwd: null pointer");
   NTF_REQUIRE(B > 0 && S > 0 && h > 0, NTF_ERR_BAD_ARG, "csr_bag_bwd: B=%d S=%d h=%d", B, S, h);
   NTF_REQUIRE(h <= 2048, NTF_ERR_UNSUPPORTED, "csr_bag_bwd: first hidden width %d > 2048", h);
+  NTF_REQUIRE(workspace_bytes >= ntf_csr_bag_bwd_workspace_bytes(S), NTF_ERR_WORKSPACE, "csr_bag_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  uint32_t* cnt = (uint32_t*)workspace;         // [S]
+  uint32_t* nhot = cnt + S;                      // [1] (padded to 64)
+  int32_t* hot = (int32_t*)(cnt + S + 64);       // [S]
+  NTF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(S + 64) * sizeof(uint32_t), st));
+  NTF_COUNT_LAUNCH; skill_count_kernel<<<min(cdiv(B * 8, 256), ctx->sm_count * 8), 256, 0, st>>>(B, indptr, indices, cnt);
+  NTF_COUNT_LAUNCH; hot_list_kernel<<<cdiv(S, 256), 256, 0, st>>>(S, cnt, hot, nhot);
   int skw = 2048 / h;  // 8 KB of accumulators per warp
   if (skw < 1) skw = 1;
   if (skw > 32) skw = 32;
   const size_t smem = (size_t)BWD_WARPS * skw * h * sizeof(float);
-  NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_cold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nchunks = cdiv(S, skw);
   const int blocks = min(cdiv(nchunks, BWD_WARPS), ctx->sm_count * 3);
-  NTF_COUNT_LAUNCH; csr_bag_bwd_kernel<<<blocks, BWD_WARPS * 32, smem, as_stream(stream)>>>(B, indptr, indices, ent_row, row_base, dZ, S, h,
-                                                                         skw, dW0T);
+  NTF_COUNT_LAUNCH; csr_bag_bwd_cold_kernel<<<blocks, BWD_WARPS * 32, smem, st>>>(B, indptr, indices, ent_row, row_base, dZ, S, h, skw, cnt, dW0T);
+  const size_t smem_hot = (size_t)(1 + BWD_WARPS) * h * sizeof(float) + (size_t)HCAP * sizeof(int);
+  NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_hot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hot));
+  NTF_COUNT_LAUNCH; csr_bag_bwd_hot_kernel<<<ctx->sm_count * 2, BWD_WARPS * 32, smem_hot, st>>>(B, indptr, indices, ent_row, row_base, dZ, h, hot, nhot, dW0T);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

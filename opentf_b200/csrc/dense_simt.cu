@@ -175,8 +175,8 @@ __global__ void sum_parts_kernel(const float* __restrict__ parts, int nparts, si
   out[i] = s;
 }
 
-// single-block fixed-order reduction of per-CTA loss partials (double accumulator), loss_out[0] (+)= result
-__global__ void loss_reduce_kernel(const float* __restrict__ part, int n, float* __restrict__ loss_out) {
+// single-block fixed-order reduction of per-CTA loss partials (double accumulator): loss_out[0] = scale * sum
+__global__ void loss_reduce_kernel(const float* __restrict__ part, int n, float scale, float* __restrict__ loss_out) {
   __shared__ double red[256];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) s += (double)part[i];
@@ -186,7 +186,7 @@ __global__ void loss_reduce_kernel(const float* __restrict__ part, int n, float*
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) loss_out[0] = (float)red[0];
+  if (threadIdx.x == 0) loss_out[0] = (float)(red[0] * (double)scale);
 }
 
 // column sums of a [R,C] matrix in two fixed-order passes
@@ -206,8 +206,8 @@ int ntf_sum_parts_impl(cudaStream_t st, const float* parts, int nparts, size_t n
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
-int ntf_loss_reduce_impl(cudaStream_t st, const float* part, int n, float* loss_out) {
-  NTF_COUNT_LAUNCH; loss_reduce_kernel<<<1, 256, 0, st>>>(part, n, loss_out);
+int ntf_loss_reduce_impl(cudaStream_t st, const float* part, int n, float scale, float* loss_out) {
+  NTF_COUNT_LAUNCH; loss_reduce_kernel<<<1, 256, 0, st>>>(part, n, scale, loss_out);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
@@ -317,7 +317,7 @@ int ntf_out_train_fp32(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* 
     EpiLoss e{a->b, flip ? w.T : nullptr, E, a->special, a->pitch_words, a->m_indptr, a->m_indices, a->tpw, a->tnw,
               a->loss_scale, train ? w.dz : nullptr, a->sign_out, (train && flip) ? w.dzs : nullptr, w.loss_part, 0.f};
     if ((rc = launch_gemm(st, g, e))) return rc;
-    if ((rc = ntf_loss_reduce_impl(st, w.loss_part, cdiv(B, BM) * cdiv(E, BN), a->loss_out))) return rc;
+    if ((rc = ntf_loss_reduce_impl(st, w.loss_part, cdiv(B, BM) * cdiv(E, BN), a->loss_scale, a->loss_out))) return rc;
   }
   if (!train) return NTF_OK;
   auto grads = [&](const float* dz, const float* Ain, const float* Wmat, float* dW, float* db, float* dA) -> int {

@@ -269,7 +269,7 @@ class Engine:
                           self.view(f'layers.{i}.weight', self.grads), self.dact[i - 1], self.ws)
         ops.act_bwd(self.dact[0], self.act[0], B, self.hidden[0], 1, self.dz[0], self.view('layers.0.bias', self.grads), self.ws)
         ops.csr_bag_bwd(B, sp.s_indptr.data_ptr() + 4 * b0, sp.s_indices, sp.s_ent_row, b0, self.dz[0], self.S, self.hidden[0],
-                        self.view('layers.0.weight', self.grads))
+                        self.view('layers.0.weight', self.grads), self.ws)
         self.optimizer_step(lr)
 
     def optimizer_step(self, lr):

@@ -55,10 +55,11 @@ def csr_bag_fwd(B, indptr_ptr, indices, W0T, b0, S, h, A):
           'ntf_csr_bag_fwd')
 
 
-def csr_bag_bwd(B, indptr_ptr, indices, ent_row, row_base, dZ, S, h, dW0T):
+def csr_bag_bwd(B, indptr_ptr, indices, ent_row, row_base, dZ, S, h, dW0T, ws):
     d = _dev(dZ)
+    p, nb = ws.get(lib().ntf_csr_bag_bwd_workspace_bytes(S))
     check(lib().ntf_csr_bag_bwd(_lib.ctx(d), _stream(d), B, indptr_ptr, _p(indices, I32), _p(ent_row, I32), row_base, _p(dZ, F32), S, h,
-                                _p(dW0T, F32)), 'ntf_csr_bag_bwd')
+                                _p(dW0T, F32), p, nb), 'ntf_csr_bag_bwd')
 
 
 def dense_fwd(A, W, b, B, inn, out, act, Y):

@@ -80,10 +80,14 @@ def test_csr_bag_fwd_matches_dense_first_layer(ops, B, S, h):
     assert rel_err(A.cpu(), ref) < 2e-6
 
 
-@pytest.mark.parametrize('B,S,h', [(1, 7, 128), (33, 50, 128), (300, 1000, 20), (513, 97, 128)])
-def test_csr_bag_bwd_matches_dense_gradient_and_is_deterministic(ops, B, S, h):
+@pytest.mark.parametrize('B,S,h', [(1, 7, 128), (33, 50, 128), (300, 1000, 20), (513, 97, 128), (6000, 200, 128)])
+def test_csr_bag_bwd_matches_dense_gradient_and_is_deterministic(ops, ws, B, S, h):
     rng = np.random.default_rng(B * 7 + h)
-    X = rand_csr(rng, B, S, 1, 9)
+    X = rand_csr(rng, B, S, 1, 9).tolil()
+    if B > 100:  # heavy-tailed popularity: skill 3 sits in ~80% of the teams, skill 5 in ~30% (the per-CTA "hot" path)
+        X[np.nonzero(rng.random(B) < 0.8)[0], 3] = 1
+        X[np.nonzero(rng.random(B) < 0.3)[0], 5] = 1
+    X = X.tocsr(); X.sort_indices()
     torch.manual_seed(B)
     dZ = torch.randn(B, h)
     ref = (dZ.t() @ dense(X)).t()  # dW[h,S] = dZ^T X, stored transposed [S,h]
@@ -92,7 +96,7 @@ def test_csr_bag_bwd_matches_dense_gradient_and_is_deterministic(ops, B, S, h):
     outs = []
     for _ in range(2):
         dW = torch.full((S, h), float('nan'), device=DEV)
-        ops.csr_bag_bwd(B, indptr.data_ptr(), indices, ent_row, 0, dZ.to(DEV), S, h, dW)
+        ops.csr_bag_bwd(B, indptr.data_ptr(), indices, ent_row, 0, dZ.to(DEV), S, h, dW, ws)
         outs.append(dW.cpu())
     assert torch.equal(outs[0], outs[1])  # run-to-run bit-stable (no atomics)
     assert rel_err(outs[0], ref) < 2e-6
@@ -100,7 +104,7 @@ def test_csr_bag_bwd_matches_dense_gradient_and_is_deterministic(ops, B, S, h):
     assert (outs[0].numpy()[untouched] == 0).all()  # every row is written, zeros where the batch has no such skill
 
 
-def test_csr_bag_on_a_batch_slice_of_a_larger_split(ops):
+def test_csr_bag_on_a_batch_slice_of_a_larger_split(ops, ws):
     """kernels address a batch by pointer offset into the split's indptr (absolute offsets)."""
     rng = np.random.default_rng(3)
     n, S, h, b0, B = 90, 40, 128, 32, 25
@@ -113,7 +117,7 @@ def test_csr_bag_on_a_batch_slice_of_a_larger_split(ops):
     ops.csr_bag_fwd(B, indptr.data_ptr() + 4 * b0, indices, W.t().contiguous().to(DEV), b.to(DEV), S, h, A)
     assert rel_err(A.cpu(), O.lrelu(dense(X[b0:b0 + B]) @ W.t() + b)) < 2e-6
     dW = torch.empty(S, h, device=DEV)
-    ops.csr_bag_bwd(B, indptr.data_ptr() + 4 * b0, indices, ent_row, b0, dZ.to(DEV), S, h, dW)
+    ops.csr_bag_bwd(B, indptr.data_ptr() + 4 * b0, indices, ent_row, b0, dZ.to(DEV), S, h, dW, ws)
     assert rel_err(dW.cpu(), (dZ.t() @ dense(X[b0:b0 + B])).t()) < 2e-6
 
 
