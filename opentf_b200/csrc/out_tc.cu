@@ -9,7 +9,7 @@
 //   It streams over the batch in tiles of 64 teams (double buffered):
 //     TMA warp      : A tile (fp32 + fp16 copy) -> smem                                     [cp.async.bulk.tensor]
 //     MMA thread    : Z^T[128e x 64n] = W . A^T          kind::tf32, fp32 accumulate in TMEM  (forward, TF32 logits)
-//     4 epilogue warps (thread = expert): TMEM -> regs, +b, lrelu, weighted BCE, dz; loss and db accumulate in
+//     8 epilogue warps (thread = expert x half of the tile's teams): TMEM -> regs, +b, lrelu, weighted BCE, dz; loss and db accumulate in
 //                     registers; dz (scaled by 1/loss_scale, fp16 = same 10-bit mantissa as tf32) -> smem
 //     MMA thread    : dW[128e x 128k] += dz^T . A        kind::f16, accumulates across all batch tiles in TMEM
 //                     dA^T[128k x 64n] = W^T . dz^T      kind::f16
@@ -147,12 +147,22 @@ struct TcArgs {
   float* loss_part;           // [gridDim.x]
   float* P;                   // inference: [B,E] probabilities
   float* Zdbg;                // debug: raw logits z [B,E] (NULL in production)
+  long long* timing;          // debug: clock64 stamps of CTA 0, [tile][8] (NULL in production)
 };
+
+constexpr int NT = 448;  // warps 0-7: logits/loss epilogue, 8-11: dA epilogue, 12: TMA producer, 13: MMA issuer
+constexpr int WARP_TMA = 12, WARP_MMA = 13;
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 // MODE 0: training / validation step.  MODE 1: inference scores P = sigmoid(lrelu(z)).
 template <int MODE>
-__global__ void __launch_bounds__(320, 1) out_tc_kernel(const __grid_constant__ CUtensorMap map_w32, const __grid_constant__ CUtensorMap map_a32,
-                                                        const __grid_constant__ CUtensorMap map_a16, TcArgs g) {
+__global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ CUtensorMap map_w32, const __grid_constant__ CUtensorMap map_a32,
+                                                       const __grid_constant__ CUtensorMap map_a16, TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));  // generic pointer to the aligned base
@@ -168,21 +178,21 @@ __global__ void __launch_bounds__(320, 1) out_tc_kernel(const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     mbar_init(bar(BAR_W), 1);
-    mbar_init(bar(BAR_W16), 256);
+    mbar_init(bar(BAR_W16), 384);
     mbar_init(bar(BAR_DW_FULL), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(BAR_A_FULL + s), 1);
       mbar_init(bar(BAR_A_EMPTY + s), 1);
       mbar_init(bar(BAR_Z_FULL + s), 1);
-      mbar_init(bar(BAR_Z_EMPTY + s), 128);
-      mbar_init(bar(BAR_DZ_FULL + s), 128);
+      mbar_init(bar(BAR_Z_EMPTY + s), 256);
+      mbar_init(bar(BAR_DZ_FULL + s), 256);
       mbar_init(bar(BAR_DZ_EMPTY + s), 1);
       mbar_init(bar(BAR_DA_FULL + s), 1);
       mbar_init(bar(BAR_DA_EMPTY + s), 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {  // TMEM allocation is owned by the MMA warp
+  if (warp == WARP_MMA) {  // TMEM allocation is owned by the MMA warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + NUM_BARS * 8), "r"(TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(320, 1) out_tc_kernel(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == WARP_TMA) {
     // =========================================== TMA producer ===========================================
     if (lane == 0) {
       mbar_expect_tx(bar(BAR_W), W32_BYTES);
@@ -200,30 +210,32 @@ __global__ void __launch_bounds__(320, 1) out_tc_kernel(const __grid_constant__ 
         const int s = t & 1;
         const uint32_t ph = (t >> 1) & 1;
         mbar_wait(bar(BAR_A_EMPTY + s), ph ^ 1);
+        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 0] = clock64();
         mbar_expect_tx(bar(BAR_A_FULL + s), train ? A32_BYTES + A16_BYTES : A32_BYTES);
         for (int c = 0; c < 4; ++c) tma_load_2d(sbase + OFF_A32 + s * A32_BYTES + c * (TB * 128), &map_a32, c * 32, t * TB, bar(BAR_A_FULL + s));
         if (train)
           for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A16 + s * A16_BYTES + c * (TB * 128), &map_a16, c * 64, t * TB, bar(BAR_A_FULL + s));
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == WARP_MMA) {
     // =========================================== MMA issuer ===========================================
     if (lane == 0) {
       auto issue_fwd = [&](int t) {
         const int s = t & 1;
         const uint32_t ph = (t >> 1) & 1;
         mbar_wait(bar(BAR_A_FULL + s), ph);
+        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 1] = clock64();
         mbar_wait(bar(BAR_Z_EMPTY + s), ph ^ 1);
+        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 2] = clock64();
         tc_fence_after();
 #pragma unroll
-        for (int i = 0; i < HK / 8; ++i) {  // 16 k-steps of 8 tf32 (32 bytes) each
-          const uint32_t koff = (i >> 2) * 128u, kin = (i & 3) * 32u;  // (chunk row pitch x rows) handled below
-          const uint64_t da = smem_desc(sbase + OFF_W32 + (i >> 2) * (TE * 128) + kin, 16, 1024);
-          const uint64_t db = smem_desc(sbase + OFF_A32 + s * A32_BYTES + (i >> 2) * (TB * 128) + kin, 16, 1024);
-          (void)koff;
+        for (int i = 0; i < HK / 8; ++i) {  // 16 k-steps of 8 tf32 (32 bytes) each: chunk i/4, 32-byte slice i%4 of the 128-byte swizzle row
+          const uint64_t da = smem_desc(sbase + OFF_W32 + (i >> 2) * (TE * 128) + (i & 3) * 32, 16, 1024);
+          const uint64_t db = smem_desc(sbase + OFF_A32 + s * A32_BYTES + (i >> 2) * (TB * 128) + (i & 3) * 32, 16, 1024);
           mma_tf32(tmem + TM_Z + s * TB, da, db, IDESC_FWD, i > 0);
         }
         tc_commit(bar(BAR_Z_FULL + s));
+        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 3] = clock64();
         if (!train) tc_commit(bar(BAR_A_EMPTY + s));  // forward-only: the A stage is free once the forward product is done
       };
       mbar_wait(bar(BAR_W), 0);
@@ -251,25 +263,27 @@ __global__ void __launch_bounds__(320, 1) out_tc_kernel(const __grid_constant__ 
           const uint64_t db = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + i * 2048, 0, 1024);                        // MN-major, N = teams
           mma_f16(tmem + TM_DA + s * TB, da, db, IDESC_DA, i > 0);
         }
+        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 7] = clock64();
         tc_commit(bar(BAR_DA_FULL + s));
         tc_commit(bar(BAR_DZ_EMPTY + s));
         tc_commit(bar(BAR_A_EMPTY + s));
         if (t == ntiles - 1) tc_commit(bar(BAR_DW_FULL));
       }
     }
-  } else if (warp < 4) {
-    // =========================================== Z epilogue: thread = expert ===========================================
-    const int jl = threadIdx.x;  // 0..127 = TMEM lane = local expert
+  } else if (warp < 8) {
+    // ====================== logits / loss epilogue: thread = (expert jl, half hh of the tile's 64 teams) ======================
+    const int jl = threadIdx.x & 127;  // TMEM lane = local expert
+    const int hh = threadIdx.x >> 7;   // teams [32*hh, 32*hh+32) of the tile
     const int e = e0 + jl;
     const bool e_ok = e < g.E;
     const float bj = e_ok ? __ldg(g.bias + e) : 0.f;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     if (train) {
       // fp16 image of the W tile for the dA product (MN-major: rows = experts, 64 hidden units per 128-byte row)
       mbar_wait(bar(BAR_W), 0);
 #pragma unroll 4
-      for (int u = 0; u < HK / 8; ++u) {  // 16 units of 8 hidden values
-        const int k = u * 8;
+      for (int uu = 0; uu < HK / 16; ++uu) {  // this half's 8 units of 8 hidden values
+        const int k = (hh * 8 + uu) * 8;
         const uint8_t* src = sgen + OFF_W32 + (k >> 5) * (TE * 128) + jl * 128;
         const int u32a = ((k & 31) >> 2), u32b = u32a + 1;
         const float4 f0 = *reinterpret_cast<const float4*>(src + ((u32a ^ (jl & 7)) << 4));
@@ -286,110 +300,132 @@ __global__ void __launch_bounds__(320, 1) out_tc_kernel(const __grid_constant__ 
     }
     if (MODE == 0) mbar_arrive(bar(BAR_W16));  // (also counted for validation steps; the MMA thread only waits when training)
     float loss_dense = 0.f, loss_sp = 0.f, db_acc = 0.f;
-    const float inv_scale_w = g.tnw;                       // dz is stored as w*(sigmoid-y)*slope  (i.e. true dz / loss_scale)
+    const float c_pos = g.tnw, c_neg = g.tnw * NTF_LRELU_SLOPE;  // dz is kept as w*(sigmoid-y)*slope, i.e. true dz / loss_scale
     for (int t = 0; t < ntiles; ++t) {
       const int s = t & 1;
       const uint32_t ph = (t >> 1) & 1;
-      const int n0 = t * TB;
-      // special-bit words of this warp's 32 experts for the tile's 64 teams: lane l holds rows n0+l and n0+32+l
-      uint32_t w_lo = 0, w_hi = 0;
+      const int n0 = t * TB + hh * 32;  // first team of this thread's half tile
+      // special bits of (32 teams x this warp's 32 experts): one coalesced word load per team, then a 32x32 bit transpose by
+      // ballots so that bit n of S = "team n0+n x my expert is a member or a sampled negative"
+      uint32_t S = 0;
       if (MODE == 0 && g.special) {
-        const int wi = (e0 >> 5) + warp;
-        if (wi < g.pitch) {
-          if (n0 + lane < g.B) w_lo = __ldg(g.special + (size_t)(n0 + lane) * g.pitch + wi);
-          if (n0 + 32 + lane < g.B) w_hi = __ldg(g.special + (size_t)(n0 + 32 + lane) * g.pitch + wi);
+        const int wi = (e0 >> 5) + (warp & 3);
+        uint32_t w = 0;
+        if (wi < g.pitch && n0 + lane < g.B) w = __ldg(g.special + (size_t)(n0 + lane) * g.pitch + wi);
+        if (__any_sync(0xffffffffu, w != 0u)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const uint32_t v = __ballot_sync(0xffffffffu, (w >> j) & 1u);
+            if (lane == j) S = v;
+          }
         }
       }
       mbar_wait(bar(BAR_Z_FULL + s), ph);
+      if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[t * 8 + 4] = clock64();
       tc_fence_after();
-      float z[TB];
-      {
-        float v[32];
-        tmem_ld32(tmem + lane_base + TM_Z + s * TB, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) z[i] = v[i];
-        tmem_ld32(tmem + lane_base + TM_Z + s * TB + 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) z[32 + i] = v[i];
-      }
+      float z[32];
+      tmem_ld32(tmem + lane_base + TM_Z + s * TB + hh * 32, z);
       tc_fence_before();
       mbar_arrive(bar(BAR_Z_EMPTY + s));
+      if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[t * 8 + 5] = clock64();
+      const int nrem = g.B - n0;  // teams of this half tile that exist
       if (MODE == 1) {
 #pragma unroll
-        for (int n = 0; n < TB; ++n)
-          if (e_ok && n0 + n < g.B) g.P[(size_t)(n0 + n) * g.E + e] = sigmoid_lrelu<true>(z[n] + bj);
+        for (int u = 0; u < 4; ++u) {
+          float p[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float zz = z[u * 8 + q] + bj;
+            const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
+            const float ex = __expf(-fabsf(x));
+            const float r = rcp_approx(1.f + ex);
+            p[q] = x >= 0.f ? r : ex * r;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (e_ok && u * 8 + q < nrem) g.P[(size_t)(n0 + u * 8 + q) * g.E + e] = p[q];
+        }
+        if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[t * 8 + 6] = clock64();
         continue;
       }
       if (g.Zdbg) {
 #pragma unroll
-        for (int n = 0; n < TB; ++n)
-          if (e_ok && n0 + n < g.B) g.Zdbg[(size_t)(n0 + n) * g.E + e] = z[n] + bj;
+        for (int n = 0; n < 32; ++n)
+          if (e_ok && n < nrem) g.Zdbg[(size_t)(n0 + n) * g.E + e] = z[n] + bj;
       }
       if (train) mbar_wait(bar(BAR_DZ_EMPTY + s), ph ^ 1);
       uint8_t* dzrow = sgen + OFF_DZ + s * DZ_BYTES + jl * 128;
+      const bool full = e_ok && nrem >= 32;
 #pragma unroll
-      for (int u = 0; u < TB / 8; ++u) {  // 8 teams -> one 16-byte unit of the dz^T row
-        __half hv[8];
+      for (int u = 0; u < 4; ++u) {  // 8 teams -> one 16-byte unit of the dz^T row; 8 independent chains for the MUFU pipe
+        float x[8], l1p[8], sig[8], gz[8], le[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int n = u * 8 + q;
-          const uint32_t wsel = __shfl_sync(0xffffffffu, n < 32 ? w_lo : w_hi, n & 31);
-          const bool sp = (wsel >> lane) & 1u;
-          const bool live = e_ok && (n0 + n < g.B);
-          const float zz = z[n] + bj;
-          // dense case first (y = 0, w = tnw): loss = max(x,0) + log1p(exp(-|x|)), dz = sigmoid(x)*slope
-          const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
-          const float ex = __expf(-fabsf(x));
+          const float zz = z[u * 8 + q] + bj;
+          x[q] = fmaxf(zz, NTF_LRELU_SLOPE * zz);
+          const float ex = __expf(-fabsf(x[q]));
           const float den = 1.f + ex;
-          const float l1p = __logf(den);
-          const float r = __frcp_rn(den);
-          const float sig = x >= 0.f ? r : ex * r;
-          const float slope = zz > 0.f ? 1.f : NTF_LRELU_SLOPE;
-          float gz = inv_scale_w * sig * slope;
-          float le = fmaxf(x, 0.f) + l1p;
-          if (sp) {  // rare: member of the team or sampled negative -> weight tpw, target from the member list
-            const bool y = is_member(g.m_indptr, g.m_indices, n0 + n, e);
-            const float yf = y ? 1.f : 0.f;
-            loss_sp += live ? g.tpw * ((1.f - yf) * x + fmaxf(-x, 0.f) + l1p) : 0.f;
-            gz = g.tpw * (sig - yf) * slope;
-            le = 0.f;
-          }
-          if (!live) { gz = 0.f; le = 0.f; }
-          loss_dense += le;
-          db_acc += gz;
-          hv[q] = __float2half_rn(gz);
+          l1p[q] = __logf(den);
+          const float r = rcp_approx(den);
+          sig[q] = x[q] >= 0.f ? r : ex * r;
+          // dense case (target 0, weight tnw): loss = max(x,0) + log1p(exp(-|x|)), dz = tnw*sigmoid(x)*slope
+          gz[q] = sig[q] * (zz > 0.f ? c_pos : c_neg);
+          le[q] = fmaxf(x[q], 0.f) + l1p[q];
         }
+        const uint32_t sb = (S >> (u * 8)) & 0xFFu;
+        if (sb) {  // rare: member of the team or sampled negative -> weight tpw, target from the member list
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if ((sb >> q) & 1u) {
+              const float yf = is_member(g.m_indptr, g.m_indices, n0 + u * 8 + q, e) ? 1.f : 0.f;
+              const float slope = z[u * 8 + q] + bj > 0.f ? 1.f : NTF_LRELU_SLOPE;
+              loss_sp += g.tpw * ((1.f - yf) * x[q] + fmaxf(-x[q], 0.f) + l1p[q]);
+              gz[q] = g.tpw * (sig[q] - yf) * slope;
+              le[q] = 0.f;
+            }
+          }
+        }
+        if (!full) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (!e_ok || u * 8 + q >= nrem) { gz[q] = 0.f; le[q] = 0.f; }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { loss_dense += le[q]; db_acc += gz[q]; }
         if (train) {
+          const __half2 h0 = __floats2half2_rn(gz[0], gz[1]), h1 = __floats2half2_rn(gz[2], gz[3]);
+          const __half2 h2 = __floats2half2_rn(gz[4], gz[5]), h3 = __floats2half2_rn(gz[6], gz[7]);
           uint4 pk;
-          pk.x = (uint32_t)__half_as_ushort(hv[0]) | ((uint32_t)__half_as_ushort(hv[1]) << 16);
-          pk.y = (uint32_t)__half_as_ushort(hv[2]) | ((uint32_t)__half_as_ushort(hv[3]) << 16);
-          pk.z = (uint32_t)__half_as_ushort(hv[4]) | ((uint32_t)__half_as_ushort(hv[5]) << 16);
-          pk.w = (uint32_t)__half_as_ushort(hv[6]) | ((uint32_t)__half_as_ushort(hv[7]) << 16);
-          *reinterpret_cast<uint4*>(dzrow + ((u ^ (jl & 7)) << 4)) = pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(dzrow + (((hh * 4 + u) ^ (jl & 7)) << 4)) = pk;
         }
       }
       if (train) {
         fence_proxy_async();
         mbar_arrive(bar(BAR_DZ_FULL + s));
       }
+      if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[t * 8 + 6] = clock64();
     }
     if (MODE == 0) {
-      // loss partial of this CTA (fixed-order combine: warp shuffle tree, then 4 warps in order)
-      float* red = reinterpret_cast<float*>(sgen + BAR_OFF + NUM_BARS * 8 + 16);
-      float tot = warp_sum(g.tnw * loss_dense + loss_sp);
+      // loss partial of this CTA and db: fixed-order combines (shuffle tree, then warps / halves in order)
+      float* red = reinterpret_cast<float*>(sgen + BAR_OFF + NUM_BARS * 8 + 16);   // [8]
+      float* dbs = reinterpret_cast<float*>(sgen + OFF_DZ);                          // [128], the dz stages are idle by now ...
+      if (train) mbar_wait(bar(BAR_DW_FULL), 0);                                     // ... once every MMA that read them has completed
+      const float tot = warp_sum(g.tnw * loss_dense + loss_sp);
       if (lane == 0) red[warp] = tot;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 0) g.loss_part[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+      if (train && hh == 1) dbs[jl] = db_acc;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) g.loss_part[blockIdx.x] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
       if (train) {
-        if (e_ok) g.db[e] = db_acc * g.scale;
-        mbar_wait(bar(BAR_DW_FULL), 0);
+        if (hh == 0 && e_ok) g.db[e] = (db_acc + dbs[jl]) * g.scale;
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < HK / 32; ++c) {
+        for (int c = 0; c < 2; ++c) {  // this half's 64 of the 128 dW columns
           float v[32];
-          tmem_ld32(tmem + lane_base + TM_DW + c * 32, v);
+          tmem_ld32(tmem + lane_base + TM_DW + hh * 64 + c * 32, v);
           if (e_ok) {
-            float4* dst = reinterpret_cast<float4*>(g.dW + (size_t)e * HK + c * 32);
+            float4* dst = reinterpret_cast<float4*>(g.dW + (size_t)e * HK + hh * 64 + c * 32);
 #pragma unroll
             for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q] * g.scale, v[4 * q + 1] * g.scale, v[4 * q + 2] * g.scale, v[4 * q + 3] * g.scale);
           }
@@ -399,10 +435,9 @@ __global__ void __launch_bounds__(320, 1) out_tc_kernel(const __grid_constant__ 
   } else {
     // =========================================== dA epilogue: thread = hidden unit ===========================================
     if (train) {
-      const int k = threadIdx.x - 128;  // 0..127 = TMEM lane = hidden unit
-      const uint32_t lane_base = (uint32_t)((warp - 4) * 32) << 16;
-      // the W16 image is written by warps 0-3 only when training; these warps take the other half of the arrival count
-      mbar_arrive(bar(BAR_W16));
+      const int k = threadIdx.x - 256;  // 0..127 = TMEM lane = hidden unit
+      const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+      mbar_arrive(bar(BAR_W16));  // these warps take the rest of the arrival count (the image is written by warps 0-7)
       for (int t = 0; t < ntiles; ++t) {
         const int s = t & 1;
         const uint32_t ph = (t >> 1) & 1;
@@ -430,7 +465,7 @@ __global__ void __launch_bounds__(320, 1) out_tc_kernel(const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
   }
@@ -487,8 +522,10 @@ int ntf_out_train_tc(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a,
   g.dW = a->dW; g.db = a->db; g.dA = a->dA; g.loss_part = loss_part; g.P = nullptr;
   const char* dbg = getenv("NTF_TC_ZDBG");  // debug hook used by tests/test_gpu_tc.py: address of a [B,E] device buffer for the raw logits
   g.Zdbg = dbg ? (float*)(uintptr_t)strtoull(dbg, nullptr, 0) : nullptr;
+  const char* tim = getenv("NTF_TC_TIMING");
+  g.timing = tim ? (long long*)(uintptr_t)strtoull(tim, nullptr, 0) : nullptr;
   NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TRAIN));
-  NTF_COUNT_LAUNCH; out_tc_kernel<0><<<nct, 320, SMEM_TRAIN, st>>>(mw, ma, mh, g);
+  NTF_COUNT_LAUNCH; out_tc_kernel<0><<<nct, NT, SMEM_TRAIN, st>>>(mw, ma, mh, g);
   NTF_LAUNCH_CHECK();
   return ntf_loss_reduce_impl(st, loss_part, nct, a->loss_scale, a->loss_out);
 }
@@ -501,8 +538,10 @@ int ntf_infer_scores_tc(ntf_ctx* ctx, cudaStream_t st, const float* A, const flo
   if ((rc = make_map(ctx, &ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, (uint64_t)B, HK, TB, 32))) return rc;
   TcArgs g{};
   g.bias = b; g.B = B; g.E = E; g.P = P;
+  const char* tim = getenv("NTF_TC_TIMING");
+  g.timing = tim ? (long long*)(uintptr_t)strtoull(tim, nullptr, 0) : nullptr;
   NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_INFER));
-  NTF_COUNT_LAUNCH; out_tc_kernel<1><<<cdiv(E, TE), 320, SMEM_INFER, st>>>(mw, ma, ma, g);
+  NTF_COUNT_LAUNCH; out_tc_kernel<1><<<cdiv(E, TE), NT, SMEM_INFER, st>>>(mw, ma, ma, g);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

@@ -180,7 +180,7 @@ def test_neg_sample_bit_exact_against_cpu_restatement(ops, ws, nsd, B, E, ns):
 
 def test_neg_sample_fallbacks(ops, ws):
     from opentf_b200._lib import NSD
-    # row 0: all mass on its own members -> uniform over ALL experts; row 1: one weighted candidate only; row 2: 2 negatives for ns=4
+    # rows 0 and 2: all mass on their own members -> uniform over ALL experts (fnn.py:67-69); row 1: two weighted candidates, rest topped up
     Y = sp.csr_matrix(np.array([[1, 1, 0, 0, 0, 0], [0, 0, 1, 0, 0, 0], [1, 1, 1, 1, 0, 0]], dtype=np.uint8))
     cdf_host = np.cumsum([1, 1, 0, 0, 0, 0])
     indptr, indices = dev_csr(Y)
@@ -189,7 +189,12 @@ def test_neg_sample_fallbacks(ops, ws):
     ops.neg_sample(NSD['unigram_b'], 5, 1, 0, 3, indptr.data_ptr(), indices, 6, 4, cdf, neg)
     ref = SO.sample_negatives('unigram_b', 5, 1, 0, member_lists(Y), 6, 4, cdf_host)
     assert (neg.cpu().numpy() == ref).all()
-    assert sorted(ref[2].tolist()) == [-1, -1, 4, 5]
+    assert {0, 1} <= set(ref[1].tolist()) and 2 not in ref[1] and len(set(ref[1].tolist())) == 4
+    for r in (0, 2): assert len(set(ref[r].tolist())) == 4 and min(ref[r]) >= 0
+    # fewer negatives than ns (uniform): the two non-members, then -1 padding
+    ops.neg_sample(NSD['uniform'], 5, 1, 0, 3, indptr.data_ptr(), indices, 6, 4, None, neg)
+    assert sorted(neg.cpu().numpy()[2].tolist()) == [-1, -1, 4, 5]
+    assert (neg.cpu().numpy() == SO.sample_negatives('uniform', 5, 1, 0, member_lists(Y), 6, 4, None)).all()
 
 
 def test_special_bits_set_and_clear(ops):

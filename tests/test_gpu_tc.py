@@ -78,28 +78,46 @@ def test_tc_forward_logits_and_loss(ops, ws, B, E):
     assert abs(loss - l_ref) <= 1e-3 * abs(l_ref), (loss, l_ref)  # stated TF32 tolerance on the loss: 1e-3 relative
 
 
+def oracle_from_logits(Z, A, W, Y, negs, tpw, tnw):
+    """loss and gradients of SURVEY 9.2 evaluated AT the given pre-activation logits Z (the device's TF32 logits): the lrelu
+    slope is discontinuous at z = 0, so a logit within TF32 error of zero may legitimately take either branch; testing the
+    backward products at the device's own logits separates that from the accuracy of the products themselves."""
+    y = dense(Y)
+    x = O.lrelu(Z)
+    w = O.loss_weights(y, None if negs is None else torch.as_tensor(negs, dtype=torch.int64), tpw, tnw)
+    loss = O.bce_with_logits(x, y, w).sum(1).mean().item()
+    dz = w * (torch.sigmoid(x) - y) / A.shape[0] * torch.where(Z > 0, 1.0, 0.01)
+    return loss, dz.t() @ A, dz.sum(0), dz @ W
+
+
 @pytest.mark.parametrize('B,E', SHAPES)
 @pytest.mark.parametrize('tpw,tnw', [(10.0, 1.0), (1.0, 0.0)])
 def test_tc_train_step_gradients(ops, ws, B, E, tpw, tnw):
     A, W, b, Y, negs = make_case(B, E, 7 * B + E)
-    loss, dW, db, dA, _ = run_tc(ops, ws, A, W, b, Y, negs, tpw, tnw)
-    l_ref, dW_ref, db_ref, dA_ref = oracle_out(A, W, b, Y, negs, tpw, tnw)
-    assert abs(loss - l_ref) <= 1e-3 * abs(l_ref) + 1e-6
+    loss, dW, db, dA, Z = run_tc(ops, ws, A, W, b, Y, negs, tpw, tnw, zdbg=True)
+    l_true = oracle_out(A, W, b, Y, negs, tpw, tnw)[0]
+    assert abs(loss - l_true) <= 1e-3 * abs(l_true) + 1e-6  # against the fp32 oracle: stated TF32 tolerance on the loss
+    l_ref, dW_ref, db_ref, dA_ref = oracle_from_logits(Z, A, W, Y, negs, tpw, tnw)
+    assert abs(loss - l_ref) <= 2e-5 * abs(l_ref) + 1e-6    # given the logits, the loss arithmetic is fp32 (MUFU ex2/lg2)
     assert not (torch.isnan(dW).any() or torch.isnan(db).any() or torch.isnan(dA).any())
-    # gradients: relative to the largest entry, 4e-3 (three 10-bit roundings + the TF32 logits under the sigmoid)
-    assert rel_err(db, db_ref) < 2e-3, ('db', rel_err(db, db_ref))
-    assert rel_err(dW, dW_ref) < 4e-3, ('dW', rel_err(dW, dW_ref))
-    assert rel_err(dA, dA_ref) < 4e-3, ('dA', rel_err(dA, dA_ref))
+    # given the logits: db is an fp32 sum (MUFU sigmoid); dW / dA carry dz, A, W rounded to 10-bit mantissas
+    assert rel_err(db, db_ref) < 2e-5, ('db', rel_err(db, db_ref))
+    assert rel_err(dW, dW_ref) < 2e-3, ('dW', rel_err(dW, dW_ref))
+    assert rel_err(dA, dA_ref) < 2e-3, ('dA', rel_err(dA, dA_ref))
 
 
 def test_tc_matches_fp32_kernel_on_device(ops, ws):
-    """same inputs through both precisions of the library: the two independent implementations must agree"""
+    """same inputs through both precisions of the library: away from the lrelu kink the two implementations agree"""
     from test_gpu_kernels import run_out_train
     A, W, b, Y, negs = make_case(777, 5000, 5)
     l32, dW32, db32, dA32 = run_out_train(ops, ws, 0, A, W, b, Y, negs, 10.0, 1.0)
-    l_tc, dW, db, dA, _ = run_tc(ops, ws, A, W, b, Y, negs, 10.0, 1.0)
+    l_tc, dW, db, dA, Z = run_tc(ops, ws, A, W, b, Y, negs, 10.0, 1.0, zdbg=True)
     assert abs(l_tc - l32) <= 1e-3 * abs(l32)
-    assert rel_err(dW, dW32) < 4e-3 and rel_err(db, db32) < 2e-3 and rel_err(dA, dA32) < 4e-3
+    z32 = A @ W.t() + b
+    flipped = ((Z > 0) != (z32 > 0))                      # logits whose sign TF32 changed: each moves one dz entry by <= tpw*0.99/B
+    allowed = 10.0 * 0.99 / 777 * flipped.sum(0).float()  # per expert, on db
+    assert ((db - db32).abs() <= allowed + 2e-3 * db32.abs().max()).all()
+    assert flipped.float().mean() < 2e-3                   # and such logits are rare
 
 
 @pytest.mark.parametrize('B,E', [(64, 128), (1000, 4097), (50, 40000)])
