@@ -243,7 +243,7 @@ extern "C" int ntf_csr_bag_fwd(ntf_ctx* ctx, void* stream, int B, const int32_t*
 namespace {
 constexpr int BWD_WARPS = 8;
 constexpr int HOT = 48;
-constexpr int HCAP = 4096;
+constexpr int HCAP = 8192;
 
 __global__ void skill_count_kernel(int B, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                    uint32_t* __restrict__ cnt) {
@@ -256,53 +256,72 @@ __global__ void hot_list_kernel(int S, const uint32_t* __restrict__ cnt, int32_t
   if (s < S && cnt[s] > HOT) hot[atomicAdd(nhot, 1u)] = s;  // list order is irrelevant: every hot skill is reduced on its own
 }
 
+constexpr int ENT_TILE = 4096;  // batch entries staged in shared memory per pass
+
 __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_cold_kernel(int B, const int32_t* __restrict__ indptr,
                                                                            const int32_t* __restrict__ indices,
                                                                            const int32_t* __restrict__ ent_row, int row_base,
                                                                            const float* __restrict__ dZ, int S, int h, int skw,
                                                                            const uint32_t* __restrict__ cnt, float* __restrict__ dW0T) {
   extern __shared__ float acc_all[];
+  int* sm_skill = reinterpret_cast<int*>(acc_all + (size_t)BWD_WARPS * skw * h);  // [ENT_TILE]
+  int* sm_row = sm_skill + ENT_TILE;                                                // [ENT_TILE]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* acc = acc_all + (size_t)w * skw * h;
   const int nchunks = (S + skw - 1) / skw;
   const int p_beg = indptr[0], p_end = indptr[B];
-  for (int chunk = blockIdx.x * BWD_WARPS + w; chunk < nchunks; chunk += gridDim.x * BWD_WARPS) {
+  const int rounds = (nchunks + gridDim.x * BWD_WARPS - 1) / (gridDim.x * BWD_WARPS);
+  for (int r = 0; r < rounds; ++r) {
+    const int chunk = (r * gridDim.x + blockIdx.x) * BWD_WARPS + w;  // warps without a chunk still take part in the staging
     const int s0 = chunk * skw, s1 = min(S, s0 + skw);
-    for (int k = lane; k < skw * h; k += 32) acc[k] = 0.f;
-    __syncwarp();
-    for (int base = p_beg; base < p_end; base += 32) {
-      const int p = base + lane;
-      int s = -1, n = 0;
-      if (p < p_end) {
-        s = __ldg(indices + p);
-        if (s >= s0 && s < s1 && __ldg(cnt + s) <= HOT) n = __ldg(ent_row + p) - row_base; else s = -1;
+    if (chunk < nchunks)
+      for (int k = lane; k < skw * h; k += 32) acc[k] = 0.f;
+    for (int tile = p_beg; tile < p_end; tile += ENT_TILE) {
+      const int nt = min(ENT_TILE, p_end - tile);
+      __syncthreads();
+      for (int i = threadIdx.x; i < nt; i += BWD_WARPS * 32) {  // coalesced staging of (skill id, batch row) of every entry
+        sm_skill[i] = __ldg(indices + tile + i);
+        sm_row[i] = __ldg(ent_row + tile + i) - row_base;
       }
-      unsigned hits = __ballot_sync(0xffffffffu, s >= 0);
-      while (hits) {
-        int sl[4], nn[4], g = 0;
+      __syncthreads();
+      if (chunk >= nchunks) continue;
+      for (int base = 0; base < nt; base += 32) {
+        const int i = base + lane;
+        int s = i < nt ? sm_skill[i] : -1;
+        if (s < s0 || s >= s1) s = -1;
+        unsigned hits = __ballot_sync(0xffffffffu, s >= 0);
+        if (hits == 0u) continue;
+        if (s >= 0 && __ldg(cnt + s) > HOT) s = -1;  // popular skills are reduced by the per-skill kernel
+        hits = __ballot_sync(0xffffffffu, s >= 0);
+        const int n = s >= 0 ? sm_row[i] : 0;
+        while (hits) {
+          int sl[4], nn[4], gcount = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (hits) {
-            const int L = __ffs(hits) - 1;
-            hits &= hits - 1;
-            sl[q] = __shfl_sync(0xffffffffu, s, L) - s0;
-            nn[q] = __shfl_sync(0xffffffffu, n, L);
-            g = q + 1;
-          } else { sl[q] = 0; nn[q] = 0; }
-        }
-        for (int c = lane; c < h; c += 32) {
-          float v[4];
+          for (int q = 0; q < 4; ++q) {
+            if (hits) {
+              const int L = __ffs(hits) - 1;
+              hits &= hits - 1;
+              sl[q] = __shfl_sync(0xffffffffu, s, L) - s0;
+              nn[q] = __shfl_sync(0xffffffffu, n, L);
+              gcount = q + 1;
+            } else { sl[q] = 0; nn[q] = 0; }
+          }
+          for (int c = lane; c < h; c += 32) {
+            float v[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) v[q] = q < g ? __ldg(dZ + (size_t)nn[q] * h + c) : 0.f;
+            for (int q = 0; q < 4; ++q) v[q] = q < gcount ? __ldg(dZ + (size_t)nn[q] * h + c) : 0.f;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (q < g) acc[(size_t)sl[q] * h + c] += v[q];  // in entry order
+            for (int q = 0; q < 4; ++q) if (q < gcount) acc[(size_t)sl[q] * h + c] += v[q];  // in entry order
+          }
         }
       }
     }
-    __syncwarp();
-    for (int k = lane; k < (s1 - s0) * h; k += 32)
-      if (__ldg(cnt + s0 + k / h) <= HOT) dW0T[(size_t)s0 * h + k] = acc[k];
-    __syncwarp();
+    if (chunk < nchunks) {
+      __syncwarp();
+      for (int k = lane; k < (s1 - s0) * h; k += 32)
+        if (__ldg(cnt + s0 + k / h) <= HOT) dW0T[(size_t)s0 * h + k] = acc[k];
+      __syncwarp();
+    }
   }
 }
 
@@ -320,34 +339,52 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_hot_kernel(int B, 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int p_beg = indptr[0], p_end = indptr[B];
   const int nhot = (int)*nhot_p;
+  constexpr int PER = 4;                    // consecutive entries per thread per pass (4 loads in flight)
+  constexpr int PASS = BWD_WARPS * 32 * PER;
   for (int hi = blockIdx.x; hi < nhot; hi += gridDim.x) {
     const int s = hot[hi];
     for (int c = tid; c < h; c += blockDim.x) total[c] = 0.f;
     int filled = 0;
     __syncthreads();
-    for (int base = p_beg; base < p_end; base += BWD_WARPS * 32) {
-      const int p = base + tid;
-      const bool flag = p < p_end && __ldg(indices + p) == s;
-      const unsigned bal = __ballot_sync(0xffffffffu, flag);
-      if (lane == 0) warp_cnt[w] = __popc(bal);
+    for (int base = p_beg; base < p_end; base += PASS) {
+      // ordered compaction of this skill's entries: thread tid owns entries base + PER*tid .. +PER-1
+      const int p0 = base + tid * PER;
+      int sk[PER];
+#pragma unroll
+      for (int q = 0; q < PER; ++q) sk[q] = p0 + q < p_end ? __ldg(indices + p0 + q) : -1;
+      int mine = 0;
+#pragma unroll
+      for (int q = 0; q < PER; ++q) mine += (sk[q] == s);
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) warp_cnt[w] = (uint32_t)incl;
       __syncthreads();
       int off = 0, tot = 0;
 #pragma unroll
       for (int q = 0; q < BWD_WARPS; ++q) { if (q < w) off += warp_cnt[q]; tot += warp_cnt[q]; }
-      if (flag) hits[filled + off + __popc(bal & ((1u << lane) - 1u))] = __ldg(ent_row + p) - row_base;
+      int slot = filled + off + incl - mine;
+#pragma unroll
+      for (int q = 0; q < PER; ++q)
+        if (sk[q] == s) hits[slot++] = __ldg(ent_row + p0 + q) - row_base;
       filled += tot;
       __syncthreads();
-      const bool last = base + BWD_WARPS * 32 >= p_end;
-      if (filled > HCAP - BWD_WARPS * 32 || last) {  // reduce this segment of the entry list
+      const bool last = base + PASS >= p_end;
+      if (filled > HCAP - PASS || last) {  // reduce this segment of the entry list: 8 warps x fixed slices, 8 rows in flight
         const int per = (filled + BWD_WARPS - 1) / BWD_WARPS;
         const int i0 = min(filled, w * per), i1 = min(filled, (w + 1) * per);
         for (int c = lane; c < h; c += 32) {
           float a = 0.f;
           int i = i0;
-          for (; i + 4 <= i1; i += 4) {
-            const float v0 = __ldg(dZ + (size_t)hits[i] * h + c), v1 = __ldg(dZ + (size_t)hits[i + 1] * h + c);
-            const float v2 = __ldg(dZ + (size_t)hits[i + 2] * h + c), v3 = __ldg(dZ + (size_t)hits[i + 3] * h + c);
-            a += v0; a += v1; a += v2; a += v3;
+          for (; i + 8 <= i1; i += 8) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = __ldg(dZ + (size_t)hits[i + q] * h + c);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a += v[q];
           }
           for (; i < i1; ++i) a += __ldg(dZ + (size_t)hits[i] * h + c);
           partial[(size_t)w * h + c] = a;
@@ -388,10 +425,10 @@ extern "C" int ntf_csr_bag_bwd(ntf_ctx* ctx, void* stream, int B, const int32_t*
   int skw = 2048 / h;  // 8 KB of accumulators per warp
   if (skw < 1) skw = 1;
   if (skw > 32) skw = 32;
-  const size_t smem = (size_t)BWD_WARPS * skw * h * sizeof(float);
+  const size_t smem = (size_t)BWD_WARPS * skw * h * sizeof(float) + (size_t)2 * ENT_TILE * sizeof(int);
   NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_cold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nchunks = cdiv(S, skw);
-  const int blocks = min(cdiv(nchunks, BWD_WARPS), ctx->sm_count * 3);
+  const int blocks = min(cdiv(nchunks, BWD_WARPS), ctx->sm_count * 2);
   NTF_COUNT_LAUNCH; csr_bag_bwd_cold_kernel<<<blocks, BWD_WARPS * 32, smem, st>>>(B, indptr, indices, ent_row, row_base, dZ, S, h, skw, cnt, dW0T);
   const size_t smem_hot = (size_t)(1 + BWD_WARPS) * h * sizeof(float) + (size_t)HCAP * sizeof(int);
   NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_hot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hot));

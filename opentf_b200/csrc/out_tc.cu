@@ -58,7 +58,9 @@ constexpr uint32_t TM_DA = 256;   // 2 x 64
 constexpr uint32_t TM_COLS = 512;
 
 enum { BAR_W = 0, BAR_A_FULL = 1, BAR_A_EMPTY = 3, BAR_Z_FULL = 5, BAR_Z_EMPTY = 7, BAR_DZ_FULL = 9, BAR_DZ_EMPTY = 11,
-       BAR_DA_FULL = 13, BAR_DA_EMPTY = 15, BAR_DW_FULL = 17, BAR_W16 = 18, NUM_BARS = 19 };
+       BAR_DA_FULL = 13, BAR_DA_EMPTY = 15, BAR_DW_FULL = 17, BAR_W16 = 18, BAR_H_FULL = 19, BAR_H_EMPTY = 21, NUM_BARS = 23 };
+// A_* : fp32 activation tile ring (forward operand, released as soon as the forward product has read it)
+// H_* : fp16 activation tile ring (dW operand, released after the backward products)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -150,12 +152,22 @@ struct TcArgs {
   long long* timing;          // debug: clock64 stamps of CTA 0, [tile][8] (NULL in production)
 };
 
-constexpr int NT = 448;  // warps 0-7: logits/loss epilogue, 8-11: dA epilogue, 12: TMA producer, 13: MMA issuer
-constexpr int WARP_TMA = 12, WARP_MMA = 13;
+constexpr int NT = 480;  // warps 0-7: logits/loss epilogue, 8-11: dA epilogue, 12: TMA (fp32 ring), 13: MMA issuer, 14: TMA (fp16 ring)
+constexpr int WARP_TMA = 12, WARP_MMA = 13, WARP_TMA16 = 14;
 
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 
@@ -183,6 +195,8 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(BAR_A_FULL + s), 1);
       mbar_init(bar(BAR_A_EMPTY + s), 1);
+      mbar_init(bar(BAR_H_FULL + s), 1);
+      mbar_init(bar(BAR_H_EMPTY + s), 1);
       mbar_init(bar(BAR_Z_FULL + s), 1);
       mbar_init(bar(BAR_Z_EMPTY + s), 256);
       mbar_init(bar(BAR_DZ_FULL + s), 256);
@@ -211,10 +225,18 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         const uint32_t ph = (t >> 1) & 1;
         mbar_wait(bar(BAR_A_EMPTY + s), ph ^ 1);
         if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 0] = clock64();
-        mbar_expect_tx(bar(BAR_A_FULL + s), train ? A32_BYTES + A16_BYTES : A32_BYTES);
+        mbar_expect_tx(bar(BAR_A_FULL + s), A32_BYTES);
         for (int c = 0; c < 4; ++c) tma_load_2d(sbase + OFF_A32 + s * A32_BYTES + c * (TB * 128), &map_a32, c * 32, t * TB, bar(BAR_A_FULL + s));
-        if (train)
-          for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A16 + s * A16_BYTES + c * (TB * 128), &map_a16, c * 64, t * TB, bar(BAR_A_FULL + s));
+      }
+    }
+  } else if (warp == WARP_TMA16) {
+    if (lane == 0 && train) {
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        mbar_wait(bar(BAR_H_EMPTY + s), ph ^ 1);
+        mbar_expect_tx(bar(BAR_H_FULL + s), A16_BYTES);
+        for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A16 + s * A16_BYTES + c * (TB * 128), &map_a16, c * 64, t * TB, bar(BAR_H_FULL + s));
       }
     }
   } else if (warp == WARP_MMA) {
@@ -236,7 +258,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         }
         tc_commit(bar(BAR_Z_FULL + s));
         if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 3] = clock64();
-        if (!train) tc_commit(bar(BAR_A_EMPTY + s));  // forward-only: the A stage is free once the forward product is done
+        tc_commit(bar(BAR_A_EMPTY + s));  // the fp32 stage is free once the forward product has read it
       };
       mbar_wait(bar(BAR_W), 0);
       if (ntiles > 0) issue_fwd(0);
@@ -247,6 +269,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         const int s = t & 1;
         const uint32_t ph = (t >> 1) & 1;
         mbar_wait(bar(BAR_DZ_FULL + s), ph);
+        mbar_wait(bar(BAR_H_FULL + s), ph);
         mbar_wait(bar(BAR_DA_EMPTY + s), ph ^ 1);
         tc_fence_after();
         // dW[128 j x 128 k] += dz^T[j, n] . A16[n, k] : K = 64 teams = 4 steps of 16
@@ -266,7 +289,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 7] = clock64();
         tc_commit(bar(BAR_DA_FULL + s));
         tc_commit(bar(BAR_DZ_EMPTY + s));
-        tc_commit(bar(BAR_A_EMPTY + s));
+        tc_commit(bar(BAR_H_EMPTY + s));
         if (t == ntiles - 1) tc_commit(bar(BAR_DW_FULL));
       }
     }
@@ -299,7 +322,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       fence_proxy_async();
     }
     if (MODE == 0) mbar_arrive(bar(BAR_W16));  // (also counted for validation steps; the MMA thread only waits when training)
-    float loss_dense = 0.f, loss_sp = 0.f, db_acc = 0.f;
+    float acc_lin = 0.f, acc_lg = 0.f, loss_sp = 0.f, db_acc = 0.f;  // dense loss = tnw*(acc_lin + ln2*acc_lg)
     const float c_pos = g.tnw, c_neg = g.tnw * NTF_LRELU_SLOPE;  // dz is kept as w*(sigmoid-y)*slope, i.e. true dz / loss_scale
     for (int t = 0; t < ntiles; ++t) {
       const int s = t & 1;
@@ -337,9 +360,9 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
           for (int q = 0; q < 8; ++q) {
             const float zz = z[u * 8 + q] + bj;
             const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
-            const float ex = __expf(-fabsf(x));
+            const float ex = ex2_approx(fabsf(x) * -1.4426950408889634f);
             const float r = rcp_approx(1.f + ex);
-            p[q] = x >= 0.f ? r : ex * r;
+            p[q] = zz > 0.f ? r : ex * r;
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q)
@@ -357,41 +380,39 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       uint8_t* dzrow = sgen + OFF_DZ + s * DZ_BYTES + jl * 128;
       const bool full = e_ok && nrem >= 32;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {  // 8 teams -> one 16-byte unit of the dz^T row; 8 independent chains for the MUFU pipe
-        float x[8], l1p[8], sig[8], gz[8], le[8];
+      for (int u = 0; u < 4; ++u) {  // 8 teams -> one 16-byte unit of the dz^T row; 8 independent chains keep the MUFU pipe fed
+        float gz[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
+          // dense case (target 0, weight tnw): loss = max(z,0) + ln2*lg2(1+e), dz = tnw*sigmoid(x)*slope, x = lrelu(z), e = exp(-|x|)
           const float zz = z[u * 8 + q] + bj;
-          x[q] = fmaxf(zz, NTF_LRELU_SLOPE * zz);
-          const float ex = __expf(-fabsf(x[q]));
+          const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
+          const float ex = ex2_approx(fabsf(x) * -1.4426950408889634f);
           const float den = 1.f + ex;
-          l1p[q] = __logf(den);
-          const float r = rcp_approx(den);
-          sig[q] = x[q] >= 0.f ? r : ex * r;
-          // dense case (target 0, weight tnw): loss = max(x,0) + log1p(exp(-|x|)), dz = tnw*sigmoid(x)*slope
-          gz[q] = sig[q] * (zz > 0.f ? c_pos : c_neg);
-          le[q] = fmaxf(x[q], 0.f) + l1p[q];
+          float le_lin = fmaxf(zz, 0.f), le_lg = lg2_approx(den);
+          gz[q] = rcp_approx(den) * (zz > 0.f ? c_pos : ex * c_neg);
+          if (!full && (!e_ok || u * 8 + q >= nrem)) { gz[q] = 0.f; le_lin = 0.f; le_lg = 0.f; }
+          acc_lin += le_lin; acc_lg += le_lg;
         }
         const uint32_t sb = (S >> (u * 8)) & 0xFFu;
         if (sb) {  // rare: member of the team or sampled negative -> weight tpw, target from the member list
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             if ((sb >> q) & 1u) {
+              const float zz = z[u * 8 + q] + bj;
+              const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
+              const float ex = ex2_approx(fabsf(x) * -1.4426950408889634f);
+              const float den = 1.f + ex, lg = lg2_approx(den), r = rcp_approx(den);
+              const float sig = zz > 0.f ? r : ex * r;
               const float yf = is_member(g.m_indptr, g.m_indices, n0 + u * 8 + q, e) ? 1.f : 0.f;
-              const float slope = z[u * 8 + q] + bj > 0.f ? 1.f : NTF_LRELU_SLOPE;
-              loss_sp += g.tpw * ((1.f - yf) * x[q] + fmaxf(-x[q], 0.f) + l1p[q]);
-              gz[q] = g.tpw * (sig[q] - yf) * slope;
-              le[q] = 0.f;
+              acc_lin -= fmaxf(zz, 0.f); acc_lg -= lg;  // take the dense contribution back out
+              loss_sp += g.tpw * ((1.f - yf) * x + fmaxf(-x, 0.f) + 0.6931471805599453f * lg);
+              gz[q] = g.tpw * (sig - yf) * (zz > 0.f ? 1.f : NTF_LRELU_SLOPE);
             }
           }
         }
-        if (!full) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (!e_ok || u * 8 + q >= nrem) { gz[q] = 0.f; le[q] = 0.f; }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { loss_dense += le[q]; db_acc += gz[q]; }
+        for (int q = 0; q < 8; ++q) db_acc += gz[q];
         if (train) {
           const __half2 h0 = __floats2half2_rn(gz[0], gz[1]), h1 = __floats2half2_rn(gz[2], gz[3]);
           const __half2 h2 = __floats2half2_rn(gz[4], gz[5]), h3 = __floats2half2_rn(gz[6], gz[7]);
@@ -412,7 +433,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       float* red = reinterpret_cast<float*>(sgen + BAR_OFF + NUM_BARS * 8 + 16);   // [8]
       float* dbs = reinterpret_cast<float*>(sgen + OFF_DZ);                          // [128], the dz stages are idle by now ...
       if (train) mbar_wait(bar(BAR_DW_FULL), 0);                                     // ... once every MMA that read them has completed
-      const float tot = warp_sum(g.tnw * loss_dense + loss_sp);
+      const float tot = warp_sum(g.tnw * (acc_lin + 0.6931471805599453f * acc_lg) + loss_sp);
       if (lane == 0) red[warp] = tot;
       if (train && hh == 1) dbs[jl] = db_acc;
       asm volatile("bar.sync 1, 256;" ::: "memory");

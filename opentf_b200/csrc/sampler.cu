@@ -39,46 +39,69 @@ __device__ __forceinline__ int upper_bound_u32(const uint32_t* __restrict__ cdf,
 }
 
 constexpr int NS_MAX = 64;
+constexpr int NS_WARPS = 4;
 
-__global__ void neg_sample_kernel(int nsd, uint64_t seed, uint64_t step, int row0, int B,
-                                  const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_indices, int E, int ns,
-                                  const uint32_t* __restrict__ cdf, int32_t* __restrict__ neg) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= B) return;
-  const int pb = m_indptr[n], pe = m_indptr[n + 1], npos = pe - pb;
-  int32_t* out = neg + (size_t)n * ns;
-  int got = 0;
-  uint32_t t = 0;
-  auto is_pos = [&](int j) { for (int p = pb; p < pe; ++p) if (m_indices[p] == j) return true; return false; };
-  auto is_dup = [&](int j) { for (int q = 0; q < got; ++q) if (out[q] == j) return true; return false; };
-  const int max_tries = 32 * ns + 64;
-
-  bool weighted = (nsd == NTF_NS_UNIGRAM || nsd == NTF_NS_UNIGRAM_B);
-  bool all_experts = false;  // fnn.py:67-69 fallback: uniform over ALL experts, members included
-  uint32_t T = 0;
-  if (weighted) {
-    T = cdf[E - 1];
-    uint32_t pos_mass = 0;
-    for (int p = pb; p < pe; ++p) { const int j = m_indices[p]; pos_mass += cdf[j] - (j ? cdf[j - 1] : 0u); }
-    if (T == pos_mass) { weighted = false; all_experts = true; }
-  }
-  if (weighted) {
-    for (int tries = 0; got < ns && tries < max_tries; ++tries, ++t) {
-      const uint32_t x = (uint32_t)__umul64hi(draw64(seed, (uint32_t)(row0 + n), t, step), (uint64_t)T);
-      const int j = upper_bound_u32(cdf, E, x);
-      if (!is_pos(j) && !is_dup(j)) out[got++] = j;
+// One warp per team.  The reference semantics (restated sequentially in oracle/sampler_oracle.py) are: walk the draw sequence
+// t = 0,1,2,..., accept draw j_t unless it is a member of the team or already accepted, stop at ns accepted.  "Accepted" = the
+// first ns DISTINCT non-member values of the sequence, so 32 draws can be evaluated at once: lane l takes draw t_base+l
+// (its own Philox counter and its own binary search), duplicates are resolved with match_any (earlier lane wins) and against
+// the accepted list, and the survivors are appended in lane order.  max_tries is a multiple of 32, so the hand-over to the
+// uniform top-up happens at the same draw index as in the sequential statement.
+__global__ void __launch_bounds__(NS_WARPS * 32) neg_sample_kernel(int nsd, uint64_t seed, uint64_t step, int row0, int B,
+                                                                   const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_indices,
+                                                                   int E, int ns, const uint32_t* __restrict__ cdf, int32_t* __restrict__ neg) {
+  __shared__ int sacc[NS_WARPS][NS_MAX];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int* acc = sacc[w];
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int n = blockIdx.x * NS_WARPS + w; n < B; n += gridDim.x * NS_WARPS) {
+    const int pb = m_indptr[n], pe = m_indptr[n + 1], npos = pe - pb;
+    auto is_pos = [&](int j) { for (int p = pb; p < pe; ++p) if (__ldg(m_indices + p) == j) return true; return false; };
+    const int max_tries = 32 * ns + 64;
+    int got = 0;
+    uint32_t t = 0;
+    bool weighted = (nsd == NTF_NS_UNIGRAM || nsd == NTF_NS_UNIGRAM_B);
+    bool all_experts = false;  // fnn.py:67-69 fallback: uniform over ALL experts, members included
+    uint32_t T = 0;
+    if (weighted) {
+      T = __ldg(cdf + E - 1);
+      uint32_t pos_mass = 0;
+      for (int p = pb; p < pe; ++p) { const int j = __ldg(m_indices + p); pos_mass += __ldg(cdf + j) - (j ? __ldg(cdf + j - 1) : 0u); }
+      if (T == pos_mass) { weighted = false; all_experts = true; }
     }
+    auto round32 = [&](bool use_cdf, bool members_ok, int want) {
+      const uint64_t r = draw64(seed, (uint32_t)(row0 + n), t + lane, step);
+      const int j = use_cdf ? upper_bound_u32(cdf, E, (uint32_t)__umul64hi(r, (uint64_t)T)) : (int)__umul64hi(r, (uint64_t)E);
+      bool keep = members_ok || !is_pos(j);
+      for (int q = 0; q < got; ++q) keep = keep && (acc[q] != j);
+      const uint32_t same = __match_any_sync(0xffffffffu, j);
+      keep = keep && ((same & lt) == 0u);
+      const uint32_t kb = __ballot_sync(0xffffffffu, keep);
+      const int slot = got + __popc(kb & lt);
+      __syncwarp();
+      if (keep && slot < want) acc[slot] = j;
+      __syncwarp();
+      got = min(want, got + __popc(kb));
+      t += 32;
+    };
+    if (weighted)
+      for (int tries = 0; got < ns && tries < max_tries; tries += 32) round32(true, false, ns);
+    // uniform mode, the all-expert fallback, and the top-up when fewer than ns weighted candidates exist
+    const int avail = all_experts ? E : E - npos;
+    const int want = min(ns, avail);
+    for (int tries = 0; got < want && tries < max_tries; tries += 32) round32(false, all_experts, want);
+    if (got < want && lane == 0) {  // pathological rows (E - npos barely >= ns): deterministic sweep
+      for (int j = 0; got < want && j < E; ++j) {
+        bool ok = all_experts || !is_pos(j);
+        for (int q = 0; q < got; ++q) ok = ok && (acc[q] != j);
+        if (ok) acc[got++] = j;
+      }
+    }
+    got = __shfl_sync(0xffffffffu, got, 0);
+    __syncwarp();
+    for (int q = lane; q < ns; q += 32) neg[(size_t)n * ns + q] = q < got ? acc[q] : -1;
+    __syncwarp();
   }
-  // uniform mode, the all-expert fallback, and the top-up when fewer than ns weighted candidates exist
-  const int avail = all_experts ? E : E - npos;
-  const int want = min(ns, avail);
-  for (int tries = 0; got < want && tries < max_tries; ++tries, ++t) {
-    const int j = (int)__umul64hi(draw64(seed, (uint32_t)(row0 + n), t, step), (uint64_t)E);
-    if ((all_experts || !is_pos(j)) && !is_dup(j)) out[got++] = j;
-  }
-  for (int j = 0; got < want && j < E; ++j)  // pathological rows (E - npos barely >= ns): deterministic sweep
-    if ((all_experts || !is_pos(j)) && !is_dup(j)) out[got++] = j;
-  for (; got < ns; ++got) out[got] = -1;
 }
 
 __global__ void special_bits_kernel(int op, int B, const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_indices,
@@ -120,7 +143,7 @@ extern "C" int ntf_neg_sample(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed
   NTF_REQUIRE(nsd >= NTF_NS_UNIFORM && nsd <= NTF_NS_UNIGRAM_B, NTF_ERR_BAD_ARG, "neg_sample: nsd=%d", nsd);
   NTF_REQUIRE(nsd == NTF_NS_UNIFORM || cdf, NTF_ERR_BAD_ARG, "neg_sample: unigram modes need a cdf");
   NTF_REQUIRE(B > 0 && E > 0 && ns > 0 && ns <= NS_MAX, NTF_ERR_UNSUPPORTED, "neg_sample: B=%d E=%d ns=%d (ns<=%d)", B, E, ns, NS_MAX);
-  NTF_COUNT_LAUNCH; neg_sample_kernel<<<cdiv(B, 128), 128, 0, as_stream(stream)>>>(nsd, seed, step, row0, B, m_indptr, m_indices, E, ns, cdf, neg);
+  NTF_COUNT_LAUNCH; neg_sample_kernel<<<min(cdiv(B, NS_WARPS), ctx->sm_count * 16), NS_WARPS * 32, 0, as_stream(stream)>>>(nsd, seed, step, row0, B, m_indptr, m_indices, E, ns, cdf, neg);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
