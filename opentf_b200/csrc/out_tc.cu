@@ -224,7 +224,6 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         const int s = t & 1;
         const uint32_t ph = (t >> 1) & 1;
         mbar_wait(bar(BAR_A_EMPTY + s), ph ^ 1);
-        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 0] = clock64();
         mbar_expect_tx(bar(BAR_A_FULL + s), A32_BYTES);
         for (int c = 0; c < 4; ++c) tma_load_2d(sbase + OFF_A32 + s * A32_BYTES + c * (TB * 128), &map_a32, c * 32, t * TB, bar(BAR_A_FULL + s));
       }
@@ -257,7 +256,10 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
           mma_tf32(tmem + TM_Z + s * TB, da, db, IDESC_FWD, i > 0);
         }
         tc_commit(bar(BAR_Z_FULL + s));
-        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 3] = clock64();
+        if (g.timing) {  // diagnostic mode serialises the pipeline: stamp the COMPLETION of the forward product
+          mbar_wait(bar(BAR_Z_FULL + s), ph);
+          if (blockIdx.x == 0) g.timing[t * 8 + 3] = clock64();
+        }
         tc_commit(bar(BAR_A_EMPTY + s));  // the fp32 stage is free once the forward product has read it
       };
       mbar_wait(bar(BAR_W), 0);
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         mbar_wait(bar(BAR_H_FULL + s), ph);
         mbar_wait(bar(BAR_DA_EMPTY + s), ph ^ 1);
         tc_fence_after();
+        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 0] = clock64();  // (overwrites the producer stamp) backward products: issue starts
         // dW[128 j x 128 k] += dz^T[j, n] . A16[n, k] : K = 64 teams = 4 steps of 16
 #pragma unroll
         for (int i = 0; i < TB / 16; ++i) {
@@ -286,8 +289,11 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
           const uint64_t db = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + i * 2048, 0, 1024);                        // MN-major, N = teams
           mma_f16(tmem + TM_DA + s * TB, da, db, IDESC_DA, i > 0);
         }
-        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 7] = clock64();
         tc_commit(bar(BAR_DA_FULL + s));
+        if (g.timing) {
+          mbar_wait(bar(BAR_DA_FULL + s), ph);
+          if (blockIdx.x == 0) g.timing[t * 8 + 7] = clock64();  // backward products complete
+        }
         tc_commit(bar(BAR_DZ_EMPTY + s));
         tc_commit(bar(BAR_H_EMPTY + s));
         if (t == ntiles - 1) tc_commit(bar(BAR_DW_FULL));
