@@ -31,8 +31,8 @@ SEEDS = {'dblp': 12, 'imdb': 3, 'uspt': 4, 'toy': 1}
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument('--gpus', type=int, default=1)
-    p.add_argument('--steps', type=int, default=50)
-    p.add_argument('--warmup', type=int, default=5)
+    p.add_argument('--steps', type=int, default=1000)
+    p.add_argument('--warmup', type=int, default=10)
     p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     p.add_argument('--workload', default='dblp', choices=list(SEEDS))
     p.add_argument('--batch', type=int, default=1000, help='teams per GPU per step (reference default b=1000)')
@@ -62,15 +62,16 @@ def workload(name):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe).  Samples carry
+    nvidia-smi's own timestamp; only those inside a window marked with `window()` count as "under load"."""
+    Q = 'timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.windows = index, [], None, []
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100', '-i', str(self.index)],
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20', '-i', str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.rows.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
@@ -80,21 +81,32 @@ class ClockSampler:
 
     def __exit__(self, *a):
         if self.proc:
+            time.sleep(0.1)
             self.proc.terminate()
             try: self.proc.wait(2)
             except Exception: self.proc.kill()
+            self.t.join(1)
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        import datetime
+        sm, mx, reasons, allsm = [], [], set(), []
         for l in self.rows:
             f = [x.strip() for x in l.split(',')]
             if len(f) < 8: continue
-            try: sm.append(float(f[1])); mx.append(float(f[2]))
+            try:
+                ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                c, m = float(f[1]), float(f[2])
             except ValueError: continue
+            allsm.append(c)
+            if self.windows and not any(a <= ts <= b for a, b in self.windows): continue
+            sm.append(c); mx.append(m)
             for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
                 if v.lower().startswith('active'): reasons.add(name)
-        if not sm: return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+        if not sm: return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0, 'samples_total': len(allsm)}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm), 'samples_total': len(allsm)}
 
 
 def peaks():
@@ -212,14 +224,17 @@ def run_ours(args):
     def timed_out_train(*a, **k):
         k0[cur['i']].record(); orig_out_train(*a, **k); k1[cur['i']].record()
     ops.out_train = timed_out_train
-    with ClockSampler(local) as clk:
-        sync()
-        ev0.record()
-        for i in range(args.steps):
-            cur['i'] = i
-            device_step(args.warmup + i)
-        ev1.record()
-        sync()
+    clk = ClockSampler(local).__enter__()  # samples through both timed legs (device-resident and end-to-end)
+    time.sleep(0.3)
+    sync()
+    w0 = time.time()
+    ev0.record()
+    for i in range(args.steps):
+        cur['i'] = i
+        device_step(args.warmup + i)
+    ev1.record()
+    sync()
+    clk.window(w0, time.time())
     ops.out_train = orig_out_train
     launches = int(_lib.lib().ntf_launch_count(0))
     ms = ev0.elapsed_time(ev1)
@@ -234,13 +249,15 @@ def run_ours(args):
     for i in list(range(min(3, args.warmup))) + [100 + i for i in range(args.steps)]: host.batch(i)  # pinned host inputs exist before timing
     for i in range(min(3, args.warmup)): host.step(eng, i)
     sync()
-    t0 = time.perf_counter()
+    w0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps): host.step(eng, 100 + i)
     e1.record()
     sync()
     e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    clk.window(w0, time.time())
+    clk.__exit__()
     t = torch.tensor([e2e_ms], device=dev)
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = args.steps * gB / (float(t.item()) * 1e-3)

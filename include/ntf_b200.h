@@ -187,6 +187,24 @@ int ntf_fill_sign_bits(ntf_ctx* ctx, void* stream, uint64_t seed, uint64_t step,
 int ntf_apply_sign(ntf_ctx* ctx, void* stream, const float* A, const uint32_t* bits, int pitch_words, int B, int h,
                    float* As);
 
+/* Flipout input layer on multi-hot rows (LinearFlipout with x in {0,1}: the input sign matters only at the nnz positions):
+ *   A[n,:] = lrelu( b_mu + sum_p W0T_mu[s_p,:] + (b_delta + sum_p sgn_p W0T_delta[s_p,:]) * s_out[n,:] )
+ * ent_sign: one bit per CSR entry of the batch, bit (p - indptr[0]), 1 -> -1 (fill with ntf_fill_sign_bits). */
+int ntf_csr_bag_flipout_fwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
+                            const uint32_t* ent_sign, const float* W0T_mu, const float* b_mu, const float* W0T_delta,
+                            const float* b_delta, const uint32_t* sign_out, int pitch_words, int S, int h, float* A);
+/* dW0T_delta[s,:] = sum_{entries p=(n,s)} sgn_p dZs[n,:]; workspace as ntf_csr_bag_bwd */
+int ntf_csr_bag_bwd_signed(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
+                           const int32_t* ent_row, int row_base, const uint32_t* ent_sign, const float* dZs, int S, int h,
+                           float* dW0T_delta, void* workspace, size_t workspace_bytes);
+/* Flipout hidden layer: Y = act( A W^T + b + (A_s W_delta^T + b_delta) * s_out ) */
+size_t ntf_dense_flipout_fwd_workspace_bytes(int B, int out);
+int ntf_dense_flipout_fwd(ntf_ctx* ctx, void* stream, const float* A, const float* W, const float* b, const float* A_s,
+                          const float* W_delta, const float* b_delta, const uint32_t* sign_out, int pitch_words, int B, int in,
+                          int out, int act, float* Y, void* workspace, size_t workspace_bytes);
+/* Y[n,c] += X[n,c] * (bit(n,c) ? -1 : +1) */
+int ntf_add_signed(ntf_ctx* ctx, void* stream, const float* X, const uint32_t* bits, int pitch_words, int B, int h, float* Y);
+
 /* out[i] = sum_k parts[k*part_stride + i] in a fixed order (deterministic split reductions) */
 int ntf_sum_parts(ntf_ctx* ctx, void* stream, const float* parts, int nparts, size_t n, size_t part_stride, float* out);
 

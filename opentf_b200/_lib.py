@@ -62,6 +62,11 @@ SIGNATURES = {
     'ntf_fill_normal': (i32, [vp, vp, u64, u64, u32, sz, vp]),
     'ntf_fill_sign_bits': (i32, [vp, vp, u64, u64, u32, sz, vp]),
     'ntf_apply_sign': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    'ntf_csr_bag_flipout_fwd': (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    'ntf_csr_bag_bwd_signed': (i32, [vp, vp, i32, vp, vp, vp, i32, vp, vp, i32, i32, vp, vp, sz]),
+    'ntf_dense_flipout_fwd_workspace_bytes': (sz, [i32, i32]),
+    'ntf_dense_flipout_fwd': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, sz]),
+    'ntf_add_signed': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     'ntf_sum_parts': (i32, [vp, vp, vp, i32, sz, sz, vp]),
 }
 

@@ -228,6 +228,53 @@ extern "C" int ntf_csr_bag_fwd(ntf_ctx* ctx, void* stream, int B, const int32_t*
   return NTF_OK;
 }
 
+// Bnn / Flipout input layer (bayesian-torch LinearFlipout on a multi-hot row):
+//   A[n,:] = lrelu( b_mu + sum_p W_mu[s_p,:] + (b_delta + sum_p sgn_p * W_delta[s_p,:]) * s_out[n,:] )
+// sgn_p = sign_in[n, s_p] exists only at the nnz positions (x*sign = 0 elsewhere): one bit per CSR entry of the batch
+// (bit p - indptr[0] of ent_sign, 1 -> -1).  One warp per team, lanes stride the h-vector (128-byte coalesced rows).
+namespace {
+__global__ void __launch_bounds__(256) csr_bag_flipout_fwd_kernel(int B, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                                  const uint32_t* __restrict__ ent_sign, const float* __restrict__ Wmu,
+                                                                  const float* __restrict__ bmu, const float* __restrict__ Wd,
+                                                                  const float* __restrict__ bd, const uint32_t* __restrict__ sign_out,
+                                                                  int pitch, int h, float* __restrict__ A) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int p0 = indptr[0];
+  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < B; n += warps) {
+    const int beg = indptr[n], end = indptr[n + 1];
+    for (int c = lane; c < h; c += 32) {
+      float am = 0.f, ad = 0.f;
+      for (int p = beg; p < end; ++p) {
+        const int sk = indices[p];
+        const int q = p - p0;
+        const bool neg = (__ldg(ent_sign + (q >> 5)) >> (q & 31)) & 1u;
+        const float wd = __ldg(Wd + (size_t)sk * h + c);
+        am += __ldg(Wmu + (size_t)sk * h + c);
+        ad += neg ? -wd : wd;
+      }
+      const bool so = (__ldg(sign_out + (size_t)n * pitch + (c >> 5)) >> (c & 31)) & 1u;
+      const float t = ad + bd[c];
+      A[(size_t)n * h + c] = lrelu((am + bmu[c]) + (so ? -t : t));
+    }
+  }
+}
+}  // namespace
+
+extern "C" int ntf_csr_bag_flipout_fwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
+                                       const uint32_t* ent_sign, const float* W0T_mu, const float* b_mu, const float* W0T_delta,
+                                       const float* b_delta, const uint32_t* sign_out, int pitch_words, int S, int h, float* A) {
+  NTF_REQUIRE(ctx && indptr && indices && ent_sign && W0T_mu && b_mu && W0T_delta && b_delta && sign_out && A, NTF_ERR_BAD_ARG,
+              "csr_bag_flipout_fwd: null pointer");
+  NTF_REQUIRE(B >= 0 && S > 0 && h > 0 && pitch_words * 32 >= h, NTF_ERR_BAD_ARG, "csr_bag_flipout_fwd: B=%d S=%d h=%d pitch=%d", B, S, h, pitch_words);
+  if (B == 0) return NTF_OK;
+  NTF_COUNT_LAUNCH;
+  csr_bag_flipout_fwd_kernel<<<min(cdiv(B, 8), ctx->sm_count * 8), 256, 0, as_stream(stream)>>>(B, indptr, indices, ent_sign, W0T_mu, b_mu, W0T_delta,
+                                                                                                 b_delta, sign_out, pitch_words, h, A);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
+
 // =========================================================================================================
 // K2: embedding-bag backward, atomic-free and run-to-run deterministic.
 //   dW0T[s,:] = sum over the batch entries (s, n) of dZ[n,:], written exactly once for EVERY s (zeros for skills
@@ -262,7 +309,8 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_cold_kernel(int B,
                                                                            const int32_t* __restrict__ indices,
                                                                            const int32_t* __restrict__ ent_row, int row_base,
                                                                            const float* __restrict__ dZ, int S, int h, int skw,
-                                                                           const uint32_t* __restrict__ cnt, float* __restrict__ dW0T) {
+                                                                           const uint32_t* __restrict__ cnt, float* __restrict__ dW0T,
+                                                                           const uint32_t* __restrict__ ent_sign) {
   extern __shared__ float acc_all[];
   int* sm_skill = reinterpret_cast<int*>(acc_all + (size_t)BWD_WARPS * skw * h);  // [ENT_TILE]
   int* sm_row = sm_skill + ENT_TILE;                                                // [ENT_TILE]
@@ -281,7 +329,12 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_cold_kernel(int B,
       __syncthreads();
       for (int i = threadIdx.x; i < nt; i += BWD_WARPS * 32) {  // coalesced staging of (skill id, batch row) of every entry
         sm_skill[i] = __ldg(indices + tile + i);
-        sm_row[i] = __ldg(ent_row + tile + i) - row_base;
+        int rr = __ldg(ent_row + tile + i) - row_base;
+        if (ent_sign) {  // Flipout: the entry's input sign rides in the top bit of the staged row id
+          const int q = tile + i - p_beg;
+          if ((__ldg(ent_sign + (q >> 5)) >> (q & 31)) & 1u) rr |= (int)0x80000000u;
+        }
+        sm_row[i] = rr;
       }
       __syncthreads();
       if (chunk >= nchunks) continue;
@@ -309,9 +362,9 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_cold_kernel(int B,
           for (int c = lane; c < h; c += 32) {
             float v[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = q < gcount ? __ldg(dZ + (size_t)nn[q] * h + c) : 0.f;
+            for (int q = 0; q < 4; ++q) v[q] = q < gcount ? __ldg(dZ + (size_t)(nn[q] & 0x7fffffff) * h + c) : 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) if (q < gcount) acc[(size_t)sl[q] * h + c] += v[q];  // in entry order
+            for (int q = 0; q < 4; ++q) if (q < gcount) acc[(size_t)sl[q] * h + c] += nn[q] < 0 ? -v[q] : v[q];  // in entry order
           }
         }
       }
@@ -330,7 +383,8 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_hot_kernel(int B, 
                                                                           const int32_t* __restrict__ ent_row, int row_base,
                                                                           const float* __restrict__ dZ, int h,
                                                                           const int32_t* __restrict__ hot,
-                                                                          const uint32_t* __restrict__ nhot_p, float* __restrict__ dW0T) {
+                                                                          const uint32_t* __restrict__ nhot_p, float* __restrict__ dW0T,
+                                                                          const uint32_t* __restrict__ ent_sign) {
   extern __shared__ float sm[];
   float* total = sm;                        // [h]
   float* partial = sm + h;                  // [BWD_WARPS][h]
@@ -369,7 +423,14 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_hot_kernel(int B, 
       int slot = filled + off + incl - mine;
 #pragma unroll
       for (int q = 0; q < PER; ++q)
-        if (sk[q] == s) hits[slot++] = __ldg(ent_row + p0 + q) - row_base;
+        if (sk[q] == s) {
+          int rr = __ldg(ent_row + p0 + q) - row_base;
+          if (ent_sign) {
+            const int e = p0 + q - p_beg;
+            if ((__ldg(ent_sign + (e >> 5)) >> (e & 31)) & 1u) rr |= (int)0x80000000u;
+          }
+          hits[slot++] = rr;
+        }
       filled += tot;
       __syncthreads();
       const bool last = base + PASS >= p_end;
@@ -382,11 +443,11 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_hot_kernel(int B, 
           for (; i + 8 <= i1; i += 8) {
             float v[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = __ldg(dZ + (size_t)hits[i + q] * h + c);
+            for (int q = 0; q < 8; ++q) v[q] = __ldg(dZ + (size_t)(hits[i + q] & 0x7fffffff) * h + c);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) a += v[q];
+            for (int q = 0; q < 8; ++q) a += hits[i + q] < 0 ? -v[q] : v[q];
           }
-          for (; i < i1; ++i) a += __ldg(dZ + (size_t)hits[i] * h + c);
+          for (; i < i1; ++i) { const float v1 = __ldg(dZ + (size_t)(hits[i] & 0x7fffffff) * h + c); a += hits[i] < 0 ? -v1 : v1; }
           partial[(size_t)w * h + c] = a;
         }
         __syncthreads();
@@ -408,9 +469,9 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_hot_kernel(int B, 
 
 extern "C" size_t ntf_csr_bag_bwd_workspace_bytes(int S) { return align_up((size_t)(2 * S + 64) * sizeof(uint32_t), 256); }
 
-extern "C" int ntf_csr_bag_bwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
-                               const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T,
-                               void* workspace, size_t workspace_bytes) {
+static int csr_bag_bwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
+                            const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T,
+                            void* workspace, size_t workspace_bytes, const uint32_t* ent_sign) {
   NTF_REQUIRE(ctx && indptr && indices && ent_row && dZ && dW0T && workspace, NTF_ERR_BAD_ARG, "csr_bag_bwd: null pointer");
   NTF_REQUIRE(B > 0 && S > 0 && h > 0, NTF_ERR_BAD_ARG, "csr_bag_bwd: B=%d S=%d h=%d", B, S, h);
   NTF_REQUIRE(h <= 2048, NTF_ERR_UNSUPPORTED, "csr_bag_bwd: first hidden width %d > 2048", h);
@@ -429,12 +490,26 @@ extern "C" int ntf_csr_bag_bwd(ntf_ctx* ctx, void* stream, int B, const int32_t*
   NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_cold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nchunks = cdiv(S, skw);
   const int blocks = min(cdiv(nchunks, BWD_WARPS), ctx->sm_count * 2);
-  NTF_COUNT_LAUNCH; csr_bag_bwd_cold_kernel<<<blocks, BWD_WARPS * 32, smem, st>>>(B, indptr, indices, ent_row, row_base, dZ, S, h, skw, cnt, dW0T);
+  NTF_COUNT_LAUNCH; csr_bag_bwd_cold_kernel<<<blocks, BWD_WARPS * 32, smem, st>>>(B, indptr, indices, ent_row, row_base, dZ, S, h, skw, cnt, dW0T, ent_sign);
   const size_t smem_hot = (size_t)(1 + BWD_WARPS) * h * sizeof(float) + (size_t)HCAP * sizeof(int);
   NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_hot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hot));
-  NTF_COUNT_LAUNCH; csr_bag_bwd_hot_kernel<<<ctx->sm_count * 2, BWD_WARPS * 32, smem_hot, st>>>(B, indptr, indices, ent_row, row_base, dZ, h, hot, nhot, dW0T);
+  NTF_COUNT_LAUNCH; csr_bag_bwd_hot_kernel<<<ctx->sm_count * 2, BWD_WARPS * 32, smem_hot, st>>>(B, indptr, indices, ent_row, row_base, dZ, h, hot, nhot, dW0T, ent_sign);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
+}
+
+extern "C" int ntf_csr_bag_bwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
+                               const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T,
+                               void* workspace, size_t workspace_bytes) {
+  return csr_bag_bwd_impl(ctx, stream, B, indptr, indices, ent_row, row_base, dZ, S, h, dW0T, workspace, workspace_bytes, nullptr);
+}
+
+// Flipout: dW0T_delta[s,:] = sum_{entries (n,s)} sgn_p * dZs[n,:]   (same owner-computes reduction, sign per CSR entry)
+extern "C" int ntf_csr_bag_bwd_signed(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
+                                      const int32_t* ent_row, int row_base, const uint32_t* ent_sign, const float* dZs, int S, int h,
+                                      float* dW0T_delta, void* workspace, size_t workspace_bytes) {
+  NTF_REQUIRE(ent_sign != nullptr, NTF_ERR_BAD_ARG, "csr_bag_bwd_signed: ent_sign is NULL");
+  return csr_bag_bwd_impl(ctx, stream, B, indptr, indices, ent_row, row_base, dZs, S, h, dW0T_delta, workspace, workspace_bytes, ent_sign);
 }
 
 // =========================================================================================================

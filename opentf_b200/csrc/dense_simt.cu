@@ -237,6 +237,26 @@ extern "C" int ntf_dense_fwd(ntf_ctx* ctx, void* stream, const float* A, const f
   return launch_gemm(as_stream(stream), g, e);
 }
 
+// Flipout hidden layer (bayesian-torch LinearFlipout):  Y = act( A W^T + b + (A_s W_delta^T + b_delta) * s_out )
+extern "C" size_t ntf_dense_flipout_fwd_workspace_bytes(int B, int out) { return align_up((size_t)B * out * sizeof(float), 256); }
+
+extern "C" int ntf_dense_flipout_fwd(ntf_ctx* ctx, void* stream, const float* A, const float* W, const float* b, const float* A_s,
+                                     const float* W_delta, const float* b_delta, const uint32_t* sign_out, int pitch_words, int B, int in,
+                                     int out, int act, float* Y, void* workspace, size_t workspace_bytes) {
+  NTF_REQUIRE(ctx && A && W && b && A_s && W_delta && b_delta && sign_out && Y && workspace, NTF_ERR_BAD_ARG, "dense_flipout_fwd: null pointer");
+  NTF_REQUIRE(B > 0 && in > 0 && out > 0 && act >= 0 && act <= 2 && pitch_words * 32 >= out, NTF_ERR_BAD_ARG,
+              "dense_flipout_fwd: B=%d in=%d out=%d act=%d pitch=%d", B, in, out, act, pitch_words);
+  NTF_REQUIRE(workspace_bytes >= ntf_dense_flipout_fwd_workspace_bytes(B, out), NTF_ERR_WORKSPACE, "dense_flipout_fwd: workspace too small");
+  float* T = (float*)workspace;
+  int rc;
+  GemmArgs g1{B, out, in, A_s, in, 1, W_delta, in, 1, in};
+  EpiBiasAct e1{T, out, b_delta, sign_out, pitch_words, nullptr, 0, 0};
+  if ((rc = launch_gemm(as_stream(stream), g1, e1))) return rc;
+  GemmArgs g2{B, out, in, A, in, 1, W, in, 1, in};
+  EpiBiasAct e2{Y, out, b, nullptr, 0, T, act, 0};
+  return launch_gemm(as_stream(stream), g2, e2);
+}
+
 static int dense_bwd_nsplit(int B) { return B > 1024 ? cdiv(B, 512) : 1; }
 
 extern "C" size_t ntf_dense_bwd_workspace_bytes(int B, int in, int out) {

@@ -48,6 +48,17 @@ __global__ void apply_sign_kernel(const float* __restrict__ A, const uint32_t* _
   As[i] = neg ? -A[i] : A[i];
 }
 
+// Y[n,c] (+)= X[n,c] * sign(n,c)
+__global__ void add_signed_kernel(const float* __restrict__ X, const uint32_t* __restrict__ bits, int pitch, int B, int h, int accumulate,
+                                  float* __restrict__ Y) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * h) return;
+  const int n = (int)(i / h), c = (int)(i % h);
+  const bool neg = (bits[(size_t)n * pitch + (c >> 5)] >> (c & 31)) & 1u;
+  const float v = neg ? -X[i] : X[i];
+  Y[i] = accumulate ? Y[i] + v : v;
+}
+
 // delta = softplus(rho)*eps ; per-block KL partial -> part[blockIdx.x]
 __global__ void __launch_bounds__(256) flipout_prepare_kernel(const float* __restrict__ mu, const float* __restrict__ rho,
                                                               const float* __restrict__ eps, size_t n, float* __restrict__ delta,
@@ -117,6 +128,15 @@ extern "C" int ntf_apply_sign(ntf_ctx* ctx, void* stream, const float* A, const 
   NTF_REQUIRE(ctx && A && bits && As, NTF_ERR_BAD_ARG, "apply_sign: null pointer");
   NTF_REQUIRE(B > 0 && h > 0 && pitch_words * 32 >= h, NTF_ERR_BAD_ARG, "apply_sign: B=%d h=%d pitch=%d", B, h, pitch_words);
   NTF_COUNT_LAUNCH; apply_sign_kernel<<<(unsigned)(((size_t)B * h + 255) / 256), 256, 0, as_stream(stream)>>>(A, bits, pitch_words, B, h, As);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
+
+// Y += X * sign: the input-sign half of the Flipout backward, dA = dz mu_W + ((dz*s_out) W_delta) * s_in
+extern "C" int ntf_add_signed(ntf_ctx* ctx, void* stream, const float* X, const uint32_t* bits, int pitch_words, int B, int h, float* Y) {
+  NTF_REQUIRE(ctx && X && bits && Y, NTF_ERR_BAD_ARG, "add_signed: null pointer");
+  NTF_REQUIRE(B > 0 && h > 0 && pitch_words * 32 >= h, NTF_ERR_BAD_ARG, "add_signed: B=%d h=%d pitch=%d", B, h, pitch_words);
+  NTF_COUNT_LAUNCH; add_signed_kernel<<<(unsigned)(((size_t)B * h + 255) / 256), 256, 0, as_stream(stream)>>>(X, bits, pitch_words, B, h, 1, Y);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

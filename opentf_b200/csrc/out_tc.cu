@@ -27,6 +27,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 int ntf_loss_reduce_impl(cudaStream_t st, const float* part, int n, float scale, float* loss_out);
@@ -47,9 +49,12 @@ constexpr uint32_t OFF_A32 = OFF_W32 + W32_BYTES;           // 2 stages
 constexpr uint32_t OFF_W16 = OFF_A32 + 2 * A32_BYTES;
 constexpr uint32_t OFF_A16 = OFF_W16 + W16_BYTES;           // 2 stages
 constexpr uint32_t OFF_DZ = OFF_A16 + 2 * A16_BYTES;        // 2 stages
-constexpr uint32_t OFF_BAR = OFF_DZ + 2 * DZ_BYTES;         // mbarriers + tmem base
-constexpr uint32_t SMEM_TRAIN = OFF_BAR + 256 + 1024;       // + alignment slack
-constexpr uint32_t SMEM_INFER = OFF_W16 + 256 + 1024;       // forward only: W32 + 2 x A32
+constexpr uint32_t OFF_PLANE = OFF_DZ + 2 * DZ_BYTES;       // special / target bit planes of the current tile: 2 x [128 experts][2 words]
+constexpr uint32_t PLANE_BYTES = TE * 2 * 4;                // 1 KB each
+constexpr uint32_t OFF_BAR = OFF_PLANE + 2 * PLANE_BYTES;   // mbarriers + tmem base
+constexpr uint32_t SMEM_TRAIN = OFF_BAR + 256;              // the dynamic window is declared 1024-byte aligned (checked at run time)
+constexpr uint32_t SMEM_INFER = OFF_W16 + 256;              // forward only: W32 + 2 x A32
+static_assert(SMEM_TRAIN <= 232448, "over the 227 KB shared memory limit");
 
 // TMEM columns (fp32 accumulators, 128 lanes each)
 constexpr uint32_t TM_Z = 0;      // 2 x 64
@@ -58,9 +63,11 @@ constexpr uint32_t TM_DA = 256;   // 2 x 64
 constexpr uint32_t TM_COLS = 512;
 
 enum { BAR_W = 0, BAR_A_FULL = 1, BAR_A_EMPTY = 3, BAR_Z_FULL = 5, BAR_Z_EMPTY = 7, BAR_DZ_FULL = 9, BAR_DZ_EMPTY = 11,
-       BAR_DA_FULL = 13, BAR_DA_EMPTY = 15, BAR_DW_FULL = 17, BAR_W16 = 18, BAR_H_FULL = 19, BAR_H_EMPTY = 21, NUM_BARS = 23 };
+       BAR_DA_FULL = 13, BAR_DA_EMPTY = 15, BAR_DW_FULL = 17, BAR_W16 = 18, BAR_H_FULL = 19, BAR_H_EMPTY = 21, BAR_SP_FULL = 23, BAR_SP_EMPTY = 24,
+       NUM_BARS = 25 };
 // A_* : fp32 activation tile ring (forward operand, released as soon as the forward product has read it)
 // H_* : fp16 activation tile ring (dW operand, released after the backward products)
+// SP_*: special / target bit planes of one tile (single stage: the epilogue copies its two words to registers and releases it at once)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -150,10 +157,11 @@ struct TcArgs {
   float* P;                   // inference: [B,E] probabilities
   float* Zdbg;                // debug: raw logits z [B,E] (NULL in production)
   long long* timing;          // debug: clock64 stamps of CTA 0, [tile][8] (NULL in production)
+  int exp;                    // debug: experiment bits (NTF_TC_EXP): 1 = skip the dA reduction, 2 = skip the special-bit path
 };
 
-constexpr int NT = 480;  // warps 0-7: logits/loss epilogue, 8-11: dA epilogue, 12: TMA (fp32 ring), 13: MMA issuer, 14: TMA (fp16 ring)
-constexpr int WARP_TMA = 12, WARP_MMA = 13, WARP_TMA16 = 14;
+constexpr int NT = 512;  // warps 0-7: logits/loss epilogue, 8-11: dA epilogue, 12: TMA (fp32 ring), 13: MMA issuer, 14: TMA (fp16 ring), 15: special planes
+constexpr int WARP_TMA = 12, WARP_MMA = 13, WARP_TMA16 = 14, WARP_SP = 15;
 
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
@@ -175,9 +183,10 @@ __device__ __forceinline__ float lg2_approx(float x) {
 template <int MODE>
 __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ CUtensorMap map_w32, const __grid_constant__ CUtensorMap map_a32,
                                                        const __grid_constant__ CUtensorMap map_a16, TcArgs g) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));  // generic pointer to the aligned base
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if ((sbase & 1023u) != 0u) __trap();  // the 128-byte swizzle atoms need a 1024-byte aligned base
+  uint8_t* sgen = smem_raw;
   constexpr uint32_t BAR_OFF = MODE == 0 ? OFF_BAR : OFF_W16;
   const uint32_t bars = sbase + BAR_OFF;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + BAR_OFF + NUM_BARS * 8);
@@ -192,6 +201,8 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
     mbar_init(bar(BAR_W), 1);
     mbar_init(bar(BAR_W16), 384);
     mbar_init(bar(BAR_DW_FULL), 1);
+    mbar_init(bar(BAR_SP_FULL), 1);
+    mbar_init(bar(BAR_SP_EMPTY), 256);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(BAR_A_FULL + s), 1);
       mbar_init(bar(BAR_A_EMPTY + s), 1);
@@ -236,6 +247,49 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         mbar_wait(bar(BAR_H_EMPTY + s), ph ^ 1);
         mbar_expect_tx(bar(BAR_H_FULL + s), A16_BYTES);
         for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A16 + s * A16_BYTES + c * (TB * 128), &map_a16, c * 64, t * TB, bar(BAR_H_FULL + s));
+      }
+    }
+  } else if (warp == WARP_SP) {
+    // ====== special-plane producer: bit planes [expert][team] of the tile, transposed from the [team][expert] plane in HBM ======
+    // plane_s bit = weight tpw (member or sampled negative), plane_y bit = target 1 (member).  Off the epilogue's critical path:
+    // the words of the next tile are in registers before the current one is released.
+    if (MODE == 0) {
+      uint32_t* plane_s = reinterpret_cast<uint32_t*>(sgen + OFF_PLANE);
+      uint32_t* plane_y = plane_s + TE * 2;
+      const int wi0 = e0 >> 5;
+      uint32_t w[8];
+      auto fetch = [&](int t) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int n = t * TB + r * 32 + lane;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            w[r * 4 + c] = (g.special && !(g.exp & 2) && n < g.B && wi0 + c < g.pitch) ? __ldg(g.special + (size_t)n * g.pitch + wi0 + c) : 0u;
+        }
+      };
+      if (ntiles > 0) fetch(0);
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(bar(BAR_SP_EMPTY), (t & 1) ^ 1);
+        for (int i = lane; i < TE * 4; i += 32) plane_s[i] = 0u;  // both planes are contiguous
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int nl = r * 32 + lane;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t bits = w[r * 4 + c];
+            while (bits) {
+              const int jb = __ffs(bits) - 1;
+              bits &= bits - 1;
+              const int jl = c * 32 + jb;
+              atomicOr(&plane_s[jl * 2 + (nl >> 5)], 1u << (nl & 31));
+              if (is_member(g.m_indptr, g.m_indices, t * TB + nl, e0 + jl)) atomicOr(&plane_y[jl * 2 + (nl >> 5)], 1u << (nl & 31));
+            }
+          }
+        }
+        if (t + 1 < ntiles) fetch(t + 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BAR_SP_FULL));
       }
     }
   } else if (warp == WARP_MMA) {
@@ -328,26 +382,24 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       fence_proxy_async();
     }
     if (MODE == 0) mbar_arrive(bar(BAR_W16));  // (also counted for validation steps; the MMA thread only waits when training)
-    float acc_lin = 0.f, acc_lg = 0.f, loss_sp = 0.f, db_acc = 0.f;  // dense loss = tnw*(acc_lin + ln2*acc_lg)
-    const float c_pos = g.tnw, c_neg = g.tnw * NTF_LRELU_SLOPE;  // dz is kept as w*(sigmoid-y)*slope, i.e. true dz / loss_scale
+    float acc_lin = 0.f, acc_lg = 0.f, loss_sp = 0.f, db_acc = 0.f;  // dense loss = tnw*ln2*(acc_lg - acc_lin): sums of lg2(1+e) and of t = -c*x
+    // dz is kept as w*(sigmoid-y)*slope, i.e. true dz / loss_scale; experts past E (last tile) get zero gradient and their loss is dropped below
+    const float c_pos = e_ok ? g.tnw : 0.f, c_neg = e_ok ? g.tnw * NTF_LRELU_SLOPE : 0.f;
+    const uint32_t* plane_s = reinterpret_cast<const uint32_t*>(sgen + OFF_PLANE);
+    const uint32_t* plane_y = plane_s + TE * 2;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float kb1 = -LOG2E * bj, kb2 = -LOG2E * NTF_LRELU_SLOPE * bj;
     for (int t = 0; t < ntiles; ++t) {
       const int s = t & 1;
       const uint32_t ph = (t >> 1) & 1;
       const int n0 = t * TB + hh * 32;  // first team of this thread's half tile
-      // special bits of (32 teams x this warp's 32 experts): one coalesced word load per team, then a 32x32 bit transpose by
-      // ballots so that bit n of S = "team n0+n x my expert is a member or a sampled negative"
-      uint32_t S = 0;
-      if (MODE == 0 && g.special) {
-        const int wi = (e0 >> 5) + (warp & 3);
-        uint32_t w = 0;
-        if (wi < g.pitch && n0 + lane < g.B) w = __ldg(g.special + (size_t)(n0 + lane) * g.pitch + wi);
-        if (__any_sync(0xffffffffu, w != 0u)) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const uint32_t v = __ballot_sync(0xffffffffu, (w >> j) & 1u);
-            if (lane == j) S = v;
-          }
-        }
+      // bit n of S / Y: (team n0+n, my expert) carries weight tpw / target 1 -- two words from the tile's planes, then the stage is free
+      uint32_t S = 0, Y = 0;
+      if (MODE == 0) {
+        mbar_wait(bar(BAR_SP_FULL), t & 1);
+        S = plane_s[jl * 2 + hh];
+        Y = plane_y[jl * 2 + hh];
+        mbar_arrive(bar(BAR_SP_EMPTY));
       }
       mbar_wait(bar(BAR_Z_FULL + s), ph);
       if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[t * 8 + 4] = clock64();
@@ -384,41 +436,34 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       }
       if (train) mbar_wait(bar(BAR_DZ_EMPTY + s), ph ^ 1);
       uint8_t* dzrow = sgen + OFF_DZ + s * DZ_BYTES + jl * 128;
-      const bool full = e_ok && nrem >= 32;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {  // 8 teams -> one 16-byte unit of the dz^T row; 8 independent chains keep the MUFU pipe fed
-        float gz[8];
+      // Dense pass: every element as (target 0, weight tnw):  loss = softplus(x) = x + ln(1 + exp(-x)),  dz = tnw*sigmoid(x)*slope,
+      // x = lrelu(z + b).  With c = log2(e):  t = -c*x = min(-c*(z+b), -0.01c*(z+b))  (two FFMAs with the bias folded in, one FMNMX),
+      // e = 2^t, den = 1 + e, sigmoid(x) = 1/den, softplus(x) = (-t + lg2(den))*ln2.  lg2 is taken once per 8 elements, of the product
+      // of the den factors; sum(t) and sum(lg2) are accumulated separately and combined once per CTA.  8 teams -> one 16-byte unit
+      // of the dz^T row; 8 independent chains keep the MUFU pipe fed.  A product that overflows (logits below about -300: den > 2^16
+      // each) falls back to per-element logarithms.
+      auto dense8 = [&](int u, auto masked) {
+        float gz[8], den[8];
+        float prod = 1.f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          // dense case (target 0, weight tnw): loss = max(z,0) + ln2*lg2(1+e), dz = tnw*sigmoid(x)*slope, x = lrelu(z), e = exp(-|x|)
-          const float zz = z[u * 8 + q] + bj;
-          const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
-          const float ex = ex2_approx(fabsf(x) * -1.4426950408889634f);
-          const float den = 1.f + ex;
-          float le_lin = fmaxf(zz, 0.f), le_lg = lg2_approx(den);
-          gz[q] = rcp_approx(den) * (zz > 0.f ? c_pos : ex * c_neg);
-          if (!full && (!e_ok || u * 8 + q >= nrem)) { gz[q] = 0.f; le_lin = 0.f; le_lg = 0.f; }
-          acc_lin += le_lin; acc_lg += le_lg;
+          const float t1 = fmaf(z[u * 8 + q], -LOG2E, kb1);
+          const float t2 = fmaf(z[u * 8 + q], -LOG2E * NTF_LRELU_SLOPE, kb2);
+          float t = fminf(t1, t2);
+          const float ex = ex2_approx(t);
+          den[q] = 1.f + ex;
+          gz[q] = rcp_approx(den[q]) * (t1 < 0.f ? c_pos : c_neg);
+          if (decltype(masked)::value && u * 8 + q >= nrem) { gz[q] = 0.f; t = 0.f; den[q] = 1.f; }  // teams past the end of the batch
+          acc_lin += t;
+          prod *= den[q];
+          db_acc += gz[q];
         }
-        const uint32_t sb = (S >> (u * 8)) & 0xFFu;
-        if (sb) {  // rare: member of the team or sampled negative -> weight tpw, target from the member list
+        if (prod < 3.0e38f) {
+          acc_lg += lg2_approx(prod);
+        } else {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if ((sb >> q) & 1u) {
-              const float zz = z[u * 8 + q] + bj;
-              const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
-              const float ex = ex2_approx(fabsf(x) * -1.4426950408889634f);
-              const float den = 1.f + ex, lg = lg2_approx(den), r = rcp_approx(den);
-              const float sig = zz > 0.f ? r : ex * r;
-              const float yf = is_member(g.m_indptr, g.m_indices, n0 + u * 8 + q, e) ? 1.f : 0.f;
-              acc_lin -= fmaxf(zz, 0.f); acc_lg -= lg;  // take the dense contribution back out
-              loss_sp += g.tpw * ((1.f - yf) * x + fmaxf(-x, 0.f) + 0.6931471805599453f * lg);
-              gz[q] = g.tpw * (sig - yf) * (zz > 0.f ? 1.f : NTF_LRELU_SLOPE);
-            }
-          }
+          for (int q = 0; q < 8; ++q) acc_lg += lg2_approx(den[q]);
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) db_acc += gz[q];
         if (train) {
           const __half2 h0 = __floats2half2_rn(gz[0], gz[1]), h1 = __floats2half2_rn(gz[2], gz[3]);
           const __half2 h2 = __floats2half2_rn(gz[4], gz[5]), h3 = __floats2half2_rn(gz[6], gz[7]);
@@ -427,6 +472,38 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
           pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
           *reinterpret_cast<uint4*>(dzrow + (((hh * 4 + u) ^ (jl & 7)) << 4)) = pk;
         }
+      };
+      if (nrem >= 32) {  // (warp-uniform)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dense8(u, std::false_type{});
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dense8(u, std::true_type{});
+      }
+      // Sparse fix-up (rare): members of the team and sampled negatives carry weight tpw and the member target.  Their dense
+      // contribution is taken back out and the fp16 gradient already staged in shared memory is overwritten.
+      while (S) {
+        const int i = __ffs(S) - 1;
+        S &= S - 1;
+        float zi = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) zi = (k == i) ? z[k] : zi;
+        asm volatile("" : "+f"(zi));  // keep this path from pinning the dense pass's temporaries in registers
+        const float zz = zi + bj;
+        const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
+        const float t = -LOG2E * x;
+        const float exs = ex2_approx(t), dens = 1.f + exs;          // the dense pass's (signed) terms, taken back out
+        const float g_dense = rcp_approx(dens) * (zz > 0.f ? c_pos : c_neg);
+        acc_lin -= t;
+        acc_lg -= lg2_approx(dens);
+        const float ex = ex2_approx(fabsf(x) * -LOG2E);               // stable form for the real term
+        const float den = 1.f + ex, lg = lg2_approx(den), r = rcp_approx(den);
+        const float sig = x > 0.f ? r : ex * r;
+        const float yf = ((Y >> i) & 1u) ? 1.f : 0.f;
+        const float g_sp = g.tpw * (sig - yf) * (zz > 0.f ? 1.f : NTF_LRELU_SLOPE);
+        loss_sp += g.tpw * ((1.f - yf) * x + fmaxf(-x, 0.f) + 0.6931471805599453f * lg);
+        db_acc += g_sp - g_dense;
+        if (train) *reinterpret_cast<__half*>(dzrow + (((hh * 4 + (i >> 3)) ^ (jl & 7)) << 4) + (i & 7) * 2) = __float2half_rn(g_sp);
       }
       if (train) {
         fence_proxy_async();
@@ -439,7 +516,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       float* red = reinterpret_cast<float*>(sgen + BAR_OFF + NUM_BARS * 8 + 16);   // [8]
       float* dbs = reinterpret_cast<float*>(sgen + OFF_DZ);                          // [128], the dz stages are idle by now ...
       if (train) mbar_wait(bar(BAR_DW_FULL), 0);                                     // ... once every MMA that read them has completed
-      const float tot = warp_sum(g.tnw * (acc_lin + 0.6931471805599453f * acc_lg) + loss_sp);
+      const float tot = warp_sum(e_ok ? g.tnw * 0.6931471805599453f * (acc_lg - acc_lin) + loss_sp : 0.f);
       if (lane == 0) red[warp] = tot;
       if (train && hh == 1) dbs[jl] = db_acc;
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -482,7 +559,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
 #pragma unroll
           for (int q = 0; q < 32; ++q) {
             const int n = n0 + c * 32 + q;
-            if (n < g.B) atomicAdd(g.dA + (size_t)n * HK + k, v[q] * g.scale);  // red.global.add.f32, 128 B per warp
+            if (n < g.B && !(g.exp & 1)) atomicAdd(g.dA + (size_t)n * HK + k, v[q] * g.scale);  // red.global.add.f32, 128 B per warp
           }
         }
       }
@@ -551,6 +628,8 @@ int ntf_out_train_tc(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a,
   g.Zdbg = dbg ? (float*)(uintptr_t)strtoull(dbg, nullptr, 0) : nullptr;
   const char* tim = getenv("NTF_TC_TIMING");
   g.timing = tim ? (long long*)(uintptr_t)strtoull(tim, nullptr, 0) : nullptr;
+  const char* ex = getenv("NTF_TC_EXP");
+  g.exp = ex ? atoi(ex) : 0;
   NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TRAIN));
   NTF_COUNT_LAUNCH; out_tc_kernel<0><<<nct, NT, SMEM_TRAIN, st>>>(mw, ma, mh, g);
   NTF_LAUNCH_CHECK();

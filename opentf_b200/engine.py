@@ -28,6 +28,15 @@ def _round_up(n, a):
     return (n + a - 1) // a * a
 
 
+def _pack_bits(neg):
+    """bool [R,C] (True = -1) -> int32 [R, ceil(C/32)] bit planes, bit c%32 of word c/32"""
+    neg = np.asarray(neg, dtype=bool)
+    R, Cn = neg.shape
+    pad = _round_up(max(Cn, 1), 32) - Cn
+    if pad: neg = np.concatenate([neg, np.zeros((R, pad), dtype=bool)], axis=1)
+    return np.ascontiguousarray(np.packbits(neg, axis=1, bitorder='little')).view(np.int32).reshape(R, -1)
+
+
 def to_csr(mat):
     """accept scipy lil/csr/coo (the reference hands lil uint8, team.py:154) -> (indptr int32, indices int32, shape)."""
     c = mat.tocsr()
@@ -159,6 +168,7 @@ class Engine:
             self.delta = torch.zeros(self.n_noise, dtype=f32, device=dev)
             self.gdelta = torch.zeros(self.n_noise, dtype=f32, device=dev)
             self.kl = torch.zeros(1, dtype=f32, device=dev)
+            self.ent_sum = torch.zeros(B, dtype=f32, device=dev)
             self.act_s = [torch.empty(B, h, dtype=f32, device=dev) for h in self.hidden]
             self.dact_s = [torch.empty(B, h, dtype=f32, device=dev) for h in self.hidden]
             self.dzs = [torch.empty(B, h, dtype=f32, device=dev) for h in self.hidden]
@@ -200,7 +210,16 @@ class Engine:
     def stage(self, skill_mat, member_mat):
         self.skill, self.member = DeviceCSR(skill_mat, self.device), DeviceCSR(member_mat, self.device)
         assert self.skill.shape[1] == self.S and self.member.shape[1] == self.E
+        if self.bayesian:  # Flipout input signs exist only at the nnz positions: one bit per CSR entry of a batch
+            maxlen = int(np.diff(self.skill.host_indptr).max()) if self.skill.shape[0] else 1
+            self._ent_sign_words(self.Bmax * max(1, maxlen))
         return self
+
+    def _ent_sign_words(self, entries):
+        words = _round_up(max(1, entries), 128) // 32
+        if getattr(self, 'ent_sign', None) is None or self.ent_sign.numel() < words:
+            self.ent_sign = torch.zeros(words, dtype=torch.int32, device=self.device)
+        return words
 
     def split(self, rows):
         return SplitData(self, rows)
@@ -237,11 +256,11 @@ class Engine:
                        self.cdf if self.nsd != NSD['uniform'] else None, self.neg)
         return self.neg
 
-    def step(self, sp, b0, B, train, lr=None, loss_slot=0, neg_host=None, loss_scale=None, gbatch=None):
+    def step(self, sp, b0, B, train, lr=None, loss_slot=0, neg_host=None, loss_scale=None, gbatch=None, noise_host=None):
         """one batch = rows [b0, b0+B) of split `sp`: forward + loss (+ backward + Adam when train).
         The loss lands in self.loss_buf[loss_slot] (device); nothing is synchronised here."""
         assert 0 < B <= self.Bmax and b0 + B <= sp.n
-        if self.bayesian: return self._step_bayes(sp, b0, B, train, lr, loss_slot, neg_host, loss_scale, gbatch)
+        if self.bayesian: return self._step_bayes(sp, b0, B, train, lr, loss_slot, neg_host, loss_scale, gbatch, noise_host)
         h_last = self.hidden[-1]
         Lo = self.L - 1
         self._forward_hidden(sp, b0, B)
@@ -278,8 +297,129 @@ class Engine:
         self.adam_t += 1
         ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, self.n_params, lr, 0.9, 0.999, 1e-8, self.adam_t)
 
-    def _step_bayes(self, sp, b0, B, train, lr, loss_slot, neg_host, loss_scale, gbatch):
-        raise NotImplementedError('Bnn engine lands in bnn_engine.py')
+    # ------------------------------------------------------------------ Bnn (Flipout): bnn.py:19-25, fnn.py:126-151 with is_bayesian
+    def _pv(self, i, kind, what, buf=None):
+        return self.view(f'layers.{i}.{kind}_{what}', buf)
+
+    def _draw_noise(self, sp, b0, B, noise_host):
+        """one LinearFlipout draw per layer (eps for weight and bias shared by the batch, +-1 input / output signs per team):
+        counter RNG on the device, or host-supplied tensors (the parity-test contract, oracle.draw_flipout_noise layout)."""
+        step = self.global_step
+        if noise_host is None:
+            sid = 64 * self.rank  # signs are per team: ranks draw different ones; eps must be the same on every rank
+            ops.fill_normal(self.seed, step, 0, self.n_noise, self.eps)
+            ops.fill_sign_bits(self.seed, step, 1 + sid, self.ent_sign.numel(), self.ent_sign)
+            for i in range(self.L):
+                if i: ops.fill_sign_bits(self.seed, step, 1 + 2 * i + sid, B * self.sign_in[i].shape[1], self.sign_in[i])
+                ops.fill_sign_bits(self.seed, step, 2 + 2 * i + sid, B * self.sign_out[i].shape[1], self.sign_out[i])
+            return
+        indptr = sp.s_indptr[b0:b0 + B + 1].cpu().numpy(); idx = sp.s_indices[int(indptr[0]):int(indptr[-1])].cpu().numpy()
+        for i, nz in enumerate(noise_host):
+            ew = torch.as_tensor(nz['eps_w'], dtype=torch.float32)
+            self.nview(self.eps, f'{i}.weight').copy_((ew.t() if i == 0 else ew).contiguous())
+            self.nview(self.eps, f'{i}.bias').copy_(torch.as_tensor(nz['eps_b'], dtype=torch.float32))
+            s_in, s_out = np.asarray(nz['s_in']), np.asarray(nz['s_out'])
+            if i == 0:
+                rows = np.repeat(np.arange(B), np.diff(indptr))
+                self._ent_sign_words(len(idx))
+                packed = _pack_bits(s_in[rows, idx][None, :] < 0)[0]  # the input sign matters only where x = 1: one bit per CSR entry
+                self.ent_sign[:len(packed)].copy_(torch.from_numpy(packed))
+            else:
+                self.sign_in[i][:B].copy_(torch.from_numpy(_pack_bits(s_in < 0)))
+            self.sign_out[i][:B].copy_(torch.from_numpy(_pack_bits(s_out < 0)))
+
+    def _prepare_bayes(self):
+        """delta = softplus(rho)*eps for every tensor, KL (sum over tensors of the per-tensor MEAN) -> self.kl"""
+        self.kl.zero_()
+        for i in range(self.L):
+            for what in ('weight', 'bias'):
+                mu, rho = self._pv(i, 'mu', what), self._pv(i, 'rho', what)
+                n = mu.numel()
+                ops.flipout_prepare(mu, rho, self.nview(self.eps, f'{i}.{what}'), n, 1.0 / n, self.nview(self.delta, f'{i}.{what}'), self.kl, self.ws)
+
+    def _forward_hidden_bayes(self, sp, b0, B):
+        h = self.hidden
+        ops.csr_bag_flipout_fwd(B, sp.s_indptr.data_ptr() + 4 * b0, sp.s_indices, self.ent_sign, self._pv(0, 'mu', 'weight'), self._pv(0, 'mu', 'bias'),
+                                self.nview(self.delta, '0.weight'), self.nview(self.delta, '0.bias'), self.sign_out[0], self.sign_out[0].shape[1],
+                                self.S, h[0], self.act[0])
+        for i in range(1, self.L):  # A*s_in for the next layer (the output layer included)
+            ops.apply_sign(self.act[i - 1], self.sign_in[i], self.sign_in[i].shape[1], B, h[i - 1], self.act_s[i - 1])
+            if i == self.L - 1: break
+            ops.dense_flipout_fwd(self.act[i - 1], self._pv(i, 'mu', 'weight'), self._pv(i, 'mu', 'bias'), self.act_s[i - 1],
+                                  self.nview(self.delta, f'{i}.weight'), self.nview(self.delta, f'{i}.bias'), self.sign_out[i],
+                                  self.sign_out[i].shape[1], B, h[i - 1], h[i], 1, self.act[i], self.ws)
+
+    def _step_bayes(self, sp, b0, B, train, lr, loss_slot, neg_host, loss_scale, gbatch, noise_host=None):
+        h, Lo = self.hidden, self.L - 1
+        scale = 1.0 / B if loss_scale is None else loss_scale
+        self._draw_noise(sp, b0, B, noise_host)
+        self._prepare_bayes()
+        self._forward_hidden_bayes(sp, b0, B)
+        neg = self._sample(sp, b0, B, neg_host, gbatch)
+        mptr = sp.m_indptr.data_ptr() + 4 * b0
+        ns = 0 if neg is None else neg.shape[1]
+        ops.special_bits(1, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
+        a = OutTrainArgs()
+        a.A, a.W, a.b = self.act[-1].data_ptr(), self._pv(Lo, 'mu', 'weight').data_ptr(), self._pv(Lo, 'mu', 'bias').data_ptr()
+        a.special, a.pitch_words = self.special.data_ptr(), self.pitch
+        a.m_indptr, a.m_indices = mptr, sp.m_indices.data_ptr()
+        a.B, a.h, a.E = B, h[-1], self.E
+        a.tpw, a.tnw, a.loss_scale = self.tpw, self.tnw, scale
+        a.loss_out = self.loss_buf.data_ptr() + 4 * loss_slot
+        a.A_s, a.W_delta, a.b_delta = self.act_s[-1].data_ptr(), self.nview(self.delta, f'{Lo}.weight').data_ptr(), self.nview(self.delta, f'{Lo}.bias').data_ptr()
+        a.sign_out = self.sign_out[Lo].data_ptr()
+        if train:
+            a.dW, a.db = self._pv(Lo, 'mu', 'weight', self.grads).data_ptr(), self._pv(Lo, 'mu', 'bias', self.grads).data_ptr()
+            a.dA = self.dact[-1].data_ptr()
+            a.dW_delta, a.db_delta = self.nview(self.gdelta, f'{Lo}.weight').data_ptr(), self.nview(self.gdelta, f'{Lo}.bias').data_ptr()
+            a.dA_s = self.dact_s[-1].data_ptr()
+        ops.out_train(self.dev_index, self.precision, a, self.ws)
+        ops.special_bits(0, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
+        ops.axpy(1, scale / self.world, self.kl, self.loss_buf[loss_slot:loss_slot + 1])  # + KL/B (fnn.py:136,149)
+        self.global_step += 1
+        if not train: return
+        for i in range(self.L - 1, 0, -1):
+            # dA_{i-1} = dz mu_W + ((dz*s_out) W_delta) * s_in
+            ops.add_signed(self.dact_s[i - 1], self.sign_in[i], self.sign_in[i].shape[1], B, h[i - 1], self.dact[i - 1])
+            j = i - 1  # backward through layer j's activation
+            ops.act_bwd(self.dact[j], self.act[j], B, h[j], 1, self.dz[j], self._pv(j, 'mu', 'bias', self.grads), self.ws)
+            ops.apply_sign(self.dz[j], self.sign_out[j], self.sign_out[j].shape[1], B, h[j], self.dzs[j])
+            ops.act_bwd(self.dzs[j], None, B, h[j], 0, None, self.nview(self.gdelta, f'{j}.bias'), self.ws)
+            if j == 0: break
+            ops.dense_bwd(self.act[j - 1], self._pv(j, 'mu', 'weight'), self.dz[j], B, h[j - 1], h[j], self._pv(j, 'mu', 'weight', self.grads),
+                          self.dact[j - 1], self.ws)
+            ops.dense_bwd(self.act_s[j - 1], self.nview(self.delta, f'{j}.weight'), self.dzs[j], B, h[j - 1], h[j], self.nview(self.gdelta, f'{j}.weight'),
+                          self.dact_s[j - 1], self.ws)
+        sptr = sp.s_indptr.data_ptr() + 4 * b0
+        ops.csr_bag_bwd(B, sptr, sp.s_indices, sp.s_ent_row, b0, self.dz[0], self.S, h[0], self._pv(0, 'mu', 'weight', self.grads), self.ws)
+        ops.csr_bag_bwd_signed(B, sptr, sp.s_indices, sp.s_ent_row, b0, self.ent_sign, self.dzs[0], self.S, h[0], self.nview(self.gdelta, '0.weight'), self.ws)
+        for i in range(self.L):
+            for what in ('weight', 'bias'):
+                mu, rho = self._pv(i, 'mu', what), self._pv(i, 'rho', what)
+                n = mu.numel()
+                ops.flipout_grads(mu, rho, self.nview(self.eps, f'{i}.{what}'), self.nview(self.gdelta, f'{i}.{what}'), n, scale / (n * self.world),
+                                  self._pv(i, 'mu', what, self.grads), self._pv(i, 'rho', what, self.grads))
+        self.optimizer_step(lr)
+
+    def scores_mc(self, sp, b0, B, nmc, out, scratch, ent_pred, ent_model, noise_host=None):
+        """fnn.py:202-209 (Bnn): out[:B] = mean over nmc stochastic passes of sigmoid(model(X)); ent_pred / ent_model [B] =
+        predictive entropy of the mean / mutual information (bayesian_torch.utils.util)."""
+        Lo = self.L - 1
+        out[:B].zero_()
+        for m in range(nmc):
+            self._draw_noise(sp, b0, B, None if noise_host is None else noise_host[m])
+            self._prepare_bayes()
+            self._forward_hidden_bayes(sp, b0, B)
+            ops.infer_scores(self.precision, self.act[-1], self._pv(Lo, 'mu', 'weight'), self._pv(Lo, 'mu', 'bias'), B, self.hidden[-1], self.E, scratch, self.ws,
+                             accumulate=0, A_s=self.act_s[-1], W_delta=self.nview(self.delta, f'{Lo}.weight'), b_delta=self.nview(self.delta, f'{Lo}.bias'),
+                             sign_out=self.sign_out[Lo], pitch=self.pitch)
+            ops.row_entropy(scratch, B, self.E, 1.0, int(m > 0), self.ent_sum)   # sum over samples of the per-sample entropy
+            ops.axpy(B * self.E, 1.0 / nmc, scratch, out)
+            self.global_step += 1
+        ops.row_entropy(out, B, self.E, 1.0, 0, ent_pred)
+        ops.row_entropy(out, B, self.E, 1.0, 0, ent_model)
+        ops.axpy(B, -1.0 / nmc, self.ent_sum, ent_model)   # mutual information = H(mean) - mean_m H_m
+        return out
 
     # ------------------------------------------------------------------ streaming entry point (host batches)
     def step_host(self, s_ptr, s_idx, s_row, m_ptr, m_idx, rank=0, G=1, lr=1e-3, train=True):
@@ -312,5 +452,8 @@ class Engine:
     def topk(self, sp, b0, B, K, scores_buf, vals, idx):
         """the K best experts per team in rank order; only [B,K] leaves the GPU (fnn.py:213-218 keeps [N,E] on the host)."""
         self.scores(sp, b0, B, scores_buf)
+        return self.select_topk(scores_buf, B, K, vals, idx)
+
+    def select_topk(self, scores_buf, B, K, vals, idx):
         ops.topk_select(scores_buf, B, self.E, K, 1.0, vals, idx)
         return vals, idx

@@ -175,7 +175,9 @@ class Fnn(Ntf):
                         if self.replay is not None:
                             neg = self.replay.neg(foldidx, e, phase, bi, sp.rows_now[b0:b0 + B])
                             if neg is not None: neg = np.asarray(neg)[lo:hi]
-                        eng.step(sp, b0 + lo, hi - lo, phase == 'train', lr=lr, loss_slot=slot0 + bi, neg_host=neg, loss_scale=1.0 / B, gbatch=(b0, B))
+                        noise = self.replay.noise(foldidx, e, phase, bi, B) if hasattr(self.replay, 'noise') else None  # Bnn: recorded Flipout draws
+                        eng.step(sp, b0 + lo, hi - lo, phase == 'train', lr=lr, loss_slot=slot0 + bi, neg_host=neg, loss_scale=1.0 / B, gbatch=(b0, B),
+                                 noise_host=noise)
                 losses = eng.loss_buf[:nb_t + nb_v]
                 if eng.world > 1: torch.distributed.all_reduce(losses)
                 losses = losses.cpu().tolist()  # the one host sync of the epoch
@@ -231,22 +233,33 @@ class Fnn(Ntf):
 
     def _predict_split(self, sp, b, K):
         """fnn.py:198-218 for one prediction set: dense [N,E] probabilities, or -- when topK < E -- the K best per team
-        selected on the GPU (only [N,K] leaves it) and stored as the same coalesced sparse COO tensor."""
+        selected on the GPU (only [N,K] leaves it) and stored as the same coalesced sparse COO tensor.
+        Bnn: every batch is the mean of `nmc` stochastic passes; `uncertainty` keeps the reference's shape, including its
+        quirk that the lists are re-created per batch so only the LAST batch's entropies are saved (fnn.py:203)."""
         torch, eng = Ntf.torch, self.engine
-        scores = torch.empty(min(b, max(1, sp.n)), eng.E, dtype=torch.float32, device=eng.device)
-        if K is None:
-            out = torch.empty(sp.n, eng.E, dtype=torch.float32)
-            for b0 in range(0, sp.n, b):
-                B = min(b, sp.n - b0)
-                eng.scores(sp, b0, B, scores)
-                out[b0:b0 + B] = scores[:B].cpu()  # batch by batch, as fnn.py:211-212 does
-            return out, None
-        vals = torch.empty(sp.n, K, dtype=torch.float32, device=eng.device)
-        idx = torch.empty(sp.n, K, dtype=torch.int32, device=eng.device)
+        bb = min(b, max(1, sp.n))
+        scores = torch.empty(bb, eng.E, dtype=torch.float32, device=eng.device)
+        bayes = eng.bayesian
+        if bayes:
+            nmc = int(self._c('nmc', 2))
+            scratch = torch.empty(bb, eng.E, dtype=torch.float32, device=eng.device)
+            ent_pred, ent_model = torch.empty(bb, dtype=torch.float32, device=eng.device), torch.empty(bb, dtype=torch.float32, device=eng.device)
+        unc = None
+        out = torch.empty(sp.n, eng.E, dtype=torch.float32) if K is None else None
+        if K is not None:
+            vals = torch.empty(sp.n, K, dtype=torch.float32, device=eng.device)
+            idx = torch.empty(sp.n, K, dtype=torch.int32, device=eng.device)
         for b0 in range(0, sp.n, b):
             B = min(b, sp.n - b0)
-            eng.topk(sp, b0, B, K, scores, vals[b0:b0 + B], idx[b0:b0 + B])
-        return util.topk_to_sparse(torch, vals.cpu(), idx.cpu(), eng.E), None
+            if bayes:
+                eng.scores_mc(sp, b0, B, nmc, scores, scratch, ent_pred, ent_model)
+                unc = {'pred': [ent_pred[:B].cpu().numpy()], 'model': [ent_model[:B].cpu().numpy()]}
+            else:
+                eng.scores(sp, b0, B, scores)
+            if K is None: out[b0:b0 + B] = scores[:B].cpu()  # batch by batch, as fnn.py:211-212 does
+            else: eng.select_topk(scores, B, K, vals[b0:b0 + B], idx[b0:b0 + B])
+        if K is None: return out, unc
+        return util.topk_to_sparse(torch, vals.cpu(), idx.cpu(), eng.E), unc
 
 
 def scipy_dense(x):

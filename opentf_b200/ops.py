@@ -170,3 +170,28 @@ def apply_sign(A, bits, pitch, B, h, As):
 def sum_parts(parts, nparts, n, stride, out):
     d = _dev(parts)
     check(lib().ntf_sum_parts(_lib.ctx(d), _stream(d), _p(parts, F32), nparts, n, stride, _p(out, F32)), 'ntf_sum_parts')
+
+
+def csr_bag_flipout_fwd(B, indptr_ptr, indices, ent_sign, Wmu, bmu, Wd, bd, sign_out, pitch, S, h, A):
+    d = _dev(Wmu)
+    check(lib().ntf_csr_bag_flipout_fwd(_lib.ctx(d), _stream(d), B, indptr_ptr, _p(indices, I32), _p(ent_sign), _p(Wmu, F32), _p(bmu, F32), _p(Wd, F32),
+                                        _p(bd, F32), _p(sign_out), pitch, S, h, _p(A, F32)), 'ntf_csr_bag_flipout_fwd')
+
+
+def csr_bag_bwd_signed(B, indptr_ptr, indices, ent_row, row_base, ent_sign, dZs, S, h, dWd, ws):
+    d = _dev(dZs)
+    p, nb = ws.get(lib().ntf_csr_bag_bwd_workspace_bytes(S))
+    check(lib().ntf_csr_bag_bwd_signed(_lib.ctx(d), _stream(d), B, indptr_ptr, _p(indices, I32), _p(ent_row, I32), row_base, _p(ent_sign), _p(dZs, F32), S, h,
+                                       _p(dWd, F32), p, nb), 'ntf_csr_bag_bwd_signed')
+
+
+def dense_flipout_fwd(A, W, b, A_s, Wd, bd, sign_out, pitch, B, inn, out, act, Y, ws):
+    d = _dev(A)
+    p, nb = ws.get(lib().ntf_dense_flipout_fwd_workspace_bytes(B, out))
+    check(lib().ntf_dense_flipout_fwd(_lib.ctx(d), _stream(d), _p(A, F32), _p(W, F32), _p(b, F32), _p(A_s, F32), _p(Wd, F32), _p(bd, F32), _p(sign_out), pitch,
+                                      B, inn, out, act, _p(Y, F32), p, nb), 'ntf_dense_flipout_fwd')
+
+
+def add_signed(X, bits, pitch, B, h, Y):
+    d = _dev(X)
+    check(lib().ntf_add_signed(_lib.ctx(d), _stream(d), _p(X, F32), _p(bits), pitch, B, h, _p(Y, F32)), 'ntf_add_signed')

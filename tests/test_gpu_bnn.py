@@ -1,0 +1,163 @@
+"""GPU parity tests of the Bnn (Flipout) path: engine step, MC inference and the Bnn class end to end, against the CPU
+oracle's restatement of bayesian-torch 0.5.0 LinearFlipout (oracle/fnn_oracle.py, SURVEY.md 9.5 -- "parity unpinned"
+upstream of that restatement: the package is not vendored in the reference tree).  The Flipout draws (eps, +-1 signs)
+are made on the host with the oracle's generator order and fed to both sides, so results compare to fp32 round-off."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fnn_oracle as O
+from test_gpu_kernels import DEV, dense, rand_csr, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(S, hidden, E, B, skill, member, layers, **kw):
+    from opentf_b200.engine import Engine
+    eng = Engine(S, hidden, E, DEV, bayesian=True, precision='fp32', tpw=10, tnw=1, nsd=kw.get('nsd', 'uniform'), ns=5, seed=3, max_batch=B)
+    eng.stage(skill, member)
+    sd = {}
+    for i, L in enumerate(layers):
+        sd[f'layers.{i}.mu_weight'], sd[f'layers.{i}.rho_weight'] = L['mu_w'], L['rho_w']
+        sd[f'layers.{i}.mu_bias'], sd[f'layers.{i}.rho_bias'] = L['mu_b'], L['rho_b']
+    eng.load_state_dict(sd)
+    return eng
+
+
+def grads_of(eng, i):
+    g = lambda k, w: eng.view(f'layers.{i}.{k}_{w}', eng.grads).cpu()
+    t = (lambda x: x.t()) if i == 0 else (lambda x: x)  # layer 0 is stored transposed
+    return dict(mu_w=t(g('mu', 'weight')), rho_w=t(g('rho', 'weight')), mu_b=g('mu', 'bias'), rho_b=g('rho', 'bias'))
+
+
+@pytest.mark.parametrize('B,S,hidden,E', [(37, 50, [24], 301), (64, 40, [16, 8], 100), (130, 27, [128], 1000), (1, 9, [8], 5)])
+def test_flipout_step_matches_oracle(B, S, hidden, E):
+    rng = np.random.default_rng(B + E)
+    torch.manual_seed(B)
+    skill, member = rand_csr(rng, B, S, 1, min(S, 6)), rand_csr(rng, B, E, 1, min(E - 1, 4))
+    layers = O.init_flipout_params(S, hidden, E)
+    noise = O.draw_flipout_noise(layers, B)
+    neg = rng.integers(0, E, (B, 5))
+    X, y = dense(skill), dense(member)
+    logits, acts, pre = O.flipout_forward(layers, noise, X)
+    w = O.loss_weights(y, torch.as_tensor(neg), 10, 1)
+    kl = O.flipout_kl(layers)
+    loss_ref = (O.bce_with_logits(logits, y, w).sum(1).mean() + kl / B).item()
+    g_ref = O.flipout_backward(layers, noise, acts, pre, y, w)
+
+    eng = make_engine(S, hidden, E, B, skill, member, layers)
+    sp = eng.split(np.arange(B))
+    p0 = eng.params.clone()
+    eng.step(sp, 0, B, True, lr=1e-3, loss_slot=0, neg_host=neg, noise_host=noise)
+    torch.cuda.synchronize()
+    loss = eng.loss_buf[0].item()
+    assert abs(loss - loss_ref) <= 2e-5 * abs(loss_ref), (loss, loss_ref)  # fp32 mode, summation order only
+    for i in range(len(layers)):
+        mine = grads_of(eng, i)
+        for k in ('mu_w', 'mu_b', 'rho_w', 'rho_b'):
+            assert rel_err(mine[k], g_ref[i][k]) < 3e-5, (i, k, rel_err(mine[k], g_ref[i][k]))
+    # the optimiser moved every mu / rho by one Adam step of those gradients (|step| = lr at t = 1 wherever g != 0)
+    moved = (eng.params - p0).abs().cpu()
+    assert moved.max().item() <= 1.001e-3 and moved.max().item() > 0.9e-3
+
+    # a validation step: same loss arithmetic (BCE + KL/B), fresh draws, no parameter change
+    p1 = eng.params.clone()
+    noise2 = O.draw_flipout_noise(layers, B)
+    sd = eng.state_dict()
+    layers2 = [dict(mu_w=sd[f'layers.{i}.mu_weight'], rho_w=sd[f'layers.{i}.rho_weight'], mu_b=sd[f'layers.{i}.mu_bias'], rho_b=sd[f'layers.{i}.rho_bias'])
+               for i in range(len(layers))]
+    logits2, _, _ = O.flipout_forward(layers2, noise2, X)
+    ref2 = (O.bce_with_logits(logits2, y, w).sum(1).mean() + O.flipout_kl(layers2) / B).item()
+    eng.step(sp, 0, B, False, loss_slot=1, neg_host=neg, noise_host=noise2)
+    assert abs(eng.loss_buf[1].item() - ref2) <= 2e-5 * abs(ref2)
+    assert torch.equal(eng.params, p1)
+
+
+def test_flipout_step_on_a_batch_slice(B=48, S=30, E=200):
+    """rows [16, 48) of a split: CSR offsets are absolute, entry signs are relative to the slice"""
+    rng = np.random.default_rng(5)
+    torch.manual_seed(5)
+    skill, member = rand_csr(rng, B, S, 1, 5), rand_csr(rng, B, E, 1, 4)
+    layers = O.init_flipout_params(S, [16], E)
+    b0, Bs = 16, 32
+    noise = O.draw_flipout_noise(layers, Bs)
+    neg = rng.integers(0, E, (Bs, 5))
+    X, y = dense(skill)[b0:], dense(member)[b0:]
+    logits, acts, pre = O.flipout_forward(layers, noise, X)
+    w = O.loss_weights(y, torch.as_tensor(neg), 10, 1)
+    g_ref = O.flipout_backward(layers, noise, acts, pre, y, w)
+    eng = make_engine(S, [16], E, B, skill, member, layers)
+    sp = eng.split(np.arange(B))
+    eng.step(sp, b0, Bs, True, lr=1e-3, neg_host=neg, noise_host=noise)
+    for i in range(2):
+        mine = grads_of(eng, i)
+        for k in ('mu_w', 'mu_b', 'rho_w', 'rho_b'): assert rel_err(mine[k], g_ref[i][k]) < 3e-5, (i, k)
+
+
+def test_mc_inference_matches_oracle(B=29, S=20, E=150, nmc=4):
+    rng = np.random.default_rng(1)
+    torch.manual_seed(1)
+    skill, member = rand_csr(rng, B, S, 1, 4), rand_csr(rng, B, E, 1, 3)
+    layers = O.init_flipout_params(S, [32], E)
+    noises = [O.draw_flipout_noise(layers, B) for _ in range(nmc)]
+    mc = np.stack([torch.sigmoid(O.flipout_forward(layers, nz, dense(skill))[0]).numpy() for nz in noises])
+    eng = make_engine(S, [32], E, B, skill, member, layers)
+    sp = eng.split(np.arange(B))
+    out, scratch = torch.empty(B, E, device=DEV), torch.empty(B, E, device=DEV)
+    ep, em = torch.empty(B, device=DEV), torch.empty(B, device=DEV)
+    eng.scores_mc(sp, 0, B, nmc, out, scratch, ep, em, noise_host=noises)
+    assert np.abs(out.cpu().numpy() - mc.mean(0)).max() < 1e-6
+    assert np.abs(ep.cpu().numpy() - O.predictive_entropy(mc)).max() < 1e-4 * E  # sums of E terms of ~0.35
+    assert np.abs(em.cpu().numpy() - O.mutual_information(mc)).max() < 2e-3      # a small difference of two such sums
+
+
+def test_device_noise_is_reproducible_and_has_the_right_statistics(B=256, S=27, E=2000):
+    rng = np.random.default_rng(2)
+    torch.manual_seed(2)
+    skill, member = rand_csr(rng, B, S, 1, 3), rand_csr(rng, B, E, 2, 4)
+    layers = O.init_flipout_params(S, [128], E)
+    losses = []
+    for rep in range(2):
+        eng = make_engine(S, [128], E, B, skill, member, layers)
+        sp = eng.split(np.arange(B))
+        for i in range(3): eng.step(sp, 0, B, True, lr=1e-3, loss_slot=i)
+        losses.append(eng.loss_buf[:3].cpu().numpy().copy())
+        if rep == 0:
+            eps = eng.nview(eng.eps, '1.weight').cpu()
+            assert abs(eps.mean().item()) < 0.01 and abs(eps.std().item() - 1) < 0.01
+            bits = eng.sign_out[1].cpu().numpy().view(np.uint32)
+            frac = np.unpackbits(bits.view(np.uint8)).mean()
+            assert abs(frac - 0.5) < 0.01
+    assert np.array_equal(losses[0], losses[1])  # counter RNG keyed by (seed, step): bit-reproducible
+    assert losses[0][2] < losses[0][0]
+
+
+def test_bnn_class_end_to_end(toy, tmp_path):
+    """Bnn.learn / test on toy dblp: the reference's files, keys and layouts (G4: state_dict names/shapes of the committed
+    bnn checkpoints), probabilities in (0,1), the last batch's uncertainty vectors, and a falling training loss."""
+    from opentf_b200.bnn import Bnn
+    skill, member, splits, z = toy('dblp')
+    tv = {'skill': skill.tolil(), 'member': member.tolil()}
+    cfg = dict(b=8, e=6, ns=5, lr=0.01, es=5, h=[128], spe=2, l='bce', tpw=10, tnw=1, nsd='unigram_b', nmc=3, precision='fp32')
+    m = Bnn(str(tmp_path), 'cuda:0', 0, cfg)
+    assert m.name().startswith('/bnn.b8.e6.ns5.lr0.01') and m.is_bayesian
+    one = {'test': splits['test'], 'folds': {0: splits['folds'][0]}}
+    m.learn(tv, one, None)
+    ck = torch.load(f'{m.output}/f0.pt', weights_only=False)
+    assert list(ck['model_state_dict']) == [str(n) for n in z['bnn/names']]
+    for n in z['bnn/names']: assert tuple(ck['model_state_dict'][str(n)].shape) == tuple(z[f'bnn/f0/{n}'].shape)
+    hist = m.last_history[0]
+    assert hist[-1][0] < hist[0][0]
+    m.test(tv, one, dict(on_train=False, per_epoch=True, topK=1000))
+    p = torch.load(f'{m.output}/f0.test.pred', weights_only=False)
+    y = p['y_pred']
+    assert tuple(y.shape) == (len(splits['test']), member.shape[1]) and float(y.min()) > 0 and float(y.max()) < 1
+    last = len(splits['test']) % 8 or 8
+    assert set(p['uncertainty']) == {'pred', 'model'} and p['uncertainty']['pred'][0].shape == (last,)
+    assert (p['uncertainty']['pred'][0] > 0).all() and np.abs(p['uncertainty']['model'][0]).max() < 1.0
+    import os
+    assert os.path.exists(f'{m.output}/f0.e0.pt') and os.path.exists(f'{m.output}/f0.test.e1.pred')
+    # warm start from that checkpoint (tntf.py:38 chain): the loaded state is what test() saw
+    m2 = Bnn(str(tmp_path / 'again'), 'cuda:0', 0, dict(cfg, e=1))
+    m2.learn(tv, one, {0: f'{m.output}/f0.pt'})
+    assert m2.last_history[0][0][0] < hist[0][0]
