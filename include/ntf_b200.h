@@ -111,6 +111,14 @@ int ntf_neg_sample(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed, uint64_t 
 int ntf_special_bits(ntf_ctx* ctx, void* stream, int op, int B, const int32_t* m_indptr, const int32_t* m_indices,
                      const int32_t* neg, int ns, int E, uint32_t* special, int pitch_words);
 
+/* The same two sets, laid out for the tensor-core kernel (NTF_TF32): teams in tiles of 128, per tile one slab of Epad = roundup(E,128)
+ * experts x 4 words; word ((n/128)*Epad + j)*4 + (n%128)/32, bit n%32.  special_t: j is a member of team n or in neg[n,:];
+ * member_t: j is a member of team n (the target y).  One plane is ntf_special_tiles_bytes(B, E) bytes, zero-initialised by the
+ * caller once; op 1 sets the bits of a batch, op 0 clears the same words again.  A CTA's (tile, 128-expert) slice is 2 KB contiguous. */
+size_t ntf_special_tiles_bytes(int B, int E);
+int ntf_special_tiles(ntf_ctx* ctx, void* stream, int op, int B, const int32_t* m_indptr, const int32_t* m_indices,
+                      const int32_t* neg, int ns, int E, uint32_t* special_t, uint32_t* member_t);
+
 /* ---- output layer, training: last layer of fnn.py:25 + fnn.py:32-46,135 + its autograd (fnn.py:137) -----------------
  * z = A W^T + b ; x = lrelu(z) ; w = special ? tpw : tnw ; y = [j is a member of team n]
  * loss_out[0] = loss_scale * sum_{n,j} w*((1-y)x + softplus(-x))          (loss_scale = 1/B of the GLOBAL batch)
@@ -140,6 +148,9 @@ typedef struct {
   float* dW_delta;             /* [E,h]                                                              */
   float* db_delta;             /* [E]                                                                */
   float* dA_s;                 /* [B,h]                                                              */
+  /* NTF_TF32 reads these instead of `special` + the member CSR (NULL: every weight tnw, every target 0)  */
+  const uint32_t* special_t;   /* ntf_special_tiles planes                                           */
+  const uint32_t* member_t;
 } ntf_out_train_args;
 /* 1 if NTF_TF32 has a tcgen05 kernel for this shape (else callers use NTF_FP32; ntf_out_train(NTF_TF32) refuses it) */
 int ntf_tc_supported(int B, int h, int E, int flipout);

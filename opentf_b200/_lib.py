@@ -21,7 +21,7 @@ class OutTrainArgs(C.Structure):
     _fields_ = [('A', vp), ('W', vp), ('b', vp), ('special', vp), ('pitch_words', i32), ('m_indptr', vp), ('m_indices', vp),
                 ('B', i32), ('h', i32), ('E', i32), ('tpw', f32), ('tnw', f32), ('loss_scale', f32),
                 ('dW', vp), ('db', vp), ('dA', vp), ('loss_out', vp),
-                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp)]
+                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/ntf_b200.h (tests/test_abi.py checks it)
@@ -46,6 +46,8 @@ SIGNATURES = {
     'ntf_expert_cdf': (i32, [vp, vp, i32, vp, vp, i32, vp, vp, vp, sz]),
     'ntf_neg_sample': (i32, [vp, vp, i32, u64, u64, i32, i32, vp, vp, i32, i32, vp, vp]),
     'ntf_special_bits': (i32, [vp, vp, i32, i32, vp, vp, vp, i32, i32, vp, i32]),
+    'ntf_special_tiles_bytes': (sz, [i32, i32]),
+    'ntf_special_tiles': (i32, [vp, vp, i32, i32, vp, vp, vp, i32, i32, vp, vp]),
     'ntf_tc_supported': (i32, [i32, i32, i32, i32]),
     'ntf_out_train_workspace_bytes': (sz, [vp, i32, i32, i32, i32, i32]),
     'ntf_out_train': (i32, [vp, vp, i32, C.POINTER(OutTrainArgs), vp, sz]),

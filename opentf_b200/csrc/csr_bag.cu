@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(256) csr_bag_fwd_kernel(int B, const int32_t* 
     const int beg = indptr[n], end = indptr[n + 1];
     if (VEC4) {
       const int h4 = h >> 2;
-      for (int c = lane; c < h4; c += 32) {
+      for (int c0 = 0; c0 < h4; c0 += 32) {  // (the shuffles need every lane: the column guard is on the memory accesses only)
+        const int c = min(c0 + lane, h4 - 1);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int p = beg;
         for (; p + 4 <= end; p += 4) {  // 4 independent 16-byte loads in flight, summed in CSR order
@@ -279,101 +280,101 @@ extern "C" int ntf_csr_bag_flipout_fwd(ntf_ctx* ctx, void* stream, int B, const 
 // K2: embedding-bag backward, atomic-free and run-to-run deterministic.
 //   dW0T[s,:] = sum over the batch entries (s, n) of dZ[n,:], written exactly once for EVERY s (zeros for skills
 //   absent from the batch: Adam is dense, SURVEY.md "Hard parts").
-// Skill popularity is heavy-tailed (a few skills sit in most teams), so the work is split by a per-batch histogram:
-//   cold skills (<= HOT entries): the skill axis is cut into chunks of SKW skills, a warp owns a chunk, keeps SKW x h
-//     accumulators in shared memory and streams over the batch's flat entry list with coalesced loads, adding dZ rows
-//     for the entries that fall in its chunk, 4 rows in flight at a time, in entry order;
+// Skill popularity is heavy-tailed (a few skills sit in most teams), so the work is split by the per-batch entry count of a skill:
+//   cold skills (<= HOT entries): pass 1 drops every batch entry into a slot of its skill (integer atomics: count and position);
+//     pass 2 gives each skill a warp, which rank-sorts the <= 32 row ids and adds the dZ rows in ascending team order, 4 rows
+//     in flight; skills absent from the batch get their zero row from the same warp;
 //   hot skills (> HOT entries): one CTA per skill compacts that skill's entries in entry order, its 8 warps sum
 //     fixed slices of the list and the 8 partials are combined in a fixed order.
 // The summation order depends on the data only.  Algorithmic bytes per team: n_s*(4h+4) + 4h read, 4h*S/B written.
 // =========================================================================================================
 namespace {
 constexpr int BWD_WARPS = 8;
-constexpr int HOT = 48;
+constexpr int HOT = 32;      // a skill with more batch entries than this is reduced by the per-skill CTA kernel
 constexpr int HCAP = 8192;
 
-__global__ void skill_count_kernel(int B, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                   uint32_t* __restrict__ cnt) {
+// pass 1: every batch entry (team n, skill s) takes the next slot of its skill: slots[s][pos] = batch row (| sign bit for Flipout).
+// The slot order is arbitrary (integer atomics), pass 2 sorts it; cnt[s] ends as the exact number of entries of skill s.
+__global__ void bag_bwd_fill_kernel(int B, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                    const int32_t* __restrict__ ent_row, int row_base, const uint32_t* __restrict__ ent_sign,
+                                    uint32_t* __restrict__ cnt, int32_t* __restrict__ slots) {
   const int p0 = indptr[0], p1 = indptr[B];
-  for (int p = p0 + blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += gridDim.x * blockDim.x) atomicAdd(cnt + indices[p], 1u);
+  for (int p = p0 + blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += gridDim.x * blockDim.x) {
+    const int s = __ldg(indices + p);
+    int rr = __ldg(ent_row + p) - row_base;
+    if (ent_sign) {
+      const int q = p - p0;
+      if ((__ldg(ent_sign + (q >> 5)) >> (q & 31)) & 1u) rr |= (int)0x80000000u;
+    }
+    const uint32_t pos = atomicAdd(cnt + s, 1u);
+    if (pos < HOT) slots[(size_t)s * HOT + pos] = rr;
+  }
 }
 
-__global__ void hot_list_kernel(int S, const uint32_t* __restrict__ cnt, int32_t* __restrict__ hot, uint32_t* __restrict__ nhot) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < S && cnt[s] > HOT) hot[atomicAdd(nhot, 1u)] = s;  // list order is irrelevant: every hot skill is reduced on its own
-}
-
-constexpr int ENT_TILE = 4096;  // batch entries staged in shared memory per pass
-
-__global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_cold_kernel(int B, const int32_t* __restrict__ indptr,
-                                                                           const int32_t* __restrict__ indices,
-                                                                           const int32_t* __restrict__ ent_row, int row_base,
-                                                                           const float* __restrict__ dZ, int S, int h, int skw,
-                                                                           const uint32_t* __restrict__ cnt, float* __restrict__ dW0T,
-                                                                           const uint32_t* __restrict__ ent_sign) {
-  extern __shared__ float acc_all[];
-  int* sm_skill = reinterpret_cast<int*>(acc_all + (size_t)BWD_WARPS * skw * h);  // [ENT_TILE]
-  int* sm_row = sm_skill + ENT_TILE;                                                // [ENT_TILE]
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* acc = acc_all + (size_t)w * skw * h;
-  const int nchunks = (S + skw - 1) / skw;
-  const int p_beg = indptr[0], p_end = indptr[B];
-  const int rounds = (nchunks + gridDim.x * BWD_WARPS - 1) / (gridDim.x * BWD_WARPS);
-  for (int r = 0; r < rounds; ++r) {
-    const int chunk = (r * gridDim.x + blockIdx.x) * BWD_WARPS + w;  // warps without a chunk still take part in the staging
-    const int s0 = chunk * skw, s1 = min(S, s0 + skw);
-    if (chunk < nchunks)
-      for (int k = lane; k < skw * h; k += 32) acc[k] = 0.f;
-    for (int tile = p_beg; tile < p_end; tile += ENT_TILE) {
-      const int nt = min(ENT_TILE, p_end - tile);
-      __syncthreads();
-      for (int i = threadIdx.x; i < nt; i += BWD_WARPS * 32) {  // coalesced staging of (skill id, batch row) of every entry
-        sm_skill[i] = __ldg(indices + tile + i);
-        int rr = __ldg(ent_row + tile + i) - row_base;
-        if (ent_sign) {  // Flipout: the entry's input sign rides in the top bit of the staged row id
-          const int q = tile + i - p_beg;
-          if ((__ldg(ent_sign + (q >> 5)) >> (q & 31)) & 1u) rr |= (int)0x80000000u;
-        }
-        sm_row[i] = rr;
-      }
-      __syncthreads();
-      if (chunk >= nchunks) continue;
-      for (int base = 0; base < nt; base += 32) {
-        const int i = base + lane;
-        int s = i < nt ? sm_skill[i] : -1;
-        if (s < s0 || s >= s1) s = -1;
-        unsigned hits = __ballot_sync(0xffffffffu, s >= 0);
-        if (hits == 0u) continue;
-        if (s >= 0 && __ldg(cnt + s) > HOT) s = -1;  // popular skills are reduced by the per-skill kernel
-        hits = __ballot_sync(0xffffffffu, s >= 0);
-        const int n = s >= 0 ? sm_row[i] : 0;
-        while (hits) {
-          int sl[4], nn[4], gcount = 0;
+// pass 2: one warp per skill (all S of them: Adam is dense, absent skills get an explicit zero row).  The <= 32 batch rows of the
+// skill are rank-sorted by row id, so the fp32 sum runs in ascending team order whatever order pass 1 filled the slots in:
+// no floating-point atomics, bit-reproducible.  Skills with more entries go to the hot list.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) bag_bwd_reduce_kernel(int S, int h, const uint32_t* __restrict__ cnt, const int32_t* __restrict__ slots,
+                                                             const float* __restrict__ dZ, float* __restrict__ dW0T, int32_t* __restrict__ hot,
+                                                             uint32_t* __restrict__ nhot) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < S; s += warps) {
+    const int n = (int)__ldg(cnt + s);
+    if (n > HOT) {
+      if (lane == 0) hot[atomicAdd(nhot, 1u)] = s;  // list order is irrelevant: every hot skill is reduced on its own
+      continue;
+    }
+    int rid = 0x7fffffff;
+    if (lane < n) rid = __ldg(slots + (size_t)s * HOT + lane);
+    const int key = rid & 0x7fffffff;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (__shfl_sync(0xffffffffu, key, j) < key);
+    // lane i now needs the entry whose rank is i
+    int sorted = 0;
+    for (int i = 0; i < n; ++i) {
+      const unsigned m = __ballot_sync(0xffffffffu, lane < n && rank == i);
+      const int v = __shfl_sync(0xffffffffu, rid, __ffs(m) - 1);
+      if (lane == i) sorted = v;
+    }
+    if (VEC4) {
+      const int h4 = h >> 2;
+      for (int c0 = 0; c0 < h4; c0 += 32) {  // (the shuffles need every lane: the column guard is on the memory accesses only)
+        const int c = min(c0 + lane, h4 - 1);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int i = 0;
+        for (; i + 4 <= n; i += 4) {  // 4 rows in flight, added in order
+          int r[4]; float4 v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) r[q] = __shfl_sync(0xffffffffu, sorted, i + q);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float4*>(dZ + (size_t)(r[q] & 0x7fffffff) * h) + c);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (hits) {
-              const int L = __ffs(hits) - 1;
-              hits &= hits - 1;
-              sl[q] = __shfl_sync(0xffffffffu, s, L) - s0;
-              nn[q] = __shfl_sync(0xffffffffu, n, L);
-              gcount = q + 1;
-            } else { sl[q] = 0; nn[q] = 0; }
-          }
-          for (int c = lane; c < h; c += 32) {
-            float v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = q < gcount ? __ldg(dZ + (size_t)(nn[q] & 0x7fffffff) * h + c) : 0.f;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (q < gcount) acc[(size_t)sl[q] * h + c] += nn[q] < 0 ? -v[q] : v[q];  // in entry order
+            const float sg = r[q] < 0 ? -1.f : 1.f;
+            acc.x += sg * v[q].x; acc.y += sg * v[q].y; acc.z += sg * v[q].z; acc.w += sg * v[q].w;
           }
         }
+        for (; i < n; ++i) {
+          const int r = __shfl_sync(0xffffffffu, sorted, i);
+          const float4 v = __ldg(reinterpret_cast<const float4*>(dZ + (size_t)(r & 0x7fffffff) * h) + c);
+          const float sg = r < 0 ? -1.f : 1.f;
+          acc.x += sg * v.x; acc.y += sg * v.y; acc.z += sg * v.z; acc.w += sg * v.w;
+        }
+        if (c0 + lane < h4) reinterpret_cast<float4*>(dW0T + (size_t)s * h)[c] = acc;
       }
-    }
-    if (chunk < nchunks) {
-      __syncwarp();
-      for (int k = lane; k < (s1 - s0) * h; k += 32)
-        if (__ldg(cnt + s0 + k / h) <= HOT) dW0T[(size_t)s0 * h + k] = acc[k];
-      __syncwarp();
+    } else {
+      for (int c0 = 0; c0 < h; c0 += 32) {  // (the shuffles need every lane: the column guard is on the memory accesses only)
+        const int c = c0 + lane;
+        float acc = 0.f;
+        for (int i = 0; i < n; ++i) {
+          const int r = __shfl_sync(0xffffffffu, sorted, i);
+          const float v = c < h ? __ldg(dZ + (size_t)(r & 0x7fffffff) * h + c) : 0.f;
+          acc += r < 0 ? -v : v;
+        }
+        if (c < h) dW0T[(size_t)s * h + c] = acc;
+      }
     }
   }
 }
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_hot_kernel(int B, 
 }
 }  // namespace
 
-extern "C" size_t ntf_csr_bag_bwd_workspace_bytes(int S) { return align_up((size_t)(2 * S + 64) * sizeof(uint32_t), 256); }
+extern "C" size_t ntf_csr_bag_bwd_workspace_bytes(int S) { return align_up(((size_t)S * (2 + HOT) + 64) * sizeof(uint32_t), 256); }
 
 static int csr_bag_bwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
                             const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T,
@@ -480,17 +481,14 @@ static int csr_bag_bwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* in
   uint32_t* cnt = (uint32_t*)workspace;         // [S]
   uint32_t* nhot = cnt + S;                      // [1] (padded to 64)
   int32_t* hot = (int32_t*)(cnt + S + 64);       // [S]
+  int32_t* slots = hot + S;                      // [S][HOT]
   NTF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(S + 64) * sizeof(uint32_t), st));
-  NTF_COUNT_LAUNCH; skill_count_kernel<<<min(cdiv(B * 8, 256), ctx->sm_count * 8), 256, 0, st>>>(B, indptr, indices, cnt);
-  NTF_COUNT_LAUNCH; hot_list_kernel<<<cdiv(S, 256), 256, 0, st>>>(S, cnt, hot, nhot);
-  int skw = 2048 / h;  // 8 KB of accumulators per warp
-  if (skw < 1) skw = 1;
-  if (skw > 32) skw = 32;
-  const size_t smem = (size_t)BWD_WARPS * skw * h * sizeof(float) + (size_t)2 * ENT_TILE * sizeof(int);
-  NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_cold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int nchunks = cdiv(S, skw);
-  const int blocks = min(cdiv(nchunks, BWD_WARPS), ctx->sm_count * 2);
-  NTF_COUNT_LAUNCH; csr_bag_bwd_cold_kernel<<<blocks, BWD_WARPS * 32, smem, st>>>(B, indptr, indices, ent_row, row_base, dZ, S, h, skw, cnt, dW0T, ent_sign);
+  NTF_COUNT_LAUNCH; bag_bwd_fill_kernel<<<min(cdiv(B * 8, 256), ctx->sm_count * 8), 256, 0, st>>>(B, indptr, indices, ent_row, row_base, ent_sign, cnt, slots);
+  const bool vec = (h % 4 == 0) && (((uintptr_t)dZ | (uintptr_t)dW0T) % 16 == 0);
+  const int blocks = min(cdiv(S, 8), ctx->sm_count * 8);
+  NTF_COUNT_LAUNCH;
+  if (vec) bag_bwd_reduce_kernel<true><<<blocks, 256, 0, st>>>(S, h, cnt, slots, dZ, dW0T, hot, nhot);
+  else bag_bwd_reduce_kernel<false><<<blocks, 256, 0, st>>>(S, h, cnt, slots, dZ, dW0T, hot, nhot);
   const size_t smem_hot = (size_t)(1 + BWD_WARPS) * h * sizeof(float) + (size_t)HCAP * sizeof(int);
   NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_hot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hot));
   NTF_COUNT_LAUNCH; csr_bag_bwd_hot_kernel<<<ctx->sm_count * 2, BWD_WARPS * 32, smem_hot, st>>>(B, indptr, indices, ent_row, row_base, dZ, h, hot, nhot, dW0T, ent_sign);

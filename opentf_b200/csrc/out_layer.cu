@@ -10,7 +10,9 @@ int ntf_infer_scores_fp32(cudaStream_t st, const float* A, const float* W, const
 size_t ntf_out_train_tc_workspace_bytes(const ntf_ctx* ctx, int B, int h, int E, int flipout);
 int ntf_out_train_tc(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a, void* workspace, size_t workspace_bytes);
 int ntf_out_tc_supported(int B, int h, int E, int flipout);
-int ntf_infer_scores_tc(ntf_ctx* ctx, cudaStream_t st, const float* A, const float* W, const float* b, int B, int h, int E, float* P);
+int ntf_infer_scores_tc(ntf_ctx* ctx, cudaStream_t st, const float* A, const float* W, const float* b, int B, int h, int E, float* P,
+                        void* workspace, size_t workspace_bytes);
+size_t ntf_infer_scores_tc_workspace_bytes(int B, int h);
 
 extern "C" int ntf_tc_supported(int B, int h, int E, int flipout) { return ntf_out_tc_supported(B, h, E, flipout); }
 
@@ -44,7 +46,8 @@ extern "C" int ntf_out_train(ntf_ctx* ctx, void* stream, int precision, const nt
 }
 
 extern "C" size_t ntf_infer_scores_workspace_bytes(int B, int E, int flipout) {
-  return flipout ? align_up((size_t)B * E * sizeof(float), 256) : 0;
+  // Flipout: the perturbation term T[B,E]; otherwise the fp16 copy of the activations for the tensor-core path (h <= 128 there)
+  return flipout ? align_up((size_t)B * E * sizeof(float), 256) : ntf_infer_scores_tc_workspace_bytes(B, 128);
 }
 
 extern "C" int ntf_infer_scores(ntf_ctx* ctx, void* stream, int precision, const float* A, const float* W, const float* b, int B,
@@ -59,7 +62,7 @@ extern "C" int ntf_infer_scores(ntf_ctx* ctx, void* stream, int precision, const
     NTF_REQUIRE(workspace && workspace_bytes >= ntf_infer_scores_workspace_bytes(B, E, 1), NTF_ERR_WORKSPACE, "infer_scores: workspace too small");
   }
   if (precision == NTF_TF32 && !flip && !accumulate && ntf_out_tc_supported(B, h, E, 0))
-    return ntf_infer_scores_tc(ctx, as_stream(stream), A, W, b, B, h, E, P);
+    return ntf_infer_scores_tc(ctx, as_stream(stream), A, W, b, B, h, E, P, workspace, workspace_bytes);
   NTF_REQUIRE(precision == NTF_FP32 || precision == NTF_TF32, NTF_ERR_BAD_ARG, "infer_scores: precision=%d", precision);
   return ntf_infer_scores_fp32(as_stream(stream), A, W, b, B, h, E, A_s, W_delta, b_delta, sign_out, pitch_words, accumulate, P,
                                (float*)workspace);

@@ -4,25 +4,30 @@
 // autograd): logits, weighted BCE, dz, dW, db and dA are produced without the [B,E] logits or gradients ever
 // touching HBM.  Structure = FlashAttention backward with Q<->A (hidden activations), K<->W, dS<->dz:
 //
-//   CTA e owns experts [128e, 128e+128): W tile resident in shared memory (fp32 for the forward, an fp16 image for
-//   the backward), dW accumulator resident in TMEM for the whole kernel, db in registers.
-//   It streams over the batch in tiles of 64 teams (double buffered):
-//     TMA warp      : A tile (fp32 + fp16 copy) -> smem                                     [cp.async.bulk.tensor]
-//     MMA thread    : Z^T[128e x 64n] = W . A^T          kind::tf32, fp32 accumulate in TMEM  (forward, TF32 logits)
-//     8 epilogue warps (thread = expert x half of the tile's teams): TMEM -> regs, +b, lrelu, weighted BCE, dz; loss and db accumulate in
-//                     registers; dz (scaled by 1/loss_scale, fp16 = same 10-bit mantissa as tf32) -> smem
-//     MMA thread    : dW[128e x 128k] += dz^T . A        kind::f16, accumulates across all batch tiles in TMEM
-//                     dA^T[128k x 64n] = W^T . dz^T      kind::f16
-//     4 dA warps    : TMEM -> regs -> red.global.add into dA[B,128]  (sum over expert tiles = across CTAs)
+//   CTA e owns experts [128e, 128e+128): an fp16 image of the W tile resident in shared memory, the dW accumulator
+//   resident in TMEM for the whole kernel, db in registers.  It streams over the batch in tiles of 128 teams:
+//     TMA warp       : W tile (fp32, once) and the fp16 activation tiles (2-stage ring)        [cp.async.bulk.tensor]
+//     MMA thread     : Z^T[128e x 128n] = W . A^T                           kind::f16, fp32 accumulate in TMEM (2 stages)
+//     16 epilogue warps (thread = expert x 32 of the tile's teams): TMEM -> regs, +b, lrelu, weighted BCE, dz; loss and db
+//                      accumulate in registers; dz (scaled by 1/loss_scale, fp16) -> shared memory
+//     special warp   : bulk-copies the tile's slice of the tile-transposed `condition` / member bit planes (ntf_special_tiles)
+//                      into shared memory, one tile ahead of the epilogue
+//     MMA thread     : dW[128e x 128k] += dz^T . A        accumulates across all batch tiles in TMEM
+//                      dA[128n x 128k]   = dz . W
+//     4 dA warps     : TMEM -> regs -> shared memory -> TMA reduce-add (cp.reduce.async.bulk.tensor) into dA[B,128]: the sum over
+//                      expert tiles (= across CTAs) is done by L2, with no SM-side atomics
 //   At the end the epilogue warps drain dW from TMEM, write db, and one loss partial per CTA.
 //
-// Why fp16 for the two backward products: their operands are needed in MN-major form (contraction over teams / over
-// experts), which tcgen05 supports for 32-bit types only through a dedicated 32B-atom swizzle that cannot share a
-// buffer with the K-major forward operands; 16-bit operands allow both majors on one 128B-swizzled image, halve
-// shared memory and run at twice the tf32 rate.  dz is scaled into fp16's normal range, so the gradient products
-// carry the same 10-bit mantissa as TF32.
+// Operand precision: all three products read fp16 operands (RN from fp32: 10-bit mantissa, the same as TF32) and accumulate
+// in fp32 -- this is what the ABI calls NTF_TF32: TF32-class tolerance (2^-10 relative per product term), stated in
+// tests/test_gpu_tc.py.  16-bit operands are what lets ONE 128B-swizzled image serve as K-major operand of the forward
+// product and as MN-major operand of the backward products (32-bit types need a different swizzle atom for MN-major), halve
+// shared-memory traffic (the binding resource next to the MUFU pipe: every SS-mode MMA re-reads both operand tiles) and run
+// at twice the tf32 MMA rate.  dz is scaled into fp16's normal range.  Values beyond fp16 range (|x| > 65504) would saturate:
+// hidden activations and weights of this model family are O(1).
 //
-// Roofline: tensor pipe.  Algorithmic flops per team = 6*h*E.
+// Roofline: tensor pipe by the contract's accounting (algorithmic flops per team = 6*h*E); the resources that
+// actually bind are the MUFU pipe (2 transcendentals per logit: ex2, rcp), shared-memory bandwidth and issue slots.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -36,38 +41,35 @@ int ntf_loss_reduce_impl(cudaStream_t st, const float* part, int n, float scale,
 namespace {
 
 constexpr int TE = 128;  // experts per CTA tile (UMMA M of the forward / dW products)
-constexpr int TB = 64;   // teams per batch tile (UMMA N of the forward / dA products)
+constexpr int TB = 128;  // teams per batch tile (UMMA N of the forward / dA products)
 constexpr int HK = 128;  // hidden width this kernel is built for
 
-constexpr uint32_t W32_BYTES = TE * HK * 4;      // 64 KB : 4 k-chunks of [128 rows][128 B]
-constexpr uint32_t A32_BYTES = TB * HK * 4;      // 32 KB : 4 k-chunks of [ 64 rows][128 B]
-constexpr uint32_t W16_BYTES = TE * HK * 2;      // 32 KB : 2 k-chunks of [128 rows j][128 B]
-constexpr uint32_t A16_BYTES = TB * HK * 2;      // 16 KB : 2 k-chunks of [ 64 rows n][128 B]
-constexpr uint32_t DZ_BYTES = TE * TB * 2;       // 16 KB : [128 rows j][64 n halfs = 128 B]
-constexpr uint32_t OFF_W32 = 0;
-constexpr uint32_t OFF_A32 = OFF_W32 + W32_BYTES;           // 2 stages
-constexpr uint32_t OFF_W16 = OFF_A32 + 2 * A32_BYTES;
+constexpr uint32_t CHUNK = 128 * 128;            // one swizzle chunk: 128 rows x 128 bytes (64 halfs)
+constexpr uint32_t W16_BYTES = TE * HK * 2;      // 32 KB : 2 chunks (hidden 0-63 | 64-127) of [128 experts][128 B]
+constexpr uint32_t A16_BYTES = TB * HK * 2;      // 32 KB : 2 chunks (hidden 0-63 | 64-127) of [128 teams  ][128 B]
+constexpr uint32_t DZ_BYTES = TE * TB * 2;       // 32 KB : 2 chunks (teams  0-63 | 64-127) of [128 experts][128 B]
+constexpr uint32_t W32_BYTES = TE * HK * 4;      // 64 KB : 4 chunks (32 hidden each) of [128 experts][128 B], staged in the dz ring
+constexpr uint32_t OFF_W16 = 0;
 constexpr uint32_t OFF_A16 = OFF_W16 + W16_BYTES;           // 2 stages
-constexpr uint32_t OFF_DZ = OFF_A16 + 2 * A16_BYTES;        // 2 stages
-constexpr uint32_t OFF_PLANE = OFF_DZ + 2 * DZ_BYTES;       // special / target bit planes of the current tile: 2 x [128 experts][2 words]
-constexpr uint32_t PLANE_BYTES = TE * 2 * 4;                // 1 KB each
-constexpr uint32_t OFF_BAR = OFF_PLANE + 2 * PLANE_BYTES;   // mbarriers + tmem base
-constexpr uint32_t SMEM_TRAIN = OFF_BAR + 256;              // the dynamic window is declared 1024-byte aligned (checked at run time)
-constexpr uint32_t SMEM_INFER = OFF_W16 + 256;              // forward only: W32 + 2 x A32
-static_assert(SMEM_TRAIN <= 232448, "over the 227 KB shared memory limit");
+constexpr uint32_t OFF_DZ = OFF_A16 + 2 * A16_BYTES;        // 2 stages (first use: landing zone of the fp32 W tile)
+constexpr uint32_t OFF_PLANE = OFF_DZ + 2 * DZ_BYTES;       // 2 stages x (special | member) bit planes of a tile, [128 experts][4 words] each
+constexpr uint32_t PLANE_BYTES = TE * 4 * 4;                // 2 KB each
+constexpr uint32_t OFF_DAST = OFF_PLANE + 4 * PLANE_BYTES;  // dA staging: 2 x [128 teams][128 B] fp32 chunks on their way to the TMA reduce-add
+constexpr uint32_t OFF_BAR = OFF_DAST + 2 * CHUNK;          // mbarriers + tmem base + small reduction scratch
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 512;              // the dynamic window is declared 1024-byte aligned (checked at run time)
+static_assert(W32_BYTES <= 2 * DZ_BYTES, "the fp32 W tile is staged in the dz ring");
+static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared memory limit");
 
 // TMEM columns (fp32 accumulators, 128 lanes each)
-constexpr uint32_t TM_Z = 0;      // 2 x 64
-constexpr uint32_t TM_DW = 128;   // 128
-constexpr uint32_t TM_DA = 256;   // 2 x 64
+constexpr uint32_t TM_Z = 0;      // 2 x 128
+constexpr uint32_t TM_DW = 256;   // 128
+constexpr uint32_t TM_DA = 384;   // 128
 constexpr uint32_t TM_COLS = 512;
 
-enum { BAR_W = 0, BAR_A_FULL = 1, BAR_A_EMPTY = 3, BAR_Z_FULL = 5, BAR_Z_EMPTY = 7, BAR_DZ_FULL = 9, BAR_DZ_EMPTY = 11,
-       BAR_DA_FULL = 13, BAR_DA_EMPTY = 15, BAR_DW_FULL = 17, BAR_W16 = 18, BAR_H_FULL = 19, BAR_H_EMPTY = 21, BAR_SP_FULL = 23, BAR_SP_EMPTY = 24,
-       NUM_BARS = 25 };
-// A_* : fp32 activation tile ring (forward operand, released as soon as the forward product has read it)
-// H_* : fp16 activation tile ring (dW operand, released after the backward products)
-// SP_*: special / target bit planes of one tile (single stage: the epilogue copies its two words to registers and releases it at once)
+enum { BAR_W32 = 0, BAR_W16 = 1, BAR_A_FULL = 2, BAR_A_EMPTY = 4, BAR_Z_FULL = 6, BAR_Z_EMPTY = 8, BAR_DZ_FULL = 10, BAR_DZ_EMPTY = 12,
+       BAR_DA_FULL = 14, BAR_DA_EMPTY = 15, BAR_DW_FULL = 16, BAR_SP_FULL = 17, BAR_SP_EMPTY = 19, NUM_BARS = 21 };
+// A_*  : fp16 activation tile ring (operand of the forward and of the dW product; released after the tile's last product)
+// SP_* : special / member bit planes of a tile (2-stage ring, filled by 1-D bulk copies from the tile-transposed planes in HBM)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -98,15 +100,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mma_tf32(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void mma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
@@ -138,16 +140,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 constexpr uint32_t instr_desc(uint32_t fmt, uint32_t a_mn, uint32_t b_mn, uint32_t M, uint32_t N) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-constexpr uint32_t IDESC_FWD = instr_desc(2, 0, 0, TE, TB);   // Z^T  = W(K-major) . A(K-major)^T            tf32, K = hidden
-constexpr uint32_t IDESC_DW = instr_desc(0, 0, 1, TE, HK);    // dW  += dz^T(K-major: K = teams) . A16(MN-major)  f16
-constexpr uint32_t IDESC_DA = instr_desc(0, 1, 1, HK, TB);    // dA^T = W16(MN-major: M = hidden) . dz^T(MN-major: N = teams)  f16, K = experts
+
 
 struct TcArgs {
   const float* bias;          // [E]
-  const uint32_t* special;    // [B, pitch] or NULL
-  int pitch;
-  const int32_t* m_indptr;
-  const int32_t* m_indices;
+  const uint32_t* special_t;  // tile-transposed planes (ntf_special_tiles), or NULL: every weight tnw, every target 0
+  const uint32_t* member_t;
+  int Epad;                   // E rounded up to 128: row count of one tile slab of the planes
   int B, E;
   float tpw, tnw, scale;      // scale = loss_scale (1/B_global)
   float* dW;                  // [E,128] or NULL (validation step: forward + loss only)
@@ -160,8 +159,10 @@ struct TcArgs {
   int exp;                    // debug: experiment bits (NTF_TC_EXP): 1 = skip the dA reduction, 2 = skip the special-bit path
 };
 
-constexpr int NT = 512;  // warps 0-7: logits/loss epilogue, 8-11: dA epilogue, 12: TMA (fp32 ring), 13: MMA issuer, 14: TMA (fp16 ring), 15: special planes
-constexpr int WARP_TMA = 12, WARP_MMA = 13, WARP_TMA16 = 14, WARP_SP = 15;
+constexpr int EPI_WARPS = 16;
+constexpr int NT = 768;  // warps 0-15: logits/loss epilogue, 16-19: dA epilogue, 20: TMA, 21: MMA issuer, 22: special planes, 23: idle
+constexpr int WARP_DA = 16, WARP_TMA = 20, WARP_MMA = 21, WARP_SP = 22;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
 
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
@@ -179,41 +180,49 @@ __device__ __forceinline__ float lg2_approx(float x) {
   return r;
 }
 
+constexpr uint32_t IDESC_FWD = instr_desc(0, 0, 0, TE, TB);   // Z^T  = W16(K-major) . A16(K-major)^T                     K = hidden
+constexpr uint32_t IDESC_DW = instr_desc(0, 0, 1, TE, HK);    // dW  += dz^T(K-major: K = teams) . A16(MN-major: N = hidden)
+constexpr uint32_t IDESC_DA = instr_desc(0, 1, 1, TB, HK);    // dA   = dz(MN-major: M = teams) . W16(MN-major: N = hidden), K = experts
+
 // MODE 0: training / validation step.  MODE 1: inference scores P = sigmoid(lrelu(z)).
 template <int MODE>
-__global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ CUtensorMap map_w32, const __grid_constant__ CUtensorMap map_a32,
-                                                       const __grid_constant__ CUtensorMap map_a16, TcArgs g) {
+__global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ CUtensorMap map_w32, const __grid_constant__ CUtensorMap map_a16,
+                                                       const __grid_constant__ CUtensorMap map_da, TcArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   if ((sbase & 1023u) != 0u) __trap();  // the 128-byte swizzle atoms need a 1024-byte aligned base
   uint8_t* sgen = smem_raw;
-  constexpr uint32_t BAR_OFF = MODE == 0 ? OFF_BAR : OFF_W16;
-  const uint32_t bars = sbase + BAR_OFF;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + BAR_OFF + NUM_BARS * 8);
+  const uint32_t bars = sbase + OFF_BAR;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + OFF_BAR + NUM_BARS * 8);
   auto bar = [&](int i) { return bars + 8u * i; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[15 * 8 + 0] = clock64();  // kernel entry
+  if (g.timing && threadIdx.x == 0) {  // every CTA: start / end on the global timer (ns) and its SM
+    unsigned long long gt; unsigned smid;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    g.timing[128 + 3 * blockIdx.x] = (long long)gt; g.timing[128 + 3 * blockIdx.x + 2] = smid;
+  }
   const int e0 = blockIdx.x * TE;
   const int ntiles = (g.B + TB - 1) / TB;
   const bool train = MODE == 0 && g.dW != nullptr;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar(BAR_W), 1);
-    mbar_init(bar(BAR_W16), 384);
+    mbar_init(bar(BAR_W32), 1);
+    mbar_init(bar(BAR_W16), EPI_THREADS);
     mbar_init(bar(BAR_DW_FULL), 1);
-    mbar_init(bar(BAR_SP_FULL), 1);
-    mbar_init(bar(BAR_SP_EMPTY), 256);
+    mbar_init(bar(BAR_DA_FULL), 1);
+    mbar_init(bar(BAR_DA_EMPTY), 128);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(BAR_A_FULL + s), 1);
       mbar_init(bar(BAR_A_EMPTY + s), 1);
-      mbar_init(bar(BAR_H_FULL + s), 1);
-      mbar_init(bar(BAR_H_EMPTY + s), 1);
       mbar_init(bar(BAR_Z_FULL + s), 1);
-      mbar_init(bar(BAR_Z_EMPTY + s), 256);
-      mbar_init(bar(BAR_DZ_FULL + s), 256);
+      mbar_init(bar(BAR_Z_EMPTY + s), EPI_THREADS);
+      mbar_init(bar(BAR_DZ_FULL + s), EPI_THREADS);
       mbar_init(bar(BAR_DZ_EMPTY + s), 1);
-      mbar_init(bar(BAR_DA_FULL + s), 1);
-      mbar_init(bar(BAR_DA_EMPTY + s), 128);
+      mbar_init(bar(BAR_SP_FULL + s), 1);
+      mbar_init(bar(BAR_SP_EMPTY + s), EPI_THREADS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -225,71 +234,32 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[15 * 8 + 1] = clock64();  // barriers + TMEM ready
 
   if (warp == WARP_TMA) {
     // =========================================== TMA producer ===========================================
     if (lane == 0) {
-      mbar_expect_tx(bar(BAR_W), W32_BYTES);
-      for (int c = 0; c < 4; ++c) tma_load_2d(sbase + OFF_W32 + c * (TE * 128), &map_w32, c * 32, e0, bar(BAR_W));
+      mbar_expect_tx(bar(BAR_W32), W32_BYTES);
+      for (int c = 0; c < 4; ++c) tma_load_2d(sbase + OFF_DZ + c * CHUNK, &map_w32, c * 32, e0, bar(BAR_W32));
       for (int t = 0; t < ntiles; ++t) {
         const int s = t & 1;
         const uint32_t ph = (t >> 1) & 1;
         mbar_wait(bar(BAR_A_EMPTY + s), ph ^ 1);
-        mbar_expect_tx(bar(BAR_A_FULL + s), A32_BYTES);
-        for (int c = 0; c < 4; ++c) tma_load_2d(sbase + OFF_A32 + s * A32_BYTES + c * (TB * 128), &map_a32, c * 32, t * TB, bar(BAR_A_FULL + s));
-      }
-    }
-  } else if (warp == WARP_TMA16) {
-    if (lane == 0 && train) {
-      for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
-        mbar_wait(bar(BAR_H_EMPTY + s), ph ^ 1);
-        mbar_expect_tx(bar(BAR_H_FULL + s), A16_BYTES);
-        for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A16 + s * A16_BYTES + c * (TB * 128), &map_a16, c * 64, t * TB, bar(BAR_H_FULL + s));
+        mbar_expect_tx(bar(BAR_A_FULL + s), A16_BYTES);
+        for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A16 + s * A16_BYTES + c * CHUNK, &map_a16, c * 64, t * TB, bar(BAR_A_FULL + s));
       }
     }
   } else if (warp == WARP_SP) {
-    // ====== special-plane producer: bit planes [expert][team] of the tile, transposed from the [team][expert] plane in HBM ======
-    // plane_s bit = weight tpw (member or sampled negative), plane_y bit = target 1 (member).  Off the epilogue's critical path:
-    // the words of the next tile are in registers before the current one is released.
-    if (MODE == 0) {
-      uint32_t* plane_s = reinterpret_cast<uint32_t*>(sgen + OFF_PLANE);
-      uint32_t* plane_y = plane_s + TE * 2;
-      const int wi0 = e0 >> 5;
-      uint32_t w[8];
-      auto fetch = [&](int t) {
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int n = t * TB + r * 32 + lane;
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            w[r * 4 + c] = (g.special && !(g.exp & 2) && n < g.B && wi0 + c < g.pitch) ? __ldg(g.special + (size_t)n * g.pitch + wi0 + c) : 0u;
-        }
-      };
-      if (ntiles > 0) fetch(0);
+    // ====== special / member planes of the tile: two 2 KB bulk copies per tile from the tile-transposed planes (ntf_special_tiles) ======
+    if (MODE == 0 && lane == 0 && g.special_t && !(g.exp & 2)) {
       for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(bar(BAR_SP_EMPTY), (t & 1) ^ 1);
-        for (int i = lane; i < TE * 4; i += 32) plane_s[i] = 0u;  // both planes are contiguous
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int nl = r * 32 + lane;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t bits = w[r * 4 + c];
-            while (bits) {
-              const int jb = __ffs(bits) - 1;
-              bits &= bits - 1;
-              const int jl = c * 32 + jb;
-              atomicOr(&plane_s[jl * 2 + (nl >> 5)], 1u << (nl & 31));
-              if (is_member(g.m_indptr, g.m_indices, t * TB + nl, e0 + jl)) atomicOr(&plane_y[jl * 2 + (nl >> 5)], 1u << (nl & 31));
-            }
-          }
-        }
-        if (t + 1 < ntiles) fetch(t + 1);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_SP_FULL));
+        const int s = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        mbar_wait(bar(BAR_SP_EMPTY + s), ph ^ 1);
+        mbar_expect_tx(bar(BAR_SP_FULL + s), 2 * PLANE_BYTES);
+        const size_t off = ((size_t)t * g.Epad + e0) * 4;
+        bulk_load(sbase + OFF_PLANE + s * 2 * PLANE_BYTES, g.special_t + off, PLANE_BYTES, bar(BAR_SP_FULL + s));
+        bulk_load(sbase + OFF_PLANE + s * 2 * PLANE_BYTES + PLANE_BYTES, g.member_t + off, PLANE_BYTES, bar(BAR_SP_FULL + s));
       }
     }
   } else if (warp == WARP_MMA) {
@@ -304,112 +274,112 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 2] = clock64();
         tc_fence_after();
 #pragma unroll
-        for (int i = 0; i < HK / 8; ++i) {  // 16 k-steps of 8 tf32 (32 bytes) each: chunk i/4, 32-byte slice i%4 of the 128-byte swizzle row
-          const uint64_t da = smem_desc(sbase + OFF_W32 + (i >> 2) * (TE * 128) + (i & 3) * 32, 16, 1024);
-          const uint64_t db = smem_desc(sbase + OFF_A32 + s * A32_BYTES + (i >> 2) * (TB * 128) + (i & 3) * 32, 16, 1024);
-          mma_tf32(tmem + TM_Z + s * TB, da, db, IDESC_FWD, i > 0);
+        for (int i = 0; i < HK / 16; ++i) {  // 8 k-steps of 16 halfs (32 bytes): chunk i/4, 32-byte slice i%4 of the 128-byte swizzle row
+          const uint64_t da = smem_desc(sbase + OFF_W16 + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
+          const uint64_t db = smem_desc(sbase + OFF_A16 + s * A16_BYTES + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
+          mma_f16(tmem + TM_Z + s * TB, da, db, IDESC_FWD, i > 0);
         }
         tc_commit(bar(BAR_Z_FULL + s));
-        if (g.timing) {  // diagnostic mode serialises the pipeline: stamp the COMPLETION of the forward product
+        if (g.timing && (g.exp & 4)) {  // diagnostic mode 4 serialises the pipeline: stamp the COMPLETION of the forward product
           mbar_wait(bar(BAR_Z_FULL + s), ph);
           if (blockIdx.x == 0) g.timing[t * 8 + 3] = clock64();
         }
-        tc_commit(bar(BAR_A_EMPTY + s));  // the fp32 stage is free once the forward product has read it
+        if (!train) tc_commit(bar(BAR_A_EMPTY + s));  // forward-only: the stage is free once the forward product has read it
       };
-      mbar_wait(bar(BAR_W), 0);
+      mbar_wait(bar(BAR_W16), 0);
+      if (g.timing && blockIdx.x == 0) g.timing[15 * 8 + 2] = clock64();  // W image ready
       if (ntiles > 0) issue_fwd(0);
-      if (train) mbar_wait(bar(BAR_W16), 0);
       for (int t = 0; t < ntiles; ++t) {
         if (t + 1 < ntiles) issue_fwd(t + 1);  // keep the tensor pipe busy while the epilogue works on tile t
         if (!train) continue;
         const int s = t & 1;
         const uint32_t ph = (t >> 1) & 1;
         mbar_wait(bar(BAR_DZ_FULL + s), ph);
-        mbar_wait(bar(BAR_H_FULL + s), ph);
-        mbar_wait(bar(BAR_DA_EMPTY + s), ph ^ 1);
         tc_fence_after();
-        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 0] = clock64();  // (overwrites the producer stamp) backward products: issue starts
-        // dW[128 j x 128 k] += dz^T[j, n] . A16[n, k] : K = 64 teams = 4 steps of 16
+        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 0] = clock64();  // backward products: issue starts
+        // dW[128 j x 128 k] += dz^T[j, n] . A16[n, k] : K = 128 teams = 8 steps of 16
 #pragma unroll
         for (int i = 0; i < TB / 16; ++i) {
-          const uint64_t da = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + i * 32, 16, 1024);                        // K-major, K = teams
-          const uint64_t db = smem_desc(sbase + OFF_A16 + s * A16_BYTES + i * 2048, TB * 128, 1024);               // MN-major, N = hidden
+          const uint64_t da = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);   // K-major, K = teams
+          const uint64_t db = smem_desc(sbase + OFF_A16 + s * A16_BYTES + i * 2048, CHUNK, 1024);                      // MN-major, N = hidden
           mma_f16(tmem + TM_DW, da, db, IDESC_DW, (t > 0 || i > 0));
         }
-        // dA^T[128 k x 64 n] = W16^T[k, j] . dz[j, n] : K = 128 experts = 8 steps of 16
+        // dA[128 n x 128 k] = dz[j, n]^T . W16[j, k] : K = 128 experts = 8 steps of 16
+        mbar_wait(bar(BAR_DA_EMPTY), (t & 1) ^ 1);
+        tc_fence_after();
 #pragma unroll
         for (int i = 0; i < TE / 16; ++i) {
-          const uint64_t da = smem_desc(sbase + OFF_W16 + i * 2048, TE * 128, 1024);                               // MN-major, M = hidden
-          const uint64_t db = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + i * 2048, 0, 1024);                        // MN-major, N = teams
-          mma_f16(tmem + TM_DA + s * TB, da, db, IDESC_DA, i > 0);
+          const uint64_t da = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + i * 2048, CHUNK, 1024);                        // MN-major, M = teams
+          const uint64_t db = smem_desc(sbase + OFF_W16 + i * 2048, CHUNK, 1024);                                      // MN-major, N = hidden
+          mma_f16(tmem + TM_DA, da, db, IDESC_DA, i > 0);
         }
-        tc_commit(bar(BAR_DA_FULL + s));
-        if (g.timing) {
-          mbar_wait(bar(BAR_DA_FULL + s), ph);
+        tc_commit(bar(BAR_DA_FULL));
+        if (g.timing && (g.exp & 4)) {
+          mbar_wait(bar(BAR_DA_FULL), t & 1);
           if (blockIdx.x == 0) g.timing[t * 8 + 7] = clock64();  // backward products complete
         }
         tc_commit(bar(BAR_DZ_EMPTY + s));
-        tc_commit(bar(BAR_H_EMPTY + s));
+        tc_commit(bar(BAR_A_EMPTY + s));
         if (t == ntiles - 1) tc_commit(bar(BAR_DW_FULL));
       }
     }
-  } else if (warp < 8) {
-    // ====================== logits / loss epilogue: thread = (expert jl, half hh of the tile's 64 teams) ======================
+  } else if (warp < EPI_WARPS) {
+    // ====================== logits / loss epilogue: thread = (expert jl, block cb of 32 of the tile's 128 teams) ======================
     const int jl = threadIdx.x & 127;  // TMEM lane = local expert
-    const int hh = threadIdx.x >> 7;   // teams [32*hh, 32*hh+32) of the tile
+    const int cb = threadIdx.x >> 7;   // teams [32*cb, 32*cb+32) of the tile
     const int e = e0 + jl;
     const bool e_ok = e < g.E;
     const float bj = e_ok ? __ldg(g.bias + e) : 0.f;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    if (train) {
-      // fp16 image of the W tile for the dA product (MN-major: rows = experts, 64 hidden units per 128-byte row)
-      mbar_wait(bar(BAR_W), 0);
-#pragma unroll 4
-      for (int uu = 0; uu < HK / 16; ++uu) {  // this half's 8 units of 8 hidden values
-        const int k = (hh * 8 + uu) * 8;
-        const uint8_t* src = sgen + OFF_W32 + (k >> 5) * (TE * 128) + jl * 128;
-        const int u32a = ((k & 31) >> 2), u32b = u32a + 1;
-        const float4 f0 = *reinterpret_cast<const float4*>(src + ((u32a ^ (jl & 7)) << 4));
-        const float4 f1 = *reinterpret_cast<const float4*>(src + ((u32b ^ (jl & 7)) << 4));
+    {
+      // fp16 image of the W tile: rows = experts, 64 hidden units per 128-byte row, 2 chunks.  This thread converts hidden units
+      // [32*cb, 32*cb+32) of its expert: chunk cb of the fp32 landing zone -> half of a row of chunk cb/2 of the image.
+      mbar_wait(bar(BAR_W32), 0);
+      const uint8_t* src = sgen + OFF_DZ + cb * CHUNK + jl * 128;
+      uint8_t* dst = sgen + OFF_W16 + (cb >> 1) * CHUNK + jl * 128;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {  // 8 hidden values -> one 16-byte unit
+        const float4 f0 = *reinterpret_cast<const float4*>(src + (((2 * m) ^ (jl & 7)) << 4));
+        const float4 f1 = *reinterpret_cast<const float4*>(src + (((2 * m + 1) ^ (jl & 7)) << 4));
         __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f0.z, f0.w);
         __half2 h2 = __floats2half2_rn(f1.x, f1.y), h3 = __floats2half2_rn(f1.z, f1.w);
         uint4 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
         pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-        uint8_t* dst = sgen + OFF_W16 + (k >> 6) * (TE * 128) + jl * 128 + ((((k & 63) >> 3) ^ (jl & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = pk;
+        *reinterpret_cast<uint4*>(dst + (((4 * (cb & 1) + m) ^ (jl & 7)) << 4)) = pk;
       }
       fence_proxy_async();
+      mbar_arrive(bar(BAR_W16));
     }
-    if (MODE == 0) mbar_arrive(bar(BAR_W16));  // (also counted for validation steps; the MMA thread only waits when training)
     float acc_lin = 0.f, acc_lg = 0.f, loss_sp = 0.f, db_acc = 0.f;  // dense loss = tnw*ln2*(acc_lg - acc_lin): sums of lg2(1+e) and of t = -c*x
     // dz is kept as w*(sigmoid-y)*slope, i.e. true dz / loss_scale; experts past E (last tile) get zero gradient and their loss is dropped below
     const float c_pos = e_ok ? g.tnw : 0.f, c_neg = e_ok ? g.tnw * NTF_LRELU_SLOPE : 0.f;
-    const uint32_t* plane_s = reinterpret_cast<const uint32_t*>(sgen + OFF_PLANE);
-    const uint32_t* plane_y = plane_s + TE * 2;
+    const bool has_sp = MODE == 0 && g.special_t && !(g.exp & 2);
     constexpr float LOG2E = 1.4426950408889634f;
     const float kb1 = -LOG2E * bj, kb2 = -LOG2E * NTF_LRELU_SLOPE * bj;
     for (int t = 0; t < ntiles; ++t) {
       const int s = t & 1;
       const uint32_t ph = (t >> 1) & 1;
-      const int n0 = t * TB + hh * 32;  // first team of this thread's half tile
+      const int n0 = t * TB + cb * 32;  // first team of this thread's block
       // bit n of S / Y: (team n0+n, my expert) carries weight tpw / target 1 -- two words from the tile's planes, then the stage is free
       uint32_t S = 0, Y = 0;
-      if (MODE == 0) {
-        mbar_wait(bar(BAR_SP_FULL), t & 1);
-        S = plane_s[jl * 2 + hh];
-        Y = plane_y[jl * 2 + hh];
-        mbar_arrive(bar(BAR_SP_EMPTY));
+      if (has_sp) {
+        const uint32_t* plane = reinterpret_cast<const uint32_t*>(sgen + OFF_PLANE + s * 2 * PLANE_BYTES);
+        mbar_wait(bar(BAR_SP_FULL + s), ph);
+        S = plane[jl * 4 + cb];
+        Y = plane[TE * 4 + jl * 4 + cb];
+        mbar_arrive(bar(BAR_SP_EMPTY + s));
+        if (!e_ok) S = 0;
       }
       mbar_wait(bar(BAR_Z_FULL + s), ph);
       if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[t * 8 + 4] = clock64();
       tc_fence_after();
       float z[32];
-      tmem_ld32(tmem + lane_base + TM_Z + s * TB + hh * 32, z);
+      tmem_ld32(tmem + lane_base + TM_Z + s * TB + cb * 32, z);
       tc_fence_before();
       mbar_arrive(bar(BAR_Z_EMPTY + s));
       if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[t * 8 + 5] = clock64();
-      const int nrem = g.B - n0;  // teams of this half tile that exist
+      const int nrem = g.B - n0;  // teams of this block that exist
       if (MODE == 1) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -418,7 +388,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
           for (int q = 0; q < 8; ++q) {
             const float zz = z[u * 8 + q] + bj;
             const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
-            const float ex = ex2_approx(fabsf(x) * -1.4426950408889634f);
+            const float ex = ex2_approx(fabsf(x) * -LOG2E);
             const float r = rcp_approx(1.f + ex);
             p[q] = zz > 0.f ? r : ex * r;
           }
@@ -434,8 +404,12 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         for (int n = 0; n < 32; ++n)
           if (e_ok && n < nrem) g.Zdbg[(size_t)(n0 + n) * g.E + e] = z[n] + bj;
       }
-      if (train) mbar_wait(bar(BAR_DZ_EMPTY + s), ph ^ 1);
-      uint8_t* dzrow = sgen + OFF_DZ + s * DZ_BYTES + jl * 128;
+      if (train) {
+        if (t == 0) mbar_wait(bar(BAR_W16), 0);  // every thread is done with the fp32 landing zone before the dz ring is written
+        mbar_wait(bar(BAR_DZ_EMPTY + s), ph ^ 1);
+      }
+      uint8_t* dzrow = sgen + OFF_DZ + s * DZ_BYTES + (cb >> 1) * CHUNK + jl * 128;
+      const int unit0 = 4 * (cb & 1);
       // Dense pass: every element as (target 0, weight tnw):  loss = softplus(x) = x + ln(1 + exp(-x)),  dz = tnw*sigmoid(x)*slope,
       // x = lrelu(z + b).  With c = log2(e):  t = -c*x = min(-c*(z+b), -0.01c*(z+b))  (two FFMAs with the bias folded in, one FMNMX),
       // e = 2^t, den = 1 + e, sigmoid(x) = 1/den, softplus(x) = (-t + lg2(den))*ln2.  lg2 is taken once per 8 elements, of the product
@@ -449,12 +423,12 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         for (int q = 0; q < 8; ++q) {
           const float t1 = fmaf(z[u * 8 + q], -LOG2E, kb1);
           const float t2 = fmaf(z[u * 8 + q], -LOG2E * NTF_LRELU_SLOPE, kb2);
-          float t = fminf(t1, t2);
-          const float ex = ex2_approx(t);
+          float tt = fminf(t1, t2);
+          const float ex = ex2_approx(tt);
           den[q] = 1.f + ex;
           gz[q] = rcp_approx(den[q]) * (t1 < 0.f ? c_pos : c_neg);
-          if (decltype(masked)::value && u * 8 + q >= nrem) { gz[q] = 0.f; t = 0.f; den[q] = 1.f; }  // teams past the end of the batch
-          acc_lin += t;
+          if (decltype(masked)::value && u * 8 + q >= nrem) { gz[q] = 0.f; tt = 0.f; den[q] = 1.f; }  // teams past the end of the batch
+          acc_lin += tt;
           prod *= den[q];
           db_acc += gz[q];
         }
@@ -470,7 +444,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
           uint4 pk;
           pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
           pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(dzrow + (((hh * 4 + u) ^ (jl & 7)) << 4)) = pk;
+          *reinterpret_cast<uint4*>(dzrow + (((unit0 + u) ^ (jl & 7)) << 4)) = pk;
         }
       };
       if (nrem >= 32) {  // (warp-uniform)
@@ -481,29 +455,43 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         for (int u = 0; u < 4; ++u) dense8(u, std::true_type{});
       }
       // Sparse fix-up (rare): members of the team and sampled negatives carry weight tpw and the member target.  Their dense
-      // contribution is taken back out and the fp16 gradient already staged in shared memory is overwritten.
-      while (S) {
-        const int i = __ffs(S) - 1;
-        S &= S - 1;
+      // contribution is taken back out and the fp16 gradient already staged in shared memory is overwritten.  Popular experts
+      // collect many such teams (Zipf), so the work is done warp-wide: for every lane (expert) that has any, its 32 logits are
+      // transposed across the warp by shuffles, lane i handles team i, and the corrections return by fixed-order shuffle sums.
+      unsigned todo = __ballot_sync(0xffffffffu, S != 0u);
+      while (todo) {
+        const int L = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t S_L = __shfl_sync(0xffffffffu, S, L), Y_L = __shfl_sync(0xffffffffu, Y, L);
+        const float bj_L = __shfl_sync(0xffffffffu, bj, L);
         float zi = 0.f;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) zi = (k == i) ? z[k] : zi;
-        asm volatile("" : "+f"(zi));  // keep this path from pinning the dense pass's temporaries in registers
-        const float zz = zi + bj;
+        for (int k = 0; k < 32; ++k) {
+          const float v = __shfl_sync(0xffffffffu, z[k], L);
+          zi = (k == lane) ? v : zi;
+        }
+        const bool mine = (S_L >> lane) & 1u;  // (team n0 + lane, expert of lane L); bits past the batch end / past E are never set
+        const float zz = zi + bj_L;
         const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
-        const float t = -LOG2E * x;
-        const float exs = ex2_approx(t), dens = 1.f + exs;          // the dense pass's (signed) terms, taken back out
-        const float g_dense = rcp_approx(dens) * (zz > 0.f ? c_pos : c_neg);
-        acc_lin -= t;
-        acc_lg -= lg2_approx(dens);
+        const float tt = -LOG2E * x;
+        const float exs = ex2_approx(tt), dens = 1.f + exs;          // the dense pass's (signed) terms, taken back out
+        const float g_dense = rcp_approx(dens) * (zz > 0.f ? g.tnw : g.tnw * NTF_LRELU_SLOPE);
         const float ex = ex2_approx(fabsf(x) * -LOG2E);               // stable form for the real term
         const float den = 1.f + ex, lg = lg2_approx(den), r = rcp_approx(den);
         const float sig = x > 0.f ? r : ex * r;
-        const float yf = ((Y >> i) & 1u) ? 1.f : 0.f;
+        const float yf = ((Y_L >> lane) & 1u) ? 1.f : 0.f;
         const float g_sp = g.tpw * (sig - yf) * (zz > 0.f ? 1.f : NTF_LRELU_SLOPE);
-        loss_sp += g.tpw * ((1.f - yf) * x + fmaxf(-x, 0.f) + 0.6931471805599453f * lg);
-        db_acc += g_sp - g_dense;
-        if (train) *reinterpret_cast<__half*>(dzrow + (((hh * 4 + (i >> 3)) ^ (jl & 7)) << 4) + (i & 7) * 2) = __float2half_rn(g_sp);
+        float d_lin = mine ? -tt : 0.f, d_lg = mine ? -lg2_approx(dens) : 0.f;
+        float d_sp = mine ? g.tpw * ((1.f - yf) * x + fmaxf(-x, 0.f) + 0.6931471805599453f * lg) : 0.f;
+        float d_db = mine ? g_sp - g_dense : 0.f;
+        __syncwarp();
+        if (mine && train) {
+          const int jl_L = jl - lane + L;
+          uint8_t* rowL = sgen + OFF_DZ + s * DZ_BYTES + (cb >> 1) * CHUNK + jl_L * 128;
+          *reinterpret_cast<__half*>(rowL + (((unit0 + (lane >> 3)) ^ (jl_L & 7)) << 4) + (lane & 7) * 2) = __float2half_rn(g_sp);
+        }
+        d_lin = warp_sum(d_lin); d_lg = warp_sum(d_lg); d_sp = warp_sum(d_sp); d_db = warp_sum(d_db);
+        if (lane == L) { acc_lin += d_lin; acc_lg += d_lg; loss_sp += d_sp; db_acc += d_db; }
       }
       if (train) {
         fence_proxy_async();
@@ -512,63 +500,84 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[t * 8 + 6] = clock64();
     }
     if (MODE == 0) {
-      // loss partial of this CTA and db: fixed-order combines (shuffle tree, then warps / halves in order)
-      float* red = reinterpret_cast<float*>(sgen + BAR_OFF + NUM_BARS * 8 + 16);   // [8]
-      float* dbs = reinterpret_cast<float*>(sgen + OFF_DZ);                          // [128], the dz stages are idle by now ...
+      // loss partial of this CTA and db: fixed-order combines (shuffle tree, then warps / team blocks in order)
+      float* red = reinterpret_cast<float*>(sgen + OFF_BAR + NUM_BARS * 8 + 16);   // [16]
+      float* dbs = reinterpret_cast<float*>(sgen + OFF_DZ);                          // [3][128], the dz stages are idle by now ...
       if (train) mbar_wait(bar(BAR_DW_FULL), 0);                                     // ... once every MMA that read them has completed
+      if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[15 * 8 + 3] = clock64();  // all products complete
       const float tot = warp_sum(e_ok ? g.tnw * 0.6931471805599453f * (acc_lg - acc_lin) + loss_sp : 0.f);
       if (lane == 0) red[warp] = tot;
-      if (train && hh == 1) dbs[jl] = db_acc;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (threadIdx.x == 0) g.loss_part[blockIdx.x] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
-      if (train) {
-        if (hh == 0 && e_ok) g.db[e] = (db_acc + dbs[jl]) * g.scale;
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {  // this half's 64 of the 128 dW columns
-          float v[32];
-          tmem_ld32(tmem + lane_base + TM_DW + hh * 64 + c * 32, v);
-          if (e_ok) {
-            float4* dst = reinterpret_cast<float4*>(g.dW + (size_t)e * HK + hh * 64 + c * 32);
+      if (train && cb > 0) dbs[(cb - 1) * TE + jl] = db_acc;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (threadIdx.x == 0) {
+        float l = 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q] * g.scale, v[4 * q + 1] * g.scale, v[4 * q + 2] * g.scale, v[4 * q + 3] * g.scale);
-          }
+        for (int q = 0; q < EPI_WARPS; ++q) l += red[q];
+        g.loss_part[blockIdx.x] = l;
+      }
+      if (train) {
+        if (cb == 0 && e_ok) g.db[e] = (((db_acc + dbs[jl]) + dbs[TE + jl]) + dbs[2 * TE + jl]) * g.scale;
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(tmem + lane_base + TM_DW + cb * 32, v);  // this thread's 32 of the 128 dW columns of its expert
+        // through shared memory (the idle activation ring; 16-byte units XOR-swizzled by row) so that the 64 KB tile goes out as
+        // fully coalesced 512-byte rows
+        float4* stage = reinterpret_cast<float4*>(sgen + OFF_A16);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          stage[jl * 32 + ((cb * 8 + q) ^ (jl & 31))] = make_float4(v[4 * q] * g.scale, v[4 * q + 1] * g.scale, v[4 * q + 2] * g.scale, v[4 * q + 3] * g.scale);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < TE / EPI_WARPS; ++i) {
+          const int r = warp * (TE / EPI_WARPS) + i;
+          if (e0 + r < g.E) reinterpret_cast<float4*>(g.dW + (size_t)(e0 + r) * HK)[lane] = stage[r * 32 + (lane ^ (r & 31))];
         }
       }
     }
-  } else {
-    // =========================================== dA epilogue: thread = hidden unit ===========================================
+  } else if (warp >= WARP_DA && warp < WARP_DA + 4) {
+    // ====== dA epilogue: thread = team.  TMEM -> regs -> swizzled fp32 chunks in shared memory -> TMA reduce-add into dA[B,128] ======
+    // (the sum over expert tiles = across CTAs happens in L2, issued by the TMA unit: no SM-side atomics; rows past B are clipped)
     if (train) {
-      const int k = threadIdx.x - 256;  // 0..127 = TMEM lane = hidden unit
+      const int r = threadIdx.x - WARP_DA * 32;  // 0..127 = TMEM lane = team of the tile
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-      mbar_arrive(bar(BAR_W16));  // these warps take the rest of the arrival count (the image is written by warps 0-7)
       for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
-        const int n0 = t * TB;
-        mbar_wait(bar(BAR_DA_FULL + s), ph);
+        mbar_wait(bar(BAR_DA_FULL), t & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < TB / 32; ++c) {
+        for (int c = 0; c < HK / 32; ++c) {  // 32 hidden units = one 128-byte chunk row
+          const uint32_t buf = OFF_DAST + ((t * (HK / 32) + c) & 1) * CHUNK;
+          if (r == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the reduce that last read this buffer is done with it
+          asm volatile("bar.sync 2, 128;" ::: "memory");
           float v[32];
-          tmem_ld32(tmem + lane_base + TM_DA + s * TB + c * 32, v);
-          if (c == TB / 32 - 1) {
+          tmem_ld32(tmem + lane_base + TM_DA + c * 32, v);
+          if (c == HK / 32 - 1) {
             tc_fence_before();
-            mbar_arrive(bar(BAR_DA_EMPTY + s));
+            mbar_arrive(bar(BAR_DA_EMPTY));
           }
+          uint8_t* row = sgen + buf + r * 128;
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const int n = n0 + c * 32 + q;
-            if (n < g.B && !(g.exp & 1)) atomicAdd(g.dA + (size_t)n * HK + k, v[q] * g.scale);  // red.global.add.f32, 128 B per warp
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(row + ((q ^ (r & 7)) << 4)) = make_float4(v[4 * q] * g.scale, v[4 * q + 1] * g.scale, v[4 * q + 2] * g.scale, v[4 * q + 3] * g.scale);
+          fence_proxy_async();
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (r == 0 && !(g.exp & 1)) {
+            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                         ::"l"(reinterpret_cast<uint64_t>(&map_da)), "r"(c * 32), "r"(t * TB), "r"(sbase + buf) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
       }
-    } else if (MODE == 0) {
-      mbar_arrive(bar(BAR_W16));
+      if (r == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[15 * 8 + 4] = clock64();  // drained
+  if (g.timing && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    g.timing[128 + 3 * blockIdx.x + 1] = (long long)gt;
+  }
   if (warp == WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
@@ -602,52 +611,63 @@ size_t ntf_out_train_tc_workspace_bytes(const ntf_ctx*, int B, int h, int E, int
   return align_up((size_t)B * h * sizeof(__half), 256) + align_up((size_t)cdiv(E, TE) * sizeof(float), 256);
 }
 
-int ntf_out_train_tc(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a, void* workspace, size_t workspace_bytes) {
-  NTF_REQUIRE(a->h == HK, NTF_ERR_UNSUPPORTED, "out_train(tf32): hidden width %d (kernel is built for %d)", a->h, HK);
-  NTF_REQUIRE(workspace_bytes >= ntf_out_train_tc_workspace_bytes(ctx, a->B, a->h, a->E, 0), NTF_ERR_WORKSPACE, "out_train(tf32): workspace too small");
-  NTF_REQUIRE((((uintptr_t)a->A | (uintptr_t)a->W) & 15) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): A and W must be 16-byte aligned");
-  const bool train = a->dW != nullptr;
-  NTF_REQUIRE(!train || (a->db && a->dA), NTF_ERR_BAD_ARG, "out_train(tf32): training needs dW, db and dA");
-  __half* A16 = (__half*)workspace;
-  float* loss_part = (float*)((char*)workspace + align_up((size_t)a->B * a->h * sizeof(__half), 256));
-  const int nct = cdiv(a->E, TE);
-  CUtensorMap mw, ma, mh;
-  int rc;
-  if ((rc = make_map(ctx, &mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->W, (uint64_t)a->E, HK, TE, 32))) return rc;
-  if ((rc = make_map(ctx, &ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->A, (uint64_t)a->B, HK, TB, 32))) return rc;
-  if ((rc = make_map(ctx, &mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)a->B, HK, TB, 64))) return rc;
-  if (train) {
-    NTF_COUNT_LAUNCH; to_half_kernel<<<min(cdiv(a->B * a->h, 256), ctx->sm_count * 4), 256, 0, st>>>(a->A, (size_t)a->B * a->h, A16);
-    NTF_CUDA(cudaMemsetAsync(a->dA, 0, (size_t)a->B * a->h * sizeof(float), st));
-  }
-  TcArgs g{};
-  g.bias = a->b; g.special = a->special; g.pitch = a->pitch_words; g.m_indptr = a->m_indptr; g.m_indices = a->m_indices;
-  g.B = a->B; g.E = a->E; g.tpw = a->tpw; g.tnw = a->tnw; g.scale = a->loss_scale;
-  g.dW = a->dW; g.db = a->db; g.dA = a->dA; g.loss_part = loss_part; g.P = nullptr;
+static void tc_debug_hooks(TcArgs& g) {
   const char* dbg = getenv("NTF_TC_ZDBG");  // debug hook used by tests/test_gpu_tc.py: address of a [B,E] device buffer for the raw logits
   g.Zdbg = dbg ? (float*)(uintptr_t)strtoull(dbg, nullptr, 0) : nullptr;
   const char* tim = getenv("NTF_TC_TIMING");
   g.timing = tim ? (long long*)(uintptr_t)strtoull(tim, nullptr, 0) : nullptr;
   const char* ex = getenv("NTF_TC_EXP");
   g.exp = ex ? atoi(ex) : 0;
-  NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TRAIN));
-  NTF_COUNT_LAUNCH; out_tc_kernel<0><<<nct, NT, SMEM_TRAIN, st>>>(mw, ma, mh, g);
+}
+
+int ntf_out_train_tc(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a, void* workspace, size_t workspace_bytes) {
+  NTF_REQUIRE(a->h == HK, NTF_ERR_UNSUPPORTED, "out_train(tf32): hidden width %d (kernel is built for %d)", a->h, HK);
+  NTF_REQUIRE(workspace_bytes >= ntf_out_train_tc_workspace_bytes(ctx, a->B, a->h, a->E, 0), NTF_ERR_WORKSPACE, "out_train(tf32): workspace too small");
+  NTF_REQUIRE((((uintptr_t)a->A | (uintptr_t)a->W) & 15) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): A and W must be 16-byte aligned");
+  const bool train = a->dW != nullptr;
+  NTF_REQUIRE(!train || (a->db && a->dA), NTF_ERR_BAD_ARG, "out_train(tf32): training needs dW, db and dA");
+  NTF_REQUIRE(!train || (((uintptr_t)a->dA | (uintptr_t)a->dW) & 15) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): dA and dW must be 16-byte aligned");
+  NTF_REQUIRE((a->special_t == nullptr) == (a->member_t == nullptr), NTF_ERR_BAD_ARG, "out_train(tf32): special_t and member_t come together");
+  NTF_REQUIRE(a->special_t || !a->special, NTF_ERR_BAD_ARG, "out_train(tf32): the tensor-core kernel reads the tile-transposed planes (ntf_special_tiles), not `special`");
+  __half* A16 = (__half*)workspace;
+  float* loss_part = (float*)((char*)workspace + align_up((size_t)a->B * a->h * sizeof(__half), 256));
+  const int nct = cdiv(a->E, TE);
+  CUtensorMap mw, mh, mda;
+  int rc;
+  if ((rc = make_map(ctx, &mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->W, (uint64_t)a->E, HK, TE, 32))) return rc;
+  if ((rc = make_map(ctx, &mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)a->B, HK, TB, 64))) return rc;
+  if ((rc = make_map(ctx, &mda, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, train ? (const void*)a->dA : (const void*)a->W, (uint64_t)(train ? a->B : a->E), HK, TB, 32))) return rc;
+  NTF_COUNT_LAUNCH; to_half_kernel<<<min(cdiv(a->B * a->h, 256), ctx->sm_count * 4), 256, 0, st>>>(a->A, (size_t)a->B * a->h, A16);
+  if (train) NTF_CUDA(cudaMemsetAsync(a->dA, 0, (size_t)a->B * a->h * sizeof(float), st));
+  TcArgs g{};
+  g.bias = a->b; g.special_t = a->special_t; g.member_t = a->member_t; g.Epad = cdiv(a->E, TE) * TE;
+  g.B = a->B; g.E = a->E; g.tpw = a->tpw; g.tnw = a->tnw; g.scale = a->loss_scale;
+  g.dW = a->dW; g.db = a->db; g.dA = a->dA; g.loss_part = loss_part; g.P = nullptr;
+  tc_debug_hooks(g);
+  NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  NTF_COUNT_LAUNCH; out_tc_kernel<0><<<nct, NT, SMEM_BYTES, st>>>(mw, mh, mda, g);
   NTF_LAUNCH_CHECK();
   return ntf_loss_reduce_impl(st, loss_part, nct, a->loss_scale, a->loss_out);
 }
 
-int ntf_infer_scores_tc(ntf_ctx* ctx, cudaStream_t st, const float* A, const float* W, const float* b, int B, int h, int E, float* P) {
+size_t ntf_infer_scores_tc_workspace_bytes(int B, int h) { return align_up((size_t)B * h * sizeof(__half), 256); }
+
+int ntf_infer_scores_tc(ntf_ctx* ctx, cudaStream_t st, const float* A, const float* W, const float* b, int B, int h, int E, float* P,
+                        void* workspace, size_t workspace_bytes) {
   NTF_REQUIRE(h == HK, NTF_ERR_UNSUPPORTED, "infer_scores(tf32): hidden width %d (kernel is built for %d)", h, HK);
-  CUtensorMap mw, ma;
+  NTF_REQUIRE(workspace && workspace_bytes >= ntf_infer_scores_tc_workspace_bytes(B, h), NTF_ERR_WORKSPACE, "infer_scores(tf32): workspace too small");
+  __half* A16 = (__half*)workspace;
+  CUtensorMap mw, mh;
   int rc;
   if ((rc = make_map(ctx, &mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, W, (uint64_t)E, HK, TE, 32))) return rc;
-  if ((rc = make_map(ctx, &ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, (uint64_t)B, HK, TB, 32))) return rc;
+  if ((rc = make_map(ctx, &mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)B, HK, TB, 64))) return rc;
+  NTF_COUNT_LAUNCH; to_half_kernel<<<min(cdiv(B * h, 256), ctx->sm_count * 4), 256, 0, st>>>(A, (size_t)B * h, A16);
   TcArgs g{};
   g.bias = b; g.B = B; g.E = E; g.P = P;
-  const char* tim = getenv("NTF_TC_TIMING");
-  g.timing = tim ? (long long*)(uintptr_t)strtoull(tim, nullptr, 0) : nullptr;
-  NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_INFER));
-  NTF_COUNT_LAUNCH; out_tc_kernel<1><<<cdiv(E, TE), NT, SMEM_INFER, st>>>(mw, ma, ma, g);
+  tc_debug_hooks(g);
+  g.Zdbg = nullptr;
+  NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  NTF_COUNT_LAUNCH; out_tc_kernel<1><<<cdiv(E, TE), NT, SMEM_BYTES, st>>>(mw, mh, mw, g);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

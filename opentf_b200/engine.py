@@ -159,6 +159,10 @@ class Engine:
         self.dz = [torch.empty(B, h, dtype=f32, device=dev) for h in self.hidden]
         self.pitch = _round_up(self.E, 32) // 32
         self.special = torch.zeros(B, self.pitch, dtype=torch.int32, device=dev)
+        if self.precision == _lib.NTF_TF32:  # the tensor-core kernel reads the same sets as tile-transposed planes
+            words = ops.special_tiles_bytes(B, self.E) // 4
+            self.special_t = torch.zeros(words, dtype=torch.int32, device=dev)
+            self.member_t = torch.zeros(words, dtype=torch.int32, device=dev)
         self.neg = torch.full((B, max(1, self.ns)), -1, dtype=torch.int32, device=dev)
         self.counts = torch.zeros(self.E, dtype=torch.int32, device=dev)
         self.cdf = torch.zeros(self.E, dtype=torch.int32, device=dev)
@@ -267,10 +271,15 @@ class Engine:
         neg = self._sample(sp, b0, B, neg_host, gbatch)
         mptr = sp.m_indptr.data_ptr() + 4 * b0
         ns = 0 if neg is None else neg.shape[1]
-        ops.special_bits(1, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
+        tc = self.precision == _lib.NTF_TF32
         a = OutTrainArgs()
+        if tc:
+            ops.special_tiles(1, B, mptr, sp.m_indices, neg, ns, self.E, self.special_t, self.member_t)
+            a.special_t, a.member_t = self.special_t.data_ptr(), self.member_t.data_ptr()
+        else:
+            ops.special_bits(1, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
+            a.special, a.pitch_words = self.special.data_ptr(), self.pitch
         a.A, a.W, a.b = self.act[-1].data_ptr(), self.view(f'layers.{Lo}.weight').data_ptr(), self.view(f'layers.{Lo}.bias').data_ptr()
-        a.special, a.pitch_words = self.special.data_ptr(), self.pitch
         a.m_indptr, a.m_indices = mptr, sp.m_indices.data_ptr()
         a.B, a.h, a.E = B, h_last, self.E
         a.tpw, a.tnw, a.loss_scale = self.tpw, self.tnw, (1.0 / B if loss_scale is None else loss_scale)
@@ -279,7 +288,8 @@ class Engine:
             a.dW, a.db = self.view(f'layers.{Lo}.weight', self.grads).data_ptr(), self.view(f'layers.{Lo}.bias', self.grads).data_ptr()
             a.dA = self.dact[-1].data_ptr()
         ops.out_train(self.dev_index, self.precision, a, self.ws)
-        ops.special_bits(0, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
+        if tc: ops.special_tiles(0, B, mptr, sp.m_indices, neg, ns, self.E, self.special_t, self.member_t)
+        else: ops.special_bits(0, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
         self.global_step += 1
         if not train: return
         for i in range(self.L - 2, 0, -1):  # hidden dense layers

@@ -98,6 +98,16 @@ def special_bits(op, B, m_indptr_ptr, m_indices, neg, ns, E, special, pitch):
           'ntf_special_bits')
 
 
+def special_tiles_bytes(B, E):
+    return lib().ntf_special_tiles_bytes(B, E)
+
+
+def special_tiles(op, B, m_indptr_ptr, m_indices, neg, ns, E, special_t, member_t):
+    d = _dev(m_indices)
+    check(lib().ntf_special_tiles(_lib.ctx(d), _stream(d), op, B, m_indptr_ptr, _p(m_indices, I32), _p(neg, I32), ns, E, _p(special_t), _p(member_t)),
+          'ntf_special_tiles')
+
+
 def out_train_workspace_bytes(dev, precision, B, h, E, flipout):
     return lib().ntf_out_train_workspace_bytes(_lib.ctx(dev), precision, B, h, E, int(flipout))
 

@@ -217,6 +217,33 @@ def test_special_bits_set_and_clear(ops):
     assert int(plane.abs().sum()) == 0
 
 
+@pytest.mark.parametrize('B,E', [(50, 1000), (300, 129), (1, 5)])
+def test_special_tiles_layout_set_and_clear(ops, B, E):
+    """the tile-transposed planes the tensor-core kernel reads: word ((n/128)*Epad + j)*4 + (n%128)/32, bit n%32"""
+    rng = np.random.default_rng(B)
+    ns = 5
+    Y = rand_csr(rng, B, E, 1, min(E - 1, 6))
+    indptr, indices = dev_csr(Y)
+    negs = rng.integers(-1, E, (B, ns)).astype(np.int32)
+    words = ops.special_tiles_bytes(B, E) // 4
+    Epad = (E + 127) // 128 * 128
+    assert words == (B + 127) // 128 * Epad * 4
+    ps, pm = torch.zeros(words, dtype=torch.int32, device=DEV), torch.zeros(words, dtype=torch.int32, device=DEV)
+    ops.special_tiles(1, B, indptr.data_ptr(), indices, torch.from_numpy(negs).to(DEV), ns, E, ps, pm)
+    member = np.asarray(Y.todense()).astype(bool)
+    special = member.copy()
+    for n in range(B):
+        for j in negs[n]:
+            if j >= 0: special[n, j] = True
+    def unpack(plane):
+        w = plane.cpu().numpy().view(np.uint32).reshape(-1, Epad, 4)                      # [tile][expert][4 words]
+        bits = ((w[:, :, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(w.shape[0], Epad, 128)  # [tile][expert][team in tile]
+        return bits.transpose(0, 2, 1).reshape(-1, Epad)[:B, :E].astype(bool)
+    assert (unpack(ps) == special).all() and (unpack(pm) == member).all()
+    ops.special_tiles(0, B, indptr.data_ptr(), indices, torch.from_numpy(negs).to(DEV), ns, E, ps, pm)
+    assert int(ps.abs().sum()) == 0 and int(pm.abs().sum()) == 0
+
+
 # ------------------------------------------------------------------------------------------------ output layer
 def run_out_train(ops, ws, precision, A, W, b, Y, negs, tpw, tnw, train=True):
     from opentf_b200._lib import OutTrainArgs

@@ -32,15 +32,15 @@ def run_tc(ops, ws, A, W, b, Y, negs, tpw, tnw, train=True, zdbg=False):
     from opentf_b200._lib import OutTrainArgs
     B, h = A.shape; E = W.shape[0]
     indptr, indices = dev_csr(Y)
-    pitch = (E + 31) // 32
-    plane = torch.zeros(B, pitch, dtype=torch.int32, device=DEV)
+    words = ops.special_tiles_bytes(B, E) // 4
+    plane_s, plane_m = torch.zeros(words, dtype=torch.int32, device=DEV), torch.zeros(words, dtype=torch.int32, device=DEV)
     negd = None if negs is None else torch.from_numpy(np.ascontiguousarray(negs, dtype=np.int32)).to(DEV)
-    ops.special_bits(1, B, indptr.data_ptr(), indices, negd, 0 if negs is None else negs.shape[1], E, plane, pitch)
+    ops.special_tiles(1, B, indptr.data_ptr(), indices, negd, 0 if negs is None else negs.shape[1], E, plane_s, plane_m)
     Ad, Wd, bd = A.to(DEV), W.to(DEV), b.to(DEV)
     dW, db, dA, loss = torch.full((E, h), float('nan'), device=DEV), torch.full((E,), float('nan'), device=DEV), torch.empty(B, h, device=DEV), torch.zeros(1, device=DEV)
     Z = torch.full((B, E), float('nan'), device=DEV) if zdbg else None
     a = OutTrainArgs()
-    a.A, a.W, a.b, a.special, a.pitch_words = Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), plane.data_ptr(), pitch
+    a.A, a.W, a.b, a.special_t, a.member_t = Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), plane_s.data_ptr(), plane_m.data_ptr()
     a.m_indptr, a.m_indices, a.B, a.h, a.E = indptr.data_ptr(), indices.data_ptr(), B, h, E
     a.tpw, a.tnw, a.loss_scale, a.loss_out = tpw, tnw, 1.0 / B, loss.data_ptr()
     if train: a.dW, a.db, a.dA = dW.data_ptr(), db.data_ptr(), dA.data_ptr()
