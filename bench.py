@@ -229,9 +229,11 @@ def run_ours(args):
     sync()
     w0 = time.time()
     ev0.record()
+    h0 = time.perf_counter()
     for i in range(args.steps):
         cur['i'] = i
         device_step(args.warmup + i)
+    host_ms = (time.perf_counter() - h0) * 1e3 / args.steps  # CPU time to ENQUEUE one step (if ~ ms_per_step the loop is launch-bound)
     ev1.record()
     sync()
     clk.window(w0, time.time())
@@ -293,7 +295,7 @@ def run_ours(args):
            'data': 'synthetic', 'config': config_of(args, tv), 'clocks': clk.summary(),
            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': host.h2d_bytes, 'd2h_bytes_per_step': 4,
                    'api': 'Engine.step_host: pinned batch CSR -> H2D -> step -> loss.item()'},
-           'gpu_launches': launches, 'roofline': roof, 'infer_topk': {'k': args.infer_k, 'value': infer_value, 'unit': 'teams/s', 'batch': ib}}
+           'gpu_launches': launches, 'host_enqueue_ms_per_step': host_ms, 'roofline': roof, 'infer_topk': {'k': args.infer_k, 'value': infer_value, 'unit': 'teams/s', 'batch': ib}}
     if not args.no_cpu_baseline:
         v, n, dt, threads = cpu_reference_steps(tv, splits, b, args.nsd, args.cpu_baseline_seconds)
         out['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',

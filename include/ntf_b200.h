@@ -74,7 +74,7 @@ int ntf_csr_bag_fwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, co
  * No floating-point atomics, run-to-run deterministic: a skill row is owned by one warp (or, for the few skills that sit
  * in most teams, by one CTA with a fixed-order combine) and summed in entry order.
  * ent_row[p] - row_base = batch row of CSR entry p (from ntf_csr_gather). */
-size_t ntf_csr_bag_bwd_workspace_bytes(int S);
+size_t ntf_csr_bag_bwd_workspace_bytes(int S, int h);
 int ntf_csr_bag_bwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
                     const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T,
                     void* workspace, size_t workspace_bytes);
@@ -114,7 +114,8 @@ int ntf_special_bits(ntf_ctx* ctx, void* stream, int op, int B, const int32_t* m
 /* The same two sets, laid out for the tensor-core kernel (NTF_TF32): teams in tiles of 128, per tile one slab of Epad = roundup(E,128)
  * experts x 4 words; word ((n/128)*Epad + j)*4 + (n%128)/32, bit n%32.  special_t: j is a member of team n or in neg[n,:];
  * member_t: j is a member of team n (the target y).  One plane is ntf_special_tiles_bytes(B, E) bytes, zero-initialised by the
- * caller once; op 1 sets the bits of a batch, op 0 clears the same words again.  A CTA's (tile, 128-expert) slice is 2 KB contiguous. */
+ * caller once; op 1 sets the bits of a batch, op 0 clears the same words again (not needed after ntf_out_train(NTF_TF32), which
+ * clears what it consumes).  A CTA's (tile, 128-expert) slice is 2 KB contiguous. */
 size_t ntf_special_tiles_bytes(int B, int E);
 int ntf_special_tiles(ntf_ctx* ctx, void* stream, int op, int B, const int32_t* m_indptr, const int32_t* m_indices,
                       const int32_t* neg, int ns, int E, uint32_t* special_t, uint32_t* member_t);
@@ -148,9 +149,10 @@ typedef struct {
   float* dW_delta;             /* [E,h]                                                              */
   float* db_delta;             /* [E]                                                                */
   float* dA_s;                 /* [B,h]                                                              */
-  /* NTF_TF32 reads these instead of `special` + the member CSR (NULL: every weight tnw, every target 0)  */
-  const uint32_t* special_t;   /* ntf_special_tiles planes                                           */
-  const uint32_t* member_t;
+  /* NTF_TF32 reads these instead of `special` + the member CSR (NULL: every weight tnw, every target 0).
+   * They are CONSUMED: the kernel zeroes every word it used, so the planes are clean for the next batch.   */
+  uint32_t* special_t;         /* ntf_special_tiles planes                                           */
+  uint32_t* member_t;
 } ntf_out_train_args;
 /* 1 if NTF_TF32 has a tcgen05 kernel for this shape (else callers use NTF_FP32; ntf_out_train(NTF_TF32) refuses it) */
 int ntf_tc_supported(int B, int h, int E, int flipout);

@@ -35,7 +35,7 @@ SIGNATURES = {
     'ntf_csr_gather_workspace_bytes': (sz, [i32]),
     'ntf_csr_gather': (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz]),
     'ntf_csr_bag_fwd': (i32, [vp, vp, i32, vp, vp, vp, vp, i32, i32, vp]),
-    'ntf_csr_bag_bwd_workspace_bytes': (sz, [i32]),
+    'ntf_csr_bag_bwd_workspace_bytes': (sz, [i32, i32]),
     'ntf_csr_bag_bwd': (i32, [vp, vp, i32, vp, vp, vp, i32, vp, i32, i32, vp, vp, sz]),
     'ntf_dense_fwd': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     'ntf_act_bwd_workspace_bytes': (sz, [i32, i32]),

@@ -292,6 +292,8 @@ namespace {
 constexpr int BWD_WARPS = 8;
 constexpr int HOT = 32;      // a skill with more batch entries than this is reduced by the per-skill CTA kernel
 constexpr int HCAP = 8192;
+constexpr int HOT_G = 8;      // team ranges a hot skill's sum is cut into
+constexpr int HOT_MAX = 1024; // hot skills that get the split treatment (a batch has at most entries/33 hot skills)
 
 // pass 1: every batch entry (team n, skill s) takes the next slot of its skill: slots[s][pos] = batch row (| sign bit for Flipout).
 // The slot order is arbitrary (integer atomics), pass 2 sorts it; cnt[s] ends as the exact number of entries of skill s.
@@ -385,18 +387,28 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_hot_kernel(int B, 
                                                                           const float* __restrict__ dZ, int h,
                                                                           const int32_t* __restrict__ hot,
                                                                           const uint32_t* __restrict__ nhot_p, float* __restrict__ dW0T,
-                                                                          const uint32_t* __restrict__ ent_sign) {
+                                                                          const uint32_t* __restrict__ ent_sign, float* __restrict__ hot_part) {
+  // Work item = (hot skill, one of HOT_G fixed ranges of the batch's teams): a popular skill's sum is cut across CTAs by TEAM
+  // range, each item adds its teams in entry order, and bag_bwd_hot_combine_kernel adds the HOT_G partials in range order --
+  // the result depends on the data only.  (Hot skills past HOT_MAX, if any, are summed whole by one CTA each.)
   extern __shared__ float sm[];
   float* total = sm;                        // [h]
   float* partial = sm + h;                  // [BWD_WARPS][h]
   int* hits = (int*)(sm + (size_t)(1 + BWD_WARPS) * h);  // [HCAP]
   __shared__ uint32_t warp_cnt[BWD_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int p_beg = indptr[0], p_end = indptr[B];
+  const int p_first = indptr[0];
   const int nhot = (int)*nhot_p;
+  const int nsplit = min(nhot, HOT_MAX);
+  const int nitems = nsplit * HOT_G + (nhot - nsplit);
   constexpr int PER = 4;                    // consecutive entries per thread per pass (4 loads in flight)
   constexpr int PASS = BWD_WARPS * 32 * PER;
-  for (int hi = blockIdx.x; hi < nhot; hi += gridDim.x) {
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const bool whole = item >= nsplit * HOT_G;
+    const int hi = whole ? nsplit + (item - nsplit * HOT_G) : item / HOT_G;
+    const int gr = whole ? 0 : item % HOT_G;
+    const int r0 = whole ? 0 : (int)((long long)B * gr / HOT_G), r1 = whole ? B : (int)((long long)B * (gr + 1) / HOT_G);
+    const int p_beg = indptr[r0], p_end = indptr[r1];
     const int s = hot[hi];
     for (int c = tid; c < h; c += blockDim.x) total[c] = 0.f;
     int filled = 0;
@@ -427,7 +439,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_hot_kernel(int B, 
         if (sk[q] == s) {
           int rr = __ldg(ent_row + p0 + q) - row_base;
           if (ent_sign) {
-            const int e = p0 + q - p_beg;
+            const int e = p0 + q - p_first;
             if ((__ldg(ent_sign + (e >> 5)) >> (e & 31)) & 1u) rr |= (int)0x80000000u;
           }
           hits[slot++] = rr;
@@ -462,13 +474,30 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) csr_bag_bwd_hot_kernel(int B, 
         __syncthreads();
       }
     }
-    for (int c = tid; c < h; c += blockDim.x) dW0T[(size_t)s * h + c] = total[c];
+    float* dst = whole ? dW0T + (size_t)s * h : hot_part + ((size_t)hi * HOT_G + gr) * h;
+    for (int c = tid; c < h; c += blockDim.x) dst[c] = total[c];
     __syncthreads();
+  }
+}
+
+__global__ void bag_bwd_hot_combine_kernel(int h, const int32_t* __restrict__ hot, const uint32_t* __restrict__ nhot_p,
+                                           const float* __restrict__ hot_part, float* __restrict__ dW0T) {
+  const int nsplit = min((int)*nhot_p, HOT_MAX);
+  for (int hi = blockIdx.x; hi < nsplit; hi += gridDim.x) {
+    const int s = hot[hi];
+    for (int c = threadIdx.x; c < h; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int gr = 0; gr < HOT_G; ++gr) t += hot_part[((size_t)hi * HOT_G + gr) * h + c];
+      dW0T[(size_t)s * h + c] = t;
+    }
   }
 }
 }  // namespace
 
-extern "C" size_t ntf_csr_bag_bwd_workspace_bytes(int S) { return align_up(((size_t)S * (2 + HOT) + 64) * sizeof(uint32_t), 256); }
+extern "C" size_t ntf_csr_bag_bwd_workspace_bytes(int S, int h) {
+  return align_up(((size_t)S * (2 + HOT) + 64) * sizeof(uint32_t), 256) + align_up((size_t)HOT_MAX * HOT_G * h * sizeof(float), 256);
+}
 
 static int csr_bag_bwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
                             const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T,
@@ -476,12 +505,13 @@ static int csr_bag_bwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* in
   NTF_REQUIRE(ctx && indptr && indices && ent_row && dZ && dW0T && workspace, NTF_ERR_BAD_ARG, "csr_bag_bwd: null pointer");
   NTF_REQUIRE(B > 0 && S > 0 && h > 0, NTF_ERR_BAD_ARG, "csr_bag_bwd: B=%d S=%d h=%d", B, S, h);
   NTF_REQUIRE(h <= 2048, NTF_ERR_UNSUPPORTED, "csr_bag_bwd: first hidden width %d > 2048", h);
-  NTF_REQUIRE(workspace_bytes >= ntf_csr_bag_bwd_workspace_bytes(S), NTF_ERR_WORKSPACE, "csr_bag_bwd: workspace too small");
+  NTF_REQUIRE(workspace_bytes >= ntf_csr_bag_bwd_workspace_bytes(S, h), NTF_ERR_WORKSPACE, "csr_bag_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
   uint32_t* cnt = (uint32_t*)workspace;         // [S]
   uint32_t* nhot = cnt + S;                      // [1] (padded to 64)
   int32_t* hot = (int32_t*)(cnt + S + 64);       // [S]
   int32_t* slots = hot + S;                      // [S][HOT]
+  float* hot_part = (float*)((char*)workspace + align_up(((size_t)S * (2 + HOT) + 64) * sizeof(uint32_t), 256));  // [HOT_MAX][HOT_G][h]
   NTF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(S + 64) * sizeof(uint32_t), st));
   NTF_COUNT_LAUNCH; bag_bwd_fill_kernel<<<min(cdiv(B * 8, 256), ctx->sm_count * 8), 256, 0, st>>>(B, indptr, indices, ent_row, row_base, ent_sign, cnt, slots);
   const bool vec = (h % 4 == 0) && (((uintptr_t)dZ | (uintptr_t)dW0T) % 16 == 0);
@@ -491,7 +521,8 @@ static int csr_bag_bwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* in
   else bag_bwd_reduce_kernel<false><<<blocks, 256, 0, st>>>(S, h, cnt, slots, dZ, dW0T, hot, nhot);
   const size_t smem_hot = (size_t)(1 + BWD_WARPS) * h * sizeof(float) + (size_t)HCAP * sizeof(int);
   NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_hot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hot));
-  NTF_COUNT_LAUNCH; csr_bag_bwd_hot_kernel<<<ctx->sm_count * 2, BWD_WARPS * 32, smem_hot, st>>>(B, indptr, indices, ent_row, row_base, dZ, h, hot, nhot, dW0T, ent_sign);
+  NTF_COUNT_LAUNCH; csr_bag_bwd_hot_kernel<<<ctx->sm_count * 2, BWD_WARPS * 32, smem_hot, st>>>(B, indptr, indices, ent_row, row_base, dZ, h, hot, nhot, dW0T, ent_sign, hot_part);
+  NTF_COUNT_LAUNCH; bag_bwd_hot_combine_kernel<<<ctx->sm_count, 128, 0, st>>>(h, hot, nhot, hot_part, dW0T);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

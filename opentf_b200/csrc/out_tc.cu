@@ -50,12 +50,13 @@ constexpr uint32_t A16_BYTES = TB * HK * 2;      // 32 KB : 2 chunks (hidden 0-6
 constexpr uint32_t DZ_BYTES = TE * TB * 2;       // 32 KB : 2 chunks (teams  0-63 | 64-127) of [128 experts][128 B]
 constexpr uint32_t W32_BYTES = TE * HK * 4;      // 64 KB : 4 chunks (32 hidden each) of [128 experts][128 B], staged in the dz ring
 constexpr uint32_t OFF_W16 = 0;
-constexpr uint32_t OFF_A16 = OFF_W16 + W16_BYTES;           // 2 stages
-constexpr uint32_t OFF_DZ = OFF_A16 + 2 * A16_BYTES;        // 2 stages (first use: landing zone of the fp32 W tile)
+constexpr int A_STAGES = 3;                                 // tile t+2's activations load while tile t's backward products still read theirs
+constexpr uint32_t OFF_A16 = OFF_W16 + W16_BYTES;
+constexpr uint32_t OFF_DZ = OFF_A16 + A_STAGES * A16_BYTES; // 2 stages (first use: landing zone of the fp32 W tile)
 constexpr uint32_t OFF_PLANE = OFF_DZ + 2 * DZ_BYTES;       // 2 stages x (special | member) bit planes of a tile, [128 experts][4 words] each
 constexpr uint32_t PLANE_BYTES = TE * 4 * 4;                // 2 KB each
-constexpr uint32_t OFF_DAST = OFF_PLANE + 4 * PLANE_BYTES;  // dA staging: 2 x [128 teams][128 B] fp32 chunks on their way to the TMA reduce-add
-constexpr uint32_t OFF_BAR = OFF_DAST + 2 * CHUNK;          // mbarriers + tmem base + small reduction scratch
+constexpr uint32_t OFF_DAST = OFF_PLANE + 4 * PLANE_BYTES;  // dA staging: one [128 teams][128 B] fp32 chunk on its way to the TMA reduce-add
+constexpr uint32_t OFF_BAR = OFF_DAST + CHUNK;              // mbarriers + tmem base + small reduction scratch
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 512;              // the dynamic window is declared 1024-byte aligned (checked at run time)
 static_assert(W32_BYTES <= 2 * DZ_BYTES, "the fp32 W tile is staged in the dz ring");
 static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared memory limit");
@@ -66,9 +67,9 @@ constexpr uint32_t TM_DW = 256;   // 128
 constexpr uint32_t TM_DA = 384;   // 128
 constexpr uint32_t TM_COLS = 512;
 
-enum { BAR_W32 = 0, BAR_W16 = 1, BAR_A_FULL = 2, BAR_A_EMPTY = 4, BAR_Z_FULL = 6, BAR_Z_EMPTY = 8, BAR_DZ_FULL = 10, BAR_DZ_EMPTY = 12,
-       BAR_DA_FULL = 14, BAR_DA_EMPTY = 15, BAR_DW_FULL = 16, BAR_SP_FULL = 17, BAR_SP_EMPTY = 19, NUM_BARS = 21 };
-// A_*  : fp16 activation tile ring (operand of the forward and of the dW product; released after the tile's last product)
+enum { BAR_W32 = 0, BAR_W16 = 1, BAR_A_FULL = 2, BAR_A_EMPTY = 5, BAR_Z_FULL = 8, BAR_Z_EMPTY = 10, BAR_DZ_FULL = 12, BAR_DZ_EMPTY = 14,
+       BAR_DA_FULL = 16, BAR_DA_EMPTY = 17, BAR_DW_FULL = 18, BAR_SP_FULL = 19, BAR_SP_EMPTY = 21, NUM_BARS = 23 };
+// A_*  : fp16 activation tile ring, 3 stages (operand of the forward and of the dW product; released after the tile's last product)
 // SP_* : special / member bit planes of a tile (2-stage ring, filled by 1-D bulk copies from the tile-transposed planes in HBM)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -144,8 +145,8 @@ constexpr uint32_t instr_desc(uint32_t fmt, uint32_t a_mn, uint32_t b_mn, uint32
 
 struct TcArgs {
   const float* bias;          // [E]
-  const uint32_t* special_t;  // tile-transposed planes (ntf_special_tiles), or NULL: every weight tnw, every target 0
-  const uint32_t* member_t;
+  uint32_t* special_t;        // tile-transposed planes (ntf_special_tiles), or NULL: every weight tnw, every target 0.
+  uint32_t* member_t;         // The kernel zeroes the words it consumed: the planes are clean again when it returns.
   int Epad;                   // E rounded up to 128: row count of one tile slab of the planes
   int B, E;
   float tpw, tnw, scale;      // scale = loss_scale (1/B_global)
@@ -157,6 +158,9 @@ struct TcArgs {
   float* Zdbg;                // debug: raw logits z [B,E] (NULL in production)
   long long* timing;          // debug: clock64 stamps of CTA 0, [tile][8] (NULL in production)
   int exp;                    // debug: experiment bits (NTF_TC_EXP): 1 = skip the dA reduction, 2 = skip the special-bit path
+  // work split: CTAs [0, n_full) own a whole expert tile (all batch tiles); the remaining expert tiles -- the partial last wave --
+  // are cut `split` ways along the batch so that the last wave is short: those CTAs ADD their dW / db partials (pre-zeroed rows)
+  int n_full, split;
 };
 
 constexpr int EPI_WARPS = 16;
@@ -204,8 +208,17 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
     asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
     g.timing[128 + 3 * blockIdx.x] = (long long)gt; g.timing[128 + 3 * blockIdx.x + 2] = smid;
   }
-  const int e0 = blockIdx.x * TE;
-  const int ntiles = (g.B + TB - 1) / TB;
+  const int nt_all = (g.B + TB - 1) / TB;
+  int etile = blockIdx.x, t_begin = 0, t_end = nt_all;
+  const bool shared_tile = (int)blockIdx.x >= g.n_full;  // this expert tile's batch range is cut across g.split CTAs
+  if (shared_tile) {
+    const int k = blockIdx.x - g.n_full, part = k % g.split;
+    etile = g.n_full + k / g.split;
+    t_begin = part * nt_all / g.split;
+    t_end = (part + 1) * nt_all / g.split;
+  }
+  const int e0 = etile * TE;
+  const int ntiles = t_end - t_begin;  // batch tiles of this CTA: local index it, global tile t_begin + it
   const bool train = MODE == 0 && g.dW != nullptr;
 
   if (threadIdx.x == 0) {
@@ -214,9 +227,11 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
     mbar_init(bar(BAR_DW_FULL), 1);
     mbar_init(bar(BAR_DA_FULL), 1);
     mbar_init(bar(BAR_DA_EMPTY), 128);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < A_STAGES; ++s) {
       mbar_init(bar(BAR_A_FULL + s), 1);
       mbar_init(bar(BAR_A_EMPTY + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(bar(BAR_Z_FULL + s), 1);
       mbar_init(bar(BAR_Z_EMPTY + s), EPI_THREADS);
       mbar_init(bar(BAR_DZ_FULL + s), EPI_THREADS);
@@ -241,23 +256,24 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
     if (lane == 0) {
       mbar_expect_tx(bar(BAR_W32), W32_BYTES);
       for (int c = 0; c < 4; ++c) tma_load_2d(sbase + OFF_DZ + c * CHUNK, &map_w32, c * 32, e0, bar(BAR_W32));
-      for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
+      for (int it = 0; it < ntiles; ++it) {
+        const int s = it % A_STAGES;
+        const uint32_t ph = (it / A_STAGES) & 1;
         mbar_wait(bar(BAR_A_EMPTY + s), ph ^ 1);
         mbar_expect_tx(bar(BAR_A_FULL + s), A16_BYTES);
-        for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A16 + s * A16_BYTES + c * CHUNK, &map_a16, c * 64, t * TB, bar(BAR_A_FULL + s));
+        for (int c = 0; c < 2; ++c)
+          tma_load_2d(sbase + OFF_A16 + s * A16_BYTES + c * CHUNK, &map_a16, c * 64, (t_begin + it) * TB, bar(BAR_A_FULL + s));
       }
     }
   } else if (warp == WARP_SP) {
     // ====== special / member planes of the tile: two 2 KB bulk copies per tile from the tile-transposed planes (ntf_special_tiles) ======
     if (MODE == 0 && lane == 0 && g.special_t && !(g.exp & 2)) {
-      for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
+      for (int it = 0; it < ntiles; ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
         mbar_wait(bar(BAR_SP_EMPTY + s), ph ^ 1);
         mbar_expect_tx(bar(BAR_SP_FULL + s), 2 * PLANE_BYTES);
-        const size_t off = ((size_t)t * g.Epad + e0) * 4;
+        const size_t off = ((size_t)(t_begin + it) * g.Epad + e0) * 4;
         bulk_load(sbase + OFF_PLANE + s * 2 * PLANE_BYTES, g.special_t + off, PLANE_BYTES, bar(BAR_SP_FULL + s));
         bulk_load(sbase + OFF_PLANE + s * 2 * PLANE_BYTES + PLANE_BYTES, g.member_t + off, PLANE_BYTES, bar(BAR_SP_FULL + s));
       }
@@ -265,47 +281,47 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
   } else if (warp == WARP_MMA) {
     // =========================================== MMA issuer ===========================================
     if (lane == 0) {
-      auto issue_fwd = [&](int t) {
-        const int s = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
-        mbar_wait(bar(BAR_A_FULL + s), ph);
-        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 1] = clock64();
+      auto issue_fwd = [&](int it) {
+        const int sa = it % A_STAGES, s = it & 1;
+        const uint32_t pha = (it / A_STAGES) & 1, ph = (it >> 1) & 1;
+        mbar_wait(bar(BAR_A_FULL + sa), pha);
+        if (g.timing && blockIdx.x == 0) g.timing[it * 8 + 1] = clock64();
         mbar_wait(bar(BAR_Z_EMPTY + s), ph ^ 1);
-        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 2] = clock64();
+        if (g.timing && blockIdx.x == 0) g.timing[it * 8 + 2] = clock64();
         tc_fence_after();
 #pragma unroll
         for (int i = 0; i < HK / 16; ++i) {  // 8 k-steps of 16 halfs (32 bytes): chunk i/4, 32-byte slice i%4 of the 128-byte swizzle row
           const uint64_t da = smem_desc(sbase + OFF_W16 + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
-          const uint64_t db = smem_desc(sbase + OFF_A16 + s * A16_BYTES + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
+          const uint64_t db = smem_desc(sbase + OFF_A16 + sa * A16_BYTES + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
           mma_f16(tmem + TM_Z + s * TB, da, db, IDESC_FWD, i > 0);
         }
         tc_commit(bar(BAR_Z_FULL + s));
         if (g.timing && (g.exp & 4)) {  // diagnostic mode 4 serialises the pipeline: stamp the COMPLETION of the forward product
           mbar_wait(bar(BAR_Z_FULL + s), ph);
-          if (blockIdx.x == 0) g.timing[t * 8 + 3] = clock64();
+          if (blockIdx.x == 0) g.timing[it * 8 + 3] = clock64();
         }
-        if (!train) tc_commit(bar(BAR_A_EMPTY + s));  // forward-only: the stage is free once the forward product has read it
+        if (!train) tc_commit(bar(BAR_A_EMPTY + sa));  // forward-only: the stage is free once the forward product has read it
       };
       mbar_wait(bar(BAR_W16), 0);
       if (g.timing && blockIdx.x == 0) g.timing[15 * 8 + 2] = clock64();  // W image ready
       if (ntiles > 0) issue_fwd(0);
-      for (int t = 0; t < ntiles; ++t) {
-        if (t + 1 < ntiles) issue_fwd(t + 1);  // keep the tensor pipe busy while the epilogue works on tile t
+      for (int it = 0; it < ntiles; ++it) {
+        if (it + 1 < ntiles) issue_fwd(it + 1);  // keep the tensor pipe busy while the epilogue works on tile it
         if (!train) continue;
-        const int s = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
+        const int sa = it % A_STAGES, s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
         mbar_wait(bar(BAR_DZ_FULL + s), ph);
         tc_fence_after();
-        if (g.timing && blockIdx.x == 0) g.timing[t * 8 + 0] = clock64();  // backward products: issue starts
+        if (g.timing && blockIdx.x == 0) g.timing[it * 8 + 0] = clock64();  // backward products: issue starts
         // dW[128 j x 128 k] += dz^T[j, n] . A16[n, k] : K = 128 teams = 8 steps of 16
 #pragma unroll
         for (int i = 0; i < TB / 16; ++i) {
           const uint64_t da = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);   // K-major, K = teams
-          const uint64_t db = smem_desc(sbase + OFF_A16 + s * A16_BYTES + i * 2048, CHUNK, 1024);                      // MN-major, N = hidden
-          mma_f16(tmem + TM_DW, da, db, IDESC_DW, (t > 0 || i > 0));
+          const uint64_t db = smem_desc(sbase + OFF_A16 + sa * A16_BYTES + i * 2048, CHUNK, 1024);                     // MN-major, N = hidden
+          mma_f16(tmem + TM_DW, da, db, IDESC_DW, (it > 0 || i > 0));
         }
         // dA[128 n x 128 k] = dz[j, n]^T . W16[j, k] : K = 128 experts = 8 steps of 16
-        mbar_wait(bar(BAR_DA_EMPTY), (t & 1) ^ 1);
+        mbar_wait(bar(BAR_DA_EMPTY), (it & 1) ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int i = 0; i < TE / 16; ++i) {
@@ -315,12 +331,12 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         }
         tc_commit(bar(BAR_DA_FULL));
         if (g.timing && (g.exp & 4)) {
-          mbar_wait(bar(BAR_DA_FULL), t & 1);
-          if (blockIdx.x == 0) g.timing[t * 8 + 7] = clock64();  // backward products complete
+          mbar_wait(bar(BAR_DA_FULL), it & 1);
+          if (blockIdx.x == 0) g.timing[it * 8 + 7] = clock64();  // backward products complete
         }
         tc_commit(bar(BAR_DZ_EMPTY + s));
-        tc_commit(bar(BAR_A_EMPTY + s));
-        if (t == ntiles - 1) tc_commit(bar(BAR_DW_FULL));
+        tc_commit(bar(BAR_A_EMPTY + sa));
+        if (it == ntiles - 1) tc_commit(bar(BAR_DW_FULL));
       }
     }
   } else if (warp < EPI_WARPS) {
@@ -357,10 +373,10 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
     const bool has_sp = MODE == 0 && g.special_t && !(g.exp & 2);
     constexpr float LOG2E = 1.4426950408889634f;
     const float kb1 = -LOG2E * bj, kb2 = -LOG2E * NTF_LRELU_SLOPE * bj;
-    for (int t = 0; t < ntiles; ++t) {
-      const int s = t & 1;
-      const uint32_t ph = (t >> 1) & 1;
-      const int n0 = t * TB + cb * 32;  // first team of this thread's block
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int n0 = (t_begin + it) * TB + cb * 32;  // first team of this thread's block
       // bit n of S / Y: (team n0+n, my expert) carries weight tpw / target 1 -- two words from the tile's planes, then the stage is free
       uint32_t S = 0, Y = 0;
       if (has_sp) {
@@ -369,16 +385,21 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         S = plane[jl * 4 + cb];
         Y = plane[TE * 4 + jl * 4 + cb];
         mbar_arrive(bar(BAR_SP_EMPTY + s));
+        if (S) {  // consumed: clear the words in HBM so that the caller's planes are clean for the next batch (no second pass over them)
+          const size_t wofs = ((size_t)(t_begin + it) * g.Epad + e) * 4 + cb;
+          g.special_t[wofs] = 0u;
+          if (Y) g.member_t[wofs] = 0u;
+        }
         if (!e_ok) S = 0;
       }
       mbar_wait(bar(BAR_Z_FULL + s), ph);
-      if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[t * 8 + 4] = clock64();
+      if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[it * 8 + 4] = clock64();
       tc_fence_after();
       float z[32];
       tmem_ld32(tmem + lane_base + TM_Z + s * TB + cb * 32, z);
       tc_fence_before();
       mbar_arrive(bar(BAR_Z_EMPTY + s));
-      if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[t * 8 + 5] = clock64();
+      if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[it * 8 + 5] = clock64();
       const int nrem = g.B - n0;  // teams of this block that exist
       if (MODE == 1) {
 #pragma unroll
@@ -396,7 +417,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
           for (int q = 0; q < 8; ++q)
             if (e_ok && u * 8 + q < nrem) g.P[(size_t)(n0 + u * 8 + q) * g.E + e] = p[q];
         }
-        if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[t * 8 + 6] = clock64();
+        if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[it * 8 + 6] = clock64();
         continue;
       }
       if (g.Zdbg) {
@@ -405,7 +426,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
           if (e_ok && n < nrem) g.Zdbg[(size_t)(n0 + n) * g.E + e] = z[n] + bj;
       }
       if (train) {
-        if (t == 0) mbar_wait(bar(BAR_W16), 0);  // every thread is done with the fp32 landing zone before the dz ring is written
+        if (it == 0) mbar_wait(bar(BAR_W16), 0);  // every thread is done with the fp32 landing zone before the dz ring is written
         mbar_wait(bar(BAR_DZ_EMPTY + s), ph ^ 1);
       }
       uint8_t* dzrow = sgen + OFF_DZ + s * DZ_BYTES + (cb >> 1) * CHUNK + jl * 128;
@@ -497,7 +518,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         fence_proxy_async();
         mbar_arrive(bar(BAR_DZ_FULL + s));
       }
-      if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[t * 8 + 6] = clock64();
+      if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[it * 8 + 6] = clock64();
     }
     if (MODE == 0) {
       // loss partial of this CTA and db: fixed-order combines (shuffle tree, then warps / team blocks in order)
@@ -516,7 +537,10 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         g.loss_part[blockIdx.x] = l;
       }
       if (train) {
-        if (cb == 0 && e_ok) g.db[e] = (((db_acc + dbs[jl]) + dbs[TE + jl]) + dbs[2 * TE + jl]) * g.scale;
+        if (cb == 0 && e_ok) {
+          const float dbv = (((db_acc + dbs[jl]) + dbs[TE + jl]) + dbs[2 * TE + jl]) * g.scale;
+          if (shared_tile) atomicAdd(g.db + e, dbv); else g.db[e] = dbv;
+        }
         tc_fence_after();
         float v[32];
         tmem_ld32(tmem + lane_base + TM_DW + cb * 32, v);  // this thread's 32 of the 128 dW columns of its expert
@@ -530,7 +554,12 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < TE / EPI_WARPS; ++i) {
           const int r = warp * (TE / EPI_WARPS) + i;
-          if (e0 + r < g.E) reinterpret_cast<float4*>(g.dW + (size_t)(e0 + r) * HK)[lane] = stage[r * 32 + (lane ^ (r & 31))];
+          if (e0 + r < g.E) {
+            const float4 v4 = stage[r * 32 + (lane ^ (r & 31))];
+            float* dst = g.dW + (size_t)(e0 + r) * HK + 4 * lane;
+            if (shared_tile) { atomicAdd(dst, v4.x); atomicAdd(dst + 1, v4.y); atomicAdd(dst + 2, v4.z); atomicAdd(dst + 3, v4.w); }
+            else *reinterpret_cast<float4*>(dst) = v4;
+          }
         }
       }
     }
@@ -540,21 +569,20 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
     if (train) {
       const int r = threadIdx.x - WARP_DA * 32;  // 0..127 = TMEM lane = team of the tile
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-      for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(bar(BAR_DA_FULL), t & 1);
+      for (int it = 0; it < ntiles; ++it) {
+        mbar_wait(bar(BAR_DA_FULL), it & 1);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < HK / 32; ++c) {  // 32 hidden units = one 128-byte chunk row
-          const uint32_t buf = OFF_DAST + ((t * (HK / 32) + c) & 1) * CHUNK;
-          if (r == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the reduce that last read this buffer is done with it
-          asm volatile("bar.sync 2, 128;" ::: "memory");
           float v[32];
           tmem_ld32(tmem + lane_base + TM_DA + c * 32, v);
           if (c == HK / 32 - 1) {
             tc_fence_before();
             mbar_arrive(bar(BAR_DA_EMPTY));
           }
-          uint8_t* row = sgen + buf + r * 128;
+          if (r == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous reduce is done reading the buffer
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          uint8_t* row = sgen + OFF_DAST + r * 128;
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(row + ((q ^ (r & 7)) << 4)) = make_float4(v[4 * q] * g.scale, v[4 * q + 1] * g.scale, v[4 * q + 2] * g.scale, v[4 * q + 3] * g.scale);
@@ -562,7 +590,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
           asm volatile("bar.sync 2, 128;" ::: "memory");
           if (r == 0 && !(g.exp & 1)) {
             asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
-                         ::"l"(reinterpret_cast<uint64_t>(&map_da)), "r"(c * 32), "r"(t * TB), "r"(sbase + buf) : "memory");
+                         ::"l"(reinterpret_cast<uint64_t>(&map_da)), "r"(c * 32), "r"((t_begin + it) * TB), "r"(sbase + OFF_DAST) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
@@ -608,7 +636,18 @@ int make_map(const ntf_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt, int esi
 int ntf_out_tc_supported(int B, int h, int E, int flipout) { return (h == HK && !flipout && B >= 1 && E >= 1) ? 1 : 0; }
 
 size_t ntf_out_train_tc_workspace_bytes(const ntf_ctx*, int B, int h, int E, int) {
-  return align_up((size_t)B * h * sizeof(__half), 256) + align_up((size_t)cdiv(E, TE) * sizeof(float), 256);
+  return align_up((size_t)B * h * sizeof(__half), 256) + align_up((size_t)(cdiv(E, TE) + 1024) * sizeof(float), 256);  // + one loss partial per CTA
+}
+
+// Work split (TcArgs::n_full / split): the expert tiles that fill whole waves of the machine get one CTA each; the tiles of the
+// partial last wave are cut along the batch so that the last wave is short instead of leaving most SMs idle for a full tile.
+static void plan_split(const ntf_ctx* ctx, int nct, int nt_all, int* n_full, int* split, int* grid) {
+  const int sm = ctx->sm_count > 0 ? ctx->sm_count : 148;
+  const int rem = nct % sm;
+  int sp = (rem > 0 && nct > sm) ? sm / rem : 1;   // (a grid smaller than one wave is left alone)
+  if (sp > nt_all) sp = nt_all;
+  if (sp < 2) { *n_full = nct; *split = 1; *grid = nct; return; }
+  *n_full = nct - rem; *split = sp; *grid = *n_full + rem * sp;
 }
 
 static void tc_debug_hooks(TcArgs& g) {
@@ -640,14 +679,22 @@ int ntf_out_train_tc(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a,
   NTF_COUNT_LAUNCH; to_half_kernel<<<min(cdiv(a->B * a->h, 256), ctx->sm_count * 4), 256, 0, st>>>(a->A, (size_t)a->B * a->h, A16);
   if (train) NTF_CUDA(cudaMemsetAsync(a->dA, 0, (size_t)a->B * a->h * sizeof(float), st));
   TcArgs g{};
-  g.bias = a->b; g.special_t = a->special_t; g.member_t = a->member_t; g.Epad = cdiv(a->E, TE) * TE;
+  g.bias = a->b; g.special_t = const_cast<uint32_t*>(a->special_t); g.member_t = const_cast<uint32_t*>(a->member_t); g.Epad = cdiv(a->E, TE) * TE;
   g.B = a->B; g.E = a->E; g.tpw = a->tpw; g.tnw = a->tnw; g.scale = a->loss_scale;
   g.dW = a->dW; g.db = a->db; g.dA = a->dA; g.loss_part = loss_part; g.P = nullptr;
   tc_debug_hooks(g);
+  int grid;
+  plan_split(ctx, nct, cdiv(a->B, TB), &g.n_full, &g.split, &grid);
+  if (g.exp & 8) { g.n_full = nct; g.split = 1; grid = nct; }  // debug: no split
+  if (train && g.split > 1) {  // the shared tiles' CTAs add their partial dW / db
+    const size_t e_first = (size_t)g.n_full * TE;
+    NTF_CUDA(cudaMemsetAsync(a->dW + e_first * HK, 0, ((size_t)a->E - e_first) * HK * sizeof(float), st));
+    NTF_CUDA(cudaMemsetAsync(a->db + e_first, 0, ((size_t)a->E - e_first) * sizeof(float), st));
+  }
   NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  NTF_COUNT_LAUNCH; out_tc_kernel<0><<<nct, NT, SMEM_BYTES, st>>>(mw, mh, mda, g);
+  NTF_COUNT_LAUNCH; out_tc_kernel<0><<<grid, NT, SMEM_BYTES, st>>>(mw, mh, mda, g);
   NTF_LAUNCH_CHECK();
-  return ntf_loss_reduce_impl(st, loss_part, nct, a->loss_scale, a->loss_out);
+  return ntf_loss_reduce_impl(st, loss_part, grid, a->loss_scale, a->loss_out);
 }
 
 size_t ntf_infer_scores_tc_workspace_bytes(int B, int h) { return align_up((size_t)B * h * sizeof(__half), 256); }
@@ -666,8 +713,10 @@ int ntf_infer_scores_tc(ntf_ctx* ctx, cudaStream_t st, const float* A, const flo
   g.bias = b; g.B = B; g.E = E; g.P = P;
   tc_debug_hooks(g);
   g.Zdbg = nullptr;
+  int grid;
+  plan_split(ctx, cdiv(E, TE), cdiv(B, TB), &g.n_full, &g.split, &grid);
   NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  NTF_COUNT_LAUNCH; out_tc_kernel<1><<<cdiv(E, TE), NT, SMEM_BYTES, st>>>(mw, mh, mw, g);
+  NTF_COUNT_LAUNCH; out_tc_kernel<1><<<grid, NT, SMEM_BYTES, st>>>(mw, mh, mw, g);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

@@ -288,8 +288,7 @@ class Engine:
             a.dW, a.db = self.view(f'layers.{Lo}.weight', self.grads).data_ptr(), self.view(f'layers.{Lo}.bias', self.grads).data_ptr()
             a.dA = self.dact[-1].data_ptr()
         ops.out_train(self.dev_index, self.precision, a, self.ws)
-        if tc: ops.special_tiles(0, B, mptr, sp.m_indices, neg, ns, self.E, self.special_t, self.member_t)
-        else: ops.special_bits(0, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
+        if not tc: ops.special_bits(0, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)  # (the tensor-core kernel clears what it consumes)
         self.global_step += 1
         if not train: return
         for i in range(self.L - 2, 0, -1):  # hidden dense layers

@@ -57,7 +57,7 @@ def csr_bag_fwd(B, indptr_ptr, indices, W0T, b0, S, h, A):
 
 def csr_bag_bwd(B, indptr_ptr, indices, ent_row, row_base, dZ, S, h, dW0T, ws):
     d = _dev(dZ)
-    p, nb = ws.get(lib().ntf_csr_bag_bwd_workspace_bytes(S))
+    p, nb = ws.get(lib().ntf_csr_bag_bwd_workspace_bytes(S, h))
     check(lib().ntf_csr_bag_bwd(_lib.ctx(d), _stream(d), B, indptr_ptr, _p(indices, I32), _p(ent_row, I32), row_base, _p(dZ, F32), S, h,
                                 _p(dW0T, F32), p, nb), 'ntf_csr_bag_bwd')
 
@@ -190,7 +190,7 @@ def csr_bag_flipout_fwd(B, indptr_ptr, indices, ent_sign, Wmu, bmu, Wd, bd, sign
 
 def csr_bag_bwd_signed(B, indptr_ptr, indices, ent_row, row_base, ent_sign, dZs, S, h, dWd, ws):
     d = _dev(dZs)
-    p, nb = ws.get(lib().ntf_csr_bag_bwd_workspace_bytes(S))
+    p, nb = ws.get(lib().ntf_csr_bag_bwd_workspace_bytes(S, h))
     check(lib().ntf_csr_bag_bwd_signed(_lib.ctx(d), _stream(d), B, indptr_ptr, _p(indices, I32), _p(ent_row, I32), row_base, _p(ent_sign), _p(dZs, F32), S, h,
                                        _p(dWd, F32), p, nb), 'ntf_csr_bag_bwd_signed')
 

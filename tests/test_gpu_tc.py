@@ -50,6 +50,7 @@ def run_tc(ops, ws, A, W, b, Y, negs, tpw, tnw, train=True, zdbg=False):
         torch.cuda.synchronize()
     finally:
         os.environ.pop('NTF_TC_ZDBG', None)
+    assert int(plane_s.abs().sum()) == 0 and int(plane_m.abs().sum()) == 0  # the kernel clears the plane words it consumed
     return loss.cpu().item(), dW.cpu(), db.cpu(), dA.cpu(), (Z.cpu() if zdbg else None)
 
 
