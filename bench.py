@@ -218,12 +218,8 @@ def run_ours(args):
     # the dominant kernel group (output layer: forward + loss + backward) timed live with events on the launching stream
     k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    orig_out_train = ops.out_train
-    cur = {'i': 0}
-
-    def timed_out_train(*a, **k):
-        k0[cur['i']].record(); orig_out_train(*a, **k); k1[cur['i']].record()
-    ops.out_train = timed_out_train
+    for e in k0 + k1: e.record()  # (creates the underlying cudaEvent_t handles)
+    torch.cuda.synchronize()
     clk = ClockSampler(local).__enter__()  # samples through both timed legs (device-resident and end-to-end)
     time.sleep(0.3)
     sync()
@@ -231,13 +227,13 @@ def run_ours(args):
     ev0.record()
     h0 = time.perf_counter()
     for i in range(args.steps):
-        cur['i'] = i
+        eng.prof_events = (k0[i], k1[i])  # ntf_fnn_step records them around its output-layer call, on the launching stream
         device_step(args.warmup + i)
+    eng.prof_events = None
     host_ms = (time.perf_counter() - h0) * 1e3 / args.steps  # CPU time to ENQUEUE one step (if ~ ms_per_step the loop is launch-bound)
     ev1.record()
     sync()
     clk.window(w0, time.time())
-    ops.out_train = orig_out_train
     launches = int(_lib.lib().ntf_launch_count(0))
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], device=dev)
@@ -294,7 +290,7 @@ def run_ours(args):
            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if precision_used == 'fp32' else 'tf32 (fp32 accumulate)',
            'data': 'synthetic', 'config': config_of(args, tv), 'clocks': clk.summary(),
            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': host.h2d_bytes, 'd2h_bytes_per_step': 4,
-                   'api': 'Engine.step_host: pinned batch CSR -> H2D -> step -> loss.item()'},
+                   'api': 'Engine.step_host: pinned batch CSR block -> one H2D copy -> ntf_fnn_step -> loss.item()'},
            'gpu_launches': launches, 'host_enqueue_ms_per_step': host_ms, 'roofline': roof, 'infer_topk': {'k': args.infer_k, 'value': infer_value, 'unit': 'teams/s', 'batch': ib}}
     if not args.no_cpu_baseline:
         v, n, dt, threads = cpu_reference_steps(tv, splits, b, args.nsd, args.cpu_baseline_seconds)
@@ -305,10 +301,9 @@ def run_ours(args):
 
 
 class HostBatches:
-    """batches as the host holds them (pinned CSR slices of teamsvecs) for the end-to-end leg."""
+    """batches as the host holds them (pinned compact CSR slices of teamsvecs, one block per batch) for the end-to-end leg."""
 
     def __init__(self, tv, train_rows, b, rank, G):
-        import torch
         from opentf_b200.engine import to_csr
         self.b, self.rank, self.G = b, rank, G
         self.s = to_csr(tv['skill']); self.m = to_csr(tv['member'])
@@ -317,26 +312,24 @@ class HostBatches:
         self.pin = {}
 
     def batch(self, i):
-        """pinned compact CSR of global batch i (built once, outside any timed region)"""
-        import torch
+        """pinned block of global batch i (built once, outside any timed region)"""
+        from opentf_b200.engine import pack_host_batch
         if i in self.pin: return self.pin[i]
         gB = self.b * self.G
         g0 = (i * gB) % (len(self.rows) - gB)
         rows = self.rows[g0:g0 + gB]
-        out = []
-        for k, (ptr, idx, _) in enumerate((self.s, self.m)):
+        parts = []
+        for ptr, idx, _ in (self.s, self.m):
             lens = ptr[rows + 1] - ptr[rows]
             p = np.zeros(len(rows) + 1, dtype=np.int32); np.cumsum(lens, out=p[1:])
-            ind = np.concatenate([idx[ptr[r]:ptr[r + 1]] for r in rows]).astype(np.int32)
-            out += [torch.from_numpy(p).pin_memory(), torch.from_numpy(ind).pin_memory()]
-            if k == 0: out.append(torch.from_numpy(np.repeat(np.arange(len(rows), dtype=np.int32), lens)).pin_memory())
-        self.pin[i] = out
-        return out
+            parts += [p, np.concatenate([idx[ptr[r]:ptr[r + 1]] for r in rows]).astype(np.int32)]
+        self.pin[i] = pack_host_batch(parts[0], parts[1], parts[2], parts[3])
+        return self.pin[i]
 
     def step(self, eng, i):
-        s_ptr, s_idx, s_row, m_ptr, m_idx = self.batch(i)
-        self.h2d_bytes = sum(t.numel() * 4 for t in (s_ptr, s_idx, s_row, m_ptr, m_idx))
-        return eng.step_host(s_ptr, s_idx, s_row, m_ptr, m_idx, self.rank, self.G, lr=1e-3)
+        packed, n, nnz_s, nnz_m = self.batch(i)
+        self.h2d_bytes = packed.numel() * 4
+        return eng.step_host(packed, n, nnz_s, nnz_m, self.rank, self.G, lr=1e-3)
 
 
 if __name__ == '__main__':

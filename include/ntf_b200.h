@@ -218,6 +218,49 @@ int ntf_dense_flipout_fwd(ntf_ctx* ctx, void* stream, const float* A, const floa
 /* Y[n,c] += X[n,c] * (bit(n,c) ? -1 : +1) */
 int ntf_add_signed(ntf_ctx* ctx, void* stream, const float* X, const uint32_t* bits, int pitch_words, int B, int h, float* Y);
 
+/* ---- one whole Fnn batch, enqueued by one call: the loop body of fnn.py:118-151 -------------------------------------------------
+ * forward (CSR bag, hidden layers), negative sampling (unless neg_given), output layer forward + weighted BCE; and when `train`:
+ * the backward pass and (when `run_adam`) the Adam step.  Exactly the sequence of the entry points above; nothing is synchronised. */
+#define NTF_MAX_LAYERS 8
+typedef struct {
+  int n_layers;                      /* linear layers (hidden layers + 1)                                              */
+  int S, E;
+  int hidden[NTF_MAX_LAYERS];        /* widths of the hidden layers: n_layers - 1 entries                             */
+  const float* W[NTF_MAX_LAYERS];    /* layer 0 TRANSPOSED [S,h0] (ntf_csr_bag_fwd); layer i>0 [out,in]                */
+  const float* b[NTF_MAX_LAYERS];
+  float* gW[NTF_MAX_LAYERS];         /* gradients, same layouts                                                        */
+  float* gb[NTF_MAX_LAYERS];
+  float* act[NTF_MAX_LAYERS];        /* [B,h_i] activations of hidden layer i (outputs)                               */
+  float* dact[NTF_MAX_LAYERS];       /* [B,h_i] scratch: d loss / d act_i                                              */
+  float* dz[NTF_MAX_LAYERS];         /* [B,h_i] scratch: d loss / d pre-activation                                     */
+  int B;                             /* this call's teams: B consecutive rows of the batch-ordered CSRs               */
+  const int32_t* s_indptr;           /* skills: B+1 absolute offsets, first row of the batch                          */
+  const int32_t* s_indices;
+  const int32_t* s_ent_row;          /* entry -> row of the gathered CSR (ntf_csr_gather); row_base = first batch row */
+  int row_base;
+  const int32_t* m_indptr;           /* members, likewise                                                             */
+  const int32_t* m_indices;
+  int gB;                            /* unigram_b over a GLOBAL batch this call is a slice of (data-parallel ranks):  */
+  const int32_t* g_m_indptr;         /*   its size and first row; gB = 0: the batch itself                            */
+  int nsd;                           /* ntf_nsd                                                                        */
+  uint64_t seed, step;
+  int row0, ns, neg_given;           /* neg_given != 0: neg[B,ns] holds caller-supplied indices (parity tests)        */
+  int32_t* neg;
+  uint32_t* counts;                  /* [E] scratch of ntf_expert_cdf                                                  */
+  uint32_t* cdf;                     /* [E]; for NTF_NS_UNIGRAM prepared by the caller once (fnn.py:82)               */
+  int precision;                     /* ntf_precision                                                                  */
+  float tpw, tnw, loss_scale;
+  float* loss_out;
+  uint32_t* special; int pitch_words;        /* NTF_FP32: row-major condition plane                                    */
+  uint32_t* special_t; uint32_t* member_t;   /* NTF_TF32: tile-transposed planes                                       */
+  int train, run_adam;
+  float* params; float* grads; float* adam_m; float* adam_v; size_t n_params;   /* the flat arena (ntf_adam_step)      */
+  double lr, beta1, beta2, eps; int64_t adam_t;
+  void* prof_ev[2];                  /* optional cudaEvent_t pair recorded around the output-layer call (bench.py's roofline timing) */
+} ntf_fnn_step_args;
+size_t ntf_fnn_step_workspace_bytes(const ntf_ctx* ctx, const ntf_fnn_step_args* args);
+int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args* args, void* workspace, size_t workspace_bytes);
+
 /* out[i] = sum_k parts[k*part_stride + i] in a fixed order (deterministic split reductions) */
 int ntf_sum_parts(ntf_ctx* ctx, void* stream, const float* parts, int nparts, size_t n, size_t part_stride, float* out);
 

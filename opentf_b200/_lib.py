@@ -24,6 +24,22 @@ class OutTrainArgs(C.Structure):
                 ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp)]
 
 
+NTF_MAX_LAYERS = 8
+_PA = vp * NTF_MAX_LAYERS
+
+
+class FnnStepArgs(C.Structure):
+    """mirror of ntf_fnn_step_args"""
+    _fields_ = [('n_layers', i32), ('S', i32), ('E', i32), ('hidden', i32 * NTF_MAX_LAYERS),
+                ('W', _PA), ('b', _PA), ('gW', _PA), ('gb', _PA), ('act', _PA), ('dact', _PA), ('dz', _PA),
+                ('B', i32), ('s_indptr', vp), ('s_indices', vp), ('s_ent_row', vp), ('row_base', i32), ('m_indptr', vp), ('m_indices', vp),
+                ('gB', i32), ('g_m_indptr', vp), ('nsd', i32), ('seed', u64), ('step', u64), ('row0', i32), ('ns', i32), ('neg_given', i32),
+                ('neg', vp), ('counts', vp), ('cdf', vp), ('precision', i32), ('tpw', f32), ('tnw', f32), ('loss_scale', f32), ('loss_out', vp),
+                ('special', vp), ('pitch_words', i32), ('special_t', vp), ('member_t', vp), ('train', i32), ('run_adam', i32),
+                ('params', vp), ('grads', vp), ('adam_m', vp), ('adam_v', vp), ('n_params', sz),
+                ('lr', f64), ('beta1', f64), ('beta2', f64), ('eps', f64), ('adam_t', i64), ('prof_ev', vp * 2)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/ntf_b200.h (tests/test_abi.py checks it)
 SIGNATURES = {
     'ntf_version': (i32, []),
@@ -69,6 +85,8 @@ SIGNATURES = {
     'ntf_dense_flipout_fwd_workspace_bytes': (sz, [i32, i32]),
     'ntf_dense_flipout_fwd': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, sz]),
     'ntf_add_signed': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    'ntf_fnn_step_workspace_bytes': (sz, [vp, C.POINTER(FnnStepArgs)]),
+    'ntf_fnn_step': (i32, [vp, vp, C.POINTER(FnnStepArgs), vp, sz]),
     'ntf_sum_parts': (i32, [vp, vp, vp, i32, sz, sz, vp]),
 }
 

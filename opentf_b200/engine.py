@@ -90,14 +90,30 @@ class SplitData:
 
 
 class _HostStage:
-    """device landing buffers of one host batch (same attributes `Engine.step` reads from a SplitData)"""
+    """device landing buffer of one host batch: ONE int32 block [s_indptr | m_indptr | s_indices | s_ent_row | m_indices] (one H2D copy
+    per step), with the same attributes `Engine.step` reads from a SplitData as views into it"""
 
-    def __init__(self, device, n, nnz_s, nnz_m):
-        i32 = torch.int32
-        self.cap, self.n = (n, nnz_s, nnz_m), 0
-        self.s_indptr = torch.zeros(n + 1, dtype=i32, device=device); self.m_indptr = torch.zeros(n + 1, dtype=i32, device=device)
-        self.s_indices = torch.zeros(nnz_s, dtype=i32, device=device); self.s_ent_row = torch.zeros(nnz_s, dtype=i32, device=device)
-        self.m_indices = torch.zeros(nnz_m, dtype=i32, device=device)
+    def __init__(self, device, words):
+        self.buf = torch.zeros(words, dtype=torch.int32, device=device)
+        self.n = 0
+
+    def view(self, n, nnz_s, nnz_m):
+        o, b = 0, self.buf
+        self.n = n
+        self.s_indptr = b[o:o + n + 1]; o += n + 1
+        self.m_indptr = b[o:o + n + 1]; o += n + 1
+        self.s_indices = b[o:o + nnz_s]; o += nnz_s
+        self.s_ent_row = b[o:o + nnz_s]; o += nnz_s
+        self.m_indices = b[o:o + nnz_m]; o += nnz_m
+        return o
+
+
+def pack_host_batch(s_ptr, s_idx, m_ptr, m_idx):
+    """compact CSR of one batch (numpy int arrays, offsets starting at 0) -> the pinned int32 block `Engine.step_host` copies"""
+    n = len(s_ptr) - 1
+    s_row = np.repeat(np.arange(n, dtype=np.int32), np.diff(s_ptr))
+    blk = np.concatenate([s_ptr, m_ptr, s_idx, s_row, m_idx]).astype(np.int32)
+    return torch.from_numpy(blk).pin_memory(), n, len(s_idx), len(m_idx)
 
 
 class Engine:
@@ -260,45 +276,60 @@ class Engine:
                        self.cdf if self.nsd != NSD['uniform'] else None, self.neg)
         return self.neg
 
+    def _fnn_args(self):
+        """the ntf_fnn_step_args of this engine with everything that does not change from step to step filled in"""
+        a = getattr(self, '_fa', None)
+        if a is not None: return a
+        a = _lib.FnnStepArgs()
+        a.n_layers, a.S, a.E = self.L, self.S, self.E
+        for i, hh in enumerate(self.hidden):
+            a.hidden[i] = hh
+            a.act[i], a.dact[i], a.dz[i] = self.act[i].data_ptr(), self.dact[i].data_ptr(), self.dz[i].data_ptr()
+        for i in range(self.L):
+            a.W[i], a.b[i] = self.view(f'layers.{i}.weight').data_ptr(), self.view(f'layers.{i}.bias').data_ptr()
+            a.gW[i], a.gb[i] = self.view(f'layers.{i}.weight', self.grads).data_ptr(), self.view(f'layers.{i}.bias', self.grads).data_ptr()
+        a.nsd, a.seed, a.ns = self.nsd, self.seed, self.ns
+        a.neg, a.counts, a.cdf = self.neg.data_ptr(), self.counts.data_ptr(), self.cdf.data_ptr()
+        a.precision, a.tpw, a.tnw = self.precision, self.tpw, self.tnw
+        if self.precision == _lib.NTF_TF32: a.special_t, a.member_t = self.special_t.data_ptr(), self.member_t.data_ptr()
+        else: a.special, a.pitch_words = self.special.data_ptr(), self.pitch
+        a.params, a.grads, a.adam_m, a.adam_v, a.n_params = self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.n_params
+        a.beta1, a.beta2, a.eps = 0.9, 0.999, 1e-8
+        self._fa = a
+        return a
+
     def step(self, sp, b0, B, train, lr=None, loss_slot=0, neg_host=None, loss_scale=None, gbatch=None, noise_host=None):
-        """one batch = rows [b0, b0+B) of split `sp`: forward + loss (+ backward + Adam when train).
-        The loss lands in self.loss_buf[loss_slot] (device); nothing is synchronised here."""
+        """one batch = rows [b0, b0+B) of split `sp`: forward + loss (+ backward + Adam when train), enqueued by one call of the
+        library (ntf_fnn_step).  The loss lands in self.loss_buf[loss_slot] (device); nothing is synchronised here."""
         assert 0 < B <= self.Bmax and b0 + B <= sp.n
         if self.bayesian: return self._step_bayes(sp, b0, B, train, lr, loss_slot, neg_host, loss_scale, gbatch, noise_host)
-        h_last = self.hidden[-1]
-        Lo = self.L - 1
-        self._forward_hidden(sp, b0, B)
-        neg = self._sample(sp, b0, B, neg_host, gbatch)
-        mptr = sp.m_indptr.data_ptr() + 4 * b0
-        ns = 0 if neg is None else neg.shape[1]
-        tc = self.precision == _lib.NTF_TF32
-        a = OutTrainArgs()
-        if tc:
-            ops.special_tiles(1, B, mptr, sp.m_indices, neg, ns, self.E, self.special_t, self.member_t)
-            a.special_t, a.member_t = self.special_t.data_ptr(), self.member_t.data_ptr()
-        else:
-            ops.special_bits(1, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
-            a.special, a.pitch_words = self.special.data_ptr(), self.pitch
-        a.A, a.W, a.b = self.act[-1].data_ptr(), self.view(f'layers.{Lo}.weight').data_ptr(), self.view(f'layers.{Lo}.bias').data_ptr()
-        a.m_indptr, a.m_indices = mptr, sp.m_indices.data_ptr()
-        a.B, a.h, a.E = B, h_last, self.E
-        a.tpw, a.tnw, a.loss_scale = self.tpw, self.tnw, (1.0 / B if loss_scale is None else loss_scale)
+        a = self._fnn_args()
+        a.B, a.row_base, a.row0 = B, b0, b0
+        a.s_indptr, a.s_indices, a.s_ent_row = sp.s_indptr.data_ptr() + 4 * b0, sp.s_indices.data_ptr(), sp.s_ent_row.data_ptr()
+        a.m_indptr, a.m_indices = sp.m_indptr.data_ptr() + 4 * b0, sp.m_indices.data_ptr()
+        if gbatch is None: a.gB, a.g_m_indptr = 0, None
+        else: a.gB, a.g_m_indptr = gbatch[1], sp.m_indptr.data_ptr() + 4 * gbatch[0]
+        a.step = self.global_step
+        a.neg_given, a.ns, a.neg = 0, self.ns, self.neg.data_ptr()
+        if neg_host is not None:  # host-supplied indices: the parity-test contract (SURVEY.md 9.3)
+            t = torch.as_tensor(np.ascontiguousarray(neg_host), dtype=torch.int32)
+            assert t.shape[0] == B
+            if t.shape[1] == self.neg.shape[1]: neg = self.neg[:B]
+            else: neg = self._neg_alt = torch.empty(B, t.shape[1], dtype=torch.int32, device=self.device)
+            neg.copy_(t)
+            a.neg_given, a.ns, a.neg = 1, t.shape[1], neg.data_ptr()
+        a.loss_scale = 1.0 / B if loss_scale is None else loss_scale
         a.loss_out = self.loss_buf.data_ptr() + 4 * loss_slot
+        a.train, a.run_adam = int(bool(train)), int(bool(train) and self.world == 1)
         if train:
-            a.dW, a.db = self.view(f'layers.{Lo}.weight', self.grads).data_ptr(), self.view(f'layers.{Lo}.bias', self.grads).data_ptr()
-            a.dA = self.dact[-1].data_ptr()
-        ops.out_train(self.dev_index, self.precision, a, self.ws)
-        if not tc: ops.special_bits(0, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)  # (the tensor-core kernel clears what it consumes)
+            a.lr, a.adam_t = float(lr), self.adam_t + 1
+        pe = getattr(self, 'prof_events', None)  # (bench.py) a recorded-once torch event pair around the output-layer call
+        a.prof_ev[0], a.prof_ev[1] = (pe[0].cuda_event, pe[1].cuda_event) if pe else (None, None)
+        ops.fnn_step(self.dev_index, a, self.ws)
         self.global_step += 1
         if not train: return
-        for i in range(self.L - 2, 0, -1):  # hidden dense layers
-            ops.act_bwd(self.dact[i], self.act[i], B, self.hidden[i], 1, self.dz[i], self.view(f'layers.{i}.bias', self.grads), self.ws)
-            ops.dense_bwd(self.act[i - 1], self.view(f'layers.{i}.weight'), self.dz[i], B, self.hidden[i - 1], self.hidden[i],
-                          self.view(f'layers.{i}.weight', self.grads), self.dact[i - 1], self.ws)
-        ops.act_bwd(self.dact[0], self.act[0], B, self.hidden[0], 1, self.dz[0], self.view('layers.0.bias', self.grads), self.ws)
-        ops.csr_bag_bwd(B, sp.s_indptr.data_ptr() + 4 * b0, sp.s_indices, sp.s_ent_row, b0, self.dz[0], self.S, self.hidden[0],
-                        self.view('layers.0.weight', self.grads), self.ws)
-        self.optimizer_step(lr)
+        if self.world == 1: self.adam_t += 1
+        else: self.optimizer_step(lr)
 
     def optimizer_step(self, lr):
         if self.world > 1:
@@ -431,19 +462,15 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ streaming entry point (host batches)
-    def step_host(self, s_ptr, s_idx, s_row, m_ptr, m_idx, rank=0, G=1, lr=1e-3, train=True):
-        """one step on a batch the HOST holds: compact CSR of the global batch (pinned int32 tensors: skill indptr / indices /
-        entry->row, member indptr / indices) is copied to the device, this rank trains on its slice, and the loss comes
-        back to the host (one sync) -- the per-step shape of the reference's loop (fnn.py:118-140: H2D of the batch, .item())."""
-        n, nnz_s, nnz_m = s_ptr.numel() - 1, s_idx.numel(), m_idx.numel()
+    def step_host(self, packed, n, nnz_s, nnz_m, rank=0, G=1, lr=1e-3, train=True):
+        """one step on a batch the HOST holds (`pack_host_batch`: compact CSR of the global batch in one pinned block): one H2D copy,
+        this rank trains on its slice, and the loss comes back to the host (one sync) -- the per-step shape of the reference's loop
+        (fnn.py:118-140: H2D of the batch, .item())."""
         st = getattr(self, '_hstage', None)
-        if st is None or st.cap[0] < n or st.cap[1] < nnz_s or st.cap[2] < nnz_m:
-            st = _HostStage(self.device, max(n, self.Bmax), 2 * nnz_s + 64, 2 * nnz_m + 64)
-            self._hstage = st
-        st.n = n
-        st.s_indptr[:n + 1].copy_(s_ptr, non_blocking=True); st.s_indices[:nnz_s].copy_(s_idx, non_blocking=True)
-        st.s_ent_row[:nnz_s].copy_(s_row, non_blocking=True)
-        st.m_indptr[:n + 1].copy_(m_ptr, non_blocking=True); st.m_indices[:nnz_m].copy_(m_idx, non_blocking=True)
+        if st is None or st.buf.numel() < packed.numel():
+            st = self._hstage = _HostStage(self.device, 2 * packed.numel() + 1024)
+        st.view(n, nnz_s, nnz_m)
+        st.buf[:packed.numel()].copy_(packed, non_blocking=True)
         b = -(-n // G)
         lo, hi = min(n, rank * b), min(n, (rank + 1) * b)
         self.step(st, lo, hi - lo, train, lr=lr, loss_slot=0, loss_scale=1.0 / n, gbatch=(0, n))

@@ -205,3 +205,10 @@ def dense_flipout_fwd(A, W, b, A_s, Wd, bd, sign_out, pitch, B, inn, out, act, Y
 def add_signed(X, bits, pitch, B, h, Y):
     d = _dev(X)
     check(lib().ntf_add_signed(_lib.ctx(d), _stream(d), _p(X, F32), _p(bits), pitch, B, h, _p(Y, F32)), 'ntf_add_signed')
+
+
+def fnn_step(dev, args, ws):
+    """one whole Fnn batch (ntf_fnn_step): args is a filled _lib.FnnStepArgs"""
+    h = _lib.ctx(dev)
+    p, nb = ws.get(lib().ntf_fnn_step_workspace_bytes(h, C.byref(args)))
+    check(lib().ntf_fnn_step(h, _stream(dev), C.byref(args), p, nb), 'ntf_fnn_step')

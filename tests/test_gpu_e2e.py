@@ -170,3 +170,29 @@ def test_evaluate_writes_reference_csvs(toy, tmp_path):
         for name in mean.index:
             assert abs(mean.loc[name, 'mean'] - z[f'eval/f{k}/mean_values'][names.index(name)]) < 1e-6, (k, name)
     assert os.path.exists(f'{m.output}/test.pred.eval.mean.csv')
+
+
+def test_step_host_is_the_same_step_as_the_resident_path(toy):
+    """Engine.step_host (host batch -> one H2D block -> ntf_fnn_step -> loss back) against Engine.step on the staged split"""
+    from opentf_b200.engine import Engine, pack_host_batch, to_csr
+    skill, member, splits, _ = toy('gith')
+    rows = np.asarray(splits['folds'][0]['train'])[:16]
+    torch.manual_seed(0)
+    layers = O.init_params(skill.shape[1], [32], member.shape[1])
+    sd = {f'layers.{i}.{n}': t for i, (W, b) in enumerate(layers) for n, t in (('weight', W), ('bias', b))}
+    out = []
+    for mode in ('resident', 'host'):
+        eng = Engine(skill.shape[1], [32], member.shape[1], 'cuda:0', precision='fp32', nsd='unigram_b', ns=5, seed=7, max_batch=16)
+        eng.stage(skill, member)
+        eng.load_state_dict(sd)
+        if mode == 'resident':
+            sp = eng.split(rows)
+            for i in range(3): eng.step(sp, 0, 16, True, lr=1e-2, loss_slot=i)
+            losses = eng.loss_buf[:3].cpu().numpy().copy()
+        else:
+            (sp_, si, _), (mp_, mi, _) = to_csr(skill[rows]), to_csr(member[rows])
+            packed = pack_host_batch(sp_, si, mp_, mi)
+            losses = np.array([eng.step_host(*packed, lr=1e-2) for _ in range(3)], dtype=np.float32)
+        out.append((losses, eng.params.cpu().clone()))
+    assert np.array_equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert out[0][0][2] < out[0][0][0]
