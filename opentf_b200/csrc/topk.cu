@@ -113,6 +113,90 @@ __global__ void __launch_bounds__(TK_THREADS) topk_select_kernel(const float* __
   }
 }
 
+// Small K (<= 32: the k = 2..10 of the evaluation metrics, evl/metric.py:17-28): ONE pass over the row.  Each warp keeps the K best of
+// its share of the row as 64-bit composites (ordered score << 32 | ~expert: larger = better score, then lower id), rank r in lane r.
+// A lane compares its four new scores with the warp's K-th best -- after the first few hundred elements almost every score fails that
+// single compare, so the warp-wide insert (one shuffle-shift) is rare -- and at the end warp 0 merges the 8 warp lists.
+// HBM/L2-bound: 4*E bytes per team, read once.
+__global__ void __launch_bounds__(TK_THREADS) topk_small_kernel(const float* __restrict__ P, int E, int K, float scale,
+                                                                float* __restrict__ vals, int32_t* __restrict__ idx) {
+  __shared__ unsigned long long wbest[TK_THREADS];  // [8 warps][32 ranks]
+  const float* p = P + (size_t)blockIdx.x * E;
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned long long mine = 0ull;   // rank `lane` of this warp's list (0 = empty; lanes >= K stay empty)
+  unsigned long long kth = 0ull;    // the warp's K-th best = the bar a new score has to clear
+  auto insert = [&](unsigned long long c) {  // warp-uniform c > kth
+    const unsigned long long up = __shfl_up_sync(0xffffffffu, mine, 1);
+    const unsigned long long prev = lane == 0 ? ~0ull : up;
+    if (c > mine) mine = c > prev ? prev : c;  // ranks below the insertion point shift down by one, the point takes c
+    if (lane >= K) mine = 0ull;
+    kth = __shfl_sync(0xffffffffu, mine, K - 1);
+  };
+  auto offer4 = [&](float4 v, int j, bool ok) {
+    unsigned long long c[4];
+    c[0] = ((unsigned long long)ordered_key(v.x * scale) << 32) | (uint32_t)(~(uint32_t)j);
+    c[1] = ((unsigned long long)ordered_key(v.y * scale) << 32) | (uint32_t)(~(uint32_t)(j + 1));
+    c[2] = ((unsigned long long)ordered_key(v.z * scale) << 32) | (uint32_t)(~(uint32_t)(j + 2));
+    c[3] = ((unsigned long long)ordered_key(v.w * scale) << 32) | (uint32_t)(~(uint32_t)(j + 3));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      unsigned hit = __ballot_sync(0xffffffffu, ok && j + q < E && c[q] > kth);
+      while (hit) {  // rare
+        const int L = __ffs(hit) - 1;
+        hit &= hit - 1;
+        const unsigned long long cand = __shfl_sync(0xffffffffu, c[q], L);
+        if (cand > kth) insert(cand);  // (an earlier insert of this round may have raised the bar)
+      }
+    }
+  };
+  const bool vec = (E & 3) == 0 && ((uintptr_t)p & 15) == 0;
+  const int n4 = (E + 3) >> 2;  // groups of 4 consecutive scores; thread tid takes groups tid, tid + 256, ...
+  for (int g0 = 0; g0 < n4; g0 += TK_THREADS * 4) {  // 4 loads in flight per thread
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int g = g0 + u * TK_THREADS + tid;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g < n4) {
+        if (vec) v[u] = __ldg(reinterpret_cast<const float4*>(p) + g);
+        else {
+          const int j = 4 * g;
+          v[u].x = __ldg(p + j);
+          if (j + 1 < E) v[u].y = __ldg(p + j + 1);
+          if (j + 2 < E) v[u].z = __ldg(p + j + 2);
+          if (j + 3 < E) v[u].w = __ldg(p + j + 3);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int g = g0 + u * TK_THREADS + tid;
+      offer4(v[u], 4 * g, g < n4);
+    }
+  }
+  wbest[tid] = mine;
+  __syncthreads();
+  if (tid < 32) {  // merge the 8 sorted warp lists: K rounds of "largest head wins and is popped"; lane l < 8 plays warp l's list
+    int head = 0;
+    unsigned long long out = 0ull;
+    for (int r = 0; r < K; ++r) {
+      unsigned long long h = (lane < TK_THREADS / 32 && head < K) ? wbest[lane * 32 + head] : 0ull;
+      unsigned long long m = h;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+      }
+      if (lane == r) out = m;
+      if (h == m && m != 0ull) ++head;  // composites are unique (they carry the expert id): exactly one list pops
+    }
+    if (lane < K) {
+      vals[(size_t)blockIdx.x * K + lane] = key_to_float((uint32_t)(out >> 32));
+      idx[(size_t)blockIdx.x * K + lane] = (int32_t)(~(uint32_t)out);
+    }
+  }
+}
+
 // merge G candidate lists of length K per team: sort G*K composites, keep K
 __global__ void __launch_bounds__(TK_THREADS) topk_merge_kernel(const float* __restrict__ vals_in, const int32_t* __restrict__ idx_in,
                                                                 int G, int B, int K, int npad, float* __restrict__ vals,
@@ -164,6 +248,11 @@ extern "C" int ntf_topk_select(ntf_ctx* ctx, void* stream, const float* P, int B
   NTF_REQUIRE(B > 0 && E > 0 && K > 0 && K <= E, NTF_ERR_BAD_ARG, "topk_select: B=%d E=%d K=%d", B, E, K);
   NTF_REQUIRE(K <= TK_KMAX, NTF_ERR_UNSUPPORTED, "topk_select: K=%d > %d", K, TK_KMAX);
   NTF_REQUIRE(scale > 0.f, NTF_ERR_BAD_ARG, "topk_select: scale must be positive");
+  if (K <= 32) {  // single-pass kernel (a zero composite = "no candidate" cannot collide: a real score has a non-zero ordered key)
+    NTF_COUNT_LAUNCH; topk_small_kernel<<<B, TK_THREADS, 0, as_stream(stream)>>>(P, E, K, scale, vals, idx);
+    NTF_LAUNCH_CHECK();
+    return NTF_OK;
+  }
   const int Kpad = next_pow2(K);
   NTF_COUNT_LAUNCH; topk_select_kernel<<<B, TK_THREADS, (size_t)Kpad * 8, as_stream(stream)>>>(P, E, K, Kpad, scale, vals, idx);
   NTF_LAUNCH_CHECK();
