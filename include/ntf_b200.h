@@ -107,9 +107,11 @@ int ntf_neg_sample(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed, uint64_t 
                    const int32_t* m_indptr, const int32_t* m_indices, int E, int ns, const uint32_t* cdf,
                    int32_t* neg);
 /* special[n, j/32] bit j%32 = 1 iff j is a member of team n or j is in neg[n,:]: the reference's `condition` tensor
- * (fnn.py:33-43), bit-packed.  op 1 sets the bits, op 0 clears the same words again (no full memset per step). */
+ * (fnn.py:33-43), bit-packed.  op 1 sets the bits, op 0 clears the same words again (no full memset per step).
+ * Expert-sharded output layer: the plane covers this rank's E columns [e_lo, e_lo + E) of the global expert axis; member
+ * and negative ids are GLOBAL and those outside the range are skipped (e_lo = 0, E = all experts otherwise). */
 int ntf_special_bits(ntf_ctx* ctx, void* stream, int op, int B, const int32_t* m_indptr, const int32_t* m_indices,
-                     const int32_t* neg, int ns, int E, uint32_t* special, int pitch_words);
+                     const int32_t* neg, int ns, int E, int e_lo, uint32_t* special, int pitch_words);
 
 /* The same two sets, laid out for the tensor-core kernel (NTF_TF32): teams in tiles of 128, per tile one slab of Epad = roundup(E,128)
  * experts x 4 words; word ((n/128)*Epad + j)*4 + (n%128)/32, bit n%32.  special_t: j is a member of team n or in neg[n,:];
@@ -118,7 +120,7 @@ int ntf_special_bits(ntf_ctx* ctx, void* stream, int op, int B, const int32_t* m
  * clears what it consumes).  A CTA's (tile, 128-expert) slice is 2 KB contiguous. */
 size_t ntf_special_tiles_bytes(int B, int E);
 int ntf_special_tiles(ntf_ctx* ctx, void* stream, int op, int B, const int32_t* m_indptr, const int32_t* m_indices,
-                      const int32_t* neg, int ns, int E, uint32_t* special_t, uint32_t* member_t);
+                      const int32_t* neg, int ns, int E, int e_lo, uint32_t* special_t, uint32_t* member_t);
 
 /* ---- output layer, training: last layer of fnn.py:25 + fnn.py:32-46,135 + its autograd (fnn.py:137) -----------------
  * z = A W^T + b ; x = lrelu(z) ; w = special ? tpw : tnw ; y = [j is a member of team n]
@@ -153,6 +155,7 @@ typedef struct {
    * They are CONSUMED: the kernel zeroes every word it used, so the planes are clean for the next batch.   */
   uint32_t* special_t;         /* ntf_special_tiles planes                                           */
   uint32_t* member_t;
+  int e_lo;                    /* expert-sharded layer: W/b/dW/db and the planes cover columns [e_lo, e_lo+E); m_indices are global */
 } ntf_out_train_args;
 /* 1 if NTF_TF32 has a tcgen05 kernel for this shape (else callers use NTF_FP32; ntf_out_train(NTF_TF32) refuses it) */
 int ntf_tc_supported(int B, int h, int E, int flipout);
@@ -224,7 +227,10 @@ int ntf_add_signed(ntf_ctx* ctx, void* stream, const float* X, const uint32_t* b
 #define NTF_MAX_LAYERS 8
 typedef struct {
   int n_layers;                      /* linear layers (hidden layers + 1)                                              */
-  int S, E;
+  int S, E;                          /* E = the output columns THIS call owns (all experts, or one shard of them)      */
+  int e_lo, E_total;                 /* expert-sharded output layer: columns [e_lo, e_lo+E) of E_total (0, E otherwise) */
+  int phase;                         /* 3 = whole step; 1 = up to and including the output layer; 2 = the rest of the backward pass +
+                                        Adam (a sharded layer all-reduces dact[last] and the loss between the two)     */
   int hidden[NTF_MAX_LAYERS];        /* widths of the hidden layers: n_layers - 1 entries                             */
   const float* W[NTF_MAX_LAYERS];    /* layer 0 TRANSPOSED [S,h0] (ntf_csr_bag_fwd); layer i>0 [out,in]                */
   const float* b[NTF_MAX_LAYERS];

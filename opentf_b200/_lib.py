@@ -21,7 +21,7 @@ class OutTrainArgs(C.Structure):
     _fields_ = [('A', vp), ('W', vp), ('b', vp), ('special', vp), ('pitch_words', i32), ('m_indptr', vp), ('m_indices', vp),
                 ('B', i32), ('h', i32), ('E', i32), ('tpw', f32), ('tnw', f32), ('loss_scale', f32),
                 ('dW', vp), ('db', vp), ('dA', vp), ('loss_out', vp),
-                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp)]
+                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp), ('e_lo', i32)]
 
 
 NTF_MAX_LAYERS = 8
@@ -30,7 +30,7 @@ _PA = vp * NTF_MAX_LAYERS
 
 class FnnStepArgs(C.Structure):
     """mirror of ntf_fnn_step_args"""
-    _fields_ = [('n_layers', i32), ('S', i32), ('E', i32), ('hidden', i32 * NTF_MAX_LAYERS),
+    _fields_ = [('n_layers', i32), ('S', i32), ('E', i32), ('e_lo', i32), ('E_total', i32), ('phase', i32), ('hidden', i32 * NTF_MAX_LAYERS),
                 ('W', _PA), ('b', _PA), ('gW', _PA), ('gb', _PA), ('act', _PA), ('dact', _PA), ('dz', _PA),
                 ('B', i32), ('s_indptr', vp), ('s_indices', vp), ('s_ent_row', vp), ('row_base', i32), ('m_indptr', vp), ('m_indices', vp),
                 ('gB', i32), ('g_m_indptr', vp), ('nsd', i32), ('seed', u64), ('step', u64), ('row0', i32), ('ns', i32), ('neg_given', i32),
@@ -61,9 +61,9 @@ SIGNATURES = {
     'ntf_expert_cdf_workspace_bytes': (sz, [i32]),
     'ntf_expert_cdf': (i32, [vp, vp, i32, vp, vp, i32, vp, vp, vp, sz]),
     'ntf_neg_sample': (i32, [vp, vp, i32, u64, u64, i32, i32, vp, vp, i32, i32, vp, vp]),
-    'ntf_special_bits': (i32, [vp, vp, i32, i32, vp, vp, vp, i32, i32, vp, i32]),
+    'ntf_special_bits': (i32, [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, i32]),
     'ntf_special_tiles_bytes': (sz, [i32, i32]),
-    'ntf_special_tiles': (i32, [vp, vp, i32, i32, vp, vp, vp, i32, i32, vp, vp]),
+    'ntf_special_tiles': (i32, [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp]),
     'ntf_tc_supported': (i32, [i32, i32, i32, i32]),
     'ntf_out_train_workspace_bytes': (sz, [vp, i32, i32, i32, i32, i32]),
     'ntf_out_train': (i32, [vp, vp, i32, C.POINTER(OutTrainArgs), vp, sz]),

@@ -120,7 +120,7 @@ struct EpiBiasAct {
 // output layer forward + weighted BCE + dz  (fnn.py:25,32-46,135 and the first step of its autograd)
 struct EpiLoss {
   const float* bias; const float* addend; long long ld;  // addend: Flipout perturbation term T[m,n] (nullable)
-  const uint32_t* special; int pitch; const int32_t* m_indptr; const int32_t* m_indices;
+  const uint32_t* special; int pitch; const int32_t* m_indptr; const int32_t* m_indices; int e_lo;
   float tpw, tnw, scale;
   float* dz;                                  // [B,E] or NULL (validation step)
   const uint32_t* sign_out; float* dzs;       // Flipout: dzs = dz * s_out
@@ -135,7 +135,7 @@ struct EpiLoss {
       float z = v[q] + __ldg(bias + n + q);
       if (addend) z += addend[(long long)m * ld + n + q];
       const bool sp = (word >> q) & 1u;
-      const bool y = sp && is_member(m_indptr, m_indices, m, n + q);
+      const bool y = sp && is_member(m_indptr, m_indices, m, n + q + e_lo);
       float l, g;
       bce_elem<false>(z, y, sp ? tpw : tnw, scale, l, g);
       loss_acc += l;
@@ -334,7 +334,7 @@ int ntf_out_train_fp32(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* 
   }
   {
     GemmArgs g{B, E, h, a->A, h, 1, a->W, h, 1, h};
-    EpiLoss e{a->b, flip ? w.T : nullptr, E, a->special, a->pitch_words, a->m_indptr, a->m_indices, a->tpw, a->tnw,
+    EpiLoss e{a->b, flip ? w.T : nullptr, E, a->special, a->pitch_words, a->m_indptr, a->m_indices, a->e_lo, a->tpw, a->tnw,
               a->loss_scale, train ? w.dz : nullptr, a->sign_out, (train && flip) ? w.dzs : nullptr, w.loss_part, 0.f};
     if ((rc = launch_gemm(st, g, e))) return rc;
     if ((rc = ntf_loss_reduce_impl(st, w.loss_part, cdiv(B, BM) * cdiv(E, BN), a->loss_scale, a->loss_out))) return rc;

@@ -105,18 +105,20 @@ __global__ void __launch_bounds__(NS_WARPS * 32) neg_sample_kernel(int nsd, uint
 }
 
 __global__ void special_bits_kernel(int op, int B, const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_indices,
-                                    const int32_t* __restrict__ neg, int ns, int E, uint32_t* __restrict__ special, int pitch) {
+                                    const int32_t* __restrict__ neg, int ns, int E, int e_lo, uint32_t* __restrict__ special, int pitch) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= B) return;
   uint32_t* row = special + (size_t)n * pitch;
   // one thread owns the whole row of the plane, so plain read-modify-write is race free
   for (int p = m_indptr[n]; p < m_indptr[n + 1]; ++p) {
-    const int j = m_indices[p];
+    const int j = m_indices[p] - e_lo;  // expert-sharded output layer: this rank's columns are [e_lo, e_lo + E)
+    if (j < 0 || j >= E) continue;
     if (op) row[j >> 5] |= 1u << (j & 31); else row[j >> 5] = 0u;
   }
   if (neg)
     for (int q = 0; q < ns; ++q) {
-      const int j = neg[(size_t)n * ns + q];
+      if (neg[(size_t)n * ns + q] < 0) continue;
+      const int j = neg[(size_t)n * ns + q] - e_lo;
       if (j < 0 || j >= E) continue;
       if (op) row[j >> 5] |= 1u << (j & 31); else row[j >> 5] = 0u;
     }
@@ -124,7 +126,7 @@ __global__ void special_bits_kernel(int op, int B, const int32_t* __restrict__ m
 
 // tile-transposed planes for the tensor-core output kernel: word ((n/128)*Epad + j)*4 + (n%128)/32, bit n%32
 __global__ void special_tiles_kernel(int op, int B, const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_indices,
-                                     const int32_t* __restrict__ neg, int ns, int E, int Epad, uint32_t* __restrict__ special_t,
+                                     const int32_t* __restrict__ neg, int ns, int E, int e_lo, int Epad, uint32_t* __restrict__ special_t,
                                      uint32_t* __restrict__ member_t) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= B) return;
@@ -132,12 +134,15 @@ __global__ void special_tiles_kernel(int op, int B, const int32_t* __restrict__ 
   const int wq = (n & 127) >> 5;
   const uint32_t bit = 1u << (n & 31);
   for (int p = m_indptr[n]; p < m_indptr[n + 1]; ++p) {
-    const size_t w = (slab + m_indices[p]) * 4 + wq;
+    const int jm = m_indices[p] - e_lo;
+    if (jm < 0 || jm >= E) continue;
+    const size_t w = (slab + jm) * 4 + wq;
     if (op) { atomicOr(special_t + w, bit); atomicOr(member_t + w, bit); } else { special_t[w] = 0u; member_t[w] = 0u; }  // clearing: every writer stores 0
   }
   if (neg)
     for (int q = 0; q < ns; ++q) {
-      const int j = neg[(size_t)n * ns + q];
+      if (neg[(size_t)n * ns + q] < 0) continue;
+      const int j = neg[(size_t)n * ns + q] - e_lo;
       if (j < 0 || j >= E) continue;
       const size_t w = (slab + j) * 4 + wq;
       if (op) atomicOr(special_t + w, bit); else special_t[w] = 0u;
@@ -148,11 +153,11 @@ __global__ void special_tiles_kernel(int op, int B, const int32_t* __restrict__ 
 extern "C" size_t ntf_special_tiles_bytes(int B, int E) { return (size_t)cdiv(B, 128) * (size_t)(cdiv(E, 128) * 128) * 16; }
 
 extern "C" int ntf_special_tiles(ntf_ctx* ctx, void* stream, int op, int B, const int32_t* m_indptr, const int32_t* m_indices,
-                                 const int32_t* neg, int ns, int E, uint32_t* special_t, uint32_t* member_t) {
+                                 const int32_t* neg, int ns, int E, int e_lo, uint32_t* special_t, uint32_t* member_t) {
   NTF_REQUIRE(ctx && m_indptr && m_indices && special_t && member_t, NTF_ERR_BAD_ARG, "special_tiles: null pointer");
   NTF_REQUIRE(B > 0 && E > 0, NTF_ERR_BAD_ARG, "special_tiles: B=%d E=%d", B, E);
   NTF_REQUIRE((((uintptr_t)special_t | (uintptr_t)member_t) & 15) == 0, NTF_ERR_BAD_ARG, "special_tiles: planes must be 16-byte aligned");
-  NTF_COUNT_LAUNCH; special_tiles_kernel<<<cdiv(B, 128), 128, 0, as_stream(stream)>>>(op, B, m_indptr, m_indices, neg, ns, E, cdiv(E, 128) * 128, special_t, member_t);
+  NTF_COUNT_LAUNCH; special_tiles_kernel<<<cdiv(B, 128), 128, 0, as_stream(stream)>>>(op, B, m_indptr, m_indices, neg, ns, E, e_lo, cdiv(E, 128) * 128, special_t, member_t);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
@@ -183,10 +188,10 @@ extern "C" int ntf_neg_sample(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed
 }
 
 extern "C" int ntf_special_bits(ntf_ctx* ctx, void* stream, int op, int B, const int32_t* m_indptr, const int32_t* m_indices,
-                                const int32_t* neg, int ns, int E, uint32_t* special, int pitch_words) {
+                                const int32_t* neg, int ns, int E, int e_lo, uint32_t* special, int pitch_words) {
   NTF_REQUIRE(ctx && m_indptr && m_indices && special, NTF_ERR_BAD_ARG, "special_bits: null pointer");
   NTF_REQUIRE(B > 0 && E > 0 && pitch_words * 32 >= E, NTF_ERR_BAD_ARG, "special_bits: B=%d E=%d pitch=%d", B, E, pitch_words);
-  NTF_COUNT_LAUNCH; special_bits_kernel<<<cdiv(B, 128), 128, 0, as_stream(stream)>>>(op, B, m_indptr, m_indices, neg, ns, E, special, pitch_words);
+  NTF_COUNT_LAUNCH; special_bits_kernel<<<cdiv(B, 128), 128, 0, as_stream(stream)>>>(op, B, m_indptr, m_indices, neg, ns, E, e_lo, special, pitch_words);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

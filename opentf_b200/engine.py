@@ -118,13 +118,20 @@ def pack_host_batch(s_ptr, s_idx, m_ptr, m_idx):
 
 class Engine:
     def __init__(self, S, hidden, E, device, bayesian=False, precision='tf32', tpw=10.0, tnw=1.0, nsd='uniform', ns=5,
-                 seed=0, max_batch=1000):
+                 seed=0, max_batch=1000, shard=None):
+        """shard=(i, n): expert-sharded output layer (BASELINE config 4): this engine owns columns
+        [E*i//n, E*(i+1)//n) of the last layer (weights, gradients, Adam state, special planes); everything else is replicated and
+        the ranks exchange only dA [B,h] per step (`allreduce`)."""
         if not torch.cuda.is_available():
             raise _lib.NtfError('opentf_b200 needs a CUDA device: the kernels are sm_100a only and there is no CPU fallback')
         self.device = torch.device(device)
         self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         _lib.ctx(self.dev_index)  # fails loudly if this is not a B200-class device
-        self.S, self.hidden, self.E = int(S), [int(x) for x in hidden], int(E)
+        self.S, self.hidden, self.E_total = int(S), [int(x) for x in hidden], int(E)
+        self.shard = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
+        self.e_lo, self.e_hi = self.E_total * self.shard[0] // self.shard[1], self.E_total * (self.shard[0] + 1) // self.shard[1]
+        self.E = self.e_hi - self.e_lo  # the output columns this engine owns
+        if self.shard[1] > 1 and bayesian: raise NotImplementedError('expert-sharded Bnn')
         self.bayesian, self.precision = bool(bayesian), PRECISION[precision]
         # 'tf32' selects the tcgen05 kernels where they exist for the shape; other shapes (toy sizes, odd widths) run the
         # CUDA-core fp32 kernels of the same library -- both are sm_100a code, neither is a fallback to another backend.
@@ -180,8 +187,8 @@ class Engine:
             self.special_t = torch.zeros(words, dtype=torch.int32, device=dev)
             self.member_t = torch.zeros(words, dtype=torch.int32, device=dev)
         self.neg = torch.full((B, max(1, self.ns)), -1, dtype=torch.int32, device=dev)
-        self.counts = torch.zeros(self.E, dtype=torch.int32, device=dev)
-        self.cdf = torch.zeros(self.E, dtype=torch.int32, device=dev)
+        self.counts = torch.zeros(self.E_total, dtype=torch.int32, device=dev)  # the sampler works on the global expert axis
+        self.cdf = torch.zeros(self.E_total, dtype=torch.int32, device=dev)
         self.loss_buf = torch.zeros(4096, dtype=f32, device=dev)
         if self.bayesian:
             self.eps = torch.zeros(self.n_noise, dtype=f32, device=dev)
@@ -211,17 +218,33 @@ class Engine:
         for name in self.views:
             t = torch.as_tensor(sd[name]).detach().to(torch.float32)
             if name.startswith('layers.0.') and name.endswith('weight'): t = t.t()
+            if name.startswith(f'layers.{self.L - 1}.') and self.shard[1] > 1: t = t[self.e_lo:self.e_hi]  # this shard's experts
             v = self.view(name)
             if tuple(t.shape) != tuple(v.shape): raise ValueError(f'{name}: shape {tuple(t.shape)} does not fit {tuple(v.shape)}')
             v.copy_(t.contiguous())
 
-    def state_dict(self):
+    def state_dict(self, gather=True):
+        """torch-layout state dict.  Expert-sharded: the last layer's shards are all-gathered (a collective: every rank calls it);
+        gather=False returns this shard only."""
         out = {}
         for name in self.views:
-            t = self.view(name).detach().cpu().clone()
+            t = self.view(name).detach()
+            if name.startswith(f'layers.{self.L - 1}.') and self.shard[1] > 1 and gather:
+                n = self.shard[1]
+                rows = max(self.E_total * (i + 1) // n - self.E_total * i // n for i in range(n))
+                pad = torch.zeros((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+                pad[:t.shape[0]] = t
+                parts = [torch.empty_like(pad) for _ in range(n)]
+                torch.distributed.all_gather(parts, pad)
+                t = torch.cat([parts[i][:self.E_total * (i + 1) // n - self.E_total * i // n] for i in range(n)])
+            t = t.cpu().clone()
             if name.startswith('layers.0.') and name.endswith('weight'): t = t.t().contiguous()
             out[name] = t
         return out
+
+    def allreduce(self, t):
+        """SUM over the ranks that share a step (tests of the sharded layer replace this with an in-process sum)"""
+        torch.distributed.all_reduce(t)
 
     def reset_optimizer(self):
         self.adam_m.zero_(); self.adam_v.zero_(); self.adam_t = 0
@@ -229,7 +252,7 @@ class Engine:
     # ------------------------------------------------------------------ data
     def stage(self, skill_mat, member_mat):
         self.skill, self.member = DeviceCSR(skill_mat, self.device), DeviceCSR(member_mat, self.device)
-        assert self.skill.shape[1] == self.S and self.member.shape[1] == self.E
+        assert self.skill.shape[1] == self.S and self.member.shape[1] == self.E_total
         if self.bayesian:  # Flipout input signs exist only at the nnz positions: one bit per CSR entry of a batch
             maxlen = int(np.diff(self.skill.host_indptr).max()) if self.skill.shape[0] else 1
             self._ent_sign_words(self.Bmax * max(1, maxlen))
@@ -247,7 +270,7 @@ class Engine:
     def set_global_unigram(self):
         """fnn.py:82: expert frequency over ALL teams -> integer counts + CDF (nsd == 'unigram')."""
         N = self.member.shape[0]
-        ops.expert_cdf(N, self.member.indptr.data_ptr(), self.member.indices, self.E, self.counts, self.cdf, self.ws)
+        ops.expert_cdf(N, self.member.indptr.data_ptr(), self.member.indices, self.E_total, self.counts, self.cdf, self.ws)
 
     # ------------------------------------------------------------------ one step
     def _forward_hidden(self, sp, b0, B):
@@ -271,8 +294,8 @@ class Engine:
         mptr = sp.m_indptr.data_ptr() + 4 * b0
         if self.nsd == NSD['unigram_b']:
             g0, gB = (b0, B) if gbatch is None else gbatch
-            ops.expert_cdf(gB, sp.m_indptr.data_ptr() + 4 * g0, sp.m_indices, self.E, self.counts, self.cdf, self.ws)
-        ops.neg_sample(self.nsd, self.seed, self.global_step, b0, B, mptr, sp.m_indices, self.E, self.ns,
+            ops.expert_cdf(gB, sp.m_indptr.data_ptr() + 4 * g0, sp.m_indices, self.E_total, self.counts, self.cdf, self.ws)
+        ops.neg_sample(self.nsd, self.seed, self.global_step, b0, B, mptr, sp.m_indices, self.E_total, self.ns,
                        self.cdf if self.nsd != NSD['uniform'] else None, self.neg)
         return self.neg
 
@@ -281,7 +304,7 @@ class Engine:
         a = getattr(self, '_fa', None)
         if a is not None: return a
         a = _lib.FnnStepArgs()
-        a.n_layers, a.S, a.E = self.L, self.S, self.E
+        a.n_layers, a.S, a.E, a.e_lo, a.E_total = self.L, self.S, self.E, self.e_lo, self.E_total
         for i, hh in enumerate(self.hidden):
             a.hidden[i] = hh
             a.act[i], a.dact[i], a.dz[i] = self.act[i].data_ptr(), self.dact[i].data_ptr(), self.dz[i].data_ptr()
@@ -320,16 +343,27 @@ class Engine:
             a.neg_given, a.ns, a.neg = 1, t.shape[1], neg.data_ptr()
         a.loss_scale = 1.0 / B if loss_scale is None else loss_scale
         a.loss_out = self.loss_buf.data_ptr() + 4 * loss_slot
-        a.train, a.run_adam = int(bool(train)), int(bool(train) and self.world == 1)
+        sharded = self.shard[1] > 1
+        dp = self.world > 1 and not sharded  # data-parallel ranks all-reduce the gradient arena before Adam
+        a.train, a.run_adam = int(bool(train)), int(bool(train) and not dp)
         if train:
             a.lr, a.adam_t = float(lr), self.adam_t + 1
         pe = getattr(self, 'prof_events', None)  # (bench.py) a recorded-once torch event pair around the output-layer call
         a.prof_ev[0], a.prof_ev[1] = (pe[0].cuda_event, pe[1].cuda_event) if pe else (None, None)
-        ops.fnn_step(self.dev_index, a, self.ws)
+        if sharded and train:
+            # every rank runs the same batch on its expert range; the only exchange is dA = sum over shards of dz W  [B,h]
+            a.phase = 1
+            ops.fnn_step(self.dev_index, a, self.ws)
+            self.allreduce(self.dact[-1][:B])
+            a.phase = 2
+            ops.fnn_step(self.dev_index, a, self.ws)
+        else:
+            a.phase = 3
+            ops.fnn_step(self.dev_index, a, self.ws)
         self.global_step += 1
         if not train: return
-        if self.world == 1: self.adam_t += 1
-        else: self.optimizer_step(lr)
+        if dp: self.optimizer_step(lr)
+        else: self.adam_t += 1
 
     def optimizer_step(self, lr):
         if self.world > 1:
@@ -491,5 +525,23 @@ class Engine:
         return self.select_topk(scores_buf, B, K, vals, idx)
 
     def select_topk(self, scores_buf, B, K, vals, idx):
-        ops.topk_select(scores_buf, B, self.E, K, 1.0, vals, idx)
+        """rank order per team.  Expert-sharded: every rank ranks its own columns, the [B,K] lists (global expert ids) are
+        all-gathered and merged by ntf_topk_merge (a collective)"""
+        n = self.shard[1]
+        if n == 1:
+            ops.topk_select(scores_buf, B, self.E, K, 1.0, vals, idx)
+            return vals, idx
+        Kl = min(K, self.E)
+        lv = torch.zeros(B, K, dtype=torch.float32, device=self.device)
+        li = torch.full((B, K), -1, dtype=torch.int32, device=self.device)
+        v_, i_ = torch.empty(B, Kl, dtype=torch.float32, device=self.device), torch.empty(B, Kl, dtype=torch.int32, device=self.device)
+        ops.topk_select(scores_buf, B, self.E, Kl, 1.0, v_, i_)
+        lv[:, :Kl] = v_; li[:, :Kl] = i_ + self.e_lo
+        gv, gi = self.allgather(lv), self.allgather(li)  # [n, B, K]
+        ops.topk_merge(gv, gi, n, B, K, vals, idx)
         return vals, idx
+
+    def allgather(self, t):
+        parts = [torch.empty_like(t) for _ in range(self.shard[1])]
+        torch.distributed.all_gather(parts, t.contiguous())
+        return torch.stack(parts).contiguous()

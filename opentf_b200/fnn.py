@@ -106,14 +106,18 @@ class Fnn(Ntf):
         return sd
 
     def init(self, input_size, output_size):
-        if self.engine is None or (self.engine.S, self.engine.E) != (input_size, output_size):
+        if self.engine is None or (self.engine.S, self.engine.E_total) != (input_size, output_size):
+            torch = Ntf.torch
+            world, rank = 1, 0
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+            # multi-GPU mode (extra knob, default 'dp'): 'dp' = data-parallel teams, 'shard' = output layer column-sharded by expert
+            shard = (rank, world) if (world > 1 and self._c('parallel', os.environ.get('NTF_PARALLEL', 'dp')) == 'shard') else None
             self.engine = Engine(input_size, list(self._c('h')), output_size, self._device(), bayesian=self.is_bayesian_cls(),
                                  precision=self._c('precision', os.environ.get('NTF_PRECISION', self.precision_default)),
                                  tpw=self._c('tpw', 1), tnw=self._c('tnw', 1), nsd=self._c('nsd'), ns=self._c('ns', 5),
-                                 seed=self.seed if self.seed is not None else 0, max_batch=self._c('b'))
-            torch = Ntf.torch
-            if torch.distributed.is_available() and torch.distributed.is_initialized():
-                self.engine.world, self.engine.rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+                                 seed=self.seed if self.seed is not None else 0, max_batch=self._c('b'), shard=shard)
+            self.engine.world, self.engine.rank = world, rank
         self.engine.load_state_dict(self._host_init(input_size, output_size))
         self.engine.reset_optimizer()
         self.model = DeviceModel(self.engine)
@@ -133,6 +137,7 @@ class Fnn(Ntf):
     def _rank_slice(self, B):
         """this rank's share [lo, hi) of a global batch of B teams (data parallel: teams are independent)."""
         G, r = self.engine.world, self.engine.rank
+        if self.engine.shard[1] > 1: return 0, B  # expert-sharded: every rank runs the whole batch on its expert range
         per = -(-B // G)
         return min(B, r * per), min(B, (r + 1) * per)
 
@@ -199,8 +204,9 @@ class Fnn(Ntf):
         w.close()
 
     def _save(self, foldidx, e, t_loss, v_loss, path):
+        sd = self.model.state_dict() if (self.engine.shard[1] > 1 or self.engine.rank == 0) else None  # (sharded: a collective gather)
         if self.engine.rank != 0: return
-        Ntf.torch.save({'model_state_dict': self.model.state_dict(), 'cfg': self.cfg, 'f': foldidx, 'e': e, 't_loss': t_loss, 'v_loss': v_loss}, path)
+        Ntf.torch.save({'model_state_dict': sd, 'cfg': self.cfg, 'f': foldidx, 'e': e, 't_loss': t_loss, 'v_loss': v_loss}, path)
         log.info(f'{self.name()} model with {util.cfg2str(self.cfg)} saved at {path}')
 
     # ---- fnn.py:172-219 ---------------------------------------------------------------------------------------
@@ -231,6 +237,8 @@ class Fnn(Ntf):
                         torch.save({'y_pred': y_pred, 'uncertainty': unc}, f'{self.output}/f{foldidx}.{pred_set}.{epoch}pred', pickle_protocol=4)
                         log.info(f'{self.name()} model predictions for fold{foldidx}.{pred_set}.{epoch} has saved at {self.output}/f{foldidx}.{pred_set}.{epoch}pred')
 
+    def _gather_columns(self, t): return _gather_columns_impl(Ntf.torch, self.engine, t)
+
     def _predict_split(self, sp, b, K):
         """fnn.py:198-218 for one prediction set: dense [N,E] probabilities, or -- when topK < E -- the K best per team
         selected on the GPU (only [N,K] leaves it) and stored as the same coalesced sparse COO tensor.
@@ -245,7 +253,7 @@ class Fnn(Ntf):
             scratch = torch.empty(bb, eng.E, dtype=torch.float32, device=eng.device)
             ent_pred, ent_model = torch.empty(bb, dtype=torch.float32, device=eng.device), torch.empty(bb, dtype=torch.float32, device=eng.device)
         unc = None
-        out = torch.empty(sp.n, eng.E, dtype=torch.float32) if K is None else None
+        out = torch.empty(sp.n, eng.E_total, dtype=torch.float32) if K is None else None
         if K is not None:
             vals = torch.empty(sp.n, K, dtype=torch.float32, device=eng.device)
             idx = torch.empty(sp.n, K, dtype=torch.int32, device=eng.device)
@@ -256,10 +264,22 @@ class Fnn(Ntf):
                 unc = {'pred': [ent_pred[:B].cpu().numpy()], 'model': [ent_model[:B].cpu().numpy()]}
             else:
                 eng.scores(sp, b0, B, scores)
-            if K is None: out[b0:b0 + B] = scores[:B].cpu()  # batch by batch, as fnn.py:211-212 does
+            if K is None:  # batch by batch, as fnn.py:211-212 does (expert-sharded: the column blocks of the ranks side by side)
+                if eng.shard[1] == 1: out[b0:b0 + B] = scores[:B].cpu()
+                else: out[b0:b0 + B] = self._gather_columns(scores[:B])
             else: eng.select_topk(scores, B, K, vals[b0:b0 + B], idx[b0:b0 + B])
         if K is None: return out, unc
-        return util.topk_to_sparse(torch, vals.cpu(), idx.cpu(), eng.E), unc
+        return util.topk_to_sparse(torch, vals.cpu(), idx.cpu(), eng.E_total), unc
+
+
+def _gather_columns_impl(torch, eng, t):
+    n = eng.shard[1]
+    widths = [eng.E_total * (i + 1) // n - eng.E_total * i // n for i in range(n)]
+    pad = torch.zeros(t.shape[0], max(widths), dtype=t.dtype, device=t.device)
+    pad[:, :t.shape[1]] = t
+    parts = [torch.empty_like(pad) for _ in range(n)]
+    torch.distributed.all_gather(parts, pad)
+    return torch.cat([parts[i][:, :widths[i]] for i in range(n)], dim=1).cpu()
 
 
 def scipy_dense(x):

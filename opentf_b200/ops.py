@@ -92,9 +92,9 @@ def neg_sample(nsd, seed, step, row0, B, m_indptr_ptr, m_indices, E, ns, cdf, ne
                                _p(neg, I32)), 'ntf_neg_sample')
 
 
-def special_bits(op, B, m_indptr_ptr, m_indices, neg, ns, E, special, pitch):
+def special_bits(op, B, m_indptr_ptr, m_indices, neg, ns, E, special, pitch, e_lo=0):
     d = _dev(m_indices)
-    check(lib().ntf_special_bits(_lib.ctx(d), _stream(d), op, B, m_indptr_ptr, _p(m_indices, I32), _p(neg, I32), ns, E, _p(special), pitch),
+    check(lib().ntf_special_bits(_lib.ctx(d), _stream(d), op, B, m_indptr_ptr, _p(m_indices, I32), _p(neg, I32), ns, E, e_lo, _p(special), pitch),
           'ntf_special_bits')
 
 
@@ -102,9 +102,9 @@ def special_tiles_bytes(B, E):
     return lib().ntf_special_tiles_bytes(B, E)
 
 
-def special_tiles(op, B, m_indptr_ptr, m_indices, neg, ns, E, special_t, member_t):
+def special_tiles(op, B, m_indptr_ptr, m_indices, neg, ns, E, special_t, member_t, e_lo=0):
     d = _dev(m_indices)
-    check(lib().ntf_special_tiles(_lib.ctx(d), _stream(d), op, B, m_indptr_ptr, _p(m_indices, I32), _p(neg, I32), ns, E, _p(special_t), _p(member_t)),
+    check(lib().ntf_special_tiles(_lib.ctx(d), _stream(d), op, B, m_indptr_ptr, _p(m_indices, I32), _p(neg, I32), ns, E, e_lo, _p(special_t), _p(member_t)),
           'ntf_special_tiles')
 
 
