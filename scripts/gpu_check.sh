@@ -6,7 +6,7 @@ TAG=${1:-r01}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu.txt 2>&1
-for f in test_gpu_kernels test_gpu_e2e test_gpu_tc test_gpu_bnn; do
+for f in test_gpu_kernels test_gpu_e2e test_gpu_tc test_gpu_bnn test_gpu_shard; do
   echo "== pytest $f"; timeout 900 python -m pytest tests/$f.py -q -m gpu 2>&1 | tail -60 > $OUT/$f.log; tail -25 $OUT/$f.log
 done
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee $OUT/smoke.log
