@@ -203,7 +203,7 @@ def run_ours(args):
 
     def device_step(i):
         g0 = (i % nb) * gB
-        eng.step(sp, g0 + rank * b, b, True, lr=1e-3, loss_slot=i % 1024, loss_scale=1.0 / gB, gbatch=(g0, gB))
+        eng.step(sp, g0 + rank * b, b, True, lr=1e-3, loss_slot=i % nb, loss_scale=1.0 / gB, gbatch=(g0, gB))
 
     def sync():
         torch.cuda.synchronize()
@@ -211,14 +211,29 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- kernel-resident timing: `value` ----
+    # the dominant kernel group (output layer: forward + loss + backward) is timed live with CUDA events on the launching stream.
+    # Graph mode (default): every batch of the split is captured once (setup pass below) with an event pair around its output-layer
+    # call (external event-record nodes), re-recorded by every replay; after the timed loop each pair holds the duration of its last
+    # replay inside the timed region.  NTF_GRAPHS=0: one pair per step, recorded by ntf_fnn_step as it enqueues.
+    graphs = eng.use_graphs
+    pairs = []
+
+    def new_pair():
+        p = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        for e in p: e.record()  # (creates the underlying cudaEvent_t handles)
+        pairs.append(p)
+        return p
+
+    if graphs:
+        eng.graph_event_factory = lambda: tuple(e.cuda_event for e in new_pair())
+        for i in range(nb): device_step(i)  # setup pass: capture
+        eng.graph_event_factory = None
+    else:
+        for _ in range(args.steps): new_pair()
     for i in range(args.warmup): device_step(i)
     sync()
     _lib.lib().ntf_launch_count(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # the dominant kernel group (output layer: forward + loss + backward) timed live with events on the launching stream
-    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    for e in k0 + k1: e.record()  # (creates the underlying cudaEvent_t handles)
     torch.cuda.synchronize()
     clk = ClockSampler(local).__enter__()  # samples through both timed legs (device-resident and end-to-end)
     time.sleep(0.3)
@@ -227,7 +242,7 @@ def run_ours(args):
     ev0.record()
     h0 = time.perf_counter()
     for i in range(args.steps):
-        eng.prof_events = (k0[i], k1[i])  # ntf_fnn_step records them around its output-layer call, on the launching stream
+        if not graphs: eng.prof_events = pairs[i]  # ntf_fnn_step records them around its output-layer call, on the launching stream
         device_step(args.warmup + i)
     eng.prof_events = None
     host_ms = (time.perf_counter() - h0) * 1e3 / args.steps  # CPU time to ENQUEUE one step (if ~ ms_per_step the loop is launch-bound)
@@ -240,11 +255,12 @@ def run_ours(args):
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = args.steps * gB / (ms * 1e-3)
-    k_ms = float(np.mean([a.elapsed_time(c) for a, c in zip(k0, k1)]))
+    used = pairs if (not graphs or args.steps >= nb) else [pairs[(args.warmup + i) % nb] for i in range(args.steps)]
+    k_ms = float(np.mean([a.elapsed_time(c) for a, c in used]))
 
     # ---- end to end through the streaming entry point: host batches in, loss out ----
     host = HostBatches(tv, train_rows, b, rank, G)
-    for i in list(range(min(3, args.warmup))) + [100 + i for i in range(args.steps)]: host.batch(i)  # pinned host inputs exist before timing
+    host.prepare(list(range(min(3, args.warmup))) + [100 + i for i in range(args.steps)])  # pinned host inputs exist before timing
     for i in range(min(3, args.warmup)): host.step(eng, i)
     sync()
     w0 = time.time()
@@ -296,8 +312,8 @@ def run_ours(args):
            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if precision_used == 'fp32' else 'f16 operands (10-bit mantissa, TF32-class), f32 accumulate',
            'data': 'synthetic', 'config': config_of(args, tv), 'clocks': clk.summary(),
            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': host.h2d_bytes, 'd2h_bytes_per_step': 4,
-                   'api': 'Engine.step_host: pinned batch CSR block -> one H2D copy -> ntf_fnn_step -> loss.item()'},
-           'gpu_launches': launches, 'host_enqueue_ms_per_step': host_ms, 'roofline': roof, 'infer_topk': {'k': args.infer_k, 'value': infer_value, 'unit': 'teams/s', 'batch': ib}}
+                   'api': 'Engine.step_host: pinned batch CSR block -> one H2D copy -> ntf_fnn_step (replayed as a CUDA graph) -> loss.item()'},
+           'gpu_launches': launches, 'cuda_graphs': bool(graphs), 'host_enqueue_ms_per_step': host_ms, 'roofline': roof, 'infer_topk': {'k': args.infer_k, 'value': infer_value, 'unit': 'teams/s', 'batch': ib}}
     if not args.no_cpu_baseline:
         v, n, dt, threads = cpu_reference_steps(tv, splits, b, args.nsd, args.cpu_baseline_seconds)
         out['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
@@ -317,25 +333,31 @@ class HostBatches:
         self.h2d_bytes = 0
         self.pin = {}
 
-    def batch(self, i):
-        """pinned block of global batch i (built once, outside any timed region)"""
-        from opentf_b200.engine import pack_host_batch
-        if i in self.pin: return self.pin[i]
+    def _rows(self, i):
         gB = self.b * self.G
         g0 = (i * gB) % (len(self.rows) - gB)
-        rows = self.rows[g0:g0 + gB]
-        parts = []
-        for ptr, idx, _ in (self.s, self.m):
-            lens = ptr[rows + 1] - ptr[rows]
-            p = np.zeros(len(rows) + 1, dtype=np.int32); np.cumsum(lens, out=p[1:])
-            parts += [p, np.concatenate([idx[ptr[r]:ptr[r + 1]] for r in rows]).astype(np.int32)]
-        self.pin[i] = pack_host_batch(parts[0], parts[1], parts[2], parts[3])
-        return self.pin[i]
+        return self.rows[g0:g0 + gB]
+
+    def prepare(self, ids):
+        """pinned blocks of the global batches `ids` (built once, outside any timed region), all packed to the same capacities:
+        one layout -> one set of device addresses -> the step replays one captured graph"""
+        from opentf_b200.engine import pack_host_batch
+        (sptr, _, _), (mptr, _, _) = self.s, self.m
+        cap = lambda ptr: int(max((ptr[self._rows(i) + 1] - ptr[self._rows(i)]).sum() for i in ids))
+        cap_s, cap_m = -(-cap(sptr) // 64) * 64, -(-cap(mptr) // 64) * 64
+        for i in ids:
+            rows = self._rows(i)
+            parts = []
+            for ptr, idx, _ in (self.s, self.m):
+                lens = ptr[rows + 1] - ptr[rows]
+                p = np.zeros(len(rows) + 1, dtype=np.int32); np.cumsum(lens, out=p[1:])
+                parts += [p, np.concatenate([idx[ptr[r]:ptr[r + 1]] for r in rows]).astype(np.int32)]
+            self.pin[i] = pack_host_batch(parts[0], parts[1], parts[2], parts[3], cap_s=cap_s, cap_m=cap_m)
 
     def step(self, eng, i):
-        packed, n, nnz_s, nnz_m = self.batch(i)
+        packed, n, cap_s, cap_m = self.pin[i]
         self.h2d_bytes = packed.numel() * 4
-        return eng.step_host(packed, n, nnz_s, nnz_m, self.rank, self.G, lr=1e-3)
+        return eng.step_host(packed, n, cap_s, cap_m, self.rank, self.G, lr=1e-3)
 
 
 if __name__ == '__main__':

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NTF_ABI_VERSION 1
+#define NTF_ABI_VERSION 2
 
 typedef enum {
   NTF_OK = 0,
@@ -53,6 +53,28 @@ int ntf_destroy(ntf_ctx* ctx);
 int ntf_sm_count(const ntf_ctx* ctx);
 /* number of kernels this library has launched in this process (reset != 0 clears it): launch accounting for bench.py */
 unsigned long long ntf_launch_count(int reset);
+
+/* ---- step-varying scalars on the device + CUDA graphs ----------------------------------------------------------------------
+ * The reference's loop (fnn.py:118-151) launches ~40 ATen kernels per batch from Python; here a step is ~17 launches, and even
+ * those cost the host more than the GPU needs to run them.  The launch sequence of batch i of a split is identical in every epoch
+ * (same buffers: the epoch's permutation moves DATA, not pointers) except for three scalars: the sampler's RNG counter, and Adam's
+ * learning rate and bias corrections.  Those live in a small DEVICE block (ntf_dyn) that the kernels read when they are handed
+ * one, so a step captured once as a CUDA graph is replayed unchanged:   ntf_dyn_update(...); ntf_graph_launch(g, stream);      */
+typedef struct {
+  uint64_t step;                                                   /* counter of the sampler's Philox stream (ntf_neg_sample)   */
+  float one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, neg_step;   /* Adam: neg_step = -lr / (1 - beta1^t), bc2_sqrt = sqrt(1 - beta2^t) */
+} ntf_dyn;
+/* writes the block (device memory, caller-owned) for the step about to run; stream-ordered, one tiny launch */
+int ntf_dyn_update(ntf_ctx* ctx, void* stream, ntf_dyn* dyn, uint64_t step, double lr, double beta1, double beta2, double eps,
+                   int64_t adam_t);
+/* capture everything this library enqueues on `stream` between begin and end (thread-local capture mode) into an executable
+ * graph; replaying it costs the host one call.  The calls in between must get the same buffers at every replay. */
+typedef struct ntf_graph ntf_graph;
+int ntf_graph_begin(ntf_ctx* ctx, void* stream);
+int ntf_graph_end(ntf_ctx* ctx, void* stream, ntf_graph** out);
+int ntf_graph_launch(ntf_graph* g, void* stream);
+int ntf_graph_kernels(const ntf_graph* g);   /* kernel nodes in the graph (launch accounting) */
+int ntf_graph_destroy(ntf_graph* g);
 
 /* ---- batching: replaces DataLoader(shuffle) + NtfDataset.__getitem__ (fnn.py:95-97, ntf.py:17-25) ------------
  * dst row i = src row rows[i] (rows == NULL: identity).  dst_indptr gets n+1 offsets (exclusive scan of the
@@ -99,13 +121,17 @@ size_t ntf_expert_cdf_workspace_bytes(int E);
 int ntf_expert_cdf(ntf_ctx* ctx, void* stream, int B, const int32_t* m_indptr, const int32_t* m_indices, int E,
                    uint32_t* counts, uint32_t* cdf, void* workspace, size_t workspace_bytes);
 /* neg[n, 0..ns) = distinct experts that are not members of team n, drawn without replacement with probability
- * proportional to counts (unigram, unigram_b) or uniformly (uniform): the distribution of the reference's
- * torch.multinomial(replacement=False) / top-ns-of-iid-keys.  Counter RNG: Philox4x32-10 keyed by seed, counter =
- * (row0+n, draw, step); restated on the CPU in oracle/sampler_oracle.py.  A row whose candidates carry no mass
- * falls back to uniform over ALL experts (fnn.py:67-69).  Unfilled slots are -1. */
+ * proportional to the expert counts (unigram: `cdf` of ntf_expert_cdf over all teams; unigram_b: counts over the batch)
+ * or uniformly (uniform): the distribution of the reference's torch.multinomial(replacement=False) / top-ns-of-iid-keys.
+ * unigram_b needs no histogram: count_j/B is the chance that a uniformly chosen ENTRY of the batch's member CSR is j, so a
+ * draw picks entry number floor(u*nnz) of the pool = rows [0, pool_rows) of `pool_indptr` (NULL / 0: the batch itself;
+ * a data-parallel rank passes the GLOBAL batch its rows are a slice of).
+ * Counter RNG: Philox4x32-10 keyed by seed, counter = (row0+n, draw, step); restated on the CPU in
+ * oracle/sampler_oracle.py.  A row whose candidates carry no mass falls back to uniform over ALL experts (fnn.py:67-69).
+ * Unfilled slots are -1. */
 int ntf_neg_sample(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed, uint64_t step, int row0, int B,
                    const int32_t* m_indptr, const int32_t* m_indices, int E, int ns, const uint32_t* cdf,
-                   int32_t* neg);
+                   const int32_t* pool_indptr, int pool_rows, int32_t* neg);
 /* special[n, j/32] bit j%32 = 1 iff j is a member of team n or j is in neg[n,:]: the reference's `condition` tensor
  * (fnn.py:33-43), bit-packed.  op 1 sets the bits, op 0 clears the same words again (no full memset per step).
  * Expert-sharded output layer: the plane covers this rank's E columns [e_lo, e_lo + E) of the global expert axis; member
@@ -156,6 +182,7 @@ typedef struct {
   uint32_t* special_t;         /* ntf_special_tiles planes                                           */
   uint32_t* member_t;
   int e_lo;                    /* expert-sharded layer: W/b/dW/db and the planes cover columns [e_lo, e_lo+E); m_indices are global */
+  const void* A16;             /* NTF_TF32, optional: A as fp16 [B,h] already (the producing kernel wrote it); NULL: converted here */
 } ntf_out_train_args;
 /* 1 if NTF_TF32 has a tcgen05 kernel for this shape (else callers use NTF_FP32; ntf_out_train(NTF_TF32) refuses it) */
 int ntf_tc_supported(int B, int h, int E, int flipout);
@@ -252,8 +279,8 @@ typedef struct {
   uint64_t seed, step;
   int row0, ns, neg_given;           /* neg_given != 0: neg[B,ns] holds caller-supplied indices (parity tests)        */
   int32_t* neg;
-  uint32_t* counts;                  /* [E] scratch of ntf_expert_cdf                                                  */
-  uint32_t* cdf;                     /* [E]; for NTF_NS_UNIGRAM prepared by the caller once (fnn.py:82)               */
+  uint32_t* counts;                  /* (unused; kept for layout)                                                      */
+  uint32_t* cdf;                     /* [E]: NTF_NS_UNIGRAM only, prepared by the caller once (ntf_expert_cdf, fnn.py:82) */
   int precision;                     /* ntf_precision                                                                  */
   float tpw, tnw, loss_scale;
   float* loss_out;
@@ -263,6 +290,7 @@ typedef struct {
   float* params; float* grads; float* adam_m; float* adam_v; size_t n_params;   /* the flat arena (ntf_adam_step)      */
   double lr, beta1, beta2, eps; int64_t adam_t;
   void* prof_ev[2];                  /* optional cudaEvent_t pair recorded around the output-layer call (bench.py's roofline timing) */
+  const ntf_dyn* dyn;                /* optional (device): `step`, `lr`, `adam_t` are read from this block instead -- graph replays */
 } ntf_fnn_step_args;
 size_t ntf_fnn_step_workspace_bytes(const ntf_ctx* ctx, const ntf_fnn_step_args* args);
 int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args* args, void* workspace, size_t workspace_bytes);

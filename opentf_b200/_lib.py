@@ -21,7 +21,7 @@ class OutTrainArgs(C.Structure):
     _fields_ = [('A', vp), ('W', vp), ('b', vp), ('special', vp), ('pitch_words', i32), ('m_indptr', vp), ('m_indices', vp),
                 ('B', i32), ('h', i32), ('E', i32), ('tpw', f32), ('tnw', f32), ('loss_scale', f32),
                 ('dW', vp), ('db', vp), ('dA', vp), ('loss_out', vp),
-                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp), ('e_lo', i32)]
+                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp), ('e_lo', i32), ('A16', vp)]
 
 
 NTF_MAX_LAYERS = 8
@@ -37,7 +37,7 @@ class FnnStepArgs(C.Structure):
                 ('neg', vp), ('counts', vp), ('cdf', vp), ('precision', i32), ('tpw', f32), ('tnw', f32), ('loss_scale', f32), ('loss_out', vp),
                 ('special', vp), ('pitch_words', i32), ('special_t', vp), ('member_t', vp), ('train', i32), ('run_adam', i32),
                 ('params', vp), ('grads', vp), ('adam_m', vp), ('adam_v', vp), ('n_params', sz),
-                ('lr', f64), ('beta1', f64), ('beta2', f64), ('eps', f64), ('adam_t', i64), ('prof_ev', vp * 2)]
+                ('lr', f64), ('beta1', f64), ('beta2', f64), ('eps', f64), ('adam_t', i64), ('prof_ev', vp * 2), ('dyn', vp)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/ntf_b200.h (tests/test_abi.py checks it)
@@ -48,6 +48,12 @@ SIGNATURES = {
     'ntf_destroy': (i32, [vp]),
     'ntf_sm_count': (i32, [vp]),
     'ntf_launch_count': (C.c_ulonglong, [i32]),
+    'ntf_dyn_update': (i32, [vp, vp, vp, u64, f64, f64, f64, f64, i64]),
+    'ntf_graph_begin': (i32, [vp, vp]),
+    'ntf_graph_end': (i32, [vp, vp, C.POINTER(vp)]),
+    'ntf_graph_launch': (i32, [vp, vp]),
+    'ntf_graph_kernels': (i32, [vp]),
+    'ntf_graph_destroy': (i32, [vp]),
     'ntf_csr_gather_workspace_bytes': (sz, [i32]),
     'ntf_csr_gather': (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz]),
     'ntf_csr_bag_fwd': (i32, [vp, vp, i32, vp, vp, vp, vp, i32, i32, vp]),
@@ -60,7 +66,7 @@ SIGNATURES = {
     'ntf_dense_bwd': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, sz]),
     'ntf_expert_cdf_workspace_bytes': (sz, [i32]),
     'ntf_expert_cdf': (i32, [vp, vp, i32, vp, vp, i32, vp, vp, vp, sz]),
-    'ntf_neg_sample': (i32, [vp, vp, i32, u64, u64, i32, i32, vp, vp, i32, i32, vp, vp]),
+    'ntf_neg_sample': (i32, [vp, vp, i32, u64, u64, i32, i32, vp, vp, i32, i32, vp, vp, i32, vp]),
     'ntf_special_bits': (i32, [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, i32]),
     'ntf_special_tiles_bytes': (sz, [i32, i32]),
     'ntf_special_tiles': (i32, [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp]),
@@ -120,6 +126,14 @@ def last_error():
 def check(rc, what=''):
     if rc != 0:
         raise NtfError(f'{what} failed with status {rc}: {last_error()}')
+
+
+def new_ctx(device_index):
+    """a handle of its own (side streams + events of ntf_fnn_step's fork/join): one per Engine, so that engines driven from
+    different host threads never share them"""
+    h = vp()
+    check(lib().ntf_create(int(device_index), C.byref(h)), 'ntf_create')
+    return h
 
 
 _ctx = {}

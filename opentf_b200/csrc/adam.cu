@@ -9,6 +9,11 @@
 namespace {
 struct AdamK { float one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, neg_step; };
 
+AdamK adam_consts(double lr, double beta1, double beta2, double eps, int64_t step) {
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  return AdamK{(float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)sqrt(bc2), (float)eps, (float)(-(lr / bc1))};
+}
+
 __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamK& k) {
   m = m + k.one_minus_b1 * (g - m);
   v = v * k.b2;
@@ -18,7 +23,8 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, con
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                   float* __restrict__ v, size_t n4, size_t n, AdamK k) {
+                                                   float* __restrict__ v, size_t n4, size_t n, AdamK k, const ntf_dyn* __restrict__ dyn) {
+  if (dyn) k = AdamK{dyn->one_minus_b1, dyn->b2, dyn->one_minus_b2, dyn->bc2_sqrt, dyn->eps, dyn->neg_step};  // a replayed graph: this step's constants
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
@@ -30,18 +36,39 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 }  // namespace
 
-extern "C" int ntf_adam_step(ntf_ctx* ctx, void* stream, float* p, const float* g, float* m, float* v, size_t n, double lr,
-                             double beta1, double beta2, double eps, int64_t step) {
+// `dyn` (device, nullable): the constants come from the block ntf_dyn_update wrote for this step instead of the arguments
+int ntf_adam_step_impl(ntf_ctx* ctx, cudaStream_t st, float* p, const float* g, float* m, float* v, size_t n, double lr, double beta1,
+                       double beta2, double eps, int64_t step, const ntf_dyn* dyn) {
   NTF_REQUIRE(ctx && p && g && m && v, NTF_ERR_BAD_ARG, "adam_step: null pointer");
-  NTF_REQUIRE(step >= 1, NTF_ERR_BAD_ARG, "adam_step: step=%lld (1-based)", (long long)step);
+  NTF_REQUIRE(dyn || step >= 1, NTF_ERR_BAD_ARG, "adam_step: step=%lld (1-based)", (long long)step);
   if (n == 0) return NTF_OK;
   const bool aligned = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0;
-  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
-  AdamK k{(float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)sqrt(bc2), (float)eps, (float)(-(lr / bc1))};
+  const AdamK k = adam_consts(lr, beta1, beta2, eps, step >= 1 ? step : 1);
   const size_t n4 = aligned ? n / 4 : 0;
   const size_t work = n4 ? n4 : n;
   const int blocks = (int)((work + 255) / 256 < (size_t)ctx->sm_count * 16 ? (work + 255) / 256 : (size_t)ctx->sm_count * 16);
-  NTF_COUNT_LAUNCH; adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n4, n, k);
+  NTF_COUNT_LAUNCH; adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n4, n, k, dyn);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
+
+extern "C" int ntf_adam_step(ntf_ctx* ctx, void* stream, float* p, const float* g, float* m, float* v, size_t n, double lr,
+                             double beta1, double beta2, double eps, int64_t step) {
+  return ntf_adam_step_impl(ctx, as_stream(stream), p, g, m, v, n, lr, beta1, beta2, eps, step, nullptr);
+}
+
+namespace {
+__global__ void dyn_update_kernel(ntf_dyn* dyn, ntf_dyn v) { *dyn = v; }
+}  // namespace
+
+extern "C" int ntf_dyn_update(ntf_ctx* ctx, void* stream, ntf_dyn* dyn, uint64_t step, double lr, double beta1, double beta2, double eps,
+                              int64_t adam_t) {
+  NTF_REQUIRE(ctx && dyn, NTF_ERR_BAD_ARG, "dyn_update: null pointer");
+  const AdamK k = adam_consts(lr, beta1, beta2, eps, adam_t >= 1 ? adam_t : 1);
+  ntf_dyn v;
+  v.step = step;
+  v.one_minus_b1 = k.one_minus_b1; v.b2 = k.b2; v.one_minus_b2 = k.one_minus_b2; v.bc2_sqrt = k.bc2_sqrt; v.eps = k.eps; v.neg_step = k.neg_step;
+  NTF_COUNT_LAUNCH; dyn_update_kernel<<<1, 1, 0, as_stream(stream)>>>(dyn, v);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

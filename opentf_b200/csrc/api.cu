@@ -45,11 +45,30 @@ extern "C" int ntf_create(int device, ntf_ctx** out) {
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) c->encode_tiled = fn;
   (void)cudaGetLastError();
+  int cur = 0;
+  NTF_CUDA(cudaGetDevice(&cur));
+  NTF_CUDA(cudaSetDevice(device));
+  cudaError_t es = cudaSuccess;
+  for (int i = 0; i < 2 && es == cudaSuccess; ++i) {
+    es = cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
+    if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+  }
+  if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  cudaSetDevice(cur);
+  if (es != cudaSuccess) {
+    ntf_set_error("ntf_create: side streams / events: %s", cudaGetErrorString(es));
+    delete c;
+    return NTF_ERR_CUDA;
+  }
   *out = c;
   return NTF_OK;
 }
 
 extern "C" int ntf_destroy(ntf_ctx* ctx) {
+  if (ctx) {
+    for (int i = 0; i < 2; ++i) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
+    cudaEventDestroy(ctx->ev_fork);
+  }
   delete ctx;
   return NTF_OK;
 }
@@ -60,4 +79,52 @@ extern "C" unsigned long long ntf_launch_count(int reset) {
   const unsigned long long v = g_ntf_launches;
   if (reset) g_ntf_launches = 0;
   return v;
+}
+
+// ---- CUDA graphs: a captured step replayed with one host call (include/ntf_b200.h) ----------------------------------------
+struct ntf_graph {
+  cudaGraphExec_t exec;
+  int kernels;
+};
+static thread_local unsigned long long g_capture_mark = 0;
+
+extern "C" int ntf_graph_begin(ntf_ctx* ctx, void* stream) {
+  NTF_REQUIRE(ctx, NTF_ERR_BAD_ARG, "graph_begin: null ctx");
+  g_capture_mark = g_ntf_launches;
+  NTF_CUDA(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeThreadLocal));
+  return NTF_OK;
+}
+
+extern "C" int ntf_graph_end(ntf_ctx* ctx, void* stream, ntf_graph** out) {
+  NTF_REQUIRE(ctx && out, NTF_ERR_BAD_ARG, "graph_end: null pointer");
+  *out = nullptr;
+  cudaGraph_t graph = nullptr;
+  NTF_CUDA(cudaStreamEndCapture(as_stream(stream), &graph));
+  const int kernels = (int)(g_ntf_launches - g_capture_mark);
+  g_ntf_launches -= (unsigned long long)kernels;  // captured launches did not run; replays are counted by ntf_graph_launch
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  NTF_REQUIRE(e == cudaSuccess, NTF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  ntf_graph* g = new ntf_graph();
+  g->exec = exec;
+  g->kernels = kernels;
+  *out = g;
+  return NTF_OK;
+}
+
+extern "C" int ntf_graph_launch(ntf_graph* g, void* stream) {
+  NTF_REQUIRE(g && g->exec, NTF_ERR_BAD_ARG, "graph_launch: null graph");
+  NTF_CUDA(cudaGraphLaunch(g->exec, as_stream(stream)));
+  g_ntf_launches += (unsigned long long)g->kernels;
+  return NTF_OK;
+}
+
+extern "C" int ntf_graph_kernels(const ntf_graph* g) { return g ? g->kernels : NTF_ERR_BAD_ARG; }
+
+extern "C" int ntf_graph_destroy(ntf_graph* g) {
+  if (!g) return NTF_OK;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  delete g;
+  return NTF_OK;
 }

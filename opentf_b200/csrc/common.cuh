@@ -13,6 +13,11 @@ struct ntf_ctx {
   int cc_major, cc_minor;
   size_t smem_optin;
   void* encode_tiled;  // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
+  // ntf_fnn_step forks the parts of a step that depend on the batch's CSR only (negative sampling + condition planes; the slot
+  // fill of the input layer's backward pass) onto side streams and joins them where their results are needed; inside a stream
+  // capture the same calls become parallel branches of the graph
+  cudaStream_t side[2];
+  cudaEvent_t ev_fork, ev_join[2];
 };
 
 // ---- launch accounting (bench.py reports how many of OUR kernels ran in the timed region) ----------------

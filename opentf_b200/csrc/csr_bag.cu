@@ -5,6 +5,8 @@
 //   ntf_csr_bag_fwd   : A = lrelu(b0 + sum_s W0T[s,:])                    -- HBM-bound gather-sum
 //   ntf_csr_bag_bwd   : dW0T[s,:] = sum_{n: s in skills(n)} dZ[n,:]       -- atomic-free, owner-computes
 //   ntf_act_bwd       : dZ = dY*lrelu'(Y), db = colsum(dZ)
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 // =========================================================================================================
@@ -173,7 +175,7 @@ template <bool VEC4>
 __global__ void __launch_bounds__(256) csr_bag_fwd_kernel(int B, const int32_t* __restrict__ indptr,
                                                           const int32_t* __restrict__ indices,
                                                           const float* __restrict__ W0T, const float* __restrict__ b0,
-                                                          int h, float* __restrict__ A) {
+                                                          int h, float* __restrict__ A, __half* __restrict__ A16) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < B; n += warps) {
@@ -203,30 +205,45 @@ __global__ void __launch_bounds__(256) csr_bag_fwd_kernel(int B, const int32_t* 
         float4 o;
         o.x = lrelu(acc.x + bb.x); o.y = lrelu(acc.y + bb.y); o.z = lrelu(acc.z + bb.z); o.w = lrelu(acc.w + bb.w);
         reinterpret_cast<float4*>(A + (size_t)n * h)[c] = o;
+        if (A16) {  // the tensor-core output layer reads fp16 operands: hand it the copy now instead of a conversion pass later
+          const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          reinterpret_cast<uint2*>(A16 + (size_t)n * h)[c] = pk;
+        }
       }
     } else {
       for (int c = lane; c < h; c += 32) {
         float acc = 0.f;
         for (int p = beg; p < end; ++p) acc += __ldg(W0T + (size_t)indices[p] * h + c);
-        A[(size_t)n * h + c] = lrelu(acc + b0[c]);
+        const float o = lrelu(acc + b0[c]);
+        A[(size_t)n * h + c] = o;
+        if (A16) A16[(size_t)n * h + c] = __float2half_rn(o);
       }
     }
   }
 }
 }  // namespace
 
-extern "C" int ntf_csr_bag_fwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
-                               const float* W0T, const float* b0, int S, int h, float* A) {
+// A16 (nullable): also write the activations as fp16 [B,h] (operand of the tensor-core output layer)
+int ntf_csr_bag_fwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices, const float* W0T,
+                         const float* b0, int S, int h, float* A, void* A16v) {
+  __half* A16 = (__half*)A16v;
   NTF_REQUIRE(ctx && indptr && indices && W0T && b0 && A, NTF_ERR_BAD_ARG, "csr_bag_fwd: null pointer");
   NTF_REQUIRE(B >= 0 && S > 0 && h > 0, NTF_ERR_BAD_ARG, "csr_bag_fwd: B=%d S=%d h=%d", B, S, h);
   if (B == 0) return NTF_OK;
   const int blocks = min(cdiv(B, 8), ctx->sm_count * 8);
-  const bool vec = (h % 4 == 0) && (((uintptr_t)W0T | (uintptr_t)b0 | (uintptr_t)A) % 16 == 0);
+  const bool vec = (h % 4 == 0) && (((uintptr_t)W0T | (uintptr_t)b0 | (uintptr_t)A) % 16 == 0) && ((uintptr_t)A16 % 8 == 0);
   NTF_COUNT_LAUNCH;
-  if (vec) csr_bag_fwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(B, indptr, indices, W0T, b0, h, A);
-  else csr_bag_fwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(B, indptr, indices, W0T, b0, h, A);
+  if (vec) csr_bag_fwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(B, indptr, indices, W0T, b0, h, A, A16);
+  else csr_bag_fwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(B, indptr, indices, W0T, b0, h, A, A16);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
+}
+
+extern "C" int ntf_csr_bag_fwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
+                               const float* W0T, const float* b0, int S, int h, float* A) {
+  return ntf_csr_bag_fwd_impl(ctx, stream, B, indptr, indices, W0T, b0, S, h, A, nullptr);
 }
 
 // Bnn / Flipout input layer (bayesian-torch LinearFlipout on a multi-hot row):
@@ -499,32 +516,58 @@ extern "C" size_t ntf_csr_bag_bwd_workspace_bytes(int S, int h) {
   return align_up(((size_t)S * (2 + HOT) + 64) * sizeof(uint32_t), 256) + align_up((size_t)HOT_MAX * HOT_G * h * sizeof(float), 256);
 }
 
-static int csr_bag_bwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
-                            const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T,
-                            void* workspace, size_t workspace_bytes, const uint32_t* ent_sign) {
-  NTF_REQUIRE(ctx && indptr && indices && ent_row && dZ && dW0T && workspace, NTF_ERR_BAD_ARG, "csr_bag_bwd: null pointer");
+struct BagBwdWs {
+  uint32_t* cnt; uint32_t* nhot; int32_t* hot; int32_t* slots; float* hot_part;
+};
+static BagBwdWs bag_bwd_ws(void* workspace, int S) {
+  BagBwdWs w;
+  w.cnt = (uint32_t*)workspace;        // [S]
+  w.nhot = w.cnt + S;                  // [1] (padded to 64)
+  w.hot = (int32_t*)(w.cnt + S + 64);  // [S]
+  w.slots = w.hot + S;                 // [S][HOT]
+  w.hot_part = (float*)((char*)workspace + align_up(((size_t)S * (2 + HOT) + 64) * sizeof(uint32_t), 256));  // [HOT_MAX][HOT_G][h]
+  return w;
+}
+
+// pass 1 depends on the batch's CSR only (not on dZ): ntf_fnn_step runs it on a side stream while the output layer computes
+int ntf_csr_bag_bwd_fill_impl(ntf_ctx* ctx, cudaStream_t st, int B, const int32_t* indptr, const int32_t* indices, const int32_t* ent_row,
+                              int row_base, int S, int h, void* workspace, size_t workspace_bytes, const uint32_t* ent_sign) {
+  NTF_REQUIRE(ctx && indptr && indices && ent_row && workspace, NTF_ERR_BAD_ARG, "csr_bag_bwd: null pointer");
   NTF_REQUIRE(B > 0 && S > 0 && h > 0, NTF_ERR_BAD_ARG, "csr_bag_bwd: B=%d S=%d h=%d", B, S, h);
+  NTF_REQUIRE(workspace_bytes >= ntf_csr_bag_bwd_workspace_bytes(S, h), NTF_ERR_WORKSPACE, "csr_bag_bwd: workspace too small");
+  const BagBwdWs w = bag_bwd_ws(workspace, S);
+  NTF_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)(S + 64) * sizeof(uint32_t), st));
+  NTF_COUNT_LAUNCH; bag_bwd_fill_kernel<<<min(cdiv(B * 8, 256), ctx->sm_count * 8), 256, 0, st>>>(B, indptr, indices, ent_row, row_base, ent_sign, w.cnt, w.slots);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
+
+int ntf_csr_bag_bwd_reduce_impl(ntf_ctx* ctx, cudaStream_t st, int B, const int32_t* indptr, const int32_t* indices, const int32_t* ent_row,
+                                int row_base, const float* dZ, int S, int h, float* dW0T, void* workspace, size_t workspace_bytes,
+                                const uint32_t* ent_sign) {
+  NTF_REQUIRE(ctx && indptr && indices && ent_row && dZ && dW0T && workspace, NTF_ERR_BAD_ARG, "csr_bag_bwd: null pointer");
   NTF_REQUIRE(h <= 2048, NTF_ERR_UNSUPPORTED, "csr_bag_bwd: first hidden width %d > 2048", h);
   NTF_REQUIRE(workspace_bytes >= ntf_csr_bag_bwd_workspace_bytes(S, h), NTF_ERR_WORKSPACE, "csr_bag_bwd: workspace too small");
-  cudaStream_t st = as_stream(stream);
-  uint32_t* cnt = (uint32_t*)workspace;         // [S]
-  uint32_t* nhot = cnt + S;                      // [1] (padded to 64)
-  int32_t* hot = (int32_t*)(cnt + S + 64);       // [S]
-  int32_t* slots = hot + S;                      // [S][HOT]
-  float* hot_part = (float*)((char*)workspace + align_up(((size_t)S * (2 + HOT) + 64) * sizeof(uint32_t), 256));  // [HOT_MAX][HOT_G][h]
-  NTF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(S + 64) * sizeof(uint32_t), st));
-  NTF_COUNT_LAUNCH; bag_bwd_fill_kernel<<<min(cdiv(B * 8, 256), ctx->sm_count * 8), 256, 0, st>>>(B, indptr, indices, ent_row, row_base, ent_sign, cnt, slots);
+  const BagBwdWs w = bag_bwd_ws(workspace, S);
   const bool vec = (h % 4 == 0) && (((uintptr_t)dZ | (uintptr_t)dW0T) % 16 == 0);
   const int blocks = min(cdiv(S, 8), ctx->sm_count * 8);
   NTF_COUNT_LAUNCH;
-  if (vec) bag_bwd_reduce_kernel<true><<<blocks, 256, 0, st>>>(S, h, cnt, slots, dZ, dW0T, hot, nhot);
-  else bag_bwd_reduce_kernel<false><<<blocks, 256, 0, st>>>(S, h, cnt, slots, dZ, dW0T, hot, nhot);
+  if (vec) bag_bwd_reduce_kernel<true><<<blocks, 256, 0, st>>>(S, h, w.cnt, w.slots, dZ, dW0T, w.hot, w.nhot);
+  else bag_bwd_reduce_kernel<false><<<blocks, 256, 0, st>>>(S, h, w.cnt, w.slots, dZ, dW0T, w.hot, w.nhot);
   const size_t smem_hot = (size_t)(1 + BWD_WARPS) * h * sizeof(float) + (size_t)HCAP * sizeof(int);
   NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_hot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hot));
-  NTF_COUNT_LAUNCH; csr_bag_bwd_hot_kernel<<<ctx->sm_count * 2, BWD_WARPS * 32, smem_hot, st>>>(B, indptr, indices, ent_row, row_base, dZ, h, hot, nhot, dW0T, ent_sign, hot_part);
-  NTF_COUNT_LAUNCH; bag_bwd_hot_combine_kernel<<<ctx->sm_count, 128, 0, st>>>(h, hot, nhot, hot_part, dW0T);
+  NTF_COUNT_LAUNCH; csr_bag_bwd_hot_kernel<<<ctx->sm_count * 2, BWD_WARPS * 32, smem_hot, st>>>(B, indptr, indices, ent_row, row_base, dZ, h, w.hot, w.nhot, dW0T, ent_sign, w.hot_part);
+  NTF_COUNT_LAUNCH; bag_bwd_hot_combine_kernel<<<ctx->sm_count, 128, 0, st>>>(h, w.hot, w.nhot, w.hot_part, dW0T);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
+}
+
+static int csr_bag_bwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
+                            const int32_t* ent_row, int row_base, const float* dZ, int S, int h, float* dW0T,
+                            void* workspace, size_t workspace_bytes, const uint32_t* ent_sign) {
+  const int rc = ntf_csr_bag_bwd_fill_impl(ctx, as_stream(stream), B, indptr, indices, ent_row, row_base, S, h, workspace, workspace_bytes, ent_sign);
+  if (rc) return rc;
+  return ntf_csr_bag_bwd_reduce_impl(ctx, as_stream(stream), B, indptr, indices, ent_row, row_base, dZ, S, h, dW0T, workspace, workspace_bytes, ent_sign);
 }
 
 extern "C" int ntf_csr_bag_bwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,

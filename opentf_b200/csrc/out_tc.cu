@@ -668,7 +668,8 @@ int ntf_out_train_tc(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a,
   NTF_REQUIRE(!train || (((uintptr_t)a->dA | (uintptr_t)a->dW) & 15) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): dA and dW must be 16-byte aligned");
   NTF_REQUIRE((a->special_t == nullptr) == (a->member_t == nullptr), NTF_ERR_BAD_ARG, "out_train(tf32): special_t and member_t come together");
   NTF_REQUIRE(a->special_t || !a->special, NTF_ERR_BAD_ARG, "out_train(tf32): the tensor-core kernel reads the tile-transposed planes (ntf_special_tiles), not `special`");
-  __half* A16 = (__half*)workspace;
+  __half* A16 = a->A16 ? (__half*)const_cast<void*>(a->A16) : (__half*)workspace;
+  NTF_REQUIRE(((uintptr_t)A16 & 15) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): A16 must be 16-byte aligned");
   float* loss_part = (float*)((char*)workspace + align_up((size_t)a->B * a->h * sizeof(__half), 256));
   const int nct = cdiv(a->E, TE);
   CUtensorMap mw, mh, mda;
@@ -676,7 +677,7 @@ int ntf_out_train_tc(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a,
   if ((rc = make_map(ctx, &mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->W, (uint64_t)a->E, HK, TE, 32))) return rc;
   if ((rc = make_map(ctx, &mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)a->B, HK, TB, 64))) return rc;
   if ((rc = make_map(ctx, &mda, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, train ? (const void*)a->dA : (const void*)a->W, (uint64_t)(train ? a->B : a->E), HK, TB, 32))) return rc;
-  NTF_COUNT_LAUNCH; to_half_kernel<<<min(cdiv(a->B * a->h, 256), ctx->sm_count * 4), 256, 0, st>>>(a->A, (size_t)a->B * a->h, A16);
+  if (!a->A16) { NTF_COUNT_LAUNCH; to_half_kernel<<<min(cdiv(a->B * a->h, 256), ctx->sm_count * 4), 256, 0, st>>>(a->A, (size_t)a->B * a->h, A16); }
   if (train) NTF_CUDA(cudaMemsetAsync(a->dA, 0, (size_t)a->B * a->h * sizeof(float), st));
   TcArgs g{};
   g.bias = a->b; g.special_t = const_cast<uint32_t*>(a->special_t); g.member_t = const_cast<uint32_t*>(a->member_t); g.Epad = cdiv(a->E, TE) * TE;

@@ -3,9 +3,12 @@
 // The reference draws B x E random keys per step and keeps the top-ns per row (uniform: fnn.py:48-56; unigram /
 // unigram_b: torch.multinomial without replacement == top-ns of p_j/Exp(1), fnn.py:58-76).  Both are "ns draws
 // without replacement from the row's negatives, with probability proportional to p_j".  Here that distribution
-// is sampled directly: successive draws from the integer CDF of the expert counts (p_j = count_j / B exactly),
-// rejecting the row's own members and experts already drawn -- O(ns log E) per team instead of O(E), all in
-// integer arithmetic so that oracle/sampler_oracle.py reproduces every index bit for bit.
+// is sampled directly by successive draws, rejecting the row's own members and experts already drawn:
+//   unigram   : inversion of the integer CDF of the all-team expert counts (built once per fold), O(ns log E) per team;
+//   unigram_b : p_j = (teams of the batch having expert j) / B, so a draw is simply a uniformly chosen ENTRY of the batch's
+//               member CSR (expert j owns count_j of the nnz entries) -- no histogram, no prefix sum, O(ns) per team;
+//   uniform   : a uniform expert id.
+// All integer arithmetic, so that oracle/sampler_oracle.py reproduces every index bit for bit.
 #include "common.cuh"
 
 int ntf_scan_u32_impl(cudaStream_t st, const uint32_t* in, size_t n, uint32_t* out, int inclusive, uint32_t* grand_total,
@@ -49,8 +52,11 @@ constexpr int NS_WARPS = 4;
 // uniform top-up happens at the same draw index as in the sequential statement.
 __global__ void __launch_bounds__(NS_WARPS * 32) neg_sample_kernel(int nsd, uint64_t seed, uint64_t step, int row0, int B,
                                                                    const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_indices,
-                                                                   int E, int ns, const uint32_t* __restrict__ cdf, int32_t* __restrict__ neg) {
+                                                                   int E, int ns, const uint32_t* __restrict__ cdf, int32_t* __restrict__ neg,
+                                                                   const ntf_dyn* __restrict__ dyn, const int32_t* __restrict__ pool_indptr,
+                                                                   int pool_rows) {
   __shared__ int sacc[NS_WARPS][NS_MAX];
+  if (dyn) step = dyn->step;  // a replayed graph: this step's RNG counter comes from the block ntf_dyn_update wrote
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int* acc = sacc[w];
   const uint32_t lt = (1u << lane) - 1u;
@@ -61,17 +67,33 @@ __global__ void __launch_bounds__(NS_WARPS * 32) neg_sample_kernel(int nsd, uint
     int got = 0;
     uint32_t t = 0;
     bool weighted = (nsd == NTF_NS_UNIGRAM || nsd == NTF_NS_UNIGRAM_B);
+    const bool pool = nsd == NTF_NS_UNIGRAM_B;  // draws are entries of the (global) batch's member CSR
     bool all_experts = false;  // fnn.py:67-69 fallback: uniform over ALL experts, members included
     uint32_t T = 0;
-    if (weighted) {
+    int q0 = 0;
+    if (pool) {
+      q0 = pool_indptr[0];
+      const int q1 = pool_indptr[pool_rows];
+      T = (uint32_t)(q1 - q0);
+      // all the mass on this team's own members <=> every entry of the pool is one of them (normally settled by the first 32 entries)
+      bool other = false;
+      for (int base = q0; base < q1 && !other; base += 32) {
+        const int p = base + lane;
+        other = __any_sync(0xffffffffu, p < q1 && !is_pos(__ldg(m_indices + p)));
+      }
+      if (!other) { weighted = false; all_experts = true; }
+    } else if (weighted) {
       T = __ldg(cdf + E - 1);
       uint32_t pos_mass = 0;
       for (int p = pb; p < pe; ++p) { const int j = __ldg(m_indices + p); pos_mass += __ldg(cdf + j) - (j ? __ldg(cdf + j - 1) : 0u); }
       if (T == pos_mass) { weighted = false; all_experts = true; }
     }
-    auto round32 = [&](bool use_cdf, bool members_ok, int want) {
+    auto round32 = [&](bool use_w, bool members_ok, int want) {
       const uint64_t r = draw64(seed, (uint32_t)(row0 + n), t + lane, step);
-      const int j = use_cdf ? upper_bound_u32(cdf, E, (uint32_t)__umul64hi(r, (uint64_t)T)) : (int)__umul64hi(r, (uint64_t)E);
+      int j;
+      if (!use_w) j = (int)__umul64hi(r, (uint64_t)E);
+      else if (pool) j = __ldg(m_indices + q0 + (int)__umul64hi(r, (uint64_t)T));
+      else j = upper_bound_u32(cdf, E, (uint32_t)__umul64hi(r, (uint64_t)T));
       bool keep = members_ok || !is_pos(j);
       for (int q = 0; q < got; ++q) keep = keep && (acc[q] != j);
       const uint32_t same = __match_any_sync(0xffffffffu, j);
@@ -175,16 +197,23 @@ extern "C" int ntf_expert_cdf(ntf_ctx* ctx, void* stream, int B, const int32_t* 
   return ntf_scan_u32_impl(st, counts, (size_t)E, cdf, 1, nullptr, workspace, workspace_bytes);
 }
 
-extern "C" int ntf_neg_sample(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed, uint64_t step, int row0, int B,
-                              const int32_t* m_indptr, const int32_t* m_indices, int E, int ns, const uint32_t* cdf,
-                              int32_t* neg) {
+int ntf_neg_sample_impl(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed, uint64_t step, int row0, int B, const int32_t* m_indptr,
+                        const int32_t* m_indices, int E, int ns, const uint32_t* cdf, const int32_t* pool_indptr, int pool_rows,
+                        int32_t* neg, const ntf_dyn* dyn) {
   NTF_REQUIRE(ctx && m_indptr && m_indices && neg, NTF_ERR_BAD_ARG, "neg_sample: null pointer");
   NTF_REQUIRE(nsd >= NTF_NS_UNIFORM && nsd <= NTF_NS_UNIGRAM_B, NTF_ERR_BAD_ARG, "neg_sample: nsd=%d", nsd);
-  NTF_REQUIRE(nsd == NTF_NS_UNIFORM || cdf, NTF_ERR_BAD_ARG, "neg_sample: unigram modes need a cdf");
+  NTF_REQUIRE(nsd != NTF_NS_UNIGRAM || cdf, NTF_ERR_BAD_ARG, "neg_sample: unigram needs the cdf of the all-team expert counts");
+  if (!pool_indptr || pool_rows <= 0) { pool_indptr = m_indptr; pool_rows = B; }  // unigram_b: the batch itself
   NTF_REQUIRE(B > 0 && E > 0 && ns > 0 && ns <= NS_MAX, NTF_ERR_UNSUPPORTED, "neg_sample: B=%d E=%d ns=%d (ns<=%d)", B, E, ns, NS_MAX);
-  NTF_COUNT_LAUNCH; neg_sample_kernel<<<min(cdiv(B, NS_WARPS), ctx->sm_count * 16), NS_WARPS * 32, 0, as_stream(stream)>>>(nsd, seed, step, row0, B, m_indptr, m_indices, E, ns, cdf, neg);
+  NTF_COUNT_LAUNCH; neg_sample_kernel<<<min(cdiv(B, NS_WARPS), ctx->sm_count * 16), NS_WARPS * 32, 0, as_stream(stream)>>>(nsd, seed, step, row0, B, m_indptr, m_indices, E, ns, cdf, neg, dyn, pool_indptr, pool_rows);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
+}
+
+extern "C" int ntf_neg_sample(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed, uint64_t step, int row0, int B,
+                              const int32_t* m_indptr, const int32_t* m_indices, int E, int ns, const uint32_t* cdf,
+                              const int32_t* pool_indptr, int pool_rows, int32_t* neg) {
+  return ntf_neg_sample_impl(ctx, stream, nsd, seed, step, row0, B, m_indptr, m_indices, E, ns, cdf, pool_indptr, pool_rows, neg, nullptr);
 }
 
 extern "C" int ntf_special_bits(ntf_ctx* ctx, void* stream, int op, int B, const int32_t* m_indptr, const int32_t* m_indices,

@@ -14,6 +14,7 @@ Data layout in HBM:
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -97,23 +98,30 @@ class _HostStage:
         self.buf = torch.zeros(words, dtype=torch.int32, device=device)
         self.n = 0
 
-    def view(self, n, nnz_s, nnz_m):
+    def view(self, n, cap_s, cap_m):
+        """segment offsets depend on (n, cap_s, cap_m) only: batches packed with the same capacities land at the same addresses"""
         o, b = 0, self.buf
         self.n = n
         self.s_indptr = b[o:o + n + 1]; o += n + 1
         self.m_indptr = b[o:o + n + 1]; o += n + 1
-        self.s_indices = b[o:o + nnz_s]; o += nnz_s
-        self.s_ent_row = b[o:o + nnz_s]; o += nnz_s
-        self.m_indices = b[o:o + nnz_m]; o += nnz_m
+        self.s_indices = b[o:o + cap_s]; o += cap_s
+        self.s_ent_row = b[o:o + cap_s]; o += cap_s
+        self.m_indices = b[o:o + cap_m]; o += cap_m
         return o
 
 
-def pack_host_batch(s_ptr, s_idx, m_ptr, m_idx):
-    """compact CSR of one batch (numpy int arrays, offsets starting at 0) -> the pinned int32 block `Engine.step_host` copies"""
+def pack_host_batch(s_ptr, s_idx, m_ptr, m_idx, cap_s=None, cap_m=None):
+    """compact CSR of one batch (numpy int arrays, offsets starting at 0) -> the pinned int32 block `Engine.step_host` copies.
+    cap_s / cap_m: pad the index segments to fixed capacities (>= nnz) so that every batch of a run has the same layout -- the
+    device addresses then never change and the step replays one captured graph."""
     n = len(s_ptr) - 1
+    cap_s = len(s_idx) if cap_s is None else int(cap_s)
+    cap_m = len(m_idx) if cap_m is None else int(cap_m)
+    assert cap_s >= len(s_idx) and cap_m >= len(m_idx)
     s_row = np.repeat(np.arange(n, dtype=np.int32), np.diff(s_ptr))
-    blk = np.concatenate([s_ptr, m_ptr, s_idx, s_row, m_idx]).astype(np.int32)
-    return torch.from_numpy(blk).pin_memory(), n, len(s_idx), len(m_idx)
+    pad = lambda a, c: np.concatenate([np.asarray(a, dtype=np.int32), np.zeros(c - len(a), dtype=np.int32)])
+    blk = np.concatenate([s_ptr, m_ptr, pad(s_idx, cap_s), pad(s_row, cap_s), pad(m_idx, cap_m)]).astype(np.int32)
+    return torch.from_numpy(blk).pin_memory(), n, cap_s, cap_m
 
 
 class Engine:
@@ -127,6 +135,8 @@ class Engine:
         self.device = torch.device(device)
         self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         _lib.ctx(self.dev_index)  # fails loudly if this is not a B200-class device
+        self.h = _lib.new_ctx(self.dev_index)  # this engine's own handle: side streams / events of ntf_fnn_step
+        self._cap_stream = torch.cuda.Stream(device=self.device)  # graph captures run here
         self.S, self.hidden, self.E_total = int(S), [int(x) for x in hidden], int(E)
         self.shard = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
         self.e_lo, self.e_hi = self.E_total * self.shard[0] // self.shard[1], self.E_total * (self.shard[0] + 1) // self.shard[1]
@@ -146,6 +156,12 @@ class Engine:
         self._layout()
         self._buffers()
         self.adam_t = 0
+        # CUDA graphs (include/ntf_b200.h): batch i of a split is the same launch sequence in every epoch, so it is captured the first
+        # time it runs and replayed afterwards; the scalars that do change (RNG counter, lr, Adam's bias corrections) sit in `dyn`.
+        self.use_graphs = os.environ.get('NTF_GRAPHS', '1') != '0'
+        self.dyn = torch.zeros(8, dtype=torch.int32, device=self.device)  # ntf_dyn (32 bytes)
+        self._graphs, self.max_graphs, self._ws_gen = {}, 8192, -1
+        self.graph_event_factory = None  # (bench.py) called at capture time -> a cudaEvent_t pair recorded around the output layer
         self.global_step = 0  # counts train AND valid steps: the sampler's Philox counter (fnn.py:148 samples in valid too)
         self.world, self.rank = 1, 0
 
@@ -292,11 +308,9 @@ class Engine:
             neg.copy_(t)
             return neg.contiguous()
         mptr = sp.m_indptr.data_ptr() + 4 * b0
-        if self.nsd == NSD['unigram_b']:
-            g0, gB = (b0, B) if gbatch is None else gbatch
-            ops.expert_cdf(gB, sp.m_indptr.data_ptr() + 4 * g0, sp.m_indices, self.E_total, self.counts, self.cdf, self.ws)
+        g0, gB = (b0, B) if gbatch is None else gbatch  # unigram_b draws from the member CSR of the global batch
         ops.neg_sample(self.nsd, self.seed, self.global_step, b0, B, mptr, sp.m_indices, self.E_total, self.ns,
-                       self.cdf if self.nsd != NSD['uniform'] else None, self.neg)
+                       self.cdf if self.nsd == NSD['unigram'] else None, self.neg, sp.m_indptr.data_ptr() + 4 * g0, gB)
         return self.neg
 
     def _fnn_args(self):
@@ -350,20 +364,57 @@ class Engine:
             a.lr, a.adam_t = float(lr), self.adam_t + 1
         pe = getattr(self, 'prof_events', None)  # (bench.py) a recorded-once torch event pair around the output-layer call
         a.prof_ev[0], a.prof_ev[1] = (pe[0].cuda_event, pe[1].cuda_event) if pe else (None, None)
+        a.dyn = None
+        graphed = self.use_graphs and neg_host is None and pe is None
+        if graphed:
+            # everything that is baked into the captured launches; the rest (step counter, lr, adam_t) goes through `dyn`
+            key = (a.s_indptr, a.s_indices, a.s_ent_row, a.m_indptr, a.m_indices, b0, B, a.train, a.run_adam, a.loss_out, a.loss_scale, a.gB, a.g_m_indptr)
+            graphed = len(self._graphs) < self.max_graphs or any(key + (ph,) in self._graphs for ph in (1, 3))
+        if graphed:
+            a.dyn = self.dyn.data_ptr()
+            ops.dyn_update(self.dev_index, self.dyn, self.global_step, float(lr) if train else 0.0, 0.9, 0.999, 1e-8, self.adam_t + 1)
         if sharded and train:
             # every rank runs the same batch on its expert range; the only exchange is dA = sum over shards of dz W  [B,h]
-            a.phase = 1
-            ops.fnn_step(self.dev_index, a, self.ws)
+            self._run(a, 1, key if graphed else None)
             self.allreduce(self.dact[-1][:B])
-            a.phase = 2
-            ops.fnn_step(self.dev_index, a, self.ws)
+            self._run(a, 2, key if graphed else None)
         else:
-            a.phase = 3
-            ops.fnn_step(self.dev_index, a, self.ws)
+            self._run(a, 3, key if graphed else None)
         self.global_step += 1
         if not train: return
         if dp: self.optimizer_step(lr)
         else: self.adam_t += 1
+
+    def _run(self, a, phase, key):
+        """enqueue one phase of ntf_fnn_step: directly (key None), or as the replay of its captured graph"""
+        a.phase = phase
+        if key is None:
+            ops.fnn_step(self.dev_index, a, self.ws, self.h)
+            return
+        ops.fnn_step_workspace(self.dev_index, a, self.ws)  # the workspace must exist before a capture starts ...
+        if self.ws.gen != self._ws_gen:  # ... and a workspace that had to grow moved: graphs captured over the old one are void
+            self._graphs.clear(); self._ws_gen = self.ws.gen
+        g = self._graphs.get(key + (phase,))
+        if g is None:
+            ev = self.graph_event_factory() if (self.graph_event_factory and phase & 1) else None
+            if ev: a.prof_ev[0], a.prof_ev[1] = ev
+            g = ops.Graph(self.dev_index, self.h, self._cap_stream)
+            with g:
+                ops.fnn_step(self.dev_index, a, self.ws, self.h)
+            a.prof_ev[0], a.prof_ev[1] = None, None
+            self._graphs[key + (phase,)] = g
+        g.launch()
+
+    def __del__(self):
+        try:
+            self._graphs.clear()
+            if getattr(self, 'h', None): _lib.lib().ntf_destroy(self.h)
+        except Exception: pass
+        self.h = None
+
+    def drop_graphs(self):
+        """forget every captured step (call after buffers the graphs point into were re-allocated)"""
+        self._graphs.clear()
 
     def optimizer_step(self, lr):
         if self.world > 1:
@@ -496,14 +547,14 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ streaming entry point (host batches)
-    def step_host(self, packed, n, nnz_s, nnz_m, rank=0, G=1, lr=1e-3, train=True):
+    def step_host(self, packed, n, cap_s, cap_m, rank=0, G=1, lr=1e-3, train=True):
         """one step on a batch the HOST holds (`pack_host_batch`: compact CSR of the global batch in one pinned block): one H2D copy,
         this rank trains on its slice, and the loss comes back to the host (one sync) -- the per-step shape of the reference's loop
         (fnn.py:118-140: H2D of the batch, .item())."""
         st = getattr(self, '_hstage', None)
         if st is None or st.buf.numel() < packed.numel():
             st = self._hstage = _HostStage(self.device, 2 * packed.numel() + 1024)
-        st.view(n, nnz_s, nnz_m)
+        st.view(n, cap_s, cap_m)
         st.buf[:packed.numel()].copy_(packed, non_blocking=True)
         b = -(-n // G)
         lo, hi = min(n, rank * b), min(n, (rank + 1) * b)

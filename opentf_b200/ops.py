@@ -33,12 +33,13 @@ class Workspace:
     """a grow-only scratch buffer owned by the caller side (the library never allocates)."""
 
     def __init__(self, device):
-        self.device, self.buf = device, None
+        self.device, self.buf, self.gen = device, None, 0  # gen counts re-allocations (captured graphs hold the old address)
 
     def get(self, nbytes):
         if nbytes <= 0: return None, 0
         if self.buf is None or self.buf.numel() < nbytes:
             self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self.gen += 1
         return self.buf.data_ptr(), self.buf.numel()
 
 
@@ -86,10 +87,10 @@ def expert_cdf(B, m_indptr_ptr, m_indices, E, counts, cdf, ws):
     check(lib().ntf_expert_cdf(_lib.ctx(d), _stream(d), B, m_indptr_ptr, _p(m_indices, I32), E, _p(counts), _p(cdf), p, nb), 'ntf_expert_cdf')
 
 
-def neg_sample(nsd, seed, step, row0, B, m_indptr_ptr, m_indices, E, ns, cdf, neg):
+def neg_sample(nsd, seed, step, row0, B, m_indptr_ptr, m_indices, E, ns, cdf, neg, pool_indptr_ptr=None, pool_rows=0):
     d = _dev(m_indices)
     check(lib().ntf_neg_sample(_lib.ctx(d), _stream(d), nsd, seed, step, row0, B, m_indptr_ptr, _p(m_indices, I32), E, ns, _p(cdf),
-                               _p(neg, I32)), 'ntf_neg_sample')
+                               pool_indptr_ptr, pool_rows, _p(neg, I32)), 'ntf_neg_sample')
 
 
 def special_bits(op, B, m_indptr_ptr, m_indices, neg, ns, E, special, pitch, e_lo=0):
@@ -207,8 +208,48 @@ def add_signed(X, bits, pitch, B, h, Y):
     check(lib().ntf_add_signed(_lib.ctx(d), _stream(d), _p(X, F32), _p(bits), pitch, B, h, _p(Y, F32)), 'ntf_add_signed')
 
 
-def fnn_step(dev, args, ws):
-    """one whole Fnn batch (ntf_fnn_step): args is a filled _lib.FnnStepArgs"""
-    h = _lib.ctx(dev)
+def dyn_update(dev, dyn, step, lr, b1, b2, eps, adam_t):
+    check(lib().ntf_dyn_update(_lib.ctx(dev), _stream(dev), _p(dyn), int(step), lr, b1, b2, eps, int(adam_t)), 'ntf_dyn_update')
+
+
+class Graph:
+    """`with Graph(dev) as g: <library calls>` captures them on torch's current stream (nothing runs); g.launch() replays."""
+
+    def __init__(self, dev, handle, capture_stream):
+        """capture_stream: a torch stream of the caller's own (the legacy default stream, torch's usual current stream, cannot be
+        captured); handle: the ntf_ctx the captured calls use"""
+        self.dev, self.h, self.ctx_h, self.cap = dev, None, handle, capture_stream
+
+    def __enter__(self):
+        self._ctx = torch.cuda.stream(self.cap)  # the calls inside the block pick this stream up as "current"
+        self._ctx.__enter__()
+        check(lib().ntf_graph_begin(self.ctx_h, _stream(self.dev)), 'ntf_graph_begin')
+        return self
+
+    def __exit__(self, et, ev, tb):
+        h = _lib.vp()
+        rc = lib().ntf_graph_end(self.ctx_h, _stream(self.dev), C.byref(h))
+        self._ctx.__exit__(et, ev, tb)
+        if et is None: check(rc, 'ntf_graph_end')
+        self.h = h if rc == 0 else None
+        return False
+
+    def launch(self):
+        check(lib().ntf_graph_launch(self.h, _stream(self.dev)), 'ntf_graph_launch')
+
+    def __del__(self):
+        try:
+            if self.h: lib().ntf_graph_destroy(self.h)
+        except Exception: pass
+        self.h = None
+
+
+def fnn_step_workspace(dev, args, ws):
+    return ws.get(lib().ntf_fnn_step_workspace_bytes(_lib.ctx(dev), C.byref(args)))
+
+
+def fnn_step(dev, args, ws, handle=None):
+    """one whole Fnn batch (ntf_fnn_step): args is a filled _lib.FnnStepArgs; handle: the caller's own ntf_ctx (its side streams)"""
+    h = handle if handle is not None else _lib.ctx(dev)
     p, nb = ws.get(lib().ntf_fnn_step_workspace_bytes(h, C.byref(args)))
     check(lib().ntf_fnn_step(h, _stream(dev), C.byref(args), p, nb), 'ntf_fnn_step')

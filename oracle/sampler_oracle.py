@@ -9,7 +9,9 @@ sampler and this restatement of its documented counter RNG.  Two checks live in 
   * distribution: chi-square of this sampler against `oracle.fnn_oracle.ns_unigram / ns_uniform` (the reference's
     arithmetic) on a small expert set.
 Everything is integer arithmetic: Philox4x32-10 (Salmon et al., SC'11) -> 64-bit draw -> multiply-high onto the
-range -> binary search in the inclusive CDF of the integer expert counts -> rejection of members / duplicates.
+range -> (unigram) binary search in the inclusive CDF of the integer all-team expert counts / (unigram_b) that entry of
+the batch's concatenated member lists (expert j owns count_j of them: the batch unigram of fnn.py:74-76 without a
+histogram) / (uniform) that expert id -> rejection of members / duplicates.
 """
 import numpy as np
 
@@ -38,14 +40,18 @@ def expert_cdf(member_rows, E):
     return counts, np.cumsum(counts)
 
 
-def sample_row(nsd, seed, step, row_id, pos, E, ns, cdf):
-    """one team: `pos` = its member ids.  Mirrors neg_sample_kernel statement by statement."""
+def sample_row(nsd, seed, step, row_id, pos, E, ns, cdf=None, pool=None):
+    """one team: `pos` = its member ids; `cdf` (unigram) = inclusive CDF of the all-team counts; `pool` (unigram_b) = the
+    member ids of every team of the (global) batch, concatenated in row order.  Mirrors neg_sample_kernel statement by statement."""
     pos = [int(p) for p in pos]
     out, t = [], 0
     max_tries = 32 * ns + 64
     weighted = nsd in ('unigram', 'unigram_b')
     all_experts = False
-    if weighted:
+    if nsd == 'unigram_b':
+        T = len(pool)
+        if all(int(j) in pos for j in pool): weighted, all_experts = False, True
+    elif weighted:
         T = int(cdf[E - 1])
         pos_mass = sum(int(cdf[j]) - (int(cdf[j - 1]) if j else 0) for j in pos)
         if T == pos_mass: weighted, all_experts = False, True
@@ -53,7 +59,7 @@ def sample_row(nsd, seed, step, row_id, pos, E, ns, cdf):
         tries = 0
         while len(out) < ns and tries < max_tries:
             x = (draw64(seed, row_id, t, step) * T) >> 64
-            j = int(np.searchsorted(cdf, x, side='right'))
+            j = int(pool[x]) if nsd == 'unigram_b' else int(np.searchsorted(cdf, x, side='right'))
             if j not in pos and j not in out: out.append(j)
             tries += 1; t += 1
     avail = E if all_experts else E - len(pos)
@@ -70,7 +76,11 @@ def sample_row(nsd, seed, step, row_id, pos, E, ns, cdf):
     return out + [-1] * (ns - len(out))
 
 
-def sample_negatives(nsd, seed, step, row0, member_rows, E, ns, cdf=None):
-    """[B, ns] int32; `cdf` = inclusive CDF of counts (batch counts for unigram_b, all-team counts for unigram)."""
-    if nsd == 'unigram_b' and cdf is None: cdf = expert_cdf(member_rows, E)[1]
-    return np.array([sample_row(nsd, seed, step, row0 + n, r, E, ns, cdf) for n, r in enumerate(member_rows)], dtype=np.int32)
+def sample_negatives(nsd, seed, step, row0, member_rows, E, ns, cdf=None, pool_rows=None):
+    """[B, ns] int32; `cdf` = inclusive CDF of the all-team counts (unigram); `pool_rows` = member lists of the global batch the
+    rows are a slice of (unigram_b; default: the rows themselves)."""
+    pool = None
+    if nsd == 'unigram_b':
+        src = member_rows if pool_rows is None else pool_rows
+        pool = np.concatenate([np.asarray(r, dtype=np.int64) for r in src]) if len(src) else np.zeros(0, dtype=np.int64)
+    return np.array([sample_row(nsd, seed, step, row0 + n, r, E, ns, cdf, pool) for n, r in enumerate(member_rows)], dtype=np.int32)

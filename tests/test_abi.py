@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(built):
     lib = ctypes.CDLL(built)
     for name in declared_symbols():
         assert hasattr(lib, name), f'{name} declared in ntf_b200.h but not exported'
-    assert lib.ntf_version() == 1
+    assert lib.ntf_version() == 2
 
 
 def test_python_binding_covers_the_header(built):

@@ -167,7 +167,7 @@ def test_neg_sample_bit_exact_against_cpu_restatement(ops, ws, nsd, B, E, ns):
     cdf_host = cdf.cpu().numpy().astype(np.int64)
     for step, row0 in ((0, 0), (7, 123), (2 ** 33 + 5, 10)):
         neg = torch.empty(B, ns, dtype=torch.int32, device=DEV)
-        ops.neg_sample(NSD[nsd], 0xDEADBEEF12345, step, row0, B, indptr.data_ptr(), indices, E, ns, cdf if nsd != 'uniform' else None, neg)
+        ops.neg_sample(NSD[nsd], 0xDEADBEEF12345, step, row0, B, indptr.data_ptr(), indices, E, ns, cdf if nsd == 'unigram' else None, neg)
         ref = SO.sample_negatives(nsd, 0xDEADBEEF12345, step, row0, member_lists(Y), E, ns, cdf_host)
         got = neg.cpu().numpy()
         assert (got == ref).all()
@@ -176,6 +176,25 @@ def test_neg_sample_bit_exact_against_cpu_restatement(ops, ws, nsd, B, E, ns):
             assert len(set(live)) == len(live)
             if nsd == 'uniform' or cdf_host[-1] > sum(cdf_host[j] - (cdf_host[j - 1] if j else 0) for j in mem):
                 assert not set(live) & set(mem)
+            if nsd == 'unigram_b' and E > 10 * B * 6:  # candidates are experts of the batch's other teams (plenty of them here)
+                assert set(live) <= set(Y.indices.tolist())
+
+
+def test_neg_sample_unigram_b_pool_is_the_global_batch(ops):
+    """a data-parallel rank samples for its slice of the rows from the member CSR of the whole global batch"""
+    from opentf_b200._lib import NSD
+    rng = np.random.default_rng(3)
+    Y = rand_csr(rng, 96, 5000, 2, 5)
+    indptr, indices = dev_csr(Y)
+    lists = member_lists(Y)
+    full = torch.empty(96, 5, dtype=torch.int32, device=DEV)
+    ops.neg_sample(NSD['unigram_b'], 11, 4, 0, 96, indptr.data_ptr(), indices, 5000, 5, None, full)
+    for lo, hi in ((0, 32), (32, 96)):
+        part = torch.empty(hi - lo, 5, dtype=torch.int32, device=DEV)
+        ops.neg_sample(NSD['unigram_b'], 11, 4, lo, hi - lo, indptr.data_ptr() + 4 * lo, indices, 5000, 5, None, part, indptr.data_ptr(), 96)
+        assert torch.equal(part, full[lo:hi])  # the same rows get the same negatives however the batch is cut across ranks
+        ref = SO.sample_negatives('unigram_b', 11, 4, lo, lists[lo:hi], 5000, 5, None, pool_rows=lists)
+        assert (part.cpu().numpy() == ref).all()
 
 
 def test_neg_sample_fallbacks(ops, ws):
@@ -186,11 +205,21 @@ def test_neg_sample_fallbacks(ops, ws):
     indptr, indices = dev_csr(Y)
     cdf = torch.from_numpy(cdf_host.astype(np.int32)).to(DEV)
     neg = torch.empty(3, 4, dtype=torch.int32, device=DEV)
-    ops.neg_sample(NSD['unigram_b'], 5, 1, 0, 3, indptr.data_ptr(), indices, 6, 4, cdf, neg)
-    ref = SO.sample_negatives('unigram_b', 5, 1, 0, member_lists(Y), 6, 4, cdf_host)
+    ops.neg_sample(NSD['unigram'], 5, 1, 0, 3, indptr.data_ptr(), indices, 6, 4, cdf, neg)
+    ref = SO.sample_negatives('unigram', 5, 1, 0, member_lists(Y), 6, 4, cdf_host)
     assert (neg.cpu().numpy() == ref).all()
     assert {0, 1} <= set(ref[1].tolist()) and 2 not in ref[1] and len(set(ref[1].tolist())) == 4
     for r in (0, 2): assert len(set(ref[r].tolist())) == 4 and min(ref[r]) >= 0
+    # unigram_b, the pool is the batch itself: row 2 owns every expert of the batch -> ALL experts; rows 0, 1: the others' experts, then the top-up
+    ops.neg_sample(NSD['unigram_b'], 5, 1, 0, 3, indptr.data_ptr(), indices, 6, 4, None, neg)
+    ref = SO.sample_negatives('unigram_b', 5, 1, 0, member_lists(Y), 6, 4)
+    assert (neg.cpu().numpy() == ref).all()
+    assert {2, 3} <= set(ref[0].tolist()) and not {0, 1} & set(ref[0].tolist())
+    assert {0, 1, 3} <= set(ref[1].tolist()) and 2 not in ref[1]
+    assert len(set(ref[2].tolist())) == 4 and min(ref[2]) >= 0
+    # a batch of one team: its own members are the whole pool
+    ops.neg_sample(NSD['unigram_b'], 5, 1, 0, 1, indptr.data_ptr(), indices, 6, 4, None, neg)
+    assert (neg.cpu().numpy()[:1] == SO.sample_negatives('unigram_b', 5, 1, 0, member_lists(Y)[:1], 6, 4)).all()
     # fewer negatives than ns (uniform): the two non-members, then -1 padding
     ops.neg_sample(NSD['uniform'], 5, 1, 0, 3, indptr.data_ptr(), indices, 6, 4, None, neg)
     assert sorted(neg.cpu().numpy()[2].tolist()) == [-1, -1, 4, 5]

@@ -117,14 +117,15 @@ def test_sampler_oracle_distribution_matches_reference_sampler():
     y = torch.zeros(1, E); y[0, [2, 7]] = 1
     members = [[0, 1, 2, 3], [2, 7], [3, 3 + 1, 5], [0, 5, 9], [0, 2]]  # batch rows -> counts
     counts, cdf = SO.expert_cdf(members, E)
+    pool = np.concatenate([np.asarray(m) for m in members])
     uni = torch.tensor(counts / len(members), dtype=torch.float32).unsqueeze(0)
-    for nsd in ('uniform', 'unigram_b'):
+    for nsd in ('uniform', 'unigram', 'unigram_b'):
         torch.manual_seed(0)
         ref = np.zeros(E); mine = np.zeros(E)
         for t in range(trials):
             r = O.ns_uniform(y, ns) if nsd == 'uniform' else O.ns_unigram(y, uni, ns)
             ref[r.numpy().ravel()] += 1
-            m = SO.sample_row(nsd, 1234, t, 0, [2, 7], E, ns, cdf)
+            m = SO.sample_row(nsd, 1234, t, 0, [2, 7], E, ns, cdf, pool)
             mine[[j for j in m if j >= 0]] += 1
         assert mine[2] == 0 and mine[7] == 0 and ref[2] == 0 and ref[7] == 0
         live = ref > 0
@@ -135,10 +136,14 @@ def test_sampler_oracle_distribution_matches_reference_sampler():
 
 def test_sampler_oracle_edge_cases():
     # no candidate mass outside the team's own members -> uniform over ALL experts (fnn.py:67-69)
-    out = SO.sample_row('unigram_b', 7, 0, 0, [1, 2], 6, 3, np.cumsum([0, 1, 1, 0, 0, 0]))
+    out = SO.sample_row('unigram', 7, 0, 0, [1, 2], 6, 3, np.cumsum([0, 1, 1, 0, 0, 0]))
+    assert len(set(out)) == 3 and all(0 <= j < 6 for j in out)
+    out = SO.sample_row('unigram_b', 7, 0, 0, [1, 2], 6, 3, None, [1, 2, 2, 1])
     assert len(set(out)) == 3 and all(0 <= j < 6 for j in out)
     # fewer weighted candidates than ns -> the rest is topped up uniformly from the non-members
-    out = SO.sample_row('unigram_b', 7, 0, 0, [1], 6, 3, np.cumsum([0, 1, 0, 0, 2, 0]))
+    out = SO.sample_row('unigram', 7, 0, 0, [1], 6, 3, np.cumsum([0, 1, 0, 0, 2, 0]))
+    assert 4 in out and 1 not in out and len(set(out)) == 3
+    out = SO.sample_row('unigram_b', 7, 0, 0, [1], 6, 3, None, [1, 4, 4])
     assert 4 in out and 1 not in out and len(set(out)) == 3
     # fewer negatives than ns -> padded with -1
     out = SO.sample_row('uniform', 7, 0, 0, [0, 1, 2], 5, 4, None)
