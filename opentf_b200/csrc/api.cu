@@ -54,6 +54,8 @@ extern "C" int ntf_create(int device, ntf_ctx** out) {
     if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
   }
   if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_fork_opt, cudaEventDisableTiming);
+  if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_join_opt, cudaEventDisableTiming);
   cudaSetDevice(cur);
   if (es != cudaSuccess) {
     ntf_set_error("ntf_create: side streams / events: %s", cudaGetErrorString(es));
@@ -68,6 +70,7 @@ extern "C" int ntf_destroy(ntf_ctx* ctx) {
   if (ctx) {
     for (int i = 0; i < 2; ++i) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
     cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_fork_opt); cudaEventDestroy(ctx->ev_join_opt);
   }
   delete ctx;
   return NTF_OK;

@@ -18,6 +18,7 @@ struct ntf_ctx {
   // capture the same calls become parallel branches of the graph
   cudaStream_t side[2];
   cudaEvent_t ev_fork, ev_join[2];
+  cudaEvent_t ev_fork_opt, ev_join_opt;  // second fork of a step: Adam on the output layer's segment next to the input layer's backward pass
 };
 
 // ---- launch accounting (bench.py reports how many of OUR kernels ran in the timed region) ----------------

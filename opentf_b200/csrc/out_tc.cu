@@ -164,7 +164,7 @@ struct TcArgs {
 };
 
 constexpr int EPI_WARPS = 16;
-constexpr int NT = 768;  // warps 0-15: logits/loss epilogue, 16-19: dA epilogue, 20: TMA, 21: MMA issuer, 22: special planes, 23: idle
+constexpr int NT = 736;  // warps 0-15: logits/loss epilogue, 16-19: dA epilogue, 20: TMA, 21: MMA issuer, 22: special planes (23 warps: 88 registers per thread)
 constexpr int WARP_DA = 16, WARP_TMA = 20, WARP_MMA = 21, WARP_SP = 22;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 
@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         // dA[128 n x 128 k] = dz[j, n]^T . W16[j, k] : K = 128 experts = 8 steps of 16
         mbar_wait(bar(BAR_DA_EMPTY), (it & 1) ^ 1);
         tc_fence_after();
+        if (g.timing && blockIdx.x == 0 && !(g.exp & 4)) g.timing[it * 8 + 7] = clock64();  // dW issued, dA accumulator free
 #pragma unroll
         for (int i = 0; i < TE / 16; ++i) {
           const uint64_t da = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + i * 2048, CHUNK, 1024);                        // MN-major, M = teams
@@ -368,6 +369,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       mbar_arrive(bar(BAR_W16));
     }
     float acc_lin = 0.f, acc_lg = 0.f, loss_sp = 0.f, db_acc = 0.f;  // dense loss = tnw*ln2*(acc_lg - acc_lin): sums of lg2(1+e) and of t = -c*x
+    float2 acc_lin2 = make_float2(0.f, 0.f), db_acc2 = make_float2(0.f, 0.f);  // the dense pass's packed halves of acc_lin / db_acc
     // dz is kept as w*(sigmoid-y)*slope, i.e. true dz / loss_scale; experts past E (last tile) get zero gradient and their loss is dropped below
     const float c_pos = e_ok ? g.tnw : 0.f, c_neg = e_ok ? g.tnw * NTF_LRELU_SLOPE : 0.f;
     const bool has_sp = MODE == 0 && g.special_t && !(g.exp & 2);
@@ -429,43 +431,60 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         if (it == 0) mbar_wait(bar(BAR_W16), 0);  // every thread is done with the fp32 landing zone before the dz ring is written
         mbar_wait(bar(BAR_DZ_EMPTY + s), ph ^ 1);
       }
-      uint8_t* dzrow = sgen + OFF_DZ + s * DZ_BYTES + (cb >> 1) * CHUNK + jl * 128;
+      // this thread's 128-byte row of the dz^T tile (shared-state-space address: no generic -> shared conversion per store); the 16-byte
+      // unit of group u is (unit0 + u) ^ (jl & 7) = kx ^ u
+      const uint32_t dzrow = sbase + OFF_DZ + s * DZ_BYTES + (cb >> 1) * CHUNK + jl * 128;
       const int unit0 = 4 * (cb & 1);
+      const uint32_t kx = (uint32_t)(unit0 ^ (jl & 7));
       // Dense pass: every element as (target 0, weight tnw):  loss = softplus(x) = x + ln(1 + exp(-x)),  dz = tnw*sigmoid(x)*slope,
       // x = lrelu(z + b).  With c = log2(e):  t = -c*x = min(-c*(z+b), -0.01c*(z+b))  (two FFMAs with the bias folded in, one FMNMX),
-      // e = 2^t, den = 1 + e, sigmoid(x) = 1/den, softplus(x) = (-t + lg2(den))*ln2.  lg2 is taken once per 8 elements, of the product
-      // of the den factors; sum(t) and sum(lg2) are accumulated separately and combined once per CTA.  8 teams -> one 16-byte unit
-      // of the dz^T row; 8 independent chains keep the MUFU pipe fed.  A product that overflows (logits below about -300: den > 2^16
-      // each) falls back to per-element logarithms.
+      // e = 2^t, den = 1 + e, sigmoid(x) = 1/den, softplus(x) = (-t + lg2(den))*ln2.
+      // The loop is bound by issue slots, so: (1) the fp32 arithmetic runs as PACKED f32x2 instructions (sm_100: FFMA2 / FADD2 / FMUL2,
+      // two elements per issue slot); (2) ONE reciprocal and ONE logarithm per 8 elements: the product tree of the 8 denominators
+      // gives lg2 of their product, and walking it back down from 1/product gives every 1/den (1.25 instead of 2.125 MUFU ops per
+      // logit).  sum(t), sum(lg2) and db are accumulated in packed registers and combined once per CTA.  8 teams -> one 16-byte unit
+      // of the dz^T row.  A product beyond 1e30 (logits below about -70) falls back to per-element logarithms / reciprocals.
       auto dense8 = [&](int u, auto masked) {
-        float gz[8], den[8];
-        float prod = 1.f;
+        const float2 k1 = make_float2(-LOG2E, -LOG2E), k2 = make_float2(-LOG2E * NTF_LRELU_SLOPE, -LOG2E * NTF_LRELU_SLOPE);
+        const float2 kb1v = make_float2(kb1, kb1), kb2v = make_float2(kb2, kb2), one2 = make_float2(1.f, 1.f);
+        float2 D[4], G[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float t1 = fmaf(z[u * 8 + q], -LOG2E, kb1);
-          const float t2 = fmaf(z[u * 8 + q], -LOG2E * NTF_LRELU_SLOPE, kb2);
-          float tt = fminf(t1, t2);
-          const float ex = ex2_approx(tt);
-          den[q] = 1.f + ex;
-          gz[q] = rcp_approx(den[q]) * (t1 < 0.f ? c_pos : c_neg);
-          if (decltype(masked)::value && u * 8 + q >= nrem) { gz[q] = 0.f; tt = 0.f; den[q] = 1.f; }  // teams past the end of the batch
-          acc_lin += tt;
-          prod *= den[q];
-          db_acc += gz[q];
+        for (int p = 0; p < 4; ++p) {
+          const float2 zz = make_float2(z[u * 8 + 2 * p], z[u * 8 + 2 * p + 1]);
+          const float2 t1 = __ffma2_rn(zz, k1, kb1v), t2 = __ffma2_rn(zz, k2, kb2v);
+          float2 tt = make_float2(fminf(t1.x, t2.x), fminf(t1.y, t2.y));
+          G[p] = make_float2(t1.x < 0.f ? c_pos : c_neg, t1.y < 0.f ? c_pos : c_neg);
+          D[p] = __fadd2_rn(make_float2(ex2_approx(tt.x), ex2_approx(tt.y)), one2);
+          if (decltype(masked)::value) {  // teams past the end of the batch
+            if (u * 8 + 2 * p >= nrem) { G[p].x = 0.f; tt.x = 0.f; D[p].x = 1.f; }
+            if (u * 8 + 2 * p + 1 >= nrem) { G[p].y = 0.f; tt.y = 0.f; D[p].y = 1.f; }
+          }
+          acc_lin2 = __fadd2_rn(acc_lin2, tt);
         }
-        if (prod < 3.0e38f) {
+        const float2 M01 = __fmul2_rn(D[0], D[1]), M23 = __fmul2_rn(D[2], D[3]);
+        const float2 Q = __fmul2_rn(M01, M23);
+        const float prod = Q.x * Q.y;
+        if (prod < 1.0e30f) {
           acc_lg += lg2_approx(prod);
+          const float r = rcp_approx(prod);
+          const float2 RQ = __fmul2_rn(make_float2(r, r), make_float2(Q.y, Q.x));  // (1/Q.x, 1/Q.y)
+          const float2 R01 = __fmul2_rn(RQ, M23), R23 = __fmul2_rn(RQ, M01);      // 1/M01, 1/M23
+          G[0] = __fmul2_rn(G[0], __fmul2_rn(R01, D[1])); G[1] = __fmul2_rn(G[1], __fmul2_rn(R01, D[0]));
+          G[2] = __fmul2_rn(G[2], __fmul2_rn(R23, D[3])); G[3] = __fmul2_rn(G[3], __fmul2_rn(R23, D[2]));
         } else {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc_lg += lg2_approx(den[q]);
+          for (int p = 0; p < 4; ++p) {
+            acc_lg += lg2_approx(D[p].x) + lg2_approx(D[p].y);
+            G[p].x *= rcp_approx(D[p].x); G[p].y *= rcp_approx(D[p].y);
+          }
         }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) db_acc2 = __fadd2_rn(db_acc2, G[p]);
         if (train) {
-          const __half2 h0 = __floats2half2_rn(gz[0], gz[1]), h1 = __floats2half2_rn(gz[2], gz[3]);
-          const __half2 h2 = __floats2half2_rn(gz[4], gz[5]), h3 = __floats2half2_rn(gz[6], gz[7]);
-          uint4 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-          pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(dzrow + (((unit0 + u) ^ (jl & 7)) << 4)) = pk;
+          const __half2 h0 = __floats2half2_rn(G[0].x, G[0].y), h1 = __floats2half2_rn(G[1].x, G[1].y);
+          const __half2 h2 = __floats2half2_rn(G[2].x, G[2].y), h3 = __floats2half2_rn(G[3].x, G[3].y);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dzrow + ((kx ^ (uint32_t)u) << 4)), "r"(*reinterpret_cast<const uint32_t*>(&h0)),
+                       "r"(*reinterpret_cast<const uint32_t*>(&h1)), "r"(*reinterpret_cast<const uint32_t*>(&h2)), "r"(*reinterpret_cast<const uint32_t*>(&h3)) : "memory");
         }
       };
       if (nrem >= 32) {  // (warp-uniform)
@@ -520,6 +539,8 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       }
       if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[it * 8 + 6] = clock64();
     }
+    acc_lin += acc_lin2.x + acc_lin2.y;
+    db_acc += db_acc2.x + db_acc2.y;
     if (MODE == 0) {
       // loss partial of this CTA and db: fixed-order combines (shuffle tree, then warps / team blocks in order)
       float* red = reinterpret_cast<float*>(sgen + OFF_BAR + NUM_BARS * 8 + 16);   // [16]
@@ -594,6 +615,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
+        if (g.timing && blockIdx.x == 0 && r == 0 && !(g.exp & 4)) g.timing[it * 8 + 3] = clock64();  // dA tile staged / reduce issued
       }
       if (r == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }

@@ -8,6 +8,8 @@
 // input layer's backward pass -- run on the handle's side streams next to the input layer / the output layer (parallel branches
 // of the captured graph) and are joined where their results are consumed.
 // No kernels in this file -- it only calls the entry points of include/ntf_b200.h in the order of fnn.py's loop body.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 int ntf_neg_sample_impl(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed, uint64_t step, int row0, int B, const int32_t* m_indptr,
@@ -109,6 +111,24 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     if (!tc) STEP(ntf_special_bits(ctx, stream, 0, B, a->m_indptr, a->m_indices, neg, ns, a->E, a->e_lo, a->special, a->pitch_words));
   }
   if (!bwd_here) return NTF_OK;
+  // ---- optimiser, part 1: the output layer's segment of the arena (its gradients are final once ntf_out_train has run) is
+  // stepped on a side stream NEXT TO the backward pass through the hidden layers (a chain of small launches that leaves most
+  // of the machine idle); the rest of the arena follows on the main stream.  Only when this call ran the output layer too.
+  size_t opt_split = a->n_params;  // floats [opt_split, n_params) belong to the last layer (arena order: layer by layer)
+  if (a->run_adam && phase == 3 && getenv("NTF_ADAM_SPLIT") == nullptr) {
+    const float* lo = a->gW[Lo] < a->gb[Lo] ? a->gW[Lo] : a->gb[Lo];
+    const size_t off = (size_t)(lo - a->grads);
+    bool last = lo >= a->grads && off < a->n_params && (off % 32) == 0;
+    for (int i = 0; i < Lo && last; ++i) last = a->gW[i] < lo && a->gb[i] < lo;
+    if (last) opt_split = off;
+  }
+  if (opt_split < a->n_params) {
+    NTF_CUDA(cudaEventRecord(ctx->ev_fork_opt, st));
+    NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork_opt, 0));
+    STEP(ntf_adam_step_impl(ctx, ctx->side[0], a->params + opt_split, a->grads + opt_split, a->adam_m + opt_split, a->adam_v + opt_split,
+                            a->n_params - opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn));
+    NTF_CUDA(cudaEventRecord(ctx->ev_join_opt, ctx->side[0]));
+  }
   // ---- backward through the hidden layers ----
   for (int i = Lo - 1; i > 0; --i) {
     STEP(ntf_act_bwd(ctx, stream, a->dact[i], a->act[i], B, h[i], 1, a->dz[i], a->gb[i], ws_main, ws_main_bytes));
@@ -118,7 +138,8 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
   NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[1], 0));
   STEP(ntf_csr_bag_bwd_reduce_impl(ctx, st, B, a->s_indptr, a->s_indices, a->s_ent_row, a->row_base, a->dz[0], a->S, h[0], a->gW[0], ws_bag, ws_bag_bytes, nullptr));
   // ---- optimiser: fnn.py:139 (skipped when the caller all-reduces the gradients first: data-parallel ranks) ----
-  if (a->run_adam) STEP(ntf_adam_step_impl(ctx, st, a->params, a->grads, a->adam_m, a->adam_v, a->n_params, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn));
+  if (a->run_adam) STEP(ntf_adam_step_impl(ctx, st, a->params, a->grads, a->adam_m, a->adam_v, opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn));
+  if (opt_split < a->n_params) NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_join_opt, 0));
 #undef STEP
   return NTF_OK;
 }

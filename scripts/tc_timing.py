@@ -8,9 +8,9 @@ from test_gpu_tc import run_tc, make_case
 ws = ops.Workspace(torch.device('cuda:0'))
 B, E = 1000, 40000
 A, W, b, Y, negs = make_case(B, E, 1)
-names = ['mma:bwd_start', 'mma:A_full', 'mma:Z_empty', 'mma:fwd_done', 'epi:Z_full', 'epi:ld_done', 'epi:tile_done', 'mma:bwd_done']
+names = ['mma:bwd_start', 'mma:A_full', 'mma:Z_empty', 'dA:drained', 'epi:Z_full', 'epi:ld_done', 'epi:tile_done', 'mma:dA_free']
 nct = (E + 127) // 128 + 256  # (+ the CTAs of a split last wave)
-for mode, exp in (('infer', '0'), ('train', '0'), ('train', '8')):
+for mode, exp in (('infer', '0'), ('train', '0'), ('train', '1'), ('train', '2'), ('train', '8')):
     tim = torch.zeros(128 + 3 * nct + 8, dtype=torch.int64, device='cuda:0')
     os.environ['NTF_TC_TIMING'] = str(tim.data_ptr()); os.environ['NTF_TC_EXP'] = exp
     for rep in range(2):
