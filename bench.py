@@ -41,6 +41,7 @@ def parse():
     p.add_argument('--cpu-baseline-seconds', type=float, default=15.0)
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--infer-k', type=int, default=10)
+    p.add_argument('--no-extras', action='store_true', help='skip the secondary legs (Bnn train on the imdb shape, top-K sweep)')
     return p.parse_args()
 
 
@@ -291,6 +292,12 @@ def run_ours(args):
     sync()
     infer_value = reps * ib * G / (i0.elapsed_time(i1) * 1e-3)
 
+    extras = {}
+    if not args.no_extras:
+        extras['infer_topk_sweep'] = topk_sweep(eng, test_sp, dev, sync, G)
+        del eng, sp, test_sp, scores
+        torch.cuda.empty_cache()
+        extras['bnn_train'] = bnn_leg(args, dev, world, rank, sync, dist)
     if rank != 0:
         if world > 1: dist.destroy_process_group()
         return
@@ -314,12 +321,82 @@ def run_ours(args):
            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': host.h2d_bytes, 'd2h_bytes_per_step': 4,
                    'api': 'Engine.step_host: pinned batch CSR block -> one H2D copy -> ntf_fnn_step (replayed as a CUDA graph) -> loss.item()'},
            'gpu_launches': launches, 'cuda_graphs': bool(graphs), 'host_enqueue_ms_per_step': host_ms, 'roofline': roof, 'infer_topk': {'k': args.infer_k, 'value': infer_value, 'unit': 'teams/s', 'batch': ib}}
+    out.update(extras)
     if not args.no_cpu_baseline:
         v, n, dt, threads = cpu_reference_steps(tv, splits, b, args.nsd, args.cpu_baseline_seconds)
         out['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                                'sample': f'{n} steps of b={b} ({dt:.1f} s) of the same workload, oracle port of fnn.py:118-140 incl. per-row densification'}
     print(json.dumps(out))
     if world > 1: dist.destroy_process_group()
+
+
+def bnn_leg(args, dev, world, rank, sync, dist):
+    """BASELINE configs[2]: Bnn (Flipout, one weight sample per step, KL/B in the loss) on the IMDB-shaped workload, data-parallel teams
+    (weak scaling, b teams per GPU): train teams/s with everything resident, CUDA events, max over ranks."""
+    import torch
+    from opentf_b200 import _lib
+    from opentf_b200.engine import Engine
+    tv, splits = workload('imdb')
+    N, S = tv['skill'].shape; E = tv['member'].shape[1]
+    b, gB = args.batch, args.batch * world
+    eng = Engine(S, [128], E, dev, bayesian=True, precision=args.precision, tpw=10, tnw=1, nsd=args.nsd, ns=5, seed=0, max_batch=b)
+    eng.world, eng.rank = world, rank
+    eng.stage(tv['skill'], tv['member'])
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for i, (fin, fout) in enumerate(((S, 128), (128, E))):  # bnn.py:19-25: mu ~ N(0,.1), rho ~ N(-3,.1)
+        sd[f'layers.{i}.mu_weight'] = torch.empty(fout, fin).normal_(0.0, 0.1, generator=g); sd[f'layers.{i}.rho_weight'] = torch.empty(fout, fin).normal_(-3.0, 0.1, generator=g)
+        sd[f'layers.{i}.mu_bias'] = torch.empty(fout).normal_(0.0, 0.1, generator=g); sd[f'layers.{i}.rho_bias'] = torch.empty(fout).normal_(-3.0, 0.1, generator=g)
+    eng.load_state_dict(sd)
+    rows = np.asarray(splits['folds'][0]['train'])
+    sp = eng.split(rows[np.random.default_rng(0).permutation(len(rows))])
+    nb = sp.n // gB
+    steps = max(1, min(args.steps, 100))
+
+    def one(i):
+        g0 = (i % nb) * gB
+        eng.step(sp, g0 + rank * b, b, True, lr=1e-3, loss_slot=i % nb, loss_scale=1.0 / gB, gbatch=(g0, gB))
+
+    for i in range(max(3, min(args.warmup, 5))): one(i)
+    sync()
+    _lib.lib().ntf_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps): one(5 + i)
+    e1.record()
+    sync()
+    launches = int(_lib.lib().ntf_launch_count(0))
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    loss = float(eng.loss_buf[(5 + steps - 1) % nb].item())
+    prec = 'tf32' if eng.precision == _lib.NTF_TF32 else 'fp32'
+    flops = 12.0 * 128 * E * b  # SURVEY 8d: K3 flops/team (Bnn-Flipout train) = 12*h_L*E
+    return {'metric': 'train teams/s (Bnn Flipout, 1 weight sample/step, unigram_b, fwd+bwd+KL+Adam)', 'value': steps * gB / (ms * 1e-3), 'unit': UNIT,
+            'workload': f'imdb-shaped synthetic teamsvecs (BASELINE configs[2]): N={N} S={S} E={E}, Bnn h=[128], nsd={args.nsd}, ns=5', 'batch_per_gpu': b,
+            'steps': steps, 'ms_per_step': ms / steps, 'gpu_launches_per_step': launches / steps, 'precision': prec, 'last_loss': loss,
+            'output_layer_tflops_if_alone': flops / (ms / steps * 1e-3) / 1e12}
+
+
+def topk_sweep(eng, test_sp, dev, sync, G):
+    """BASELINE configs[4]: top-K expert ranking over all experts for held-out teams, K sweep at the bench batch (device resident)"""
+    import torch
+    out = []
+    ib = min(eng.Bmax, test_sp.n)
+    scores = torch.empty(ib, eng.E, device=dev)
+    for K in (2, 10, 100, 1000):
+        if K > eng.E: continue
+        vals, idx = torch.empty(ib, K, device=dev), torch.empty(ib, K, dtype=torch.int32, device=dev)
+        for _ in range(2): eng.topk(test_sp, 0, ib, K, scores, vals, idx)
+        sync()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        i0.record()
+        for r in range(reps): eng.topk(test_sp, (r * ib) % max(1, test_sp.n - ib + 1), ib, K, scores, vals, idx)
+        i1.record()
+        sync()
+        out.append({'k': K, 'batch': ib, 'value': reps * ib * G / (i0.elapsed_time(i1) * 1e-3), 'unit': 'teams/s'})
+    return out
 
 
 class HostBatches:

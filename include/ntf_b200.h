@@ -210,6 +210,13 @@ int ntf_topk_merge(ntf_ctx* ctx, void* stream, const float* vals_in, const int32
                    float* vals, int32_t* idx);
 /* Bnn test-time uncertainty (fnn.py:206-208): out[n] (+)= -sum_j q log(q+1e-15), q = scale*P[n,j] */
 int ntf_row_entropy(ntf_ctx* ctx, void* stream, const float* P, int B, int E, float scale, int accumulate, float* out);
+/* ranking metrics of the top-K output on the device: the per-team loop of src/evl/metric.py:12-33 (argpartition/argsort, two
+ * dicts per team, pytrec_eval) called from Ntf.evaluate (src/mdl/ntf.py:59-62).  idx/vals [n,K]: every team's candidates in ANY order
+ * (idx < 0 = padding); m_indptr (n+1 absolute offsets) / m_indices: the teams' true members, columns ascending; ks[nk]: cut-offs,
+ * ascending, HOST array (<= 16); out [n][5][nk] fp64 (device), families in the order P, recall, ndcg_cut, map_cut, success.
+ * Ranking follows trec_eval: score descending, ties by the document id STRING ('d'+str(expert), metric.py:31) descending. K <= 1024. */
+int ntf_eval_ranked(ntf_ctx* ctx, void* stream, int n, int K, const int32_t* idx, const float* vals, const int32_t* m_indptr,
+                    const int32_t* m_indices, const int* ks, int nk, double* out);
 int ntf_axpy(ntf_ctx* ctx, void* stream, size_t n, float a, const float* x, float* y); /* y += a*x (MC mean, fnn.py:209) */
 
 /* ---- Bnn / Flipout parameter pass (bayesian-torch 0.5.0 LinearFlipout + get_kl_loss; bnn.py:19-25, fnn.py:136) ---------

@@ -79,6 +79,7 @@ SIGNATURES = {
     'ntf_topk_select': (i32, [vp, vp, vp, i32, i32, i32, f32, vp, vp]),
     'ntf_topk_merge': (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),
     'ntf_row_entropy': (i32, [vp, vp, vp, i32, i32, f32, i32, vp]),
+    'ntf_eval_ranked': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(i32), i32, vp]),
     'ntf_axpy': (i32, [vp, vp, sz, f32, vp, vp]),
     'ntf_flipout_prepare_workspace_bytes': (sz, [vp]),
     'ntf_flipout_prepare': (i32, [vp, vp, vp, vp, vp, sz, f32, vp, vp, vp, sz]),

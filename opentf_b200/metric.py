@@ -68,6 +68,54 @@ def calculate_metrics(Y, Y_, topK=None, per_instance=False, metrics=('P_2,5,10',
     return (df if per_instance else None), df_mean
 
 
+EVAL_MAXK = 1024  # candidates per team ntf_eval_ranked ranks in shared memory
+
+
+def calculate_metrics_device(Y, Y_, topK=None, per_instance=False, metrics=('P_2,5,10', 'recall_2,5,10', 'ndcg_cut_2,5,10'), device='cuda:0',
+                             chunk=8192):
+    """`calculate_metrics` with the per-team loop (metric.py:12-33) on the GPU: the candidates of each team (the stored top-K of a
+    sparse .pred, or the first-stage top-K of a dense one, selected by ntf_topk_select) are ranked and scored by ntf_eval_ranked against
+    the team's member row; only [n,5,nk] numbers come back.  Same frames as the host version.  No CPU fallback: raises without the library."""
+    import pandas as pd
+    import torch
+    from . import ops
+    assert Y.shape == Y_.shape, f'Shape mismatch between truth Y {Y.shape} vs preds Y_ {Y_.shape}!'
+    fams = parse_metrics(metrics)
+    ks = sorted({k for _, kk in fams for k in kk})
+    N, E = Y.shape
+    first_stage = min(topK, E) if topK else E
+    if ks[-1] > EVAL_MAXK: raise ValueError(f'cut-off {ks[-1]} beyond the {EVAL_MAXK} candidates ntf_eval_ranked ranks per team')
+    Yc = sp.csr_matrix(Y); Yc.sort_indices()
+    dev = torch.device(device)
+    out = np.zeros((N, 5, len(ks)))
+    Yr = sp.csr_matrix(Y_) if sp.issparse(Y_) else None
+    for r0 in range(0, N, chunk):
+        r1 = min(N, r0 + chunk); n = r1 - r0
+        m_ptr = torch.as_tensor((Yc.indptr[r0:r1 + 1] - Yc.indptr[r0]).astype(np.int32), device=dev)
+        m_idx = torch.as_tensor(Yc.indices[Yc.indptr[r0]:Yc.indptr[r1]].astype(np.int32), device=dev)
+        if m_idx.numel() == 0: m_idx = torch.zeros(1, dtype=torch.int32, device=dev)
+        lens = np.diff(Yr.indptr[r0:r1 + 1]) if Yr is not None else None
+        if Yr is not None and lens.max(initial=0) <= min(first_stage, EVAL_MAXK):  # the stored candidates as they are, padded with -1
+            K = max(int(lens.max(initial=0)), 1)
+            ci = np.full((n, K), -1, np.int32); cv = np.zeros((n, K), np.float32)
+            pos = np.arange(Yr.indptr[r0], Yr.indptr[r1]) - np.repeat(Yr.indptr[r0:r1], lens)
+            rows = np.repeat(np.arange(n), lens)
+            ci[rows, pos] = Yr.indices[Yr.indptr[r0]:Yr.indptr[r1]]; cv[rows, pos] = Yr.data[Yr.indptr[r0]:Yr.indptr[r1]]
+            idx, vals = torch.as_tensor(ci, device=dev), torch.as_tensor(cv, device=dev)
+        else:  # first-stage retrieval on the device (metric.py:12,19-28)
+            dense = np.asarray(Yr[r0:r1].todense(), dtype=np.float32) if Yr is not None else np.ascontiguousarray(Y_[r0:r1], dtype=np.float32)
+            K = min(first_stage, EVAL_MAXK)
+            P = torch.as_tensor(dense, device=dev)
+            vals = torch.empty(n, K, dtype=torch.float32, device=dev); idx = torch.empty(n, K, dtype=torch.int32, device=dev)
+            ops.topk_select(P, n, E, K, 1.0, vals, idx)
+        o = torch.empty(n, 5, len(ks), dtype=torch.float64, device=dev)
+        ops.eval_ranked(idx, vals, m_ptr, m_idx, ks, o)
+        out[r0:r1] = o.cpu().numpy()
+    df = pd.DataFrame({f'{f}_{k}': out[:, FAMILIES.index(f), ks.index(k)] for f, kk in fams for k in kk})
+    df_mean = df.mean().to_frame('mean').rename_axis('metrics')
+    return (df if per_instance else None), df_mean
+
+
 def calculate_auc_roc(Y, Y_, curve=False):
     """metric.py:37-42 (micro-averaged; densifies like the reference)."""
     from sklearn import metrics as skm

@@ -57,7 +57,11 @@ class Ntf:
                     assert Y.shape == Y_.shape, f'Shape mismatch between truth Y {Y.shape} vs preds Y_ {Y_.shape}!'
                     df, df_mean = pd.DataFrame(), pd.DataFrame()
                     if trec:
-                        df, df_mean = metric.calculate_metrics(Y, Y_, g(evalcfg, 'topK'), g(evalcfg, 'per_instance'), trec)
+                        if str(self.device).startswith('cuda'):  # the per-team ranking loop runs on the GPU (ntf_eval_ranked); no fallback
+                            df, df_mean = metric.calculate_metrics_device(Y, Y_, g(evalcfg, 'topK'), g(evalcfg, 'per_instance'), trec,
+                                                                          device=util.first_device(self.device))
+                        else:
+                            df, df_mean = metric.calculate_metrics(Y, Y_, g(evalcfg, 'topK'), g(evalcfg, 'per_instance'), trec)
                         if df is None: df = pd.DataFrame()
                     if (m := [m for m in other if 'aucroc' in m]):
                         aucroc, fpr_tpr = metric.calculate_auc_roc(Y, Y_, curve=(m[0] == 'aucroc+'))

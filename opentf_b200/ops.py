@@ -145,6 +145,17 @@ def row_entropy(P, B, E, scale, accumulate, out):
     check(lib().ntf_row_entropy(_lib.ctx(d), _stream(d), _p(P, F32), B, E, scale, accumulate, _p(out, F32)), 'ntf_row_entropy')
 
 
+def eval_ranked(idx, vals, m_indptr, m_indices, ks, out):
+    """ranking metrics per team on the device (ntf_eval_ranked): idx/vals [n,K] candidates, member CSR rows, ks ascending cut-offs,
+    out [n,5,len(ks)] fp64 in the order P, recall, ndcg_cut, map_cut, success"""
+    d = _dev(vals)
+    n, K = vals.shape
+    assert out.dtype == torch.float64 and tuple(out.shape) == (n, 5, len(ks))
+    karr = (C.c_int * len(ks))(*[int(k) for k in ks])
+    check(lib().ntf_eval_ranked(_lib.ctx(d), _stream(d), n, K, _p(idx, I32), _p(vals, F32), _p(m_indptr, I32), _p(m_indices, I32), karr, len(ks),
+                                _p(out, torch.float64)), 'ntf_eval_ranked')
+
+
 def axpy(n, a, x, y):
     d = _dev(x)
     check(lib().ntf_axpy(_lib.ctx(d), _stream(d), n, a, _p(x, F32), _p(y, F32)), 'ntf_axpy')

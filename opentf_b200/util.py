@@ -80,3 +80,13 @@ def torch_sparse_2_scipy_sparse(Y_, type='coo'):
     i, v = Y_.indices().cpu().numpy(), Y_.values().cpu().numpy()
     cls = scipy.sparse.coo_matrix if type == 'coo' else scipy.sparse.csr_matrix
     return cls((v, (i[0], i[1])), shape=tuple(Y_.size()))
+
+
+def first_device(device):
+    """'cuda' / 'cuda:N' / the reference's 'cuda:0,1,...' list (nmt.py:74) -> this process's 'cuda:N'."""
+    import os
+    d = str(device)
+    if ',' in d:
+        ids = d.split(':')[1].split(',')
+        return f'cuda:{ids[int(os.environ.get("LOCAL_RANK", 0)) % len(ids)]}'
+    return d if ':' in d else 'cuda:0'
