@@ -41,6 +41,7 @@ def parse():
     p.add_argument('--cpu-baseline-seconds', type=float, default=15.0)
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--infer-k', type=int, default=10)
+    p.add_argument('--leg', default='all', choices=['all', 'bnn'], help="'bnn': only the Bnn train leg (its dict is the output line; for profiling)")
     p.add_argument('--no-extras', action='store_true', help='skip the secondary legs (Bnn train on the imdb shape, top-K sweep)')
     return p.parse_args()
 
@@ -185,6 +186,15 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f'cuda:{local}')
     if world > 1: dist.init_process_group('nccl', device_id=dev)
+    if args.leg == 'bnn':
+        def sync0():
+            torch.cuda.synchronize()
+            if world > 1: dist.barrier()
+            torch.cuda.synchronize()
+        r = bnn_leg(args, dev, world, rank, sync0, dist)
+        if rank == 0: print(json.dumps(r))
+        if world > 1: dist.destroy_process_group()
+        return
     tv, splits = workload(args.workload)
     N, S = tv['skill'].shape; E = tv['member'].shape[1]
     b, G = args.batch, world

@@ -13,6 +13,10 @@ int ntf_out_tc_supported(int B, int h, int E, int flipout);
 int ntf_infer_scores_tc(ntf_ctx* ctx, cudaStream_t st, const float* A, const float* W, const float* b, int B, int h, int E, float* P,
                         void* workspace, size_t workspace_bytes);
 size_t ntf_infer_scores_tc_workspace_bytes(int B, int h);
+size_t ntf_infer_scores_tc_flip_workspace_bytes(int B, int h, int E);
+int ntf_infer_scores_tc_flip(ntf_ctx* ctx, cudaStream_t st, const float* A, const float* W, const float* b, int B, int h, int E, const float* A_s,
+                             const float* W_delta, const float* b_delta, const uint32_t* sign_out, int pitch_words, float* P, void* workspace,
+                             size_t workspace_bytes);
 
 extern "C" int ntf_tc_supported(int B, int h, int E, int flipout) { return ntf_out_tc_supported(B, h, E, flipout); }
 
@@ -46,8 +50,11 @@ extern "C" int ntf_out_train(ntf_ctx* ctx, void* stream, int precision, const nt
 }
 
 extern "C" size_t ntf_infer_scores_workspace_bytes(int B, int E, int flipout) {
-  // Flipout: the perturbation term T[B,E]; otherwise the fp16 copy of the activations for the tensor-core path (h <= 128 there)
-  return flipout ? align_up((size_t)B * E * sizeof(float), 256) : ntf_infer_scores_tc_workspace_bytes(B, 128);
+  // Flipout: the perturbation term T[B,E] (fp32 kernels) or the fp16 tiles of the tensor-core path, whichever is larger; otherwise the
+  // fp16 copy of the activations for the tensor-core path (h <= 128 there)
+  if (!flipout) return ntf_infer_scores_tc_workspace_bytes(B, 128);
+  const size_t a = align_up((size_t)B * E * sizeof(float), 256), t = ntf_infer_scores_tc_flip_workspace_bytes(B, 128, E);
+  return a > t ? a : t;
 }
 
 extern "C" int ntf_infer_scores(ntf_ctx* ctx, void* stream, int precision, const float* A, const float* W, const float* b, int B,
@@ -63,6 +70,8 @@ extern "C" int ntf_infer_scores(ntf_ctx* ctx, void* stream, int precision, const
   }
   if (precision == NTF_TF32 && !flip && !accumulate && ntf_out_tc_supported(B, h, E, 0))
     return ntf_infer_scores_tc(ctx, as_stream(stream), A, W, b, B, h, E, P, workspace, workspace_bytes);
+  if (precision == NTF_TF32 && flip && !accumulate && ntf_out_tc_supported(B, h, E, 1))
+    return ntf_infer_scores_tc_flip(ctx, as_stream(stream), A, W, b, B, h, E, A_s, W_delta, b_delta, sign_out, pitch_words, P, workspace, workspace_bytes);
   NTF_REQUIRE(precision == NTF_FP32 || precision == NTF_TF32, NTF_ERR_BAD_ARG, "infer_scores: precision=%d", precision);
   return ntf_infer_scores_fp32(as_stream(stream), A, W, b, B, h, E, A_s, W_delta, b_delta, sign_out, pitch_words, accumulate, P,
                                (float*)workspace);

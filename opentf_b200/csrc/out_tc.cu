@@ -52,6 +52,8 @@ constexpr uint32_t W32_BYTES = TE * HK * 4;      // 64 KB : 4 chunks (32 hidden 
 constexpr uint32_t OFF_W16 = 0;
 constexpr int A_STAGES = 3;                                 // tile t+2's activations load while tile t's backward products still read theirs
 constexpr uint32_t OFF_A16 = OFF_W16 + W16_BYTES;
+constexpr uint32_t OFF_Q = OFF_A16 + 2 * A16_BYTES;          // Flipout: the third activation slot holds the perturbation-term tile instead
+constexpr uint32_t Q_BYTES = TE * TB * 2;
 constexpr uint32_t OFF_DZ = OFF_A16 + A_STAGES * A16_BYTES; // 2 stages (first use: landing zone of the fp32 W tile)
 constexpr uint32_t OFF_PLANE = OFF_DZ + 2 * DZ_BYTES;       // 2 stages x (special | member) bit planes of a tile, [128 experts][4 words] each
 constexpr uint32_t PLANE_BYTES = TE * 4 * 4;                // 2 KB each
@@ -68,9 +70,10 @@ constexpr uint32_t TM_DA = 384;   // 128
 constexpr uint32_t TM_COLS = 512;
 
 enum { BAR_W32 = 0, BAR_W16 = 1, BAR_A_FULL = 2, BAR_A_EMPTY = 5, BAR_Z_FULL = 8, BAR_Z_EMPTY = 10, BAR_DZ_FULL = 12, BAR_DZ_EMPTY = 14,
-       BAR_DA_FULL = 16, BAR_DA_EMPTY = 17, BAR_DW_FULL = 18, BAR_SP_FULL = 19, BAR_SP_EMPTY = 21, NUM_BARS = 23 };
+       BAR_DA_FULL = 16, BAR_DA_EMPTY = 17, BAR_DW_FULL = 18, BAR_SP_FULL = 19, BAR_SP_EMPTY = 21, BAR_Q_FULL = 23, BAR_Q_EMPTY = 24, NUM_BARS = 25 };
 // A_*  : fp16 activation tile ring, 3 stages (operand of the forward and of the dW product; released after the tile's last product)
 // SP_* : special / member bit planes of a tile (2-stage ring, filled by 1-D bulk copies from the tile-transposed planes in HBM)
+// Q_*  : Flipout only: the tile of the perturbation term (one stage, living in the third activation slot; the activation ring has 2 stages then)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -161,6 +164,12 @@ struct TcArgs {
   // work split: CTAs [0, n_full) own a whole expert tile (all batch tiles); the remaining expert tiles -- the partial last wave --
   // are cut `split` ways along the batch so that the last wave is short: those CTAs ADD their dW / db partials (pre-zeroed rows)
   int n_full, split;
+  // Flipout (Bnn): z += s_out * (A_s W_delta^T + b_delta).  The perturbation term is a product of its own (MODE 2) whose
+  // signed result crosses HBM once as fp16 tiles; its backward products (MODE 3) read s_out*dz tiles written by the MODE 0 epilogue.
+  const uint32_t* sign_t;     // s_out as a tile-transposed plane (bit = 1: -1), word layout of special_t; read-only
+  __half* Q;                  // [tiles of 128 teams][Epad/128][16 units][128 experts][8 halfs]: s_out*(Z2 + b_delta) (MODE 2 writes, MODE 0/1 add)
+  __half* DZS;                // [tiles of 128 teams * Epad][128 teams] row-major: s_out*dz/loss_scale (MODE 0 writes, MODE 3 loads by TMA)
+  float* db_delta;            // [E]: colsum(s_out*dz)
 };
 
 constexpr int EPI_WARPS = 16;
@@ -189,9 +198,14 @@ constexpr uint32_t IDESC_DW = instr_desc(0, 0, 1, TE, HK);    // dW  += dz^T(K-m
 constexpr uint32_t IDESC_DA = instr_desc(0, 1, 1, TB, HK);    // dA   = dz(MN-major: M = teams) . W16(MN-major: N = hidden), K = experts
 
 // MODE 0: training / validation step.  MODE 1: inference scores P = sigmoid(lrelu(z)).
-template <int MODE>
+// Flipout (FLIP): MODE 2: forward product of the perturbation path only, Q = s_out*(A_s W_delta^T + b_delta) -> HBM (fp16 tiles);
+//                 MODE 0/1 with FLIP add the Q tile to the logits; MODE 0 also writes s_out*dz tiles (DZS) and db_delta;
+//                 MODE 3: backward products of the perturbation path only: dW_delta += DZS^T A_s, dA_s = DZS W_delta (dz tiles come by TMA).
+template <int MODE, bool FLIP>
 __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ CUtensorMap map_w32, const __grid_constant__ CUtensorMap map_a16,
-                                                       const __grid_constant__ CUtensorMap map_da, TcArgs g) {
+                                                       const __grid_constant__ CUtensorMap map_da, const __grid_constant__ CUtensorMap map_dzs, TcArgs g) {
+  constexpr int AST = (FLIP && MODE < 2) ? 2 : A_STAGES;  // activation ring stages in use (the Q tile takes the third slot)
+  constexpr bool QIN = FLIP && MODE < 2;                  // this instance adds the perturbation-term tile to its logits
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   if ((sbase & 1023u) != 0u) __trap();  // the 128-byte swizzle atoms need a 1024-byte aligned base
@@ -219,7 +233,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
   }
   const int e0 = etile * TE;
   const int ntiles = t_end - t_begin;  // batch tiles of this CTA: local index it, global tile t_begin + it
-  const bool train = MODE == 0 && g.dW != nullptr;
+  const bool train = (MODE == 0 && g.dW != nullptr) || MODE == 3;  // backward products run
 
   if (threadIdx.x == 0) {
     mbar_init(bar(BAR_W32), 1);
@@ -227,6 +241,8 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
     mbar_init(bar(BAR_DW_FULL), 1);
     mbar_init(bar(BAR_DA_FULL), 1);
     mbar_init(bar(BAR_DA_EMPTY), 128);
+    mbar_init(bar(BAR_Q_FULL), 1);
+    mbar_init(bar(BAR_Q_EMPTY), EPI_THREADS);
     for (int s = 0; s < A_STAGES; ++s) {
       mbar_init(bar(BAR_A_FULL + s), 1);
       mbar_init(bar(BAR_A_EMPTY + s), 1);
@@ -234,7 +250,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(BAR_Z_FULL + s), 1);
       mbar_init(bar(BAR_Z_EMPTY + s), EPI_THREADS);
-      mbar_init(bar(BAR_DZ_FULL + s), EPI_THREADS);
+      mbar_init(bar(BAR_DZ_FULL + s), MODE == 3 ? 1 : EPI_THREADS);  // MODE 3: the dz tiles arrive by TMA
       mbar_init(bar(BAR_DZ_EMPTY + s), 1);
       mbar_init(bar(BAR_SP_FULL + s), 1);
       mbar_init(bar(BAR_SP_EMPTY + s), EPI_THREADS);
@@ -257,33 +273,49 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       mbar_expect_tx(bar(BAR_W32), W32_BYTES);
       for (int c = 0; c < 4; ++c) tma_load_2d(sbase + OFF_DZ + c * CHUNK, &map_w32, c * 32, e0, bar(BAR_W32));
       for (int it = 0; it < ntiles; ++it) {
-        const int s = it % A_STAGES;
-        const uint32_t ph = (it / A_STAGES) & 1;
+        const int s = it % AST;
+        const uint32_t ph = (it / AST) & 1;
         mbar_wait(bar(BAR_A_EMPTY + s), ph ^ 1);
         mbar_expect_tx(bar(BAR_A_FULL + s), A16_BYTES);
         for (int c = 0; c < 2; ++c)
           tma_load_2d(sbase + OFF_A16 + s * A16_BYTES + c * CHUNK, &map_a16, c * 64, (t_begin + it) * TB, bar(BAR_A_FULL + s));
+        if (MODE == 3) {  // the s_out*dz tile of (batch tile, expert tile): rows = experts, 2 chunks of 64 teams, same swizzled image the epilogue writes
+          const int s2 = it & 1;
+          if (it == 0) mbar_wait(bar(BAR_W16), 0);  // the dz ring was the landing zone of the fp32 W tile
+          mbar_wait(bar(BAR_DZ_EMPTY + s2), ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(bar(BAR_DZ_FULL + s2), DZ_BYTES);
+          for (int c = 0; c < 2; ++c)
+            tma_load_2d(sbase + OFF_DZ + s2 * DZ_BYTES + c * CHUNK, &map_dzs, c * 64, (t_begin + it) * g.Epad + e0, bar(BAR_DZ_FULL + s2));
+        }
       }
     }
   } else if (warp == WARP_SP) {
     // ====== special / member planes of the tile: two 2 KB bulk copies per tile from the tile-transposed planes (ntf_special_tiles) ======
-    if (MODE == 0 && lane == 0 && g.special_t && !(g.exp & 2)) {
+    const bool planes = MODE == 0 && g.special_t && !(g.exp & 2);
+    if (lane == 0 && (planes || QIN)) {
       for (int it = 0; it < ntiles; ++it) {
-        const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(bar(BAR_SP_EMPTY + s), ph ^ 1);
-        mbar_expect_tx(bar(BAR_SP_FULL + s), 2 * PLANE_BYTES);
-        const size_t off = ((size_t)(t_begin + it) * g.Epad + e0) * 4;
-        bulk_load(sbase + OFF_PLANE + s * 2 * PLANE_BYTES, g.special_t + off, PLANE_BYTES, bar(BAR_SP_FULL + s));
-        bulk_load(sbase + OFF_PLANE + s * 2 * PLANE_BYTES + PLANE_BYTES, g.member_t + off, PLANE_BYTES, bar(BAR_SP_FULL + s));
+        if (planes) {
+          const int s = it & 1;
+          const uint32_t ph = (it >> 1) & 1;
+          mbar_wait(bar(BAR_SP_EMPTY + s), ph ^ 1);
+          mbar_expect_tx(bar(BAR_SP_FULL + s), 2 * PLANE_BYTES);
+          const size_t off = ((size_t)(t_begin + it) * g.Epad + e0) * 4;
+          bulk_load(sbase + OFF_PLANE + s * 2 * PLANE_BYTES, g.special_t + off, PLANE_BYTES, bar(BAR_SP_FULL + s));
+          bulk_load(sbase + OFF_PLANE + s * 2 * PLANE_BYTES + PLANE_BYTES, g.member_t + off, PLANE_BYTES, bar(BAR_SP_FULL + s));
+        }
+        if (QIN) {  // the 32 KB perturbation-term tile (contiguous in HBM), one tile ahead of the epilogue
+          mbar_wait(bar(BAR_Q_EMPTY), (it & 1) ^ 1);
+          mbar_expect_tx(bar(BAR_Q_FULL), Q_BYTES);
+          bulk_load(sbase + OFF_Q, g.Q + ((size_t)(t_begin + it) * g.Epad + e0) * TB, Q_BYTES, bar(BAR_Q_FULL));
+        }
       }
     }
   } else if (warp == WARP_MMA) {
     // =========================================== MMA issuer ===========================================
     if (lane == 0) {
       auto issue_fwd = [&](int it) {
-        const int sa = it % A_STAGES, s = it & 1;
-        const uint32_t pha = (it / A_STAGES) & 1, ph = (it >> 1) & 1;
+        const int sa = it % AST, s = it & 1;
+        const uint32_t pha = (it / AST) & 1, ph = (it >> 1) & 1;
         mbar_wait(bar(BAR_A_FULL + sa), pha);
         if (g.timing && blockIdx.x == 0) g.timing[it * 8 + 1] = clock64();
         mbar_wait(bar(BAR_Z_EMPTY + s), ph ^ 1);
@@ -304,12 +336,13 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       };
       mbar_wait(bar(BAR_W16), 0);
       if (g.timing && blockIdx.x == 0) g.timing[15 * 8 + 2] = clock64();  // W image ready
-      if (ntiles > 0) issue_fwd(0);
+      if (MODE != 3 && ntiles > 0) issue_fwd(0);
       for (int it = 0; it < ntiles; ++it) {
-        if (it + 1 < ntiles) issue_fwd(it + 1);  // keep the tensor pipe busy while the epilogue works on tile it
+        if (MODE != 3 && it + 1 < ntiles) issue_fwd(it + 1);  // keep the tensor pipe busy while the epilogue works on tile it
         if (!train) continue;
-        const int sa = it % A_STAGES, s = it & 1;
+        const int sa = it % AST, s = it & 1;
         const uint32_t ph = (it >> 1) & 1;
+        if (MODE == 3) mbar_wait(bar(BAR_A_FULL + sa), (it / AST) & 1);  // (no forward product waited for the activation tile)
         mbar_wait(bar(BAR_DZ_FULL + s), ph);
         tc_fence_after();
         if (g.timing && blockIdx.x == 0) g.timing[it * 8 + 0] = clock64();  // backward products: issue starts
@@ -370,15 +403,30 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
     }
     float acc_lin = 0.f, acc_lg = 0.f, loss_sp = 0.f, db_acc = 0.f;  // dense loss = tnw*ln2*(acc_lg - acc_lin): sums of lg2(1+e) and of t = -c*x
     float2 acc_lin2 = make_float2(0.f, 0.f), db_acc2 = make_float2(0.f, 0.f);  // the dense pass's packed halves of acc_lin / db_acc
+    float2 dbd2 = make_float2(0.f, 0.f);                                        // Flipout: colsum(s_out*dz) of this thread's teams
+    // Flipout: bit n of Sg = s_out(team n0+n, my expert) is -1.  One word per tile from the tile-transposed plane, fetched one tile ahead.
+    auto sign_word = [&](int it) -> uint32_t {
+      return (FLIP && MODE != 3 && g.sign_t && it < ntiles) ? __ldg(g.sign_t + ((size_t)(t_begin + it) * g.Epad + e) * 4 + (threadIdx.x >> 7)) : 0u;
+    };
+    uint32_t Sg_next = sign_word(0);
     // dz is kept as w*(sigmoid-y)*slope, i.e. true dz / loss_scale; experts past E (last tile) get zero gradient and their loss is dropped below
     const float c_pos = e_ok ? g.tnw : 0.f, c_neg = e_ok ? g.tnw * NTF_LRELU_SLOPE : 0.f;
     const bool has_sp = MODE == 0 && g.special_t && !(g.exp & 2);
     constexpr float LOG2E = 1.4426950408889634f;
     const float kb1 = -LOG2E * bj, kb2 = -LOG2E * NTF_LRELU_SLOPE * bj;
-    for (int it = 0; it < ntiles; ++it) {
+    for (int it = 0; it < (MODE == 3 ? 0 : ntiles); ++it) {  // (MODE 3 has no logits: these warps convert the W tile and drain dW)
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       const int n0 = (t_begin + it) * TB + cb * 32;  // first team of this thread's block
+      const uint32_t Sg = Sg_next;
+      Sg_next = sign_word(it + 1);
+      uint4 qv[4];
+      if (QIN) {  // this thread's 32 values of the perturbation-term tile: unit (4*cb+u) of expert jl (unit-major tile: conflict-free 16-byte reads)
+        mbar_wait(bar(BAR_Q_FULL), it & 1);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qv[u] = *reinterpret_cast<const uint4*>(sgen + OFF_Q + (((cb * 4 + u) * TE + jl) << 4));
+        mbar_arrive(bar(BAR_Q_EMPTY));
+      }
       // bit n of S / Y: (team n0+n, my expert) carries weight tpw / target 1 -- two words from the tile's planes, then the stage is free
       uint32_t S = 0, Y = 0;
       if (has_sp) {
@@ -403,6 +451,35 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       mbar_arrive(bar(BAR_Z_EMPTY + s));
       if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[it * 8 + 5] = clock64();
       const int nrem = g.B - n0;  // teams of this block that exist
+      if (QIN) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t w[4] = {qv[u].x, qv[u].y, qv[u].z, qv[u].w};
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[p]));
+            z[u * 8 + 2 * p] += f.x; z[u * 8 + 2 * p + 1] += f.y;
+          }
+        }
+      }
+      if (MODE == 2) {
+        // Q = s_out * (Z2 + b_delta) as fp16: unit (4*cb+u) = teams [8u, 8u+8) of this thread's block; lanes write consecutive 16-byte units
+        uint4* qt = reinterpret_cast<uint4*>(g.Q + ((size_t)(t_begin + it) * g.Epad + e0) * TB);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint32_t w[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int k = u * 8 + 2 * p;
+            const float a = __uint_as_float(__float_as_uint(z[k] + bj) ^ ((Sg << (31 - k)) & 0x80000000u));
+            const float b = __uint_as_float(__float_as_uint(z[k + 1] + bj) ^ ((Sg << (30 - k)) & 0x80000000u));
+            const __half2 h = __floats2half2_rn(a, b);
+            w[p] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          qt[(cb * 4 + u) * TE + jl] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        continue;
+      }
       if (MODE == 1) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -533,6 +610,24 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         d_lin = warp_sum(d_lin); d_lg = warp_sum(d_lg); d_sp = warp_sum(d_sp); d_db = warp_sum(d_db);
         if (lane == L) { acc_lin += d_lin; acc_lg += d_lg; loss_sp += d_sp; db_acc += d_db; }
       }
+      if (FLIP && MODE == 0 && train) {
+        // Flipout: s_out*dz of this thread's (expert, 32 teams) -> the DZS tile in HBM (operand of the perturbation path's backward
+        // products, MODE 3) and db_delta.  Read back from the staged fp16 row so that the fix-up's corrections are included.
+        __syncwarp();
+        __half* drow = g.DZS + ((size_t)(t_begin + it) * g.Epad + e) * TB + cb * 32;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint32_t w[4];
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(dzrow + ((kx ^ (uint32_t)u) << 4)) : "memory");
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int k = u * 8 + 2 * p;
+            w[p] ^= ((Sg >> k) & 1u) << 15 | ((Sg >> (k + 1)) & 1u) << 31;
+            dbd2 = __fadd2_rn(dbd2, __half22float2(*reinterpret_cast<const __half2*>(&w[p])));
+          }
+          *reinterpret_cast<uint4*>(drow + u * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
       if (train) {
         fence_proxy_async();
         mbar_arrive(bar(BAR_DZ_FULL + s));
@@ -541,27 +636,36 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
     }
     acc_lin += acc_lin2.x + acc_lin2.y;
     db_acc += db_acc2.x + db_acc2.y;
-    if (MODE == 0) {
+    if (MODE == 0 || MODE == 3) {
       // loss partial of this CTA and db: fixed-order combines (shuffle tree, then warps / team blocks in order)
       float* red = reinterpret_cast<float*>(sgen + OFF_BAR + NUM_BARS * 8 + 16);   // [16]
       float* dbs = reinterpret_cast<float*>(sgen + OFF_DZ);                          // [3][128], the dz stages are idle by now ...
+      float* dbs2 = dbs + 3 * TE;                                                    // [3][128] Flipout: the db_delta partials
       if (train) mbar_wait(bar(BAR_DW_FULL), 0);                                     // ... once every MMA that read them has completed
       if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[15 * 8 + 3] = clock64();  // all products complete
-      const float tot = warp_sum(e_ok ? g.tnw * 0.6931471805599453f * (acc_lg - acc_lin) + loss_sp : 0.f);
-      if (lane == 0) red[warp] = tot;
-      if (train && cb > 0) dbs[(cb - 1) * TE + jl] = db_acc;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (threadIdx.x == 0) {
-        float l = 0.f;
+      if (MODE == 0) {
+        const float tot = warp_sum(e_ok ? g.tnw * 0.6931471805599453f * (acc_lg - acc_lin) + loss_sp : 0.f);
+        const float dbd = dbd2.x + dbd2.y;
+        if (lane == 0) red[warp] = tot;
+        if (train && cb > 0) dbs[(cb - 1) * TE + jl] = db_acc;
+        if (FLIP && train && cb > 0) dbs2[(cb - 1) * TE + jl] = dbd;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (threadIdx.x == 0) {
+          float l = 0.f;
 #pragma unroll
-        for (int q = 0; q < EPI_WARPS; ++q) l += red[q];
-        g.loss_part[blockIdx.x] = l;
-      }
-      if (train) {
-        if (cb == 0 && e_ok) {
+          for (int q = 0; q < EPI_WARPS; ++q) l += red[q];
+          g.loss_part[blockIdx.x] = l;
+        }
+        if (train && cb == 0 && e_ok) {
           const float dbv = (((db_acc + dbs[jl]) + dbs[TE + jl]) + dbs[2 * TE + jl]) * g.scale;
           if (shared_tile) atomicAdd(g.db + e, dbv); else g.db[e] = dbv;
+          if (FLIP) {
+            const float dv = (((dbd + dbs2[jl]) + dbs2[TE + jl]) + dbs2[2 * TE + jl]) * g.scale;
+            if (shared_tile) atomicAdd(g.db_delta + e, dv); else g.db_delta[e] = dv;
+          }
         }
+      }
+      if (train) {
         tc_fence_after();
         float v[32];
         tmem_ld32(tmem + lane_base + TM_DW + cb * 32, v);  // this thread's 32 of the 128 dW columns of its expert
@@ -638,6 +742,26 @@ __global__ void to_half_kernel(const float* __restrict__ x, size_t n, __half* __
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = __float2half_rn(x[i]);
 }
 
+// Flipout: the row-major s_out bit plane [B, pitch] (bit j of word (n, j/32) = 1: s_out[n,j] = -1) -> the tile-transposed plane the
+// epilogue threads read (word ((n/128)*Epad + j)*4 + (n%128)/32, bit n%32).  One warp per (tile, block of 32 teams, word column):
+// lane i holds the word of team i, 32 ballots transpose the 32x32 bit block, lane j keeps expert j's word.
+__global__ void sign_tiles_kernel(const uint32_t* __restrict__ sign, int B, int pitch, int Epad, int ntiles, uint32_t* __restrict__ sign_t) {
+  const int wcols = Epad / 32;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= (long long)ntiles * 4 * wcols) return;
+  const int wc = (int)(gw % wcols), cb = (int)((gw / wcols) & 3), t = (int)(gw / (4LL * wcols));
+  const int n = t * TB + cb * 32 + lane;
+  const uint32_t w = (n < B && wc < pitch) ? __ldg(sign + (size_t)n * pitch + wc) : 0u;
+  uint32_t mine = 0u;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const uint32_t r = __ballot_sync(0xffffffffu, (w >> j) & 1u);
+    if (j == lane) mine = r;
+  }
+  sign_t[((size_t)t * Epad + wc * 32 + lane) * 4 + cb] = mine;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -655,10 +779,27 @@ int make_map(const ntf_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt, int esi
 }
 }  // namespace
 
-int ntf_out_tc_supported(int B, int h, int E, int flipout) { return (h == HK && !flipout && B >= 1 && E >= 1) ? 1 : 0; }
+int ntf_out_tc_supported(int B, int h, int E, int flipout) { (void)flipout; return (h == HK && B >= 1 && E >= 1) ? 1 : 0; }
 
-size_t ntf_out_train_tc_workspace_bytes(const ntf_ctx*, int B, int h, int E, int) {
-  return align_up((size_t)B * h * sizeof(__half), 256) + align_up((size_t)(cdiv(E, TE) + 1024) * sizeof(float), 256);  // + one loss partial per CTA
+// Flipout workspace behind the Fnn part: fp16 A_s | s_out tile plane | Q tiles | DZS tiles
+struct FlipWs { size_t as16, sign_t, q, dzs, total; };
+static FlipWs flip_ws(int B, int h, int E, bool train) {
+  const size_t Epad = (size_t)cdiv(E, TE) * TE, nt = (size_t)cdiv(B, TB);
+  FlipWs w;
+  w.as16 = 0;
+  w.sign_t = w.as16 + align_up((size_t)B * h * sizeof(__half), 1024);
+  w.q = w.sign_t + align_up(nt * Epad * 4 * sizeof(uint32_t), 1024);
+  w.dzs = w.q + align_up(nt * Epad * TB * sizeof(__half), 1024);
+  w.total = w.dzs + (train ? align_up(nt * Epad * TB * sizeof(__half), 1024) : 0);
+  return w;
+}
+
+static size_t tc_base_ws(int B, int h, int E) {
+  return align_up((size_t)B * h * sizeof(__half), 256) + align_up((size_t)(cdiv(E, TE) + 1024) * sizeof(float), 1024);  // + one loss partial per CTA
+}
+
+size_t ntf_out_train_tc_workspace_bytes(const ntf_ctx*, int B, int h, int E, int flipout) {
+  return tc_base_ws(B, h, E) + (flipout ? flip_ws(B, h, E, true).total : 0);
 }
 
 // Work split (TcArgs::n_full / split): the expert tiles that fill whole waves of the machine get one CTA each; the tiles of the
@@ -681,13 +822,94 @@ static void tc_debug_hooks(TcArgs& g) {
   g.exp = ex ? atoi(ex) : 0;
 }
 
+template <int MODE>
+static int launch_flip(cudaStream_t st, int grid, const CUtensorMap& mw, const CUtensorMap& ma, const CUtensorMap& mda, const CUtensorMap& mdz, const TcArgs& g) {
+  NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  NTF_COUNT_LAUNCH; out_tc_kernel<MODE, true><<<grid, NT, SMEM_BYTES, st>>>(mw, ma, mda, mdz, g);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
+
+// fp16 copies + the s_out tile plane + MODE 2 (Q = s_out*(A_s W_delta^T + b_delta)); shared by the training and the inference entry points
+static int flip_forward(ntf_ctx* ctx, cudaStream_t st, const float* A_s, const float* W_delta, const float* b_delta, const uint32_t* sign_out, int pitch_words,
+                        int B, int E, char* fws, const FlipWs& fw, TcArgs* gq, CUtensorMap* mwd, CUtensorMap* mas) {
+  const int Epad = cdiv(E, TE) * TE, nt = cdiv(B, TB);
+  __half* As16 = (__half*)(fws + fw.as16);
+  uint32_t* sign_t = (uint32_t*)(fws + fw.sign_t);
+  int rc;
+  if ((rc = make_map(ctx, mwd, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, W_delta, (uint64_t)E, HK, TE, 32))) return rc;
+  if ((rc = make_map(ctx, mas, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, As16, (uint64_t)B, HK, TB, 64))) return rc;
+  NTF_COUNT_LAUNCH; to_half_kernel<<<min(cdiv(B * HK, 256), ctx->sm_count * 4), 256, 0, st>>>(A_s, (size_t)B * HK, As16);
+  const long long warps = (long long)nt * 4 * (Epad / 32);
+  NTF_COUNT_LAUNCH; sign_tiles_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(sign_out, B, pitch_words, Epad, nt, sign_t);
+  TcArgs g{};
+  g.bias = b_delta; g.Epad = Epad; g.B = B; g.E = E;
+  g.sign_t = sign_t; g.Q = (__half*)(fws + fw.q);
+  tc_debug_hooks(g);
+  g.Zdbg = nullptr; g.timing = nullptr;
+  int grid;
+  plan_split(ctx, cdiv(E, TE), nt, &g.n_full, &g.split, &grid);
+  *gq = g;
+  return launch_flip<2>(st, grid, *mwd, *mas, *mwd, *mwd, g);
+}
+
+// Flipout training step of the output layer: three launches of the same pipeline (out_tc_kernel modes 2, 0, 3)
+static int out_train_tc_flip(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a, __half* A16, float* loss_part, char* fws) {
+  const bool train = a->dW != nullptr;
+  const FlipWs fw = flip_ws(a->B, a->h, a->E, true);
+  const int Epad = cdiv(a->E, TE) * TE, nt = cdiv(a->B, TB), nct = cdiv(a->E, TE);
+  CUtensorMap mw, mh, mda, mwd, mas, mdas, mdz;
+  TcArgs gq;
+  int rc;
+  if ((rc = flip_forward(ctx, st, a->A_s, a->W_delta, a->b_delta, a->sign_out, a->pitch_words, a->B, a->E, fws, fw, &gq, &mwd, &mas))) return rc;
+  __half* DZS = (__half*)(fws + fw.dzs);
+  if ((rc = make_map(ctx, &mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->W, (uint64_t)a->E, HK, TE, 32))) return rc;
+  if ((rc = make_map(ctx, &mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)a->B, HK, TB, 64))) return rc;
+  if ((rc = make_map(ctx, &mda, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, train ? (const void*)a->dA : (const void*)a->W, (uint64_t)(train ? a->B : a->E), HK, TB, 32))) return rc;
+  if ((rc = make_map(ctx, &mdas, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, train ? (const void*)a->dA_s : (const void*)a->W, (uint64_t)(train ? a->B : a->E), HK, TB, 32))) return rc;
+  if ((rc = make_map(ctx, &mdz, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, DZS, (uint64_t)nt * Epad, TB, TE, 64))) return rc;
+  if (!a->A16) { NTF_COUNT_LAUNCH; to_half_kernel<<<min(cdiv(a->B * a->h, 256), ctx->sm_count * 4), 256, 0, st>>>(a->A, (size_t)a->B * a->h, A16); }
+  if (train) {
+    NTF_CUDA(cudaMemsetAsync(a->dA, 0, (size_t)a->B * a->h * sizeof(float), st));
+    NTF_CUDA(cudaMemsetAsync(a->dA_s, 0, (size_t)a->B * a->h * sizeof(float), st));
+  }
+  TcArgs g = gq;  // same tiling / split as the Q launch
+  g.bias = a->b; g.special_t = const_cast<uint32_t*>(a->special_t); g.member_t = const_cast<uint32_t*>(a->member_t);
+  g.tpw = a->tpw; g.tnw = a->tnw; g.scale = a->loss_scale;
+  g.dW = a->dW; g.db = a->db; g.dA = a->dA; g.loss_part = loss_part; g.DZS = DZS; g.db_delta = a->db_delta;
+  tc_debug_hooks(g);
+  const int grid = g.n_full + (nct - g.n_full) * g.split;
+  if (train && g.split > 1) {  // the shared tiles' CTAs add their partials
+    const size_t e_first = (size_t)g.n_full * TE, rows = (size_t)a->E - e_first;
+    NTF_CUDA(cudaMemsetAsync(a->dW + e_first * HK, 0, rows * HK * sizeof(float), st));
+    NTF_CUDA(cudaMemsetAsync(a->db + e_first, 0, rows * sizeof(float), st));
+    NTF_CUDA(cudaMemsetAsync(a->dW_delta + e_first * HK, 0, rows * HK * sizeof(float), st));
+    NTF_CUDA(cudaMemsetAsync(a->db_delta + e_first, 0, rows * sizeof(float), st));
+  }
+  if ((rc = launch_flip<0>(st, grid, mw, mh, mda, mda, g))) return rc;
+  if (train) {
+    TcArgs g3 = gq;
+    g3.bias = a->b_delta; g3.scale = a->loss_scale; g3.dW = a->dW_delta; g3.dA = a->dA_s; g3.Q = nullptr; g3.sign_t = nullptr;
+    if ((rc = launch_flip<3>(st, grid, mwd, mas, mdas, mdz, g3))) return rc;
+  }
+  return ntf_loss_reduce_impl(st, loss_part, grid, a->loss_scale, a->loss_out);
+}
+
 int ntf_out_train_tc(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a, void* workspace, size_t workspace_bytes) {
   NTF_REQUIRE(a->h == HK, NTF_ERR_UNSUPPORTED, "out_train(tf32): hidden width %d (kernel is built for %d)", a->h, HK);
-  NTF_REQUIRE(workspace_bytes >= ntf_out_train_tc_workspace_bytes(ctx, a->B, a->h, a->E, 0), NTF_ERR_WORKSPACE, "out_train(tf32): workspace too small");
+  const bool flip = a->W_delta != nullptr;
+  NTF_REQUIRE(workspace_bytes >= ntf_out_train_tc_workspace_bytes(ctx, a->B, a->h, a->E, flip), NTF_ERR_WORKSPACE, "out_train(tf32): workspace too small");
+  NTF_REQUIRE(((uintptr_t)workspace & 255) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): the workspace must be 256-byte aligned");
   NTF_REQUIRE((((uintptr_t)a->A | (uintptr_t)a->W) & 15) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): A and W must be 16-byte aligned");
   const bool train = a->dW != nullptr;
   NTF_REQUIRE(!train || (a->db && a->dA), NTF_ERR_BAD_ARG, "out_train(tf32): training needs dW, db and dA");
   NTF_REQUIRE(!train || (((uintptr_t)a->dA | (uintptr_t)a->dW) & 15) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): dA and dW must be 16-byte aligned");
+  if (flip) {
+    NTF_REQUIRE(a->A_s && a->b_delta && a->sign_out, NTF_ERR_BAD_ARG, "out_train(tf32): incomplete Flipout arguments");
+    NTF_REQUIRE(!train || (a->dW_delta && a->db_delta && a->dA_s), NTF_ERR_BAD_ARG, "out_train(tf32): Flipout training needs dW_delta, db_delta and dA_s");
+    NTF_REQUIRE((((uintptr_t)a->A_s | (uintptr_t)a->W_delta | (uintptr_t)a->dW_delta | (uintptr_t)a->dA_s) & 15) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): Flipout tensors must be 16-byte aligned");
+    NTF_REQUIRE(a->e_lo == 0, NTF_ERR_UNSUPPORTED, "out_train(tf32): expert-sharded Flipout layer");
+  }
   NTF_REQUIRE((a->special_t == nullptr) == (a->member_t == nullptr), NTF_ERR_BAD_ARG, "out_train(tf32): special_t and member_t come together");
   NTF_REQUIRE(a->special_t || !a->special, NTF_ERR_BAD_ARG, "out_train(tf32): the tensor-core kernel reads the tile-transposed planes (ntf_special_tiles), not `special`");
   __half* A16 = a->A16 ? (__half*)const_cast<void*>(a->A16) : (__half*)workspace;
@@ -696,6 +918,7 @@ int ntf_out_train_tc(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a,
   const int nct = cdiv(a->E, TE);
   CUtensorMap mw, mh, mda;
   int rc;
+  if (flip) return out_train_tc_flip(ctx, st, a, A16, loss_part, (char*)workspace + tc_base_ws(a->B, a->h, a->E));
   if ((rc = make_map(ctx, &mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->W, (uint64_t)a->E, HK, TE, 32))) return rc;
   if ((rc = make_map(ctx, &mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)a->B, HK, TB, 64))) return rc;
   if ((rc = make_map(ctx, &mda, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, train ? (const void*)a->dA : (const void*)a->W, (uint64_t)(train ? a->B : a->E), HK, TB, 32))) return rc;
@@ -714,8 +937,8 @@ int ntf_out_train_tc(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a,
     NTF_CUDA(cudaMemsetAsync(a->dW + e_first * HK, 0, ((size_t)a->E - e_first) * HK * sizeof(float), st));
     NTF_CUDA(cudaMemsetAsync(a->db + e_first, 0, ((size_t)a->E - e_first) * sizeof(float), st));
   }
-  NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  NTF_COUNT_LAUNCH; out_tc_kernel<0><<<grid, NT, SMEM_BYTES, st>>>(mw, mh, mda, g);
+  NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  NTF_COUNT_LAUNCH; out_tc_kernel<0, false><<<grid, NT, SMEM_BYTES, st>>>(mw, mh, mda, mda, g);
   NTF_LAUNCH_CHECK();
   return ntf_loss_reduce_impl(st, loss_part, grid, a->loss_scale, a->loss_out);
 }
@@ -738,8 +961,33 @@ int ntf_infer_scores_tc(ntf_ctx* ctx, cudaStream_t st, const float* A, const flo
   g.Zdbg = nullptr;
   int grid;
   plan_split(ctx, cdiv(E, TE), cdiv(B, TB), &g.n_full, &g.split, &grid);
-  NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  NTF_COUNT_LAUNCH; out_tc_kernel<1><<<grid, NT, SMEM_BYTES, st>>>(mw, mh, mw, g);
+  NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  NTF_COUNT_LAUNCH; out_tc_kernel<1, false><<<grid, NT, SMEM_BYTES, st>>>(mw, mh, mw, mw, g);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
+}
+
+// Flipout inference (fnn.py:202-209 with a Bnn): P = sigmoid(lrelu(A mu^T + mu_b + s_out*(A_s W_delta^T + b_delta))): MODE 2 then MODE 1
+size_t ntf_infer_scores_tc_flip_workspace_bytes(int B, int h, int E) { return align_up((size_t)B * h * sizeof(__half), 1024) + flip_ws(B, h, E, false).total; }
+
+int ntf_infer_scores_tc_flip(ntf_ctx* ctx, cudaStream_t st, const float* A, const float* W, const float* b, int B, int h, int E, const float* A_s,
+                             const float* W_delta, const float* b_delta, const uint32_t* sign_out, int pitch_words, float* P, void* workspace,
+                             size_t workspace_bytes) {
+  NTF_REQUIRE(h == HK, NTF_ERR_UNSUPPORTED, "infer_scores(tf32): hidden width %d (kernel is built for %d)", h, HK);
+  NTF_REQUIRE(workspace && workspace_bytes >= ntf_infer_scores_tc_flip_workspace_bytes(B, h, E), NTF_ERR_WORKSPACE, "infer_scores(tf32, Flipout): workspace too small");
+  NTF_REQUIRE((((uintptr_t)workspace & 255) | (((uintptr_t)A | (uintptr_t)W | (uintptr_t)A_s | (uintptr_t)W_delta) & 15)) == 0, NTF_ERR_BAD_ARG, "infer_scores(tf32, Flipout): misaligned pointer");
+  __half* A16 = (__half*)workspace;
+  char* fws = (char*)workspace + align_up((size_t)B * h * sizeof(__half), 1024);
+  const FlipWs fw = flip_ws(B, h, E, false);
+  CUtensorMap mw, mh, mwd, mas;
+  TcArgs gq;
+  int rc;
+  if ((rc = flip_forward(ctx, st, A_s, W_delta, b_delta, sign_out, pitch_words, B, E, fws, fw, &gq, &mwd, &mas))) return rc;
+  if ((rc = make_map(ctx, &mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, W, (uint64_t)E, HK, TE, 32))) return rc;
+  if ((rc = make_map(ctx, &mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)B, HK, TB, 64))) return rc;
+  NTF_COUNT_LAUNCH; to_half_kernel<<<min(cdiv(B * h, 256), ctx->sm_count * 4), 256, 0, st>>>(A, (size_t)B * h, A16);
+  TcArgs g = gq;
+  g.bias = b; g.P = P;
+  const int grid = g.n_full + (cdiv(E, TE) - g.n_full) * g.split;
+  return launch_flip<1>(st, grid, mw, mh, mw, mw, g);
 }

@@ -483,10 +483,14 @@ class Engine:
         neg = self._sample(sp, b0, B, neg_host, gbatch)
         mptr = sp.m_indptr.data_ptr() + 4 * b0
         ns = 0 if neg is None else neg.shape[1]
-        ops.special_bits(1, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
+        tc = self.precision == _lib.NTF_TF32  # tcgen05 kernels: the sets travel as tile-transposed planes, consumed (cleared) by the kernel
+        if tc: ops.special_tiles(1, B, mptr, sp.m_indices, neg, ns, self.E, self.special_t, self.member_t)
+        else: ops.special_bits(1, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
         a = OutTrainArgs()
         a.A, a.W, a.b = self.act[-1].data_ptr(), self._pv(Lo, 'mu', 'weight').data_ptr(), self._pv(Lo, 'mu', 'bias').data_ptr()
-        a.special, a.pitch_words = self.special.data_ptr(), self.pitch
+        a.pitch_words = self.pitch  # (of sign_out; the condition plane has the same pitch)
+        if tc: a.special_t, a.member_t = self.special_t.data_ptr(), self.member_t.data_ptr()
+        else: a.special = self.special.data_ptr()
         a.m_indptr, a.m_indices = mptr, sp.m_indices.data_ptr()
         a.B, a.h, a.E = B, h[-1], self.E
         a.tpw, a.tnw, a.loss_scale = self.tpw, self.tnw, scale
@@ -499,7 +503,7 @@ class Engine:
             a.dW_delta, a.db_delta = self.nview(self.gdelta, f'{Lo}.weight').data_ptr(), self.nview(self.gdelta, f'{Lo}.bias').data_ptr()
             a.dA_s = self.dact_s[-1].data_ptr()
         ops.out_train(self.dev_index, self.precision, a, self.ws)
-        ops.special_bits(0, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
+        if not tc: ops.special_bits(0, B, mptr, sp.m_indices, neg, ns, self.E, self.special, self.pitch)
         ops.axpy(1, scale / self.world, self.kl, self.loss_buf[loss_slot:loss_slot + 1])  # + KL/B (fnn.py:136,149)
         self.global_step += 1
         if not train: return

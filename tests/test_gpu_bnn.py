@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 def make_engine(S, hidden, E, B, skill, member, layers, **kw):
     from opentf_b200.engine import Engine
-    eng = Engine(S, hidden, E, DEV, bayesian=True, precision='fp32', tpw=10, tnw=1, nsd=kw.get('nsd', 'uniform'), ns=5, seed=3, max_batch=B)
+    eng = Engine(S, hidden, E, DEV, bayesian=True, precision=kw.get('precision', 'fp32'), tpw=10, tnw=1, nsd=kw.get('nsd', 'uniform'), ns=5, seed=3, max_batch=B)
     eng.stage(skill, member)
     sd = {}
     for i, L in enumerate(layers):
@@ -161,3 +161,68 @@ def test_bnn_class_end_to_end(toy, tmp_path):
     m2 = Bnn(str(tmp_path / 'again'), 'cuda:0', 0, dict(cfg, e=1))
     m2.learn(tv, one, {0: f'{m.output}/f0.pt'})
     assert m2.last_history[0][0][0] < hist[0][0]
+
+
+# ---- tensor-core Flipout output layer (out_tc_kernel modes 2 / 0 / 3): fp16 operands (10-bit mantissa) and fp16 perturbation-term /
+# gradient tiles, fp32 accumulation.  Tolerances: loss 2e-3 relative; gradients 5e-3 in norm (a logit within rounding distance of the
+# lrelu kink may take the other slope: rare entries, so the comparison is in norm, as for the Fnn kernel in test_gpu_tc.py) -- except the
+# output layer's rho gradients, 2e-2: dW_delta = sum_n s_out*dz*a_s sums RANDOMLY SIGNED terms (norm ~ sqrt(B) terms) while a kink flip
+# changes a term by its full size, so a fraction f of flipped logits costs sqrt(f) relative (measured f ~ 4e-5 -> 6e-3); the mu
+# gradients sum coherently (norm ~ B terms) and see f^(1/2)/B^(1/2) of it.
+@pytest.mark.parametrize('B,S,hidden,E', [(130, 27, [128], 1000), (256, 40, [128], 300), (1000, 27, [128], 20000), (77, 30, [16, 128], 129)])
+def test_flipout_step_tensor_core_matches_oracle(B, S, hidden, E):
+    from opentf_b200 import _lib
+    rng = np.random.default_rng(B + E)
+    torch.manual_seed(B)
+    skill, member = rand_csr(rng, B, S, 1, min(S, 6)), rand_csr(rng, B, E, 1, min(E - 1, 4))
+    layers = O.init_flipout_params(S, hidden, E)
+    noise = O.draw_flipout_noise(layers, B)
+    neg = rng.integers(0, E, (B, 5))
+    X, y = dense(skill), dense(member)
+    logits, acts, pre = O.flipout_forward(layers, noise, X)
+    w = O.loss_weights(y, torch.as_tensor(neg), 10, 1)
+    loss_ref = (O.bce_with_logits(logits, y, w).sum(1).mean() + O.flipout_kl(layers) / B).item()
+    g_ref = O.flipout_backward(layers, noise, acts, pre, y, w)
+    eng = make_engine(S, hidden, E, B, skill, member, layers, precision='tf32')
+    assert eng.precision == _lib.NTF_TF32  # the tcgen05 path is the one under test
+    sp = eng.split(np.arange(B))
+    eng.step(sp, 0, B, True, lr=1e-3, loss_slot=0, neg_host=neg, noise_host=noise)
+    torch.cuda.synchronize()
+    loss = eng.loss_buf[0].item()
+    assert abs(loss - loss_ref) <= 2e-3 * abs(loss_ref), (loss, loss_ref)
+    nrm = lambda a, b: ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+    for i in range(len(layers)):
+        mine = grads_of(eng, i)
+        for k in ('mu_w', 'mu_b', 'rho_w', 'rho_b'):
+            tol = 2e-2 if (i == len(layers) - 1 and k.startswith('rho')) else 5e-3
+            assert nrm(mine[k], g_ref[i][k]) < tol, (i, k, nrm(mine[k], g_ref[i][k]))
+    assert int(eng.special_t.abs().sum()) == 0 and int(eng.member_t.abs().sum()) == 0  # the planes were consumed
+    # a second step on the same engine (planes clean, workspace reused) and a validation step
+    noise2 = O.draw_flipout_noise(layers, B)
+    sd = eng.state_dict()
+    layers2 = [dict(mu_w=sd[f'layers.{i}.mu_weight'], rho_w=sd[f'layers.{i}.rho_weight'], mu_b=sd[f'layers.{i}.mu_bias'], rho_b=sd[f'layers.{i}.rho_bias'])
+               for i in range(len(layers))]
+    logits2, _, _ = O.flipout_forward(layers2, noise2, X)
+    ref2 = (O.bce_with_logits(logits2, y, w).sum(1).mean() + O.flipout_kl(layers2) / B).item()
+    p1 = eng.params.clone()
+    eng.step(sp, 0, B, False, loss_slot=1, neg_host=neg, noise_host=noise2)
+    assert abs(eng.loss_buf[1].item() - ref2) <= 2e-3 * abs(ref2)
+    assert torch.equal(eng.params, p1)
+
+
+def test_mc_inference_tensor_core_matches_oracle(B=200, S=20, E=1500, nmc=3):
+    from opentf_b200 import _lib
+    rng = np.random.default_rng(1)
+    torch.manual_seed(1)
+    skill, member = rand_csr(rng, B, S, 1, 4), rand_csr(rng, B, E, 1, 3)
+    layers = O.init_flipout_params(S, [128], E)
+    noises = [O.draw_flipout_noise(layers, B) for _ in range(nmc)]
+    mc = np.stack([torch.sigmoid(O.flipout_forward(layers, nz, dense(skill))[0]).numpy() for nz in noises])
+    eng = make_engine(S, [128], E, B, skill, member, layers, precision='tf32')
+    assert eng.precision == _lib.NTF_TF32
+    sp = eng.split(np.arange(B))
+    out, scratch = torch.empty(B, E, device=DEV), torch.empty(B, E, device=DEV)
+    ep, em = torch.empty(B, device=DEV), torch.empty(B, device=DEV)
+    eng.scores_mc(sp, 0, B, nmc, out, scratch, ep, em, noise_host=noises)
+    assert np.abs(out.cpu().numpy() - mc.mean(0)).max() < 2e-3  # probabilities in (0,1): absolute
+    assert np.abs(ep.cpu().numpy() - O.predictive_entropy(mc)).max() < 2e-3 * E
