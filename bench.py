@@ -200,6 +200,8 @@ def run_ours(args):
     b, G = args.batch, world
     eng = Engine(S, [128], E, dev, precision=args.precision, tpw=10, tnw=1, nsd=args.nsd, ns=5, seed=0, max_batch=b)
     eng.world, eng.rank = world, rank
+    if world > 1 and os.environ.get('NTF_DP_NCCL', '1') != '0': eng.attach_comm()  # gradient exchange inside ntf_fnn_step (own NCCL communicator)
+    eng_comm = eng.comm is not None
     eng.stage(tv['skill'], tv['member'])
     torch.manual_seed(0)
     lin = [torch.nn.Linear(S, 128), torch.nn.Linear(128, E)]
@@ -330,7 +332,9 @@ def run_ours(args):
            'data': 'synthetic', 'config': config_of(args, tv), 'clocks': clk.summary(),
            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': host.h2d_bytes, 'd2h_bytes_per_step': 4,
                    'api': 'Engine.step_host: pinned batch CSR block -> one H2D copy -> ntf_fnn_step (replayed as a CUDA graph) -> loss.item()'},
-           'gpu_launches': launches, 'cuda_graphs': bool(graphs), 'host_enqueue_ms_per_step': host_ms, 'roofline': roof, 'infer_topk': {'k': args.infer_k, 'value': infer_value, 'unit': 'teams/s', 'batch': ib}}
+           'gpu_launches': launches, 'cuda_graphs': bool(graphs),
+           'dp_exchange': None if G == 1 else ('ncclAllReduce inside ntf_fnn_step: 2 overlapped arena segments, captured in the step graph' if eng_comm else
+                                               'torch.distributed.all_reduce between the halves of a step'), 'host_enqueue_ms_per_step': host_ms, 'roofline': roof, 'infer_topk': {'k': args.infer_k, 'value': infer_value, 'unit': 'teams/s', 'batch': ib}}
     out.update(extras)
     if not args.no_cpu_baseline:
         v, n, dt, threads = cpu_reference_steps(tv, splits, b, args.nsd, args.cpu_baseline_seconds)

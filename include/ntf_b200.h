@@ -85,6 +85,10 @@ int ntf_csr_gather(ntf_ctx* ctx, void* stream, const int32_t* rows, int n, const
                    const int32_t* src_indices, int32_t* dst_indptr, int32_t* dst_indices, int32_t* dst_ent_row,
                    void* workspace, size_t workspace_bytes);
 
+/* dense (embedded) skill input (main.py:148-153 replaces teamsvecs['skill'] by d2v/gnn vectors; ntf.py:24 hands the row as is):
+ * dst[i,:] = src[rows[i],:] (rows == NULL: identity) -- the batch-ordered copy of a split, rebuilt per epoch like ntf_csr_gather. */
+int ntf_rows_gather(ntf_ctx* ctx, void* stream, const int32_t* rows, int n, int d, const float* src, float* dst);
+
 /* ---- input layer: multi-hot skills --------------------------------------------------------------------------
  * replaces ntf.py:23 (row -> dense float), fnn.py:120 (H2D of dense X) and layer 0 of fnn.py:25
  * (aten::linear over a 99.97%-zero X, + leaky_relu):
@@ -259,6 +263,8 @@ int ntf_add_signed(ntf_ctx* ctx, void* stream, const float* X, const uint32_t* b
  * forward (CSR bag, hidden layers), negative sampling (unless neg_given), output layer forward + weighted BCE; and when `train`:
  * the backward pass and (when `run_adam`) the Adam step.  Exactly the sequence of the entry points above; nothing is synchronised. */
 #define NTF_MAX_LAYERS 8
+/* ncclAllReduce(sendbuff, recvbuff, count, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) -> ncclResult_t (0 = success) */
+typedef int (*ntf_allreduce_fn)(const void* send, void* recv, size_t count, int dtype, int op, void* comm, void* stream);
 typedef struct {
   int n_layers;                      /* linear layers (hidden layers + 1)                                              */
   int S, E;                          /* E = the output columns THIS call owns (all experts, or one shard of them)      */
@@ -298,6 +304,13 @@ typedef struct {
   double lr, beta1, beta2, eps; int64_t adam_t;
   void* prof_ev[2];                  /* optional cudaEvent_t pair recorded around the output-layer call (bench.py's roofline timing) */
   const ntf_dyn* dyn;                /* optional (device): `step`, `lr`, `adam_t` are read from this block instead -- graph replays */
+  void* comm; void* allreduce;       /* data-parallel ranks: an NCCL communicator as an opaque pointer and the address of
+                                        ncclAllReduce (ntf_allreduce_fn).  Non-NULL (train, phase 3, run_adam): the step sums the gradient
+                                        arena over the ranks itself, in two segments on its own stream -- the output layer's while the
+                                        hidden layers' backward runs, the rest while the output layer's segment is stepped -- so the
+                                        whole data-parallel step is ONE capturable launch sequence.  The library does not link NCCL. */
+  const float* x_dense;              /* dense (embedded) skill input, ntf.py:24: [B,S] rows of this batch.  Non-NULL: layer 0 is a dense
+                                        layer (ntf_dense_fwd / ntf_dense_bwd), W[0] / gW[0] are in torch layout [h0,S], s_* unused */
 } ntf_fnn_step_args;
 size_t ntf_fnn_step_workspace_bytes(const ntf_ctx* ctx, const ntf_fnn_step_args* args);
 int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args* args, void* workspace, size_t workspace_bytes);

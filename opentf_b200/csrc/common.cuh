@@ -19,6 +19,10 @@ struct ntf_ctx {
   cudaStream_t side[2];
   cudaEvent_t ev_fork, ev_join[2];
   cudaEvent_t ev_fork_opt, ev_join_opt;  // second fork of a step: Adam on the output layer's segment next to the input layer's backward pass
+  // data-parallel ranks (ntf_fnn_step_args.comm): the gradient all-reduces run on their own stream so that the output layer's segment
+  // is exchanged while the backward pass through the hidden layers runs, and stepped while the rest is exchanged
+  cudaStream_t comm_st;
+  cudaEvent_t ev_ar[2], ev_bwd;
 };
 
 // ---- launch accounting (bench.py reports how many of OUR kernels ran in the timed region) ----------------

@@ -166,6 +166,35 @@ extern "C" int ntf_csr_gather(ntf_ctx* ctx, void* stream, const int32_t* rows, i
   return NTF_OK;
 }
 
+// ---- dense (embedded) skill input: ntf.py:24 -- a team's row is a d-vector instead of a multi-hot set ----------------------------
+// dst[i,:] = src[rows[i],:]: the per-epoch shuffle of fnn.py:95 for dense rows (HBM-bound: 8*d bytes per team).
+namespace {
+__global__ void __launch_bounds__(256) rows_gather_kernel(const int32_t* __restrict__ rows, int n, int d, const float* __restrict__ src,
+                                                          float* __restrict__ dst) {
+  const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const size_t r = rows ? (size_t)rows[i] : (size_t)i;
+    const float* s = src + r * d;
+    float* t = dst + (size_t)i * d;
+    if ((d & 3) == 0) {
+      for (int c = lane; c < (d >> 2); c += 32) reinterpret_cast<float4*>(t)[c] = __ldg(reinterpret_cast<const float4*>(s) + c);
+    } else {
+      for (int c = lane; c < d; c += 32) t[c] = __ldg(s + c);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int ntf_rows_gather(ntf_ctx* ctx, void* stream, const int32_t* rows, int n, int d, const float* src, float* dst) {
+  NTF_REQUIRE(ctx && src && dst, NTF_ERR_BAD_ARG, "rows_gather: null pointer");
+  NTF_REQUIRE(n >= 0 && d > 0, NTF_ERR_BAD_ARG, "rows_gather: n=%d d=%d", n, d);
+  if (n == 0) return NTF_OK;
+  const int blocks = min(cdiv(n * 32, 256), ctx->sm_count * 8);
+  NTF_COUNT_LAUNCH; rows_gather_kernel<<<blocks, 256, 0, as_stream(stream)>>>(rows, n, d, src, dst);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
+
 // =========================================================================================================
 // K1: embedding-bag forward.  One warp per team; a lane owns float4 slices of the h-vector.
 // Algorithmic bytes per team: n_s*(4h+4) + 8 + 4h   

@@ -28,7 +28,7 @@ int ntf_csr_bag_bwd_reduce_impl(ntf_ctx* ctx, cudaStream_t st, int B, const int3
 static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 
 // workspace = [ input-layer backward (slots, lives from the fork to the end of the step) | everything that runs on the main stream ]
-static size_t bag_region(const ntf_fnn_step_args* a) { return align_up(ntf_csr_bag_bwd_workspace_bytes(a->S, a->hidden[0]), 256); }
+static size_t bag_region(const ntf_fnn_step_args* a) { return a->x_dense ? 0 : align_up(ntf_csr_bag_bwd_workspace_bytes(a->S, a->hidden[0]), 256); }
 
 extern "C" size_t ntf_fnn_step_workspace_bytes(const ntf_ctx* ctx, const ntf_fnn_step_args* a) {
   if (!a || a->n_layers < 2 || a->n_layers > NTF_MAX_LAYERS) return 0;
@@ -37,6 +37,7 @@ extern "C" size_t ntf_fnn_step_workspace_bytes(const ntf_ctx* ctx, const ntf_fnn
   w = max_sz(w, ntf_out_train_workspace_bytes(ctx, a->precision, a->B, h_last, a->E, 0));
   for (int i = 0; i < L - 1; ++i) w = max_sz(w, ntf_act_bwd_workspace_bytes(a->B, a->hidden[i]));
   for (int i = 1; i < L - 1; ++i) w = max_sz(w, ntf_dense_bwd_workspace_bytes(a->B, a->hidden[i - 1], a->hidden[i]));
+  if (a->x_dense) w = max_sz(w, ntf_dense_bwd_workspace_bytes(a->B, a->S, a->hidden[0]));
   return bag_region(a) + w;
 }
 
@@ -60,7 +61,7 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
 #define STEP(call) do { if ((rc = (call)) != NTF_OK) return rc; } while (0)
   // ---- fork: what needs the batch's CSR only ----
   if ((phase & 1) || bwd_here) NTF_CUDA(cudaEventRecord(ctx->ev_fork, st));
-  if (bwd_here) {  // side 1: every (team, skill) entry takes a slot of its skill (pass 1 of the input layer's backward)
+  if (bwd_here && !a->x_dense) {  // side 1: every (team, skill) entry takes a slot of its skill (pass 1 of the input layer's backward)
     NTF_CUDA(cudaStreamWaitEvent(ctx->side[1], ctx->ev_fork, 0));
     STEP(ntf_csr_bag_bwd_fill_impl(ctx, ctx->side[1], B, a->s_indptr, a->s_indices, a->s_ent_row, a->row_base, a->S, h[0], ws_bag, ws_bag_bytes, nullptr));
     NTF_CUDA(cudaEventRecord(ctx->ev_join[1], ctx->side[1]));
@@ -91,8 +92,9 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     NTF_CUDA(cudaEventRecord(ctx->ev_join[0], ctx->side[0]));
     // ---- main: forward through the hidden layers: fnn.py:25 (layer 0 = CSR bag, ntf.py:23 never densified) ----
     // (one hidden layer + tensor-core output layer: the bag kernel also writes the fp16 operand copy the output layer reads)
-    void* A16 = (tc && Lo == 1 && (h[0] % 8) == 0) ? ws_main : nullptr;
-    STEP(ntf_csr_bag_fwd_impl(ctx, stream, B, a->s_indptr, a->s_indices, a->W[0], a->b[0], a->S, h[0], a->act[0], A16));
+    void* A16 = (tc && Lo == 1 && (h[0] % 8) == 0 && !a->x_dense) ? ws_main : nullptr;
+    if (a->x_dense) STEP(ntf_dense_fwd(ctx, stream, a->x_dense, a->W[0], a->b[0], B, a->S, h[0], 1, a->act[0]));  // ntf.py:24: embedded skills
+    else STEP(ntf_csr_bag_fwd_impl(ctx, stream, B, a->s_indptr, a->s_indices, a->W[0], a->b[0], a->S, h[0], a->act[0], A16));
     for (int i = 1; i < Lo; ++i) STEP(ntf_dense_fwd(ctx, stream, a->act[i - 1], a->W[i], a->b[i], B, h[i - 1], h[i], 1, a->act[i]));
     // ---- output layer: forward + weighted BCE (+ backward): fnn.py:32-46,135,137 ----
     o.A = a->act[Lo - 1]; o.W = a->W[Lo]; o.b = a->b[Lo]; o.A16 = A16;
@@ -122,8 +124,25 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     for (int i = 0; i < Lo && last; ++i) last = a->gW[i] < lo && a->gb[i] < lo;
     if (last) opt_split = off;
   }
+  // data-parallel ranks: sum the gradients over the ranks before they are stepped (ncclAllReduce, in place, fp32 sum) -- on the
+  // communication stream, so that the exchange of the output layer's segment hides behind the hidden layers' backward pass and
+  // its Adam step behind the exchange of the rest
+  const bool dp = a->comm != nullptr;
+  NTF_REQUIRE(!dp || (a->allreduce && a->run_adam && phase == 3), NTF_ERR_BAD_ARG, "fnn_step: comm needs allreduce, run_adam and phase 3");
+  const ntf_allreduce_fn allreduce = (ntf_allreduce_fn)a->allreduce;
+#define ALLREDUCE(ptr, count)                                                                                               \
+  do {                                                                                                                      \
+    const int nr = allreduce((ptr), (ptr), (count), /*ncclFloat32*/ 7, /*ncclSum*/ 0, a->comm, (void*)ctx->comm_st);        \
+    NTF_REQUIRE(nr == 0, NTF_ERR_CUDA, "fnn_step: ncclAllReduce failed with ncclResult %d", nr);                          \
+  } while (0)
   if (opt_split < a->n_params) {
     NTF_CUDA(cudaEventRecord(ctx->ev_fork_opt, st));
+    if (dp) {
+      NTF_CUDA(cudaStreamWaitEvent(ctx->comm_st, ctx->ev_fork_opt, 0));
+      ALLREDUCE(a->grads + opt_split, a->n_params - opt_split);
+      NTF_CUDA(cudaEventRecord(ctx->ev_ar[0], ctx->comm_st));
+      NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_ar[0], 0));
+    } else
     NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork_opt, 0));
     STEP(ntf_adam_step_impl(ctx, ctx->side[0], a->params + opt_split, a->grads + opt_split, a->adam_m + opt_split, a->adam_v + opt_split,
                             a->n_params - opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn));
@@ -135,9 +154,21 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     STEP(ntf_dense_bwd(ctx, stream, a->act[i - 1], a->W[i], a->dz[i], B, h[i - 1], h[i], a->gW[i], a->dact[i - 1], ws_main, ws_main_bytes));
   }
   STEP(ntf_act_bwd(ctx, stream, a->dact[0], a->act[0], B, h[0], 1, a->dz[0], a->gb[0], ws_main, ws_main_bytes));
-  NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[1], 0));
-  STEP(ntf_csr_bag_bwd_reduce_impl(ctx, st, B, a->s_indptr, a->s_indices, a->s_ent_row, a->row_base, a->dz[0], a->S, h[0], a->gW[0], ws_bag, ws_bag_bytes, nullptr));
+  if (a->x_dense) {  // dW0[h0,S] = dz0^T X; the input needs no gradient
+    STEP(ntf_dense_bwd(ctx, stream, a->x_dense, a->W[0], a->dz[0], B, a->S, h[0], a->gW[0], nullptr, ws_main, ws_main_bytes));
+  } else {
+    NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[1], 0));
+    STEP(ntf_csr_bag_bwd_reduce_impl(ctx, st, B, a->s_indptr, a->s_indices, a->s_ent_row, a->row_base, a->dz[0], a->S, h[0], a->gW[0], ws_bag, ws_bag_bytes, nullptr));
+  }
   // ---- optimiser: fnn.py:139 (skipped when the caller all-reduces the gradients first: data-parallel ranks) ----
+  if (dp) {
+    NTF_CUDA(cudaEventRecord(ctx->ev_bwd, st));
+    NTF_CUDA(cudaStreamWaitEvent(ctx->comm_st, ctx->ev_bwd, 0));
+    ALLREDUCE(a->grads, opt_split);
+    NTF_CUDA(cudaEventRecord(ctx->ev_ar[1], ctx->comm_st));
+    NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_ar[1], 0));
+  }
+#undef ALLREDUCE
   if (a->run_adam) STEP(ntf_adam_step_impl(ctx, st, a->params, a->grads, a->adam_m, a->adam_v, opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn));
   if (opt_split < a->n_params) NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_join_opt, 0));
 #undef STEP

@@ -61,6 +61,16 @@ class DeviceCSR:
         return int((self.host_indptr[rows + 1] - self.host_indptr[rows]).sum())
 
 
+class DeviceRows:
+    """dense (embedded) skill vectors of all teams on the device: teamsvecs['skill'] as main.py:148-153 leaves it (ndarray [N,d])"""
+
+    def __init__(self, mat, device):
+        m = np.ascontiguousarray(np.asarray(mat), dtype=np.float32)  # ntf.py:24 `.float()`
+        if m.ndim != 2: raise ValueError(f'dense skill input must be [N,d], got {m.shape}')
+        self.shape = m.shape
+        self.x = torch.from_numpy(m).to(device)
+
+
 class SplitData:
     """teams `rows` (in that order) of the skill and member CSR, gathered on the device.  `regather(order)`
     rebuilds the copy for a new order of the same teams (the per-epoch shuffle of fnn.py:95)."""
@@ -70,10 +80,13 @@ class SplitData:
         self.rows_host = np.ascontiguousarray(np.asarray(rows), dtype=np.int32)
         self.n = len(self.rows_host)
         dev = eng.device
-        self.nnz_s, self.nnz_m = eng.skill.nnz_of(self.rows_host), eng.member.nnz_of(self.rows_host)
-        self.s_indptr = torch.empty(self.n + 1, dtype=torch.int32, device=dev)
-        self.s_indices = torch.empty(max(1, self.nnz_s), dtype=torch.int32, device=dev)
-        self.s_ent_row = torch.empty(max(1, self.nnz_s), dtype=torch.int32, device=dev)
+        self.dense = eng.dense_input
+        self.nnz_s, self.nnz_m = (0 if self.dense else eng.skill.nnz_of(self.rows_host)), eng.member.nnz_of(self.rows_host)
+        if self.dense: self.x = torch.empty(max(1, self.n), eng.S, dtype=torch.float32, device=dev)  # [n,d] rows in batch order
+        else:
+            self.s_indptr = torch.empty(self.n + 1, dtype=torch.int32, device=dev)
+            self.s_indices = torch.empty(max(1, self.nnz_s), dtype=torch.int32, device=dev)
+            self.s_ent_row = torch.empty(max(1, self.nnz_s), dtype=torch.int32, device=dev)
         self.m_indptr = torch.empty(self.n + 1, dtype=torch.int32, device=dev)
         self.m_indices = torch.empty(max(1, self.nnz_m), dtype=torch.int32, device=dev)
         self.rows_dev = torch.empty(max(1, self.n), dtype=torch.int32, device=dev)
@@ -86,7 +99,8 @@ class SplitData:
         if self.n == 0: return
         self.rows_dev.copy_(torch.from_numpy(np.ascontiguousarray(rows)), non_blocking=False)
         e = self.eng
-        ops.csr_gather(self.rows_dev, self.n, e.skill.indptr, e.skill.indices, self.s_indptr, self.s_indices, self.s_ent_row, e.ws)
+        if self.dense: ops.rows_gather(self.rows_dev, self.n, e.S, e.skill.x, self.x)
+        else: ops.csr_gather(self.rows_dev, self.n, e.skill.indptr, e.skill.indices, self.s_indptr, self.s_indices, self.s_ent_row, e.ws)
         ops.csr_gather(self.rows_dev, self.n, e.member.indptr, e.member.indices, self.m_indptr, self.m_indices, None, e.ws)
 
 
@@ -126,7 +140,7 @@ def pack_host_batch(s_ptr, s_idx, m_ptr, m_idx, cap_s=None, cap_m=None):
 
 class Engine:
     def __init__(self, S, hidden, E, device, bayesian=False, precision='tf32', tpw=10.0, tnw=1.0, nsd='uniform', ns=5,
-                 seed=0, max_batch=1000, shard=None):
+                 seed=0, max_batch=1000, shard=None, dense_input=False):
         """shard=(i, n): expert-sharded output layer (BASELINE config 4): this engine owns columns
         [E*i//n, E*(i+1)//n) of the last layer (weights, gradients, Adam state, special planes); everything else is replicated and
         the ranks exchange only dA [B,h] per step (`allreduce`)."""
@@ -142,6 +156,10 @@ class Engine:
         self.e_lo, self.e_hi = self.E_total * self.shard[0] // self.shard[1], self.E_total * (self.shard[0] + 1) // self.shard[1]
         self.E = self.e_hi - self.e_lo  # the output columns this engine owns
         if self.shard[1] > 1 and bayesian: raise NotImplementedError('expert-sharded Bnn')
+        # dense_input: teamsvecs['skill'] is a dense [N,d] matrix of skill embeddings (main.py:148-153, ntf.py:24): layer 0 is then
+        # a dense layer in torch layout [h0,d] instead of the CSR bag over a transposed weight
+        self.dense_input = bool(dense_input)
+        if self.dense_input and bayesian: raise NotImplementedError('Bnn on dense (embedded) skill input')
         self.bayesian, self.precision = bool(bayesian), PRECISION[precision]
         # 'tf32' selects the tcgen05 kernels where they exist for the shape; other shapes (toy sizes, odd widths) run the
         # CUDA-core fp32 kernels of the same library -- both are sm_100a code, neither is a fallback to another backend.
@@ -164,6 +182,10 @@ class Engine:
         self.graph_event_factory = None  # (bench.py) called at capture time -> a cudaEvent_t pair recorded around the output layer
         self.global_step = 0  # counts train AND valid steps: the sampler's Philox counter (fnn.py:148 samples in valid too)
         self.world, self.rank = 1, 0
+        # data-parallel ranks: exchange the gradient arena in two overlapped segments (NTF_DP_OVERLAP=0: one all-reduce after the step)
+        self.dp_overlap = os.environ.get('NTF_DP_OVERLAP', '1') != '0'
+        self._dp_stream = self._dp_ev = None
+        self.comm = None  # nccl.Comm: the library then runs the exchange inside ntf_fnn_step (attach_comm)
 
     # ------------------------------------------------------------------ memory
     def _layout(self):
@@ -172,7 +194,7 @@ class Engine:
         kinds = ['mu_', 'rho_'] if self.bayesian else ['']
         for i in range(self.L):
             fin, fout = self.sizes[i], self.sizes[i + 1]
-            wshape = (fin, fout) if i == 0 else (fout, fin)  # layer 0 stored transposed
+            wshape = (fin, fout) if (i == 0 and not self.dense_input) else (fout, fin)  # layer 0 stored transposed (CSR bag)
             for k in kinds:
                 self.views[f'layers.{i}.{k}weight'] = (off, wshape); off += _round_up(fin * fout, ALIGN)
             for k in kinds:
@@ -233,7 +255,7 @@ class Engine:
         if missing: raise KeyError(f'state_dict is missing {missing}')
         for name in self.views:
             t = torch.as_tensor(sd[name]).detach().to(torch.float32)
-            if name.startswith('layers.0.') and name.endswith('weight'): t = t.t()
+            if name.startswith('layers.0.') and name.endswith('weight') and not self.dense_input: t = t.t()
             if name.startswith(f'layers.{self.L - 1}.') and self.shard[1] > 1: t = t[self.e_lo:self.e_hi]  # this shard's experts
             v = self.view(name)
             if tuple(t.shape) != tuple(v.shape): raise ValueError(f'{name}: shape {tuple(t.shape)} does not fit {tuple(v.shape)}')
@@ -254,7 +276,7 @@ class Engine:
                 torch.distributed.all_gather(parts, pad)
                 t = torch.cat([parts[i][:self.E_total * (i + 1) // n - self.E_total * i // n] for i in range(n)])
             t = t.cpu().clone()
-            if name.startswith('layers.0.') and name.endswith('weight'): t = t.t().contiguous()
+            if name.startswith('layers.0.') and name.endswith('weight') and not self.dense_input: t = t.t().contiguous()
             out[name] = t
         return out
 
@@ -267,8 +289,10 @@ class Engine:
 
     # ------------------------------------------------------------------ data
     def stage(self, skill_mat, member_mat):
-        self.skill, self.member = DeviceCSR(skill_mat, self.device), DeviceCSR(member_mat, self.device)
-        assert self.skill.shape[1] == self.S and self.member.shape[1] == self.E_total
+        if self.dense_input: self.skill = DeviceRows(skill_mat, self.device)
+        else: self.skill = DeviceCSR(skill_mat, self.device)
+        self.member = DeviceCSR(member_mat, self.device)
+        assert self.skill.shape[1] == self.S and self.member.shape[1] == self.E_total and self.skill.shape[0] == self.member.shape[0]
         if self.bayesian:  # Flipout input signs exist only at the nnz positions: one bit per CSR entry of a batch
             maxlen = int(np.diff(self.skill.host_indptr).max()) if self.skill.shape[0] else 1
             self._ent_sign_words(self.Bmax * max(1, maxlen))
@@ -290,7 +314,9 @@ class Engine:
 
     # ------------------------------------------------------------------ one step
     def _forward_hidden(self, sp, b0, B):
-        ops.csr_bag_fwd(B, sp.s_indptr.data_ptr() + 4 * b0, sp.s_indices, self.view('layers.0.weight'), self.view('layers.0.bias'),
+        if self.dense_input:
+            ops.dense_fwd(sp.x[b0:b0 + B], self.view('layers.0.weight'), self.view('layers.0.bias'), B, self.S, self.hidden[0], 1, self.act[0])
+        else: ops.csr_bag_fwd(B, sp.s_indptr.data_ptr() + 4 * b0, sp.s_indices, self.view('layers.0.weight'), self.view('layers.0.bias'),
                         self.S, self.hidden[0], self.act[0])
         for i in range(1, self.L - 1):
             ops.dense_fwd(self.act[i - 1], self.view(f'layers.{i}.weight'), self.view(f'layers.{i}.bias'), B, self.hidden[i - 1],
@@ -342,7 +368,8 @@ class Engine:
         if self.bayesian: return self._step_bayes(sp, b0, B, train, lr, loss_slot, neg_host, loss_scale, gbatch, noise_host)
         a = self._fnn_args()
         a.B, a.row_base, a.row0 = B, b0, b0
-        a.s_indptr, a.s_indices, a.s_ent_row = sp.s_indptr.data_ptr() + 4 * b0, sp.s_indices.data_ptr(), sp.s_ent_row.data_ptr()
+        if self.dense_input: a.x_dense, a.s_indptr, a.s_indices, a.s_ent_row = sp.x.data_ptr() + 4 * self.S * b0, None, None, None
+        else: a.x_dense, a.s_indptr, a.s_indices, a.s_ent_row = None, sp.s_indptr.data_ptr() + 4 * b0, sp.s_indices.data_ptr(), sp.s_ent_row.data_ptr()
         a.m_indptr, a.m_indices = sp.m_indptr.data_ptr() + 4 * b0, sp.m_indices.data_ptr()
         if gbatch is None: a.gB, a.g_m_indptr = 0, None
         else: a.gB, a.g_m_indptr = gbatch[1], sp.m_indptr.data_ptr() + 4 * gbatch[0]
@@ -359,7 +386,9 @@ class Engine:
         a.loss_out = self.loss_buf.data_ptr() + 4 * loss_slot
         sharded = self.shard[1] > 1
         dp = self.world > 1 and not sharded  # data-parallel ranks all-reduce the gradient arena before Adam
-        a.train, a.run_adam = int(bool(train)), int(bool(train) and not dp)
+        in_step = dp and train and self.comm is not None  # the library exchanges the gradients itself (ntf_fnn_step_args.comm)
+        a.train, a.run_adam = int(bool(train)), int(bool(train) and (not dp or in_step))
+        a.comm, a.allreduce = (self.comm.ptr, self.comm.allreduce_addr) if in_step else (None, None)
         if train:
             a.lr, a.adam_t = float(lr), self.adam_t + 1
         pe = getattr(self, 'prof_events', None)  # (bench.py) a recorded-once torch event pair around the output-layer call
@@ -368,7 +397,7 @@ class Engine:
         graphed = self.use_graphs and neg_host is None and pe is None
         if graphed:
             # everything that is baked into the captured launches; the rest (step counter, lr, adam_t) goes through `dyn`
-            key = (a.s_indptr, a.s_indices, a.s_ent_row, a.m_indptr, a.m_indices, b0, B, a.train, a.run_adam, a.loss_out, a.loss_scale, a.gB, a.g_m_indptr)
+            key = (a.comm, a.x_dense, a.s_indptr, a.s_indices, a.s_ent_row, a.m_indptr, a.m_indices, b0, B, a.train, a.run_adam, a.loss_out, a.loss_scale, a.gB, a.g_m_indptr)
             graphed = len(self._graphs) < self.max_graphs or any(key + (ph,) in self._graphs for ph in (1, 3))
         if graphed:
             a.dyn = self.dyn.data_ptr()
@@ -378,12 +407,68 @@ class Engine:
             self._run(a, 1, key if graphed else None)
             self.allreduce(self.dact[-1][:B])
             self._run(a, 2, key if graphed else None)
+        elif in_step:
+            self._run(a, 3, key if graphed else None)
+            self.global_step += 1; self.adam_t += 1
+            return
+        elif dp and train and self.dp_overlap:
+            return self._dp_overlapped(a, key if graphed else None, lr)
         else:
             self._run(a, 3, key if graphed else None)
         self.global_step += 1
         if not train: return
         if dp: self.optimizer_step(lr)
         else: self.adam_t += 1
+
+    def attach_comm(self, comm=None):
+        """data-parallel ranks: hand the library an NCCL communicator (nccl.Comm) so that ntf_fnn_step exchanges the gradients itself --
+        two all-reduces on its own stream inside the (captured) step instead of torch.distributed calls between two halves of it."""
+        if comm is None:
+            from . import nccl
+            comm = nccl.Comm(self.rank, self.world, self.device)
+        self.comm = comm
+        self._graphs.clear()
+        return comm
+
+    def idle_step(self, train, lr=None):
+        """a data-parallel rank whose slice of a (short, last) global batch is empty: it contributes zero gradients but must take part in
+        the exchange and step its replica with the same sums.  The exchange mirrors step()'s (two segments when overlapped)."""
+        self.global_step += 1
+        if not (train and self.world > 1 and self.shard[1] == 1): return
+        self.grads.zero_()
+        if self.bayesian or not (self.dp_overlap or self.comm): return self.optimizer_step(lr)
+        split = min(self.views[f'layers.{self.L - 1}.{k}'][0] for k in ('weight', 'bias'))
+        ar = self.comm.allreduce if (self.comm and not self.bayesian) else self.allreduce
+        ar(self.grads[split:])
+        ar(self.grads[:split])
+        self.adam_t += 1
+        ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, self.n_params, lr, 0.9, 0.999, 1e-8, self.adam_t)
+
+    def _dp_overlapped(self, a, key, lr):
+        """data-parallel train step with the gradient exchange cut in two along the arena: the output layer's
+        segment (its gradients are final after phase 1) is summed over the ranks and stepped on a side stream WHILE the backward
+        pass through the hidden layers runs; the rest follows on the main stream while the side stream runs its Adam segment.
+        Adam is elementwise, so the result equals optimizer_step()'s bit for bit given the same sums."""
+        split = min(self.views[f'layers.{self.L - 1}.{k}'][0] for k in ('weight', 'bias'))
+        assert all(self.views[f'layers.{i}.{k}'][0] < split for i in range(self.L - 1) for k in ('weight', 'bias'))
+        n, t = self.n_params, self.adam_t + 1
+        main = torch.cuda.current_stream(self.device)
+        if self._dp_stream is None:
+            self._dp_stream = torch.cuda.Stream(device=self.device)
+            self._dp_ev = (torch.cuda.Event(), torch.cuda.Event())
+        self._run(a, 1, key)
+        self._dp_ev[0].record(main)
+        with torch.cuda.stream(self._dp_stream):
+            self._dp_stream.wait_event(self._dp_ev[0])
+            self.allreduce(self.grads[split:])
+            ops.adam_step(self.params[split:], self.grads[split:], self.adam_m[split:], self.adam_v[split:], n - split, lr, 0.9, 0.999, 1e-8, t)
+            self._dp_ev[1].record(self._dp_stream)
+        self._run(a, 2, key)
+        self.allreduce(self.grads[:split])
+        ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, split, lr, 0.9, 0.999, 1e-8, t)
+        main.wait_event(self._dp_ev[1])
+        self.adam_t = t
+        self.global_step += 1
 
     def _run(self, a, phase, key):
         """enqueue one phase of ntf_fnn_step: directly (key None), or as the replay of its captured graph"""
@@ -418,7 +503,7 @@ class Engine:
 
     def optimizer_step(self, lr):
         if self.world > 1:
-            torch.distributed.all_reduce(self.grads)  # sum over ranks; every rank scaled its loss by 1/B_global
+            self.allreduce(self.grads)  # sum over ranks; every rank scaled its loss by 1/B_global
         self.adam_t += 1
         ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, self.n_params, lr, 0.9, 0.999, 1e-8, self.adam_t)
 

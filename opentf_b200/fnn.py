@@ -106,18 +106,24 @@ class Fnn(Ntf):
         return sd
 
     def init(self, input_size, output_size):
-        if self.engine is None or (self.engine.S, self.engine.E_total) != (input_size, output_size):
+        dense = bool(getattr(self, '_dense_input', False))  # set by learn/test from teamsvecs['skill'] (ndarray = embedded skills, ntf.py:24)
+        if self.engine is None or (self.engine.S, self.engine.E_total, self.engine.dense_input) != (input_size, output_size, dense):
             torch = Ntf.torch
             world, rank = 1, 0
             if torch.distributed.is_available() and torch.distributed.is_initialized():
                 world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
-            # multi-GPU mode (extra knob, default 'dp'): 'dp' = data-parallel teams, 'shard' = output layer column-sharded by expert
+            # multi-GPU mode (extra knob, default 'dp'): 'dp' = data-parallel teams, 'shard' = output layer column-sharded by expert,
+            # 'none' = this process trains alone even inside a process group (what the N-GPU modes are checked against)
+            if self._c('parallel', os.environ.get('NTF_PARALLEL', 'dp')) == 'none': world, rank = 1, 0
             shard = (rank, world) if (world > 1 and self._c('parallel', os.environ.get('NTF_PARALLEL', 'dp')) == 'shard') else None
             self.engine = Engine(input_size, list(self._c('h')), output_size, self._device(), bayesian=self.is_bayesian_cls(),
                                  precision=self._c('precision', os.environ.get('NTF_PRECISION', self.precision_default)),
                                  tpw=self._c('tpw', 1), tnw=self._c('tnw', 1), nsd=self._c('nsd'), ns=self._c('ns', 5),
-                                 seed=self.seed if self.seed is not None else 0, max_batch=self._c('b'), shard=shard)
+                                 seed=self.seed if self.seed is not None else 0, max_batch=self._c('b'), shard=shard, dense_input=dense)
             self.engine.world, self.engine.rank = world, rank
+            # data-parallel Fnn: the library exchanges the gradients inside the step over its own NCCL communicator (engine.attach_comm);
+            # NTF_DP_NCCL=0 keeps the exchange in torch.distributed calls between the two halves of a step
+            if world > 1 and shard is None and not self.is_bayesian_cls() and os.environ.get('NTF_DP_NCCL', '1') != '0': self.engine.attach_comm()
         self.engine.load_state_dict(self._host_init(input_size, output_size))
         self.engine.reset_optimizer()
         self.model = DeviceModel(self.engine)
@@ -144,7 +150,7 @@ class Fnn(Ntf):
     # ---- fnn.py:78-170 ----------------------------------------------------------------------------------------
     def learn(self, teamsvecs, splits, prev_model):
         torch = Ntf.torch
-        if scipy_dense(teamsvecs['skill']): raise NotImplementedError('dense (embedded) skill input is a "next" row (SURVEY.md 8f-2)')
+        self._dense_input = scipy_dense(teamsvecs['skill'])  # main.py:148-153: skill embeddings instead of the multi-hot rows
         input_size, output_size = teamsvecs['skill'].shape[1], teamsvecs['member'].shape[1]
         b, nsd = int(self._c('b')), self._c('nsd')
         w = self.writer(log_dir=f'{self.output}/logs4tboard/run_{int(time.time())}')
@@ -175,7 +181,9 @@ class Fnn(Ntf):
                     for bi in range(nb):
                         b0, B = bi * b, min(b, sp.n - bi * b)
                         lo, hi = self._rank_slice(B)
-                        if hi <= lo: continue
+                        if hi <= lo:  # (data parallel, a last batch shorter than the number of ranks)
+                            eng.idle_step(phase == 'train', lr)
+                            continue
                         neg = None
                         if self.replay is not None:
                             neg = self.replay.neg(foldidx, e, phase, bi, sp.rows_now[b0:b0 + B])
@@ -205,14 +213,16 @@ class Fnn(Ntf):
 
     def _save(self, foldidx, e, t_loss, v_loss, path):
         sd = self.model.state_dict() if (self.engine.shard[1] > 1 or self.engine.rank == 0) else None  # (sharded: a collective gather)
-        if self.engine.rank != 0: return
-        Ntf.torch.save({'model_state_dict': sd, 'cfg': self.cfg, 'f': foldidx, 'e': e, 't_loss': t_loss, 'v_loss': v_loss}, path)
-        log.info(f'{self.name()} model with {util.cfg2str(self.cfg)} saved at {path}')
+        if self.engine.rank == 0:
+            Ntf.torch.save({'model_state_dict': sd, 'cfg': self.cfg, 'f': foldidx, 'e': e, 't_loss': t_loss, 'v_loss': v_loss}, path)
+            log.info(f'{self.name()} model with {util.cfg2str(self.cfg)} saved at {path}')
+        if self.engine.world > 1: Ntf.torch.distributed.barrier()  # the other ranks read this file next (test(), tNtf's next year)
 
     # ---- fnn.py:172-219 ---------------------------------------------------------------------------------------
     def test(self, teamsvecs, splits, testcfg):
         torch = Ntf.torch
         assert os.path.isdir(self.output), f'No folder for {self.output} exist!'
+        self._dense_input = scipy_dense(teamsvecs['skill'])
         input_size, output_size = teamsvecs['skill'].shape[1], teamsvecs['member'].shape[1]
         b = int(self._c('b'))
         topK = util.cfg_get(testcfg, 'topK')

@@ -50,6 +50,11 @@ def csr_gather(rows, n, src_indptr, src_indices, dst_indptr, dst_indices, dst_en
                                _p(dst_indptr, I32), _p(dst_indices, I32), _p(dst_ent_row, I32), p, nb), 'ntf_csr_gather')
 
 
+def rows_gather(rows, n, d, src, dst):
+    dv = _dev(src)
+    check(lib().ntf_rows_gather(_lib.ctx(dv), _stream(dv), _p(rows, I32), n, d, _p(src, F32), _p(dst, F32)), 'ntf_rows_gather')
+
+
 def csr_bag_fwd(B, indptr_ptr, indices, W0T, b0, S, h, A):
     d = _dev(W0T)
     check(lib().ntf_csr_bag_fwd(_lib.ctx(d), _stream(d), B, indptr_ptr, _p(indices, I32), _p(W0T, F32), _p(b0, F32), S, h, _p(A, F32)),

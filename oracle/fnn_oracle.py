@@ -63,8 +63,10 @@ def forward(layers, X):
 
 
 def densify(mat, rows=None):
-    """ntf.py:23: row -> dense fp32.  `mat` is scipy lil/csr uint8 (team.py:154)."""
+    """ntf.py:23: row -> dense fp32.  `mat` is scipy lil/csr uint8 (team.py:154); ntf.py:24: a dense ndarray of skill
+    embeddings (main.py:148-153) is handed through as is (`.float()`)."""
     m = mat if rows is None else mat[rows]
+    if isinstance(m, np.ndarray): return torch.as_tensor(np.ascontiguousarray(m, dtype=np.float32))
     return torch.as_tensor(np.asarray(m.todense(), dtype=np.float32))
 
 
@@ -225,6 +227,8 @@ def learn_fold(skill, member, train_rows, valid_rows, cfg, trace=None, feed=None
     Returns dict(layers, e, t_loss, v_loss, ckpt_epochs, history)."""
     S, E = skill.shape[1], member.shape[1]
     layers = cfg.get('init_layers') or init_params(S, cfg['h'], E)
+    # fnn.py:99-101: init() has drawn fresh weights (the generator advanced), THEN prev_model's checkpoint overwrites them (tNtf's warm start)
+    if cfg.get('prev_layers'): layers = cfg['prev_layers']
     layers = [(W.clone(), b.clone()) for W, b in layers]
     flat = [t for Wb in layers for t in Wb]
     opt, sched, es = Adam(flat, cfg['lr']), Plateau(), EarlyStop(cfg['es'], cfg['lr'])

@@ -27,10 +27,18 @@ for mode in ('shard', 'dp'):
         pr = torch.load(f'{m.output}/f0.test.pred', weights_only=False)['y_pred']
         res[mode] = (ck, pr, m.last_history[0])
 if rank == 0:
-    # single-process reference of the same seed
-    dist.barrier()
-else:
-    dist.barrier()
+    # single-process reference of the same seed: the whole batch on one GPU
+    cfg = dict(b=8, e=4, ns=5, lr=0.01, es=10, h=[32], spe=0, l='bce', tpw=10, tnw=1, nsd='unigram_b', precision='fp32', parallel='none')
+    m = Fnn(f'{root}/none', f'cuda:{local}', 0, cfg)
+    m.learn(tv, one, None)
+    ck1 = torch.load(f'{m.output}/f0.pt', weights_only=False)['model_state_dict']
+    for k, v in ck1.items():
+        d = (v - res['dp'][0]['model_state_dict'][k]).abs().max().item()
+        print(k, 'max |single - dp| =', d)
+        assert d < 1e-4, k
+    print('losses single', m.last_history[0][-1], 'dp', res['dp'][2][-1])
+    assert abs(m.last_history[0][-1][0] - res['dp'][2][-1][0]) < 1e-4 * abs(res['dp'][2][-1][0])
+dist.barrier()
 if rank == 0:
     a, b = res['shard'], res['dp']
     for k in a[0]['model_state_dict']:

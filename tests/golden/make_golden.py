@@ -107,11 +107,17 @@ def dump_toy(key):
     print(key, 'pairs:', len(pairs), 'bytes:', os.path.getsize(f'{HERE}/toy_{key}.npz'))
 
 
-def record_trajectory(nsd, key='dblp', seed=0, tag=None, **cfg_over):
+def dense_skill_vectors(n, d, seed=7):
+    """stand-in for the d2v/gnn skill embeddings main.py:148-153 puts in teamsvecs['skill'] (one fp32 d-vector per team)"""
+    return np.random.default_rng(seed).standard_normal((n, d)).astype(np.float32)
+
+
+def record_trajectory(nsd, key='dblp', seed=0, tag=None, dense_d=0, **cfg_over):
     """run the verbatim reference and tap (without editing it) the dataset index order, the sampler
-    output and the per-step loss."""
+    output and the per-step loss.  dense_d > 0: teamsvecs['skill'] is replaced by dense vectors (the ntf.py:24 branch)."""
     Fnn = ref_shim.load_reference_fnn()
     root, tv, sp_ = load_toy(key)
+    if dense_d: tv = dict(tv, skill=dense_skill_vectors(tv['skill'].shape[0], dense_d))
     outdir = tempfile.mkdtemp()
     cfg = ref_shim.default_cfg(nsd=nsd, **cfg_over)
     mdl = Fnn(outdir, 'cpu', seed, cfg)
@@ -149,7 +155,8 @@ def record_trajectory(nsd, key='dblp', seed=0, tag=None, **cfg_over):
     mdl.learn(tv, sp_, None)
     DS.__getitem__ = orig_getitem
 
-    out = {'seed': np.int64(seed), 'nsd': np.array(nsd), 'cfg_keys': np.array(list(cfg.keys())), 'cfg_vals': np.array([str(v) for v in cfg.values()])}
+    out = {'seed': np.int64(seed), 'nsd': np.array(nsd), 'dense_d': np.int64(dense_d), 'cfg_keys': np.array(list(cfg.keys())), 'cfg_vals': np.array([str(v) for v in cfg.values()])}
+    if dense_d: out['dense_x'] = np.asarray(tv['skill'], dtype=np.float32)  # the inputs travel with the recording
     # the DataLoader prefetches nothing with num_workers=0, so `fetched` at bxe time is exactly this batch's
     # positions WITHIN the fold's train/valid subset; translate to team row ids.
     fold_ids = list(sp_['folds'].keys())
@@ -178,8 +185,42 @@ def record_trajectory(nsd, key='dblp', seed=0, tag=None, **cfg_over):
     return out
 
 
+def record_tntf(key='gith', seed=0):
+    """the reference's temporal wrapper (tntf.py) around its Fnn, unmodified: year-by-year fine-tuning with warm starts.  nsd is unset,
+    so bxe draws nothing (fnn.py:39) and the run is a function of the seed alone -- the CUDA path is compared free-running."""
+    Fnn = ref_shim.load_reference_fnn()
+    from mdl.tntf import tNtf
+    root, tv, sp_ = load_toy(key)
+    n = tv['skill'].shape[0]
+    year_idx = [(0, 2000), (n // 3, 2001), (2 * n // 3, 2002), (n - 4, 2003)]  # 3 training intervals, the last year is for test
+    cfg = ref_shim.default_cfg(nsd=None, b=8, e=5, h=[16], lr=0.01, es=5, spe=0)
+    tcfg = ref_shim.Cfg(tfolds=2, step_ahead=1)
+    outdir = tempfile.mkdtemp()
+    inner = Fnn(outdir, 'cpu', seed, cfg)
+    w = tNtf(outdir, 'cpu', seed, tcfg, inner, year_idx)
+    splits = {'test': np.arange(year_idx[-1][0], n), 'folds': {k: {'train': None, 'valid': None} for k in range(2)}}
+    w.learn(tv, splits, None)
+    out = {'year_idx': np.array(year_idx, dtype=np.int64), 'seed': np.int64(seed)}
+    for _, year in year_idx[:-1]:
+        sp_y = pickle.load(open(f'{w.output}/{year}/splits.pkl', 'rb'))
+        for k in range(2):
+            ck = torch.load(f'{w.output}/{year}/f{k}.pt', map_location='cpu', weights_only=False)
+            for nm, t in ck['model_state_dict'].items(): out[f'{year}/f{k}/{nm}'] = t.numpy()
+            out[f'{year}/f{k}/e'] = np.int64(ck['e']); out[f'{year}/f{k}/t_loss'] = np.float64(ck['t_loss']); out[f'{year}/f{k}/v_loss'] = np.float64(ck['v_loss'])
+            out[f'{year}/f{k}/train'] = np.asarray(sp_y['folds'][k]['train'], dtype=np.int64)
+            out[f'{year}/f{k}/valid'] = np.asarray(sp_y['folds'][k]['valid'], dtype=np.int64)
+    np.savez_compressed(f'{HERE}/tntf_{key}.npz', **out)
+    print('tntf', key, {y: (int(out[f'{y}/f0/e']), float(out[f'{y}/f0/t_loss'])) for _, y in year_idx[:-1]})
+
+
 if __name__ == '__main__':
     assert ref_shim.available(), 'run this where /root/reference is mounted'
+    if sys.argv[1:] == ['tntf']:
+        record_tntf()
+        sys.exit(0)
+    if sys.argv[1:] == ['dense']:
+        record_trajectory('unigram_b', key='gith', tag='dense16', dense_d=16, b=32, h=[24], e=8, lr=0.01)
+        sys.exit(0)
     for key in TOYS: dump_toy(key)
     t = record_trajectory('unigram_b')
     committed = np.load(f'{HERE}/toy_dblp.npz')
@@ -193,3 +234,5 @@ if __name__ == '__main__':
     record_trajectory('uniform')
     record_trajectory('unigram')
     record_trajectory('unigram_b', key='imdb', tag='unigram_b_small', b=4, h=[16, 8], e=6)  # short last batches + 3 layers
+    record_trajectory('unigram_b', key='gith', tag='dense16', dense_d=16, b=32, h=[24], e=8, lr=0.01)  # dense (embedded) skill input, several batches per epoch
+    record_tntf()

@@ -158,3 +158,81 @@ def test_g3_metrics_match_committed_eval_csv(toy):
         names = list(z[f'eval/f{k}/mean_names'])
         for name, arr in m.items():
             assert abs(arr.mean() - z[f'eval/f{k}/mean_values'][names.index(name)]) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------- dense (embedded) skill input
+def test_g2_dense_skill_input_trajectory(toy):
+    """SURVEY 8f-2 / ntf.py:24: teamsvecs['skill'] as a dense [N,d] matrix of skill embeddings.  The recording is the UNMODIFIED
+    reference run on seeded dense vectors (tests/golden/make_golden.py dense); the oracle must retrace it free-running
+    (bit-equal negatives) and replayed with fed indices."""
+    _, member, splits, _ = toy('gith')
+    t = np.load(os.path.join(GOLDEN, 'traj_gith_dense16.npz'))
+    X = t['dense_x']
+    assert X.shape == (member.shape[0], int(t['dense_d']))
+    cfg = dict(b=32, e=8, ns=5, lr=0.01, es=5, h=[24], spe=10, tpw=10, tnw=1, nsd='unigram_b')
+    _seed(0)
+    for k in range(3):
+        trace = []
+        r = O.learn_fold(X, member, splits['folds'][k]['train'], splits['folds'][k]['valid'], cfg, trace=trace)
+        assert r['e'] == int(t[f'f{k}/e']) and len(trace) == len(t[f'f{k}/loss'])
+        ptr = t[f'f{k}/rows_ptr']
+        for i, (e, ph, rows, neg, loss) in enumerate(trace):
+            assert (rows == t[f'f{k}/rows'][ptr[i]:ptr[i + 1]]).all()
+            assert (neg.numpy() == t[f'f{k}/neg'][ptr[i]:ptr[i + 1]]).all()
+            assert abs(loss - t[f'f{k}/loss'][i]) <= 2e-5 * abs(loss), (k, i)
+        for i, (W, b) in enumerate(r['layers']):
+            assert np.abs(W.numpy() - t[f'f{k}/final/layers.{i}.weight']).max() < 2e-5
+    k = 0
+    cfg['init_layers'] = [(torch.from_numpy(t[f'f{k}/init/layers.{i}.weight']), torch.from_numpy(t[f'f{k}/init/layers.{i}.bias'])) for i in range(2)]
+    r = O.learn_fold(X, member, splits['folds'][k]['train'], splits['folds'][k]['valid'], cfg, feed=iter_feed(t, k))
+    assert abs(r['t_loss'] - float(t[f'f{k}/t_loss'])) < 1e-4 * r['t_loss']
+    for i, (W, b) in enumerate(r['layers']):
+        assert np.abs(W.numpy() - t[f'f{k}/final/layers.{i}.weight']).max() < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------- tNtf: year-by-year warm starts
+def test_tntf_chain_recorded_from_the_reference(toy):
+    """tntf.py:17-38 around fnn.py:99-101: every interval trains k folds starting from the previous interval's checkpoints.  The recording
+    (tests/golden/tntf_gith.npz) is the reference's own tNtf(Fnn) run, nsd unset, seed 0; the oracle retraces it from the seed alone."""
+    skill, member, _, _ = toy('gith')
+    t = np.load(os.path.join(GOLDEN, 'tntf_gith.npz'))
+    cfg = dict(b=8, e=5, ns=5, lr=0.01, es=5, h=[16], spe=0, tpw=10, tnw=1, nsd=None)
+    _seed(0)
+    prev = {}
+    for _, year in t['year_idx'][:-1]:
+        for k in range(2):
+            c = dict(cfg, prev_layers=prev.get(k))
+            r = O.learn_fold(skill, member, t[f'{year}/f{k}/train'], t[f'{year}/f{k}/valid'], c)
+            assert r['e'] == int(t[f'{year}/f{k}/e'])
+            assert abs(r['t_loss'] - float(t[f'{year}/f{k}/t_loss'])) < 1e-5 * r['t_loss']
+            for i, (W, b) in enumerate(r['layers']):
+                assert np.abs(W.numpy() - t[f'{year}/f{k}/layers.{i}.weight']).max() < 2e-5, (year, k, i)
+            prev[k] = r['layers']
+
+
+def test_tntf_wrapper_host_logic(tmp_path):
+    """opentf_b200.tntf.tNtf: interval row ranges, per-year KFold, run directories, splits.pkl, prev_model chaining and the resume rule,
+    with a recording stand-in for the wrapped model -- and the folds must be the ones the reference's tNtf produced."""
+    import pickle
+    from opentf_b200.tntf import tNtf
+    t = np.load(os.path.join(GOLDEN, 'tntf_gith.npz'))
+    year_idx = [tuple(int(v) for v in r) for r in t['year_idx']]
+
+    class Inner:
+        def __init__(self, out): self.output, self.calls = out, []
+        def learn(self, tv, splits, prev): self.calls.append((self.output, {k: (v['train'].copy(), v['valid'].copy()) for k, v in splits['folds'].items()}, prev))
+
+    inner = Inner(str(tmp_path))
+    w = tNtf(str(tmp_path), 'cpu', 0, dict(tfolds=2, step_ahead=1), inner, year_idx)
+    splits = {'test': np.arange(year_idx[-1][0], 40), 'folds': {k: {'train': None, 'valid': None} for k in range(2)}}
+    w.learn({}, splits, None)
+    assert [os.path.basename(c[0]) for c in inner.calls] == ['2000', '2001', '2002']
+    for (out, folds, prev), (_, year) in zip(inner.calls, year_idx[:-1]):
+        for k in range(2):
+            assert (folds[k][0] == t[f'{year}/f{k}/train']).all() and (folds[k][1] == t[f'{year}/f{k}/valid']).all()
+        assert os.path.exists(f'{out}/splits.pkl') and set(pickle.load(open(f'{out}/splits.pkl', 'rb'))['folds']) == {0, 1}
+    assert inner.calls[0][2] is None and inner.calls[1][2] == {0: f'{tmp_path}/2000/f0.pt', 1: f'{tmp_path}/2000/f1.pt'}
+    # resume (tntf.py:19-27): with the directories of 2000..2002 present, the first two intervals are skipped
+    inner2 = Inner(str(tmp_path))
+    tNtf(str(tmp_path), 'cpu', 0, dict(tfolds=2, step_ahead=1), inner2, year_idx).learn({}, splits, None)
+    assert [os.path.basename(c[0]) for c in inner2.calls] == ['2002']
