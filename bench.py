@@ -200,8 +200,9 @@ def run_ours(args):
     b, G = args.batch, world
     eng = Engine(S, [128], E, dev, precision=args.precision, tpw=10, tnw=1, nsd=args.nsd, ns=5, seed=0, max_batch=b)
     eng.world, eng.rank = world, rank
-    if world > 1 and os.environ.get('NTF_DP_NCCL', '1') != '0': eng.attach_comm()  # gradient exchange inside ntf_fnn_step (own NCCL communicator)
-    eng_comm = eng.comm is not None
+    xmode = os.environ.get('NTF_DP_EXCHANGE', 'peer')  # how data-parallel ranks exchange gradients (opentf_b200/fnn.py: Fnn.init)
+    if world > 1 and xmode == 'peer': eng.attach_peers()
+    elif world > 1 and xmode == 'nccl': eng.attach_comm()
     eng.stage(tv['skill'], tv['member'])
     torch.manual_seed(0)
     lin = [torch.nn.Linear(S, 128), torch.nn.Linear(128, E)]
@@ -310,6 +311,7 @@ def run_ours(args):
         del eng, sp, test_sp, scores
         torch.cuda.empty_cache()
         extras['bnn_train'] = bnn_leg(args, dev, world, rank, sync, dist)
+        extras['batch_sweep'] = batch_sweep(args, tv, splits, dev, world, rank, sync, dist)
     if rank != 0:
         if world > 1: dist.destroy_process_group()
         return
@@ -333,8 +335,9 @@ def run_ours(args):
            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': host.h2d_bytes, 'd2h_bytes_per_step': 4,
                    'api': 'Engine.step_host: pinned batch CSR block -> one H2D copy -> ntf_fnn_step (replayed as a CUDA graph) -> loss.item()'},
            'gpu_launches': launches, 'cuda_graphs': bool(graphs),
-           'dp_exchange': None if G == 1 else ('ncclAllReduce inside ntf_fnn_step: 2 overlapped arena segments, captured in the step graph' if eng_comm else
-                                               'torch.distributed.all_reduce between the halves of a step'), 'host_enqueue_ms_per_step': host_ms, 'roofline': roof, 'infer_topk': {'k': args.infer_k, 'value': infer_value, 'unit': 'teams/s', 'batch': ib}}
+           'dp_exchange': None if G == 1 else {'peer': 'reduce-scatter + Adam + all-gather fused in one pass over peer memory inside ntf_fnn_step (csrc/peer.cu), 2 overlapped arena segments',
+                                               'nccl': 'ncclAllReduce inside ntf_fnn_step: 2 overlapped arena segments, captured in the step graph'}.get(
+                                                   xmode, 'torch.distributed.all_reduce between the halves of a step'), 'host_enqueue_ms_per_step': host_ms, 'roofline': roof, 'infer_topk': {'k': args.infer_k, 'value': infer_value, 'unit': 'teams/s', 'batch': ib}}
     out.update(extras)
     if not args.no_cpu_baseline:
         v, n, dt, threads = cpu_reference_steps(tv, splits, b, args.nsd, args.cpu_baseline_seconds)
@@ -355,6 +358,7 @@ def bnn_leg(args, dev, world, rank, sync, dist):
     b, gB = args.batch, args.batch * world
     eng = Engine(S, [128], E, dev, bayesian=True, precision=args.precision, tpw=10, tnw=1, nsd=args.nsd, ns=5, seed=0, max_batch=b)
     eng.world, eng.rank = world, rank
+    if world > 1 and os.environ.get('NTF_DP_EXCHANGE', 'peer') == 'peer': eng.attach_peers()
     eng.stage(tv['skill'], tv['member'])
     g = torch.Generator().manual_seed(0)
     sd = {}
@@ -390,6 +394,51 @@ def bnn_leg(args, dev, world, rank, sync, dist):
             'workload': f'imdb-shaped synthetic teamsvecs (BASELINE configs[2]): N={N} S={S} E={E}, Bnn h=[128], nsd={args.nsd}, ns=5', 'batch_per_gpu': b,
             'steps': steps, 'ms_per_step': ms / steps, 'gpu_launches_per_step': launches / steps, 'precision': prec, 'last_loss': loss,
             'output_layer_tflops_if_alone': flops / (ms / steps * 1e-3) / 1e12}
+
+
+def batch_sweep(args, tv, splits, dev, world, rank, sync, dist):
+    """the same Fnn workload at larger batches (b = 4096, 16384 teams per GPU).  At the reference's default b=1000 the dense
+    Adam pass over 8.96 M parameters (251 MB of HBM traffic per step) is a fixed cost per STEP; larger batches amortise it."""
+    import torch
+    from opentf_b200 import _lib
+    from opentf_b200.engine import Engine
+    N, S = tv['skill'].shape; E = tv['member'].shape[1]
+    rows = np.asarray(splits['folds'][0]['train'])
+    out = []
+    for b in (4096, 16384):
+        gB = b * world
+        if len(rows) < gB: continue
+        eng = Engine(S, [128], E, dev, precision=args.precision, tpw=10, tnw=1, nsd=args.nsd, ns=5, seed=0, max_batch=b)
+        eng.world, eng.rank = world, rank
+        if world > 1 and os.environ.get('NTF_DP_EXCHANGE', 'peer') == 'peer': eng.attach_peers()
+        eng.stage(tv['skill'], tv['member'])
+        torch.manual_seed(0)
+        lin = [torch.nn.Linear(S, 128), torch.nn.Linear(128, E)]
+        for m in lin: torch.nn.init.xavier_uniform_(m.weight)
+        eng.load_state_dict({f'layers.{i}.{n}': getattr(m, n).detach() for i, m in enumerate(lin) for n in ('weight', 'bias')})
+        sp = eng.split(rows[np.random.default_rng(0).permutation(len(rows))])
+        nb = sp.n // gB
+        steps = max(1, min(args.steps, 100))
+
+        def one(i):
+            g0 = (i % nb) * gB
+            eng.step(sp, g0 + rank * b, b, True, lr=1e-3, loss_slot=i % nb, loss_scale=1.0 / gB, gbatch=(g0, gB))
+
+        for i in range(nb + 3): one(i)  # (captures every batch's graph, then warm)
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps): one(i)
+        e1.record()
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out.append({'batch_per_gpu': b, 'value': steps * gB / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / steps, 'steps': steps,
+                    'precision': 'tf32' if eng.precision == _lib.NTF_TF32 else 'fp32', 'output_layer_tflops_if_alone': 6.0 * 128 * E * b / (ms / steps * 1e-3) / 1e12})
+        del eng, sp
+        torch.cuda.empty_cache()
+    return out
 
 
 def topk_sweep(eng, test_sp, dev, sync, G):

@@ -259,6 +259,35 @@ int ntf_dense_flipout_fwd(ntf_ctx* ctx, void* stream, const float* A, const floa
 /* Y[n,c] += X[n,c] * (bit(n,c) ? -1 : +1) */
 int ntf_add_signed(ntf_ctx* ctx, void* stream, const float* X, const uint32_t* bits, int pitch_words, int B, int h, float* Y);
 
+/* ---- data-parallel ranks: gradient exchange + optimiser in one pass over peer memory ---------------------------------
+ * Replaces "all-reduce the gradients, then torch.optim.Adam on every rank" (fnn.py:137-139 under data parallelism): rank r owns the
+ * r-th slice of the flat arena; it sums that slice of every rank's gradients straight out of the peers' arenas (NVLink loads, rank
+ * order), applies Adam to its slice of (p, m, v) and stores the new parameters into EVERY rank's arena (peer stores) -- reduce-scatter,
+ * optimiser and all-gather fused, between two flag barriers in peer memory.  Per rank 4P(G-1)/G bytes each way over the links and 28P/G
+ * bytes of HBM; m/v are only ever touched on the owner's slice.  The replicas stay bit-identical (one rank computes each element).
+ * Arenas and flag blocks are cudaMalloc blocks of the owning process, made visible to the others through CUDA IPC:
+ *   ntf_peer_alloc (zeroed) / ntf_peer_free; ntf_peer_export -> 64-byte handle (send it to the other processes by any means);
+ *   ntf_peer_import -> the address of that block in this process / ntf_peer_release. */
+#define NTF_MAX_PEERS 8
+#define NTF_PEER_HANDLE_BYTES 64
+#define NTF_PEER_FLAG_BYTES 256
+typedef struct {
+  int rank, world;
+  float* grads[NTF_MAX_PEERS];     /* gradient arena of every rank, as addressed from THIS process (own arena included)  */
+  float* params[NTF_MAX_PEERS];    /* parameter arena of every rank                                                      */
+  uint32_t* flags[NTF_MAX_PEERS];  /* NTF_PEER_FLAG_BYTES per rank, zero before the first exchange                       */
+} ntf_peers;
+int ntf_peer_alloc(ntf_ctx* ctx, size_t bytes, void** out);
+int ntf_peer_free(ntf_ctx* ctx, void* p);
+int ntf_peer_export(ntf_ctx* ctx, void* p, void* handle64);
+int ntf_peer_import(ntf_ctx* ctx, const void* handle64, void** out);
+int ntf_peer_release(ntf_ctx* ctx, void* imported);
+/* floats [offset, offset+n) of the arenas (multiples of 4); every rank calls it with the same arguments, stream-ordered after its
+ * gradients are complete.  Returns once enqueued; the parameters are consistent on every rank when the call's work completes.
+ * channel (0|1): exchanges that may be in flight at the same time (different streams) must use different channels (flag sets). */
+int ntf_peer_exchange_adam(ntf_ctx* ctx, void* stream, const ntf_peers* peers, float* adam_m, float* adam_v, size_t offset, size_t n,
+                           double lr, double beta1, double beta2, double eps, int64_t step, int channel);
+
 /* ---- one whole Fnn batch, enqueued by one call: the loop body of fnn.py:118-151 -------------------------------------------------
  * forward (CSR bag, hidden layers), negative sampling (unless neg_given), output layer forward + weighted BCE; and when `train`:
  * the backward pass and (when `run_adam`) the Adam step.  Exactly the sequence of the entry points above; nothing is synchronised. */
@@ -309,6 +338,8 @@ typedef struct {
                                         arena over the ranks itself, in two segments on its own stream -- the output layer's while the
                                         hidden layers' backward runs, the rest while the output layer's segment is stepped -- so the
                                         whole data-parallel step is ONE capturable launch sequence.  The library does not link NCCL. */
+  const ntf_peers* peers;            /* data-parallel ranks, preferred over comm: the exchange and Adam run as ntf_peer_exchange_adam inside
+                                        the step (train, phase 3, run_adam), the output layer's segment next to the hidden layers' backward */
   const float* x_dense;              /* dense (embedded) skill input, ntf.py:24: [B,S] rows of this batch.  Non-NULL: layer 0 is a dense
                                         layer (ntf_dense_fwd / ntf_dense_bwd), W[0] / gW[0] are in torch layout [h0,S], s_* unused */
 } ntf_fnn_step_args;

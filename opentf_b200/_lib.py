@@ -28,6 +28,14 @@ NTF_MAX_LAYERS = 8
 _PA = vp * NTF_MAX_LAYERS
 
 
+NTF_MAX_PEERS = 8
+
+
+class Peers(C.Structure):
+    """mirror of ntf_peers"""
+    _fields_ = [('rank', i32), ('world', i32), ('grads', vp * NTF_MAX_PEERS), ('params', vp * NTF_MAX_PEERS), ('flags', vp * NTF_MAX_PEERS)]
+
+
 class FnnStepArgs(C.Structure):
     """mirror of ntf_fnn_step_args"""
     _fields_ = [('n_layers', i32), ('S', i32), ('E', i32), ('e_lo', i32), ('E_total', i32), ('phase', i32), ('hidden', i32 * NTF_MAX_LAYERS),
@@ -37,7 +45,7 @@ class FnnStepArgs(C.Structure):
                 ('neg', vp), ('counts', vp), ('cdf', vp), ('precision', i32), ('tpw', f32), ('tnw', f32), ('loss_scale', f32), ('loss_out', vp),
                 ('special', vp), ('pitch_words', i32), ('special_t', vp), ('member_t', vp), ('train', i32), ('run_adam', i32),
                 ('params', vp), ('grads', vp), ('adam_m', vp), ('adam_v', vp), ('n_params', sz),
-                ('lr', f64), ('beta1', f64), ('beta2', f64), ('eps', f64), ('adam_t', i64), ('prof_ev', vp * 2), ('dyn', vp), ('comm', vp), ('allreduce', vp), ('x_dense', vp)]
+                ('lr', f64), ('beta1', f64), ('beta2', f64), ('eps', f64), ('adam_t', i64), ('prof_ev', vp * 2), ('dyn', vp), ('comm', vp), ('allreduce', vp), ('peers', vp), ('x_dense', vp)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/ntf_b200.h (tests/test_abi.py checks it)
@@ -56,6 +64,12 @@ SIGNATURES = {
     'ntf_graph_destroy': (i32, [vp]),
     'ntf_csr_gather_workspace_bytes': (sz, [i32]),
     'ntf_csr_gather': (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz]),
+    'ntf_peer_alloc': (i32, [vp, sz, C.POINTER(vp)]),
+    'ntf_peer_free': (i32, [vp, vp]),
+    'ntf_peer_export': (i32, [vp, vp, vp]),
+    'ntf_peer_import': (i32, [vp, vp, C.POINTER(vp)]),
+    'ntf_peer_release': (i32, [vp, vp]),
+    'ntf_peer_exchange_adam': (i32, [vp, vp, vp, vp, vp, sz, sz, f64, f64, f64, f64, i64, i32]),
     'ntf_rows_gather': (i32, [vp, vp, vp, i32, i32, vp, vp]),
     'ntf_csr_bag_fwd': (i32, [vp, vp, i32, vp, vp, vp, vp, i32, i32, vp]),
     'ntf_csr_bag_bwd_workspace_bytes': (sz, [i32, i32]),

@@ -7,20 +7,6 @@
 #include "common.cuh"
 
 namespace {
-struct AdamK { float one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, neg_step; };
-
-AdamK adam_consts(double lr, double beta1, double beta2, double eps, int64_t step) {
-  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
-  return AdamK{(float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)sqrt(bc2), (float)eps, (float)(-(lr / bc1))};
-}
-
-__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamK& k) {
-  m = m + k.one_minus_b1 * (g - m);
-  v = v * k.b2;
-  v = v + (k.one_minus_b2 * g) * g;
-  const float denom = sqrtf(v) / k.bc2_sqrt + k.eps;
-  p = p + k.neg_step * (m / denom);
-}
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, size_t n4, size_t n, AdamK k, const ntf_dyn* __restrict__ dyn) {

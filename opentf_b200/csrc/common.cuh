@@ -1,6 +1,7 @@
 // common.cuh -- shared helpers for libntf_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -98,6 +99,23 @@ __device__ __forceinline__ float sigmoid_lrelu(float z) {
     return x >= 0.f ? r : e * r;
   }
   return 1.f / (1.f + expf(-x));  // torch.sigmoid's fp32 formula
+}
+
+// torch.optim.Adam's single-tensor update (fnn.py:104,139), one element:  m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2);
+// denom = sqrt(v)/sqrt(bc2) + eps; p.addcdiv_(m, denom, -lr/bc1).  Every operation rounded on its own (no fused multiply-add), written
+// with explicit-rounding intrinsics so that every kernel
+// that steps parameters (adam.cu, peer.cu) performs the SAME operations -- the compiler may not re-associate or fuse them differently
+// from one kernel to the next, and data-parallel replicas / single-GPU runs stay bit-comparable.
+struct AdamK { float one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, neg_step; };
+static inline AdamK adam_consts(double lr, double beta1, double beta2, double eps, int64_t step) {
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  return AdamK{(float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)sqrt(bc2), (float)eps, (float)(-(lr / bc1))};
+}
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamK& k) {
+  m = __fadd_rn(m, __fmul_rn(k.one_minus_b1, __fsub_rn(g, m)));
+  v = __fadd_rn(__fmul_rn(v, k.b2), __fmul_rn(__fmul_rn(k.one_minus_b2, g), g));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), k.bc2_sqrt), k.eps);
+  p = __fadd_rn(p, __fmul_rn(k.neg_step, __fdiv_rn(m, denom)));
 }
 
 // is expert j a member of team `row`?  (member rows are short: 2-10 entries, sorted)

@@ -25,6 +25,9 @@ int ntf_csr_bag_bwd_reduce_impl(ntf_ctx* ctx, cudaStream_t st, int B, const int3
                                 int row_base, const float* dZ, int S, int h, float* dW0T, void* workspace, size_t workspace_bytes,
                                 const uint32_t* ent_sign);
 
+int ntf_peer_exchange_adam_impl(ntf_ctx* ctx, cudaStream_t st, const ntf_peers* pr, float* adam_m, float* adam_v, size_t off, size_t n, double lr,
+                                double beta1, double beta2, double eps, int64_t step, const ntf_dyn* dyn, int channel);
+
 static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 
 // workspace = [ input-layer backward (slots, lives from the fork to the end of the step) | everything that runs on the main stream ]
@@ -127,7 +130,10 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
   // data-parallel ranks: sum the gradients over the ranks before they are stepped (ncclAllReduce, in place, fp32 sum) -- on the
   // communication stream, so that the exchange of the output layer's segment hides behind the hidden layers' backward pass and
   // its Adam step behind the exchange of the rest
-  const bool dp = a->comm != nullptr;
+  const bool peers = a->peers != nullptr;  // exchange + Adam fused over peer memory (peer.cu); takes precedence over comm
+  NTF_REQUIRE(!peers || (a->run_adam && phase == 3 && a->peers->params[a->peers->rank] == a->params && a->peers->grads[a->peers->rank] == a->grads),
+              NTF_ERR_BAD_ARG, "fnn_step: peers needs run_adam, phase 3 and this rank's own arenas in the table");
+  const bool dp = a->comm != nullptr && !peers;
   NTF_REQUIRE(!dp || (a->allreduce && a->run_adam && phase == 3), NTF_ERR_BAD_ARG, "fnn_step: comm needs allreduce, run_adam and phase 3");
   const ntf_allreduce_fn allreduce = (ntf_allreduce_fn)a->allreduce;
 #define ALLREDUCE(ptr, count)                                                                                               \
@@ -144,6 +150,9 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
       NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_ar[0], 0));
     } else
     NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork_opt, 0));
+    if (peers) STEP(ntf_peer_exchange_adam_impl(ctx, ctx->side[0], a->peers, a->adam_m, a->adam_v, opt_split, a->n_params - opt_split, a->lr, a->beta1,
+                                                a->beta2, a->eps, a->adam_t, a->dyn, 1));
+    else
     STEP(ntf_adam_step_impl(ctx, ctx->side[0], a->params + opt_split, a->grads + opt_split, a->adam_m + opt_split, a->adam_v + opt_split,
                             a->n_params - opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn));
     NTF_CUDA(cudaEventRecord(ctx->ev_join_opt, ctx->side[0]));
@@ -169,6 +178,8 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_ar[1], 0));
   }
 #undef ALLREDUCE
+  if (peers) STEP(ntf_peer_exchange_adam_impl(ctx, st, a->peers, a->adam_m, a->adam_v, 0, opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn, 0));
+  else
   if (a->run_adam) STEP(ntf_adam_step_impl(ctx, st, a->params, a->grads, a->adam_m, a->adam_v, opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn));
   if (opt_split < a->n_params) NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_join_opt, 0));
 #undef STEP

@@ -186,6 +186,7 @@ class Engine:
         self.dp_overlap = os.environ.get('NTF_DP_OVERLAP', '1') != '0'
         self._dp_stream = self._dp_ev = None
         self.comm = None  # nccl.Comm: the library then runs the exchange inside ntf_fnn_step (attach_comm)
+        self.peers = None  # _lib.Peers: exchange + Adam fused over peer memory inside ntf_fnn_step (attach_peers); preferred over comm
 
     # ------------------------------------------------------------------ memory
     def _layout(self):
@@ -386,9 +387,10 @@ class Engine:
         a.loss_out = self.loss_buf.data_ptr() + 4 * loss_slot
         sharded = self.shard[1] > 1
         dp = self.world > 1 and not sharded  # data-parallel ranks all-reduce the gradient arena before Adam
-        in_step = dp and train and self.comm is not None  # the library exchanges the gradients itself (ntf_fnn_step_args.comm)
+        in_step = dp and train and (self.comm is not None or self.peers is not None)  # the library exchanges the gradients itself
         a.train, a.run_adam = int(bool(train)), int(bool(train) and (not dp or in_step))
-        a.comm, a.allreduce = (self.comm.ptr, self.comm.allreduce_addr) if in_step else (None, None)
+        a.comm, a.allreduce = (self.comm.ptr, self.comm.allreduce_addr) if (in_step and self.peers is None) else (None, None)
+        a.peers = C.addressof(self.peers) if (in_step and self.peers is not None) else None
         if train:
             a.lr, a.adam_t = float(lr), self.adam_t + 1
         pe = getattr(self, 'prof_events', None)  # (bench.py) a recorded-once torch event pair around the output-layer call
@@ -397,7 +399,7 @@ class Engine:
         graphed = self.use_graphs and neg_host is None and pe is None
         if graphed:
             # everything that is baked into the captured launches; the rest (step counter, lr, adam_t) goes through `dyn`
-            key = (a.comm, a.x_dense, a.s_indptr, a.s_indices, a.s_ent_row, a.m_indptr, a.m_indices, b0, B, a.train, a.run_adam, a.loss_out, a.loss_scale, a.gB, a.g_m_indptr)
+            key = (a.comm, a.peers, a.x_dense, a.s_indptr, a.s_indices, a.s_ent_row, a.m_indptr, a.m_indices, b0, B, a.train, a.run_adam, a.loss_out, a.loss_scale, a.gB, a.g_m_indptr)
             graphed = len(self._graphs) < self.max_graphs or any(key + (ph,) in self._graphs for ph in (1, 3))
         if graphed:
             a.dyn = self.dyn.data_ptr()
@@ -430,12 +432,71 @@ class Engine:
         self._graphs.clear()
         return comm
 
+    def attach_peers(self, local=None):
+        """data-parallel ranks: move the parameter and gradient arenas into IPC-shareable blocks, exchange the handles over the existing
+        process group and hand the library the table of every rank's arenas (ntf_peers): the step then runs reduce-scatter + Adam +
+        all-gather as one pass over peer memory (csrc/peer.cu) -- no NCCL on the data path.  `local`: engines of all ranks living in THIS
+        process on this GPU (tests: two ranks on one device, on different streams); their arenas are addressed directly."""
+        d = self.dev_index
+        if getattr(self, '_peer_blocks', None) is None:
+            new_p, pp = ops.peer_alloc(d, self.n_params, torch.float32)
+            new_g, pg = ops.peer_alloc(d, self.n_params, torch.float32)
+            fl, pf = ops.peer_alloc(d, 64, torch.int32)  # NTF_PEER_FLAG_BYTES
+            new_p.copy_(self.params); new_g.copy_(self.grads)
+            self.params, self.grads, self._peer_flags = new_p, new_g, fl
+            self._peer_blocks = (pp, pg, pf)
+            self._fa = None
+            self._graphs.clear()
+        torch.cuda.synchronize(self.device)
+        if local is not None:
+            if any(getattr(e, '_peer_blocks', None) is None for e in local): return None  # (the last engine of the list builds every table)
+            for e in local:
+                t = _lib.Peers()
+                t.rank, t.world = e.rank, len(local)
+                for r, o in enumerate(local): t.params[r], t.grads[r], t.flags[r] = o._peer_blocks
+                e.peers = t
+            return self.peers
+        handles = tuple(ops.peer_export(d, p) for p in self._peer_blocks)
+        got = [None] * self.world
+        torch.distributed.all_gather_object(got, handles)
+        t = _lib.Peers()
+        t.rank, t.world = self.rank, self.world
+        self._imported = []
+        for r, hs in enumerate(got):
+            if r == self.rank: ptrs = self._peer_blocks
+            else:
+                ptrs = tuple(ops.peer_import(d, h) for h in hs)
+                self._imported += list(ptrs)
+            t.params[r], t.grads[r], t.flags[r] = ptrs
+        torch.distributed.barrier()  # every rank has opened every block before anyone signals through it
+        self.peers = t
+        return t
+
+    def peer_error(self):
+        """non-zero if a barrier of the peer exchange gave up waiting (a rank died or fell out of step)"""
+        return 0 if self.peers is None else int(self._peer_flags[36].item())
+
+    def _peer_exchange(self, lr):
+        """the eager counterpart of what ntf_fnn_step does with `peers`: output layer's segment on channel 1, the rest on channel 0"""
+        split = min(self.views[f'layers.{self.L - 1}.{k}'][0] for k in self._last_kinds())
+        t = self.adam_t + 1
+        if split % 4 == 0 and 0 < split < self.n_params:
+            ops.peer_exchange_adam(self.dev_index, self.peers, self.adam_m, self.adam_v, split, self.n_params - split, lr, 0.9, 0.999, 1e-8, t, 1)
+            ops.peer_exchange_adam(self.dev_index, self.peers, self.adam_m, self.adam_v, 0, split, lr, 0.9, 0.999, 1e-8, t, 0)
+        else:
+            ops.peer_exchange_adam(self.dev_index, self.peers, self.adam_m, self.adam_v, 0, self.n_params, lr, 0.9, 0.999, 1e-8, t, 0)
+        self.adam_t = t
+
+    def _last_kinds(self):
+        return ('mu_weight', 'rho_weight', 'mu_bias', 'rho_bias') if self.bayesian else ('weight', 'bias')
+
     def idle_step(self, train, lr=None):
         """a data-parallel rank whose slice of a (short, last) global batch is empty: it contributes zero gradients but must take part in
         the exchange and step its replica with the same sums.  The exchange mirrors step()'s (two segments when overlapped)."""
         self.global_step += 1
         if not (train and self.world > 1 and self.shard[1] == 1): return
         self.grads.zero_()
+        if self.peers is not None: return self._peer_exchange(lr)
         if self.bayesian or not (self.dp_overlap or self.comm): return self.optimizer_step(lr)
         split = min(self.views[f'layers.{self.L - 1}.{k}'][0] for k in ('weight', 'bias'))
         ar = self.comm.allreduce if (self.comm and not self.bayesian) else self.allreduce
@@ -502,6 +563,7 @@ class Engine:
         self._graphs.clear()
 
     def optimizer_step(self, lr):
+        if self.world > 1 and self.peers is not None: return self._peer_exchange(lr)  # exchange + Adam in one pass over peer memory
         if self.world > 1:
             self.allreduce(self.grads)  # sum over ranks; every rank scaled its loss by 1/B_global
         self.adam_t += 1

@@ -121,9 +121,14 @@ class Fnn(Ntf):
                                  tpw=self._c('tpw', 1), tnw=self._c('tnw', 1), nsd=self._c('nsd'), ns=self._c('ns', 5),
                                  seed=self.seed if self.seed is not None else 0, max_batch=self._c('b'), shard=shard, dense_input=dense)
             self.engine.world, self.engine.rank = world, rank
-            # data-parallel Fnn: the library exchanges the gradients inside the step over its own NCCL communicator (engine.attach_comm);
-            # NTF_DP_NCCL=0 keeps the exchange in torch.distributed calls between the two halves of a step
-            if world > 1 and shard is None and not self.is_bayesian_cls() and os.environ.get('NTF_DP_NCCL', '1') != '0': self.engine.attach_comm()
+            # data-parallel ranks: how the gradients are exchanged (extra knob `exchange` / NTF_DP_EXCHANGE):
+            #   'peer'  (default) reduce-scatter + Adam + all-gather as one pass over peer memory inside the step (csrc/peer.cu)
+            #   'nccl'  ncclAllReduce on the library's own communicator inside the step (Fnn only)
+            #   'torch' torch.distributed.all_reduce between the two halves of a step
+            if world > 1 and shard is None:
+                mode = self._c('exchange', os.environ.get('NTF_DP_EXCHANGE', 'peer'))
+                if mode == 'peer': self.engine.attach_peers()
+                elif mode == 'nccl' and not self.is_bayesian_cls(): self.engine.attach_comm()
         self.engine.load_state_dict(self._host_init(input_size, output_size))
         self.engine.reset_optimizer()
         self.model = DeviceModel(self.engine)

@@ -50,6 +50,42 @@ def csr_gather(rows, n, src_indptr, src_indices, dst_indptr, dst_indices, dst_en
                                _p(dst_indptr, I32), _p(dst_indices, I32), _p(dst_ent_row, I32), p, nb), 'ntf_csr_gather')
 
 
+# ---- peer memory (data-parallel ranks): include/ntf_b200.h "gradient exchange + optimiser in one pass over peer memory"
+class _RawCuda:
+    """a cudaMalloc block of the library seen as a torch tensor (zero copy, __cuda_array_interface__)"""
+
+    def __init__(self, ptr, shape, typestr):
+        self.ptr = ptr
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (ptr, False), 'version': 2}
+
+
+def peer_alloc(dev_index, n, dtype):
+    """-> (tensor of n zeros living in an IPC-exportable cudaMalloc block, raw pointer)"""
+    ptr = _lib.vp()
+    item = 4
+    check(lib().ntf_peer_alloc(_lib.ctx(dev_index), n * item, _lib.C.byref(ptr)), 'ntf_peer_alloc')
+    t = torch.as_tensor(_RawCuda(ptr.value, (n,), '<f4' if dtype == torch.float32 else '<i4'), device=torch.device('cuda', dev_index))
+    assert t.data_ptr() == ptr.value
+    return t, ptr.value
+
+
+def peer_export(dev_index, ptr):
+    h = _lib.C.create_string_buffer(64)
+    check(lib().ntf_peer_export(_lib.ctx(dev_index), ptr, h), 'ntf_peer_export')
+    return h.raw
+
+
+def peer_import(dev_index, handle):
+    out = _lib.vp()
+    check(lib().ntf_peer_import(_lib.ctx(dev_index), _lib.C.create_string_buffer(handle, 64), _lib.C.byref(out)), 'ntf_peer_import')
+    return out.value
+
+
+def peer_exchange_adam(dev_index, peers, m, v, offset, n, lr, b1, b2, eps, step, channel):
+    check(lib().ntf_peer_exchange_adam(_lib.ctx(dev_index), _stream(dev_index), _lib.C.addressof(peers), _p(m, F32), _p(v, F32), offset, n, lr, b1, b2,
+                                       eps, step, channel), 'ntf_peer_exchange_adam')
+
+
 def rows_gather(rows, n, d, src, dst):
     dv = _dev(src)
     check(lib().ntf_rows_gather(_lib.ctx(dv), _stream(dv), _p(rows, I32), n, d, _p(src, F32), _p(dst, F32)), 'ntf_rows_gather')

@@ -332,7 +332,7 @@ def test_adam_matches_torch_semantics(ops):
         adam.step([g])
         ops.adam_step(mine, g.to(DEV), m, v, n, 1e-3, 0.9, 0.999, 1e-8, t)
     assert rel_err(mine.cpu(), ref[0]) < 1e-6
-    assert (mine.cpu() - ref[0]).abs().max() < 2e-7
+    assert (mine.cpu() - ref[0]).abs().max() < 3e-7  # one ulp at the largest |p| (in [2,4)) after 7 steps
 
 
 # ------------------------------------------------------------------------------------------------ inference + ranking
