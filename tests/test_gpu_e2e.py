@@ -196,3 +196,30 @@ def test_step_host_is_the_same_step_as_the_resident_path(toy):
         out.append((losses, eng.params.cpu().clone()))
     assert np.array_equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
     assert out[0][0][2] < out[0][0][0]
+
+
+# ---------------------------------------------------------------------------------------------- tNtf: year-by-year fine-tuning
+def test_tntf_chain_retraces_the_reference_run(toy, tmp_path):
+    """opentf_b200.tntf.tNtf around opentf_b200.fnn.Fnn, free-running from seed 0 (nsd unset: nothing is drawn in bxe), against the run of
+    the reference's OWN tNtf(Fnn) recorded in tests/golden/tntf_gith.npz: per year and fold the same stop epoch, epoch losses to 1e-5
+    relative and final weights to 2e-5 -- every year starts from the previous year's checkpoint (fnn.py:101) and the host generator is
+    consumed in the reference's order across the whole chain."""
+    from opentf_b200.tntf import tNtf
+    tv, _, _ = teamsvecs(toy, 'gith')
+    t = np.load(os.path.join(GOLDEN, 'tntf_gith.npz'))
+    year_idx = [tuple(int(v) for v in r) for r in t['year_idx']]
+    cfg = base_cfg(nsd=None, b=8, e=5, h=[16], lr=0.01, es=5, spe=0)
+    inner = make(tmp_path, cfg)
+    w = tNtf(str(tmp_path), 'cuda:0', 0, dict(tfolds=2, step_ahead=1), inner, year_idx)
+    splits = {'test': np.arange(year_idx[-1][0], tv['skill'].shape[0]), 'folds': {k: {'train': None, 'valid': None} for k in range(2)}}
+    w.learn(tv, splits, None)
+    for _, year in year_idx[:-1]:
+        for k in range(2):
+            ck = torch.load(f'{w.output}/{year}/f{k}.pt', weights_only=False)
+            assert ck['e'] == int(t[f'{year}/f{k}/e'])
+            assert abs(ck['t_loss'] - float(t[f'{year}/f{k}/t_loss'])) <= 1e-5 * ck['t_loss']
+            assert abs(ck['v_loss'] - float(t[f'{year}/f{k}/v_loss'])) <= 1e-5 * ck['v_loss']
+            for n_, wt in ck['model_state_dict'].items():
+                assert np.abs(wt.numpy() - t[f'{year}/f{k}/{n_}']).max() < 2e-5, (year, k, n_)
+    w.test(tv, splits, dict(on_train=False, per_epoch=False, topK=None))  # the wrapped model tests from the LAST year's directory
+    assert os.path.exists(f'{w.output}/{year_idx[-2][1]}/f0.test.pred')
