@@ -67,6 +67,10 @@ typedef struct {
 /* writes the block (device memory, caller-owned) for the step about to run; stream-ordered, one tiny launch */
 int ntf_dyn_update(ntf_ctx* ctx, void* stream, ntf_dyn* dyn, uint64_t step, double lr, double beta1, double beta2, double eps,
                    int64_t adam_t);
+/* host-driven sequences (the Bnn step is ~45 separate calls): while a block is set on the handle, ntf_fill_normal, ntf_fill_sign_bits,
+ * ntf_neg_sample, ntf_adam_step and ntf_peer_exchange_adam enqueue kernels that read `step` / the Adam constants from it instead of
+ * their host arguments, so a sequence captured between ntf_graph_begin/end replays with this step's values.  NULL clears it. */
+int ntf_set_dyn(ntf_ctx* ctx, const ntf_dyn* dyn);
 /* capture everything this library enqueues on `stream` between begin and end (thread-local capture mode) into an executable
  * graph; replaying it costs the host one call.  The calls in between must get the same buffers at every replay. */
 typedef struct ntf_graph ntf_graph;

@@ -57,6 +57,7 @@ SIGNATURES = {
     'ntf_sm_count': (i32, [vp]),
     'ntf_launch_count': (C.c_ulonglong, [i32]),
     'ntf_dyn_update': (i32, [vp, vp, vp, u64, f64, f64, f64, f64, i64]),
+    'ntf_set_dyn': (i32, [vp, vp]),
     'ntf_graph_begin': (i32, [vp, vp]),
     'ntf_graph_end': (i32, [vp, vp, C.POINTER(vp)]),
     'ntf_graph_launch': (i32, [vp, vp]),

@@ -40,7 +40,7 @@ int ntf_adam_step_impl(ntf_ctx* ctx, cudaStream_t st, float* p, const float* g, 
 
 extern "C" int ntf_adam_step(ntf_ctx* ctx, void* stream, float* p, const float* g, float* m, float* v, size_t n, double lr,
                              double beta1, double beta2, double eps, int64_t step) {
-  return ntf_adam_step_impl(ctx, as_stream(stream), p, g, m, v, n, lr, beta1, beta2, eps, step, nullptr);
+  return ntf_adam_step_impl(ctx, as_stream(stream), p, g, m, v, n, lr, beta1, beta2, eps, step, ctx ? ctx->dyn_override : nullptr);
 }
 
 namespace {

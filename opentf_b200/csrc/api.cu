@@ -40,6 +40,7 @@ extern "C" int ntf_create(int device, ntf_ctx** out) {
   c->cc_minor = prop.minor;
   c->smem_optin = prop.sharedMemPerBlockOptin;
   c->encode_tiled = nullptr;
+  c->dyn_override = nullptr;
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -77,6 +78,12 @@ extern "C" int ntf_destroy(ntf_ctx* ctx) {
     cudaStreamDestroy(ctx->comm_st); cudaEventDestroy(ctx->ev_ar[0]); cudaEventDestroy(ctx->ev_ar[1]); cudaEventDestroy(ctx->ev_bwd);
   }
   delete ctx;
+  return NTF_OK;
+}
+
+extern "C" int ntf_set_dyn(ntf_ctx* ctx, const ntf_dyn* dyn) {
+  NTF_REQUIRE(ctx, NTF_ERR_BAD_ARG, "set_dyn: null ctx");
+  ctx->dyn_override = dyn;
   return NTF_OK;
 }
 

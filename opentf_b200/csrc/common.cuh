@@ -22,6 +22,7 @@ struct ntf_ctx {
   cudaEvent_t ev_fork_opt, ev_join_opt;  // second fork of a step: Adam on the output layer's segment next to the input layer's backward pass
   // data-parallel ranks (ntf_fnn_step_args.comm): the gradient all-reduces run on their own stream so that the output layer's segment
   // is exchanged while the backward pass through the hidden layers runs, and stepped while the rest is exchanged
+  const ntf_dyn* dyn_override;  // ntf_set_dyn: while set, the entry points that take step / lr / adam_t as host arguments enqueue kernels that read them from this device block
   cudaStream_t comm_st;
   cudaEvent_t ev_ar[2], ev_bwd;
 };

@@ -19,7 +19,8 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint64_t step, uint32_t s
   sincospif(2.f * u3, &s, &c); z[2] = rb * c; z[3] = rb * s;
 }
 
-__global__ void fill_normal_kernel(uint64_t seed, uint64_t step, uint32_t stream_id, size_t n, float* __restrict__ out) {
+__global__ void fill_normal_kernel(uint64_t seed, uint64_t step, uint32_t stream_id, size_t n, float* __restrict__ out, const ntf_dyn* __restrict__ dyn) {
+  if (dyn) step = dyn->step;  // a replayed graph: this step's counter
   const size_t nb = (n + 3) / 4;
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
     float z[4];
@@ -29,7 +30,9 @@ __global__ void fill_normal_kernel(uint64_t seed, uint64_t step, uint32_t stream
   }
 }
 
-__global__ void fill_sign_bits_kernel(uint64_t seed, uint64_t step, uint32_t stream_id, size_t n_words, uint32_t* __restrict__ bits) {
+__global__ void fill_sign_bits_kernel(uint64_t seed, uint64_t step, uint32_t stream_id, size_t n_words, uint32_t* __restrict__ bits,
+                                      const ntf_dyn* __restrict__ dyn) {
+  if (dyn) step = dyn->step;
   const size_t nb = (n_words + 3) / 4;
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
     const Philox4 r = philox4x32_10((uint32_t)b, stream_id, (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)seed,
@@ -110,7 +113,7 @@ static int grid_for(const ntf_ctx* ctx, size_t n) {
 extern "C" int ntf_fill_normal(ntf_ctx* ctx, void* stream, uint64_t seed, uint64_t step, uint32_t stream_id, size_t n, float* out) {
   NTF_REQUIRE(ctx && out, NTF_ERR_BAD_ARG, "fill_normal: null pointer");
   if (!n) return NTF_OK;
-  NTF_COUNT_LAUNCH; fill_normal_kernel<<<grid_for(ctx, (n + 3) / 4), 256, 0, as_stream(stream)>>>(seed, step, stream_id, n, out);
+  NTF_COUNT_LAUNCH; fill_normal_kernel<<<grid_for(ctx, (n + 3) / 4), 256, 0, as_stream(stream)>>>(seed, step, stream_id, n, out, ctx->dyn_override);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
@@ -119,7 +122,7 @@ extern "C" int ntf_fill_sign_bits(ntf_ctx* ctx, void* stream, uint64_t seed, uin
                                   uint32_t* bits) {
   NTF_REQUIRE(ctx && bits, NTF_ERR_BAD_ARG, "fill_sign_bits: null pointer");
   if (!n_words) return NTF_OK;
-  NTF_COUNT_LAUNCH; fill_sign_bits_kernel<<<grid_for(ctx, (n_words + 3) / 4), 256, 0, as_stream(stream)>>>(seed, step, stream_id, n_words, bits);
+  NTF_COUNT_LAUNCH; fill_sign_bits_kernel<<<grid_for(ctx, (n_words + 3) / 4), 256, 0, as_stream(stream)>>>(seed, step, stream_id, n_words, bits, ctx->dyn_override);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }

@@ -124,7 +124,7 @@ int ntf_peer_exchange_adam_impl(ntf_ctx* ctx, cudaStream_t st, const ntf_peers* 
 
 extern "C" int ntf_peer_exchange_adam(ntf_ctx* ctx, void* stream, const ntf_peers* peers, float* adam_m, float* adam_v, size_t offset, size_t n,
                                       double lr, double beta1, double beta2, double eps, int64_t step, int channel) {
-  return ntf_peer_exchange_adam_impl(ctx, as_stream(stream), peers, adam_m, adam_v, offset, n, lr, beta1, beta2, eps, step, nullptr, channel);
+  return ntf_peer_exchange_adam_impl(ctx, as_stream(stream), peers, adam_m, adam_v, offset, n, lr, beta1, beta2, eps, step, ctx ? ctx->dyn_override : nullptr, channel);
 }
 
 // ---- peer-visible memory: plain cudaMalloc blocks + CUDA IPC handles (one process per GPU) -------------------------------------

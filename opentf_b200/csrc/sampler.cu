@@ -213,7 +213,7 @@ int ntf_neg_sample_impl(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed, uint
 extern "C" int ntf_neg_sample(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed, uint64_t step, int row0, int B,
                               const int32_t* m_indptr, const int32_t* m_indices, int E, int ns, const uint32_t* cdf,
                               const int32_t* pool_indptr, int pool_rows, int32_t* neg) {
-  return ntf_neg_sample_impl(ctx, stream, nsd, seed, step, row0, B, m_indptr, m_indices, E, ns, cdf, pool_indptr, pool_rows, neg, nullptr);
+  return ntf_neg_sample_impl(ctx, stream, nsd, seed, step, row0, B, m_indptr, m_indices, E, ns, cdf, pool_indptr, pool_rows, neg, ctx ? ctx->dyn_override : nullptr);
 }
 
 extern "C" int ntf_special_bits(ntf_ctx* ctx, void* stream, int op, int B, const int32_t* m_indptr, const int32_t* m_indices,

@@ -622,6 +622,46 @@ class Engine:
                                   self.sign_out[i].shape[1], B, h[i - 1], h[i], 1, self.act[i], self.ws)
 
     def _step_bayes(self, sp, b0, B, train, lr, loss_slot, neg_host, loss_scale, gbatch, noise_host=None):
+        """the Bnn step is ~45 calls of the library driven from here; like the Fnn step it is captured once per batch as a CUDA graph
+        (the calls land on the capture stream; RNG counter / lr / Adam constants come from the ntf_dyn block: ntf_set_dyn) and replayed.
+        Eager when the caller supplies negatives or noise (parity tests), for the very first step (workspaces grow to their final size
+        outside a capture) and when the gradients travel through torch.distributed."""
+        graphed = (self.use_graphs and neg_host is None and noise_host is None and getattr(self, '_bayes_warm', False)
+                   and (self.world == 1 or not train or self.peers is not None))
+        key = None
+        if graphed:
+            key = ('bayes', sp.s_indptr.data_ptr(), sp.s_indices.data_ptr(), sp.s_ent_row.data_ptr(), sp.m_indptr.data_ptr(), sp.m_indices.data_ptr(),
+                   b0, B, bool(train), loss_slot, loss_scale, gbatch, self.loss_buf.data_ptr(), id(self.peers))
+            graphed = key in self._graphs or len(self._graphs) < self.max_graphs
+        if not graphed:
+            self._bayes_body(sp, b0, B, train, lr, loss_slot, neg_host, loss_scale, gbatch, noise_host)
+            self._bayes_warm = True
+            return
+        ops.dyn_update(self.dev_index, self.dyn, self.global_step, float(lr) if train else 0.0, 0.9, 0.999, 1e-8, self.adam_t + 1)
+        if self.ws.gen != self._ws_gen: self._graphs.clear(); self._ws_gen = self.ws.gen
+        g = self._graphs.get(key)
+        if g is None:
+            counters = (self.global_step, self.adam_t)
+            ops.set_dyn(self.dev_index, self.dyn)
+            try:
+                g = ops.Graph(self.dev_index, self.h, self._cap_stream)
+                with g: self._bayes_body(sp, b0, B, train, lr if train else 0.0, loss_slot, None, loss_scale, gbatch, None)
+            finally:
+                ops.set_dyn(self.dev_index, None)
+            self.global_step, self.adam_t = counters  # (the captured calls did not run; the host counters advance per replay below)
+            if self.ws.gen != self._ws_gen:  # the workspace grew inside the capture: that graph points at freed memory
+                self._ws_gen = self.ws.gen
+                return self._step_bayes_eager_after_growth(sp, b0, B, train, lr, loss_slot, loss_scale, gbatch)
+            self._graphs[key] = g
+        g.launch()
+        self.global_step += 1
+        if train: self.adam_t += 1
+
+    def _step_bayes_eager_after_growth(self, sp, b0, B, train, lr, loss_slot, loss_scale, gbatch):
+        self._graphs.clear()
+        self._bayes_body(sp, b0, B, train, lr, loss_slot, None, loss_scale, gbatch, None)
+
+    def _bayes_body(self, sp, b0, B, train, lr, loss_slot, neg_host, loss_scale, gbatch, noise_host=None):
         h, Lo = self.hidden, self.L - 1
         scale = 1.0 / B if loss_scale is None else loss_scale
         self._draw_noise(sp, b0, B, noise_host)

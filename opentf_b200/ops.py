@@ -264,6 +264,11 @@ def dyn_update(dev, dyn, step, lr, b1, b2, eps, adam_t):
     check(lib().ntf_dyn_update(_lib.ctx(dev), _stream(dev), _p(dyn), int(step), lr, b1, b2, eps, int(adam_t)), 'ntf_dyn_update')
 
 
+def set_dyn(dev, dyn):
+    """while set (a device ntf_dyn block, or None to clear): step / lr / adam_t arguments of the eager entry points come from the block"""
+    check(lib().ntf_set_dyn(_lib.ctx(dev), None if dyn is None else _p(dyn)), 'ntf_set_dyn')
+
+
 class Graph:
     """`with Graph(dev) as g: <library calls>` captures them on torch's current stream (nothing runs); g.launch() replays."""
 

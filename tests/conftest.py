@@ -4,9 +4,6 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-# tests/test_gpu_dp.py runs several data-parallel RANKS on one device, each with its own streams, and the ranks wait for each other inside
-# kernels: with the default 8 hardware queues two streams may share a queue and the waiting kernel would block the one it waits for
-os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 if ROOT not in sys.path: sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 

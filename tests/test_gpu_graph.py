@@ -96,3 +96,41 @@ def test_step_host_replays_one_graph_for_every_batch_of_a_layout():
             assert len(eng._graphs) == 1
         out.append((losses, eng.params.cpu().clone()))
     assert np.array_equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32'])
+def test_bnn_step_graph_replay_equals_direct_launches(precision):
+    """the Bnn (Flipout) step is ~45 host-driven calls; captured per batch (ntf_set_dyn feeds the RNG counter and Adam's constants from
+    the device block) it must reproduce the eager run: bit for bit in fp32 mode, to round-off on the tensor-core path (dA / split-tile
+    sums arrive in L2 order).  Device-side noise: same counters, same draws."""
+    from opentf_b200 import synth, _lib
+    from opentf_b200.engine import Engine
+    tv = synth.make_teamsvecs('toy', seed=2)
+    S, E, B, h = tv['skill'].shape[1], tv['member'].shape[1], 128, 128
+    if precision == 'tf32' and not _lib.lib().ntf_tc_supported(B, h, E, 1): pytest.skip('shape not on the tensor-core path')
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for i, (fin, fout) in enumerate(((S, h), (h, E))):
+        sd[f'layers.{i}.mu_weight'] = torch.empty(fout, fin).normal_(0.0, 0.1, generator=g); sd[f'layers.{i}.rho_weight'] = torch.empty(fout, fin).normal_(-3.0, 0.1, generator=g)
+        sd[f'layers.{i}.mu_bias'] = torch.empty(fout).normal_(0.0, 0.1, generator=g); sd[f'layers.{i}.rho_bias'] = torch.empty(fout).normal_(-3.0, 0.1, generator=g)
+    res = []
+    for graphs in (False, True):
+        eng = Engine(S, [h], E, 'cuda:0', bayesian=True, precision=precision, tpw=10, tnw=1, nsd='unigram_b', ns=5, seed=3, max_batch=B)
+        eng.use_graphs = graphs
+        eng.stage(tv['skill'], tv['member'])
+        eng.load_state_dict(sd)
+        sp, vsp = eng.split(np.arange(0, 300)), eng.split(np.arange(300, 420))
+        out = []
+        for e in range(3):
+            lr = 1e-2 * (0.1 ** e)
+            for bi in range(3): eng.step(sp, bi * 100, 100, True, lr=lr, loss_slot=bi)
+            eng.step(vsp, 0, 120, False, loss_slot=3)
+            out.append(eng.loss_buf[:4].cpu().clone())
+        torch.cuda.synchronize()
+        res.append((torch.stack(out), eng.params.cpu().clone(), eng.adam_t, eng.global_step, len(eng._graphs)))
+    (l0, p0, t0, s0, g0), (l1, p1, t1, s1, g1) = res
+    assert t0 == t1 == 9 and s0 == s1 == 12
+    assert g0 == 0 and g1 == 4  # 3 train batches + 1 validation batch, captured at their first occurrence after the warm-up step
+    if precision == 'fp32': assert torch.equal(l0, l1) and torch.equal(p0, p1)
+    else: assert torch.allclose(l0, l1, rtol=1e-4) and (p0 - p1).norm() <= 1e-3 * p0.norm()
+    assert l0[-1, :3].mean() < l0[0, :3].mean()
