@@ -57,6 +57,8 @@ extern "C" int ntf_create(int device, ntf_ctx** out) {
   if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_fork_opt, cudaEventDisableTiming);
   if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_join_opt, cudaEventDisableTiming);
+  if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_hot_fork, cudaEventDisableTiming);
+  if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_hot_join, cudaEventDisableTiming);
   if (es == cudaSuccess) es = cudaStreamCreateWithFlags(&c->comm_st, cudaStreamNonBlocking);
   for (int i = 0; i < 2 && es == cudaSuccess; ++i) es = cudaEventCreateWithFlags(&c->ev_ar[i], cudaEventDisableTiming);
   if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_bwd, cudaEventDisableTiming);
@@ -75,6 +77,7 @@ extern "C" int ntf_destroy(ntf_ctx* ctx) {
     for (int i = 0; i < 2; ++i) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_fork_opt); cudaEventDestroy(ctx->ev_join_opt);
+    cudaEventDestroy(ctx->ev_hot_fork); cudaEventDestroy(ctx->ev_hot_join);
     cudaStreamDestroy(ctx->comm_st); cudaEventDestroy(ctx->ev_ar[0]); cudaEventDestroy(ctx->ev_ar[1]); cudaEventDestroy(ctx->ev_bwd);
   }
   delete ctx;

@@ -23,6 +23,7 @@ struct ntf_ctx {
   // data-parallel ranks (ntf_fnn_step_args.comm): the gradient all-reduces run on their own stream so that the output layer's segment
   // is exchanged while the backward pass through the hidden layers runs, and stepped while the rest is exchanged
   const ntf_dyn* dyn_override;  // ntf_set_dyn: while set, the entry points that take step / lr / adam_t as host arguments enqueue kernels that read them from this device block
+  cudaEvent_t ev_hot_fork, ev_hot_join;  // input layer's backward: the hot skills' kernels next to the warp-per-skill reduction
   cudaStream_t comm_st;
   cudaEvent_t ev_ar[2], ev_bwd;
 };

@@ -362,6 +362,13 @@ __global__ void bag_bwd_fill_kernel(int B, const int32_t* __restrict__ indptr, c
 // pass 2: one warp per skill (all S of them: Adam is dense, absent skills get an explicit zero row).  The <= 32 batch rows of the
 // skill are rank-sorted by row id, so the fp32 sum runs in ascending team order whatever order pass 1 filled the slots in:
 // no floating-point atomics, bit-reproducible.  Skills with more entries go to the hot list.
+// skills with more than HOT entries in the batch -> the hot list.  Needs the counts only, so it runs with the slot fill (off the
+// critical path of a step); list order is irrelevant: every hot skill is reduced on its own.
+__global__ void bag_bwd_hotlist_kernel(int S, const uint32_t* __restrict__ cnt, int32_t* __restrict__ hot, uint32_t* __restrict__ nhot) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < S && cnt[s] > (uint32_t)HOT) hot[atomicAdd(nhot, 1u)] = s;
+}
+
 template <bool VEC4>
 __global__ void __launch_bounds__(256) bag_bwd_reduce_kernel(int S, int h, const uint32_t* __restrict__ cnt, const int32_t* __restrict__ slots,
                                                              const float* __restrict__ dZ, float* __restrict__ dW0T, int32_t* __restrict__ hot,
@@ -370,10 +377,7 @@ __global__ void __launch_bounds__(256) bag_bwd_reduce_kernel(int S, int h, const
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < S; s += warps) {
     const int n = (int)__ldg(cnt + s);
-    if (n > HOT) {
-      if (lane == 0) hot[atomicAdd(nhot, 1u)] = s;  // list order is irrelevant: every hot skill is reduced on its own
-      continue;
-    }
+    if (n > HOT) continue;  // on the hot list (bag_bwd_hotlist_kernel): reduced by csr_bag_bwd_hot_kernel, possibly at the same time
     int rid = 0x7fffffff;
     if (lane < n) rid = __ldg(slots + (size_t)s * HOT + lane);
     const int key = rid & 0x7fffffff;
@@ -567,27 +571,38 @@ int ntf_csr_bag_bwd_fill_impl(ntf_ctx* ctx, cudaStream_t st, int B, const int32_
   const BagBwdWs w = bag_bwd_ws(workspace, S);
   NTF_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)(S + 64) * sizeof(uint32_t), st));
   NTF_COUNT_LAUNCH; bag_bwd_fill_kernel<<<min(cdiv(B * 8, 256), ctx->sm_count * 8), 256, 0, st>>>(B, indptr, indices, ent_row, row_base, ent_sign, w.cnt, w.slots);
+  NTF_COUNT_LAUNCH; bag_bwd_hotlist_kernel<<<cdiv(S, 256), 256, 0, st>>>(S, w.cnt, w.hot, w.nhot);
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
 
 int ntf_csr_bag_bwd_reduce_impl(ntf_ctx* ctx, cudaStream_t st, int B, const int32_t* indptr, const int32_t* indices, const int32_t* ent_row,
                                 int row_base, const float* dZ, int S, int h, float* dW0T, void* workspace, size_t workspace_bytes,
-                                const uint32_t* ent_sign) {
+                                const uint32_t* ent_sign, cudaStream_t st_hot) {
+  // st_hot (nullable): the hot skills' kernels run there, next to the warp-per-skill reduction on `st` (disjoint rows of dW0T); joined
+  // back into `st` before returning.  Both need dZ, which is complete on `st` when this is called.
   NTF_REQUIRE(ctx && indptr && indices && ent_row && dZ && dW0T && workspace, NTF_ERR_BAD_ARG, "csr_bag_bwd: null pointer");
   NTF_REQUIRE(h <= 2048, NTF_ERR_UNSUPPORTED, "csr_bag_bwd: first hidden width %d > 2048", h);
   NTF_REQUIRE(workspace_bytes >= ntf_csr_bag_bwd_workspace_bytes(S, h), NTF_ERR_WORKSPACE, "csr_bag_bwd: workspace too small");
   const BagBwdWs w = bag_bwd_ws(workspace, S);
   const bool vec = (h % 4 == 0) && (((uintptr_t)dZ | (uintptr_t)dW0T) % 16 == 0);
   const int blocks = min(cdiv(S, 8), ctx->sm_count * 8);
+  if (st_hot != nullptr && st_hot != st) NTF_CUDA(cudaEventRecord(ctx->ev_hot_fork, st));
   NTF_COUNT_LAUNCH;
   if (vec) bag_bwd_reduce_kernel<true><<<blocks, 256, 0, st>>>(S, h, w.cnt, w.slots, dZ, dW0T, w.hot, w.nhot);
   else bag_bwd_reduce_kernel<false><<<blocks, 256, 0, st>>>(S, h, w.cnt, w.slots, dZ, dW0T, w.hot, w.nhot);
   const size_t smem_hot = (size_t)(1 + BWD_WARPS) * h * sizeof(float) + (size_t)HCAP * sizeof(int);
   NTF_CUDA(cudaFuncSetAttribute(csr_bag_bwd_hot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hot));
-  NTF_COUNT_LAUNCH; csr_bag_bwd_hot_kernel<<<ctx->sm_count * 2, BWD_WARPS * 32, smem_hot, st>>>(B, indptr, indices, ent_row, row_base, dZ, h, w.hot, w.nhot, dW0T, ent_sign, w.hot_part);
-  NTF_COUNT_LAUNCH; bag_bwd_hot_combine_kernel<<<ctx->sm_count, 128, 0, st>>>(h, w.hot, w.nhot, w.hot_part, dW0T);
+  const bool fork = st_hot != nullptr && st_hot != st;
+  cudaStream_t sh = fork ? st_hot : st;
+  if (fork) NTF_CUDA(cudaStreamWaitEvent(sh, ctx->ev_hot_fork, 0));  // (recorded on st before the reduce kernel was enqueued, below)
+  NTF_COUNT_LAUNCH; csr_bag_bwd_hot_kernel<<<ctx->sm_count * 2, BWD_WARPS * 32, smem_hot, sh>>>(B, indptr, indices, ent_row, row_base, dZ, h, w.hot, w.nhot, dW0T, ent_sign, w.hot_part);
+  NTF_COUNT_LAUNCH; bag_bwd_hot_combine_kernel<<<ctx->sm_count, 128, 0, sh>>>(h, w.hot, w.nhot, w.hot_part, dW0T);
   NTF_LAUNCH_CHECK();
+  if (fork) {
+    NTF_CUDA(cudaEventRecord(ctx->ev_hot_join, sh));
+    NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_hot_join, 0));
+  }
   return NTF_OK;
 }
 
@@ -596,7 +611,7 @@ static int csr_bag_bwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* in
                             void* workspace, size_t workspace_bytes, const uint32_t* ent_sign) {
   const int rc = ntf_csr_bag_bwd_fill_impl(ctx, as_stream(stream), B, indptr, indices, ent_row, row_base, S, h, workspace, workspace_bytes, ent_sign);
   if (rc) return rc;
-  return ntf_csr_bag_bwd_reduce_impl(ctx, as_stream(stream), B, indptr, indices, ent_row, row_base, dZ, S, h, dW0T, workspace, workspace_bytes, ent_sign);
+  return ntf_csr_bag_bwd_reduce_impl(ctx, as_stream(stream), B, indptr, indices, ent_row, row_base, dZ, S, h, dW0T, workspace, workspace_bytes, ent_sign, nullptr);
 }
 
 extern "C" int ntf_csr_bag_bwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
@@ -618,7 +633,7 @@ extern "C" int ntf_csr_bag_bwd_signed(ntf_ctx* ctx, void* stream, int B, const i
 // order inside a block of rows, then across row-blocks by a second fixed-order pass: deterministic.
 // =========================================================================================================
 namespace {
-constexpr int ACT_ROWS = 64;  // rows per block
+constexpr int ACT_ROWS = 16;  // rows per block (B=1000: 63 blocks; the partials are combined in block order)
 
 __global__ void act_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, int B, int h, int act,
                                float* __restrict__ dZ, float* __restrict__ part) {

@@ -13,6 +13,8 @@
 // links busy at once), Adam's HBM traffic and its m/v state cut by G, no staging buffers, and the sum is taken in rank order by ONE
 // rank per element, so the replicas stay bit-identical.  Arenas and flags are plain cudaMalloc blocks shared through CUDA IPC
 // (ntf_peer_*); one process per GPU.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -57,7 +59,12 @@ __global__ void peer_barrier_kernel(ntf_peers pr, int phase /* 2*channel + {0,1}
   }
 }
 
-template <int G>
+// Software-pipelined: a thread issues the peer loads of its NEXT batch (UNR grid-strided elements, UNR*G independent 16-byte loads)
+// before it steps and stores the current one.  A slice is only a few passes of the grid, so without the overlap the kernel would
+// first read over the links and then write over them, using each direction half of the time; with it the inbound gradient loads
+// of pass k+1 and the outbound parameter stores of pass k are in flight together (NVLink is full duplex), and enough loads are
+// outstanding to cover the link + switch latency (Little's law).
+template <int G, int UNR>
 __global__ void __launch_bounds__(512) peer_reduce_adam_kernel(ntf_peers pr, float* __restrict__ m, float* __restrict__ v, size_t lo4, size_t hi4,
                                                                AdamK k, const ntf_dyn* __restrict__ dyn) {
   if (dyn) k = AdamK{dyn->one_minus_b1, dyn->b2, dyn->one_minus_b2, dyn->bc2_sqrt, dyn->eps, dyn->neg_step};
@@ -65,18 +72,45 @@ __global__ void __launch_bounds__(512) peer_reduce_adam_kernel(ntf_peers pr, flo
   float4* P = reinterpret_cast<float4*>(pr.params[pr.rank]);
   float4* M = reinterpret_cast<float4*>(m);
   float4* V = reinterpret_cast<float4*>(v);
-  for (size_t i = lo4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += stride) {
-    float4 g[G];
+  float4 g[2][UNR][G];
+  auto load = [&](int buf, size_t i0) {
 #pragma unroll
-    for (int r = 0; r < G; ++r) g[r] = ld_peer(reinterpret_cast<const float4*>(pr.grads[r]) + i);  // G independent 16-byte loads in flight
-    float4 p = P[i], mm = M[i], vv = V[i];
-    float4 s = g[0];
+    for (int u = 0; u < UNR; ++u) {
+      const size_t i = i0 + (size_t)u * stride;
+      if (i < hi4) {
 #pragma unroll
-    for (int r = 1; r < G; ++r) { s.x += g[r].x; s.y += g[r].y; s.z += g[r].z; s.w += g[r].w; }  // rank order: the same sum on every rank
-    adam1(p.x, s.x, mm.x, vv.x, k); adam1(p.y, s.y, mm.y, vv.y, k); adam1(p.z, s.z, mm.z, vv.z, k); adam1(p.w, s.w, mm.w, vv.w, k);
-    M[i] = mm; V[i] = vv;
+        for (int r = 0; r < G; ++r) g[buf][u][r] = ld_peer(reinterpret_cast<const float4*>(pr.grads[r]) + i);
+      }
+    }
+  };
+  auto step_store = [&](int buf, size_t i0) {
 #pragma unroll
-    for (int r = 0; r < G; ++r) reinterpret_cast<float4*>(pr.params[r])[i] = p;
+    for (int u = 0; u < UNR; ++u) {
+      const size_t i = i0 + (size_t)u * stride;
+      if (i < hi4) {
+        float4 p = P[i], mm = M[i], vv = V[i];
+        float4 s = g[buf][u][0];
+#pragma unroll
+        for (int r = 1; r < G; ++r) { s.x += g[buf][u][r].x; s.y += g[buf][u][r].y; s.z += g[buf][u][r].z; s.w += g[buf][u][r].w; }  // rank order: the same sum on every rank
+        adam1(p.x, s.x, mm.x, vv.x, k); adam1(p.y, s.y, mm.y, vv.y, k); adam1(p.z, s.z, mm.z, vv.z, k); adam1(p.w, s.w, mm.w, vv.w, k);
+        M[i] = mm; V[i] = vv;
+#pragma unroll
+        for (int r = 0; r < G; ++r) reinterpret_cast<float4*>(pr.params[r])[i] = p;
+      }
+    }
+  };
+  size_t i0 = lo4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= hi4) return;
+  load(0, i0);
+  for (;;) {  // (two passes per trip so that the buffer index is a compile-time constant: g stays in registers)
+    const size_t i1 = i0 + stride * UNR;
+    if (i1 < hi4) load(1, i1);
+    step_store(0, i0);
+    if (i1 >= hi4) break;
+    i0 = i1 + stride * UNR;
+    if (i0 < hi4) load(0, i0);
+    step_store(1, i1);
+    if (i0 >= hi4) break;
   }
 }
 
@@ -108,10 +142,15 @@ int ntf_peer_exchange_adam_impl(ntf_ctx* ctx, cudaStream_t st, const ntf_peers* 
   NTF_LAUNCH_CHECK();
   if (hi4 > lo4) {
     const size_t work = hi4 - lo4;
-    const int blocks = (int)((work + 511) / 512 < (size_t)ctx->sm_count * 2 ? (work + 511) / 512 : (size_t)ctx->sm_count * 2);
+    const int unr = pr->world <= 2 ? 2 : 1;
+    size_t want = (work + (size_t)512 * unr * 4 - 1) / ((size_t)512 * unr * 4);  // CTAs for ~4 pipelined passes per thread
+    const size_t cap = (size_t)ctx->sm_count * 2, floor_ = (size_t)ctx->sm_count;  // (at least one CTA per SM issuing)
+    if (want > cap) want = cap;
+    if (want < floor_) want = floor_ < (work + 511) / 512 ? floor_ : (work + 511) / 512;
+    const int blocks = (int)(want ? want : 1);
     NTF_COUNT_LAUNCH;
     switch (pr->world) {
-#define CASE(G) case G: peer_reduce_adam_kernel<G><<<blocks, 512, 0, st>>>(*pr, adam_m, adam_v, lo4, hi4, k, dyn); break;
+#define CASE(G) case G: peer_reduce_adam_kernel<G, (G <= 2 ? 2 : 1)><<<blocks, 512, 0, st>>>(*pr, adam_m, adam_v, lo4, hi4, k, dyn); break;
       CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     }

@@ -23,7 +23,7 @@ int ntf_csr_bag_bwd_fill_impl(ntf_ctx* ctx, cudaStream_t st, int B, const int32_
                               int row_base, int S, int h, void* workspace, size_t workspace_bytes, const uint32_t* ent_sign);
 int ntf_csr_bag_bwd_reduce_impl(ntf_ctx* ctx, cudaStream_t st, int B, const int32_t* indptr, const int32_t* indices, const int32_t* ent_row,
                                 int row_base, const float* dZ, int S, int h, float* dW0T, void* workspace, size_t workspace_bytes,
-                                const uint32_t* ent_sign);
+                                const uint32_t* ent_sign, cudaStream_t st_hot);
 
 int ntf_peer_exchange_adam_impl(ntf_ctx* ctx, cudaStream_t st, const ntf_peers* pr, float* adam_m, float* adam_v, size_t off, size_t n, double lr,
                                 double beta1, double beta2, double eps, int64_t step, const ntf_dyn* dyn, int channel);
@@ -167,7 +167,8 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     STEP(ntf_dense_bwd(ctx, stream, a->x_dense, a->W[0], a->dz[0], B, a->S, h[0], a->gW[0], nullptr, ws_main, ws_main_bytes));
   } else {
     NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[1], 0));
-    STEP(ntf_csr_bag_bwd_reduce_impl(ctx, st, B, a->s_indptr, a->s_indices, a->s_ent_row, a->row_base, a->dz[0], a->S, h[0], a->gW[0], ws_bag, ws_bag_bytes, nullptr));
+    STEP(ntf_csr_bag_bwd_reduce_impl(ctx, st, B, a->s_indptr, a->s_indices, a->s_ent_row, a->row_base, a->dz[0], a->S, h[0], a->gW[0], ws_bag, ws_bag_bytes, nullptr,
+                                     ctx->side[1]));  // (side 1 is idle since the slot fill: the hot skills' kernels go there)
   }
   // ---- optimiser: fnn.py:139 (skipped when the caller all-reduces the gradients first: data-parallel ranks) ----
   if (dp) {
