@@ -43,6 +43,7 @@ def parse():
     p.add_argument('--infer-k', type=int, default=10)
     p.add_argument('--leg', default='all', choices=['all', 'bnn'], help="'bnn': only the Bnn train leg (its dict is the output line; for profiling)")
     p.add_argument('--no-extras', action='store_true', help='skip the secondary legs (Bnn train on the imdb shape, top-K sweep)')
+    p.add_argument('--extras', action='store_true', help='run the secondary legs under torchrun too (default: single-GPU runs only)')
     return p.parse_args()
 
 
@@ -306,12 +307,19 @@ def run_ours(args):
     infer_value = reps * ib * G / (i0.elapsed_time(i1) * 1e-3)
 
     extras = {}
-    if not args.no_extras:
-        extras['infer_topk_sweep'] = topk_sweep(eng, test_sp, dev, sync, G)
+    # secondary legs: on one GPU by default; under torchrun only when asked for (--extras) -- the headline line of a scaling run should not
+    # depend on them (a leg that fails on one rank would leave the others waiting in a collective).  `--leg bnn` runs the Bnn leg alone at any N.
+    if not args.no_extras and (world == 1 or args.extras):
+        def leg(name, fn):
+            try: extras[name] = fn()
+            except Exception as ex:  # (single process: report and go on; the headline measurement above is already taken)
+                if world > 1: raise
+                extras[name] = {'error': f'{type(ex).__name__}: {ex}'}
+        leg('infer_topk_sweep', lambda: topk_sweep(eng, test_sp, dev, sync, G))
         del eng, sp, test_sp, scores
         torch.cuda.empty_cache()
-        extras['bnn_train'] = bnn_leg(args, dev, world, rank, sync, dist)
-        extras['batch_sweep'] = batch_sweep(args, tv, splits, dev, world, rank, sync, dist)
+        leg('bnn_train', lambda: bnn_leg(args, dev, world, rank, sync, dist))
+        leg('batch_sweep', lambda: batch_sweep(args, tv, splits, dev, world, rank, sync, dist))
     if rank != 0:
         if world > 1: dist.destroy_process_group()
         return
