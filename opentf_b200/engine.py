@@ -413,7 +413,7 @@ class Engine:
             self._run(a, 3, key if graphed else None)
             self.global_step += 1; self.adam_t += 1
             return
-        elif dp and train and self.dp_overlap:
+        elif dp and train and self.dp_overlap and self._arena_split() is not None:
             return self._dp_overlapped(a, key if graphed else None, lr)
         else:
             self._run(a, 3, key if graphed else None)
@@ -478,9 +478,9 @@ class Engine:
 
     def _peer_exchange(self, lr):
         """the eager counterpart of what ntf_fnn_step does with `peers`: output layer's segment on channel 1, the rest on channel 0"""
-        split = min(self.views[f'layers.{self.L - 1}.{k}'][0] for k in self._last_kinds())
+        split = self._arena_split()
         t = self.adam_t + 1
-        if split % 4 == 0 and 0 < split < self.n_params:
+        if split is not None:
             ops.peer_exchange_adam(self.dev_index, self.peers, self.adam_m, self.adam_v, split, self.n_params - split, lr, 0.9, 0.999, 1e-8, t, 1)
             ops.peer_exchange_adam(self.dev_index, self.peers, self.adam_m, self.adam_v, 0, split, lr, 0.9, 0.999, 1e-8, t, 0)
         else:
@@ -490,18 +490,44 @@ class Engine:
     def _last_kinds(self):
         return ('mu_weight', 'rho_weight', 'mu_bias', 'rho_bias') if self.bayesian else ('weight', 'bias')
 
-    def idle_step(self, train, lr=None):
-        """a data-parallel rank whose slice of a (short, last) global batch is empty: it contributes zero gradients but must take part in
-        the exchange and step its replica with the same sums.  The exchange mirrors step()'s (two segments when overlapped)."""
+    def _arena_split(self):
+        """offset of the output layer's segment when a step exchanges the arena in two overlapped segments, else None -- the SAME decision
+        ntf_fnn_step takes (step.cu: NTF_ADAM_SPLIT unset, the last layer's tensors at the end of the arena, offset a multiple of 32 floats),
+        so that a rank that sits a batch out (idle_step) issues the same number of collectives as the ranks that step"""
+        if os.environ.get('NTF_ADAM_SPLIT') is not None: return None
+        split = min(self.views[f'layers.{self.L - 1}.{k}'][0] for k in self._last_kinds())
+        others = [self.views[f'layers.{i}.{k}'][0] for i in range(self.L - 1) for k in self._last_kinds()]
+        return split if (split % 32 == 0 and 0 < split < self.n_params and all(o < split for o in others)) else None
+
+    def idle_step(self, train, lr=None, loss_scale=None, loss_slot=None):
+        """a data-parallel rank whose slice of a (short, last) global batch is empty: it contributes zero data gradients but must take part in
+        the exchange and step its replica with the same sums.  The exchange mirrors step()'s (two segments when overlapped).  Bnn: every rank
+        adds its 1/world share of KL/B to the loss and of the KL gradient (engine._bayes_body), so an idle rank still owes that share."""
+        step_now = self.global_step
         self.global_step += 1
-        if not (train and self.world > 1 and self.shard[1] == 1): return
+        if self.world <= 1 or self.shard[1] > 1: return
+        if self.bayesian and loss_scale is not None:
+            ops.fill_normal(self.seed, step_now, 0, self.n_noise, self.eps)  # eps is the same on every rank (same counter)
+            self._prepare_bayes()
+            if loss_slot is not None: ops.axpy(1, loss_scale / self.world, self.kl, self.loss_buf[loss_slot:loss_slot + 1])
+        if not train: return
         self.grads.zero_()
+        if self.bayesian and loss_scale is not None:
+            self.gdelta.zero_()
+            for i in range(self.L):
+                for what in ('weight', 'bias'):
+                    mu, rho = self._pv(i, 'mu', what), self._pv(i, 'rho', what)
+                    n = mu.numel()
+                    ops.flipout_grads(mu, rho, self.nview(self.eps, f'{i}.{what}'), self.nview(self.gdelta, f'{i}.{what}'), n, loss_scale / (n * self.world),
+                                      self._pv(i, 'mu', what, self.grads), self._pv(i, 'rho', what, self.grads))
         if self.peers is not None: return self._peer_exchange(lr)
         if self.bayesian or not (self.dp_overlap or self.comm): return self.optimizer_step(lr)
-        split = min(self.views[f'layers.{self.L - 1}.{k}'][0] for k in ('weight', 'bias'))
-        ar = self.comm.allreduce if (self.comm and not self.bayesian) else self.allreduce
-        ar(self.grads[split:])
-        ar(self.grads[:split])
+        split = self._arena_split()
+        ar = self.comm.allreduce if self.comm else self.allreduce
+        if split is None: ar(self.grads)
+        else:
+            ar(self.grads[split:])
+            ar(self.grads[:split])
         self.adam_t += 1
         ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, self.n_params, lr, 0.9, 0.999, 1e-8, self.adam_t)
 
@@ -510,8 +536,7 @@ class Engine:
         segment (its gradients are final after phase 1) is summed over the ranks and stepped on a side stream WHILE the backward
         pass through the hidden layers runs; the rest follows on the main stream while the side stream runs its Adam segment.
         Adam is elementwise, so the result equals optimizer_step()'s bit for bit given the same sums."""
-        split = min(self.views[f'layers.{self.L - 1}.{k}'][0] for k in ('weight', 'bias'))
-        assert all(self.views[f'layers.{i}.{k}'][0] < split for i in range(self.L - 1) for k in ('weight', 'bias'))
+        split = self._arena_split()
         n, t = self.n_params, self.adam_t + 1
         main = torch.cuda.current_stream(self.device)
         if self._dp_stream is None:

@@ -187,7 +187,7 @@ class Fnn(Ntf):
                         b0, B = bi * b, min(b, sp.n - bi * b)
                         lo, hi = self._rank_slice(B)
                         if hi <= lo:  # (data parallel, a last batch shorter than the number of ranks)
-                            eng.idle_step(phase == 'train', lr)
+                            eng.idle_step(phase == 'train', lr, loss_scale=1.0 / B, loss_slot=slot0 + bi)
                             continue
                         neg = None
                         if self.replay is not None:
@@ -199,6 +199,7 @@ class Fnn(Ntf):
                 losses = eng.loss_buf[:nb_t + nb_v]
                 if eng.world > 1: torch.distributed.all_reduce(losses)
                 losses = losses.cpu().tolist()  # the one host sync of the epoch
+                self._check_peers()
                 t_loss = sum(losses[:nb_t]) / nb_t
                 v_loss = sum(losses[nb_t:]) / nb_v
                 history.append((t_loss, v_loss))
@@ -216,7 +217,15 @@ class Fnn(Ntf):
             self.last_history[foldidx] = history
         w.close()
 
+    def _check_peers(self):
+        """data-parallel ranks exchanging gradients over peer memory: a flag barrier that gave up (a rank stalled past the timeout or died)
+        leaves the replicas summed over stale gradients -- stop the run instead of training on / checkpointing corrupt parameters."""
+        err = self.engine.peer_error()
+        if err: raise RuntimeError(f'peer-memory gradient exchange timed out (flag {err}) on rank {self.engine.rank}: replicas are out of step; '
+                                   f'raise NTF_PEER_TIMEOUT_S or use exchange=nccl')
+
     def _save(self, foldidx, e, t_loss, v_loss, path):
+        self._check_peers()
         sd = self.model.state_dict() if (self.engine.shard[1] > 1 or self.engine.rank == 0) else None  # (sharded: a collective gather)
         if self.engine.rank == 0:
             Ntf.torch.save({'model_state_dict': sd, 'cfg': self.cfg, 'f': foldidx, 'e': e, 't_loss': t_loss, 'v_loss': v_loss}, path)
@@ -251,6 +260,8 @@ class Fnn(Ntf):
                     if eng.rank == 0:
                         torch.save({'y_pred': y_pred, 'uncertainty': unc}, f'{self.output}/f{foldidx}.{pred_set}.{epoch}pred', pickle_protocol=4)
                         log.info(f'{self.name()} model predictions for fold{foldidx}.{pred_set}.{epoch} has saved at {self.output}/f{foldidx}.{pred_set}.{epoch}pred')
+        # rank 0 wrote the files; evaluate() (main.py:189) reads them next, on whichever rank runs it
+        if self.engine is not None and self.engine.world > 1: torch.distributed.barrier()
 
     def _gather_columns(self, t): return _gather_columns_impl(Ntf.torch, self.engine, t)
 

@@ -94,16 +94,29 @@ def calculate_metrics_device(Y, Y_, topK=None, per_instance=False, metrics=('P_2
         m_ptr = torch.as_tensor((Yc.indptr[r0:r1 + 1] - Yc.indptr[r0]).astype(np.int32), device=dev)
         m_idx = torch.as_tensor(Yc.indices[Yc.indptr[r0]:Yc.indptr[r1]].astype(np.int32), device=dev)
         if m_idx.numel() == 0: m_idx = torch.zeros(1, dtype=torch.int32, device=dev)
-        lens = np.diff(Yr.indptr[r0:r1 + 1]) if Yr is not None else None
-        if Yr is not None and lens.max(initial=0) <= min(first_stage, EVAL_MAXK):  # the stored candidates as they are, padded with -1
-            K = max(int(lens.max(initial=0)), 1)
+        if Yr is not None:
+            # sparse .pred: ONLY the stored entries are candidates (metric.py:15-23) -- a row with fewer stored scores than the cut-off
+            # retrieves fewer documents, it never gains unstored experts.  Rows are padded with -1; a row holding more than `cap` entries
+            # is cut to its cap best by value first (metric.py:19-21: argpartition on the stored values).
+            cap = min(first_stage, EVAL_MAXK)
+            lens = np.diff(Yr.indptr[r0:r1 + 1])
+            K = max(int(min(lens.max(initial=0), cap)), 1)
             ci = np.full((n, K), -1, np.int32); cv = np.zeros((n, K), np.float32)
-            pos = np.arange(Yr.indptr[r0], Yr.indptr[r1]) - np.repeat(Yr.indptr[r0:r1], lens)
-            rows = np.repeat(np.arange(n), lens)
-            ci[rows, pos] = Yr.indices[Yr.indptr[r0]:Yr.indptr[r1]]; cv[rows, pos] = Yr.data[Yr.indptr[r0]:Yr.indptr[r1]]
+            short = lens <= cap
+            ls = np.where(short, lens, 0)
+            starts = Yr.indptr[r0:r1]
+            src = np.repeat(starts, ls) + (np.arange(int(ls.sum())) - np.repeat(np.cumsum(ls) - ls, ls))
+            pos = np.arange(int(ls.sum())) - np.repeat(np.cumsum(ls) - ls, ls)
+            rows = np.repeat(np.arange(n), ls)
+            ci[rows, pos] = Yr.indices[src]; cv[rows, pos] = Yr.data[src]
+            for r in np.nonzero(~short)[0]:
+                a, b = Yr.indptr[r0 + r], Yr.indptr[r0 + r + 1]
+                v = Yr.data[a:b]
+                keep = np.argpartition(-v, cap - 1)[:cap]
+                ci[r, :cap] = Yr.indices[a:b][keep]; cv[r, :cap] = v[keep]
             idx, vals = torch.as_tensor(ci, device=dev), torch.as_tensor(cv, device=dev)
         else:  # first-stage retrieval on the device (metric.py:12,19-28)
-            dense = np.asarray(Yr[r0:r1].todense(), dtype=np.float32) if Yr is not None else np.ascontiguousarray(Y_[r0:r1], dtype=np.float32)
+            dense = np.ascontiguousarray(Y_[r0:r1], dtype=np.float32)
             K = min(first_stage, EVAL_MAXK)
             P = torch.as_tensor(dense, device=dev)
             vals = torch.empty(n, K, dtype=torch.float32, device=dev); idx = torch.empty(n, K, dtype=torch.int32, device=dev)

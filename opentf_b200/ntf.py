@@ -40,6 +40,18 @@ class Ntf:
         import pandas as pd
         torch = Ntf.torch
         assert os.path.isdir(self.output), f'No folder for {self.output} exist!'
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            # one process per GPU: the CSVs are written once, by rank 0; the others wait so that whatever follows sees complete files
+            if torch.distributed.get_rank() != 0:
+                torch.distributed.barrier()
+                return
+            try: return self._evaluate(teamsvecs, splits, evalcfg)
+            finally: torch.distributed.barrier()
+        return self._evaluate(teamsvecs, splits, evalcfg)
+
+    def _evaluate(self, teamsvecs, splits, evalcfg):
+        import pandas as pd
+        torch = Ntf.torch
         g = util.cfg_get
         y_test = teamsvecs['member'][splits['test']]
         mcfg = g(evalcfg, 'metrics')
