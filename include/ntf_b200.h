@@ -212,6 +212,25 @@ int ntf_infer_scores(ntf_ctx* ctx, void* stream, int precision, const float* A, 
 /* per row: the K largest of scale*P[n,:] in rank order (value descending, ties -> lower expert id first); K <= 2048 */
 int ntf_topk_select(ntf_ctx* ctx, void* stream, const float* P, int B, int E, int K, float scale, float* vals,
                     int32_t* idx);
+/* K5, fused: the K best experts per team straight from the last hidden layer's activations -- output layer product, sigmoid and
+ * top-K in one call; the [B,E] score matrix of fnn.py:211 never reaches HBM (csrc/infer_topk.cu: two passes of the tcgen05 product,
+ * block maxima -> threshold -> candidates).  Replaces `sigmoid(model(X))` + `topk_sparse` (fnn.py:204-218, pkgmgr.py:125-134) when
+ * testcfg.topK < E.  Rank order and values as ntf_infer_scores(NTF_TF32) + ntf_topk_select give (ties between DISTINCT logits whose
+ * probabilities round to the same float are ranked by logit).  idx = e_lo + column (global expert ids of an expert shard). */
+typedef struct ntf_infer_topk_args {
+  const float* A;   /* [B,h] activations of the last hidden layer (read when A16 is NULL) */
+  const void* A16;  /* [B,h] the same as fp16 (e.g. written by the input-layer kernel), or NULL */
+  const void* W16;  /* [E,h] fp16 image of the output layer's weight (ntf_to_half of layers.L.weight) */
+  const float* b;   /* [E] */
+  int B, h, E, K, e_lo;
+  float* vals;      /* [B,K] out: probabilities, rank order */
+  int32_t* idx;     /* [B,K] out: expert ids */
+} ntf_infer_topk_args;
+int ntf_infer_topk_supported(int B, int h, int E, int K); /* h == 128, K <= 128, 32*K <= E */
+size_t ntf_infer_topk_workspace_bytes(int B, int h, int E, int K);
+int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_args* args, void* workspace, size_t workspace_bytes);
+/* y[i] = fp16(x[i]) round-to-nearest: the fp16 operand images the tensor-core kernels read (10-bit mantissa = TF32's) */
+int ntf_to_half(ntf_ctx* ctx, void* stream, const float* x, size_t n, void* y);
 /* merge G per-shard candidate lists [G][B][K] (idx = global expert ids, -1 = empty) into the global top-K per row:
  * the merge step of the expert-sharded output layer. */
 int ntf_topk_merge(ntf_ctx* ctx, void* stream, const float* vals_in, const int32_t* idx_in, int G, int B, int K,

@@ -24,6 +24,11 @@ class OutTrainArgs(C.Structure):
                 ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp), ('e_lo', i32), ('A16', vp)]
 
 
+class InferTopkArgs(C.Structure):
+    """mirror of ntf_infer_topk_args"""
+    _fields_ = [('A', vp), ('A16', vp), ('W16', vp), ('b', vp), ('B', i32), ('h', i32), ('E', i32), ('K', i32), ('e_lo', i32), ('vals', vp), ('idx', vp)]
+
+
 NTF_MAX_LAYERS = 8
 _PA = vp * NTF_MAX_LAYERS
 
@@ -93,6 +98,10 @@ SIGNATURES = {
     'ntf_infer_scores_workspace_bytes': (sz, [i32, i32, i32]),
     'ntf_infer_scores': (i32, [vp, vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, sz]),
     'ntf_topk_select': (i32, [vp, vp, vp, i32, i32, i32, f32, vp, vp]),
+    'ntf_infer_topk_supported': (i32, [i32, i32, i32, i32]),
+    'ntf_infer_topk_workspace_bytes': (sz, [i32, i32, i32, i32]),
+    'ntf_infer_topk': (i32, [vp, vp, C.POINTER(InferTopkArgs), vp, sz]),
+    'ntf_to_half': (i32, [vp, vp, vp, sz, vp]),
     'ntf_topk_merge': (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),
     'ntf_row_entropy': (i32, [vp, vp, vp, i32, i32, f32, i32, vp]),
     'ntf_eval_ranked': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(i32), i32, vp]),

@@ -1,0 +1,319 @@
+// infer_topk.cu -- K5: test-time top-K expert ranking fused with the output layer (fnn.py:204-218, pkgmgr.py:125-134).
+//
+// The reference computes sigmoid(model(X)) as a dense [N,E] matrix, moves it to the host and runs torch.topk over it.  Here the
+// [B,E] score matrix never exists: the logits live in TMEM for the time a CTA looks at them, and only O(K) numbers per team
+// leave the SM.  Selection is done on the logit z = a.w + b (sigmoid(lrelu(.)) is monotone, so the K best logits are the K best
+// probabilities; the probability is evaluated for the K winners only), in TWO passes over the same tcgen05 product:
+//
+//   pass 1   Z[128 teams x 128 experts] = A16 . W16^T per (batch tile, expert tile); every epilogue thread (team, block of 32
+//            consecutive experts) keeps only the block's MAXIMUM -> bm[B, E/32]   (4*E/32 bytes per team instead of 4*E)
+//   select   per team the K-th largest block maximum (ntf_topk_select's kernels on the [B, E/32] matrix): value Tz, block bK.
+//            K blocks have a maximum >= Tz, so Tz is a lower bound of the K-th best logit, and everything that can be in the
+//            top K has  z > Tz  or  (z == Tz and its block <= bK)  -- at most 32*K elements, all inside those K blocks.
+//   pass 2   the same product again; elements passing that test are appended to the team's candidate list (global atomics on a
+//            per-team counter: a few dozen per team), everything else is dropped in registers.
+//   final    per team: sort the candidates by (z descending, expert id ascending), emit the first K as (probability, expert id).
+//
+// Recomputing the product is cheaper than writing and re-reading [B,E] (FlashAttention's trade): per team 2*2*h*E flops on the
+// tensor pipe against 8*E bytes of HBM traffic.  Exact: the result equals the K best of the full score row under the library's
+// rank order (value descending, ties -> lower expert id), as ntf_topk_select gives on ntf_infer_scores' output, whenever the
+// logits are distinct where the probabilities are (equal probabilities of distinct logits -- sigmoid saturation -- are ranked
+// by logit: a permutation among exact score ties).
+//
+// Layout: CTA = (batch tile of 128 teams, chunk of consecutive expert tiles); grid = batch tiles x chunks sized to one wave.
+//   warp 16     TMA: the fp16 activation tile once, then the fp16 W tiles of the chunk through a 4-stage ring
+//   warp 17     MMA issuer: M = 128 teams, N = 128 experts, K = 128 hidden (8 x kind::f16), 4 accumulator stages in TMEM
+//   warps 0-15  epilogue: thread = (team = TMEM lane, 32-expert column block): tcgen05.ld, + bias, max / threshold test
+// W16 is an fp16 image of the layer's weight kept by the caller (ntf_to_half; rewritten when the parameters change).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TT = 128;   // teams per batch tile (UMMA M)
+constexpr int TX = 128;   // experts per expert tile (UMMA N)
+constexpr int HK = 128;   // hidden width
+constexpr uint32_t CHUNK = 128 * 128;        // one swizzle chunk: 128 rows x 128 bytes (64 halfs)
+constexpr uint32_t TILE_BYTES = 2 * CHUNK;   // an fp16 [128 x 128] operand tile: 2 chunks (hidden 0-63 | 64-127)
+constexpr int W_STAGES = 4;
+constexpr int Z_STAGES = 4;
+constexpr uint32_t OFF_A = 0;
+constexpr uint32_t OFF_W = OFF_A + TILE_BYTES;
+constexpr uint32_t OFF_BAR = OFF_W + W_STAGES * TILE_BYTES;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 256;
+enum { BAR_A_FULL = 0, BAR_W_FULL = 1, BAR_W_EMPTY = 1 + W_STAGES, BAR_Z_FULL = 1 + 2 * W_STAGES, BAR_Z_EMPTY = 1 + 2 * W_STAGES + Z_STAGES,
+       NUM_BARS = 1 + 2 * W_STAGES + 2 * Z_STAGES };
+static_assert(NUM_BARS * 8 + 8 <= 256, "barrier block");
+constexpr int EPI_WARPS = 16, WARP_TMA = 16, WARP_MMA = 17, NT = 18 * 32;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr uint32_t IDESC = instr_desc(0, 0, 0, TT, TX);  // Z = A16(K-major) . W16(K-major)^T, fp16 operands, fp32 accumulate
+constexpr int BLK = 32;  // experts per block (= the 32 TMEM columns one epilogue thread reads)
+
+__device__ __forceinline__ uint32_t ordered_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+struct ItArgs {
+  const float* bias;     // [E]
+  int B, E, K;
+  int nbt, nct, nchunk;  // batch tiles, expert tiles, chunks of expert tiles
+  int nblk;              // row pitch of bm = 4 * nct (blocks of 32 experts, the last tile padded)
+  float* bm;             // pass 1 out: [B, nblk] block maxima (-inf for blocks past E)
+  const float* thr_val;  // pass 2 in: [B, K] the K largest block maxima in rank order, and
+  const int32_t* thr_blk;  //          [B, K] their block ids (ntf_topk_select on bm)
+  unsigned long long* cand;  // pass 2 out: [B, cap] composites (ordered logit << 32 | ~expert)
+  int* cnt;                  // [B] candidates appended so far (zeroed by the caller)
+  int cap;
+};
+
+template <int PASS>
+__global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, ItArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if ((sbase & 1023u) != 0u) __trap();
+  const uint32_t bars = sbase + OFF_BAR;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + OFF_BAR + NUM_BARS * 8);
+  auto bar = [&](int i) { return bars + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // consecutive CTAs take different batch tiles of the SAME chunk: they stream the same W tiles at the same time (L2 hits)
+  const int bt = blockIdx.x % g.nbt, chunk = blockIdx.x / g.nbt;
+  const int t0 = (int)((long long)chunk * g.nct / g.nchunk), t1 = (int)((long long)(chunk + 1) * g.nct / g.nchunk);
+  const int ntiles = t1 - t0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(BAR_A_FULL), 1);
+    for (int s = 0; s < W_STAGES; ++s) { mbar_init(bar(BAR_W_FULL + s), 1); mbar_init(bar(BAR_W_EMPTY + s), 1); }
+    for (int s = 0; s < Z_STAGES; ++s) { mbar_init(bar(BAR_Z_FULL + s), 1); mbar_init(bar(BAR_Z_EMPTY + s), EPI_THREADS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WARP_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + NUM_BARS * 8), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == WARP_TMA) {
+    if (lane == 0) {
+      mbar_expect_tx(bar(BAR_A_FULL), TILE_BYTES);
+      for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A + c * CHUNK, &map_a, c * 64, bt * TT, bar(BAR_A_FULL));
+      for (int it = 0; it < ntiles; ++it) {
+        const int s = it % W_STAGES;
+        mbar_wait(bar(BAR_W_EMPTY + s), ((it / W_STAGES) & 1) ^ 1);
+        mbar_expect_tx(bar(BAR_W_FULL + s), TILE_BYTES);
+        for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_W + s * TILE_BYTES + c * CHUNK, &map_w, c * 64, (t0 + it) * TX, bar(BAR_W_FULL + s));
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    if (lane == 0) {
+      mbar_wait(bar(BAR_A_FULL), 0);
+      for (int it = 0; it < ntiles; ++it) {
+        const int s = it % W_STAGES, zs = it % Z_STAGES;
+        mbar_wait(bar(BAR_W_FULL + s), (it / W_STAGES) & 1);
+        mbar_wait(bar(BAR_Z_EMPTY + zs), ((it / Z_STAGES) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < HK / 16; ++i) {  // 8 k-steps of 16 halfs: chunk i/4, 32-byte slice i%4 of the 128-byte swizzle row
+          const uint64_t da = smem_desc(sbase + OFF_A + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
+          const uint64_t db = smem_desc(sbase + OFF_W + s * TILE_BYTES + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
+          mma_f16(tmem + zs * TX, da, db, IDESC, i > 0);
+        }
+        tc_commit(bar(BAR_Z_FULL + zs));
+        tc_commit(bar(BAR_W_EMPTY + s));
+      }
+    }
+  } else {
+    // ---- epilogue: thread = (team = TMEM lane, column block cb of 32 experts) ----
+    const int q = warp & 3, cb = warp >> 2;
+    const int team = bt * TT + q * 32 + lane;
+    const bool team_ok = team < g.B;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float Tz = 0.f;
+    int bK = 0;
+    if (PASS == 2 && team_ok) {
+      Tz = __ldg(g.thr_val + (size_t)team * g.K + (g.K - 1));
+      bK = __ldg(g.thr_blk + (size_t)team * g.K + (g.K - 1));
+    }
+    const float NEG_INF = __int_as_float(0xff800000);
+    for (int it = 0; it < ntiles; ++it) {
+      const int zs = it % Z_STAGES;
+      const int e_base = (t0 + it) * TX + cb * BLK;  // first expert of this thread's block
+      const int blk = (t0 + it) * 4 + cb;
+      // the block's biases (the same 32 addresses in every lane: broadcast loads); past E: -inf so that the column can never win
+      float bv[BLK];
+      if (e_base + BLK <= g.E) {
+#pragma unroll
+        for (int u = 0; u < BLK / 4; ++u) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(g.bias + e_base) + u);
+          bv[4 * u] = f.x; bv[4 * u + 1] = f.y; bv[4 * u + 2] = f.z; bv[4 * u + 3] = f.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < BLK; ++i) bv[i] = (e_base + i < g.E) ? __ldg(g.bias + e_base + i) : NEG_INF;
+      }
+      mbar_wait(bar(BAR_Z_FULL + zs), (it / Z_STAGES) & 1);
+      tc_fence_after();
+      float z[BLK];
+      tmem_ld32(tmem + lane_base + zs * TX + cb * BLK, z);
+      tc_fence_before();
+      mbar_arrive(bar(BAR_Z_EMPTY + zs));
+      float m = NEG_INF;
+#pragma unroll
+      for (int i = 0; i < BLK; ++i) { z[i] += bv[i]; m = fmaxf(m, z[i]); }
+      if (PASS == 1) {
+        if (team_ok) g.bm[(size_t)team * g.nblk + blk] = m;
+      } else {
+        if (team_ok && m >= Tz && (m > Tz || blk <= bK)) {  // rare: K of the E/32 blocks of a team get here
+#pragma unroll
+          for (int i = 0; i < BLK; ++i) {
+            const float v = z[i];
+            if (v > Tz || (v == Tz && blk <= bK)) {
+              const int slot = atomicAdd(g.cnt + team, 1);
+              if (slot < g.cap) g.cand[(size_t)team * g.cap + slot] = ((unsigned long long)ordered_key(v) << 32) | (uint32_t)(~(uint32_t)(e_base + i));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// per team: the candidates in rank order -> the first K as (probability, global expert id).  One CTA per team; bitonic sort in shared memory.
+constexpr int FIN_THREADS = 128;
+__global__ void __launch_bounds__(FIN_THREADS) infer_topk_final_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cnt, int cap, int K,
+                                                                        int e_lo, float* __restrict__ vals, int32_t* __restrict__ idx) {
+  extern __shared__ unsigned long long sel[];
+  const int n = blockIdx.x;
+  const int c = min(cnt[n], cap);
+  int npad = 32;
+  while (npad < c) npad <<= 1;
+  for (int i = threadIdx.x; i < npad; i += FIN_THREADS) sel[i] = i < c ? cand[(size_t)n * cap + i] : 0ull;
+  __syncthreads();
+  for (int k = 2; k <= npad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npad; i += FIN_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long x = sel[i], y = sel[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (x < y) : (x > y)) { sel[i] = y; sel[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  constexpr float LOG2E = 1.4426950408889634f;
+  for (int i = threadIdx.x; i < K; i += FIN_THREADS) {
+    const unsigned long long cmp = i < c ? sel[i] : 0ull;
+    float p = 0.f;
+    int32_t e = -1;
+    if (cmp) {
+      const float zz = key_to_float((uint32_t)(cmp >> 32));
+      const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);           // the arithmetic of ntf_infer_scores' tensor-core epilogue (out_tc.cu, MODE 1)
+      const float ex = ex2_approx(fabsf(x) * -LOG2E);
+      const float r = rcp_approx(1.f + ex);
+      p = zz > 0.f ? r : ex * r;
+      e = e_lo + (int32_t)(~(uint32_t)cmp);
+    }
+    vals[(size_t)n * K + i] = p;
+    idx[(size_t)n * K + i] = e;
+  }
+}
+
+__global__ void to_half_kernel(const float* __restrict__ x, size_t n, __half* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = __float2half_rn(x[i]);
+}
+
+struct ItWs { size_t a16, bm, tv, ti, cnt, cand, total; };
+ItWs it_ws(int B, int h, int E, int K) {
+  const size_t nblk = (size_t)cdiv(E, TX) * 4;
+  ItWs w;
+  w.a16 = 0;
+  w.bm = w.a16 + align_up((size_t)B * h * sizeof(__half), 1024);
+  w.tv = w.bm + align_up((size_t)B * nblk * sizeof(float), 1024);
+  w.ti = w.tv + align_up((size_t)B * K * sizeof(float), 1024);
+  w.cnt = w.ti + align_up((size_t)B * K * sizeof(int32_t), 1024);
+  w.cand = w.cnt + align_up((size_t)B * sizeof(int), 1024);
+  w.total = w.cand + align_up((size_t)B * (size_t)(BLK * K) * sizeof(unsigned long long), 1024);
+  return w;
+}
+}  // namespace
+
+extern "C" int ntf_to_half(ntf_ctx* ctx, void* stream, const float* x, size_t n, void* y) {
+  NTF_REQUIRE(ctx && x && y, NTF_ERR_BAD_ARG, "to_half: null pointer");
+  if (n == 0) return NTF_OK;
+  const size_t blocks = (n + 255) / 256;
+  NTF_COUNT_LAUNCH; to_half_kernel<<<(unsigned)(blocks < (size_t)ctx->sm_count * 8 ? blocks : (size_t)ctx->sm_count * 8), 256, 0, as_stream(stream)>>>(x, n, (__half*)y);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
+
+// the fused path needs the tensor-core width, at least K blocks of 32 experts per team, and a candidate list that sorts in shared memory
+extern "C" int ntf_infer_topk_supported(int B, int h, int E, int K) {
+  return (h == HK && B >= 1 && K >= 1 && K <= 128 && (long long)K * BLK <= (long long)E) ? 1 : 0;
+}
+
+extern "C" size_t ntf_infer_topk_workspace_bytes(int B, int h, int E, int K) { return it_ws(B, h, E, K).total; }
+
+extern "C" int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_args* a, void* workspace, size_t workspace_bytes) {
+  NTF_REQUIRE(ctx && a && a->W16 && a->b && a->vals && a->idx && (a->A || a->A16), NTF_ERR_BAD_ARG, "infer_topk: null pointer");
+  NTF_REQUIRE(ntf_infer_topk_supported(a->B, a->h, a->E, a->K), NTF_ERR_UNSUPPORTED, "infer_topk: B=%d h=%d E=%d K=%d (needs h=%d, K <= 128, 32*K <= E)", a->B, a->h, a->E,
+              a->K, HK);
+  const ItWs w = it_ws(a->B, a->h, a->E, a->K);
+  NTF_REQUIRE(workspace && workspace_bytes >= w.total, NTF_ERR_WORKSPACE, "infer_topk: workspace too small");
+  NTF_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)a->W16 & 15) == 0 && ((uintptr_t)a->b & 15) == 0, NTF_ERR_BAD_ARG, "infer_topk: misaligned pointer");
+  cudaStream_t st = as_stream(stream);
+  char* ws = (char*)workspace;
+  const __half* A16 = (const __half*)a->A16;
+  if (!A16) {
+    NTF_REQUIRE(((uintptr_t)a->A & 15) == 0, NTF_ERR_BAD_ARG, "infer_topk: misaligned activations");
+    int rc = ntf_to_half(ctx, stream, a->A, (size_t)a->B * a->h, ws + w.a16);
+    if (rc) return rc;
+    A16 = (const __half*)(ws + w.a16);
+  }
+  NTF_REQUIRE(((uintptr_t)A16 & 15) == 0, NTF_ERR_BAD_ARG, "infer_topk: misaligned fp16 activations");
+  ItArgs g{};
+  g.bias = a->b; g.B = a->B; g.E = a->E; g.K = a->K;
+  g.nbt = cdiv(a->B, TT); g.nct = cdiv(a->E, TX);
+  const int sm = ctx->sm_count > 0 ? ctx->sm_count : 148;
+  g.nchunk = g.nbt >= sm ? 1 : sm / g.nbt;  // one wave: batch tiles x chunks <= SMs
+  if (g.nchunk > g.nct) g.nchunk = g.nct;
+  g.nblk = g.nct * 4;
+  g.bm = (float*)(ws + w.bm);
+  float* tv = (float*)(ws + w.tv);
+  int32_t* ti = (int32_t*)(ws + w.ti);
+  g.thr_val = tv; g.thr_blk = ti;
+  g.cnt = (int*)(ws + w.cnt);
+  g.cand = (unsigned long long*)(ws + w.cand);
+  g.cap = BLK * a->K;
+  CUtensorMap ma, mw;
+  int rc;
+  if ((rc = make_map(ctx, &ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)a->B, HK, TT, 64))) return rc;
+  if ((rc = make_map(ctx, &mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->W16, (uint64_t)a->E, HK, TX, 64))) return rc;
+  const int grid = g.nbt * g.nchunk;
+  NTF_CUDA(cudaFuncSetAttribute(infer_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  NTF_CUDA(cudaFuncSetAttribute(infer_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  NTF_CUDA(cudaMemsetAsync(g.cnt, 0, (size_t)a->B * sizeof(int), st));
+  NTF_COUNT_LAUNCH; infer_topk_kernel<1><<<grid, NT, SMEM_BYTES, st>>>(ma, mw, g);
+  NTF_LAUNCH_CHECK();
+  if ((rc = ntf_topk_select(ctx, stream, g.bm, a->B, g.nblk, a->K, 1.0f, tv, ti))) return rc;
+  NTF_COUNT_LAUNCH; infer_topk_kernel<2><<<grid, NT, SMEM_BYTES, st>>>(ma, mw, g);
+  NTF_LAUNCH_CHECK();
+  int npad = 32;
+  while (npad < g.cap) npad <<= 1;
+  NTF_COUNT_LAUNCH; infer_topk_final_kernel<<<a->B, FIN_THREADS, (size_t)npad * 8, st>>>(g.cand, g.cnt, g.cap, a->K, a->e_lo, a->vals, a->idx);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}

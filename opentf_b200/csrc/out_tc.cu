@@ -34,7 +34,7 @@
 
 #include <type_traits>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 int ntf_loss_reduce_impl(cudaStream_t st, const float* part, int n, float scale, float* loss_out);
 
@@ -75,77 +75,6 @@ enum { BAR_W32 = 0, BAR_W16 = 1, BAR_A_FULL = 2, BAR_A_EMPTY = 5, BAR_Z_FULL = 8
 // SP_* : special / member bit planes of a tile (2-stage ring, filled by 1-D bulk copies from the tile-transposed planes in HBM)
 // Q_*  : Flipout only: the tile of the perturbation term (one stage, living in the third activation slot; the activation ring has 2 stages then)
 
-// ---- PTX wrappers -----------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets TMEM lane (lane_base + t), columns [col, col+32)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
-      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// ---- descriptors (cute/arch/mma_sm100_desc.hpp bit layout) ------------------------------------------------------
-// shared memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | swizzle [61,64) (2 = 128B)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) |
-         (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D fmt [4,6) 1=f32 | A fmt [7,10) | B fmt [10,13) (0=f16, 2=tf32) | A major [15] | B major [16] (1 = MN) | N>>3 [17,23) | M>>4 [24,29)
-constexpr uint32_t instr_desc(uint32_t fmt, uint32_t a_mn, uint32_t b_mn, uint32_t M, uint32_t N) {
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
-}
-
-
 struct TcArgs {
   const float* bias;          // [E]
   uint32_t* special_t;        // tile-transposed planes (ntf_special_tiles), or NULL: every weight tnw, every target 0.
@@ -178,22 +107,6 @@ constexpr int EPI_WARPS = 16;
 constexpr int NT = 736;  // warps 0-15: logits/loss epilogue, 16-19: dA epilogue, 20: TMA, 21: MMA issuer, 22: special planes (23 warps: 88 registers per thread)
 constexpr int WARP_DA = 16, WARP_TMA = 20, WARP_MMA = 21, WARP_SP = 22;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float lg2_approx(float x) {
-  float r;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
 
 constexpr uint32_t IDESC_FWD = instr_desc(0, 0, 0, TE, TB);   // Z^T  = W16(K-major) . A16(K-major)^T                     K = hidden
 constexpr uint32_t IDESC_DW = instr_desc(0, 0, 1, TE, HK);    // dW  += dz^T(K-major: K = teams) . A16(MN-major: N = hidden)
@@ -787,21 +700,6 @@ __global__ void sign_tiles_kernel(const uint32_t* __restrict__ sign, int B, int 
   sign_t[((size_t)t * Epad + wc * 32 + lane) * 4 + cb] = mine;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int make_map(const ntf_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-             uint32_t box_cols) {
-  NTF_REQUIRE(ctx->encode_tiled != nullptr, NTF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t gdim[2] = {cols, rows};
-  const cuuint64_t gstride[1] = {cols * (uint64_t)esize};
-  const cuuint32_t box[2] = {box_cols, box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  NTF_REQUIRE(r == CUDA_SUCCESS, NTF_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  return NTF_OK;
-}
 }  // namespace
 
 int ntf_out_tc_supported(int B, int h, int E, int flipout) { (void)flipout; return (h == HK && B >= 1 && E >= 1) ? 1 : 0; }

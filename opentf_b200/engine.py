@@ -261,6 +261,7 @@ class Engine:
             v = self.view(name)
             if tuple(t.shape) != tuple(v.shape): raise ValueError(f'{name}: shape {tuple(t.shape)} does not fit {tuple(v.shape)}')
             v.copy_(t.contiguous())
+        self._load_ver = getattr(self, '_load_ver', 0) + 1
 
     def state_dict(self, gather=True):
         """torch-layout state dict.  Expert-sharded: the last layer's shards are all-gathered (a collective: every rank calls it);
@@ -786,10 +787,48 @@ class Engine:
                          self.E, out, self.ws)
         return out
 
+    def w16(self):
+        """fp16 image of the output layer's weight for the fused top-K kernel, refreshed when the parameters changed since it was made"""
+        Lo = self.L - 1
+        W = self.view(f'layers.{Lo}.weight')
+        if getattr(self, '_w16', None) is None or self._w16.numel() != W.numel():
+            self._w16, self._w16_ver = torch.empty(W.numel(), dtype=torch.float16, device=self.device), None
+        ver = (self.adam_t, self.global_step, getattr(self, '_load_ver', 0), W.data_ptr())
+        if self._w16_ver != ver:
+            ops.to_half(W, W.numel(), self._w16)
+            self._w16_ver = ver
+        return self._w16
+
+    def fused_topk_ok(self, B, K):
+        return (not self.bayesian and self.precision == _lib.NTF_TF32 and os.environ.get('NTF_FUSED_TOPK', '1') != '0'
+                and ops.infer_topk_supported(B, self.hidden[-1], self.E, min(K, self.E)))
+
     def topk(self, sp, b0, B, K, scores_buf, vals, idx):
-        """the K best experts per team in rank order; only [B,K] leaves the GPU (fnn.py:213-218 keeps [N,E] on the host)."""
+        """the K best experts per team in rank order; only [B,K] leaves the GPU (fnn.py:213-218 keeps [N,E] on the host).
+        Tensor-core mode with K <= 128 and 32*K <= E: output layer + sigmoid + selection fused (ntf_infer_topk), the [B,E] scores
+        never reach HBM; otherwise scores -> ntf_topk_select."""
+        if self.fused_topk_ok(B, K):
+            self._forward_hidden(sp, b0, B)
+            return self.select_topk_fused(B, K, vals, idx)
         self.scores(sp, b0, B, scores_buf)
         return self.select_topk(scores_buf, B, K, vals, idx)
+
+    def select_topk_fused(self, B, K, vals, idx):
+        """top-K of the batch whose last hidden activations are in self.act[-1].  Expert-sharded: local fused top-K (global ids), then the
+        all-gather + ntf_topk_merge of select_topk"""
+        Lo, n = self.L - 1, self.shard[1]
+        if n == 1:
+            ops.infer_topk(self.act[-1], self.w16(), self.view(f'layers.{Lo}.bias'), B, self.hidden[-1], self.E, K, vals, idx, self.ws)
+            return vals, idx
+        Kl = min(K, self.E)
+        lv = torch.zeros(B, K, dtype=torch.float32, device=self.device)
+        li = torch.full((B, K), -1, dtype=torch.int32, device=self.device)
+        v_, i_ = torch.empty(B, Kl, dtype=torch.float32, device=self.device), torch.empty(B, Kl, dtype=torch.int32, device=self.device)
+        ops.infer_topk(self.act[-1], self.w16(), self.view(f'layers.{Lo}.bias'), B, self.hidden[-1], self.E, Kl, v_, i_, self.ws, e_lo=self.e_lo)
+        lv[:, :Kl] = v_; li[:, :Kl] = i_
+        gv, gi = self.allgather(lv), self.allgather(li)
+        ops.topk_merge(gv, gi, n, B, K, vals, idx)
+        return vals, idx
 
     def select_topk(self, scores_buf, B, K, vals, idx):
         """rank order per team.  Expert-sharded: every rank ranks its own columns, the [B,K] lists (global expert ids) are

@@ -272,29 +272,57 @@ class Fnn(Ntf):
         quirk that the lists are re-created per batch so only the LAST batch's entropies are saved (fnn.py:203)."""
         torch, eng = Ntf.torch, self.engine
         bb = min(b, max(1, sp.n))
-        scores = torch.empty(bb, eng.E, dtype=torch.float32, device=eng.device)
         bayes = eng.bayesian
+        fused = K is not None and eng.fused_topk_ok(bb, K)  # output layer + sigmoid + top-K in one call: no [B,E] score buffer at all
+        scores = None if fused else torch.empty(bb, eng.E, dtype=torch.float32, device=eng.device)
         if bayes:
             nmc = int(self._c('nmc', 2))
             scratch = torch.empty(bb, eng.E, dtype=torch.float32, device=eng.device)
             ent_pred, ent_model = torch.empty(bb, dtype=torch.float32, device=eng.device), torch.empty(bb, dtype=torch.float32, device=eng.device)
         unc = None
-        out = torch.empty(sp.n, eng.E_total, dtype=torch.float32) if K is None else None
+        # data-parallel ranks (replicas): the teams of the set are independent, so batch i is predicted by rank i % world and the
+        # pieces are put together afterwards (SURVEY.md 8e; the expert-sharded layer instead runs every batch on every rank)
+        G, r = (eng.world, eng.rank) if eng.shard[1] == 1 else (1, 0)
+        nb = -(-sp.n // b)
+        out = torch.empty(sp.n, eng.E_total, dtype=torch.float32) if (K is None and eng.rank == 0) else None
         if K is not None:
-            vals = torch.empty(sp.n, K, dtype=torch.float32, device=eng.device)
-            idx = torch.empty(sp.n, K, dtype=torch.int32, device=eng.device)
-        for b0 in range(0, sp.n, b):
+            vals = torch.zeros(sp.n, K, dtype=torch.float32, device=eng.device)
+            idx = torch.zeros(sp.n, K, dtype=torch.int32, device=eng.device)
+        for bi in range(nb):
+            b0 = bi * b
             B = min(b, sp.n - b0)
-            if bayes:
-                eng.scores_mc(sp, b0, B, nmc, scores, scratch, ent_pred, ent_model)
-                unc = {'pred': [ent_pred[:B].cpu().numpy()], 'model': [ent_model[:B].cpu().numpy()]}
-            else:
-                eng.scores(sp, b0, B, scores)
+            mine = bi % G == r
+            if mine:
+                if bayes:
+                    eng.scores_mc(sp, b0, B, nmc, scores, scratch, ent_pred, ent_model)
+                    if bi == nb - 1: unc = {'pred': [ent_pred[:B].cpu().numpy()], 'model': [ent_model[:B].cpu().numpy()]}
+                elif fused:
+                    eng._forward_hidden(sp, b0, B)
+                    eng.select_topk_fused(B, K, vals[b0:b0 + B], idx[b0:b0 + B])
+                else:
+                    eng.scores(sp, b0, B, scores)
+                if K is not None and not fused: eng.select_topk(scores, B, K, vals[b0:b0 + B], idx[b0:b0 + B])
             if K is None:  # batch by batch, as fnn.py:211-212 does (expert-sharded: the column blocks of the ranks side by side)
-                if eng.shard[1] == 1: out[b0:b0 + B] = scores[:B].cpu()
-                else: out[b0:b0 + B] = self._gather_columns(scores[:B])
-            else: eng.select_topk(scores, B, K, vals[b0:b0 + B], idx[b0:b0 + B])
+                if eng.shard[1] > 1:
+                    g = self._gather_columns(scores[:B])
+                    if out is not None: out[b0:b0 + B] = g
+                elif G == 1: out[b0:b0 + B] = scores[:B].cpu()
+                elif bi % G == G - 1 or bi == nb - 1:  # a round of G batches is done: every rank hands its batch to rank 0
+                    parts = [torch.empty_like(scores) for _ in range(G)] if r == 0 else None
+                    torch.distributed.gather(scores, parts, dst=0)
+                    if r == 0:
+                        for q in range(bi % G + 1):
+                            bq = (bi - bi % G + q) * b
+                            out[bq:bq + min(b, sp.n - bq)] = parts[q][:min(b, sp.n - bq)].cpu()
+        if G > 1 and bayes:  # the reference keeps the LAST batch's entropies (fnn.py:203): they live on the rank that predicted it
+            last_B = sp.n - (nb - 1) * b
+            buf = torch.zeros(2, last_B, dtype=torch.float32, device=eng.device)
+            if unc is not None: buf[0], buf[1] = torch.as_tensor(unc['pred'][0], device=eng.device), torch.as_tensor(unc['model'][0], device=eng.device)
+            torch.distributed.broadcast(buf, src=(nb - 1) % G)
+            unc = {'pred': [buf[0].cpu().numpy()], 'model': [buf[1].cpu().numpy()]}
         if K is None: return out, unc
+        if G > 1:  # every row was written by exactly one rank, zeros elsewhere
+            torch.distributed.all_reduce(vals); torch.distributed.all_reduce(idx)
         return util.topk_to_sparse(torch, vals.cpu(), idx.cpu(), eng.E_total), unc
 
 

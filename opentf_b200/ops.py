@@ -176,6 +176,27 @@ def topk_select(P, B, E, K, scale, vals, idx):
     check(lib().ntf_topk_select(_lib.ctx(d), _stream(d), _p(P, F32), B, E, K, scale, _p(vals, F32), _p(idx, I32)), 'ntf_topk_select')
 
 
+def infer_topk_supported(B, h, E, K):
+    return bool(lib().ntf_infer_topk_supported(int(B), int(h), int(E), int(K)))
+
+
+def to_half(x, n, y):
+    d = _dev(x)
+    assert y.dtype == torch.float16 and y.numel() >= n
+    check(lib().ntf_to_half(_lib.ctx(d), _stream(d), _p(x, F32), n, _p(y)), 'ntf_to_half')
+
+
+def infer_topk(A, W16, b, B, h, E, K, vals, idx, ws, e_lo=0, A16=None):
+    """fused output layer + sigmoid + top-K (csrc/infer_topk.cu): only [B,K] values / ids are written"""
+    d = _dev(W16)
+    a = _lib.InferTopkArgs()
+    a.A, a.A16, a.W16, a.b = _p(A, F32), _p(A16), _p(W16), _p(b, F32)
+    a.B, a.h, a.E, a.K, a.e_lo = B, h, E, K, e_lo
+    a.vals, a.idx = _p(vals, F32), _p(idx, I32)
+    p, nb = ws.get(lib().ntf_infer_topk_workspace_bytes(B, h, E, K))
+    check(lib().ntf_infer_topk(_lib.ctx(d), _stream(d), C.byref(a), p, nb), 'ntf_infer_topk')
+
+
 def topk_merge(vals_in, idx_in, G, B, K, vals, idx):
     d = _dev(vals_in)
     check(lib().ntf_topk_merge(_lib.ctx(d), _stream(d), _p(vals_in, F32), _p(idx_in, I32), G, B, K, _p(vals, F32), _p(idx, I32)), 'ntf_topk_merge')

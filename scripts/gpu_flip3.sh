@@ -7,3 +7,4 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv | tee $OUT/gpu.
 for e in 0 32 16 48; do
   echo "== NTF_TC_EXP=$e"; NTF_TC_EXP=$e timeout 300 python scripts/flip_stress3.py 40 2>&1 | tail -40 | tee $OUT/stress3_exp$e.txt
 done
+echo "== mb_reduce"; timeout 120 ./scripts/mb/mb_reduce 2>&1 | tee $OUT/mb_reduce.txt
