@@ -155,17 +155,58 @@ def cpu_reference_steps(tv, splits, batch, nsd, max_seconds, min_steps=1, warmup
     return n * batch / dt, n, dt, torch.get_num_threads()
 
 
+def verbatim_reference_steps(tv, splits, batch, nsd, steps, warmup):
+    """the UNMODIFIED reference (src/mdl/fnn.py `Fnn.learn`, placed under oracle/_ref by oracle/make_ref.py, imported through the
+    environment shims of oracle/ref_shim.py) on the CPU with all host threads: one epoch over (warmup + steps) fold-0 train batches of
+    the same workload, through its own DataLoader / NtfDataset (per-row lil -> dense, ntf.py:17-25), bxe, autograd and torch.optim.Adam.
+    Step boundaries come from a global optimizer-step post hook (the reference calls optimizer.step() once per batch, fnn.py:139), so
+    nothing of the reference is edited.  Returns (teams/s over the timed steps, steps, seconds, threads)."""
+    import tempfile
+    import torch
+    from oracle import ref_shim
+    torch.set_num_threads(os.cpu_count())
+    Fnn = ref_shim.load_reference_fnn()
+    rows = np.asarray(splits['folds'][0]['train'])[:(warmup + steps) * batch]
+    assert len(rows) == (warmup + steps) * batch, 'workload smaller than the requested sample'
+    sub = {'test': np.asarray(splits['test'])[:1], 'folds': {0: {'train': rows, 'valid': np.asarray(splits['folds'][0]['valid'])[:min(batch, 64)]}}}
+    teamsvecs = {'skill': tv['skill'].tolil(), 'member': tv['member'].tolil()}  # what the reference is handed (team.py:154)
+    stamps = []
+    from torch.optim.optimizer import register_optimizer_step_post_hook
+    handle = register_optimizer_step_post_hook(lambda *a, **k: stamps.append(time.perf_counter()))
+    try:
+        with tempfile.TemporaryDirectory() as out:
+            f = Fnn(out, 'cpu', 0, ref_shim.default_cfg(b=batch, e=1, nsd=nsd, spe=0))
+            f.learn(teamsvecs, sub, None)
+    finally:
+        handle.remove()
+    assert len(stamps) == warmup + steps, (len(stamps), warmup, steps)
+    dt = stamps[-1] - stamps[warmup - 1] if warmup > 0 else None
+    assert dt is not None, 'the reference arm needs at least one warm-up step (its end is the start of the timed region)'
+    return steps * batch / dt, steps, dt, torch.get_num_threads()
+
+
+def reference_arm(tv, splits, batch, nsd, steps, warmup):
+    """-> (teams/s, steps, seconds, threads, kind, what): the verbatim reference when oracle/_ref (or /root/reference) is there, else the oracle port"""
+    from oracle import ref_shim
+    if ref_shim.available():
+        v, n, dt, th = verbatim_reference_steps(tv, splits, batch, nsd, steps, max(1, warmup))
+        return v, n, dt, th, 'reference', ('UNMODIFIED reference src/mdl/fnn.py Fnn.learn (oracle/_ref via oracle/ref_shim.py): DataLoader + per-row lil->dense, bxe, '
+                                           'autograd, Adam, loss.item(); step boundaries from an optimizer-step hook')
+    v, n, dt, th = cpu_reference_steps(tv, splits, batch, nsd, 1e9, min_steps=steps, warmup=warmup, max_steps=steps)
+    return v, n, dt, th, 'port', 'oracle port of fnn.py:118-140 incl. per-row densification (oracle/_ref absent)'
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0: return  # rank 0 alone runs the CPU arm
     tv, splits = workload(args.workload)
-    steps = max(1, min(args.steps, 20))
-    v, n, dt, threads = cpu_reference_steps(tv, splits, args.batch, args.nsd, 1e9, min_steps=steps, warmup=min(args.warmup, 2), max_steps=steps)
-    sample = f'{n} steps of b={args.batch} on fold-0 train rows of the {args.workload}-shaped workload (oracle port of fnn.py:118-140 incl. per-row densification)'
+    steps = max(1, min(args.steps, 40))  # bounded sample: ~1.3 s per step of b=1000 on 16 cores
+    v, n, dt, threads, kind, what = reference_arm(tv, splits, args.batch, args.nsd, steps, args.warmup)
+    sample = f'{n} steps of b={args.batch} on fold-0 train rows of the {args.workload}-shaped workload after {max(1, args.warmup)} warm-up steps; {what}'
     print(json.dumps({
-        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': n, 'warmup': min(args.warmup, 2),
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': n, 'warmup': args.warmup,
         'ms_per_step': 1e3 * dt / n, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': config_of(args, tv), 'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'config': config_of(args, tv), 'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': kind, 'sample': sample},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
 
 
@@ -348,9 +389,8 @@ def run_ours(args):
                                                    xmode, 'torch.distributed.all_reduce between the halves of a step'), 'host_enqueue_ms_per_step': host_ms, 'roofline': roof, 'infer_topk': {'k': args.infer_k, 'value': infer_value, 'unit': 'teams/s', 'batch': ib}}
     out.update(extras)
     if not args.no_cpu_baseline:
-        v, n, dt, threads = cpu_reference_steps(tv, splits, b, args.nsd, args.cpu_baseline_seconds)
-        out['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                               'sample': f'{n} steps of b={b} ({dt:.1f} s) of the same workload, oracle port of fnn.py:118-140 incl. per-row densification'}
+        v, n, dt, threads, kind, what = reference_arm(tv, splits, b, args.nsd, max(1, int(args.cpu_baseline_seconds / 1.3)), 1)
+        out['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': kind, 'sample': f'{n} steps of b={b} ({dt:.1f} s) of the same workload; {what}'}
     print(json.dumps(out))
     if world > 1: dist.destroy_process_group()
 

@@ -3,8 +3,9 @@
 TEST INFRASTRUCTURE ONLY.  This module exists to (a) pin the oracle restatement
 (`oracle/fnn_oracle.py`) against the real reference and (b) generate the golden
 fixtures under `tests/golden/` (see `tests/golden/make_golden.py`).  It is never
-imported by the product (`opentf_b200/`), and it cannot run on the GPU box because
-`/root/reference` does not exist there.
+imported by the product (`opentf_b200/`).  On the GPU box `/root/reference` does not exist:
+there the same unmodified files are found under `oracle/_ref/src` (placed by `oracle/make_ref.py`
+at build time, git-ignored) and serve as the CPU baseline of `bench.py`.
 
 Five environment shims, none of which touches arithmetic:
   1. a stub `pkgmgr` module (the real one imports omegaconf and opens
@@ -16,11 +17,12 @@ Five environment shims, none of which touches arithmetic:
 """
 import importlib, os, random, sys, types
 
-REF_SRC = '/root/reference/src'
+_LOCAL = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref', 'src')
+REF_SRC = '/root/reference/src' if os.path.isdir('/root/reference/src/mdl') else _LOCAL
 
 
 def available():
-    return os.path.isdir(REF_SRC)
+    return os.path.isfile(os.path.join(REF_SRC, 'mdl', 'fnn.py'))
 
 
 class Cfg(dict):
