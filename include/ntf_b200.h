@@ -191,6 +191,8 @@ typedef struct {
   uint32_t* member_t;
   int e_lo;                    /* expert-sharded layer: W/b/dW/db and the planes cover columns [e_lo, e_lo+E); m_indices are global */
   const void* A16;             /* NTF_TF32, optional: A as fp16 [B,h] already (the producing kernel wrote it); NULL: converted here */
+  const void* W16;             /* NTF_TF32, optional: fp16 image of W [E,h] kept by the caller (ntf_to_half; the optimiser entry points of ntf_fnn_step
+                                  rewrite it); NULL: made per call.  Ignored by the Flipout layer */
 } ntf_out_train_args;
 /* 1 if NTF_TF32 has a tcgen05 kernel for this shape (else callers use NTF_FP32; ntf_out_train(NTF_TF32) refuses it) */
 int ntf_tc_supported(int B, int h, int E, int flipout);
@@ -226,7 +228,7 @@ typedef struct ntf_infer_topk_args {
   float* vals;      /* [B,K] out: probabilities, rank order */
   int32_t* idx;     /* [B,K] out: expert ids */
 } ntf_infer_topk_args;
-int ntf_infer_topk_supported(int B, int h, int E, int K); /* h == 128, K <= 128, 32*K <= E */
+int ntf_infer_topk_supported(int B, int h, int E, int K); /* h == 128, K <= 128, 32*K <= E <= 131072 */
 size_t ntf_infer_topk_workspace_bytes(int B, int h, int E, int K);
 int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_args* args, void* workspace, size_t workspace_bytes);
 /* y[i] = fp16(x[i]) round-to-nearest: the fp16 operand images the tensor-core kernels read (10-bit mantissa = TF32's) */
@@ -368,6 +370,28 @@ typedef struct {
 } ntf_fnn_step_args;
 size_t ntf_fnn_step_workspace_bytes(const ntf_ctx* ctx, const ntf_fnn_step_args* args);
 int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args* args, void* workspace, size_t workspace_bytes);
+
+/* one call per test batch (the loop body of fnn.py:198-218): hidden layers (layer 0 = CSR bag, or dense rows when x_dense is set), then
+ * ntf_infer_topk.  W[i]/b[i]: layer i's parameters as in ntf_fnn_step_args (layer 0 transposed [S,h0] for the CSR input); act[i]: [B,hidden[i]]
+ * scratch; W16: fp16 image of W[n_layers-1]. */
+typedef struct ntf_fnn_infer_topk_args {
+  int n_layers, S, E, e_lo;
+  int hidden[NTF_MAX_LAYERS];
+  const float* W[NTF_MAX_LAYERS];
+  const float* b[NTF_MAX_LAYERS];
+  float* act[NTF_MAX_LAYERS];
+  int B;
+  const int32_t* s_indptr;  /* B+1 absolute offsets into s_indices */
+  const int32_t* s_indices;
+  const float* x_dense;     /* [B,S] embedded skills (ntf.py:24) instead of the CSR rows, or NULL */
+  const void* W16;
+  int K;
+  float* vals;
+  int32_t* idx;
+} ntf_fnn_infer_topk_args;
+size_t ntf_fnn_infer_topk_workspace_bytes(const ntf_ctx* ctx, const ntf_fnn_infer_topk_args* args);
+int ntf_fnn_infer_topk(ntf_ctx* ctx, void* stream, const ntf_fnn_infer_topk_args* args, void* workspace, size_t workspace_bytes);
+
 
 /* out[i] = sum_k parts[k*part_stride + i] in a fixed order (deterministic split reductions) */
 int ntf_sum_parts(ntf_ctx* ctx, void* stream, const float* parts, int nparts, size_t n, size_t part_stride, float* out);

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libntf_b200.so')
+LIB_PATH = os.environ.get('NTF_B200_LIB') or os.path.join(_HERE, 'csrc', 'libntf_b200.so')  # (NTF_B200_LIB: bug-hunt builds, scripts/flip_variants.sh)
 
 NTF_FP32, NTF_TF32 = 0, 1
 NSD = {None: 0, '': 0, 'none': 0, 'None': 0, 'uniform': 1, 'unigram': 2, 'unigram_b': 3}
@@ -21,7 +21,7 @@ class OutTrainArgs(C.Structure):
     _fields_ = [('A', vp), ('W', vp), ('b', vp), ('special', vp), ('pitch_words', i32), ('m_indptr', vp), ('m_indices', vp),
                 ('B', i32), ('h', i32), ('E', i32), ('tpw', f32), ('tnw', f32), ('loss_scale', f32),
                 ('dW', vp), ('db', vp), ('dA', vp), ('loss_out', vp),
-                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp), ('e_lo', i32), ('A16', vp)]
+                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp), ('e_lo', i32), ('A16', vp), ('W16', vp)]
 
 
 class InferTopkArgs(C.Structure):
@@ -39,6 +39,12 @@ NTF_MAX_PEERS = 8
 class Peers(C.Structure):
     """mirror of ntf_peers"""
     _fields_ = [('rank', i32), ('world', i32), ('grads', vp * NTF_MAX_PEERS), ('params', vp * NTF_MAX_PEERS), ('flags', vp * NTF_MAX_PEERS)]
+
+
+class FnnInferTopkArgs(C.Structure):
+    """mirror of ntf_fnn_infer_topk_args"""
+    _fields_ = [('n_layers', i32), ('S', i32), ('E', i32), ('e_lo', i32), ('hidden', i32 * NTF_MAX_LAYERS), ('W', _PA), ('b', _PA), ('act', _PA),
+                ('B', i32), ('s_indptr', vp), ('s_indices', vp), ('x_dense', vp), ('W16', vp), ('K', i32), ('vals', vp), ('idx', vp)]
 
 
 class FnnStepArgs(C.Structure):
@@ -119,6 +125,8 @@ SIGNATURES = {
     'ntf_add_signed': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     'ntf_fnn_step_workspace_bytes': (sz, [vp, C.POINTER(FnnStepArgs)]),
     'ntf_fnn_step': (i32, [vp, vp, C.POINTER(FnnStepArgs), vp, sz]),
+    'ntf_fnn_infer_topk_workspace_bytes': (sz, [vp, C.POINTER(FnnInferTopkArgs)]),
+    'ntf_fnn_infer_topk': (i32, [vp, vp, C.POINTER(FnnInferTopkArgs), vp, sz]),
     'ntf_sum_parts': (i32, [vp, vp, vp, i32, sz, sz, vp]),
 }
 

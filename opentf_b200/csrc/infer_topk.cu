@@ -64,8 +64,8 @@ struct ItArgs {
   int nbt, nct, nchunk;  // batch tiles, expert tiles, chunks of expert tiles
   int nblk;              // row pitch of bm = 4 * nct (blocks of 32 experts, the last tile padded)
   float* bm;             // pass 1 out: [B, nblk] block maxima (-inf for blocks past E)
-  const float* thr_val;  // pass 2 in: [B, K] the K largest block maxima in rank order, and
-  const int32_t* thr_blk;  //          [B, K] their block ids (ntf_topk_select on bm)
+  float* thr_val;        // pass 2 in: [B] the K-th largest block maximum of the team (blockmax_threshold_kernel), and
+  int32_t* thr_blk;      //            [B] the block it belongs to under the rank order (value descending, block ascending)
   unsigned long long* cand;  // pass 2 out: [B, cap] composites (ordered logit << 32 | ~expert)
   int* cnt;                  // [B] candidates appended so far (zeroed by the caller)
   int cap;
@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
     float Tz = 0.f;
     int bK = 0;
     if (PASS == 2 && team_ok) {
-      Tz = __ldg(g.thr_val + (size_t)team * g.K + (g.K - 1));
-      bK = __ldg(g.thr_blk + (size_t)team * g.K + (g.K - 1));
+      Tz = __ldg(g.thr_val + team);
+      bK = __ldg(g.thr_blk + team);
     }
     const float NEG_INF = __int_as_float(0xff800000);
     for (int it = 0; it < ntiles; ++it) {
@@ -232,6 +232,50 @@ __global__ void __launch_bounds__(FIN_THREADS) infer_topk_final_kernel(const uns
   }
 }
 
+// per team (one warp): Tz = the K-th largest of the row's block maxima and bK = the block that holds it under the rank order (value
+// descending, ties -> lower block first).  Bisection on the order-preserving integer image of the fp32 maxima: 32 rounds of "how many
+// keys >= candidate", the row held in registers (PL keys per lane, contiguous chunks so that ties can be ranked by block id).
+template <int PL>
+__global__ void __launch_bounds__(128) blockmax_threshold_kernel(const float* __restrict__ bm, int B, int nblk, int K, float* __restrict__ thr_val,
+                                                                 int32_t* __restrict__ thr_blk) {
+  const int team = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (team >= B) return;
+  const int per = (nblk + 31) / 32;  // <= PL (checked by the host)
+  const float* row = bm + (size_t)team * nblk;
+  const int first = lane * per;
+  uint32_t key[PL];
+#pragma unroll
+  for (int i = 0; i < PL; ++i) key[i] = (i < per && first + i < nblk) ? ordered_key(__ldg(row + first + i)) : 0u;  // 0 < every real key
+  uint32_t T = 0u;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < PL; ++i) c += key[i] >= cand;
+    if (__reduce_add_sync(0xffffffffu, c) >= K) T = cand;
+  }
+  int gt = 0, eq = 0;
+#pragma unroll
+  for (int i = 0; i < PL; ++i) { gt += key[i] > T; eq += key[i] == T; }
+  const int need = K - __reduce_add_sync(0xffffffffu, gt);  // the need-th block (in id order) whose maximum equals Tz is the K-th block
+  int incl = eq;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int before = incl - eq;
+  if (before < need && need <= incl) {
+    int seen = before, blk = first;
+#pragma unroll
+    for (int i = 0; i < PL; ++i)
+      if (key[i] == T && ++seen == need) blk = first + i;
+    thr_val[team] = key_to_float(T);
+    thr_blk[team] = blk;
+  }
+}
+
 __global__ void to_half_kernel(const float* __restrict__ x, size_t n, __half* __restrict__ y) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = __float2half_rn(x[i]);
 }
@@ -243,8 +287,8 @@ ItWs it_ws(int B, int h, int E, int K) {
   w.a16 = 0;
   w.bm = w.a16 + align_up((size_t)B * h * sizeof(__half), 1024);
   w.tv = w.bm + align_up((size_t)B * nblk * sizeof(float), 1024);
-  w.ti = w.tv + align_up((size_t)B * K * sizeof(float), 1024);
-  w.cnt = w.ti + align_up((size_t)B * K * sizeof(int32_t), 1024);
+  w.ti = w.tv + align_up((size_t)B * sizeof(float), 1024);
+  w.cnt = w.ti + align_up((size_t)B * sizeof(int32_t), 1024);
   w.cand = w.cnt + align_up((size_t)B * sizeof(int), 1024);
   w.total = w.cand + align_up((size_t)B * (size_t)(BLK * K) * sizeof(unsigned long long), 1024);
   return w;
@@ -262,14 +306,14 @@ extern "C" int ntf_to_half(ntf_ctx* ctx, void* stream, const float* x, size_t n,
 
 // the fused path needs the tensor-core width, at least K blocks of 32 experts per team, and a candidate list that sorts in shared memory
 extern "C" int ntf_infer_topk_supported(int B, int h, int E, int K) {
-  return (h == HK && B >= 1 && K >= 1 && K <= 128 && (long long)K * BLK <= (long long)E) ? 1 : 0;
+  return (h == HK && B >= 1 && K >= 1 && K <= 128 && (long long)K * BLK <= (long long)E && cdiv(cdiv(E, TX) * 4, 32) <= 128) ? 1 : 0;  // (E <= 131072 per shard)
 }
 
 extern "C" size_t ntf_infer_topk_workspace_bytes(int B, int h, int E, int K) { return it_ws(B, h, E, K).total; }
 
 extern "C" int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_args* a, void* workspace, size_t workspace_bytes) {
   NTF_REQUIRE(ctx && a && a->W16 && a->b && a->vals && a->idx && (a->A || a->A16), NTF_ERR_BAD_ARG, "infer_topk: null pointer");
-  NTF_REQUIRE(ntf_infer_topk_supported(a->B, a->h, a->E, a->K), NTF_ERR_UNSUPPORTED, "infer_topk: B=%d h=%d E=%d K=%d (needs h=%d, K <= 128, 32*K <= E)", a->B, a->h, a->E,
+  NTF_REQUIRE(ntf_infer_topk_supported(a->B, a->h, a->E, a->K), NTF_ERR_UNSUPPORTED, "infer_topk: B=%d h=%d E=%d K=%d (needs h=%d, K <= 128, 32*K <= E <= 131072)", a->B, a->h, a->E,
               a->K, HK);
   const ItWs w = it_ws(a->B, a->h, a->E, a->K);
   NTF_REQUIRE(workspace && workspace_bytes >= w.total, NTF_ERR_WORKSPACE, "infer_topk: workspace too small");
@@ -308,7 +352,14 @@ extern "C" int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_a
   NTF_CUDA(cudaMemsetAsync(g.cnt, 0, (size_t)a->B * sizeof(int), st));
   NTF_COUNT_LAUNCH; infer_topk_kernel<1><<<grid, NT, SMEM_BYTES, st>>>(ma, mw, g);
   NTF_LAUNCH_CHECK();
-  if ((rc = ntf_topk_select(ctx, stream, g.bm, a->B, g.nblk, a->K, 1.0f, tv, ti))) return rc;
+  {
+    const int per = cdiv(g.nblk, 32), tblocks = cdiv(a->B, 4);  // 4 warps (teams) per CTA
+    NTF_COUNT_LAUNCH;
+    if (per <= 16) blockmax_threshold_kernel<16><<<tblocks, 128, 0, st>>>(g.bm, a->B, g.nblk, a->K, tv, ti);
+    else if (per <= 64) blockmax_threshold_kernel<64><<<tblocks, 128, 0, st>>>(g.bm, a->B, g.nblk, a->K, tv, ti);
+    else blockmax_threshold_kernel<128><<<tblocks, 128, 0, st>>>(g.bm, a->B, g.nblk, a->K, tv, ti);
+    NTF_LAUNCH_CHECK();
+  }
   NTF_COUNT_LAUNCH; infer_topk_kernel<2><<<grid, NT, SMEM_BYTES, st>>>(ma, mw, g);
   NTF_LAUNCH_CHECK();
   int npad = 32;

@@ -1,5 +1,7 @@
 // out_layer.cu -- C-ABI entry points of the output layer (training step + inference scores); dispatches on precision
 // to the CUDA-core fp32 path (dense_simt.cu) or the tcgen05/TMEM path (out_tc.cu).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 size_t ntf_out_train_fp32_workspace_bytes(int B, int h, int E, int flipout);
@@ -10,6 +12,8 @@ int ntf_infer_scores_fp32(cudaStream_t st, const float* A, const float* W, const
 size_t ntf_out_train_tc_workspace_bytes(const ntf_ctx* ctx, int B, int h, int E, int flipout);
 int ntf_out_train_tc(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a, void* workspace, size_t workspace_bytes);
 int ntf_out_tc_supported(int B, int h, int E, int flipout);
+size_t ntf_out_train_tc2_workspace_bytes(int B, int h, int E);
+int ntf_out_train_tc2(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a, void* workspace, size_t workspace_bytes);
 int ntf_infer_scores_tc(ntf_ctx* ctx, cudaStream_t st, const float* A, const float* W, const float* b, int B, int h, int E, float* P,
                         void* workspace, size_t workspace_bytes);
 size_t ntf_infer_scores_tc_workspace_bytes(int B, int h);
@@ -21,7 +25,10 @@ int ntf_infer_scores_tc_flip(ntf_ctx* ctx, cudaStream_t st, const float* A, cons
 extern "C" int ntf_tc_supported(int B, int h, int E, int flipout) { return ntf_out_tc_supported(B, h, E, flipout); }
 
 extern "C" size_t ntf_out_train_workspace_bytes(const ntf_ctx* ctx, int precision, int B, int h, int E, int flipout) {
-  if (precision == NTF_TF32) return ntf_out_train_tc_workspace_bytes(ctx, B, h, E, flipout);
+  if (precision == NTF_TF32) {
+    const size_t v1 = ntf_out_train_tc_workspace_bytes(ctx, B, h, E, flipout), v2 = flipout ? 0 : ntf_out_train_tc2_workspace_bytes(B, h, E);
+    return v1 > v2 ? v1 : v2;
+  }
   return ntf_out_train_fp32_workspace_bytes(B, h, E, flipout);
 }
 
@@ -43,6 +50,8 @@ extern "C" int ntf_out_train(ntf_ctx* ctx, void* stream, int precision, const nt
   if (precision == NTF_TF32) {
     NTF_REQUIRE(ntf_out_tc_supported(a->B, a->h, a->E, flip), NTF_ERR_UNSUPPORTED,
                 "out_train(tf32): shape B=%d h=%d E=%d flipout=%d not supported by the tcgen05 kernel (use NTF_FP32)", a->B, a->h, a->E, (int)flip);
+    // Fnn: the persistent kernel (out_tc2.cu); the Flipout layer and NTF_TC_V1=1 (round 1's one-CTA-per-expert-tile kernel, kept for A/B runs): out_tc.cu
+    if (!flip && getenv("NTF_TC_V1") == nullptr) return ntf_out_train_tc2(ctx, as_stream(stream), a, workspace, workspace_bytes);
     return ntf_out_train_tc(ctx, as_stream(stream), a, workspace, workspace_bytes);
   }
   NTF_REQUIRE(precision == NTF_FP32, NTF_ERR_BAD_ARG, "out_train: precision=%d", precision);

@@ -88,8 +88,6 @@ struct TcArgs {
   float* loss_part;           // [gridDim.x]
   float* P;                   // inference: [B,E] probabilities
   float* Zdbg;                // debug: raw logits z [B,E] (NULL in production)
-  float* Zraw;                // debug: the TMEM accumulator as read, before bias / perturbation term [B,E]
-  float* Qdbg;                // debug (Flipout): the perturbation-term values as read from shared memory [B,E]
   long long* timing;          // debug: clock64 stamps of CTA 0, [tile][8] (NULL in production)
   int exp;                    // debug: experiment bits (NTF_TC_EXP): 1 = skip the dA reduction, 2 = skip the special-bit path
   // work split: CTAs [0, n_full) own a whole expert tile (all batch tiles); the remaining expert tiles -- the partial last wave --
@@ -130,10 +128,6 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
   auto bar = [&](int i) { return bars + 8u * i; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (g.exp & 32) {  // debug: poison the whole window (NaN pattern) so that a read-before-arrival is not masked by the previous launch's residue
-    for (uint32_t i = threadIdx.x; i < OFF_BAR / 16; i += NT) reinterpret_cast<uint4*>(sgen)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
-    fence_proxy_async();
-  }
   if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[15 * 8 + 0] = clock64();  // kernel entry
   if (g.timing && threadIdx.x == 0) {  // every CTA: start / end on the global timer (ns) and its SM
     unsigned long long gt; unsigned smid;
@@ -344,8 +338,9 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         mbar_wait(bar(BAR_Q_FULL), it & 1);
 #pragma unroll
         for (int u = 0; u < 4; ++u) qv[u] = *reinterpret_cast<const uint4*>(sgen + OFF_Q + (((cb * 4 + u) * TE + jl) << 4));
-        if (g.exp & 16) fence_proxy_async();
-        mbar_arrive(bar(BAR_Q_EMPTY));
+#ifdef NTF_FLIP_EARLY_RELEASE  // the round-1 hand-over, kept to reproduce its race (scripts/flip_variants.sh): the slot is released right after the
+        mbar_arrive(bar(BAR_Q_EMPTY));  // loads were ISSUED -- see the release below
+#endif
       }
       // bit n of S / Y: (team n0+n, my expert) carries weight tpw / target 1 -- two words from the tile's planes, then the stage is free
       uint32_t S = 0, Y = 0;
@@ -354,13 +349,12 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
         mbar_wait(bar(BAR_SP_FULL + s), ph);
         S = plane[jl * 4 + cb];
         Y = plane[TE * 4 + jl * 4 + cb];
-        if (g.exp & 16) fence_proxy_async();
-        mbar_arrive(bar(BAR_SP_EMPTY + s));
         if (S) {  // consumed: clear the words in HBM so that the caller's planes are clean for the next batch (no second pass over them)
           const size_t wofs = ((size_t)(t_begin + it) * g.Epad + e) * 4 + cb;
           g.special_t[wofs] = 0u;
           if (Y) g.member_t[wofs] = 0u;
         }
+        mbar_arrive(bar(BAR_SP_EMPTY + s));  // (after the branch above consumed S and Y: the loads have completed, not merely issued)
         if (!e_ok) S = 0;
       }
       mbar_wait(bar(BAR_Z_FULL + s), ph);
@@ -372,23 +366,6 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       mbar_arrive(bar(BAR_Z_EMPTY + s));
       if (g.timing && blockIdx.x == 0 && threadIdx.x == 0) g.timing[it * 8 + 5] = clock64();
       const int nrem = g.B - n0;  // teams of this block that exist
-      if (g.Zraw) {
-#pragma unroll
-        for (int n = 0; n < 32; ++n)
-          if (e_ok && n < nrem) g.Zraw[(size_t)(n0 + n) * g.E + e] = z[n];
-      }
-      if (QIN && g.Qdbg) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t w[4] = {qv[u].x, qv[u].y, qv[u].z, qv[u].w};
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[p]));
-            if (e_ok && u * 8 + 2 * p < nrem) g.Qdbg[(size_t)(n0 + u * 8 + 2 * p) * g.E + e] = f.x;
-            if (e_ok && u * 8 + 2 * p + 1 < nrem) g.Qdbg[(size_t)(n0 + u * 8 + 2 * p + 1) * g.E + e] = f.y;
-          }
-        }
-      }
       if (QIN) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -399,6 +376,15 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
             z[u * 8 + 2 * p] += f.x; z[u * 8 + 2 * p + 1] += f.y;
           }
         }
+#ifndef NTF_FLIP_EARLY_RELEASE
+        // The single-stage Q slot goes back to its producer only HERE.  Round 1 arrived on Q_EMPTY right after issuing the four LDS.128 above;
+        // the producer thread spins on that barrier and re-arms the slot with the NEXT tile's bulk copy (async proxy) the moment the 512th
+        // arrival lands, and on a near-empty machine that copy could overtake shared-memory reads that were issued but not yet performed:
+        // tile 0's logits then carried tile 1's perturbation term (bisected in profiles/r02a_flipout_bisect_variants.txt).
+        // The adds above consumed the loaded registers, so the reads have completed; the proxy fence orders them before the async-proxy write.
+        fence_proxy_async();
+        mbar_arrive(bar(BAR_Q_EMPTY));
+#endif
       }
       if (MODE == 2) {
         // Q = s_out * (Z2 + b_delta) as fp16: unit (4*cb+u) = teams [8u, 8u+8) of this thread's block; lanes write consecutive 16-byte units
@@ -739,10 +725,6 @@ static void plan_split(const ntf_ctx* ctx, int nct, int nt_all, int* n_full, int
 static void tc_debug_hooks(TcArgs& g) {
   const char* dbg = getenv("NTF_TC_ZDBG");  // debug hook used by tests/test_gpu_tc.py: address of a [B,E] device buffer for the raw logits
   g.Zdbg = dbg ? (float*)(uintptr_t)strtoull(dbg, nullptr, 0) : nullptr;
-  const char* zr = getenv("NTF_TC_ZRAW");
-  g.Zraw = zr ? (float*)(uintptr_t)strtoull(zr, nullptr, 0) : nullptr;
-  const char* qd = getenv("NTF_TC_QDBG");
-  g.Qdbg = qd ? (float*)(uintptr_t)strtoull(qd, nullptr, 0) : nullptr;
   const char* tim = getenv("NTF_TC_TIMING");
   g.timing = tim ? (long long*)(uintptr_t)strtoull(tim, nullptr, 0) : nullptr;
   const char* ex = getenv("NTF_TC_EXP");
@@ -773,7 +755,7 @@ static int flip_forward(ntf_ctx* ctx, cudaStream_t st, const float* A_s, const f
   g.bias = b_delta; g.Epad = Epad; g.B = B; g.E = E;
   g.sign_t = sign_t; g.Q = (__half*)(fws + fw.q);
   tc_debug_hooks(g);
-  g.Zdbg = nullptr; g.timing = nullptr; g.Zraw = nullptr; g.Qdbg = nullptr;
+  g.Zdbg = nullptr; g.timing = nullptr;
   int grid;
   plan_split(ctx, cdiv(E, TE), nt, &g.n_full, &g.split, &grid);
   *gq = g;
@@ -885,7 +867,7 @@ int ntf_infer_scores_tc(ntf_ctx* ctx, cudaStream_t st, const float* A, const flo
   TcArgs g{};
   g.bias = b; g.B = B; g.E = E; g.P = P;
   tc_debug_hooks(g);
-  g.Zdbg = nullptr; g.Zraw = nullptr; g.Qdbg = nullptr;
+  g.Zdbg = nullptr;
   int grid;
   plan_split(ctx, cdiv(E, TE), cdiv(B, TB), &g.n_full, &g.split, &grid);
   NTF_CUDA(cudaFuncSetAttribute(out_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));

@@ -1,0 +1,540 @@
+// out_tc2.cu -- NTF_TF32 training / validation step of the Fnn output layer, PERSISTENT version (round 2).
+//
+// Same mathematics and the same per-tile pipeline as out_tc.cu's MODE 0 (fnn.py:25 last layer, 32-46, 135 and its autograd in one
+// kernel; logits, losses and dz live in TMEM / registers / shared memory only) -- what changes is how the work is laid over the machine.
+// Round 1 launched one CTA per expert tile: 313 CTAs over 148 SMs = 2.1 waves, each CTA paying its own prologue (fp32 W tile in, fp16
+// conversion: ~5000 cycles), pipeline fill and dW drain (~4500 cycles) for 8 batch tiles of work, and every dA tile left through a
+// single 16 KB staging buffer whose TMA reduce-add had to finish READING before the next chunk could be staged (measured: 4600 cycles
+// per tile for that drain alone = the kernel's tile period; scripts/mb/mb_reduce.cu).  Here:
+//   * one CTA per SM walks a contiguous range of the (expert tile, batch tile) sequence -- no waves, no split last wave;
+//   * the W tile arrives as fp16 straight from an fp16 image of the weight (TMA, no conversion pass); the caller keeps the image
+//     (ntf_out_train_args.W16, rewritten by the optimiser) or this file makes it per call;
+//   * the dW drain of an expert tile goes through the idle dz ring, so the NEXT tile's W / activation loads and first forward
+//     product run underneath it;
+//   * dA chunks leave through THREE staging buffers (the third activation stage of round 1, which its timeline showed idle).
+// An expert tile whose batch range is cut between two CTAs adds its dW / db partials into rows zeroed beforehand; with at most two
+// contributions per element (0 + a + b) the sums are order-independent, so dW / db are run-to-run deterministic whenever
+// E >= 128 * (number of SMs); dA is still summed by L2 in arrival order.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include <type_traits>
+
+#include "tc_common.cuh"
+
+int ntf_loss_reduce_impl(cudaStream_t st, const float* part, int n, float scale, float* loss_out);
+
+namespace {
+
+constexpr int TE = 128, TB = 128, HK = 128;
+constexpr uint32_t CHUNK = 128 * 128;
+constexpr uint32_t W16_BYTES = TE * HK * 2, A16_BYTES = TB * HK * 2, DZ_BYTES = TE * TB * 2;
+constexpr uint32_t OFF_W16 = 0;
+constexpr uint32_t OFF_A16 = OFF_W16 + W16_BYTES;       // 2 stages
+constexpr uint32_t OFF_DZ = OFF_A16 + 2 * A16_BYTES;    // 2 stages; at the end of an expert tile: staging of the dW drain (64 KB)
+constexpr uint32_t OFF_PLANE = OFF_DZ + 2 * DZ_BYTES;   // 2 stages x (special | member) planes, 2 KB each
+constexpr uint32_t PLANE_BYTES = TE * 4 * 4;
+constexpr uint32_t OFF_DAST = OFF_PLANE + 4 * PLANE_BYTES;
+constexpr int DA_BUFS = 3;                              // dA staging buffers: [128 teams][128 B] fp32 chunks on their way to the TMA reduce-add
+constexpr uint32_t OFF_BAR = OFF_DAST + DA_BUFS * CHUNK;
+constexpr uint32_t OFF_DBS = OFF_BAR + 512;              // [4][128] fp32 scratch of the db combine
+constexpr uint32_t SMEM_BYTES = OFF_DBS + 4 * TE * 4;
+static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared memory limit");
+
+constexpr uint32_t TM_Z = 0, TM_DW = 256, TM_DA = 384, TM_COLS = 512;
+
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = 1, BAR_A_FULL = 2, BAR_A_EMPTY = 4, BAR_Z_FULL = 6, BAR_Z_EMPTY = 8, BAR_DZ_FULL = 10, BAR_DZ_EMPTY = 12,
+       BAR_DA_FULL = 14, BAR_DA_EMPTY = 15, BAR_DW_FULL = 16, BAR_DW_EMPTY = 17, BAR_SP_FULL = 18, BAR_SP_EMPTY = 20, NUM_BARS = 22 };
+
+struct Tc2Args {
+  const float* bias;
+  uint32_t* special_t;
+  uint32_t* member_t;
+  int Epad, B, E;
+  float tpw, tnw, scale;
+  float* dW;        // [E,128] or NULL (validation: forward + loss only)
+  float* db;
+  float* loss_part; // [gridDim.x]
+  float* Zdbg;      // debug: raw logits [B,E]
+  long long* timing;  // debug: per CTA (start ns, end ns, smid)
+  int nct, nbt;     // expert tiles, batch tiles
+  int split;        // 0: CTA c owns tiles [c*T/G, (c+1)*T/G) of the expert-major sequence; s > 0: expert tile c/s, batch part c%s of s
+};
+
+constexpr int EPI_WARPS = 16, NT = 736, WARP_DA = 16, WARP_TMA = 20, WARP_MMA = 21, WARP_SP = 22, EPI_THREADS = EPI_WARPS * 32;
+constexpr uint32_t IDESC_FWD = instr_desc(0, 0, 0, TE, TB);
+constexpr uint32_t IDESC_DW = instr_desc(0, 0, 1, TE, HK);
+constexpr uint32_t IDESC_DA = instr_desc(0, 1, 1, TB, HK);
+
+__device__ __forceinline__ void tile_range(const Tc2Args& g, int c, int G, int* L0, int* L1) {
+  if (g.split == 0) {
+    const long long T = (long long)g.nct * g.nbt;
+    *L0 = (int)(T * c / G); *L1 = (int)(T * (c + 1) / G);
+  } else {
+    const int e = c / g.split, part = c % g.split;
+    *L0 = e * g.nbt + part * g.nbt / g.split; *L1 = e * g.nbt + (part + 1) * g.nbt / g.split;
+  }
+}
+
+// rows of dW / db that receive partial sums from two (or, split > 2, more) CTAs: zeroed here, one CTA per cut expert tile
+__global__ void __launch_bounds__(256) zero_cut_tiles_kernel(Tc2Args g) {
+  int L0, L1;
+  tile_range(g, blockIdx.x, gridDim.x, &L0, &L1);
+  // range mode: a tile is cut iff a CTA's range starts inside it (ranges are at least one expert tile long: at most one cut per tile);
+  // split mode: every tile is cut `split` ways, part 0 zeroes it
+  const bool mine = g.split == 0 ? (L0 < L1 && L0 % g.nbt != 0) : (g.split > 1 && blockIdx.x % g.split == 0);
+  if (!mine) return;
+  const int e0 = (L0 / g.nbt) * TE;
+  const int rows = min(TE, g.E - e0);
+  float4* w = reinterpret_cast<float4*>(g.dW + (size_t)e0 * HK);
+  for (int i = threadIdx.x; i < rows * (HK / 4); i += 256) w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < rows; i += 256) g.db[e0 + i] = 0.f;
+}
+
+__global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ CUtensorMap map_w16, const __grid_constant__ CUtensorMap map_a16,
+                                                        const __grid_constant__ CUtensorMap map_da, Tc2Args g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if ((sbase & 1023u) != 0u) __trap();
+  uint8_t* sgen = smem_raw;
+  const uint32_t bars = sbase + OFF_BAR;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + OFF_BAR + NUM_BARS * 8);
+  auto bar = [&](int i) { return bars + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (g.timing && threadIdx.x == 0) {
+    unsigned long long gt; unsigned smid;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    g.timing[3 * blockIdx.x] = (long long)gt; g.timing[3 * blockIdx.x + 2] = smid;
+  }
+  int L0, L1;
+  tile_range(g, blockIdx.x, gridDim.x, &L0, &L1);
+  const bool train = g.dW != nullptr;
+  const bool has_sp = g.special_t != nullptr;
+  const int nbt = g.nbt;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(BAR_W_FULL), 1); mbar_init(bar(BAR_W_EMPTY), 1);
+    mbar_init(bar(BAR_DA_FULL), 1); mbar_init(bar(BAR_DA_EMPTY), 128);
+    mbar_init(bar(BAR_DW_FULL), 1); mbar_init(bar(BAR_DW_EMPTY), EPI_THREADS);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(BAR_A_FULL + s), 1); mbar_init(bar(BAR_A_EMPTY + s), 1);
+      mbar_init(bar(BAR_Z_FULL + s), 1); mbar_init(bar(BAR_Z_EMPTY + s), EPI_THREADS);
+      mbar_init(bar(BAR_DZ_FULL + s), EPI_THREADS); mbar_init(bar(BAR_DZ_EMPTY + s), 1);
+      mbar_init(bar(BAR_SP_FULL + s), 1); mbar_init(bar(BAR_SP_EMPTY + s), EPI_THREADS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WARP_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + NUM_BARS * 8), "r"(TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // Every role walks the same sequence: tile n = L - L0 is (expert tile e, batch tile t) = (L / nbt, L % nbt); an ITEM is a maximal run of
+  // tiles with the same e (index j).  Ring stages / phases follow n (A, Z, dz, planes: 2 stages) or j (W image, dW accumulator: 1 stage).
+  if (warp == WARP_TMA) {
+    if (lane == 0) {
+      int j = -1;
+      for (int L = L0, n = 0; L < L1; ++L, ++n) {
+        const int e = L / nbt, t = L - e * nbt;
+        if (L == L0 || t == 0) {
+          ++j;
+          mbar_wait(bar(BAR_W_EMPTY), (j & 1) ^ 1);  // the previous item's last products have read the image
+          mbar_expect_tx(bar(BAR_W_FULL), W16_BYTES);
+          for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_W16 + c * CHUNK, &map_w16, c * 64, e * TE, bar(BAR_W_FULL));
+        }
+        const int s = n & 1;
+        mbar_wait(bar(BAR_A_EMPTY + s), ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(bar(BAR_A_FULL + s), A16_BYTES);
+        for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A16 + s * A16_BYTES + c * CHUNK, &map_a16, c * 64, t * TB, bar(BAR_A_FULL + s));
+      }
+    }
+  } else if (warp == WARP_SP) {
+    if (lane == 0 && has_sp) {
+      for (int L = L0, n = 0; L < L1; ++L, ++n) {
+        const int e = L / nbt, t = L - e * nbt, s = n & 1;
+        mbar_wait(bar(BAR_SP_EMPTY + s), ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(bar(BAR_SP_FULL + s), 2 * PLANE_BYTES);
+        const size_t off = ((size_t)t * g.Epad + (size_t)e * TE) * 4;
+        bulk_load(sbase + OFF_PLANE + s * 2 * PLANE_BYTES, g.special_t + off, PLANE_BYTES, bar(BAR_SP_FULL + s));
+        bulk_load(sbase + OFF_PLANE + s * 2 * PLANE_BYTES + PLANE_BYTES, g.member_t + off, PLANE_BYTES, bar(BAR_SP_FULL + s));
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    if (lane == 0) {
+      auto issue_fwd = [&](int n, bool item_last) {
+        const int s = n & 1;
+        const uint32_t ph = (n >> 1) & 1;
+        mbar_wait(bar(BAR_A_FULL + s), ph);
+        mbar_wait(bar(BAR_Z_EMPTY + s), ph ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < HK / 16; ++i) {
+          const uint64_t da = smem_desc(sbase + OFF_W16 + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
+          const uint64_t db = smem_desc(sbase + OFF_A16 + s * A16_BYTES + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
+          mma_f16(tmem + TM_Z + s * TB, da, db, IDESC_FWD, i > 0);
+        }
+        tc_commit(bar(BAR_Z_FULL + s));
+        if (!train) {  // forward only: the operands are free once this product has read them
+          tc_commit(bar(BAR_A_EMPTY + s));
+          if (item_last) tc_commit(bar(BAR_W_EMPTY));
+        }
+      };
+      int j = -1;
+      for (int L = L0, n = 0; L < L1; ++L, ++n) {
+        const int e = L / nbt, t = L - e * nbt;
+        const bool first = (L == L0 || t == 0), last = (L == L1 - 1 || t == nbt - 1);
+        if (first) {
+          ++j;
+          mbar_wait(bar(BAR_W_FULL), j & 1);
+          issue_fwd(n, last);  // (no product of this item could be issued ahead: the image was the previous item's until now)
+        }
+        if (!last) issue_fwd(n + 1, (L + 1 == L1 - 1) || (t + 1 == nbt - 1));  // keeps the tensor pipe busy while the epilogue works on tile n
+        if (!train) continue;
+        const int s = n & 1;
+        mbar_wait(bar(BAR_DZ_FULL + s), (n >> 1) & 1);
+        if (first && j > 0) mbar_wait(bar(BAR_DW_EMPTY), (j - 1) & 1);  // the previous item's dW has left TMEM
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < TB / 16; ++i) {  // dW[128 j x 128 k] += dz^T[j, n] . A16[n, k]
+          const uint64_t da = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
+          const uint64_t db = smem_desc(sbase + OFF_A16 + s * A16_BYTES + i * 2048, CHUNK, 1024);
+          mma_f16(tmem + TM_DW, da, db, IDESC_DW, (!first || i > 0));
+        }
+        mbar_wait(bar(BAR_DA_EMPTY), (n & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < TE / 16; ++i) {  // dA[128 n x 128 k] = dz[j, n]^T . W16[j, k]
+          const uint64_t da = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + i * 2048, CHUNK, 1024);
+          const uint64_t db = smem_desc(sbase + OFF_W16 + i * 2048, CHUNK, 1024);
+          mma_f16(tmem + TM_DA, da, db, IDESC_DA, i > 0);
+        }
+        tc_commit(bar(BAR_DA_FULL));
+        tc_commit(bar(BAR_DZ_EMPTY + s));
+        tc_commit(bar(BAR_A_EMPTY + s));
+        if (last) { tc_commit(bar(BAR_W_EMPTY)); tc_commit(bar(BAR_DW_FULL)); }
+      }
+    }
+  } else if (warp < EPI_WARPS) {
+    // ====================== logits / loss epilogue: thread = (expert jl, block cb of 32 of the tile's 128 teams) ======================
+    const int jl = threadIdx.x & 127, cb = threadIdx.x >> 7;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    constexpr float LOG2E = 1.4426950408889634f;
+    float loss_total = 0.f;
+    // per item (expert tile):
+    int j = -1, e0 = 0, e = 0;
+    bool e_ok = false, whole = false;
+    float bj = 0.f, c_pos = 0.f, c_neg = 0.f, kb1 = 0.f, kb2 = 0.f;
+    float acc_lin = 0.f, acc_lg = 0.f, loss_sp = 0.f, db_acc = 0.f;
+    float2 acc_lin2 = make_float2(0.f, 0.f), db_acc2 = make_float2(0.f, 0.f);
+    for (int L = L0, n = 0; L < L1; ++L, ++n) {
+      const int et = L / nbt, t = L - et * nbt;
+      const bool first = (L == L0 || t == 0), last = (L == L1 - 1 || t == nbt - 1);
+      if (first) {
+        ++j;
+        e0 = et * TE; e = e0 + jl; e_ok = e < g.E;
+        bj = e_ok ? __ldg(g.bias + e) : 0.f;
+        c_pos = e_ok ? g.tnw : 0.f; c_neg = e_ok ? g.tnw * NTF_LRELU_SLOPE : 0.f;
+        kb1 = -LOG2E * bj; kb2 = -LOG2E * NTF_LRELU_SLOPE * bj;
+        acc_lin = acc_lg = loss_sp = db_acc = 0.f;
+        acc_lin2 = make_float2(0.f, 0.f); db_acc2 = make_float2(0.f, 0.f);
+        whole = (t == 0) && (L + nbt <= L1);  // this CTA runs every batch tile of the expert tile: plain stores, no partial sums
+      }
+      const int s = n & 1;
+      const uint32_t ph = (n >> 1) & 1;
+      const int n0 = t * TB + cb * 32;
+      uint32_t S = 0, Y = 0;
+      if (has_sp) {
+        const uint32_t* plane = reinterpret_cast<const uint32_t*>(sgen + OFF_PLANE + s * 2 * PLANE_BYTES);
+        mbar_wait(bar(BAR_SP_FULL + s), ph);
+        S = plane[jl * 4 + cb];
+        Y = plane[TE * 4 + jl * 4 + cb];
+        if (S) {  // consumed: clear the words in HBM so that the caller's planes are clean for the next batch
+          const size_t wofs = ((size_t)t * g.Epad + e) * 4 + cb;
+          g.special_t[wofs] = 0u;
+          if (Y) g.member_t[wofs] = 0u;
+        }
+        mbar_arrive(bar(BAR_SP_EMPTY + s));  // (after the branch consumed S and Y: the loads have completed, not merely issued)
+        if (!e_ok) S = 0;
+      }
+      mbar_wait(bar(BAR_Z_FULL + s), ph);
+      tc_fence_after();
+      float z[32];
+      tmem_ld32(tmem + lane_base + TM_Z + s * TB + cb * 32, z);
+      tc_fence_before();
+      mbar_arrive(bar(BAR_Z_EMPTY + s));
+      const int nrem = g.B - n0;
+      if (g.Zdbg) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          if (e_ok && q < nrem) g.Zdbg[(size_t)(n0 + q) * g.E + e] = z[q] + bj;
+      }
+      if (train) mbar_wait(bar(BAR_DZ_EMPTY + s), ph ^ 1);
+      const uint32_t dzrow = sbase + OFF_DZ + s * DZ_BYTES + (cb >> 1) * CHUNK + jl * 128;
+      const int unit0 = 4 * (cb & 1);
+      const uint32_t kx = (uint32_t)(unit0 ^ (jl & 7));
+      // dense pass (out_tc.cu has the derivation): every element as (target 0, weight tnw); t = -log2e*lrelu(z+b) by two FFMA2 + FMNMX,
+      // e = 2^t, one reciprocal and one logarithm per 8 elements through the product of the 8 denominators
+      auto dense8 = [&](int u, auto masked) {
+        const float2 k1 = make_float2(-LOG2E, -LOG2E), k2 = make_float2(-LOG2E * NTF_LRELU_SLOPE, -LOG2E * NTF_LRELU_SLOPE);
+        const float2 kb1v = make_float2(kb1, kb1), kb2v = make_float2(kb2, kb2), one2 = make_float2(1.f, 1.f);
+        float2 D[4], G[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float2 zz = make_float2(z[u * 8 + 2 * p], z[u * 8 + 2 * p + 1]);
+          const float2 t1 = __ffma2_rn(zz, k1, kb1v), t2 = __ffma2_rn(zz, k2, kb2v);
+          float2 tt = make_float2(fminf(t1.x, t2.x), fminf(t1.y, t2.y));
+          G[p] = make_float2(t1.x < 0.f ? c_pos : c_neg, t1.y < 0.f ? c_pos : c_neg);
+          D[p] = __fadd2_rn(make_float2(ex2_approx(tt.x), ex2_approx(tt.y)), one2);
+          if (decltype(masked)::value) {
+            if (u * 8 + 2 * p >= nrem) { G[p].x = 0.f; tt.x = 0.f; D[p].x = 1.f; }
+            if (u * 8 + 2 * p + 1 >= nrem) { G[p].y = 0.f; tt.y = 0.f; D[p].y = 1.f; }
+          }
+          acc_lin2 = __fadd2_rn(acc_lin2, tt);
+        }
+        const float2 M01 = __fmul2_rn(D[0], D[1]), M23 = __fmul2_rn(D[2], D[3]);
+        const float2 Q = __fmul2_rn(M01, M23);
+        const float prod = Q.x * Q.y;
+        if (prod < 1.0e30f) {
+          acc_lg += lg2_approx(prod);
+          const float r = rcp_approx(prod);
+          const float2 RQ = __fmul2_rn(make_float2(r, r), make_float2(Q.y, Q.x));
+          const float2 R01 = __fmul2_rn(RQ, M23), R23 = __fmul2_rn(RQ, M01);
+          G[0] = __fmul2_rn(G[0], __fmul2_rn(R01, D[1])); G[1] = __fmul2_rn(G[1], __fmul2_rn(R01, D[0]));
+          G[2] = __fmul2_rn(G[2], __fmul2_rn(R23, D[3])); G[3] = __fmul2_rn(G[3], __fmul2_rn(R23, D[2]));
+        } else {
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            acc_lg += lg2_approx(D[p].x) + lg2_approx(D[p].y);
+            G[p].x *= rcp_approx(D[p].x); G[p].y *= rcp_approx(D[p].y);
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) db_acc2 = __fadd2_rn(db_acc2, G[p]);
+        if (train) {
+          const __half2 h0 = __floats2half2_rn(G[0].x, G[0].y), h1 = __floats2half2_rn(G[1].x, G[1].y);
+          const __half2 h2 = __floats2half2_rn(G[2].x, G[2].y), h3 = __floats2half2_rn(G[3].x, G[3].y);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dzrow + ((kx ^ (uint32_t)u) << 4)), "r"(*reinterpret_cast<const uint32_t*>(&h0)),
+                       "r"(*reinterpret_cast<const uint32_t*>(&h1)), "r"(*reinterpret_cast<const uint32_t*>(&h2)), "r"(*reinterpret_cast<const uint32_t*>(&h3)) : "memory");
+        }
+      };
+      if (nrem >= 32) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dense8(u, std::false_type{});
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dense8(u, std::true_type{});
+      }
+      // sparse fix-up: members / sampled negatives (weight tpw, member target), warp-cooperative (out_tc.cu)
+      unsigned todo = __ballot_sync(0xffffffffu, S != 0u);
+      while (todo) {
+        const int Ln = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t S_L = __shfl_sync(0xffffffffu, S, Ln), Y_L = __shfl_sync(0xffffffffu, Y, Ln);
+        const float bj_L = __shfl_sync(0xffffffffu, bj, Ln);
+        float zi = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float v = __shfl_sync(0xffffffffu, z[k], Ln);
+          zi = (k == lane) ? v : zi;
+        }
+        const bool mine = (S_L >> lane) & 1u;
+        const float zz = zi + bj_L;
+        const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
+        const float tt = -LOG2E * x;
+        const float exs = ex2_approx(tt), dens = 1.f + exs;
+        const float g_dense = rcp_approx(dens) * (zz > 0.f ? g.tnw : g.tnw * NTF_LRELU_SLOPE);
+        const float ex = ex2_approx(fabsf(x) * -LOG2E);
+        const float den = 1.f + ex, lg = lg2_approx(den), r = rcp_approx(den);
+        const float sig = x > 0.f ? r : ex * r;
+        const float yf = ((Y_L >> lane) & 1u) ? 1.f : 0.f;
+        const float g_sp = g.tpw * (sig - yf) * (zz > 0.f ? 1.f : NTF_LRELU_SLOPE);
+        float d_lin = mine ? -tt : 0.f, d_lg = mine ? -lg2_approx(dens) : 0.f;
+        float d_sp = mine ? g.tpw * ((1.f - yf) * x + fmaxf(-x, 0.f) + 0.6931471805599453f * lg) : 0.f;
+        float d_db = mine ? g_sp - g_dense : 0.f;
+        __syncwarp();
+        if (mine && train) {
+          const int jl_L = jl - lane + Ln;
+          uint8_t* rowL = sgen + OFF_DZ + s * DZ_BYTES + (cb >> 1) * CHUNK + jl_L * 128;
+          *reinterpret_cast<__half*>(rowL + (((unit0 + (lane >> 3)) ^ (jl_L & 7)) << 4) + (lane & 7) * 2) = __float2half_rn(g_sp);
+        }
+        d_lin = warp_sum(d_lin); d_lg = warp_sum(d_lg); d_sp = warp_sum(d_sp); d_db = warp_sum(d_db);
+        if (lane == Ln) { acc_lin += d_lin; acc_lg += d_lg; loss_sp += d_sp; db_acc += d_db; }
+      }
+      if (train) {
+        fence_proxy_async();
+        mbar_arrive(bar(BAR_DZ_FULL + s));
+      }
+      if (!last) continue;
+      // ---- end of the expert tile: fold its loss terms, drain dW / db ----
+      acc_lin += acc_lin2.x + acc_lin2.y;
+      db_acc += db_acc2.x + db_acc2.y;
+      loss_total += e_ok ? g.tnw * 0.6931471805599453f * (acc_lg - acc_lin) + loss_sp : 0.f;
+      if (train) {
+        mbar_wait(bar(BAR_DW_FULL), j & 1);  // every product of the item has completed: the dz ring is free for staging
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(tmem + lane_base + TM_DW + cb * 32, v);
+        tc_fence_before();
+        mbar_arrive(bar(BAR_DW_EMPTY));
+        // staging (the 64 KB of the dz ring): [128 experts][32 x 16-byte units], units XOR-swizzled by row -> coalesced 512-byte rows out
+        float4* stage = reinterpret_cast<float4*>(sgen + OFF_DZ);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          stage[jl * 32 + ((cb * 8 + q) ^ (jl & 31))] = make_float4(v[4 * q] * g.scale, v[4 * q + 1] * g.scale, v[4 * q + 2] * g.scale, v[4 * q + 3] * g.scale);
+        float* dbsum = reinterpret_cast<float*>(sgen + OFF_DBS);  // [4][128] db partials of the four team blocks, combined in a fixed order
+        dbsum[cb * TE + jl] = db_acc;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < TE / EPI_WARPS; ++i) {
+          const int r = warp * (TE / EPI_WARPS) + i;
+          if (e0 + r < g.E) {
+            const float4 v4 = stage[r * 32 + (lane ^ (r & 31))];
+            float* dst = g.dW + (size_t)(e0 + r) * HK + 4 * lane;
+            if (whole) *reinterpret_cast<float4*>(dst) = v4;
+            else { atomicAdd(dst, v4.x); atomicAdd(dst + 1, v4.y); atomicAdd(dst + 2, v4.z); atomicAdd(dst + 3, v4.w); }
+          }
+        }
+        if (cb == 0 && e_ok) {
+          const float dbv = (((dbsum[jl] + dbsum[TE + jl]) + dbsum[2 * TE + jl]) + dbsum[3 * TE + jl]) * g.scale;
+          if (whole) g.db[e] = dbv; else atomicAdd(g.db + e, dbv);
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");  // staging and db scratch are free again before anyone writes the next tile's dz
+      }
+    }
+    // one loss partial per CTA: fixed-order combine (shuffle tree, then warps in order)
+    float* red = reinterpret_cast<float*>(sgen + OFF_BAR + NUM_BARS * 8 + 16);  // [16]
+    const float tot = warp_sum(loss_total);
+    if (lane == 0) red[warp] = tot;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (threadIdx.x == 0) {
+      float l = 0.f;
+#pragma unroll
+      for (int q = 0; q < EPI_WARPS; ++q) l += red[q];
+      g.loss_part[blockIdx.x] = l;
+    }
+  } else if (warp >= WARP_DA && warp < WARP_DA + 4) {
+    // ====== dA epilogue: thread = team.  TMEM -> regs -> swizzled fp32 chunk in one of three staging buffers -> TMA reduce-add into dA[B,128] ======
+    if (train) {
+      const int r = threadIdx.x - WARP_DA * 32;
+      const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+      int k = 0;
+      for (int L = L0, n = 0; L < L1; ++L, ++n) {
+        const int t = L % nbt;
+        mbar_wait(bar(BAR_DA_FULL), n & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < HK / 32; ++c, ++k) {
+          float v[32];
+          tmem_ld32(tmem + lane_base + TM_DA + c * 32, v);
+          if (c == HK / 32 - 1) {
+            tc_fence_before();
+            mbar_arrive(bar(BAR_DA_EMPTY));
+          }
+          const uint32_t buf = (uint32_t)(k % DA_BUFS) * CHUNK;
+          if (r == 0) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");  // the reduce that used this buffer three chunks ago is done reading it
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          uint8_t* row = sgen + OFF_DAST + buf + r * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(row + ((q ^ (r & 7)) << 4)) = make_float4(v[4 * q] * g.scale, v[4 * q + 1] * g.scale, v[4 * q + 2] * g.scale, v[4 * q + 3] * g.scale);
+          fence_proxy_async();
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (r == 0) {
+            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                         ::"l"(reinterpret_cast<uint64_t>(&map_da)), "r"(c * 32), "r"(t * TB), "r"(sbase + OFF_DAST + buf) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+      if (r == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (g.timing && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    g.timing[3 * blockIdx.x + 1] = (long long)gt;
+  }
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
+  }
+}
+
+__global__ void to_half_kernel2(const float* __restrict__ x, size_t n, __half* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = __float2half_rn(x[i]);
+}
+}  // namespace
+
+// workspace: fp16 A | loss partials | fp16 W image (when the caller keeps none)
+size_t ntf_out_train_tc2_workspace_bytes(int B, int h, int E) {
+  return align_up((size_t)B * h * sizeof(__half), 256) + align_up((size_t)(1024 + 8) * sizeof(float), 1024) + align_up((size_t)E * h * sizeof(__half), 1024);
+}
+
+int ntf_out_train_tc2(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a, void* workspace, size_t workspace_bytes) {
+  NTF_REQUIRE(a->h == HK, NTF_ERR_UNSUPPORTED, "out_train(tf32): hidden width %d (kernel is built for %d)", a->h, HK);
+  NTF_REQUIRE(!a->W_delta, NTF_ERR_UNSUPPORTED, "out_train(tf32, persistent): the Flipout layer runs on out_tc.cu");
+  NTF_REQUIRE(workspace_bytes >= ntf_out_train_tc2_workspace_bytes(a->B, a->h, a->E), NTF_ERR_WORKSPACE, "out_train(tf32): workspace too small");
+  NTF_REQUIRE(((uintptr_t)workspace & 255) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): the workspace must be 256-byte aligned");
+  NTF_REQUIRE((((uintptr_t)a->A | (uintptr_t)a->W) & 15) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): A and W must be 16-byte aligned");
+  const bool train = a->dW != nullptr;
+  NTF_REQUIRE(!train || (a->db && a->dA), NTF_ERR_BAD_ARG, "out_train(tf32): training needs dW, db and dA");
+  NTF_REQUIRE(!train || (((uintptr_t)a->dA | (uintptr_t)a->dW) & 15) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): dA and dW must be 16-byte aligned");
+  NTF_REQUIRE((a->special_t == nullptr) == (a->member_t == nullptr), NTF_ERR_BAD_ARG, "out_train(tf32): special_t and member_t come together");
+  NTF_REQUIRE(a->special_t || !a->special, NTF_ERR_BAD_ARG, "out_train(tf32): the tensor-core kernel reads the tile-transposed planes (ntf_special_tiles), not `special`");
+  char* ws = (char*)workspace;
+  __half* A16 = a->A16 ? (__half*)const_cast<void*>(a->A16) : (__half*)ws;
+  float* loss_part = (float*)(ws + align_up((size_t)a->B * a->h * sizeof(__half), 256));
+  const __half* W16 = (const __half*)a->W16;
+  const int blocks_h = ctx->sm_count * 8;
+  if (!W16) {  // no image kept by the caller: made here (one pass over W: 6 bytes per weight)
+    __half* w = (__half*)(ws + align_up((size_t)a->B * a->h * sizeof(__half), 256) + align_up((size_t)(1024 + 8) * sizeof(float), 1024));
+    const size_t nw = (size_t)a->E * HK;
+    NTF_COUNT_LAUNCH; to_half_kernel2<<<(unsigned)(cdiv((int)((nw + 255) / 256), 1) < blocks_h ? (nw + 255) / 256 : blocks_h), 256, 0, st>>>(a->W, nw, w);
+    NTF_LAUNCH_CHECK();
+    W16 = w;
+  }
+  NTF_REQUIRE((((uintptr_t)A16 | (uintptr_t)W16) & 15) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): fp16 operands must be 16-byte aligned");
+  if (!a->A16) {
+    const size_t na = (size_t)a->B * HK;
+    NTF_COUNT_LAUNCH; to_half_kernel2<<<(unsigned)((na + 255) / 256 < (size_t)blocks_h ? (na + 255) / 256 : blocks_h), 256, 0, st>>>(a->A, na, A16);
+    NTF_LAUNCH_CHECK();
+  }
+  CUtensorMap mw, mh, mda;
+  int rc;
+  if ((rc = make_map(ctx, &mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, W16, (uint64_t)a->E, HK, TE, 64))) return rc;
+  if ((rc = make_map(ctx, &mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)a->B, HK, TB, 64))) return rc;
+  if ((rc = make_map(ctx, &mda, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, train ? (const void*)a->dA : (const void*)a->W, (uint64_t)(train ? a->B : a->E), HK, TB, 32))) return rc;
+  if (train) NTF_CUDA(cudaMemsetAsync(a->dA, 0, (size_t)a->B * a->h * sizeof(float), st));
+  Tc2Args g{};
+  g.bias = a->b; g.special_t = const_cast<uint32_t*>(a->special_t); g.member_t = const_cast<uint32_t*>(a->member_t); g.Epad = cdiv(a->E, TE) * TE;
+  g.B = a->B; g.E = a->E; g.tpw = a->tpw; g.tnw = a->tnw; g.scale = a->loss_scale;
+  g.dW = a->dW; g.db = a->db; g.loss_part = loss_part;
+  g.nct = cdiv(a->E, TE); g.nbt = cdiv(a->B, TB);
+  const char* dbg = getenv("NTF_TC_ZDBG");
+  g.Zdbg = dbg ? (float*)(uintptr_t)strtoull(dbg, nullptr, 0) : nullptr;
+  const char* tim = getenv("NTF_TC_TIMING");
+  g.timing = tim ? (long long*)(uintptr_t)strtoull(tim, nullptr, 0) : nullptr;
+  const int sm = ctx->sm_count > 0 ? ctx->sm_count : 148;
+  int grid;
+  if (g.nct >= sm) { g.split = 0; grid = sm; }
+  else {
+    int s = sm / g.nct;
+    if (s > g.nbt) s = g.nbt;
+    if (s < 1) s = 1;
+    g.split = s; grid = g.nct * s;
+  }
+  NTF_REQUIRE(grid <= 1024, NTF_ERR_UNSUPPORTED, "out_train(tf32): %d CTAs", grid);
+  if (train && !(g.split == 1)) { NTF_COUNT_LAUNCH; zero_cut_tiles_kernel<<<grid, 256, 0, st>>>(g); NTF_LAUNCH_CHECK(); }
+  NTF_CUDA(cudaFuncSetAttribute(out_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  NTF_COUNT_LAUNCH; out_tc2_kernel<<<grid, NT, SMEM_BYTES, st>>>(mw, mh, mda, g);
+  NTF_LAUNCH_CHECK();
+  return ntf_loss_reduce_impl(st, loss_part, grid, a->loss_scale, a->loss_out);
+}

@@ -186,3 +186,35 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
 #undef STEP
   return NTF_OK;
 }
+
+// ---- test time: one call per batch of fnn.py:198-218 -- hidden layers, then the fused output layer + sigmoid + top-K (infer_topk.cu) ----
+static size_t a16_region(const ntf_fnn_infer_topk_args* a) { return align_up((size_t)a->B * a->hidden[a->n_layers - 2] * 2, 1024); }
+
+extern "C" size_t ntf_fnn_infer_topk_workspace_bytes(const ntf_ctx* ctx, const ntf_fnn_infer_topk_args* a) {
+  (void)ctx;
+  if (!a || a->n_layers < 2 || a->n_layers > NTF_MAX_LAYERS) return 0;
+  return a16_region(a) + ntf_infer_topk_workspace_bytes(a->B, a->hidden[a->n_layers - 2], a->E, a->K);
+}
+
+extern "C" int ntf_fnn_infer_topk(ntf_ctx* ctx, void* stream, const ntf_fnn_infer_topk_args* a, void* workspace, size_t workspace_bytes) {
+  NTF_REQUIRE(ctx && a, NTF_ERR_BAD_ARG, "fnn_infer_topk: null ctx/args");
+  NTF_REQUIRE(a->n_layers >= 2 && a->n_layers <= NTF_MAX_LAYERS, NTF_ERR_UNSUPPORTED, "fnn_infer_topk: %d layers (2..%d)", a->n_layers, NTF_MAX_LAYERS);
+  NTF_REQUIRE(a->B > 0 && a->S > 0 && a->E > 0 && a->K > 0, NTF_ERR_BAD_ARG, "fnn_infer_topk: B=%d S=%d E=%d K=%d", a->B, a->S, a->E, a->K);
+  NTF_REQUIRE(workspace && workspace_bytes >= ntf_fnn_infer_topk_workspace_bytes(ctx, a), NTF_ERR_WORKSPACE, "fnn_infer_topk: workspace too small");
+  const int L = a->n_layers, Lo = L - 1;
+  const int* h = a->hidden;
+  int rc;
+  // one hidden layer: the bag kernel writes the fp16 operand image the tensor-core product reads next to the fp32 activations
+  void* A16 = (Lo == 1 && (h[0] % 8) == 0 && !a->x_dense) ? workspace : nullptr;
+  if (a->x_dense) rc = ntf_dense_fwd(ctx, stream, a->x_dense, a->W[0], a->b[0], a->B, a->S, h[0], 1, a->act[0]);
+  else rc = ntf_csr_bag_fwd_impl(ctx, stream, a->B, a->s_indptr, a->s_indices, a->W[0], a->b[0], a->S, h[0], a->act[0], A16);
+  if (rc) return rc;
+  for (int i = 1; i < Lo; ++i)
+    if ((rc = ntf_dense_fwd(ctx, stream, a->act[i - 1], a->W[i], a->b[i], a->B, h[i - 1], h[i], 1, a->act[i]))) return rc;
+  ntf_infer_topk_args t;
+  memset(&t, 0, sizeof(t));
+  t.A = a->act[Lo - 1]; t.A16 = A16; t.W16 = a->W16; t.b = a->b[Lo];
+  t.B = a->B; t.h = h[Lo - 1]; t.E = a->E; t.K = a->K; t.e_lo = a->e_lo;
+  t.vals = a->vals; t.idx = a->idx;
+  return ntf_infer_topk(ctx, stream, &t, (char*)workspace + a16_region(a), workspace_bytes - a16_region(a));
+}

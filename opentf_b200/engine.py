@@ -789,29 +789,51 @@ class Engine:
 
     def w16(self):
         """fp16 image of the output layer's weight for the fused top-K kernel, refreshed when the parameters changed since it was made"""
-        Lo = self.L - 1
-        W = self.view(f'layers.{Lo}.weight')
-        if getattr(self, '_w16', None) is None or self._w16.numel() != W.numel():
-            self._w16, self._w16_ver = torch.empty(W.numel(), dtype=torch.float16, device=self.device), None
-        ver = (self.adam_t, self.global_step, getattr(self, '_load_ver', 0), W.data_ptr())
-        if self._w16_ver != ver:
+        ver = (self.adam_t, getattr(self, '_load_ver', 0), self.params.data_ptr())
+        if getattr(self, '_w16_ver', None) != ver:
+            W = self.view(f'layers.{self.L - 1}.weight')
+            if getattr(self, '_w16', None) is None or self._w16.numel() != W.numel():
+                self._w16 = torch.empty(W.numel(), dtype=torch.float16, device=self.device)
             ops.to_half(W, W.numel(), self._w16)
             self._w16_ver = ver
         return self._w16
 
-    def fused_topk_ok(self, B, K):
-        return (not self.bayesian and self.precision == _lib.NTF_TF32 and os.environ.get('NTF_FUSED_TOPK', '1') != '0'
-                and ops.infer_topk_supported(B, self.hidden[-1], self.E, min(K, self.E)))
-
     def topk(self, sp, b0, B, K, scores_buf, vals, idx):
         """the K best experts per team in rank order; only [B,K] leaves the GPU (fnn.py:213-218 keeps [N,E] on the host).
-        Tensor-core mode with K <= 128 and 32*K <= E: output layer + sigmoid + selection fused (ntf_infer_topk), the [B,E] scores
-        never reach HBM; otherwise scores -> ntf_topk_select."""
+        Tensor-core mode with K <= 128 and 32*K <= E: hidden layers + output layer + sigmoid + selection in ONE library call
+        (ntf_fnn_infer_topk), the [B,E] scores never reach HBM; otherwise scores -> ntf_topk_select."""
         if self.fused_topk_ok(B, K):
+            if self.shard[1] == 1: return self._topk_one_call(sp, b0, B, K, vals, idx)
             self._forward_hidden(sp, b0, B)
             return self.select_topk_fused(B, K, vals, idx)
         self.scores(sp, b0, B, scores_buf)
         return self.select_topk(scores_buf, B, K, vals, idx)
+
+    def fused_topk_ok(self, B, K):
+        key = (B, K)
+        c = getattr(self, '_fused_ok', None)
+        if c is None: c = self._fused_ok = {}
+        if key not in c:
+            c[key] = (not self.bayesian and self.precision == _lib.NTF_TF32 and ops.infer_topk_supported(B, self.hidden[-1], self.E, min(K, self.E)))
+        return c[key] and os.environ.get('NTF_FUSED_TOPK', '1') != '0'
+
+    def _topk_one_call(self, sp, b0, B, K, vals, idx, e_lo=0):
+        a = getattr(self, '_ita', None)
+        if a is None:
+            a = self._ita = _lib.FnnInferTopkArgs()
+            a.n_layers, a.S, a.E = self.L, self.S, self.E
+            for i, hh in enumerate(self.hidden): a.hidden[i], a.act[i] = hh, self.act[i].data_ptr()
+            self._ita_ws = {}
+        if getattr(self, '_ita_params', None) != self.params.data_ptr():  # (the arena moves when peers are attached)
+            for i in range(self.L): a.W[i], a.b[i] = self.view(f'layers.{i}.weight').data_ptr(), self.view(f'layers.{i}.bias').data_ptr()
+            self._ita_params = self.params.data_ptr()
+        a.W16 = self.w16().data_ptr()
+        a.B, a.K, a.e_lo = B, K, e_lo
+        if self.dense_input: a.x_dense, a.s_indptr, a.s_indices = sp.x.data_ptr() + 4 * self.S * b0, None, None
+        else: a.x_dense, a.s_indptr, a.s_indices = None, sp.s_indptr.data_ptr() + 4 * b0, sp.s_indices.data_ptr()
+        a.vals, a.idx = vals.data_ptr(), idx.data_ptr()
+        self._ita_ws[(B, K)] = ops.fnn_infer_topk(self.dev_index, a, self.ws, self._ita_ws.get((B, K)))
+        return vals, idx
 
     def select_topk_fused(self, B, K, vals, idx):
         """top-K of the batch whose last hidden activations are in self.act[-1].  Expert-sharded: local fused top-K (global ids), then the

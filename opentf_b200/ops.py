@@ -197,6 +197,15 @@ def infer_topk(A, W16, b, B, h, E, K, vals, idx, ws, e_lo=0, A16=None):
     check(lib().ntf_infer_topk(_lib.ctx(d), _stream(d), C.byref(a), p, nb), 'ntf_infer_topk')
 
 
+def fnn_infer_topk(dev, args, ws, nbytes=None):
+    """one call per test batch: hidden layers + fused output layer / sigmoid / top-K (ntf_fnn_infer_topk).  `nbytes`: the workspace size if the
+    caller cached it for this (B, K)"""
+    if nbytes is None: nbytes = lib().ntf_fnn_infer_topk_workspace_bytes(_lib.ctx(dev), C.byref(args))
+    p, nb = ws.get(nbytes)
+    check(lib().ntf_fnn_infer_topk(_lib.ctx(dev), _stream(dev), C.byref(args), p, nb), 'ntf_fnn_infer_topk')
+    return nbytes
+
+
 def topk_merge(vals_in, idx_in, G, B, K, vals, idx):
     d = _dev(vals_in)
     check(lib().ntf_topk_merge(_lib.ctx(d), _stream(d), _p(vals_in, F32), _p(idx_in, I32), G, B, K, _p(vals, F32), _p(idx, I32)), 'ntf_topk_merge')

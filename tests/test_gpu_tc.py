@@ -64,7 +64,9 @@ def make_case(B, E, seed, h=128, ns=5):
     return A, W, b, Y, negs
 
 
-SHAPES = [(64, 128), (100, 200), (1, 13), (1000, 4097), (333, 40000)]
+# (1000, 40000) and (1000, 44774) are the exact output-layer shapes of BASELINE configs[1] / configs[2] (C2: b=1000, E=40000; C3: E=44774);
+# (256, 300): fewer expert tiles than SMs -> every expert tile cut along the batch; (2000, 20000): 157 expert tiles x 16 batch tiles in ranges
+SHAPES = [(64, 128), (100, 200), (1, 13), (1000, 4097), (333, 40000), (256, 300), (2000, 20000), (1000, 40000), (1000, 44774)]
 
 
 @pytest.mark.parametrize('B,E', SHAPES)
@@ -105,6 +107,26 @@ def test_tc_train_step_gradients(ops, ws, B, E, tpw, tnw):
     assert rel_err(db, db_ref) < 2e-5, ('db', rel_err(db, db_ref))
     assert rel_err(dW, dW_ref) < 2e-3, ('dW', rel_err(dW, dW_ref))
     assert rel_err(dA, dA_ref) < 2e-3, ('dA', rel_err(dA, dA_ref))
+
+
+def test_tc_operand_range_edges(ops, ws):
+    """the tensor-core path reads fp16 operands: same 10-bit mantissa as TF32 but a 5-bit exponent (max 65504, normals down to 6.1e-5,
+    subnormals to 6e-8).  Activations up to ~1e4 and weights spread over 1e-7 .. 1 (a third of them in fp16's subnormal range, where the
+    ABSOLUTE rounding error is <= 2^-25) still meet the elementwise logit bound; beyond 65504 is outside the kernel's contract."""
+    rng = np.random.default_rng(99)
+    torch.manual_seed(99)
+    B, E, h = 200, 1000, 128
+    A = torch.randn(B, h).abs() * torch.tensor(10.0) ** torch.randint(-3, 5, (B, h)).float()          # 1e-3 .. 1e4
+    W = torch.randn(E, h) * torch.tensor(10.0) ** torch.randint(-7, 1, (E, h)).float() * 1e-2           # 1e-9 .. 1e-2 scale: many fp16 subnormals / zeros
+    b = torch.randn(E) * 0.1
+    Y = rand_csr(rng, B, E, 1, 5)
+    negs = rng.integers(-1, E, (B, 5))
+    assert float(A.max()) < 65504 and float(A.max()) > 1e4
+    loss, _, _, _, Z = run_tc(ops, ws, A, W, b, Y, negs, 10.0, 1.0, train=False, zdbg=True)
+    z_ref = A.double() @ W.double().t() + b.double()
+    bound = 2.1 * TF32_EPS * (A.abs() @ W.abs().t()) + (A.abs().sum(1, keepdim=True) * 2.0 ** -25) + 1e-6  # relative part + subnormal absolute part
+    assert not torch.isnan(Z).any() and not torch.isinf(Z).any()
+    assert ((Z.double() - z_ref).abs() <= bound.double()).all(), float(((Z.double() - z_ref).abs() / bound.double()).max())
 
 
 def test_tc_matches_fp32_kernel_on_device(ops, ws):
