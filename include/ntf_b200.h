@@ -312,6 +312,10 @@ int ntf_peer_release(ntf_ctx* ctx, void* imported);
  * channel (0|1): exchanges that may be in flight at the same time (different streams) must use different channels (flag sets). */
 int ntf_peer_exchange_adam(ntf_ctx* ctx, void* stream, const ntf_peers* peers, float* adam_m, float* adam_v, size_t offset, size_t n,
                            double lr, double beta1, double beta2, double eps, int64_t step, int channel);
+/* expert-sharded output layer: dst[i] = sum over ranks r (in rank order) of peers->grads[r][i], i < n (a multiple of 4) -- the dA [B,h]
+ * exchange of a sharded step as one pass over peer memory between two flag barriers.  peers->grads[r] = rank r's partial (a peer-visible
+ * block, ntf_peer_alloc); dst is private and must not alias it; peers->params is not used.  Every rank calls it with the same n. */
+int ntf_peer_allreduce(ntf_ctx* ctx, void* stream, const ntf_peers* peers, size_t n, float* dst, int channel);
 
 /* ---- one whole Fnn batch, enqueued by one call: the loop body of fnn.py:118-151 -------------------------------------------------
  * forward (CSR bag, hidden layers), negative sampling (unless neg_given), output layer forward + weighted BCE; and when `train`:
@@ -364,9 +368,15 @@ typedef struct {
                                         hidden layers' backward runs, the rest while the output layer's segment is stepped -- so the
                                         whole data-parallel step is ONE capturable launch sequence.  The library does not link NCCL. */
   const ntf_peers* peers;            /* data-parallel ranks, preferred over comm: the exchange and Adam run as ntf_peer_exchange_adam inside
-                                        the step (train, phase 3, run_adam), the output layer's segment next to the hidden layers' backward */
+                                        the step (train, phase 3, run_adam), the output layer's segment next to the hidden layers' backward.
+                                        EXPERT-SHARDED layer (E < E_total): the table of the dA exchange blocks instead (peers->grads[r] = rank r's
+                                        [B,h_last] partial): the output layer writes this rank's dA there and ntf_peer_allreduce sums the shards into
+                                        dact[n_layers-2] inside the step, so that a sharded step, too, is one call (phase 3) / one graph */
   const float* x_dense;              /* dense (embedded) skill input, ntf.py:24: [B,S] rows of this batch.  Non-NULL: layer 0 is a dense
                                         layer (ntf_dense_fwd / ntf_dense_bwd), W[0] / gW[0] are in torch layout [h0,S], s_* unused */
+  void* W16;                         /* NTF_TF32, optional: fp16 image [E,h_last] of the output layer's weight W[n_layers-1], made once with ntf_to_half.
+                                        The output layer TMA-loads it instead of converting W, and the optimiser launch that steps that weight rewrites
+                                        it (after a peer-memory exchange: a local conversion pass), so it stays current from step to step */
 } ntf_fnn_step_args;
 size_t ntf_fnn_step_workspace_bytes(const ntf_ctx* ctx, const ntf_fnn_step_args* args);
 int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args* args, void* workspace, size_t workspace_bytes);

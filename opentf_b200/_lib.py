@@ -56,7 +56,7 @@ class FnnStepArgs(C.Structure):
                 ('neg', vp), ('counts', vp), ('cdf', vp), ('precision', i32), ('tpw', f32), ('tnw', f32), ('loss_scale', f32), ('loss_out', vp),
                 ('special', vp), ('pitch_words', i32), ('special_t', vp), ('member_t', vp), ('train', i32), ('run_adam', i32),
                 ('params', vp), ('grads', vp), ('adam_m', vp), ('adam_v', vp), ('n_params', sz),
-                ('lr', f64), ('beta1', f64), ('beta2', f64), ('eps', f64), ('adam_t', i64), ('prof_ev', vp * 2), ('dyn', vp), ('comm', vp), ('allreduce', vp), ('peers', vp), ('x_dense', vp)]
+                ('lr', f64), ('beta1', f64), ('beta2', f64), ('eps', f64), ('adam_t', i64), ('prof_ev', vp * 2), ('dyn', vp), ('comm', vp), ('allreduce', vp), ('peers', vp), ('x_dense', vp), ('W16', vp)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/ntf_b200.h (tests/test_abi.py checks it)
@@ -82,6 +82,7 @@ SIGNATURES = {
     'ntf_peer_import': (i32, [vp, vp, C.POINTER(vp)]),
     'ntf_peer_release': (i32, [vp, vp]),
     'ntf_peer_exchange_adam': (i32, [vp, vp, vp, vp, vp, sz, sz, f64, f64, f64, f64, i64, i32]),
+    'ntf_peer_allreduce': (i32, [vp, vp, vp, sz, vp, i32]),
     'ntf_rows_gather': (i32, [vp, vp, vp, i32, i32, vp, vp]),
     'ntf_csr_bag_fwd': (i32, [vp, vp, i32, vp, vp, vp, vp, i32, i32, vp]),
     'ntf_csr_bag_bwd_workspace_bytes': (sz, [i32, i32]),

@@ -7,7 +7,7 @@
 //
 //   pass 1   Z[128 teams x 128 experts] = A16 . W16^T per (batch tile, expert tile); every epilogue thread (team, block of 32
 //            consecutive experts) keeps only the block's MAXIMUM -> bm[B, E/32]   (4*E/32 bytes per team instead of 4*E)
-//   select   per team the K-th largest block maximum (ntf_topk_select's kernels on the [B, E/32] matrix): value Tz, block bK.
+//   select   per team the K-th largest block maximum (blockmax_threshold_kernel: bisection on the ordered keys): value Tz, block bK.
 //            K blocks have a maximum >= Tz, so Tz is a lower bound of the K-th best logit, and everything that can be in the
 //            top K has  z > Tz  or  (z == Tz and its block <= bK)  -- at most 32*K elements, all inside those K blocks.
 //   pass 2   the same product again; elements passing that test are appended to the team's candidate list (global atomics on a
@@ -20,9 +20,9 @@
 // logits are distinct where the probabilities are (equal probabilities of distinct logits -- sigmoid saturation -- are ranked
 // by logit: a permutation among exact score ties).
 //
-// Layout: CTA = (batch tile of 128 teams, chunk of consecutive expert tiles); grid = batch tiles x chunks sized to one wave.
-//   warp 16     TMA: the fp16 activation tile once, then the fp16 W tiles of the chunk through a 4-stage ring
-//   warp 17     MMA issuer: M = 128 teams, N = 128 experts, K = 128 hidden (8 x kind::f16), 4 accumulator stages in TMEM
+// Layout: CTA = (a PAIR of batch tiles of 128 teams, chunk of consecutive expert tiles); grid = pairs x chunks sized to one wave.
+//   warp 16     TMA: the two fp16 activation tiles once, then the fp16 W tiles of the chunk through a 3-stage ring
+//   warp 17     MMA issuer: per W tile two products (M = 128 teams, N = 128 experts, K = 128 hidden: 8 x kind::f16), 4 accumulator stages in TMEM
 //   warps 0-15  epilogue: thread = (team = TMEM lane, 32-expert column block): tcgen05.ld, + bias, max / threshold test
 // W16 is an fp16 image of the layer's weight kept by the caller (ntf_to_half; rewritten when the parameters change).
 #include <cuda.h>
@@ -38,10 +38,12 @@ constexpr int TX = 128;   // experts per expert tile (UMMA N)
 constexpr int HK = 128;   // hidden width
 constexpr uint32_t CHUNK = 128 * 128;        // one swizzle chunk: 128 rows x 128 bytes (64 halfs)
 constexpr uint32_t TILE_BYTES = 2 * CHUNK;   // an fp16 [128 x 128] operand tile: 2 chunks (hidden 0-63 | 64-127)
-constexpr int W_STAGES = 4;
+constexpr int W_STAGES = 3;
 constexpr int Z_STAGES = 4;
+constexpr int NH = 2;     // batch tiles per CTA: every W tile that comes in is multiplied with both (halves the W traffic out of L2, which bound the
+                          // one-tile version: 8 batch tiles x 10 MB per pass at ~4.4 TB/s = 18.6 us measured)
 constexpr uint32_t OFF_A = 0;
-constexpr uint32_t OFF_W = OFF_A + TILE_BYTES;
+constexpr uint32_t OFF_W = OFF_A + NH * TILE_BYTES;
 constexpr uint32_t OFF_BAR = OFF_W + W_STAGES * TILE_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256;
 enum { BAR_A_FULL = 0, BAR_W_FULL = 1, BAR_W_EMPTY = 1 + W_STAGES, BAR_Z_FULL = 1 + 2 * W_STAGES, BAR_Z_EMPTY = 1 + 2 * W_STAGES + Z_STAGES,
@@ -80,8 +82,10 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + OFF_BAR + NUM_BARS * 8);
   auto bar = [&](int i) { return bars + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // consecutive CTAs take different batch tiles of the SAME chunk: they stream the same W tiles at the same time (L2 hits)
-  const int bt = blockIdx.x % g.nbt, chunk = blockIdx.x / g.nbt;
+  // consecutive CTAs take different batch-tile pairs of the SAME chunk: they stream the same W tiles at the same time (L2 hits)
+  const int nbp = (g.nbt + NH - 1) / NH;  // batch-tile pairs
+  const int bp = blockIdx.x % nbp, chunk = blockIdx.x / nbp;
+  const int nh = min(NH, g.nbt - bp * NH);  // batch tiles this CTA really has
   const int t0 = (int)((long long)chunk * g.nct / g.nchunk), t1 = (int)((long long)(chunk + 1) * g.nct / g.nchunk);
   const int ntiles = t1 - t0;
 
@@ -102,8 +106,9 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
 
   if (warp == WARP_TMA) {
     if (lane == 0) {
-      mbar_expect_tx(bar(BAR_A_FULL), TILE_BYTES);
-      for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A + c * CHUNK, &map_a, c * 64, bt * TT, bar(BAR_A_FULL));
+      mbar_expect_tx(bar(BAR_A_FULL), nh * TILE_BYTES);
+      for (int hf = 0; hf < nh; ++hf)
+        for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A + hf * TILE_BYTES + c * CHUNK, &map_a, c * 64, (bp * NH + hf) * TT, bar(BAR_A_FULL));
       for (int it = 0; it < ntiles; ++it) {
         const int s = it % W_STAGES;
         mbar_wait(bar(BAR_W_EMPTY + s), ((it / W_STAGES) & 1) ^ 1);
@@ -112,38 +117,43 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
       }
     }
   } else if (warp == WARP_MMA) {
-    if (lane == 0) {
-      mbar_wait(bar(BAR_A_FULL), 0);
-      for (int it = 0; it < ntiles; ++it) {
-        const int s = it % W_STAGES, zs = it % Z_STAGES;
-        mbar_wait(bar(BAR_W_FULL + s), (it / W_STAGES) & 1);
-        mbar_wait(bar(BAR_Z_EMPTY + zs), ((it / Z_STAGES) & 1) ^ 1);
+    // the whole warp runs this loop converged; one elected lane issues the MMAs and the commits (tc_common.cuh: elect_one)
+    mbar_wait(bar(BAR_A_FULL), 0);
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it % W_STAGES;
+      mbar_wait(bar(BAR_W_FULL + s), (it / W_STAGES) & 1);
+      const uint64_t d_w = smem_desc(sbase + OFF_W + s * TILE_BYTES, 16, 1024);
+      for (int hf = 0; hf < nh; ++hf) {
+        const int q = it * nh + hf, zs = q % Z_STAGES;  // accumulator stages are handed out per product
+        mbar_wait(bar(BAR_Z_EMPTY + zs), ((q / Z_STAGES) & 1) ^ 1);
         tc_fence_after();
+        const uint64_t d_a = smem_desc(sbase + OFF_A + hf * TILE_BYTES, 16, 1024);
 #pragma unroll
         for (int i = 0; i < HK / 16; ++i) {  // 8 k-steps of 16 halfs: chunk i/4, 32-byte slice i%4 of the 128-byte swizzle row
-          const uint64_t da = smem_desc(sbase + OFF_A + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
-          const uint64_t db = smem_desc(sbase + OFF_W + s * TILE_BYTES + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
-          mma_f16(tmem + zs * TX, da, db, IDESC, i > 0);
+          const uint64_t koff = (uint64_t)(((i >> 2) * CHUNK + (i & 3) * 32) >> 4);
+          if (elect_one()) mma_f16(tmem + zs * TX, d_a + koff, d_w + koff, IDESC, i > 0);
         }
-        tc_commit(bar(BAR_Z_FULL + zs));
-        tc_commit(bar(BAR_W_EMPTY + s));
+        if (elect_one()) tc_commit(bar(BAR_Z_FULL + zs));
       }
+      if (elect_one()) tc_commit(bar(BAR_W_EMPTY + s));
     }
   } else {
     // ---- epilogue: thread = (team = TMEM lane, column block cb of 32 experts) ----
-    const int q = warp & 3, cb = warp >> 2;
-    const int team = bt * TT + q * 32 + lane;
-    const bool team_ok = team < g.B;
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    float Tz = 0.f;
-    int bK = 0;
-    if (PASS == 2 && team_ok) {
-      Tz = __ldg(g.thr_val + team);
-      bK = __ldg(g.thr_blk + team);
+    const int qd = warp & 3, cb = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    int team[NH];
+    bool team_ok[NH];
+    float Tz[NH];
+    int bK[NH];
+#pragma unroll
+    for (int hf = 0; hf < NH; ++hf) {
+      team[hf] = (bp * NH + hf) * TT + qd * 32 + lane;
+      team_ok[hf] = hf < nh && team[hf] < g.B;
+      Tz[hf] = 0.f; bK[hf] = 0;
+      if (PASS == 2 && team_ok[hf]) { Tz[hf] = __ldg(g.thr_val + team[hf]); bK[hf] = __ldg(g.thr_blk + team[hf]); }
     }
     const float NEG_INF = __int_as_float(0xff800000);
     for (int it = 0; it < ntiles; ++it) {
-      const int zs = it % Z_STAGES;
       const int e_base = (t0 + it) * TX + cb * BLK;  // first expert of this thread's block
       const int blk = (t0 + it) * 4 + cb;
       // the block's biases (the same 32 addresses in every lane: broadcast loads); past E: -inf so that the column can never win
@@ -158,25 +168,32 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
 #pragma unroll
         for (int i = 0; i < BLK; ++i) bv[i] = (e_base + i < g.E) ? __ldg(g.bias + e_base + i) : NEG_INF;
       }
-      mbar_wait(bar(BAR_Z_FULL + zs), (it / Z_STAGES) & 1);
-      tc_fence_after();
-      float z[BLK];
-      tmem_ld32(tmem + lane_base + zs * TX + cb * BLK, z);
-      tc_fence_before();
-      mbar_arrive(bar(BAR_Z_EMPTY + zs));
-      float m = NEG_INF;
 #pragma unroll
-      for (int i = 0; i < BLK; ++i) { z[i] += bv[i]; m = fmaxf(m, z[i]); }
-      if (PASS == 1) {
-        if (team_ok) g.bm[(size_t)team * g.nblk + blk] = m;
-      } else {
-        if (team_ok && m >= Tz && (m > Tz || blk <= bK)) {  // rare: K of the E/32 blocks of a team get here
+      for (int hf = 0; hf < NH; ++hf) {
+        if (hf >= nh) break;
+        const int q = it * nh + hf, zs = q % Z_STAGES;
+        mbar_wait(bar(BAR_Z_FULL + zs), (q / Z_STAGES) & 1);
+        tc_fence_after();
+        float z[BLK];
+        tmem_ld32(tmem + lane_base + zs * TX + cb * BLK, z);
+        tc_fence_before();
+        mbar_arrive(bar(BAR_Z_EMPTY + zs));
+        float m = NEG_INF;
 #pragma unroll
-          for (int i = 0; i < BLK; ++i) {
-            const float v = z[i];
-            if (v > Tz || (v == Tz && blk <= bK)) {
-              const int slot = atomicAdd(g.cnt + team, 1);
-              if (slot < g.cap) g.cand[(size_t)team * g.cap + slot] = ((unsigned long long)ordered_key(v) << 32) | (uint32_t)(~(uint32_t)(e_base + i));
+        for (int i = 0; i < BLK; ++i) { z[i] += bv[i]; m = fmaxf(m, z[i]); }
+        if (PASS == 1) {
+          if (team_ok[hf]) g.bm[(size_t)team[hf] * g.nblk + blk] = m;
+        } else {
+          const float tz = Tz[hf];
+          const bool tie_ok = blk <= bK[hf];
+          if (team_ok[hf] && m >= tz && (m > tz || tie_ok)) {  // rare: K of the E/32 blocks of a team get here
+#pragma unroll
+            for (int i = 0; i < BLK; ++i) {
+              const float v = z[i];
+              if (v > tz || (v == tz && tie_ok)) {
+                const int slot = atomicAdd(g.cnt + team[hf], 1);
+                if (slot < g.cap) g.cand[(size_t)team[hf] * g.cap + slot] = ((unsigned long long)ordered_key(v) << 32) | (uint32_t)(~(uint32_t)(e_base + i));
+              }
             }
           }
         }
@@ -232,17 +249,18 @@ __global__ void __launch_bounds__(FIN_THREADS) infer_topk_final_kernel(const uns
   }
 }
 
-// per team (one warp): Tz = the K-th largest of the row's block maxima and bK = the block that holds it under the rank order (value
-// descending, ties -> lower block first).  Bisection on the order-preserving integer image of the fp32 maxima: 32 rounds of "how many
-// keys >= candidate", the row held in registers (PL keys per lane, contiguous chunks so that ties can be ranked by block id).
+// per team (one CTA of 4 warps): Tz = the K-th largest of the row's block maxima and bK = the block that holds it under the rank order (value
+// descending, ties -> lower block first).  Bisection on the order-preserving integer image of the fp32 maxima: 32 rounds of "how many keys
+// >= candidate" (register-resident keys, PL per thread in contiguous chunks so that ties can be ranked by block id; one barrier per round).
 template <int PL>
-__global__ void __launch_bounds__(128) blockmax_threshold_kernel(const float* __restrict__ bm, int B, int nblk, int K, float* __restrict__ thr_val,
+__global__ void __launch_bounds__(128) blockmax_threshold_kernel(const float* __restrict__ bm, int nblk, int K, float* __restrict__ thr_val,
                                                                  int32_t* __restrict__ thr_blk) {
-  const int team = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (team >= B) return;
-  const int per = (nblk + 31) / 32;  // <= PL (checked by the host)
+  __shared__ int cnt[2][4];
+  __shared__ int wsum[2][4];
+  const int team = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int per = (nblk + 127) / 128;  // <= PL (checked by the host)
   const float* row = bm + (size_t)team * nblk;
-  const int first = lane * per;
+  const int first = tid * per;
   uint32_t key[PL];
 #pragma unroll
   for (int i = 0; i < PL; ++i) key[i] = (i < per && first + i < nblk) ? ordered_key(__ldg(row + first + i)) : 0u;  // 0 < every real key
@@ -250,23 +268,31 @@ __global__ void __launch_bounds__(128) blockmax_threshold_kernel(const float* __
 #pragma unroll 1
   for (int bit = 31; bit >= 0; --bit) {
     const uint32_t cand = T | (1u << bit);
-    int c = 0;
+    int c0 = 0, c1 = 0;
 #pragma unroll
-    for (int i = 0; i < PL; ++i) c += key[i] >= cand;
-    if (__reduce_add_sync(0xffffffffu, c) >= K) T = cand;
+    for (int i = 0; i < PL; i += 2) { c0 += key[i] >= cand; if (i + 1 < PL) c1 += key[i + 1] >= cand; }
+    const int c = __reduce_add_sync(0xffffffffu, c0 + c1);
+    if (lane == 0) cnt[bit & 1][w] = c;
+    __syncthreads();  // (the buffer of round r is rewritten in round r+2, after everybody passed round r+1's barrier)
+    if (cnt[bit & 1][0] + cnt[bit & 1][1] + cnt[bit & 1][2] + cnt[bit & 1][3] >= K) T = cand;
   }
   int gt = 0, eq = 0;
 #pragma unroll
   for (int i = 0; i < PL; ++i) { gt += key[i] > T; eq += key[i] == T; }
-  const int need = K - __reduce_add_sync(0xffffffffu, gt);  // the need-th block (in id order) whose maximum equals Tz is the K-th block
+  const int gtw = __reduce_add_sync(0xffffffffu, gt);
   int incl = eq;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int v = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += v;
   }
-  const int before = incl - eq;
-  if (before < need && need <= incl) {
+  if (lane == 0) wsum[0][w] = gtw;
+  if (lane == 31) wsum[1][w] = incl;
+  __syncthreads();
+  const int need = K - (wsum[0][0] + wsum[0][1] + wsum[0][2] + wsum[0][3]);  // the need-th block (in id order) whose maximum equals Tz is the K-th block
+  int before = incl - eq;
+  for (int q = 0; q < w; ++q) before += wsum[1][q];
+  if (before < need && need <= before + eq) {
     int seen = before, blk = first;
 #pragma unroll
     for (int i = 0; i < PL; ++i)
@@ -306,7 +332,7 @@ extern "C" int ntf_to_half(ntf_ctx* ctx, void* stream, const float* x, size_t n,
 
 // the fused path needs the tensor-core width, at least K blocks of 32 experts per team, and a candidate list that sorts in shared memory
 extern "C" int ntf_infer_topk_supported(int B, int h, int E, int K) {
-  return (h == HK && B >= 1 && K >= 1 && K <= 128 && (long long)K * BLK <= (long long)E && cdiv(cdiv(E, TX) * 4, 32) <= 128) ? 1 : 0;  // (E <= 131072 per shard)
+  return (h == HK && B >= 1 && K >= 1 && K <= 128 && (long long)K * BLK <= (long long)E && cdiv(cdiv(E, TX) * 4, 128) <= 32) ? 1 : 0;  // (E <= 131072 per shard)
 }
 
 extern "C" size_t ntf_infer_topk_workspace_bytes(int B, int h, int E, int K) { return it_ws(B, h, E, K).total; }
@@ -332,7 +358,8 @@ extern "C" int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_a
   g.bias = a->b; g.B = a->B; g.E = a->E; g.K = a->K;
   g.nbt = cdiv(a->B, TT); g.nct = cdiv(a->E, TX);
   const int sm = ctx->sm_count > 0 ? ctx->sm_count : 148;
-  g.nchunk = g.nbt >= sm ? 1 : sm / g.nbt;  // one wave: batch tiles x chunks <= SMs
+  const int nbp = cdiv(g.nbt, NH);
+  g.nchunk = nbp >= sm ? 1 : sm / nbp;  // one wave: batch-tile pairs x chunks <= SMs
   if (g.nchunk > g.nct) g.nchunk = g.nct;
   g.nblk = g.nct * 4;
   g.bm = (float*)(ws + w.bm);
@@ -346,18 +373,22 @@ extern "C" int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_a
   int rc;
   if ((rc = make_map(ctx, &ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)a->B, HK, TT, 64))) return rc;
   if ((rc = make_map(ctx, &mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->W16, (uint64_t)a->E, HK, TX, 64))) return rc;
-  const int grid = g.nbt * g.nchunk;
-  NTF_CUDA(cudaFuncSetAttribute(infer_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  NTF_CUDA(cudaFuncSetAttribute(infer_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  const int grid = nbp * g.nchunk;
+  static bool attr_set[64] = {};  // (per device: the attribute call costs about as much as a launch)
+  if (!attr_set[ctx->device & 63]) {
+    NTF_CUDA(cudaFuncSetAttribute(infer_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    NTF_CUDA(cudaFuncSetAttribute(infer_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set[ctx->device & 63] = true;
+  }
   NTF_CUDA(cudaMemsetAsync(g.cnt, 0, (size_t)a->B * sizeof(int), st));
   NTF_COUNT_LAUNCH; infer_topk_kernel<1><<<grid, NT, SMEM_BYTES, st>>>(ma, mw, g);
   NTF_LAUNCH_CHECK();
   {
-    const int per = cdiv(g.nblk, 32), tblocks = cdiv(a->B, 4);  // 4 warps (teams) per CTA
+    const int per = cdiv(g.nblk, 128);
     NTF_COUNT_LAUNCH;
-    if (per <= 16) blockmax_threshold_kernel<16><<<tblocks, 128, 0, st>>>(g.bm, a->B, g.nblk, a->K, tv, ti);
-    else if (per <= 64) blockmax_threshold_kernel<64><<<tblocks, 128, 0, st>>>(g.bm, a->B, g.nblk, a->K, tv, ti);
-    else blockmax_threshold_kernel<128><<<tblocks, 128, 0, st>>>(g.bm, a->B, g.nblk, a->K, tv, ti);
+    if (per <= 4) blockmax_threshold_kernel<4><<<a->B, 128, 0, st>>>(g.bm, g.nblk, a->K, tv, ti);
+    else if (per <= 12) blockmax_threshold_kernel<12><<<a->B, 128, 0, st>>>(g.bm, g.nblk, a->K, tv, ti);
+    else blockmax_threshold_kernel<32><<<a->B, 128, 0, st>>>(g.bm, g.nblk, a->K, tv, ti);
     NTF_LAUNCH_CHECK();
   }
   NTF_COUNT_LAUNCH; infer_topk_kernel<2><<<grid, NT, SMEM_BYTES, st>>>(ma, mw, g);

@@ -11,7 +11,9 @@
 //     (ntf_out_train_args.W16, rewritten by the optimiser) or this file makes it per call;
 //   * the dW drain of an expert tile goes through the idle dz ring, so the NEXT tile's W / activation loads and first forward
 //     product run underneath it;
-//   * dA chunks leave through THREE staging buffers (the third activation stage of round 1, which its timeline showed idle).
+//   * dA is produced TRANSPOSED (hidden unit on the TMEM lane), so its warps add it into dA[B,128] with coalesced red.global.add from
+//     registers -- no staging buffer, no barriers, no proxy fences -- and the 48 KB of staging go to a third activation stage, which takes
+//     tile n+1's activation load off the critical path of tile n-1's backward products.
 // An expert tile whose batch range is cut between two CTAs adds its dW / db partials into rows zeroed beforehand; with at most two
 // contributions per element (0 + a + b) the sums are order-independent, so dW / db are run-to-run deterministic whenever
 // E >= 128 * (number of SMs); dA is still summed by L2 in arrival order.
@@ -31,21 +33,20 @@ constexpr int TE = 128, TB = 128, HK = 128;
 constexpr uint32_t CHUNK = 128 * 128;
 constexpr uint32_t W16_BYTES = TE * HK * 2, A16_BYTES = TB * HK * 2, DZ_BYTES = TE * TB * 2;
 constexpr uint32_t OFF_W16 = 0;
-constexpr uint32_t OFF_A16 = OFF_W16 + W16_BYTES;       // 2 stages
-constexpr uint32_t OFF_DZ = OFF_A16 + 2 * A16_BYTES;    // 2 stages; at the end of an expert tile: staging of the dW drain (64 KB)
+constexpr int AST = 3;                                  // activation stages: tile n+1's load must not wait for tile n-1's backward products
+constexpr uint32_t OFF_A16 = OFF_W16 + W16_BYTES;
+constexpr uint32_t OFF_DZ = OFF_A16 + AST * A16_BYTES;  // 2 stages; at the end of an expert tile: staging of the dW drain (64 KB)
 constexpr uint32_t OFF_PLANE = OFF_DZ + 2 * DZ_BYTES;   // 2 stages x (special | member) planes, 2 KB each
 constexpr uint32_t PLANE_BYTES = TE * 4 * 4;
-constexpr uint32_t OFF_DAST = OFF_PLANE + 4 * PLANE_BYTES;
-constexpr int DA_BUFS = 3;                              // dA staging buffers: [128 teams][128 B] fp32 chunks on their way to the TMA reduce-add
-constexpr uint32_t OFF_BAR = OFF_DAST + DA_BUFS * CHUNK;
+constexpr uint32_t OFF_BAR = OFF_PLANE + 4 * PLANE_BYTES;
 constexpr uint32_t OFF_DBS = OFF_BAR + 512;              // [4][128] fp32 scratch of the db combine
 constexpr uint32_t SMEM_BYTES = OFF_DBS + 4 * TE * 4;
 static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared memory limit");
 
 constexpr uint32_t TM_Z = 0, TM_DW = 256, TM_DA = 384, TM_COLS = 512;
 
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = 1, BAR_A_FULL = 2, BAR_A_EMPTY = 4, BAR_Z_FULL = 6, BAR_Z_EMPTY = 8, BAR_DZ_FULL = 10, BAR_DZ_EMPTY = 12,
-       BAR_DA_FULL = 14, BAR_DA_EMPTY = 15, BAR_DW_FULL = 16, BAR_DW_EMPTY = 17, BAR_SP_FULL = 18, BAR_SP_EMPTY = 20, NUM_BARS = 22 };
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = 1, BAR_A_FULL = 2, BAR_A_EMPTY = 5, BAR_Z_FULL = 8, BAR_Z_EMPTY = 10, BAR_DZ_FULL = 12, BAR_DZ_EMPTY = 14,
+       BAR_DA_FULL = 16, BAR_DA_EMPTY = 17, BAR_DW_FULL = 18, BAR_DW_EMPTY = 19, BAR_SP_FULL = 20, BAR_SP_EMPTY = 22, NUM_BARS = 24 };
 
 struct Tc2Args {
   const float* bias;
@@ -55,13 +56,15 @@ struct Tc2Args {
   float tpw, tnw, scale;
   float* dW;        // [E,128] or NULL (validation: forward + loss only)
   float* db;
+  float* dA;        // [B,128], zeroed by the caller; every CTA adds its expert tiles' contribution (red.global.add)
   float* loss_part; // [gridDim.x]
   float* Zdbg;      // debug: raw logits [B,E]
-  long long* timing;  // debug: per CTA (start ns, end ns, smid)
+  long long* timing;  // debug: per CTA TSLOTS slots: start ns, end ns, smid, start / end clock; from slot 8, 8 per tile n < 60: Z ready, tile done, drain start, drain end, bwd issue start / end, dA staged, dW products complete
   int nct, nbt;     // expert tiles, batch tiles
   int split;        // 0: CTA c owns tiles [c*T/G, (c+1)*T/G) of the expert-major sequence; s > 0: expert tile c/s, batch part c%s of s
 };
 
+constexpr int TSLOTS = 512;  // debug stamps per CTA (Tc2Args::timing)
 constexpr int EPI_WARPS = 16, NT = 736, WARP_DA = 16, WARP_TMA = 20, WARP_MMA = 21, WARP_SP = 22, EPI_THREADS = EPI_WARPS * 32;
 constexpr uint32_t IDESC_FWD = instr_desc(0, 0, 0, TE, TB);
 constexpr uint32_t IDESC_DW = instr_desc(0, 0, 1, TE, HK);
@@ -92,8 +95,7 @@ __global__ void __launch_bounds__(256) zero_cut_tiles_kernel(Tc2Args g) {
   for (int i = threadIdx.x; i < rows; i += 256) g.db[e0 + i] = 0.f;
 }
 
-__global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ CUtensorMap map_w16, const __grid_constant__ CUtensorMap map_a16,
-                                                        const __grid_constant__ CUtensorMap map_da, Tc2Args g) {
+__global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ CUtensorMap map_w16, const __grid_constant__ CUtensorMap map_a16, Tc2Args g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   if ((sbase & 1023u) != 0u) __trap();
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
     unsigned long long gt; unsigned smid;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    g.timing[3 * blockIdx.x] = (long long)gt; g.timing[3 * blockIdx.x + 2] = smid;
+    g.timing[TSLOTS * blockIdx.x] = (long long)gt; g.timing[TSLOTS * blockIdx.x + 2] = smid; g.timing[TSLOTS * blockIdx.x + 3] = clock64();
   }
   int L0, L1;
   tile_range(g, blockIdx.x, gridDim.x, &L0, &L1);
@@ -118,8 +120,8 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
     mbar_init(bar(BAR_W_FULL), 1); mbar_init(bar(BAR_W_EMPTY), 1);
     mbar_init(bar(BAR_DA_FULL), 1); mbar_init(bar(BAR_DA_EMPTY), 128);
     mbar_init(bar(BAR_DW_FULL), 1); mbar_init(bar(BAR_DW_EMPTY), EPI_THREADS);
+    for (int s = 0; s < AST; ++s) { mbar_init(bar(BAR_A_FULL + s), 1); mbar_init(bar(BAR_A_EMPTY + s), 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar(BAR_A_FULL + s), 1); mbar_init(bar(BAR_A_EMPTY + s), 1);
       mbar_init(bar(BAR_Z_FULL + s), 1); mbar_init(bar(BAR_Z_EMPTY + s), EPI_THREADS);
       mbar_init(bar(BAR_DZ_FULL + s), EPI_THREADS); mbar_init(bar(BAR_DZ_EMPTY + s), 1);
       mbar_init(bar(BAR_SP_FULL + s), 1); mbar_init(bar(BAR_SP_EMPTY + s), EPI_THREADS);
@@ -148,8 +150,8 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
           mbar_expect_tx(bar(BAR_W_FULL), W16_BYTES);
           for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_W16 + c * CHUNK, &map_w16, c * 64, e * TE, bar(BAR_W_FULL));
         }
-        const int s = n & 1;
-        mbar_wait(bar(BAR_A_EMPTY + s), ((n >> 1) & 1) ^ 1);
+        const int s = n % AST;
+        mbar_wait(bar(BAR_A_EMPTY + s), ((n / AST) & 1) ^ 1);
         mbar_expect_tx(bar(BAR_A_FULL + s), A16_BYTES);
         for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A16 + s * A16_BYTES + c * CHUNK, &map_a16, c * 64, t * TB, bar(BAR_A_FULL + s));
       }
@@ -166,59 +168,68 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
       }
     }
   } else if (warp == WARP_MMA) {
-    if (lane == 0) {
-      auto issue_fwd = [&](int n, bool item_last) {
-        const int s = n & 1;
-        const uint32_t ph = (n >> 1) & 1;
-        mbar_wait(bar(BAR_A_FULL + s), ph);
-        mbar_wait(bar(BAR_Z_EMPTY + s), ph ^ 1);
-        tc_fence_after();
+    // the whole warp runs this loop converged; one elected lane issues the MMAs and the commits (tc_common.cuh: elect_one)
+    const uint64_t d_w16_k = smem_desc(sbase + OFF_W16, 16, 1024);      // W16 as K-major operand (forward), + chunk / 32-byte slice per k-step
+    const uint64_t d_w16_mn = smem_desc(sbase + OFF_W16, CHUNK, 1024);  // W16 as MN-major operand (dA^T: M = hidden), + 2048 bytes per k-step
+    auto issue_fwd = [&](int n, bool item_last) {
+      const int s = n & 1, sa = n % AST;
+      const uint32_t ph = (n >> 1) & 1;
+      mbar_wait(bar(BAR_A_FULL + sa), (n / AST) & 1);
+      mbar_wait(bar(BAR_Z_EMPTY + s), ph ^ 1);
+      tc_fence_after();
+      const uint64_t d_a = smem_desc(sbase + OFF_A16 + sa * A16_BYTES, 16, 1024);
 #pragma unroll
-        for (int i = 0; i < HK / 16; ++i) {
-          const uint64_t da = smem_desc(sbase + OFF_W16 + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
-          const uint64_t db = smem_desc(sbase + OFF_A16 + s * A16_BYTES + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
-          mma_f16(tmem + TM_Z + s * TB, da, db, IDESC_FWD, i > 0);
-        }
+      for (int i = 0; i < HK / 16; ++i) {
+        const uint64_t koff = (uint64_t)(((i >> 2) * CHUNK + (i & 3) * 32) >> 4);  // (the address field holds bytes >> 4)
+        if (elect_one()) mma_f16(tmem + TM_Z + s * TB, d_w16_k + koff, d_a + koff, IDESC_FWD, i > 0);
+      }
+      if (elect_one()) {
         tc_commit(bar(BAR_Z_FULL + s));
         if (!train) {  // forward only: the operands are free once this product has read them
-          tc_commit(bar(BAR_A_EMPTY + s));
+          tc_commit(bar(BAR_A_EMPTY + sa));
           if (item_last) tc_commit(bar(BAR_W_EMPTY));
         }
-      };
-      int j = -1;
-      for (int L = L0, n = 0; L < L1; ++L, ++n) {
-        const int e = L / nbt, t = L - e * nbt;
-        const bool first = (L == L0 || t == 0), last = (L == L1 - 1 || t == nbt - 1);
-        if (first) {
-          ++j;
-          mbar_wait(bar(BAR_W_FULL), j & 1);
-          issue_fwd(n, last);  // (no product of this item could be issued ahead: the image was the previous item's until now)
-        }
-        if (!last) issue_fwd(n + 1, (L + 1 == L1 - 1) || (t + 1 == nbt - 1));  // keeps the tensor pipe busy while the epilogue works on tile n
-        if (!train) continue;
-        const int s = n & 1;
-        mbar_wait(bar(BAR_DZ_FULL + s), (n >> 1) & 1);
-        if (first && j > 0) mbar_wait(bar(BAR_DW_EMPTY), (j - 1) & 1);  // the previous item's dW has left TMEM
-        tc_fence_after();
+      }
+    };
+    int j = -1;
+    for (int L = L0, n = 0; L < L1; ++L, ++n) {
+      const int e = L / nbt, t = L - e * nbt;
+      const bool first = (L == L0 || t == 0), last = (L == L1 - 1 || t == nbt - 1);
+      if (first) {
+        ++j;
+        mbar_wait(bar(BAR_W_FULL), j & 1);
+        issue_fwd(n, last);  // (no product of this item could be issued ahead: the image was the previous item's until now)
+      }
+      if (!last) issue_fwd(n + 1, (L + 1 == L1 - 1) || (t + 1 == nbt - 1));  // keeps the tensor pipe busy while the epilogue works on tile n
+      if (!train) continue;
+      const int s = n & 1;
+      mbar_wait(bar(BAR_DZ_FULL + s), (n >> 1) & 1);
+      if (first && j > 0) mbar_wait(bar(BAR_DW_EMPTY), (j - 1) & 1);  // the previous item's dW has left TMEM
+      tc_fence_after();
+      if (g.timing && lane == 0 && n < 60) g.timing[TSLOTS * blockIdx.x + 8 + 8 * n + 4] = clock64();
+      const uint64_t d_dz_k = smem_desc(sbase + OFF_DZ + s * DZ_BYTES, 16, 1024);       // dz^T as K-major operand (K = teams)
+      const uint64_t d_dz_mn = smem_desc(sbase + OFF_DZ + s * DZ_BYTES, CHUNK, 1024);   // dz as MN-major operand (M = teams)
+      const int sa = n % AST;
+      const uint64_t d_a_mn = smem_desc(sbase + OFF_A16 + sa * A16_BYTES, CHUNK, 1024);  // A16 as MN-major operand (N = hidden)
 #pragma unroll
-        for (int i = 0; i < TB / 16; ++i) {  // dW[128 j x 128 k] += dz^T[j, n] . A16[n, k]
-          const uint64_t da = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
-          const uint64_t db = smem_desc(sbase + OFF_A16 + s * A16_BYTES + i * 2048, CHUNK, 1024);
-          mma_f16(tmem + TM_DW, da, db, IDESC_DW, (!first || i > 0));
-        }
-        mbar_wait(bar(BAR_DA_EMPTY), (n & 1) ^ 1);
-        tc_fence_after();
+      for (int i = 0; i < TB / 16; ++i) {  // dW[128 j x 128 k] += dz^T[j, n] . A16[n, k]
+        const uint64_t koff = (uint64_t)(((i >> 2) * CHUNK + (i & 3) * 32) >> 4);
+        if (elect_one()) mma_f16(tmem + TM_DW, d_dz_k + koff, d_a_mn + (uint64_t)((i * 2048) >> 4), IDESC_DW, (!first || i > 0));
+      }
+      mbar_wait(bar(BAR_DA_EMPTY), (n & 1) ^ 1);
+      tc_fence_after();
 #pragma unroll
-        for (int i = 0; i < TE / 16; ++i) {  // dA[128 n x 128 k] = dz[j, n]^T . W16[j, k]
-          const uint64_t da = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + i * 2048, CHUNK, 1024);
-          const uint64_t db = smem_desc(sbase + OFF_W16 + i * 2048, CHUNK, 1024);
-          mma_f16(tmem + TM_DA, da, db, IDESC_DA, i > 0);
-        }
+      for (int i = 0; i < TE / 16; ++i) {  // dA^T[128 k x 128 n] = W16[j, k]^T . dz[j, n]: hidden on the TMEM lanes (see the dA warps)
+        const uint64_t koff = (uint64_t)((i * 2048) >> 4);
+        if (elect_one()) mma_f16(tmem + TM_DA, d_w16_mn + koff, d_dz_mn + koff, IDESC_DA, i > 0);
+      }
+      if (elect_one()) {
         tc_commit(bar(BAR_DA_FULL));
         tc_commit(bar(BAR_DZ_EMPTY + s));
-        tc_commit(bar(BAR_A_EMPTY + s));
+        tc_commit(bar(BAR_A_EMPTY + sa));
         if (last) { tc_commit(bar(BAR_W_EMPTY)); tc_commit(bar(BAR_DW_FULL)); }
       }
+      if (g.timing && lane == 0 && n < 60) g.timing[TSLOTS * blockIdx.x + 8 + 8 * n + 5] = clock64();
     }
   } else if (warp < EPI_WARPS) {
     // ====================== logits / loss epilogue: thread = (expert jl, block cb of 32 of the tile's 128 teams) ======================
@@ -263,6 +274,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
         if (!e_ok) S = 0;
       }
       mbar_wait(bar(BAR_Z_FULL + s), ph);
+      if (g.timing && threadIdx.x == 0 && n < 60) g.timing[TSLOTS * blockIdx.x + 8 + 8 * n] = clock64();
       tc_fence_after();
       float z[32];
       tmem_ld32(tmem + lane_base + TM_Z + s * TB + cb * 32, z);
@@ -370,13 +382,16 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
         fence_proxy_async();
         mbar_arrive(bar(BAR_DZ_FULL + s));
       }
+      if (g.timing && lane == 0 && n < 60) atomicMax((unsigned long long*)(g.timing + TSLOTS * blockIdx.x + 8 + 8 * n + 1), (unsigned long long)clock64());  // slowest warp
       if (!last) continue;
       // ---- end of the expert tile: fold its loss terms, drain dW / db ----
       acc_lin += acc_lin2.x + acc_lin2.y;
       db_acc += db_acc2.x + db_acc2.y;
       loss_total += e_ok ? g.tnw * 0.6931471805599453f * (acc_lg - acc_lin) + loss_sp : 0.f;
       if (train) {
+        if (g.timing && threadIdx.x == 0 && n < 60) g.timing[TSLOTS * blockIdx.x + 8 + 8 * n + 2] = clock64();
         mbar_wait(bar(BAR_DW_FULL), j & 1);  // every product of the item has completed: the dz ring is free for staging
+        if (g.timing && threadIdx.x == 0 && n < 60) g.timing[TSLOTS * blockIdx.x + 8 + 8 * n + 7] = clock64();
         tc_fence_after();
         float v[32];
         tmem_ld32(tmem + lane_base + TM_DW + cb * 32, v);
@@ -394,10 +409,18 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
         for (int i = 0; i < TE / EPI_WARPS; ++i) {
           const int r = warp * (TE / EPI_WARPS) + i;
           if (e0 + r < g.E) {
-            const float4 v4 = stage[r * 32 + (lane ^ (r & 31))];
-            float* dst = g.dW + (size_t)(e0 + r) * HK + 4 * lane;
-            if (whole) *reinterpret_cast<float4*>(dst) = v4;
-            else { atomicAdd(dst, v4.x); atomicAdd(dst + 1, v4.y); atomicAdd(dst + 2, v4.z); atomicAdd(dst + 3, v4.w); }
+            if (whole) {
+              *reinterpret_cast<float4*>(g.dW + (size_t)(e0 + r) * HK + 4 * lane) = stage[r * 32 + (lane ^ (r & 31))];
+            } else {
+              // a cut tile: partial sums into zeroed rows.  Lane = consecutive floats (128 bytes per instruction): the L2 reduction units take
+              // coalesced scalar adds at ~5 TB/s chip-wide, 16-byte-strided ones at an eighth of that (scripts/mb/mb_reduce.cu)
+              const float* srow = reinterpret_cast<const float*>(stage + r * 32);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int col = q * 32 + lane;
+                atomicAdd(g.dW + (size_t)(e0 + r) * HK + col, srow[(((col >> 2) ^ (r & 31)) << 2) + (col & 3)]);
+              }
+            }
           }
         }
         if (cb == 0 && e_ok) {
@@ -405,6 +428,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
           if (whole) g.db[e] = dbv; else atomicAdd(g.db + e, dbv);
         }
         asm volatile("bar.sync 1, 512;" ::: "memory");  // staging and db scratch are free again before anyone writes the next tile's dz
+        if (g.timing && threadIdx.x == 0 && n < 60) g.timing[TSLOTS * blockIdx.x + 8 + 8 * n + 3] = clock64();
       }
     }
     // one loss partial per CTA: fixed-order combine (shuffle tree, then warps in order)
@@ -419,40 +443,39 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
       g.loss_part[blockIdx.x] = l;
     }
   } else if (warp >= WARP_DA && warp < WARP_DA + 4) {
-    // ====== dA epilogue: thread = team.  TMEM -> regs -> swizzled fp32 chunk in one of three staging buffers -> TMA reduce-add into dA[B,128] ======
+    // ====== dA epilogue.  The product is taken TRANSPOSED (dA^T = W^T dz: hidden unit on the TMEM lane, teams along the columns), so a
+    // warp's 32 lanes hold 32 consecutive hidden units of ONE team: red.global.add.f32 straight from registers, 128 contiguous bytes per
+    // instruction -- the access pattern the L2 reduction units take at full rate (scripts/mb/mb_reduce.cu: as fast as the TMA reduce-add,
+    // without its shared-memory staging, barriers and proxy fences).  The sum over expert tiles (= across CTAs) happens in L2. ======
     if (train) {
-      const int r = threadIdx.x - WARP_DA * 32;
+      const int k = threadIdx.x - WARP_DA * 32;  // hidden unit = TMEM lane
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-      int k = 0;
       for (int L = L0, n = 0; L < L1; ++L, ++n) {
         const int t = L % nbt;
         mbar_wait(bar(BAR_DA_FULL), n & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < HK / 32; ++c, ++k) {
+        for (int c = 0; c < TB / 32; ++c) {
           float v[32];
           tmem_ld32(tmem + lane_base + TM_DA + c * 32, v);
-          if (c == HK / 32 - 1) {
+          if (c == TB / 32 - 1) {
             tc_fence_before();
             mbar_arrive(bar(BAR_DA_EMPTY));
           }
-          const uint32_t buf = (uint32_t)(k % DA_BUFS) * CHUNK;
-          if (r == 0) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");  // the reduce that used this buffer three chunks ago is done reading it
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          uint8_t* row = sgen + OFF_DAST + buf + r * 128;
+          const int team0 = t * TB + c * 32;
+          float* dst = g.dA + (size_t)team0 * HK + k;
+          const int nrem = g.B - team0;
+          if (nrem >= 32) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(row + ((q ^ (r & 7)) << 4)) = make_float4(v[4 * q] * g.scale, v[4 * q + 1] * g.scale, v[4 * q + 2] * g.scale, v[4 * q + 3] * g.scale);
-          fence_proxy_async();
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          if (r == 0) {
-            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
-                         ::"l"(reinterpret_cast<uint64_t>(&map_da)), "r"(c * 32), "r"(t * TB), "r"(sbase + OFF_DAST + buf) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            for (int i = 0; i < 32; ++i) atomicAdd(dst + (size_t)i * HK, v[i] * g.scale);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nrem) atomicAdd(dst + (size_t)i * HK, v[i] * g.scale);
           }
         }
+        if (g.timing && k == 0 && n < 60) g.timing[TSLOTS * blockIdx.x + 8 + 8 * n + 6] = clock64();
       }
-      if (r == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
   tc_fence_before();
@@ -460,7 +483,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
   if (g.timing && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-    g.timing[3 * blockIdx.x + 1] = (long long)gt;
+    g.timing[TSLOTS * blockIdx.x + 1] = (long long)gt; g.timing[TSLOTS * blockIdx.x + 4] = clock64();
   }
   if (warp == WARP_MMA) {
     tc_fence_after();
@@ -507,16 +530,15 @@ int ntf_out_train_tc2(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a
     NTF_COUNT_LAUNCH; to_half_kernel2<<<(unsigned)((na + 255) / 256 < (size_t)blocks_h ? (na + 255) / 256 : blocks_h), 256, 0, st>>>(a->A, na, A16);
     NTF_LAUNCH_CHECK();
   }
-  CUtensorMap mw, mh, mda;
+  CUtensorMap mw, mh;
   int rc;
   if ((rc = make_map(ctx, &mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, W16, (uint64_t)a->E, HK, TE, 64))) return rc;
   if ((rc = make_map(ctx, &mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)a->B, HK, TB, 64))) return rc;
-  if ((rc = make_map(ctx, &mda, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, train ? (const void*)a->dA : (const void*)a->W, (uint64_t)(train ? a->B : a->E), HK, TB, 32))) return rc;
   if (train) NTF_CUDA(cudaMemsetAsync(a->dA, 0, (size_t)a->B * a->h * sizeof(float), st));
   Tc2Args g{};
   g.bias = a->b; g.special_t = const_cast<uint32_t*>(a->special_t); g.member_t = const_cast<uint32_t*>(a->member_t); g.Epad = cdiv(a->E, TE) * TE;
   g.B = a->B; g.E = a->E; g.tpw = a->tpw; g.tnw = a->tnw; g.scale = a->loss_scale;
-  g.dW = a->dW; g.db = a->db; g.loss_part = loss_part;
+  g.dW = a->dW; g.db = a->db; g.dA = a->dA; g.loss_part = loss_part;
   g.nct = cdiv(a->E, TE); g.nbt = cdiv(a->B, TB);
   const char* dbg = getenv("NTF_TC_ZDBG");
   g.Zdbg = dbg ? (float*)(uintptr_t)strtoull(dbg, nullptr, 0) : nullptr;
@@ -534,7 +556,7 @@ int ntf_out_train_tc2(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a
   NTF_REQUIRE(grid <= 1024, NTF_ERR_UNSUPPORTED, "out_train(tf32): %d CTAs", grid);
   if (train && !(g.split == 1)) { NTF_COUNT_LAUNCH; zero_cut_tiles_kernel<<<grid, 256, 0, st>>>(g); NTF_LAUNCH_CHECK(); }
   NTF_CUDA(cudaFuncSetAttribute(out_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  NTF_COUNT_LAUNCH; out_tc2_kernel<<<grid, NT, SMEM_BYTES, st>>>(mw, mh, mda, g);
+  NTF_COUNT_LAUNCH; out_tc2_kernel<<<grid, NT, SMEM_BYTES, st>>>(mw, mh, g);
   NTF_LAUNCH_CHECK();
   return ntf_loss_reduce_impl(st, loss_part, grid, a->loss_scale, a->loss_out);
 }

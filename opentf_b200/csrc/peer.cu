@@ -166,6 +166,54 @@ extern "C" int ntf_peer_exchange_adam(ntf_ctx* ctx, void* stream, const ntf_peer
   return ntf_peer_exchange_adam_impl(ctx, as_stream(stream), peers, adam_m, adam_v, offset, n, lr, beta1, beta2, eps, step, ctx ? ctx->dyn_override : nullptr, channel);
 }
 
+// ---- expert-sharded output layer (BASELINE configs[3]): the one exchange of a step is dA = sum over shards of dz_shard . W_shard,
+// [B, h] fp32 (512 KB at B = 1000): latency-bound, so it is ONE pass over peer memory between two flag barriers instead of a collective
+// call between two halves of the step.  Every rank's partial sits in a peer-visible block (ntf_peers::grads[r]); every rank reads all of
+// them (16-byte loads over NVLink) and adds them in RANK ORDER into its own private result -- the same sum, bit for bit, on every rank,
+// so the replicated hidden layers stay identical without exchanging their gradients.
+namespace {
+template <int G>
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(ntf_peers pr, size_t n4, float4* __restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v[G];
+#pragma unroll
+    for (int r = 0; r < G; ++r) v[r] = ld_peer(reinterpret_cast<const float4*>(pr.grads[r]) + i);
+    float4 s = v[0];
+#pragma unroll
+    for (int r = 1; r < G; ++r) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+    dst[i] = s;
+  }
+}
+}  // namespace
+
+int ntf_peer_allreduce_impl(ntf_ctx* ctx, cudaStream_t st, const ntf_peers* pr, size_t n, float* dst, int channel) {
+  NTF_REQUIRE(ctx && pr && dst && (channel == 0 || channel == 1), NTF_ERR_BAD_ARG, "peer_allreduce: null pointer / channel");
+  NTF_REQUIRE(pr->world >= 1 && pr->world <= NTF_MAX_PEERS && pr->rank >= 0 && pr->rank < pr->world, NTF_ERR_BAD_ARG, "peer_allreduce: rank %d of %d", pr->rank, pr->world);
+  NTF_REQUIRE((n % 4) == 0 && ((uintptr_t)dst % 16) == 0, NTF_ERR_BAD_ARG, "peer_allreduce: n must be a multiple of 4 floats, dst 16-byte aligned");
+  for (int r = 0; r < pr->world; ++r)
+    NTF_REQUIRE(pr->grads[r] && pr->flags[r] && ((uintptr_t)pr->grads[r] % 16) == 0, NTF_ERR_BAD_ARG, "peer_allreduce: block of rank %d missing or misaligned", r);
+  NTF_REQUIRE(dst != pr->grads[pr->rank], NTF_ERR_BAD_ARG, "peer_allreduce: the result must not alias the exchange block (peers are still reading it)");
+  if (n == 0) return NTF_OK;
+  NTF_COUNT_LAUNCH; peer_barrier_kernel<<<1, 32, 0, st>>>(*pr, 2 * channel);  // every rank's partial is complete
+  NTF_LAUNCH_CHECK();
+  const size_t n4 = n / 4;
+  const int blocks = (int)((n4 + 255) / 256 < (size_t)ctx->sm_count * 2 ? (n4 + 255) / 256 : (size_t)ctx->sm_count * 2);
+  NTF_COUNT_LAUNCH;
+  switch (pr->world) {
+#define CASE(G) case G: peer_allreduce_kernel<G><<<blocks, 256, 0, st>>>(*pr, n4, reinterpret_cast<float4*>(dst)); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+  }
+  NTF_LAUNCH_CHECK();
+  NTF_COUNT_LAUNCH; peer_barrier_kernel<<<1, 32, 0, st>>>(*pr, 2 * channel + 1);  // everybody has read every block: it may be rewritten
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
+
+extern "C" int ntf_peer_allreduce(ntf_ctx* ctx, void* stream, const ntf_peers* peers, size_t n, float* dst, int channel) {
+  return ntf_peer_allreduce_impl(ctx, as_stream(stream), peers, n, dst, channel);
+}
+
 // ---- peer-visible memory: plain cudaMalloc blocks + CUDA IPC handles (one process per GPU) -------------------------------------
 extern "C" int ntf_peer_alloc(ntf_ctx* ctx, size_t bytes, void** out) {
   NTF_REQUIRE(ctx && out && bytes > 0, NTF_ERR_BAD_ARG, "peer_alloc: bad argument");

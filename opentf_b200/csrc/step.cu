@@ -16,7 +16,7 @@ int ntf_neg_sample_impl(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed, uint
                         const int32_t* m_indices, int E, int ns, const uint32_t* cdf, const int32_t* pool_indptr, int pool_rows,
                         int32_t* neg, const ntf_dyn* dyn);
 int ntf_adam_step_impl(ntf_ctx* ctx, cudaStream_t st, float* p, const float* g, float* m, float* v, size_t n, double lr, double beta1,
-                       double beta2, double eps, int64_t step, const ntf_dyn* dyn);
+                       double beta2, double eps, int64_t step, const ntf_dyn* dyn, void* shadow, size_t sh_off, size_t sh_n);
 int ntf_csr_bag_fwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices, const float* W0T,
                          const float* b0, int S, int h, float* A, void* A16);
 int ntf_csr_bag_bwd_fill_impl(ntf_ctx* ctx, cudaStream_t st, int B, const int32_t* indptr, const int32_t* indices, const int32_t* ent_row,
@@ -27,6 +27,8 @@ int ntf_csr_bag_bwd_reduce_impl(ntf_ctx* ctx, cudaStream_t st, int B, const int3
 
 int ntf_peer_exchange_adam_impl(ntf_ctx* ctx, cudaStream_t st, const ntf_peers* pr, float* adam_m, float* adam_v, size_t off, size_t n, double lr,
                                 double beta1, double beta2, double eps, int64_t step, const ntf_dyn* dyn, int channel);
+
+int ntf_peer_allreduce_impl(ntf_ctx* ctx, cudaStream_t st, const ntf_peers* pr, size_t n, float* dst, int channel);
 
 static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 
@@ -100,11 +102,13 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     else STEP(ntf_csr_bag_fwd_impl(ctx, stream, B, a->s_indptr, a->s_indices, a->W[0], a->b[0], a->S, h[0], a->act[0], A16));
     for (int i = 1; i < Lo; ++i) STEP(ntf_dense_fwd(ctx, stream, a->act[i - 1], a->W[i], a->b[i], B, h[i - 1], h[i], 1, a->act[i]));
     // ---- output layer: forward + weighted BCE (+ backward): fnn.py:32-46,135,137 ----
-    o.A = a->act[Lo - 1]; o.W = a->W[Lo]; o.b = a->b[Lo]; o.A16 = A16;
+    o.A = a->act[Lo - 1]; o.W = a->W[Lo]; o.b = a->b[Lo]; o.A16 = A16; o.W16 = a->W16;
     o.m_indptr = a->m_indptr; o.m_indices = a->m_indices;
     o.B = B; o.h = h[Lo - 1]; o.E = a->E; o.e_lo = a->e_lo;
     o.tpw = a->tpw; o.tnw = a->tnw; o.loss_scale = a->loss_scale; o.loss_out = a->loss_out;
-    if (a->train) { o.dW = a->gW[Lo]; o.db = a->gb[Lo]; o.dA = a->dact[Lo - 1]; }
+    // expert-sharded layer with a peer table: this shard's dA goes to its peer-visible exchange block, the sum over shards into dact below
+    const bool shard_x = a->peers != nullptr && a->E < Etot;
+    if (a->train) { o.dW = a->gW[Lo]; o.db = a->gb[Lo]; o.dA = shard_x ? a->peers->grads[a->peers->rank] : a->dact[Lo - 1]; }
     NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
     // (inside a stream capture the pair becomes two external event-record nodes, re-recorded by every replay of the graph)
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -114,11 +118,20 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     STEP(ntf_out_train(ctx, stream, a->precision, &o, ws_main, ws_main_bytes));
     if (a->prof_ev[1]) NTF_CUDA(cudaEventRecordWithFlags((cudaEvent_t)a->prof_ev[1], st, evf));
     if (!tc) STEP(ntf_special_bits(ctx, stream, 0, B, a->m_indptr, a->m_indices, neg, ns, a->E, a->e_lo, a->special, a->pitch_words));
+    if (shard_x && a->train) {
+      NTF_REQUIRE((((size_t)B * h[Lo - 1]) % 4) == 0, NTF_ERR_UNSUPPORTED, "fnn_step: sharded exchange needs B*h a multiple of 4");
+      STEP(ntf_peer_allreduce_impl(ctx, st, a->peers, (size_t)B * h[Lo - 1], a->dact[Lo - 1], 0));
+    }
   }
   if (!bwd_here) return NTF_OK;
   // ---- optimiser, part 1: the output layer's segment of the arena (its gradients are final once ntf_out_train has run) is
   // stepped on a side stream NEXT TO the backward pass through the hidden layers (a chain of small launches that leaves most
   // of the machine idle); the rest of the arena follows on the main stream.  Only when this call ran the output layer too.
+  // the fp16 image of the last layer's weight (a->W16, read by the tensor-core output layer) follows the parameters: the Adam launch that
+  // steps that weight rewrites it; after a peer-memory exchange (other ranks stepped most of it) a local conversion pass does
+  const size_t w_off = (size_t)(a->W[Lo] - a->params), w_n = (size_t)a->E * h[Lo - 1];
+  const bool shadow = a->W16 != nullptr && a->run_adam && a->W[Lo] >= a->params && w_off + w_n <= a->n_params && (w_off % 4) == 0 && (w_n % 4) == 0;
+  NTF_REQUIRE(a->W16 == nullptr || !a->run_adam || shadow, NTF_ERR_BAD_ARG, "fnn_step: W16 given but the last layer's weight is not a 4-float aligned part of the arena");
   size_t opt_split = a->n_params;  // floats [opt_split, n_params) belong to the last layer (arena order: layer by layer)
   if (a->run_adam && phase == 3 && getenv("NTF_ADAM_SPLIT") == nullptr) {
     const float* lo = a->gW[Lo] < a->gb[Lo] ? a->gW[Lo] : a->gb[Lo];
@@ -130,7 +143,8 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
   // data-parallel ranks: sum the gradients over the ranks before they are stepped (ncclAllReduce, in place, fp32 sum) -- on the
   // communication stream, so that the exchange of the output layer's segment hides behind the hidden layers' backward pass and
   // its Adam step behind the exchange of the rest
-  const bool peers = a->peers != nullptr;  // exchange + Adam fused over peer memory (peer.cu); takes precedence over comm
+  const bool peers = a->peers != nullptr && !(a->E < Etot);  // exchange + Adam fused over peer memory (peer.cu); takes precedence over comm
+                                                             // (an expert-sharded layer's table is the dA exchange above: its Adam is local)
   NTF_REQUIRE(!peers || (a->run_adam && phase == 3 && a->peers->params[a->peers->rank] == a->params && a->peers->grads[a->peers->rank] == a->grads),
               NTF_ERR_BAD_ARG, "fnn_step: peers needs run_adam, phase 3 and this rank's own arenas in the table");
   const bool dp = a->comm != nullptr && !peers;
@@ -150,11 +164,15 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
       NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_ar[0], 0));
     } else
     NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork_opt, 0));
-    if (peers) STEP(ntf_peer_exchange_adam_impl(ctx, ctx->side[0], a->peers, a->adam_m, a->adam_v, opt_split, a->n_params - opt_split, a->lr, a->beta1,
-                                                a->beta2, a->eps, a->adam_t, a->dyn, 1));
-    else
+    const bool sh_here = shadow && w_off >= opt_split;
+    if (peers) {
+      STEP(ntf_peer_exchange_adam_impl(ctx, ctx->side[0], a->peers, a->adam_m, a->adam_v, opt_split, a->n_params - opt_split, a->lr, a->beta1,
+                                       a->beta2, a->eps, a->adam_t, a->dyn, 1));
+      if (sh_here) STEP(ntf_to_half(ctx, (void*)ctx->side[0], a->W[Lo], w_n, const_cast<void*>(a->W16)));
+    } else
     STEP(ntf_adam_step_impl(ctx, ctx->side[0], a->params + opt_split, a->grads + opt_split, a->adam_m + opt_split, a->adam_v + opt_split,
-                            a->n_params - opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn));
+                            a->n_params - opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn, sh_here ? const_cast<void*>(a->W16) : nullptr,
+                            sh_here ? w_off - opt_split : 0, sh_here ? w_n : 0));
     NTF_CUDA(cudaEventRecord(ctx->ev_join_opt, ctx->side[0]));
   }
   // ---- backward through the hidden layers ----
@@ -179,9 +197,13 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_ar[1], 0));
   }
 #undef ALLREDUCE
-  if (peers) STEP(ntf_peer_exchange_adam_impl(ctx, st, a->peers, a->adam_m, a->adam_v, 0, opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn, 0));
-  else
-  if (a->run_adam) STEP(ntf_adam_step_impl(ctx, st, a->params, a->grads, a->adam_m, a->adam_v, opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn));
+  const bool sh_main = shadow && w_off < opt_split;  // (only when the arena is stepped in one piece)
+  if (peers) {
+    STEP(ntf_peer_exchange_adam_impl(ctx, st, a->peers, a->adam_m, a->adam_v, 0, opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn, 0));
+    if (sh_main) STEP(ntf_to_half(ctx, stream, a->W[Lo], w_n, const_cast<void*>(a->W16)));
+  } else if (a->run_adam)
+    STEP(ntf_adam_step_impl(ctx, st, a->params, a->grads, a->adam_m, a->adam_v, opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn,
+                            sh_main ? const_cast<void*>(a->W16) : nullptr, sh_main ? w_off : 0, sh_main ? w_n : 0));
   if (opt_split < a->n_params) NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_join_opt, 0));
 #undef STEP
   return NTF_OK;

@@ -52,6 +52,14 @@ __device__ __forceinline__ void mma_f16(uint32_t d, uint64_t a, uint64_t b, uint
   asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
                ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+// one lane of the (converged) warp: the same one for the same member mask, so the MMAs and the commits that track them come from one thread.
+// Issuing tcgen05.mma under elect.sync in warp-uniform control flow keeps its descriptors in uniform registers; under `if (lane == 0)`
+// ptxas wraps every MMA in an ELECT / BRA.U.ANY loop and the issue sequence gets ~3x longer.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets TMEM lane (lane_base + t), columns [col, col+32)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];

@@ -261,7 +261,7 @@ class Engine:
             v = self.view(name)
             if tuple(t.shape) != tuple(v.shape): raise ValueError(f'{name}: shape {tuple(t.shape)} does not fit {tuple(v.shape)}')
             v.copy_(t.contiguous())
-        self._load_ver = getattr(self, '_load_ver', 0) + 1
+        self._w16_dirty = True
 
     def state_dict(self, gather=True):
         """torch-layout state dict.  Expert-sharded: the last layer's shards are all-gathered (a collective: every rank calls it);
@@ -392,10 +392,14 @@ class Engine:
         a.train, a.run_adam = int(bool(train)), int(bool(train) and (not dp or in_step))
         a.comm, a.allreduce = (self.comm.ptr, self.comm.allreduce_addr) if (in_step and self.peers is None) else (None, None)
         a.peers = C.addressof(self.peers) if (in_step and self.peers is not None) else None
+        sp_tab = getattr(self, 'shard_peers', None)
+        if sharded and train and sp_tab is not None: a.peers = C.addressof(sp_tab)  # the dA exchange runs inside the step (ntf_peer_allreduce)
         if train:
             a.lr, a.adam_t = float(lr), self.adam_t + 1
         pe = getattr(self, 'prof_events', None)  # (bench.py) a recorded-once torch event pair around the output-layer call
         a.prof_ev[0], a.prof_ev[1] = (pe[0].cuda_event, pe[1].cuda_event) if pe else (None, None)
+        # tensor-core output layer: the fp16 weight image (made here if stale; the step's own Adam launch keeps it current afterwards)
+        a.W16 = self.w16().data_ptr() if self.precision == _lib.NTF_TF32 else None
         a.dyn = None
         graphed = self.use_graphs and neg_host is None and pe is None
         if graphed:
@@ -405,7 +409,9 @@ class Engine:
         if graphed:
             a.dyn = self.dyn.data_ptr()
             ops.dyn_update(self.dev_index, self.dyn, self.global_step, float(lr) if train else 0.0, 0.9, 0.999, 1e-8, self.adam_t + 1)
-        if sharded and train:
+        if sharded and train and sp_tab is not None:
+            self._run(a, 3, key if graphed else None)  # one call: the shards' dA are summed over peer memory between the two halves
+        elif sharded and train:
             # every rank runs the same batch on its expert range; the only exchange is dA = sum over shards of dz W  [B,h]
             self._run(a, 1, key if graphed else None)
             self.allreduce(self.dact[-1][:B])
@@ -473,12 +479,46 @@ class Engine:
         self.peers = t
         return t
 
+    def attach_shard_peers(self, local=None):
+        """expert-sharded output layer: put this rank's dA partial [Bmax, h_last] into an IPC-shareable block, exchange the handles and hand
+        the library the table (ntf_peers with grads[r] = rank r's block): ntf_fnn_step then sums the shards' dA itself (ntf_peer_allreduce,
+        one pass over peer memory between two flag barriers) and a sharded step becomes ONE call / one CUDA graph instead of two halves
+        around a torch.distributed.all_reduce.  `local`: a list with this engine alone = a table of one rank (single-GPU plumbing tests)."""
+        d = self.dev_index
+        if getattr(self, '_x_blocks', None) is None:
+            xb, px = ops.peer_alloc(d, self.Bmax * self.hidden[-1], torch.float32)
+            fl, pf = ops.peer_alloc(d, 64, torch.int32)
+            self._x_buf, self._peer_flags, self._x_blocks = xb, fl, (px, pf)
+        torch.cuda.synchronize(self.device)
+        t = _lib.Peers()
+        if local is not None:
+            assert local == [self]
+            t.rank, t.world = 0, 1
+            t.grads[0], t.params[0], t.flags[0] = self._x_blocks[0], self._x_blocks[0], self._x_blocks[1]
+        else:
+            handles = tuple(ops.peer_export(d, p) for p in self._x_blocks)
+            got = [None] * self.shard[1]
+            torch.distributed.all_gather_object(got, handles)
+            t.rank, t.world = self.shard
+            self._imported = []
+            for r, hs in enumerate(got):
+                if r == self.shard[0]: ptrs = self._x_blocks
+                else:
+                    ptrs = tuple(ops.peer_import(d, h) for h in hs)
+                    self._imported += list(ptrs)
+                t.grads[r], t.params[r], t.flags[r] = ptrs[0], ptrs[0], ptrs[1]
+            torch.distributed.barrier()
+        self.shard_peers = t
+        self._graphs.clear()
+        return t
+
     def peer_error(self):
         """non-zero if a barrier of the peer exchange gave up waiting (a rank died or fell out of step)"""
-        return 0 if self.peers is None else int(self._peer_flags[36].item())
+        return 0 if (self.peers is None and getattr(self, 'shard_peers', None) is None) else int(self._peer_flags[36].item())
 
     def _peer_exchange(self, lr):
         """the eager counterpart of what ntf_fnn_step does with `peers`: output layer's segment on channel 1, the rest on channel 0"""
+        self._w16_dirty = True
         split = self._arena_split()
         t = self.adam_t + 1
         if split is not None:
@@ -530,6 +570,7 @@ class Engine:
             ar(self.grads[split:])
             ar(self.grads[:split])
         self.adam_t += 1
+        self._w16_dirty = True
         ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, self.n_params, lr, 0.9, 0.999, 1e-8, self.adam_t)
 
     def _dp_overlapped(self, a, key, lr):
@@ -554,6 +595,7 @@ class Engine:
         self.allreduce(self.grads[:split])
         ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, split, lr, 0.9, 0.999, 1e-8, t)
         main.wait_event(self._dp_ev[1])
+        self._w16_dirty = True
         self.adam_t = t
         self.global_step += 1
 
@@ -593,6 +635,7 @@ class Engine:
         if self.world > 1:
             self.allreduce(self.grads)  # sum over ranks; every rank scaled its loss by 1/B_global
         self.adam_t += 1
+        self._w16_dirty = True
         ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, self.n_params, lr, 0.9, 0.999, 1e-8, self.adam_t)
 
     # ------------------------------------------------------------------ Bnn (Flipout): bnn.py:19-25, fnn.py:126-151 with is_bayesian
@@ -788,14 +831,16 @@ class Engine:
         return out
 
     def w16(self):
-        """fp16 image of the output layer's weight for the fused top-K kernel, refreshed when the parameters changed since it was made"""
-        ver = (self.adam_t, getattr(self, '_load_ver', 0), self.params.data_ptr())
-        if getattr(self, '_w16_ver', None) != ver:
+        """fp16 image [E,h_last] of the output layer's weight: what the tensor-core kernels TMA-load (training: out_tc2.cu, test time:
+        infer_topk.cu).  ntf_fnn_step keeps it current while it steps the parameters itself; every other writer of the arena
+        (load_state_dict, eager optimiser steps) marks it dirty and it is remade here on the next use."""
+        if getattr(self, '_w16', None) is None:
             W = self.view(f'layers.{self.L - 1}.weight')
-            if getattr(self, '_w16', None) is None or self._w16.numel() != W.numel():
-                self._w16 = torch.empty(W.numel(), dtype=torch.float16, device=self.device)
+            self._w16, self._w16_dirty = torch.empty(W.numel(), dtype=torch.float16, device=self.device), True
+        if self._w16_dirty:
+            W = self.view(f'layers.{self.L - 1}.weight')
             ops.to_half(W, W.numel(), self._w16)
-            self._w16_ver = ver
+            self._w16_dirty = False
         return self._w16
 
     def topk(self, sp, b0, B, K, scores_buf, vals, idx):

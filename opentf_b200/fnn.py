@@ -125,6 +125,7 @@ class Fnn(Ntf):
             #   'peer'  (default) reduce-scatter + Adam + all-gather as one pass over peer memory inside the step (csrc/peer.cu)
             #   'nccl'  ncclAllReduce on the library's own communicator inside the step (Fnn only)
             #   'torch' torch.distributed.all_reduce between the two halves of a step
+            if shard is not None and self._c('exchange', os.environ.get('NTF_DP_EXCHANGE', 'peer')) == 'peer': self.engine.attach_shard_peers()
             if world > 1 and shard is None:
                 mode = self._c('exchange', os.environ.get('NTF_DP_EXCHANGE', 'peer'))
                 if mode == 'peer': self.engine.attach_peers()

@@ -110,3 +110,31 @@ def test_special_planes_of_a_shard_cover_its_expert_range_only():
     words = plane.cpu().numpy().view(np.uint32)
     got = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(B, -1)[:, :El].astype(bool)
     assert (got == ref[:, e_lo:e_lo + El]).all()
+
+
+@pytest.mark.parametrize('precision,graphs', [('fp32', False), ('tf32', True)])
+def test_sharded_step_in_one_call_equals_the_two_phase_step(precision, graphs, monkeypatch):
+    """ntf_fnn_step with a peer table on an expert shard: the dA exchange (ntf_peer_allreduce) runs inside the call.  One GPU: a table of ONE
+    rank (the sum over shards is this shard's own partial), against the two-phase step with an identity all-reduce -- same arithmetic, so the
+    parameters must agree bit for bit in fp32 mode; this checks the plumbing (exchange block, flags, the phase-3 sequence, graph capture)."""
+    monkeypatch.setenv('NTF_GRAPHS', '1' if graphs else '0')
+    rng = np.random.default_rng(17)
+    torch.manual_seed(17)
+    B, S, E, hidden = 128, 40, 1000, [128]
+    skill, member = rand_csr(rng, 4 * B, S, 1, 5), rand_csr(rng, 4 * B, E, 1, 4)
+    layers = O.init_params(S, hidden, E)
+    sd = {f'layers.{i}.{n}': t for i, (W, b) in enumerate(layers) for n, t in (('weight', W), ('bias', b))}
+    res = []
+    for one_call in (False, True):
+        eng = build(S, hidden, E, B, skill, member, sd, (1, 2), precision)
+        if one_call: eng.attach_shard_peers(local=[eng])
+        else: eng.allreduce = lambda t: t
+        sp = eng.split(np.arange(4 * B))
+        for e in range(3):
+            for bi in range(4): eng.step(sp, bi * B, B, True, lr=1e-2, loss_slot=bi)
+        torch.cuda.synchronize()
+        assert eng.peer_error() == 0
+        res.append((eng.loss_buf[:4].cpu().clone(), eng.params.cpu().clone()))
+    (l0, p0), (l1, p1) = res
+    if precision == 'fp32': assert torch.equal(l0, l1) and torch.equal(p0, p1)
+    else: assert torch.allclose(l0, l1, rtol=1e-4) and (p0 - p1).norm() <= 1e-3 * p0.norm()  # dA is summed by L2 in arrival order
