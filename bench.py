@@ -38,6 +38,9 @@ def parse():
     p.add_argument('--batch', type=int, default=1000, help='teams per GPU per step (reference default b=1000)')
     p.add_argument('--precision', default='tf32', choices=['tf32', 'fp32'])
     p.add_argument('--nsd', default='unigram_b')
+    p.add_argument('--parallel', default='dp', choices=['dp', 'shard'],
+                   help="multi-GPU mode: 'dp' data-parallel teams (weak scaling, --batch teams per GPU); 'shard' output layer column-sharded by expert "
+                        "(BASELINE configs[3]: every rank runs the same --batch teams on its expert range, strong scaling)")
     p.add_argument('--cpu-baseline-seconds', type=float, default=15.0)
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--infer-k', type=int, default=10)
@@ -212,8 +215,12 @@ def run_reference(args):
 
 def config_of(args, tv):
     N, S = tv['skill'].shape; E = tv['member'].shape[1]
-    return {'workload': f'{args.workload}-shaped synthetic teamsvecs (BASELINE configs[1]): N={N} S={S} E={E}, Fnn h=[128], nsd={args.nsd}, ns=5, tpw=10, tnw=1',
-            'batch_per_gpu': args.batch, 'global_batch': args.batch * args.gpus, 'parallelism': f'dp{args.gpus}', 'precision': args.precision,
+    cfgno = {'dblp': 1, 'imdb': 2, 'uspt': 3}.get(args.workload, 1)
+    shard = getattr(args, 'parallel', 'dp') == 'shard'
+    return {'workload': f'{args.workload}-shaped synthetic teamsvecs (BASELINE configs[{cfgno}]): N={N} S={S} E={E}, Fnn h=[128], nsd={args.nsd}, ns=5, tpw=10, tnw=1',
+            'batch_per_gpu': args.batch, 'global_batch': args.batch * (1 if shard else args.gpus),
+            'parallelism': (f'shard{args.gpus} (output layer column-sharded by expert, {-(-E // args.gpus)} experts per GPU; layer 0 replicated)' if shard else f'dp{args.gpus}'),
+            'precision': args.precision,
             'l2_policy': 'no flush: one step touches params+grads+Adam state (>140 MB) and the [B,E] work set, larger than the 126 MB L2'}
 
 
@@ -240,10 +247,13 @@ def run_ours(args):
     tv, splits = workload(args.workload)
     N, S = tv['skill'].shape; E = tv['member'].shape[1]
     b, G = args.batch, world
-    eng = Engine(S, [128], E, dev, precision=args.precision, tpw=10, tnw=1, nsd=args.nsd, ns=5, seed=0, max_batch=b)
+    shard = args.parallel == 'shard'
+    eng = Engine(S, [128], E, dev, precision=args.precision, tpw=10, tnw=1, nsd=args.nsd, ns=5, seed=0, max_batch=b, shard=(rank, world) if shard else None)
     eng.world, eng.rank = world, rank
     xmode = os.environ.get('NTF_DP_EXCHANGE', 'peer')  # how data-parallel ranks exchange gradients (opentf_b200/fnn.py: Fnn.init)
-    if world > 1 and xmode == 'peer': eng.attach_peers()
+    if shard:
+        if world > 1 and xmode == 'peer': eng.attach_shard_peers()  # the dA exchange inside the step, over peer memory
+    elif world > 1 and xmode == 'peer': eng.attach_peers()
     elif world > 1 and xmode == 'nccl': eng.attach_comm()
     eng.stage(tv['skill'], tv['member'])
     torch.manual_seed(0)
@@ -252,14 +262,14 @@ def run_ours(args):
     eng.load_state_dict({f'layers.{i}.{n}': getattr(m, n).detach() for i, m in enumerate(lin) for n in ('weight', 'bias')})
     train_rows = np.asarray(splits['folds'][0]['train'])
     sp = eng.split(train_rows[np.random.default_rng(0).permutation(len(train_rows))])
-    gB = b * G
-    nb = sp.n // gB
+    gB = b if shard else b * G  # sharded layer: every rank runs the SAME batch on its expert range
+    nb = min(sp.n // gB, 64)
     assert nb >= 1, 'workload smaller than one global batch'
     precision_used = 'tf32' if eng.precision == _lib.NTF_TF32 else 'fp32'
 
     def device_step(i):
         g0 = (i % nb) * gB
-        eng.step(sp, g0 + rank * b, b, True, lr=1e-3, loss_slot=i % nb, loss_scale=1.0 / gB, gbatch=(g0, gB))
+        eng.step(sp, g0 + (0 if shard else rank * b), b, True, lr=1e-3, loss_slot=i % nb, loss_scale=1.0 / gB, gbatch=(g0, gB))
 
     def sync():
         torch.cuda.synchronize()
@@ -315,7 +325,7 @@ def run_ours(args):
     k_ms = float(np.mean([a.elapsed_time(c) for a, c in used]))
 
     # ---- end to end through the streaming entry point: host batches in, loss out ----
-    host = HostBatches(tv, train_rows, b, rank, G)
+    host = HostBatches(tv, train_rows, b, 0 if shard else rank, 1 if shard else G)
     host.prepare(list(range(min(3, args.warmup))) + [100 + i for i in range(args.steps)])  # pinned host inputs exist before timing
     for i in range(min(3, args.warmup)): host.step(eng, i)
     sync()
@@ -345,7 +355,7 @@ def run_ours(args):
     for r in range(reps): eng.topk(test_sp, (r * ib) % max(1, test_sp.n - ib + 1), ib, args.infer_k, scores, vals, idx)
     i1.record()
     sync()
-    infer_value = reps * ib * G / (i0.elapsed_time(i1) * 1e-3)
+    infer_value = reps * ib * (1 if shard else G) / (i0.elapsed_time(i1) * 1e-3)
 
     extras = {}
     # secondary legs: on one GPU by default; under torchrun only when asked for (--extras) -- the headline line of a scaling run should not
@@ -365,7 +375,7 @@ def run_ours(args):
         if world > 1: dist.destroy_process_group()
         return
     pk = peaks()
-    flops = 6.0 * 128 * E * b  # K3 flops/team (Fnn train) = 6*h_L*E, per launch of b teams
+    flops = 6.0 * 128 * eng.E * b  # K3 flops/team (Fnn train) = 6*h_L*E, per launch of b teams (sharded: this rank's experts)
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'out_tc_traffic.json')
     if precision_used == 'tf32' and args.workload == 'dblp' and b == 1000 and os.path.exists(tpath):
@@ -379,7 +389,7 @@ def run_ours(args):
             'note': 'h=128: per logit 768 tensor flops vs ~14 issue slots + 2 MUFU ops + 24 B of shared-memory traffic; MUFU / smem bandwidth bind before the tensor pipe (DESIGN.md 4.1)'}
     roof['frac'] = roof['achieved'] / roof['peak']
     out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': G, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
-           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if precision_used == 'fp32' else 'f16 operands (10-bit mantissa, TF32-class), f32 accumulate',
+           'higher_is_better': True, 'scaling': 'strong' if shard else 'weak', 'vs_baseline': None, 'dtype': 'f32' if precision_used == 'fp32' else 'f16 operands (10-bit mantissa, TF32-class), f32 accumulate',
            'data': 'synthetic', 'config': config_of(args, tv), 'clocks': clk.summary(),
            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': host.h2d_bytes, 'd2h_bytes_per_step': 4,
                    'api': 'Engine.step_host: pinned batch CSR block -> one H2D copy -> ntf_fnn_step (replayed as a CUDA graph) -> loss.item()'},

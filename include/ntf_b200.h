@@ -193,6 +193,11 @@ typedef struct {
   const void* A16;             /* NTF_TF32, optional: A as fp16 [B,h] already (the producing kernel wrote it); NULL: converted here */
   const void* W16;             /* NTF_TF32, optional: fp16 image of W [E,h] kept by the caller (ntf_to_half; the optimiser entry points of ntf_fnn_step
                                   rewrite it); NULL: made per call.  Ignored by the Flipout layer */
+  const int32_t* neg;          /* NTF_TF32 Fnn (persistent kernel, csrc/out_tc2.cu): the sampled negatives [B,ns] (global expert ids, -1 = none) --
+                                  with the member CSR they name the (team, expert) pairs of weight tpw directly; the tensor-core pass treats every
+                                  pair as (target 0, weight tnw) and a sparse correction pass puts these few right.  Given `neg` (or ns == 0 and
+                                  special_t == NULL) the planes are not needed */
+  int ns;
 } ntf_out_train_args;
 /* 1 if NTF_TF32 has a tcgen05 kernel for this shape (else callers use NTF_FP32; ntf_out_train(NTF_TF32) refuses it) */
 int ntf_tc_supported(int B, int h, int E, int flipout);

@@ -51,7 +51,7 @@ extern "C" int ntf_out_train(ntf_ctx* ctx, void* stream, int precision, const nt
     NTF_REQUIRE(ntf_out_tc_supported(a->B, a->h, a->E, flip), NTF_ERR_UNSUPPORTED,
                 "out_train(tf32): shape B=%d h=%d E=%d flipout=%d not supported by the tcgen05 kernel (use NTF_FP32)", a->B, a->h, a->E, (int)flip);
     // Fnn: the persistent kernel (out_tc2.cu); the Flipout layer and NTF_TC_V1=1 (round 1's one-CTA-per-expert-tile kernel, kept for A/B runs): out_tc.cu
-    if (!flip && getenv("NTF_TC_V1") == nullptr) return ntf_out_train_tc2(ctx, as_stream(stream), a, workspace, workspace_bytes);
+    if (!flip && !a->special_t && getenv("NTF_TC_V1") == nullptr) return ntf_out_train_tc2(ctx, as_stream(stream), a, workspace, workspace_bytes);
     return ntf_out_train_tc(ctx, as_stream(stream), a, workspace, workspace_bytes);
   }
   NTF_REQUIRE(precision == NTF_FP32, NTF_ERR_BAD_ARG, "out_train: precision=%d", precision);

@@ -14,6 +14,11 @@
 //   * dA is produced TRANSPOSED (hidden unit on the TMEM lane), so its warps add it into dA[B,128] with coalesced red.global.add from
 //     registers -- no staging buffer, no barriers, no proxy fences -- and the 48 KB of staging go to a third activation stage, which takes
 //     tile n+1's activation load off the critical path of tile n-1's backward products.
+//   * the kernel is purely DENSE: every (team, expert) pair is treated as (target 0, weight tnw).  The few pairs that are not -- a team's
+//     members and its sampled negatives, ~8 per team -- are put right afterwards by out_fix_kernel (one warp per team: logit by a 128-term
+//     dot product of the same fp16 operands, rank-1 corrections of dW / dA / db / loss).  Round 1 fixed them up inside the epilogue from
+//     bit planes; with Zipf-distributed experts that made a few warps (popular experts) several times slower than the rest, and the
+//     slowest warp gates every tile.  No planes, no plane loads, no clearing stores are left in the hot loop.
 // An expert tile whose batch range is cut between two CTAs adds its dW / db partials into rows zeroed beforehand; with at most two
 // contributions per element (0 + a + b) the sums are order-independent, so dW / db are run-to-run deterministic whenever
 // E >= 128 * (number of SMs); dA is still summed by L2 in arrival order.
@@ -36,9 +41,7 @@ constexpr uint32_t OFF_W16 = 0;
 constexpr int AST = 3;                                  // activation stages: tile n+1's load must not wait for tile n-1's backward products
 constexpr uint32_t OFF_A16 = OFF_W16 + W16_BYTES;
 constexpr uint32_t OFF_DZ = OFF_A16 + AST * A16_BYTES;  // 2 stages; at the end of an expert tile: staging of the dW drain (64 KB)
-constexpr uint32_t OFF_PLANE = OFF_DZ + 2 * DZ_BYTES;   // 2 stages x (special | member) planes, 2 KB each
-constexpr uint32_t PLANE_BYTES = TE * 4 * 4;
-constexpr uint32_t OFF_BAR = OFF_PLANE + 4 * PLANE_BYTES;
+constexpr uint32_t OFF_BAR = OFF_DZ + 2 * DZ_BYTES;
 constexpr uint32_t OFF_DBS = OFF_BAR + 512;              // [4][128] fp32 scratch of the db combine
 constexpr uint32_t SMEM_BYTES = OFF_DBS + 4 * TE * 4;
 static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared memory limit");
@@ -46,13 +49,11 @@ static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared memory limit");
 constexpr uint32_t TM_Z = 0, TM_DW = 256, TM_DA = 384, TM_COLS = 512;
 
 enum { BAR_W_FULL = 0, BAR_W_EMPTY = 1, BAR_A_FULL = 2, BAR_A_EMPTY = 5, BAR_Z_FULL = 8, BAR_Z_EMPTY = 10, BAR_DZ_FULL = 12, BAR_DZ_EMPTY = 14,
-       BAR_DA_FULL = 16, BAR_DA_EMPTY = 17, BAR_DW_FULL = 18, BAR_DW_EMPTY = 19, BAR_SP_FULL = 20, BAR_SP_EMPTY = 22, NUM_BARS = 24 };
+       BAR_DA_FULL = 16, BAR_DA_EMPTY = 17, BAR_DW_FULL = 18, BAR_DW_EMPTY = 19, NUM_BARS = 20 };
 
 struct Tc2Args {
   const float* bias;
-  uint32_t* special_t;
-  uint32_t* member_t;
-  int Epad, B, E;
+  int B, E;
   float tpw, tnw, scale;
   float* dW;        // [E,128] or NULL (validation: forward + loss only)
   float* db;
@@ -65,7 +66,7 @@ struct Tc2Args {
 };
 
 constexpr int TSLOTS = 512;  // debug stamps per CTA (Tc2Args::timing)
-constexpr int EPI_WARPS = 16, NT = 736, WARP_DA = 16, WARP_TMA = 20, WARP_MMA = 21, WARP_SP = 22, EPI_THREADS = EPI_WARPS * 32;
+constexpr int EPI_WARPS = 16, NT = 704, WARP_DA = 16, WARP_TMA = 20, WARP_MMA = 21, EPI_THREADS = EPI_WARPS * 32;
 constexpr uint32_t IDESC_FWD = instr_desc(0, 0, 0, TE, TB);
 constexpr uint32_t IDESC_DW = instr_desc(0, 0, 1, TE, HK);
 constexpr uint32_t IDESC_DA = instr_desc(0, 1, 1, TB, HK);
@@ -113,7 +114,6 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
   int L0, L1;
   tile_range(g, blockIdx.x, gridDim.x, &L0, &L1);
   const bool train = g.dW != nullptr;
-  const bool has_sp = g.special_t != nullptr;
   const int nbt = g.nbt;
 
   if (threadIdx.x == 0) {
@@ -124,7 +124,6 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(BAR_Z_FULL + s), 1); mbar_init(bar(BAR_Z_EMPTY + s), EPI_THREADS);
       mbar_init(bar(BAR_DZ_FULL + s), EPI_THREADS); mbar_init(bar(BAR_DZ_EMPTY + s), 1);
-      mbar_init(bar(BAR_SP_FULL + s), 1); mbar_init(bar(BAR_SP_EMPTY + s), EPI_THREADS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -154,17 +153,6 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
         mbar_wait(bar(BAR_A_EMPTY + s), ((n / AST) & 1) ^ 1);
         mbar_expect_tx(bar(BAR_A_FULL + s), A16_BYTES);
         for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A16 + s * A16_BYTES + c * CHUNK, &map_a16, c * 64, t * TB, bar(BAR_A_FULL + s));
-      }
-    }
-  } else if (warp == WARP_SP) {
-    if (lane == 0 && has_sp) {
-      for (int L = L0, n = 0; L < L1; ++L, ++n) {
-        const int e = L / nbt, t = L - e * nbt, s = n & 1;
-        mbar_wait(bar(BAR_SP_EMPTY + s), ((n >> 1) & 1) ^ 1);
-        mbar_expect_tx(bar(BAR_SP_FULL + s), 2 * PLANE_BYTES);
-        const size_t off = ((size_t)t * g.Epad + (size_t)e * TE) * 4;
-        bulk_load(sbase + OFF_PLANE + s * 2 * PLANE_BYTES, g.special_t + off, PLANE_BYTES, bar(BAR_SP_FULL + s));
-        bulk_load(sbase + OFF_PLANE + s * 2 * PLANE_BYTES + PLANE_BYTES, g.member_t + off, PLANE_BYTES, bar(BAR_SP_FULL + s));
       }
     }
   } else if (warp == WARP_MMA) {
@@ -241,7 +229,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
     int j = -1, e0 = 0, e = 0;
     bool e_ok = false, whole = false;
     float bj = 0.f, c_pos = 0.f, c_neg = 0.f, kb1 = 0.f, kb2 = 0.f;
-    float acc_lin = 0.f, acc_lg = 0.f, loss_sp = 0.f, db_acc = 0.f;
+    float acc_lin = 0.f, acc_lg = 0.f, db_acc = 0.f;
     float2 acc_lin2 = make_float2(0.f, 0.f), db_acc2 = make_float2(0.f, 0.f);
     for (int L = L0, n = 0; L < L1; ++L, ++n) {
       const int et = L / nbt, t = L - et * nbt;
@@ -252,27 +240,13 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
         bj = e_ok ? __ldg(g.bias + e) : 0.f;
         c_pos = e_ok ? g.tnw : 0.f; c_neg = e_ok ? g.tnw * NTF_LRELU_SLOPE : 0.f;
         kb1 = -LOG2E * bj; kb2 = -LOG2E * NTF_LRELU_SLOPE * bj;
-        acc_lin = acc_lg = loss_sp = db_acc = 0.f;
+        acc_lin = acc_lg = db_acc = 0.f;
         acc_lin2 = make_float2(0.f, 0.f); db_acc2 = make_float2(0.f, 0.f);
         whole = (t == 0) && (L + nbt <= L1);  // this CTA runs every batch tile of the expert tile: plain stores, no partial sums
       }
       const int s = n & 1;
       const uint32_t ph = (n >> 1) & 1;
       const int n0 = t * TB + cb * 32;
-      uint32_t S = 0, Y = 0;
-      if (has_sp) {
-        const uint32_t* plane = reinterpret_cast<const uint32_t*>(sgen + OFF_PLANE + s * 2 * PLANE_BYTES);
-        mbar_wait(bar(BAR_SP_FULL + s), ph);
-        S = plane[jl * 4 + cb];
-        Y = plane[TE * 4 + jl * 4 + cb];
-        if (S) {  // consumed: clear the words in HBM so that the caller's planes are clean for the next batch
-          const size_t wofs = ((size_t)t * g.Epad + e) * 4 + cb;
-          g.special_t[wofs] = 0u;
-          if (Y) g.member_t[wofs] = 0u;
-        }
-        mbar_arrive(bar(BAR_SP_EMPTY + s));  // (after the branch consumed S and Y: the loads have completed, not merely issued)
-        if (!e_ok) S = 0;
-      }
       mbar_wait(bar(BAR_Z_FULL + s), ph);
       if (g.timing && threadIdx.x == 0 && n < 60) g.timing[TSLOTS * blockIdx.x + 8 + 8 * n] = clock64();
       tc_fence_after();
@@ -290,7 +264,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
       const uint32_t dzrow = sbase + OFF_DZ + s * DZ_BYTES + (cb >> 1) * CHUNK + jl * 128;
       const int unit0 = 4 * (cb & 1);
       const uint32_t kx = (uint32_t)(unit0 ^ (jl & 7));
-      // dense pass (out_tc.cu has the derivation): every element as (target 0, weight tnw); t = -log2e*lrelu(z+b) by two FFMA2 + FMNMX,
+      // the pass is dense (out_tc.cu has the derivation): every element as (target 0, weight tnw); t = -log2e*lrelu(z+b) by two FFMA2 + FMNMX,
       // e = 2^t, one reciprocal and one logarithm per 8 elements through the product of the 8 denominators
       auto dense8 = [&](int u, auto masked) {
         const float2 k1 = make_float2(-LOG2E, -LOG2E), k2 = make_float2(-LOG2E * NTF_LRELU_SLOPE, -LOG2E * NTF_LRELU_SLOPE);
@@ -342,42 +316,6 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
 #pragma unroll
         for (int u = 0; u < 4; ++u) dense8(u, std::true_type{});
       }
-      // sparse fix-up: members / sampled negatives (weight tpw, member target), warp-cooperative (out_tc.cu)
-      unsigned todo = __ballot_sync(0xffffffffu, S != 0u);
-      while (todo) {
-        const int Ln = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t S_L = __shfl_sync(0xffffffffu, S, Ln), Y_L = __shfl_sync(0xffffffffu, Y, Ln);
-        const float bj_L = __shfl_sync(0xffffffffu, bj, Ln);
-        float zi = 0.f;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float v = __shfl_sync(0xffffffffu, z[k], Ln);
-          zi = (k == lane) ? v : zi;
-        }
-        const bool mine = (S_L >> lane) & 1u;
-        const float zz = zi + bj_L;
-        const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
-        const float tt = -LOG2E * x;
-        const float exs = ex2_approx(tt), dens = 1.f + exs;
-        const float g_dense = rcp_approx(dens) * (zz > 0.f ? g.tnw : g.tnw * NTF_LRELU_SLOPE);
-        const float ex = ex2_approx(fabsf(x) * -LOG2E);
-        const float den = 1.f + ex, lg = lg2_approx(den), r = rcp_approx(den);
-        const float sig = x > 0.f ? r : ex * r;
-        const float yf = ((Y_L >> lane) & 1u) ? 1.f : 0.f;
-        const float g_sp = g.tpw * (sig - yf) * (zz > 0.f ? 1.f : NTF_LRELU_SLOPE);
-        float d_lin = mine ? -tt : 0.f, d_lg = mine ? -lg2_approx(dens) : 0.f;
-        float d_sp = mine ? g.tpw * ((1.f - yf) * x + fmaxf(-x, 0.f) + 0.6931471805599453f * lg) : 0.f;
-        float d_db = mine ? g_sp - g_dense : 0.f;
-        __syncwarp();
-        if (mine && train) {
-          const int jl_L = jl - lane + Ln;
-          uint8_t* rowL = sgen + OFF_DZ + s * DZ_BYTES + (cb >> 1) * CHUNK + jl_L * 128;
-          *reinterpret_cast<__half*>(rowL + (((unit0 + (lane >> 3)) ^ (jl_L & 7)) << 4) + (lane & 7) * 2) = __float2half_rn(g_sp);
-        }
-        d_lin = warp_sum(d_lin); d_lg = warp_sum(d_lg); d_sp = warp_sum(d_sp); d_db = warp_sum(d_db);
-        if (lane == Ln) { acc_lin += d_lin; acc_lg += d_lg; loss_sp += d_sp; db_acc += d_db; }
-      }
       if (train) {
         fence_proxy_async();
         mbar_arrive(bar(BAR_DZ_FULL + s));
@@ -387,7 +325,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
       // ---- end of the expert tile: fold its loss terms, drain dW / db ----
       acc_lin += acc_lin2.x + acc_lin2.y;
       db_acc += db_acc2.x + db_acc2.y;
-      loss_total += e_ok ? g.tnw * 0.6931471805599453f * (acc_lg - acc_lin) + loss_sp : 0.f;
+      loss_total += e_ok ? g.tnw * 0.6931471805599453f * (acc_lg - acc_lin) : 0.f;
       if (train) {
         if (g.timing && threadIdx.x == 0 && n < 60) g.timing[TSLOTS * blockIdx.x + 8 + 8 * n + 2] = clock64();
         mbar_wait(bar(BAR_DW_FULL), j & 1);  // every product of the item has completed: the dz ring is free for staging
@@ -491,14 +429,115 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
   }
 }
 
+// ---- sparse correction pass: the (team, expert) pairs that are NOT (target 0, weight tnw) -----------------------------------------------
+// fnn.py:33-43: a team's members carry target 1 and weight tpw, its sampled negatives target 0 (unless they are members) and weight tpw.
+// One warp per team: the candidates (members, then negatives; duplicates and -1 dropped; experts outside this shard skipped) are handled
+// one after the other by the whole warp -- z = a.w + b from the SAME fp16 operand images the tensor-core pass read (fp32 accumulation),
+// then the difference between what the pair should contribute and what the dense pass already contributed for it:
+//   loss += tpw*bce(x, y) - tnw*softplus(x);  dg = fp16(g_true) - fp16(g_dense)  (the dense pass fed fp16(g_dense) to its products)
+//   dW[e,:] += scale*dg*a16[n,:]  (atomic: several teams may hit one expert);  db[e] += scale*(g_true - g_dense);
+//   dA[n,:] += scale*dg*w16[e,:]  (accumulated in registers, one read-modify-write per team: this warp owns the row)
+// Runs after out_tc2_kernel on the same stream.
+struct FixArgs {
+  const __half* A16;   // [B,128]
+  const __half* W16;   // [E,128]
+  const float* bias;   // [E]
+  const int32_t* m_indptr; const int32_t* m_indices;  // member CSR of the batch (absolute offsets, GLOBAL expert ids, ascending per team)
+  const int32_t* neg; int ns;                          // [B,ns] global expert ids, -1 = none (may be NULL: ns = 0)
+  int B, E, e_lo;
+  float tpw, tnw, scale;
+  float* dW; float* db; float* dA;  // NULL on a validation step
+  float* loss_part;                   // [gridDim.x] this pass's loss partials (summed with the dense pass's by ntf_loss_reduce)
+};
+constexpr int FIX_WARPS = 8;
+
+__global__ void __launch_bounds__(FIX_WARPS * 32) out_fix_kernel(FixArgs g) {
+  __shared__ float red[FIX_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * FIX_WARPS + warp;
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  float loss = 0.f;
+  if (n < g.B) {
+    const bool train = g.dW != nullptr;
+    const int mb = g.m_indptr[n], me = g.m_indptr[n + 1], nm = me - mb;
+    // this lane's slice of the team's activations: hidden units lane, lane+32, lane+64, lane+96 (coalesced 64-byte loads / 128-byte adds)
+    float a[4], dacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[q] = __half2float(g.A16[(size_t)n * HK + q * 32 + lane]);
+    const int ncand = nm + g.ns;
+    for (int c0 = 0; c0 < ncand; c0 += 32) {
+      // candidate c0 + lane: a member (ascending, unique) or a negative; a negative is dropped if it is -1, a member, or a repeat of an earlier negative
+      const int c = c0 + lane;
+      int e = -1;
+      bool member = false;
+      if (c < nm) { e = g.m_indices[mb + c]; member = true; }
+      else if (c < ncand) {
+        e = g.neg[(size_t)n * g.ns + (c - nm)];
+        if (e >= 0) {
+          for (int p = mb; p < me; ++p) if (g.m_indices[p] == e) { e = -1; break; }
+          for (int p = 0; p < c - nm && e >= 0; ++p) if (g.neg[(size_t)n * g.ns + p] == e) e = -1;
+        }
+      }
+      const int el = e - g.e_lo;  // column of this shard
+      unsigned todo = __ballot_sync(0xffffffffu, e >= 0 && el >= 0 && el < g.E);
+      while (todo) {
+        const int L = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int j = __shfl_sync(0xffffffffu, el, L);
+        const bool y = __shfl_sync(0xffffffffu, (int)member, L) != 0;
+        float w[4], dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { w[q] = __half2float(g.W16[(size_t)j * HK + q * 32 + lane]); dot = fmaf(a[q], w[q], dot); }
+        dot = warp_sum(dot);
+        const float zz = dot + __ldg(g.bias + j);
+        const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
+        const float slope = zz > 0.f ? 1.f : NTF_LRELU_SLOPE;
+        // what the dense pass computed for this pair (its formulas: t = -log2e*x, e = 2^t, sigmoid = 1/(1+e), softplus = (lg2(1+e) - t)*ln2)
+        const float tt = -LOG2E * x;
+        const float dens = 1.f + ex2_approx(tt);
+        const float g_dense = g.tnw * slope * rcp_approx(dens);
+        const float l_dense = g.tnw * LN2 * (lg2_approx(dens) - tt);
+        // what it should contribute (stable form)
+        const float ex = ex2_approx(fabsf(x) * -LOG2E), den = 1.f + ex, r = rcp_approx(den);
+        const float sig = x > 0.f ? r : ex * r, yf = y ? 1.f : 0.f;
+        const float g_true = g.tpw * (sig - yf) * slope;
+        const float l_true = g.tpw * ((1.f - yf) * x + fmaxf(-x, 0.f) + LN2 * lg2_approx(den));
+        loss += l_true - l_dense;  // (the same value in every lane; lane 0's copy is used)
+        if (train) {
+          const float dg = (__half2float(__float2half_rn(g_true)) - __half2float(__float2half_rn(g_dense))) * g.scale;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            atomicAdd(g.dW + (size_t)j * HK + q * 32 + lane, dg * a[q]);
+            dacc[q] = fmaf(dg, w[q], dacc[q]);
+          }
+          if (lane == 0) atomicAdd(g.db + j, (g_true - g_dense) * g.scale);
+        }
+      }
+    }
+    if (train) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) g.dA[(size_t)n * HK + q * 32 + lane] += dacc[q];
+    }
+  }
+  if (lane == 0) red[warp] = loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.f;
+#pragma unroll
+    for (int q = 0; q < FIX_WARPS; ++q) l += red[q];
+    g.loss_part[blockIdx.x] = l;
+  }
+}
+
 __global__ void to_half_kernel2(const float* __restrict__ x, size_t n, __half* __restrict__ y) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = __float2half_rn(x[i]);
 }
 }  // namespace
 
 // workspace: fp16 A | loss partials | fp16 W image (when the caller keeps none)
+static size_t tc2_loss_slots(int B) { return (size_t)1024 + (size_t)cdiv(B, FIX_WARPS) + 8; }  // dense pass: one per CTA; correction pass: one per block
 size_t ntf_out_train_tc2_workspace_bytes(int B, int h, int E) {
-  return align_up((size_t)B * h * sizeof(__half), 256) + align_up((size_t)(1024 + 8) * sizeof(float), 1024) + align_up((size_t)E * h * sizeof(__half), 1024);
+  return align_up((size_t)B * h * sizeof(__half), 256) + align_up(tc2_loss_slots(B) * sizeof(float), 1024) + align_up((size_t)E * h * sizeof(__half), 1024);
 }
 
 int ntf_out_train_tc2(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a, void* workspace, size_t workspace_bytes) {
@@ -510,15 +549,16 @@ int ntf_out_train_tc2(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a
   const bool train = a->dW != nullptr;
   NTF_REQUIRE(!train || (a->db && a->dA), NTF_ERR_BAD_ARG, "out_train(tf32): training needs dW, db and dA");
   NTF_REQUIRE(!train || (((uintptr_t)a->dA | (uintptr_t)a->dW) & 15) == 0, NTF_ERR_BAD_ARG, "out_train(tf32): dA and dW must be 16-byte aligned");
-  NTF_REQUIRE((a->special_t == nullptr) == (a->member_t == nullptr), NTF_ERR_BAD_ARG, "out_train(tf32): special_t and member_t come together");
-  NTF_REQUIRE(a->special_t || !a->special, NTF_ERR_BAD_ARG, "out_train(tf32): the tensor-core kernel reads the tile-transposed planes (ntf_special_tiles), not `special`");
+  NTF_REQUIRE(!a->special && !a->special_t, NTF_ERR_BAD_ARG, "out_train(tf32, persistent): takes the member CSR and `neg` (the sparse correction pass), not bit planes");
+  NTF_REQUIRE(a->ns == 0 || a->neg, NTF_ERR_BAD_ARG, "out_train(tf32): ns=%d without neg", a->ns);
+  NTF_REQUIRE(a->m_indptr && a->m_indices, NTF_ERR_BAD_ARG, "out_train(tf32): the member CSR is missing");
   char* ws = (char*)workspace;
   __half* A16 = a->A16 ? (__half*)const_cast<void*>(a->A16) : (__half*)ws;
   float* loss_part = (float*)(ws + align_up((size_t)a->B * a->h * sizeof(__half), 256));
   const __half* W16 = (const __half*)a->W16;
   const int blocks_h = ctx->sm_count * 8;
   if (!W16) {  // no image kept by the caller: made here (one pass over W: 6 bytes per weight)
-    __half* w = (__half*)(ws + align_up((size_t)a->B * a->h * sizeof(__half), 256) + align_up((size_t)(1024 + 8) * sizeof(float), 1024));
+    __half* w = (__half*)(ws + align_up((size_t)a->B * a->h * sizeof(__half), 256) + align_up(tc2_loss_slots(a->B) * sizeof(float), 1024));
     const size_t nw = (size_t)a->E * HK;
     NTF_COUNT_LAUNCH; to_half_kernel2<<<(unsigned)(cdiv((int)((nw + 255) / 256), 1) < blocks_h ? (nw + 255) / 256 : blocks_h), 256, 0, st>>>(a->W, nw, w);
     NTF_LAUNCH_CHECK();
@@ -536,7 +576,7 @@ int ntf_out_train_tc2(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a
   if ((rc = make_map(ctx, &mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)a->B, HK, TB, 64))) return rc;
   if (train) NTF_CUDA(cudaMemsetAsync(a->dA, 0, (size_t)a->B * a->h * sizeof(float), st));
   Tc2Args g{};
-  g.bias = a->b; g.special_t = const_cast<uint32_t*>(a->special_t); g.member_t = const_cast<uint32_t*>(a->member_t); g.Epad = cdiv(a->E, TE) * TE;
+  g.bias = a->b;
   g.B = a->B; g.E = a->E; g.tpw = a->tpw; g.tnw = a->tnw; g.scale = a->loss_scale;
   g.dW = a->dW; g.db = a->db; g.dA = a->dA; g.loss_part = loss_part;
   g.nct = cdiv(a->E, TE); g.nbt = cdiv(a->B, TB);
@@ -558,5 +598,12 @@ int ntf_out_train_tc2(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a
   NTF_CUDA(cudaFuncSetAttribute(out_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   NTF_COUNT_LAUNCH; out_tc2_kernel<<<grid, NT, SMEM_BYTES, st>>>(mw, mh, g);
   NTF_LAUNCH_CHECK();
-  return ntf_loss_reduce_impl(st, loss_part, grid, a->loss_scale, a->loss_out);
+  FixArgs f{};
+  f.A16 = A16; f.W16 = W16; f.bias = a->b; f.m_indptr = a->m_indptr; f.m_indices = a->m_indices; f.neg = a->neg; f.ns = a->neg ? a->ns : 0;
+  f.B = a->B; f.E = a->E; f.e_lo = a->e_lo; f.tpw = a->tpw; f.tnw = a->tnw; f.scale = a->loss_scale;
+  f.dW = a->dW; f.db = a->db; f.dA = a->dA; f.loss_part = loss_part + grid;
+  const int fix_blocks = cdiv(a->B, FIX_WARPS);
+  NTF_COUNT_LAUNCH; out_fix_kernel<<<fix_blocks, FIX_WARPS * 32, 0, st>>>(f);
+  NTF_LAUNCH_CHECK();
+  return ntf_loss_reduce_impl(st, loss_part, grid + fix_blocks, a->loss_scale, a->loss_out);
 }

@@ -87,7 +87,9 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     }
     ntf_out_train_args o;
     memset(&o, 0, sizeof(o));
-    if (tc) {
+    if (tc && getenv("NTF_TC_V1") == nullptr) {
+      o.neg = neg; o.ns = ns;  // persistent kernel + sparse correction pass (out_tc2.cu): the pairs of weight tpw are named by the lists themselves
+    } else if (tc) {
       STEP(ntf_special_tiles(ctx, ctx->side[0], 1, B, a->m_indptr, a->m_indices, neg, ns, a->E, a->e_lo, a->special_t, a->member_t));
       o.special_t = a->special_t; o.member_t = a->member_t;
     } else {

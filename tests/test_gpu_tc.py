@@ -28,19 +28,23 @@ def ws(ops):
     return ops.Workspace(torch.device(DEV))
 
 
-def run_tc(ops, ws, A, W, b, Y, negs, tpw, tnw, train=True, zdbg=False):
+def run_tc(ops, ws, A, W, b, Y, negs, tpw, tnw, train=True, zdbg=False, planes=False):
+    """planes=False: the persistent kernel + sparse correction pass (out_tc2.cu; the member CSR and `neg` name the pairs of weight tpw);
+    planes=True: round 1's kernel (out_tc.cu MODE 0, still the Flipout layer's pipeline), fed the tile-transposed bit planes"""
     from opentf_b200._lib import OutTrainArgs
     B, h = A.shape; E = W.shape[0]
     indptr, indices = dev_csr(Y)
     words = ops.special_tiles_bytes(B, E) // 4
     plane_s, plane_m = torch.zeros(words, dtype=torch.int32, device=DEV), torch.zeros(words, dtype=torch.int32, device=DEV)
     negd = None if negs is None else torch.from_numpy(np.ascontiguousarray(negs, dtype=np.int32)).to(DEV)
-    ops.special_tiles(1, B, indptr.data_ptr(), indices, negd, 0 if negs is None else negs.shape[1], E, plane_s, plane_m)
+    if planes: ops.special_tiles(1, B, indptr.data_ptr(), indices, negd, 0 if negs is None else negs.shape[1], E, plane_s, plane_m)
     Ad, Wd, bd = A.to(DEV), W.to(DEV), b.to(DEV)
     dW, db, dA, loss = torch.full((E, h), float('nan'), device=DEV), torch.full((E,), float('nan'), device=DEV), torch.empty(B, h, device=DEV), torch.zeros(1, device=DEV)
     Z = torch.full((B, E), float('nan'), device=DEV) if zdbg else None
     a = OutTrainArgs()
-    a.A, a.W, a.b, a.special_t, a.member_t = Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), plane_s.data_ptr(), plane_m.data_ptr()
+    a.A, a.W, a.b = Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr()
+    if planes: a.special_t, a.member_t = plane_s.data_ptr(), plane_m.data_ptr()
+    elif negd is not None: a.neg, a.ns = negd.data_ptr(), negs.shape[1]
     a.m_indptr, a.m_indices, a.B, a.h, a.E = indptr.data_ptr(), indices.data_ptr(), B, h, E
     a.tpw, a.tnw, a.loss_scale, a.loss_out = tpw, tnw, 1.0 / B, loss.data_ptr()
     if train: a.dW, a.db, a.dA = dW.data_ptr(), db.data_ptr(), dA.data_ptr()
@@ -127,6 +131,17 @@ def test_tc_operand_range_edges(ops, ws):
     bound = 2.1 * TF32_EPS * (A.abs() @ W.abs().t()) + (A.abs().sum(1, keepdim=True) * 2.0 ** -25) + 1e-6  # relative part + subnormal absolute part
     assert not torch.isnan(Z).any() and not torch.isinf(Z).any()
     assert ((Z.double() - z_ref).abs() <= bound.double()).all(), float(((Z.double() - z_ref).abs() / bound.double()).max())
+
+
+@pytest.mark.parametrize('B,E', [(100, 200), (1000, 4097), (256, 300)])
+def test_tc_round1_kernel_fed_bit_planes_still_matches(ops, ws, B, E):
+    """out_tc.cu MODE 0 (one CTA per expert tile, fix-up from the tile-transposed planes inside the epilogue): the pipeline the Flipout layer
+    still runs on; kept selectable for the Fnn layer (planes given / NTF_TC_V1=1) for A/B runs"""
+    A, W, b, Y, negs = make_case(B, E, 7 * B + E)
+    loss, dW, db, dA, Z = run_tc(ops, ws, A, W, b, Y, negs, 10.0, 1.0, zdbg=True, planes=True)
+    l_ref, dW_ref, db_ref, dA_ref = oracle_from_logits(Z, A, W, Y, negs, 10.0, 1.0)
+    assert abs(loss - l_ref) <= 2e-5 * abs(l_ref) + 1e-6
+    assert rel_err(db, db_ref) < 2e-5 and rel_err(dW, dW_ref) < 2e-3 and rel_err(dA, dA_ref) < 2e-3
 
 
 def test_tc_matches_fp32_kernel_on_device(ops, ws):
