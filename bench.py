@@ -325,14 +325,16 @@ def run_ours(args):
     k_ms = float(np.mean([a.elapsed_time(c) for a, c in used]))
 
     # ---- end to end through the streaming entry point: host batches in, loss out ----
+    # Every step: the global batch's rows are PACKED from the host teamsvecs CSR into a pinned block (ntf_pack_host_batch, the loader's work),
+    # copied to the device (one H2D transfer), stepped, and the loss is read back (D2H + sync).  Packing of batch i+1 runs on the host while the
+    # GPU works on batch i, as a loader thread would; all of it is inside the timed region.
     host = HostBatches(tv, train_rows, b, 0 if shard else rank, 1 if shard else G)
-    host.prepare(list(range(min(3, args.warmup))) + [100 + i for i in range(args.steps)])  # pinned host inputs exist before timing
     for i in range(min(3, args.warmup)): host.step(eng, i)
     sync()
     w0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps): host.step(eng, 100 + i)
+    host.run(eng, 100, args.steps)
     e1.record()
     sync()
     e2e_ms = max(e0.elapsed_time(e1), 0.0)
@@ -366,9 +368,10 @@ def run_ours(args):
             except Exception as ex:  # (single process: report and go on; the headline measurement above is already taken)
                 if world > 1: raise
                 extras[name] = {'error': f'{type(ex).__name__}: {ex}'}
-        leg('infer_topk_sweep', lambda: topk_sweep(eng, test_sp, dev, sync, G))
+        lin_sd = {f'layers.{i}.{n}': getattr(m, n).detach() for i, m in enumerate(lin) for n in ('weight', 'bias')}
         del eng, sp, test_sp, scores
         torch.cuda.empty_cache()
+        if not shard: leg('infer_topk_sweep', lambda: topk_sweep(args, tv, splits, dev, sync, G, lin_sd))
         leg('bnn_train', lambda: bnn_leg(args, dev, world, rank, sync, dist))
         leg('batch_sweep', lambda: batch_sweep(args, tv, splits, dev, world, rank, sync, dist))
     if rank != 0:
@@ -392,7 +395,8 @@ def run_ours(args):
            'higher_is_better': True, 'scaling': 'strong' if shard else 'weak', 'vs_baseline': None, 'dtype': 'f32' if precision_used == 'fp32' else 'f16 operands (10-bit mantissa, TF32-class), f32 accumulate',
            'data': 'synthetic', 'config': config_of(args, tv), 'clocks': clk.summary(),
            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': host.h2d_bytes, 'd2h_bytes_per_step': 4,
-                   'api': 'Engine.step_host: pinned batch CSR block -> one H2D copy -> ntf_fnn_step (replayed as a CUDA graph) -> loss.item()'},
+                   'api': 'HostPacker.pack (ntf_pack_host_batch: rows of the host teamsvecs CSR -> pinned block; batch i+1 packed while the GPU works on batch i) '
+                          '-> Engine.step_host: one H2D copy -> ntf_fnn_step (replayed as a CUDA graph) -> loss read back (D2H + sync); all inside the timed region'},
            'gpu_launches': launches, 'cuda_graphs': bool(graphs),
            'dp_exchange': None if G == 1 else {'peer': 'reduce-scatter + Adam + all-gather fused in one pass over peer memory inside ntf_fnn_step (csrc/peer.cu), 2 overlapped arena segments',
                                                'nccl': 'ncclAllReduce inside ntf_fnn_step: 2 overlapped arena segments, captured in the step graph'}.get(
@@ -501,63 +505,80 @@ def batch_sweep(args, tv, splits, dev, world, rank, sync, dist):
     return out
 
 
-def topk_sweep(eng, test_sp, dev, sync, G):
-    """BASELINE configs[4]: top-K expert ranking over all experts for held-out teams, K sweep at the bench batch (device resident)"""
+def topk_sweep(args, tv, splits, dev, sync, G, lin_sd):
+    """BASELINE configs[4]: top-K expert ranking over all experts, K x batch sweep (device resident; team-parallel: every rank ranks its own
+    batches, the aggregate is G x one rank's rate).  K <= 128 runs the fused kernel (the [B,E] scores never reach HBM), K = 1000 (the
+    reference's default testcfg.topK) the scores -> radix-select path.  Small batches are latency-bound (one library call per batch: ~6
+    launches); the teams/s at batch >= 4096 is the throughput figure."""
     import torch
+    from opentf_b200.engine import Engine
+    N, S = tv['skill'].shape; E = tv['member'].shape[1]
+    rows = np.asarray(splits['folds'][0]['train'])
+    batches = [b for b in (1, 8, 64, 512, 4096, 32768) if b <= len(rows)]
+    Bmax = max(batches)
+    eng = Engine(S, [128], E, dev, precision=args.precision, nsd=args.nsd, ns=5, seed=0, max_batch=Bmax)
+    eng.stage(tv['skill'], tv['member'])
+    eng.load_state_dict(lin_sd)
+    sp = eng.split(rows[:max(Bmax, min(len(rows), 40000))])
     out = []
-    ib = min(eng.Bmax, test_sp.n)
-    scores = torch.empty(ib, eng.E, device=dev)
-    for K in (2, 10, 100, 1000):
-        if K > eng.E: continue
-        vals, idx = torch.empty(ib, K, device=dev), torch.empty(ib, K, dtype=torch.int32, device=dev)
-        for _ in range(2): eng.topk(test_sp, 0, ib, K, scores, vals, idx)
-        sync()
-        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        i0.record()
-        for r in range(reps): eng.topk(test_sp, (r * ib) % max(1, test_sp.n - ib + 1), ib, K, scores, vals, idx)
-        i1.record()
-        sync()
-        out.append({'k': K, 'batch': ib, 'value': reps * ib * G / (i0.elapsed_time(i1) * 1e-3), 'unit': 'teams/s'})
+    scores = None
+    for K in (2, 5, 10, 20, 50, 100, 1000):
+        if K > E: continue
+        for ib in batches:
+            fused = eng.fused_topk_ok(ib, K)
+            if not fused and (scores is None or scores.shape[0] < ib): scores = torch.empty(ib, E, device=dev)
+            vals, idx = torch.empty(ib, K, device=dev), torch.empty(ib, K, dtype=torch.int32, device=dev)
+            span = max(1, sp.n - ib + 1)
+            for r in range(2): eng.topk(sp, (r * ib) % span, ib, K, scores, vals, idx)
+            sync()
+            reps = int(max(3, min(200, 2e5 // max(ib, 256))))
+            i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            i0.record()
+            for r in range(reps): eng.topk(sp, (r * ib) % span, ib, K, scores, vals, idx)
+            i1.record()
+            sync()
+            ms = i0.elapsed_time(i1) / reps
+            out.append({'k': K, 'batch': ib, 'value': ib * G / (ms * 1e-3), 'unit': 'teams/s', 'us_per_call': ms * 1e3, 'fused': bool(fused)})
+    del eng, sp, scores
+    torch.cuda.empty_cache()
     return out
 
 
 class HostBatches:
-    """batches as the host holds them (pinned compact CSR slices of teamsvecs, one block per batch) for the end-to-end leg."""
+    """the host side of the end-to-end leg: global batches are packed from the host teamsvecs CSR into pinned blocks (engine.HostPacker)."""
 
     def __init__(self, tv, train_rows, b, rank, G):
-        from opentf_b200.engine import to_csr
+        from opentf_b200.engine import HostPacker, to_csr
         self.b, self.rank, self.G = b, rank, G
         self.s = to_csr(tv['skill']); self.m = to_csr(tv['member'])
-        self.rows = train_rows
-        self.h2d_bytes = 0
-        self.pin = {}
+        self.rows = np.asarray(train_rows, dtype=np.int32)
+        gB = b * G
+        # capacities: the longest global batch of the run (+ slack), so that every batch has the same device layout (one captured graph)
+        ls, lm = np.diff(self.s[0])[self.rows], np.diff(self.m[0])[self.rows]
+        nb = len(self.rows) // gB
+        cap = lambda l: int(-(-int(l[:nb * gB].reshape(nb, gB).sum(1).max() * 1.02 + 64) // 64) * 64)
+        self.cap_s, self.cap_m = cap(ls), cap(lm)
+        self.packer = HostPacker(self.s, self.m, gB, self.cap_s, self.cap_m)
+        self.h2d_bytes = self.packer.words * 4
 
     def _rows(self, i):
         gB = self.b * self.G
         g0 = (i * gB) % (len(self.rows) - gB)
         return self.rows[g0:g0 + gB]
 
-    def prepare(self, ids):
-        """pinned blocks of the global batches `ids` (built once, outside any timed region), all packed to the same capacities:
-        one layout -> one set of device addresses -> the step replays one captured graph"""
-        from opentf_b200.engine import pack_host_batch
-        (sptr, _, _), (mptr, _, _) = self.s, self.m
-        cap = lambda ptr: int(max((ptr[self._rows(i) + 1] - ptr[self._rows(i)]).sum() for i in ids))
-        cap_s, cap_m = -(-cap(sptr) // 64) * 64, -(-cap(mptr) // 64) * 64
-        for i in ids:
-            rows = self._rows(i)
-            parts = []
-            for ptr, idx, _ in (self.s, self.m):
-                lens = ptr[rows + 1] - ptr[rows]
-                p = np.zeros(len(rows) + 1, dtype=np.int32); np.cumsum(lens, out=p[1:])
-                parts += [p, np.concatenate([idx[ptr[r]:ptr[r + 1]] for r in rows]).astype(np.int32)]
-            self.pin[i] = pack_host_batch(parts[0], parts[1], parts[2], parts[3], cap_s=cap_s, cap_m=cap_m)
-
     def step(self, eng, i):
-        packed, n, cap_s, cap_m = self.pin[i]
-        self.h2d_bytes = packed.numel() * 4
-        return eng.step_host(packed, n, cap_s, cap_m, self.rank, self.G, lr=1e-3)
+        return eng.step_host(self.packer.pack(self._rows(i)), self.b * self.G, self.cap_s, self.cap_m, self.rank, self.G, lr=1e-3)
+
+    def run(self, eng, first, steps):
+        """`steps` consecutive batches: pack(i+1) overlaps the GPU's work on batch i; the loss of every step is read back"""
+        gB = self.b * self.G
+        blk = self.packer.pack(self._rows(first))
+        loss = None
+        for i in range(steps):
+            eng.step_host(blk, gB, self.cap_s, self.cap_m, self.rank, self.G, lr=1e-3, sync=False)
+            if i + 1 < steps: blk = self.packer.pack(self._rows(first + i + 1))
+            loss = eng.step_host_loss()
+        return loss
 
 
 if __name__ == '__main__':

@@ -198,7 +198,21 @@ typedef struct {
                                   pair as (target 0, weight tnw) and a sparse correction pass puts these few right.  Given `neg` (or ns == 0 and
                                   special_t == NULL) the planes are not needed */
   int ns;
+  /* optional fusion of the step that follows when layer n_layers-2 feeds the output layer directly and dA needs no exchange (one hidden
+   * layer, not expert-sharded): the correction pass, which owns each team's dA row last, also applies the activation's derivative and
+   * the bias gradient of that layer -- dz_prev = dA * lrelu'(act_prev), db_prev = colsum(dz_prev) -- i.e. ntf_act_bwd; dA itself is then
+   * not written back.  All three or none. */
+  const float* act_prev;       /* [B,h] lrelu output of the previous layer                              */
+  float* dz_prev;              /* [B,h]                                                                  */
+  float* db_prev;              /* [h]                                                                    */
+  int prepared;                /* != 0: the caller ran ntf_out_train_prepare for this call already (off the critical path) */
+  int defer_finish;            /* != 0: leave the call's final reductions (loss_out; db_prev when fused) to ntf_out_train_finish, which the caller
+                                  runs with the same args / workspace on any stream ordered after this call -- they gate nothing but the optimiser */
 } ntf_out_train_args;
+int ntf_out_train_finish(ntf_ctx* ctx, void* stream, const ntf_out_train_args* args, void* workspace, size_t workspace_bytes);
+/* NTF_TF32 Fnn: what ntf_out_train has to clear before its kernel -- dA and the dW/db rows of expert tiles that two CTAs share.  A caller
+ * that knows the shapes early (ntf_fnn_step: at the top of the step, on a side stream) runs it there and sets args.prepared. */
+int ntf_out_train_prepare(ntf_ctx* ctx, void* stream, int B, int h, int E, float* dW, float* db, float* dA);
 /* 1 if NTF_TF32 has a tcgen05 kernel for this shape (else callers use NTF_FP32; ntf_out_train(NTF_TF32) refuses it) */
 int ntf_tc_supported(int B, int h, int E, int flipout);
 size_t ntf_out_train_workspace_bytes(const ntf_ctx* ctx, int precision, int B, int h, int E, int flipout);
@@ -407,6 +421,13 @@ typedef struct ntf_fnn_infer_topk_args {
 size_t ntf_fnn_infer_topk_workspace_bytes(const ntf_ctx* ctx, const ntf_fnn_infer_topk_args* args);
 int ntf_fnn_infer_topk(ntf_ctx* ctx, void* stream, const ntf_fnn_infer_topk_args* args, void* workspace, size_t workspace_bytes);
 
+
+/* HOST function (no device work): rows `rows[0..n)` of the skill / member CSR (int32 indptr / indices of all teams) -> the int32 block
+ * [s_indptr n+1 | m_indptr n+1 | s_indices cap_s | s_ent_row cap_s | m_indices cap_m] (offsets from 0, segments zero-padded to the capacities)
+ * that the streaming entry point copies to the device in one transfer.  Replaces the per-row work of the reference's Dataset / DataLoader
+ * (ntf.py:17-25, fnn.py:95,118-121).  `out` is typically pinned host memory. */
+int ntf_pack_host_batch(const int32_t* rows, int n, const int32_t* s_indptr, const int32_t* s_indices, const int32_t* m_indptr,
+                        const int32_t* m_indices, int cap_s, int cap_m, int32_t* out, size_t out_words);
 
 /* out[i] = sum_k parts[k*part_stride + i] in a fixed order (deterministic split reductions) */
 int ntf_sum_parts(ntf_ctx* ctx, void* stream, const float* parts, int nparts, size_t n, size_t part_stride, float* out);

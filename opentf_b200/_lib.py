@@ -21,7 +21,7 @@ class OutTrainArgs(C.Structure):
     _fields_ = [('A', vp), ('W', vp), ('b', vp), ('special', vp), ('pitch_words', i32), ('m_indptr', vp), ('m_indices', vp),
                 ('B', i32), ('h', i32), ('E', i32), ('tpw', f32), ('tnw', f32), ('loss_scale', f32),
                 ('dW', vp), ('db', vp), ('dA', vp), ('loss_out', vp),
-                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp), ('e_lo', i32), ('A16', vp), ('W16', vp), ('neg', vp), ('ns', i32)]
+                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp), ('e_lo', i32), ('A16', vp), ('W16', vp), ('neg', vp), ('ns', i32), ('act_prev', vp), ('dz_prev', vp), ('db_prev', vp), ('prepared', i32), ('defer_finish', i32)]
 
 
 class InferTopkArgs(C.Structure):
@@ -101,6 +101,8 @@ SIGNATURES = {
     'ntf_tc_supported': (i32, [i32, i32, i32, i32]),
     'ntf_out_train_workspace_bytes': (sz, [vp, i32, i32, i32, i32, i32]),
     'ntf_out_train': (i32, [vp, vp, i32, C.POINTER(OutTrainArgs), vp, sz]),
+    'ntf_out_train_finish': (i32, [vp, vp, C.POINTER(OutTrainArgs), vp, sz]),
+    'ntf_out_train_prepare': (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
     'ntf_adam_step': (i32, [vp, vp, vp, vp, vp, vp, sz, f64, f64, f64, f64, i64]),
     'ntf_infer_scores_workspace_bytes': (sz, [i32, i32, i32]),
     'ntf_infer_scores': (i32, [vp, vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, sz]),
@@ -128,6 +130,7 @@ SIGNATURES = {
     'ntf_fnn_step': (i32, [vp, vp, C.POINTER(FnnStepArgs), vp, sz]),
     'ntf_fnn_infer_topk_workspace_bytes': (sz, [vp, C.POINTER(FnnInferTopkArgs)]),
     'ntf_fnn_infer_topk': (i32, [vp, vp, C.POINTER(FnnInferTopkArgs), vp, sz]),
+    'ntf_pack_host_batch': (i32, [vp, i32, vp, vp, vp, vp, i32, i32, vp, sz]),
     'ntf_sum_parts': (i32, [vp, vp, vp, i32, sz, sz, vp]),
 }
 

@@ -62,6 +62,7 @@ extern "C" int ntf_create(int device, ntf_ctx** out) {
   if (es == cudaSuccess) es = cudaStreamCreateWithFlags(&c->comm_st, cudaStreamNonBlocking);
   for (int i = 0; i < 2 && es == cudaSuccess; ++i) es = cudaEventCreateWithFlags(&c->ev_ar[i], cudaEventDisableTiming);
   if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_bwd, cudaEventDisableTiming);
+  if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_finish, cudaEventDisableTiming);
   cudaSetDevice(cur);
   if (es != cudaSuccess) {
     ntf_set_error("ntf_create: side streams / events: %s", cudaGetErrorString(es));
@@ -78,7 +79,7 @@ extern "C" int ntf_destroy(ntf_ctx* ctx) {
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_fork_opt); cudaEventDestroy(ctx->ev_join_opt);
     cudaEventDestroy(ctx->ev_hot_fork); cudaEventDestroy(ctx->ev_hot_join);
-    cudaStreamDestroy(ctx->comm_st); cudaEventDestroy(ctx->ev_ar[0]); cudaEventDestroy(ctx->ev_ar[1]); cudaEventDestroy(ctx->ev_bwd);
+    cudaStreamDestroy(ctx->comm_st); cudaEventDestroy(ctx->ev_ar[0]); cudaEventDestroy(ctx->ev_ar[1]); cudaEventDestroy(ctx->ev_bwd); cudaEventDestroy(ctx->ev_finish);
   }
   delete ctx;
   return NTF_OK;
@@ -143,5 +144,38 @@ extern "C" int ntf_graph_destroy(ntf_graph* g) {
   if (!g) return NTF_OK;
   if (g->exec) cudaGraphExecDestroy(g->exec);
   delete g;
+  return NTF_OK;
+}
+
+// ---- host side of the streaming entry point (no device work): one global batch of the teamsvecs CSR -> the pinned block Engine.step_host
+// copies to the device in ONE transfer.  Layout (int32 words): [s_indptr n+1 | m_indptr n+1 | s_indices cap_s | s_ent_row cap_s | m_indices cap_m];
+// offsets start at 0; the index segments are padded to fixed capacities so that every batch of a run lands at the same device addresses (the
+// step then replays one captured graph).  The reference does this work per row in Python (ntf.py:17-25: lil row -> dense float vector, default
+// collate); here it is a memcpy per row of the already-CSR teamsvecs.
+extern "C" int ntf_pack_host_batch(const int32_t* rows, int n, const int32_t* s_indptr, const int32_t* s_indices, const int32_t* m_indptr,
+                                   const int32_t* m_indices, int cap_s, int cap_m, int32_t* out, size_t out_words) {
+  NTF_REQUIRE(rows && s_indptr && s_indices && m_indptr && m_indices && out && n > 0, NTF_ERR_BAD_ARG, "pack_host_batch: null pointer / empty batch");
+  const size_t need = 2 * ((size_t)n + 1) + 2 * (size_t)cap_s + (size_t)cap_m;
+  NTF_REQUIRE(out_words >= need, NTF_ERR_WORKSPACE, "pack_host_batch: block of %zu words, %zu needed", out_words, need);
+  int32_t* sp = out;
+  int32_t* mp = sp + n + 1;
+  int32_t* si = mp + n + 1;
+  int32_t* sr = si + cap_s;
+  int32_t* mi = sr + cap_s;
+  int ns = 0, nm = 0;
+  sp[0] = 0; mp[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    const int r = rows[i];
+    const int a = s_indptr[r], ls = s_indptr[r + 1] - a, b = m_indptr[r], lm = m_indptr[r + 1] - b;
+    NTF_REQUIRE(ns + ls <= cap_s && nm + lm <= cap_m, NTF_ERR_BAD_ARG, "pack_host_batch: capacities (%d, %d) too small at row %d", cap_s, cap_m, i);
+    memcpy(si + ns, s_indices + a, (size_t)ls * sizeof(int32_t));
+    for (int k = 0; k < ls; ++k) sr[ns + k] = i;
+    memcpy(mi + nm, m_indices + b, (size_t)lm * sizeof(int32_t));
+    ns += ls; nm += lm;
+    sp[i + 1] = ns; mp[i + 1] = nm;
+  }
+  memset(si + ns, 0, (size_t)(cap_s - ns) * sizeof(int32_t));
+  memset(sr + ns, 0, (size_t)(cap_s - ns) * sizeof(int32_t));
+  memset(mi + nm, 0, (size_t)(cap_m - nm) * sizeof(int32_t));
   return NTF_OK;
 }

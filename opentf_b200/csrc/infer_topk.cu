@@ -71,6 +71,8 @@ struct ItArgs {
   unsigned long long* cand;  // pass 2 out: [B, cap] composites (ordered logit << 32 | ~expert)
   int* cnt;                  // [B] candidates appended so far (zeroed by the caller)
   int cap;
+  long long* timing;         // debug (NTF_IT_TIMING): per CTA 256 slots: [0] start clock, [1] end clock; from 8, 4 per product q < 60: W tile landed (MMA warp),
+                             // product issued, logits ready (epilogue thread 0), epilogue done
 };
 
 template <int PASS>
@@ -88,6 +90,7 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
   const int nh = min(NH, g.nbt - bp * NH);  // batch tiles this CTA really has
   const int t0 = (int)((long long)chunk * g.nct / g.nchunk), t1 = (int)((long long)(chunk + 1) * g.nct / g.nchunk);
   const int ntiles = t1 - t0;
+  if (g.timing && threadIdx.x == 0) g.timing[256 * blockIdx.x] = clock64();
 
   if (threadIdx.x == 0) {
     mbar_init(bar(BAR_A_FULL), 1);
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
       const uint64_t d_w = smem_desc(sbase + OFF_W + s * TILE_BYTES, 16, 1024);
       for (int hf = 0; hf < nh; ++hf) {
         const int q = it * nh + hf, zs = q % Z_STAGES;  // accumulator stages are handed out per product
+        if (g.timing && lane == 0 && q < 60) g.timing[256 * blockIdx.x + 8 + 4 * q] = clock64();
         mbar_wait(bar(BAR_Z_EMPTY + zs), ((q / Z_STAGES) & 1) ^ 1);
         tc_fence_after();
         const uint64_t d_a = smem_desc(sbase + OFF_A + hf * TILE_BYTES, 16, 1024);
@@ -134,6 +138,7 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
           if (elect_one()) mma_f16(tmem + zs * TX, d_a + koff, d_w + koff, IDESC, i > 0);
         }
         if (elect_one()) tc_commit(bar(BAR_Z_FULL + zs));
+        if (g.timing && lane == 0 && q < 60) g.timing[256 * blockIdx.x + 8 + 4 * q + 1] = clock64();
       }
       if (elect_one()) tc_commit(bar(BAR_W_EMPTY + s));
     }
@@ -173,6 +178,7 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
         if (hf >= nh) break;
         const int q = it * nh + hf, zs = q % Z_STAGES;
         mbar_wait(bar(BAR_Z_FULL + zs), (q / Z_STAGES) & 1);
+        if (g.timing && threadIdx.x == 0 && q < 60) g.timing[256 * blockIdx.x + 8 + 4 * q + 2] = clock64();
         tc_fence_after();
         float z[BLK];
         tmem_ld32(tmem + lane_base + zs * TX + cb * BLK, z);
@@ -197,11 +203,13 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
             }
           }
         }
+        if (g.timing && threadIdx.x == 0 && q < 60) g.timing[256 * blockIdx.x + 8 + 4 * q + 3] = clock64();
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (g.timing && threadIdx.x == 0) g.timing[256 * blockIdx.x + 1] = clock64();
   if (warp == WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
@@ -369,6 +377,8 @@ extern "C" int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_a
   g.cnt = (int*)(ws + w.cnt);
   g.cand = (unsigned long long*)(ws + w.cand);
   g.cap = BLK * a->K;
+  const char* tim = getenv("NTF_IT_TIMING");
+  g.timing = tim ? (long long*)(uintptr_t)strtoull(tim, nullptr, 0) : nullptr;
   CUtensorMap ma, mw;
   int rc;
   if ((rc = make_map(ctx, &ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)a->B, HK, TT, 64))) return rc;

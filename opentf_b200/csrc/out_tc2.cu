@@ -9,8 +9,8 @@
 //   * one CTA per SM walks a contiguous range of the (expert tile, batch tile) sequence -- no waves, no split last wave;
 //   * the W tile arrives as fp16 straight from an fp16 image of the weight (TMA, no conversion pass); the caller keeps the image
 //     (ntf_out_train_args.W16, rewritten by the optimiser) or this file makes it per call;
-//   * the dW drain of an expert tile goes through the idle dz ring, so the NEXT tile's W / activation loads and first forward
-//     product run underneath it;
+//   * the dW drain of an expert tile is staged in the idle dz ring and handed to the TMA unit (tensor store, or reduce-add for a tile two
+//     CTAs share), so the NEXT tile's W / activation loads, first forward product and epilogue run underneath it;
 //   * dA is produced TRANSPOSED (hidden unit on the TMEM lane), so its warps add it into dA[B,128] with coalesced red.global.add from
 //     registers -- no staging buffer, no barriers, no proxy fences -- and the 48 KB of staging go to a third activation stage, which takes
 //     tile n+1's activation load off the critical path of tile n-1's backward products.
@@ -62,6 +62,7 @@ struct Tc2Args {
   float* Zdbg;      // debug: raw logits [B,E]
   long long* timing;  // debug: per CTA TSLOTS slots: start ns, end ns, smid, start / end clock; from slot 8, 8 per tile n < 60: Z ready, tile done, drain start, drain end, bwd issue start / end, dA staged, dW products complete
   int nct, nbt;     // expert tiles, batch tiles
+  unsigned* done;   // block counter of the correction pass that follows: cleared here (CTA 0), so that pass needs no launch of its own for it
   int split;        // 0: CTA c owns tiles [c*T/G, (c+1)*T/G) of the expert-major sequence; s > 0: expert tile c/s, batch part c%s of s
 };
 
@@ -96,7 +97,8 @@ __global__ void __launch_bounds__(256) zero_cut_tiles_kernel(Tc2Args g) {
   for (int i = threadIdx.x; i < rows; i += 256) g.db[e0 + i] = 0.f;
 }
 
-__global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ CUtensorMap map_w16, const __grid_constant__ CUtensorMap map_a16, Tc2Args g) {
+__global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ CUtensorMap map_w16, const __grid_constant__ CUtensorMap map_a16,
+                                                        const __grid_constant__ CUtensorMap map_dw, Tc2Args g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   if ((sbase & 1023u) != 0u) __trap();
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
   }
   int L0, L1;
   tile_range(g, blockIdx.x, gridDim.x, &L0, &L1);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && g.done) g.done[0] = 0u;
   const bool train = g.dW != nullptr;
   const int nbt = g.nbt;
 
@@ -225,6 +228,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     constexpr float LOG2E = 1.4426950408889634f;
     float loss_total = 0.f;
+    bool drain_pending = false;
     // per item (expert tile):
     int j = -1, e0 = 0, e = 0;
     bool e_ok = false, whole = false;
@@ -261,6 +265,11 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
           if (e_ok && q < nrem) g.Zdbg[(size_t)(n0 + q) * g.E + e] = z[q] + bj;
       }
       if (train) mbar_wait(bar(BAR_DZ_EMPTY + s), ph ^ 1);
+      if (drain_pending) {  // (warp-uniform) the previous expert tile's dW is leaving through the dz ring: its staging must have been read
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        drain_pending = false;
+      }
       const uint32_t dzrow = sbase + OFF_DZ + s * DZ_BYTES + (cb >> 1) * CHUNK + jl * 128;
       const int unit0 = 4 * (cb & 1);
       const uint32_t kx = (uint32_t)(unit0 ^ (jl & 7));
@@ -335,40 +344,39 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
         tmem_ld32(tmem + lane_base + TM_DW + cb * 32, v);
         tc_fence_before();
         mbar_arrive(bar(BAR_DW_EMPTY));
-        // staging (the 64 KB of the dz ring): [128 experts][32 x 16-byte units], units XOR-swizzled by row -> coalesced 512-byte rows out
-        float4* stage = reinterpret_cast<float4*>(sgen + OFF_DZ);
+        // staging (the 64 KB of the dz ring) as four TMA boxes: chunk cb = columns [32cb, 32cb+32) of the tile, [128 experts][128 B], 128-byte
+        // swizzled.  One thread then hands the tile to the TMA unit -- a plain tensor store when this CTA ran the whole expert tile, a
+        // reduce-add into zeroed rows when two CTAs share it (two contributions: order-independent) -- and the warps go straight on to the
+        // next expert tile; rows past E are clipped by the tensor map.
+        uint8_t* srow = sgen + OFF_DZ + cb * CHUNK + jl * 128;
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          stage[jl * 32 + ((cb * 8 + q) ^ (jl & 31))] = make_float4(v[4 * q] * g.scale, v[4 * q + 1] * g.scale, v[4 * q + 2] * g.scale, v[4 * q + 3] * g.scale);
+          *reinterpret_cast<float4*>(srow + ((q ^ (jl & 7)) << 4)) = make_float4(v[4 * q] * g.scale, v[4 * q + 1] * g.scale, v[4 * q + 2] * g.scale, v[4 * q + 3] * g.scale);
         float* dbsum = reinterpret_cast<float*>(sgen + OFF_DBS);  // [4][128] db partials of the four team blocks, combined in a fixed order
         dbsum[cb * TE + jl] = db_acc;
+        fence_proxy_async();
         asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < TE / EPI_WARPS; ++i) {
-          const int r = warp * (TE / EPI_WARPS) + i;
-          if (e0 + r < g.E) {
-            if (whole) {
-              *reinterpret_cast<float4*>(g.dW + (size_t)(e0 + r) * HK + 4 * lane) = stage[r * 32 + (lane ^ (r & 31))];
-            } else {
-              // a cut tile: partial sums into zeroed rows.  Lane = consecutive floats (128 bytes per instruction): the L2 reduction units take
-              // coalesced scalar adds at ~5 TB/s chip-wide, 16-byte-strided ones at an eighth of that (scripts/mb/mb_reduce.cu)
-              const float* srow = reinterpret_cast<const float*>(stage + r * 32);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int col = q * 32 + lane;
-                atomicAdd(g.dW + (size_t)(e0 + r) * HK + col, srow[(((col >> 2) ^ (r & 31)) << 2) + (col & 3)]);
-              }
-            }
+          for (int c = 0; c < 4; ++c) {
+            if (whole)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                           ::"l"(reinterpret_cast<uint64_t>(&map_dw)), "r"(c * 32), "r"(e0), "r"(sbase + OFF_DZ + c * CHUNK) : "memory");
+            else
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                           ::"l"(reinterpret_cast<uint64_t>(&map_dw)), "r"(c * 32), "r"(e0), "r"(sbase + OFF_DZ + c * CHUNK) : "memory");
           }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (cb == 0 && e_ok) {
           const float dbv = (((dbsum[jl] + dbsum[TE + jl]) + dbsum[2 * TE + jl]) + dbsum[3 * TE + jl]) * g.scale;
           if (whole) g.db[e] = dbv; else atomicAdd(g.db + e, dbv);
         }
-        asm volatile("bar.sync 1, 512;" ::: "memory");  // staging and db scratch are free again before anyone writes the next tile's dz
+        drain_pending = true;  // the TMA unit is still reading the staging: see the first dz write of the next expert tile
         if (g.timing && threadIdx.x == 0 && n < 60) g.timing[TSLOTS * blockIdx.x + 8 + 8 * n + 3] = clock64();
       }
     }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the last tile has left
     // one loss partial per CTA: fixed-order combine (shuffle tree, then warps in order)
     float* red = reinterpret_cast<float*>(sgen + OFF_BAR + NUM_BARS * 8 + 16);  // [16]
     const float tot = warp_sum(loss_total);
@@ -431,13 +439,16 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
 
 // ---- sparse correction pass: the (team, expert) pairs that are NOT (target 0, weight tnw) -----------------------------------------------
 // fnn.py:33-43: a team's members carry target 1 and weight tpw, its sampled negatives target 0 (unless they are members) and weight tpw.
-// One warp per team: the candidates (members, then negatives; duplicates and -1 dropped; experts outside this shard skipped) are handled
-// one after the other by the whole warp -- z = a.w + b from the SAME fp16 operand images the tensor-core pass read (fp32 accumulation),
-// then the difference between what the pair should contribute and what the dense pass already contributed for it:
+// One CTA per team, one warp per candidate (members, then negatives; duplicates and -1 dropped; experts outside this shard skipped), all
+// candidates of a team in flight at once (the pass is latency-bound: a handful of dependent global loads per candidate).  A warp computes
+// z = a.w + b from the SAME fp16 operand images the tensor-core pass read (fp32 accumulation), then the difference between what the pair
+// should contribute and what the dense pass already contributed for it:
 //   loss += tpw*bce(x, y) - tnw*softplus(x);  dg = fp16(g_true) - fp16(g_dense)  (the dense pass fed fp16(g_dense) to its products)
 //   dW[e,:] += scale*dg*a16[n,:]  (atomic: several teams may hit one expert);  db[e] += scale*(g_true - g_dense);
-//   dA[n,:] += scale*dg*w16[e,:]  (accumulated in registers, one read-modify-write per team: this warp owns the row)
-// Runs after out_tc2_kernel on the same stream.
+//   dA[n,:] += scale*dg*w16[e,:]  (summed over the team's candidates in shared memory, fixed order; the CTA owns the row)
+// The CTA then finishes its row: dA + corrections, or -- fused ntf_act_bwd of the layer below -- dz_prev = that times lrelu'(act_prev).
+// The loss partials of both passes (and, when fused, the column sums of dz_prev) are added up by out_tail_kernel -- they gate nothing but
+// the optimiser, so ntf_fnn_step runs that kernel on a side stream.  Runs after out_tc2_kernel.
 struct FixArgs {
   const __half* A16;   // [B,128]
   const __half* W16;   // [E,128]
@@ -447,86 +458,168 @@ struct FixArgs {
   int B, E, e_lo;
   float tpw, tnw, scale;
   float* dW; float* db; float* dA;  // NULL on a validation step
-  float* loss_part;                   // [gridDim.x] this pass's loss partials (summed with the dense pass's by ntf_loss_reduce)
+  float* loss_part;                   // [n_dense + B]: the dense pass's loss partials, then one per team
+  int n_dense;
+  const float* act_prev; float* dz_prev;  // optional fusion of ntf_act_bwd for the layer below (ntf_out_train_args.act_prev)
+  int exp;                                // debug (NTF_FIX_EXP): 1 = no dW / db atomics, 2 = no loss finalisation, 4 = no candidate work at all
 };
 constexpr int FIX_WARPS = 8;
 
 __global__ void __launch_bounds__(FIX_WARPS * 32) out_fix_kernel(FixArgs g) {
-  __shared__ float red[FIX_WARPS];
+  __shared__ float sd[FIX_WARPS][HK];
+  __shared__ float sloss[FIX_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * FIX_WARPS + warp;
+  const int n = blockIdx.x;
   constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-  float loss = 0.f;
-  if (n < g.B) {
-    const bool train = g.dW != nullptr;
-    const int mb = g.m_indptr[n], me = g.m_indptr[n + 1], nm = me - mb;
-    // this lane's slice of the team's activations: hidden units lane, lane+32, lane+64, lane+96 (coalesced 64-byte loads / 128-byte adds)
-    float a[4], dacc[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool train = g.dW != nullptr;
+  // the row this CTA finishes at the end: in flight while the candidates are worked on
+  float row0 = 0.f, rslope = 1.f;
+  if (train && threadIdx.x < HK) {
+    row0 = g.dA[(size_t)n * HK + threadIdx.x];
+    if (g.dz_prev) rslope = g.act_prev[(size_t)n * HK + threadIdx.x] > 0.f ? 1.f : NTF_LRELU_SLOPE;
+  }
+  const int mb = g.m_indptr[n], me = g.m_indptr[n + 1], nm = me - mb;
+  // this lane's slice of the team's activations: hidden units lane, lane+32, lane+64, lane+96 (coalesced 64-byte loads / 128-byte adds)
+  float a[4], dacc[4] = {0.f, 0.f, 0.f, 0.f}, loss = 0.f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) a[q] = __half2float(g.A16[(size_t)n * HK + q * 32 + lane]);
-    const int ncand = nm + g.ns;
-    for (int c0 = 0; c0 < ncand; c0 += 32) {
-      // candidate c0 + lane: a member (ascending, unique) or a negative; a negative is dropped if it is -1, a member, or a repeat of an earlier negative
-      const int c = c0 + lane;
-      int e = -1;
-      bool member = false;
-      if (c < nm) { e = g.m_indices[mb + c]; member = true; }
-      else if (c < ncand) {
-        e = g.neg[(size_t)n * g.ns + (c - nm)];
-        if (e >= 0) {
-          for (int p = mb; p < me; ++p) if (g.m_indices[p] == e) { e = -1; break; }
-          for (int p = 0; p < c - nm && e >= 0; ++p) if (g.neg[(size_t)n * g.ns + p] == e) e = -1;
-        }
-      }
-      const int el = e - g.e_lo;  // column of this shard
-      unsigned todo = __ballot_sync(0xffffffffu, e >= 0 && el >= 0 && el < g.E);
-      while (todo) {
-        const int L = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int j = __shfl_sync(0xffffffffu, el, L);
-        const bool y = __shfl_sync(0xffffffffu, (int)member, L) != 0;
-        float w[4], dot = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { w[q] = __half2float(g.W16[(size_t)j * HK + q * 32 + lane]); dot = fmaf(a[q], w[q], dot); }
-        dot = warp_sum(dot);
-        const float zz = dot + __ldg(g.bias + j);
-        const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
-        const float slope = zz > 0.f ? 1.f : NTF_LRELU_SLOPE;
-        // what the dense pass computed for this pair (its formulas: t = -log2e*x, e = 2^t, sigmoid = 1/(1+e), softplus = (lg2(1+e) - t)*ln2)
-        const float tt = -LOG2E * x;
-        const float dens = 1.f + ex2_approx(tt);
-        const float g_dense = g.tnw * slope * rcp_approx(dens);
-        const float l_dense = g.tnw * LN2 * (lg2_approx(dens) - tt);
-        // what it should contribute (stable form)
-        const float ex = ex2_approx(fabsf(x) * -LOG2E), den = 1.f + ex, r = rcp_approx(den);
-        const float sig = x > 0.f ? r : ex * r, yf = y ? 1.f : 0.f;
-        const float g_true = g.tpw * (sig - yf) * slope;
-        const float l_true = g.tpw * ((1.f - yf) * x + fmaxf(-x, 0.f) + LN2 * lg2_approx(den));
-        loss += l_true - l_dense;  // (the same value in every lane; lane 0's copy is used)
-        if (train) {
-          const float dg = (__half2float(__float2half_rn(g_true)) - __half2float(__float2half_rn(g_dense))) * g.scale;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            atomicAdd(g.dW + (size_t)j * HK + q * 32 + lane, dg * a[q]);
-            dacc[q] = fmaf(dg, w[q], dacc[q]);
-          }
-          if (lane == 0) atomicAdd(g.db + j, (g_true - g_dense) * g.scale);
-        }
-      }
+  for (int q = 0; q < 4; ++q) a[q] = __half2float(g.A16[(size_t)n * HK + q * 32 + lane]);
+  const int ncand = nm + g.ns;
+  int kth = 0;  // running index of the valid candidates: warp w takes those with kth % FIX_WARPS == w
+  for (int c0 = 0; c0 < ncand; c0 += 32) {
+    // candidate c0 + lane (the same in every warp): a member (ascending, unique) or a negative; a negative is dropped if it is -1, a member,
+    // or a repeat of an earlier negative
+    const int c = c0 + lane;
+    int e = -1;
+    bool member = false;
+    if (c < nm) { e = g.m_indices[mb + c]; member = true; }
+    else if (c < ncand) e = g.neg[(size_t)n * g.ns + (c - nm)];
+    const unsigned same = __match_any_sync(0xffffffffu, e);  // duplicates inside this group: the lowest lane keeps the value (members sit lowest)
+    if (e >= 0 && (same & ((1u << lane) - 1u)) != 0u) e = -1;
+    if (c0 > 0 && e >= 0) {  // (more than 32 candidates: rare) also against the earlier groups, from memory
+      for (int p = mb; p < me && p - mb < c0; ++p) if (g.m_indices[p] == e) { e = -1; break; }
+      for (int p = max(0, c0 - nm) - 1; p >= 0 && e >= 0; --p) if (g.neg[(size_t)n * g.ns + p] == e) e = -1;
     }
-    if (train) {
+    const int el = e - g.e_lo;  // column of this shard
+    unsigned todo = __ballot_sync(0xffffffffu, e >= 0 && el >= 0 && el < g.E);
+    if (g.exp & 4) todo = 0u;
+    while (todo) {
+      const int L = __ffs(todo) - 1;
+      todo &= todo - 1;
+      if ((kth++ % FIX_WARPS) != warp) continue;
+      const int j = __shfl_sync(0xffffffffu, el, L);
+      const bool y = __shfl_sync(0xffffffffu, (int)member, L) != 0;
+      float w[4], dot = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) g.dA[(size_t)n * HK + q * 32 + lane] += dacc[q];
+      for (int q = 0; q < 4; ++q) { w[q] = __half2float(g.W16[(size_t)j * HK + q * 32 + lane]); dot = fmaf(a[q], w[q], dot); }
+      const float bj = __ldg(g.bias + j);
+      dot = warp_sum(dot);
+      const float zz = dot + bj;
+      const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);
+      const float slope = zz > 0.f ? 1.f : NTF_LRELU_SLOPE;
+      // what the dense pass computed for this pair (its formulas: t = -log2e*x, e = 2^t, sigmoid = 1/(1+e), softplus = (lg2(1+e) - t)*ln2)
+      const float tt = -LOG2E * x;
+      const float dens = 1.f + ex2_approx(tt);
+      const float g_dense = g.tnw * slope * rcp_approx(dens);
+      const float l_dense = g.tnw * LN2 * (lg2_approx(dens) - tt);
+      // what it should contribute (stable form)
+      const float ex = ex2_approx(fabsf(x) * -LOG2E), den = 1.f + ex, r = rcp_approx(den);
+      const float sig = x > 0.f ? r : ex * r, yf = y ? 1.f : 0.f;
+      const float g_true = g.tpw * (sig - yf) * slope;
+      const float l_true = g.tpw * ((1.f - yf) * x + fmaxf(-x, 0.f) + LN2 * lg2_approx(den));
+      loss += l_true - l_dense;  // (the same value in every lane; lane 0's copy is used)
+      if (train) {
+        const float dg = (__half2float(__float2half_rn(g_true)) - __half2float(__float2half_rn(g_dense))) * g.scale;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (!(g.exp & 1)) atomicAdd(g.dW + (size_t)j * HK + q * 32 + lane, dg * a[q]);
+          dacc[q] = fmaf(dg, w[q], dacc[q]);
+        }
+        if (lane == 0 && !(g.exp & 1)) atomicAdd(g.db + j, (g_true - g_dense) * g.scale);
+      }
     }
   }
-  if (lane == 0) red[warp] = loss;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) sd[warp][q * 32 + lane] = dacc[q];
+  if (lane == 0) sloss[warp] = loss;
   __syncthreads();
+  if (train && threadIdx.x < HK) {
+    float d = row0;
+#pragma unroll
+    for (int q = 0; q < FIX_WARPS; ++q) d += sd[q][threadIdx.x];
+    if (g.dz_prev) g.dz_prev[(size_t)n * HK + threadIdx.x] = d * rslope;  // the layer below's activation derivative (fnn.py:25 lrelu), fused
+    else g.dA[(size_t)n * HK + threadIdx.x] = d;
+  }
   if (threadIdx.x == 0) {
     float l = 0.f;
 #pragma unroll
-    for (int q = 0; q < FIX_WARPS; ++q) l += red[q];
-    g.loss_part[blockIdx.x] = l;
+    for (int q = 0; q < FIX_WARPS; ++q) l += sloss[q];
+    g.loss_part[g.n_dense + n] = l;
   }
+}
+
+// final reductions of a call, fixed order (deterministic): loss_out = scale * (sum of the loss partials of both passes) and, after the fused
+// activation backward, db_prev = colsum(dz_prev): 8 teams per CTA -> per-CTA column partials -> the last CTA to finish adds them in CTA
+// order (thread = 4 columns x one of 8 interleaved slices of the CTAs: 16-byte loads, four independent chains, then the slices in order)
+constexpr int TAIL_ROWS = 8;
+__global__ void __launch_bounds__(256) out_tail_kernel(const float* __restrict__ dz, int B, float* __restrict__ col_part, float* __restrict__ db_prev,
+                                                       const float* __restrict__ loss_part, int n_loss, float scale, float* __restrict__ loss_out,
+                                                       unsigned* __restrict__ done) {
+  __shared__ float cs[8][HK];
+  __shared__ double dred[256];
+  __shared__ int last_s;
+  if (dz) {
+    const int c = threadIdx.x & (HK - 1), half = threadIdx.x >> 7;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < TAIL_ROWS / 2; ++i) {
+      const int r = blockIdx.x * TAIL_ROWS + half * (TAIL_ROWS / 2) + i;
+      if (r < B) s += dz[(size_t)r * HK + c];
+    }
+    cs[half][c] = s;
+    __syncthreads();
+    if (threadIdx.x < HK) col_part[(size_t)blockIdx.x * HK + threadIdx.x] = cs[0][threadIdx.x] + cs[1][threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last_s = (atomicAdd(done, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence();
+    const int cg = threadIdx.x & 31, sl8 = threadIdx.x >> 5, nb = (int)gridDim.x;
+    const float4* cp = reinterpret_cast<const float4*>(col_part);
+    float4 acc[4] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    for (int b0 = sl8; b0 < nb; b0 += 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int b = b0 + 8 * u;
+        if (b < nb) {
+          const float4 v = __ldcg(cp + (size_t)b * (HK / 4) + cg);
+          acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+        }
+      }
+    }
+    const float4 t = make_float4((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
+                                 (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
+    __syncthreads();
+    reinterpret_cast<float4*>(&cs[sl8][0])[cg] = t;
+    __syncthreads();
+    if (threadIdx.x < HK) {
+      float c = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) c += cs[q][threadIdx.x];
+      db_prev[threadIdx.x] = c;
+    }
+    if (threadIdx.x == 0) *done = 0u;
+  }
+  // (one CTA gets here: the last one, or the only one when there are no column sums to take)
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_loss; i += 256) acc += (double)__ldcg(loss_part + i);
+  dred[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_out[0] = (float)(dred[0] * (double)scale);
 }
 
 __global__ void to_half_kernel2(const float* __restrict__ x, size_t n, __half* __restrict__ y) {
@@ -535,10 +628,35 @@ __global__ void to_half_kernel2(const float* __restrict__ x, size_t n, __half* _
 }  // namespace
 
 // workspace: fp16 A | loss partials | fp16 W image (when the caller keeps none)
-static size_t tc2_loss_slots(int B) { return (size_t)1024 + (size_t)cdiv(B, FIX_WARPS) + 8; }  // dense pass: one per CTA; correction pass: one per block
-size_t ntf_out_train_tc2_workspace_bytes(int B, int h, int E) {
-  return align_up((size_t)B * h * sizeof(__half), 256) + align_up(tc2_loss_slots(B) * sizeof(float), 1024) + align_up((size_t)E * h * sizeof(__half), 1024);
+// workspace: fp16 A | loss partials (dense pass: one per CTA; correction pass: one per block) + block counter | column-sum partials | fp16 W image
+static size_t tc2_loss_slots(int B) { return (size_t)1024 + (size_t)B + 8; }  // dense pass: one per CTA; correction pass: one per team; 2 counters
+static size_t tc2_off_loss(int B, int h) { return align_up((size_t)B * h * sizeof(__half), 256); }
+static size_t tc2_off_col(int B, int h) { return tc2_off_loss(B, h) + align_up(tc2_loss_slots(B) * sizeof(float), 1024); }
+static size_t tc2_off_w16(int B, int h) { return tc2_off_col(B, h) + align_up((size_t)cdiv(B, TAIL_ROWS) * HK * sizeof(float), 1024); }
+size_t ntf_out_train_tc2_workspace_bytes(int B, int h, int E) { return tc2_off_w16(B, h) + align_up((size_t)E * h * sizeof(__half), 1024); }
+
+static void tc2_plan(const ntf_ctx* ctx, int B, int E, Tc2Args* g, int* grid) {
+  g->nct = cdiv(E, TE); g->nbt = cdiv(B, TB);
+  const int sm = ctx->sm_count > 0 ? ctx->sm_count : 148;
+  if (g->nct >= sm) { g->split = 0; *grid = sm; return; }
+  int s = sm / g->nct;
+  if (s > g->nbt) s = g->nbt;
+  if (s < 1) s = 1;
+  g->split = s; *grid = g->nct * s;
 }
+
+extern "C" int ntf_out_train_prepare(ntf_ctx* ctx, void* stream, int B, int h, int E, float* dW, float* db, float* dA) {
+  NTF_REQUIRE(ctx && dW && db && dA && h == HK && B > 0 && E > 0, NTF_ERR_BAD_ARG, "out_train_prepare: bad argument");
+  cudaStream_t st = as_stream(stream);
+  NTF_CUDA(cudaMemsetAsync(dA, 0, (size_t)B * h * sizeof(float), st));
+  Tc2Args g{};
+  g.B = B; g.E = E; g.dW = dW; g.db = db;
+  int grid;
+  tc2_plan(ctx, B, E, &g, &grid);
+  if (g.split != 1) { NTF_COUNT_LAUNCH; zero_cut_tiles_kernel<<<grid, 256, 0, st>>>(g); NTF_LAUNCH_CHECK(); }
+  return NTF_OK;
+}
+
 
 int ntf_out_train_tc2(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a, void* workspace, size_t workspace_bytes) {
   NTF_REQUIRE(a->h == HK, NTF_ERR_UNSUPPORTED, "out_train(tf32): hidden width %d (kernel is built for %d)", a->h, HK);
@@ -554,11 +672,15 @@ int ntf_out_train_tc2(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a
   NTF_REQUIRE(a->m_indptr && a->m_indices, NTF_ERR_BAD_ARG, "out_train(tf32): the member CSR is missing");
   char* ws = (char*)workspace;
   __half* A16 = a->A16 ? (__half*)const_cast<void*>(a->A16) : (__half*)ws;
-  float* loss_part = (float*)(ws + align_up((size_t)a->B * a->h * sizeof(__half), 256));
+  float* loss_part = (float*)(ws + tc2_off_loss(a->B, a->h));
+  unsigned* done = (unsigned*)(loss_part + tc2_loss_slots(a->B) - 2);  // (zeroed once per context below; the kernel leaves it zero)
   const __half* W16 = (const __half*)a->W16;
+  NTF_REQUIRE((a->act_prev != nullptr) == (a->dz_prev != nullptr) && (a->act_prev != nullptr) == (a->db_prev != nullptr), NTF_ERR_BAD_ARG,
+              "out_train(tf32): act_prev, dz_prev and db_prev come together");
+  NTF_REQUIRE(!a->act_prev || train, NTF_ERR_BAD_ARG, "out_train(tf32): the fused activation backward needs a training step");
   const int blocks_h = ctx->sm_count * 8;
   if (!W16) {  // no image kept by the caller: made here (one pass over W: 6 bytes per weight)
-    __half* w = (__half*)(ws + align_up((size_t)a->B * a->h * sizeof(__half), 256) + align_up(tc2_loss_slots(a->B) * sizeof(float), 1024));
+    __half* w = (__half*)(ws + tc2_off_w16(a->B, a->h));
     const size_t nw = (size_t)a->E * HK;
     NTF_COUNT_LAUNCH; to_half_kernel2<<<(unsigned)(cdiv((int)((nw + 255) / 256), 1) < blocks_h ? (nw + 255) / 256 : blocks_h), 256, 0, st>>>(a->W, nw, w);
     NTF_LAUNCH_CHECK();
@@ -570,40 +692,52 @@ int ntf_out_train_tc2(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a
     NTF_COUNT_LAUNCH; to_half_kernel2<<<(unsigned)((na + 255) / 256 < (size_t)blocks_h ? (na + 255) / 256 : blocks_h), 256, 0, st>>>(a->A, na, A16);
     NTF_LAUNCH_CHECK();
   }
-  CUtensorMap mw, mh;
+  CUtensorMap mw, mh, mdw;
   int rc;
   if ((rc = make_map(ctx, &mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, W16, (uint64_t)a->E, HK, TE, 64))) return rc;
   if ((rc = make_map(ctx, &mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A16, (uint64_t)a->B, HK, TB, 64))) return rc;
-  if (train) NTF_CUDA(cudaMemsetAsync(a->dA, 0, (size_t)a->B * a->h * sizeof(float), st));
+  if ((rc = make_map(ctx, &mdw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, train ? (const void*)a->dW : (const void*)a->W, (uint64_t)a->E, HK, TE, 32))) return rc;
+  if (train && !a->prepared) NTF_CUDA(cudaMemsetAsync(a->dA, 0, (size_t)a->B * a->h * sizeof(float), st));
   Tc2Args g{};
   g.bias = a->b;
   g.B = a->B; g.E = a->E; g.tpw = a->tpw; g.tnw = a->tnw; g.scale = a->loss_scale;
-  g.dW = a->dW; g.db = a->db; g.dA = a->dA; g.loss_part = loss_part;
-  g.nct = cdiv(a->E, TE); g.nbt = cdiv(a->B, TB);
+  g.dW = a->dW; g.db = a->db; g.dA = a->dA; g.loss_part = loss_part; g.done = done;
   const char* dbg = getenv("NTF_TC_ZDBG");
   g.Zdbg = dbg ? (float*)(uintptr_t)strtoull(dbg, nullptr, 0) : nullptr;
   const char* tim = getenv("NTF_TC_TIMING");
   g.timing = tim ? (long long*)(uintptr_t)strtoull(tim, nullptr, 0) : nullptr;
-  const int sm = ctx->sm_count > 0 ? ctx->sm_count : 148;
   int grid;
-  if (g.nct >= sm) { g.split = 0; grid = sm; }
-  else {
-    int s = sm / g.nct;
-    if (s > g.nbt) s = g.nbt;
-    if (s < 1) s = 1;
-    g.split = s; grid = g.nct * s;
-  }
+  tc2_plan(ctx, a->B, a->E, &g, &grid);
   NTF_REQUIRE(grid <= 1024, NTF_ERR_UNSUPPORTED, "out_train(tf32): %d CTAs", grid);
-  if (train && !(g.split == 1)) { NTF_COUNT_LAUNCH; zero_cut_tiles_kernel<<<grid, 256, 0, st>>>(g); NTF_LAUNCH_CHECK(); }
+  if (train && !a->prepared && g.split != 1) { NTF_COUNT_LAUNCH; zero_cut_tiles_kernel<<<grid, 256, 0, st>>>(g); NTF_LAUNCH_CHECK(); }
   NTF_CUDA(cudaFuncSetAttribute(out_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  NTF_COUNT_LAUNCH; out_tc2_kernel<<<grid, NT, SMEM_BYTES, st>>>(mw, mh, g);
+  NTF_COUNT_LAUNCH; out_tc2_kernel<<<grid, NT, SMEM_BYTES, st>>>(mw, mh, mdw, g);
   NTF_LAUNCH_CHECK();
   FixArgs f{};
   f.A16 = A16; f.W16 = W16; f.bias = a->b; f.m_indptr = a->m_indptr; f.m_indices = a->m_indices; f.neg = a->neg; f.ns = a->neg ? a->ns : 0;
   f.B = a->B; f.E = a->E; f.e_lo = a->e_lo; f.tpw = a->tpw; f.tnw = a->tnw; f.scale = a->loss_scale;
-  f.dW = a->dW; f.db = a->db; f.dA = a->dA; f.loss_part = loss_part + grid;
-  const int fix_blocks = cdiv(a->B, FIX_WARPS);
-  NTF_COUNT_LAUNCH; out_fix_kernel<<<fix_blocks, FIX_WARPS * 32, 0, st>>>(f);
+  f.dW = a->dW; f.db = a->db; f.dA = a->dA; f.loss_part = loss_part; f.n_dense = grid;
+  f.act_prev = a->act_prev; f.dz_prev = a->dz_prev;
+  { const char* fx = getenv("NTF_FIX_EXP"); f.exp = fx ? atoi(fx) : 0; }
+  NTF_COUNT_LAUNCH; out_fix_kernel<<<a->B, FIX_WARPS * 32, 0, st>>>(f);
   NTF_LAUNCH_CHECK();
-  return ntf_loss_reduce_impl(st, loss_part, grid + fix_blocks, a->loss_scale, a->loss_out);
+  if (a->defer_finish) return NTF_OK;
+  return ntf_out_train_finish(ctx, (void*)st, a, workspace, workspace_bytes);
+}
+
+// the call's final reductions (out_tail_kernel); see ntf_out_train_args.defer_finish
+extern "C" int ntf_out_train_finish(ntf_ctx* ctx, void* stream, const ntf_out_train_args* a, void* workspace, size_t workspace_bytes) {
+  NTF_REQUIRE(ctx && a && workspace && workspace_bytes >= ntf_out_train_tc2_workspace_bytes(a->B, a->h, a->E), NTF_ERR_BAD_ARG, "out_train_finish: bad argument");
+  char* ws = (char*)workspace;
+  float* loss_part = (float*)(ws + tc2_off_loss(a->B, a->h));
+  unsigned* done = (unsigned*)(loss_part + tc2_loss_slots(a->B) - 2);
+  Tc2Args g{};
+  int grid;
+  tc2_plan(ctx, a->B, a->E, &g, &grid);
+  const bool fused = a->dz_prev != nullptr;
+  NTF_COUNT_LAUNCH;
+  out_tail_kernel<<<fused ? cdiv(a->B, TAIL_ROWS) : 1, 256, 0, as_stream(stream)>>>(fused ? a->dz_prev : nullptr, a->B, (float*)(ws + tc2_off_col(a->B, a->h)), a->db_prev,
+                                                                                   loss_part, grid + a->B, a->loss_scale, a->loss_out, done);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
 }

@@ -62,13 +62,26 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
   void* ws_main = (char*)workspace + ws_bag_bytes;
   const size_t ws_main_bytes = workspace_bytes - ws_bag_bytes;
   const bool bwd_here = a->train && (phase & 2);
+  // tensor-core Fnn output layer = the persistent kernel + sparse correction pass of out_tc2.cu (NTF_TC_V1=1: round 1's kernel, bit planes)
+  const bool tc2 = a->precision == NTF_TF32 && getenv("NTF_TC_V1") == nullptr;
+  const bool shard_x = a->peers != nullptr && a->E < Etot;  // expert shard with a peer table: dA is exchanged inside the step
+  float* dA_out = shard_x ? a->peers->grads[a->peers->rank] : a->dact[Lo - 1];
+  // one hidden layer, nothing between the output layer's dA and layer 0's activation derivative: the correction pass finishes it (no ntf_act_bwd)
+  const bool act_fused = tc2 && Lo == 1 && a->train && phase == 3 && !shard_x;
+  ntf_out_train_args o;  // the output layer's call; its final reductions may run later, off the critical path (finish_pending)
+  memset(&o, 0, sizeof(o));
+  bool finish_pending = false, finish_side = false;
   int rc;
 #define STEP(call) do { if ((rc = (call)) != NTF_OK) return rc; } while (0)
   // ---- fork: what needs the batch's CSR only ----
   if ((phase & 1) || bwd_here) NTF_CUDA(cudaEventRecord(ctx->ev_fork, st));
-  if (bwd_here && !a->x_dense) {  // side 1: every (team, skill) entry takes a slot of its skill (pass 1 of the input layer's backward)
+  const bool prep = bwd_here && tc2 && (phase & 1);
+  if (bwd_here && (!a->x_dense || prep)) {
     NTF_CUDA(cudaStreamWaitEvent(ctx->side[1], ctx->ev_fork, 0));
-    STEP(ntf_csr_bag_bwd_fill_impl(ctx, ctx->side[1], B, a->s_indptr, a->s_indices, a->s_ent_row, a->row_base, a->S, h[0], ws_bag, ws_bag_bytes, nullptr));
+    // side 1: what the output layer's kernel needs cleared (dA, the dW / db rows two CTAs share) -- off the critical path
+    if (prep) STEP(ntf_out_train_prepare(ctx, (void*)ctx->side[1], B, h[Lo - 1], a->E, a->gW[Lo], a->gb[Lo], dA_out));
+    // ... and every (team, skill) entry takes a slot of its skill (pass 1 of the input layer's backward)
+    if (!a->x_dense) STEP(ntf_csr_bag_bwd_fill_impl(ctx, ctx->side[1], B, a->s_indptr, a->s_indices, a->s_ent_row, a->row_base, a->S, h[0], ws_bag, ws_bag_bytes, nullptr));
     NTF_CUDA(cudaEventRecord(ctx->ev_join[1], ctx->side[1]));
   }
   if (phase & 1) {
@@ -85,10 +98,14 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
                                a->neg, a->dyn));
       neg = a->neg; ns = a->ns;
     }
-    ntf_out_train_args o;
-    memset(&o, 0, sizeof(o));
-    if (tc && getenv("NTF_TC_V1") == nullptr) {
+    if (tc2) {
       o.neg = neg; o.ns = ns;  // persistent kernel + sparse correction pass (out_tc2.cu): the pairs of weight tpw are named by the lists themselves
+      o.prepared = prep ? 1 : 0;
+      if (act_fused) { o.act_prev = a->act[0]; o.dz_prev = a->dz[0]; o.db_prev = a->gb[0]; }
+      // loss_out / db_prev gate nothing but the optimiser: their reductions run next to the input layer's backward pass (side stream).  Only in
+      // the one-hidden-layer CSR configuration: there nothing else touches the main part of the workspace while they are pending
+      o.defer_finish = (bwd_here && a->run_adam && act_fused && !a->x_dense) ? 1 : 0;
+      finish_pending = o.defer_finish != 0;
     } else if (tc) {
       STEP(ntf_special_tiles(ctx, ctx->side[0], 1, B, a->m_indptr, a->m_indices, neg, ns, a->E, a->e_lo, a->special_t, a->member_t));
       o.special_t = a->special_t; o.member_t = a->member_t;
@@ -108,10 +125,10 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     o.m_indptr = a->m_indptr; o.m_indices = a->m_indices;
     o.B = B; o.h = h[Lo - 1]; o.E = a->E; o.e_lo = a->e_lo;
     o.tpw = a->tpw; o.tnw = a->tnw; o.loss_scale = a->loss_scale; o.loss_out = a->loss_out;
-    // expert-sharded layer with a peer table: this shard's dA goes to its peer-visible exchange block, the sum over shards into dact below
-    const bool shard_x = a->peers != nullptr && a->E < Etot;
-    if (a->train) { o.dW = a->gW[Lo]; o.db = a->gb[Lo]; o.dA = shard_x ? a->peers->grads[a->peers->rank] : a->dact[Lo - 1]; }
+    // (expert-sharded layer with a peer table: this shard's dA goes to its peer-visible exchange block, the sum over shards into dact below)
+    if (a->train) { o.dW = a->gW[Lo]; o.db = a->gb[Lo]; o.dA = dA_out; }
     NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
+    if (prep) NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[1], 0));
     // (inside a stream capture the pair becomes two external event-record nodes, re-recorded by every replay of the graph)
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (a->prof_ev[0]) NTF_CUDA(cudaStreamIsCapturing(st, &cap));
@@ -166,6 +183,11 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
       NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_ar[0], 0));
     } else
     NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork_opt, 0));
+    if (finish_pending) {
+      STEP(ntf_out_train_finish(ctx, (void*)ctx->side[0], &o, ws_main, ws_main_bytes));
+      NTF_CUDA(cudaEventRecord(ctx->ev_finish, ctx->side[0]));
+      finish_pending = false; finish_side = true;
+    }
     const bool sh_here = shadow && w_off >= opt_split;
     if (peers) {
       STEP(ntf_peer_exchange_adam_impl(ctx, ctx->side[0], a->peers, a->adam_m, a->adam_v, opt_split, a->n_params - opt_split, a->lr, a->beta1,
@@ -177,12 +199,13 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
                             sh_here ? w_off - opt_split : 0, sh_here ? w_n : 0));
     NTF_CUDA(cudaEventRecord(ctx->ev_join_opt, ctx->side[0]));
   }
+  if (finish_pending) { STEP(ntf_out_train_finish(ctx, stream, &o, ws_main, ws_main_bytes)); finish_pending = false; }  // (no side stream this step)
   // ---- backward through the hidden layers ----
   for (int i = Lo - 1; i > 0; --i) {
     STEP(ntf_act_bwd(ctx, stream, a->dact[i], a->act[i], B, h[i], 1, a->dz[i], a->gb[i], ws_main, ws_main_bytes));
     STEP(ntf_dense_bwd(ctx, stream, a->act[i - 1], a->W[i], a->dz[i], B, h[i - 1], h[i], a->gW[i], a->dact[i - 1], ws_main, ws_main_bytes));
   }
-  STEP(ntf_act_bwd(ctx, stream, a->dact[0], a->act[0], B, h[0], 1, a->dz[0], a->gb[0], ws_main, ws_main_bytes));
+  if (!act_fused) STEP(ntf_act_bwd(ctx, stream, a->dact[0], a->act[0], B, h[0], 1, a->dz[0], a->gb[0], ws_main, ws_main_bytes));
   if (a->x_dense) {  // dW0[h0,S] = dz0^T X; the input needs no gradient
     STEP(ntf_dense_bwd(ctx, stream, a->x_dense, a->W[0], a->dz[0], B, a->S, h[0], a->gW[0], nullptr, ws_main, ws_main_bytes));
   } else {
@@ -191,6 +214,7 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
                                      ctx->side[1]));  // (side 1 is idle since the slot fill: the hot skills' kernels go there)
   }
   // ---- optimiser: fnn.py:139 (skipped when the caller all-reduces the gradients first: data-parallel ranks) ----
+  if (finish_side) NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_finish, 0));  // the fused bias gradient of layer 0 is part of the segment stepped / exchanged next
   if (dp) {
     NTF_CUDA(cudaEventRecord(ctx->ev_bwd, st));
     NTF_CUDA(cudaStreamWaitEvent(ctx->comm_st, ctx->ev_bwd, 0));

@@ -138,6 +138,26 @@ def pack_host_batch(s_ptr, s_idx, m_ptr, m_idx, cap_s=None, cap_m=None):
     return torch.from_numpy(blk).pin_memory(), n, cap_s, cap_m
 
 
+class HostPacker:
+    """packs global batches of the HOST teamsvecs CSR into pinned blocks for `Engine.step_host` (ntf_pack_host_batch: a memcpy per row), two
+    blocks in rotation so that batch i+1 can be packed while batch i is on the GPU -- the loader side of the streaming entry point"""
+
+    def __init__(self, skill_csr, member_csr, n, cap_s, cap_m):
+        (self.sp, self.si, _), (self.mp, self.mi, _) = skill_csr, member_csr  # to_csr() triples: int32 indptr, indices
+        self.n, self.cap_s, self.cap_m = int(n), int(cap_s), int(cap_m)
+        self.words = 2 * (self.n + 1) + 2 * self.cap_s + self.cap_m
+        self.blocks = [torch.zeros(self.words, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.k = 0
+
+    def pack(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        assert len(rows) == self.n
+        blk = self.blocks[self.k]; self.k ^= 1
+        _lib.check(_lib.lib().ntf_pack_host_batch(rows.ctypes.data, self.n, self.sp.ctypes.data, self.si.ctypes.data, self.mp.ctypes.data, self.mi.ctypes.data,
+                                                  self.cap_s, self.cap_m, blk.data_ptr(), self.words), 'ntf_pack_host_batch')
+        return blk
+
+
 class Engine:
     def __init__(self, S, hidden, E, device, bayesian=False, precision='tf32', tpw=10.0, tnw=1.0, nsd='uniform', ns=5,
                  seed=0, max_batch=1000, shard=None, dense_input=False):
@@ -159,7 +179,6 @@ class Engine:
         # dense_input: teamsvecs['skill'] is a dense [N,d] matrix of skill embeddings (main.py:148-153, ntf.py:24): layer 0 is then
         # a dense layer in torch layout [h0,d] instead of the CSR bag over a transposed weight
         self.dense_input = bool(dense_input)
-        if self.dense_input and bayesian: raise NotImplementedError('Bnn on dense (embedded) skill input')
         self.bayesian, self.precision = bool(bayesian), PRECISION[precision]
         # 'tf32' selects the tcgen05 kernels where they exist for the shape; other shapes (toy sizes, odd widths) run the
         # CUDA-core fp32 kernels of the same library -- both are sm_100a code, neither is a fallback to another backend.
@@ -205,7 +224,7 @@ class Engine:
             self.nviews, off = {}, 0
             for i in range(self.L):
                 fin, fout = self.sizes[i], self.sizes[i + 1]
-                self.nviews[f'{i}.weight'] = (off, (fin, fout) if i == 0 else (fout, fin)); off += _round_up(fin * fout, ALIGN)
+                self.nviews[f'{i}.weight'] = (off, (fin, fout) if (i == 0 and not self.dense_input) else (fout, fin)); off += _round_up(fin * fout, ALIGN)
                 self.nviews[f'{i}.bias'] = (off, (fout,)); off += _round_up(fout, ALIGN)
             self.n_noise = off
 
@@ -238,7 +257,10 @@ class Engine:
             self.act_s = [torch.empty(B, h, dtype=f32, device=dev) for h in self.hidden]
             self.dact_s = [torch.empty(B, h, dtype=f32, device=dev) for h in self.hidden]
             self.dzs = [torch.empty(B, h, dtype=f32, device=dev) for h in self.hidden]
-            self.sign_in = [None] + [torch.zeros(B, _round_up(h, 32) // 32, dtype=torch.int32, device=dev) for h in self.hidden]
+            # (CSR input: the input signs of layer 0 exist only at the nnz positions, `ent_sign`; dense input: a [B, S] plane like the other layers')
+            self.sign_in = [torch.zeros(B, _round_up(self.S, 32) // 32, dtype=torch.int32, device=dev) if self.dense_input else None]
+            self.sign_in += [torch.zeros(B, _round_up(h, 32) // 32, dtype=torch.int32, device=dev) for h in self.hidden]
+            if self.dense_input: self.x_s = torch.empty(B, self.S, dtype=f32, device=dev)  # x * s_in of layer 0
             self.sign_out = [torch.zeros(B, _round_up(o, 32) // 32, dtype=torch.int32, device=dev) for o in self.sizes[1:]]
 
     def view(self, name, buf=None):
@@ -295,7 +317,7 @@ class Engine:
         else: self.skill = DeviceCSR(skill_mat, self.device)
         self.member = DeviceCSR(member_mat, self.device)
         assert self.skill.shape[1] == self.S and self.member.shape[1] == self.E_total and self.skill.shape[0] == self.member.shape[0]
-        if self.bayesian:  # Flipout input signs exist only at the nnz positions: one bit per CSR entry of a batch
+        if self.bayesian and not self.dense_input:  # Flipout input signs exist only at the nnz positions: one bit per CSR entry of a batch
             maxlen = int(np.diff(self.skill.host_indptr).max()) if self.skill.shape[0] else 1
             self._ent_sign_words(self.Bmax * max(1, maxlen))
         return self
@@ -649,18 +671,19 @@ class Engine:
         if noise_host is None:
             sid = 64 * self.rank  # signs are per team: ranks draw different ones; eps must be the same on every rank
             ops.fill_normal(self.seed, step, 0, self.n_noise, self.eps)
-            ops.fill_sign_bits(self.seed, step, 1 + sid, self.ent_sign.numel(), self.ent_sign)
+            if not self.dense_input: ops.fill_sign_bits(self.seed, step, 1 + sid, self.ent_sign.numel(), self.ent_sign)
             for i in range(self.L):
-                if i: ops.fill_sign_bits(self.seed, step, 1 + 2 * i + sid, B * self.sign_in[i].shape[1], self.sign_in[i])
+                if i or self.dense_input: ops.fill_sign_bits(self.seed, step, 1 + 2 * i + sid, B * self.sign_in[i].shape[1], self.sign_in[i])
                 ops.fill_sign_bits(self.seed, step, 2 + 2 * i + sid, B * self.sign_out[i].shape[1], self.sign_out[i])
             return
-        indptr = sp.s_indptr[b0:b0 + B + 1].cpu().numpy(); idx = sp.s_indices[int(indptr[0]):int(indptr[-1])].cpu().numpy()
+        if not self.dense_input:
+            indptr = sp.s_indptr[b0:b0 + B + 1].cpu().numpy(); idx = sp.s_indices[int(indptr[0]):int(indptr[-1])].cpu().numpy()
         for i, nz in enumerate(noise_host):
             ew = torch.as_tensor(nz['eps_w'], dtype=torch.float32)
-            self.nview(self.eps, f'{i}.weight').copy_((ew.t() if i == 0 else ew).contiguous())
+            self.nview(self.eps, f'{i}.weight').copy_((ew.t() if (i == 0 and not self.dense_input) else ew).contiguous())
             self.nview(self.eps, f'{i}.bias').copy_(torch.as_tensor(nz['eps_b'], dtype=torch.float32))
             s_in, s_out = np.asarray(nz['s_in']), np.asarray(nz['s_out'])
-            if i == 0:
+            if i == 0 and not self.dense_input:
                 rows = np.repeat(np.arange(B), np.diff(indptr))
                 self._ent_sign_words(len(idx))
                 packed = _pack_bits(s_in[rows, idx][None, :] < 0)[0]  # the input sign matters only where x = 1: one bit per CSR entry
@@ -680,9 +703,15 @@ class Engine:
 
     def _forward_hidden_bayes(self, sp, b0, B):
         h = self.hidden
-        ops.csr_bag_flipout_fwd(B, sp.s_indptr.data_ptr() + 4 * b0, sp.s_indices, self.ent_sign, self._pv(0, 'mu', 'weight'), self._pv(0, 'mu', 'bias'),
-                                self.nview(self.delta, '0.weight'), self.nview(self.delta, '0.bias'), self.sign_out[0], self.sign_out[0].shape[1],
-                                self.S, h[0], self.act[0])
+        if self.dense_input:  # ntf.py:24: embedded skills -- layer 0 is a dense Flipout layer like the hidden ones
+            x = sp.x[b0:b0 + B]
+            ops.apply_sign(x, self.sign_in[0], self.sign_in[0].shape[1], B, self.S, self.x_s)
+            ops.dense_flipout_fwd(x, self._pv(0, 'mu', 'weight'), self._pv(0, 'mu', 'bias'), self.x_s, self.nview(self.delta, '0.weight'),
+                                  self.nview(self.delta, '0.bias'), self.sign_out[0], self.sign_out[0].shape[1], B, self.S, h[0], 1, self.act[0], self.ws)
+        else:
+            ops.csr_bag_flipout_fwd(B, sp.s_indptr.data_ptr() + 4 * b0, sp.s_indices, self.ent_sign, self._pv(0, 'mu', 'weight'), self._pv(0, 'mu', 'bias'),
+                                    self.nview(self.delta, '0.weight'), self.nview(self.delta, '0.bias'), self.sign_out[0], self.sign_out[0].shape[1],
+                                    self.S, h[0], self.act[0])
         for i in range(1, self.L):  # A*s_in for the next layer (the output layer included)
             ops.apply_sign(self.act[i - 1], self.sign_in[i], self.sign_in[i].shape[1], B, h[i - 1], self.act_s[i - 1])
             if i == self.L - 1: break
@@ -699,7 +728,8 @@ class Engine:
                    and (self.world == 1 or not train or self.peers is not None))
         key = None
         if graphed:
-            key = ('bayes', sp.s_indptr.data_ptr(), sp.s_indices.data_ptr(), sp.s_ent_row.data_ptr(), sp.m_indptr.data_ptr(), sp.m_indices.data_ptr(),
+            skey = (sp.x.data_ptr(),) if self.dense_input else (sp.s_indptr.data_ptr(), sp.s_indices.data_ptr(), sp.s_ent_row.data_ptr())
+            key = ('bayes',) + skey + (sp.m_indptr.data_ptr(), sp.m_indices.data_ptr(),
                    b0, B, bool(train), loss_slot, loss_scale, gbatch, self.loss_buf.data_ptr(), id(self.peers))
             graphed = key in self._graphs or len(self._graphs) < self.max_graphs
         if not graphed:
@@ -775,9 +805,13 @@ class Engine:
                           self.dact[j - 1], self.ws)
             ops.dense_bwd(self.act_s[j - 1], self.nview(self.delta, f'{j}.weight'), self.dzs[j], B, h[j - 1], h[j], self.nview(self.gdelta, f'{j}.weight'),
                           self.dact_s[j - 1], self.ws)
-        sptr = sp.s_indptr.data_ptr() + 4 * b0
-        ops.csr_bag_bwd(B, sptr, sp.s_indices, sp.s_ent_row, b0, self.dz[0], self.S, h[0], self._pv(0, 'mu', 'weight', self.grads), self.ws)
-        ops.csr_bag_bwd_signed(B, sptr, sp.s_indices, sp.s_ent_row, b0, self.ent_sign, self.dzs[0], self.S, h[0], self.nview(self.gdelta, '0.weight'), self.ws)
+        if self.dense_input:  # dW0 = dz0^T x, dW0_delta = (dz0*s_out)^T (x*s_in); the input needs no gradient
+            ops.dense_bwd(sp.x[b0:b0 + B], self._pv(0, 'mu', 'weight'), self.dz[0], B, self.S, h[0], self._pv(0, 'mu', 'weight', self.grads), None, self.ws)
+            ops.dense_bwd(self.x_s, self.nview(self.delta, '0.weight'), self.dzs[0], B, self.S, h[0], self.nview(self.gdelta, '0.weight'), None, self.ws)
+        else:
+            sptr = sp.s_indptr.data_ptr() + 4 * b0
+            ops.csr_bag_bwd(B, sptr, sp.s_indices, sp.s_ent_row, b0, self.dz[0], self.S, h[0], self._pv(0, 'mu', 'weight', self.grads), self.ws)
+            ops.csr_bag_bwd_signed(B, sptr, sp.s_indices, sp.s_ent_row, b0, self.ent_sign, self.dzs[0], self.S, h[0], self.nview(self.gdelta, '0.weight'), self.ws)
         for i in range(self.L):
             for what in ('weight', 'bias'):
                 mu, rho = self._pv(i, 'mu', what), self._pv(i, 'rho', what)
@@ -807,7 +841,7 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ streaming entry point (host batches)
-    def step_host(self, packed, n, cap_s, cap_m, rank=0, G=1, lr=1e-3, train=True):
+    def step_host(self, packed, n, cap_s, cap_m, rank=0, G=1, lr=1e-3, train=True, sync=True):
         """one step on a batch the HOST holds (`pack_host_batch`: compact CSR of the global batch in one pinned block): one H2D copy,
         this rank trains on its slice, and the loss comes back to the host (one sync) -- the per-step shape of the reference's loop
         (fnn.py:118-140: H2D of the batch, .item())."""
@@ -819,6 +853,11 @@ class Engine:
         b = -(-n // G)
         lo, hi = min(n, rank * b), min(n, (rank + 1) * b)
         self.step(st, lo, hi - lo, train, lr=lr, loss_slot=0, loss_scale=1.0 / n, gbatch=(0, n))
+        if not sync: return None  # (the caller overlaps host work -- packing the next batch -- and reads the loss with step_host_loss)
+        return float(self.loss_buf[0].item())
+
+    def step_host_loss(self):
+        """the loss of the last step_host(sync=False): the D2H read + sync of the streaming loop (fnn.py:140 `loss.item()`)"""
         return float(self.loss_buf[0].item())
 
     # ------------------------------------------------------------------ inference

@@ -1,0 +1,12 @@
+#!/bin/bash
+TAG=${1:-r2k}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+echo "== pytest tc/e2e"; timeout 1500 python -m pytest tests/test_gpu_tc.py tests/test_gpu_e2e.py tests/test_gpu_graph.py tests/test_gpu_shard.py -q -x --timeout=600 2>&1 | tail -5 | tee $OUT/tests.txt
+echo "== bench"; timeout 900 python bench.py --steps 300 --warmup 10 --no-cpu-baseline --no-extras 2>&1 | tail -1 | tee $OUT/bench.json | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print('value',d['value'],'ms/step',d['ms_per_step'],'e2e',d['e2e']['value'],'roof',d['roofline']['avg_launch_ms'],d['roofline']['frac'],'infer',d['infer_topk']['value'],d['clocks'])"
+echo "== ncu launch list (bench)"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras > $OUT/bench_under_ncu.log 2>&1
+python scripts/summarize_launches.py $OUT/launches.csv 2>&1 | tail -30 | head -16 | tee $OUT/launches_summary.txt
+echo "== ncu full (out_tc2_kernel, out_fix_kernel)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"out_tc2_kernel|out_fix_kernel" -s 2 -c 2 -o $OUT/prof_tc2 -f python scripts/tc2_timing.py > $OUT/ncu_tc2.log 2>&1
+ls -la $OUT
