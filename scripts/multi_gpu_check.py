@@ -48,7 +48,7 @@ for b in (8, 7):
     if rank == 0: print(f'--- b={b}: {n_train} train rows, last batch of {n_train % b or b}')
     ref = run(f'none_b{b}', b, parallel='none')
     dist.barrier()
-    for tag, over in (('dp_peer', dict(parallel='dp', exchange='peer')), ('dp_nccl', dict(parallel='dp', exchange='nccl')),
+    for tag, over in (('dp_peer', dict(parallel='dp', exchange='peer')), ('dp_nccl', dict(parallel='dp', exchange='nccl')), ('shard_torch', dict(parallel='shard', exchange='torch')),
                       ('dp_torch', dict(parallel='dp', exchange='torch')), ('shard', dict(parallel='shard'))):
         got = run(f'{tag}_b{b}', b, **over)
         if rank == 0: same(f'{tag} b={b} N={world}', got, ref)

@@ -275,3 +275,43 @@ def test_flipout_tensor_core_step_is_reproducible_on_fresh_engines(iters=60):
             assert nrm(out[k].float(), ref[k].float()) < 2e-6, (it, k, nrm(out[k].float(), ref[k].float()))
         assert nrm(grads_of(eng, 0)['mu_w'], g_ref[0]['mu_w']) < 5e-3, it
         del eng
+
+
+@pytest.mark.parametrize('B,d,hidden,E', [(40, 16, [24], 301), (64, 128, [16, 8], 100)])
+def test_flipout_step_on_dense_skill_input_matches_oracle(B, d, hidden, E):
+    """Bnn on embedded skills (main.py:148-153, ntf.py:24; the reference's CI runs mdl.bnn.Bnn with d2v / gnn vectors): layer 0 is a dense
+    Flipout layer -- forward, loss (+ KL/B) and every gradient against the oracle, host-drawn noise on both sides (fp32 mode: round-off only)."""
+    from opentf_b200.engine import Engine
+    rng = np.random.default_rng(B + E)
+    torch.manual_seed(B)
+    X = torch.from_numpy(rng.standard_normal((B, d)).astype(np.float32))
+    member = rand_csr(rng, B, E, 1, min(E - 1, 4))
+    layers = O.init_flipout_params(d, hidden, E)
+    noise = O.draw_flipout_noise(layers, B)
+    neg = rng.integers(0, E, (B, 5))
+    y = dense(member)
+    logits, acts, pre = O.flipout_forward(layers, noise, X)
+    w = O.loss_weights(y, torch.as_tensor(neg), 10, 1)
+    loss_ref = (O.bce_with_logits(logits, y, w).sum(1).mean() + O.flipout_kl(layers) / B).item()
+    g_ref = O.flipout_backward(layers, noise, acts, pre, y, w)
+    eng = Engine(d, hidden, E, DEV, bayesian=True, precision='fp32', tpw=10, tnw=1, nsd='uniform', ns=5, seed=3, max_batch=B, dense_input=True)
+    eng.stage(X.numpy(), member)
+    sd = {}
+    for i, L in enumerate(layers):
+        sd[f'layers.{i}.mu_weight'], sd[f'layers.{i}.rho_weight'] = L['mu_w'], L['rho_w']
+        sd[f'layers.{i}.mu_bias'], sd[f'layers.{i}.rho_bias'] = L['mu_b'], L['rho_b']
+    eng.load_state_dict(sd)
+    sp = eng.split(np.arange(B))
+    eng.step(sp, 0, B, True, lr=1e-3, loss_slot=0, neg_host=neg, noise_host=noise)
+    torch.cuda.synchronize()
+    loss = eng.loss_buf[0].item()
+    assert abs(loss - loss_ref) <= 2e-5 * abs(loss_ref), (loss, loss_ref)
+    for i in range(len(layers)):
+        g = lambda k, w_: eng.view(f'layers.{i}.{k}_{w_}', eng.grads).cpu()  # (dense input: layer 0 is stored in torch layout too)
+        mine = dict(mu_w=g('mu', 'weight'), rho_w=g('rho', 'weight'), mu_b=g('mu', 'bias'), rho_b=g('rho', 'bias'))
+        for k in ('mu_w', 'mu_b', 'rho_w', 'rho_b'):
+            assert rel_err(mine[k], g_ref[i][k]) < 3e-5, (i, k, rel_err(mine[k], g_ref[i][k]))
+    # a second, graph-less step with device-drawn noise runs (counter RNG: signs for the [B,d] input plane)
+    eng.step(sp, 0, B, True, lr=1e-3, loss_slot=1)
+    torch.cuda.synchronize()
+    assert np.isfinite(eng.loss_buf[1].item())
