@@ -605,8 +605,9 @@ class HostBatches:
         # capacities: the longest global batch of the run (+ slack), so that every batch has the same device layout (one captured graph)
         ls, lm = np.diff(self.s[0])[self.rows], np.diff(self.m[0])[self.rows]
         nb = len(self.rows) // gB
-        cap = lambda l: int(-(-int(l[:nb * gB].reshape(nb, gB).sum(1).max() * 1.02 + 64) // 64) * 64)
-        self.cap_s, self.cap_m = cap(ls), cap(lm)
+        lo, hi = self._slice()  # the skill CSR travels for this rank's rows only, the member CSR for the whole global batch
+        cap = lambda l, a, z: int(-(-int(l[:nb * gB].reshape(nb, gB)[:, a:z].sum(1).max() * 1.02 + 64) // 64) * 64)
+        self.cap_s, self.cap_m = cap(ls, lo, hi), cap(lm, 0, gB)
         self.packer = HostPacker(self.s, self.m, gB, self.cap_s, self.cap_m)
         self.h2d_bytes = self.packer.words * 4
 
@@ -615,17 +616,23 @@ class HostBatches:
         g0 = (i * gB) % (len(self.rows) - gB)
         return self.rows[g0:g0 + gB]
 
+    def _slice(self):
+        gB = self.b * self.G
+        per = -(-gB // self.G)
+        return min(gB, self.rank * per), min(gB, (self.rank + 1) * per)
+
     def step(self, eng, i):
-        return eng.step_host(self.packer.pack(self._rows(i)), self.b * self.G, self.cap_s, self.cap_m, self.rank, self.G, lr=1e-3)
+        return eng.step_host(self.packer.pack(self._rows(i), *self._slice()), self.b * self.G, self.cap_s, self.cap_m, self.rank, self.G, lr=1e-3)
 
     def run(self, eng, first, steps):
         """`steps` consecutive batches: pack(i+1) overlaps the GPU's work on batch i; the loss of every step is read back"""
         gB = self.b * self.G
-        blk = self.packer.pack(self._rows(first))
+        lo, hi = self._slice()
+        blk = self.packer.pack(self._rows(first), lo, hi)
         loss = None
         for i in range(steps):
             eng.step_host(blk, gB, self.cap_s, self.cap_m, self.rank, self.G, lr=1e-3, sync=False)
-            if i + 1 < steps: blk = self.packer.pack(self._rows(first + i + 1))
+            if i + 1 < steps: blk = self.packer.pack(self._rows(first + i + 1), lo, hi)
             loss = eng.step_host_loss()
         return loss
 

@@ -425,9 +425,10 @@ int ntf_fnn_infer_topk(ntf_ctx* ctx, void* stream, const ntf_fnn_infer_topk_args
 /* HOST function (no device work): rows `rows[0..n)` of the skill / member CSR (int32 indptr / indices of all teams) -> the int32 block
  * [s_indptr n+1 | m_indptr n+1 | s_indices cap_s | s_ent_row cap_s | m_indices cap_m] (offsets from 0, segments zero-padded to the capacities)
  * that the streaming entry point copies to the device in one transfer.  Replaces the per-row work of the reference's Dataset / DataLoader
- * (ntf.py:17-25, fnn.py:95,118-121).  `out` is typically pinned host memory. */
+ * (ntf.py:17-25, fnn.py:95,118-121).  `out` is typically pinned host memory.  [lo, hi): the rows this rank trains on -- the skill CSR
+ * is packed for them only (empty skill rows elsewhere), the member CSR for all n rows (unigram_b samples from the whole batch). */
 int ntf_pack_host_batch(const int32_t* rows, int n, const int32_t* s_indptr, const int32_t* s_indices, const int32_t* m_indptr,
-                        const int32_t* m_indices, int cap_s, int cap_m, int32_t* out, size_t out_words);
+                        const int32_t* m_indices, int cap_s, int cap_m, int lo, int hi, int32_t* out, size_t out_words);
 
 /* out[i] = sum_k parts[k*part_stride + i] in a fixed order (deterministic split reductions) */
 int ntf_sum_parts(ntf_ctx* ctx, void* stream, const float* parts, int nparts, size_t n, size_t part_stride, float* out);

@@ -130,7 +130,7 @@ SIGNATURES = {
     'ntf_fnn_step': (i32, [vp, vp, C.POINTER(FnnStepArgs), vp, sz]),
     'ntf_fnn_infer_topk_workspace_bytes': (sz, [vp, C.POINTER(FnnInferTopkArgs)]),
     'ntf_fnn_infer_topk': (i32, [vp, vp, C.POINTER(FnnInferTopkArgs), vp, sz]),
-    'ntf_pack_host_batch': (i32, [vp, i32, vp, vp, vp, vp, i32, i32, vp, sz]),
+    'ntf_pack_host_batch': (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, sz]),
     'ntf_sum_parts': (i32, [vp, vp, vp, i32, sz, sz, vp]),
 }
 

@@ -152,9 +152,12 @@ extern "C" int ntf_graph_destroy(ntf_graph* g) {
 // offsets start at 0; the index segments are padded to fixed capacities so that every batch of a run lands at the same device addresses (the
 // step then replays one captured graph).  The reference does this work per row in Python (ntf.py:17-25: lil row -> dense float vector, default
 // collate); here it is a memcpy per row of the already-CSR teamsvecs.
+// Data-parallel ranks train on rows [lo, hi) of the global batch but sample negatives from the whole batch's members (unigram_b): the member
+// CSR is packed for all n rows, the skill CSR for the slice only (the other rows get empty skill rows, so the offsets stay those of the batch).
 extern "C" int ntf_pack_host_batch(const int32_t* rows, int n, const int32_t* s_indptr, const int32_t* s_indices, const int32_t* m_indptr,
-                                   const int32_t* m_indices, int cap_s, int cap_m, int32_t* out, size_t out_words) {
+                                   const int32_t* m_indices, int cap_s, int cap_m, int lo, int hi, int32_t* out, size_t out_words) {
   NTF_REQUIRE(rows && s_indptr && s_indices && m_indptr && m_indices && out && n > 0, NTF_ERR_BAD_ARG, "pack_host_batch: null pointer / empty batch");
+  NTF_REQUIRE(0 <= lo && lo <= hi && hi <= n, NTF_ERR_BAD_ARG, "pack_host_batch: slice [%d,%d) of %d rows", lo, hi, n);
   const size_t need = 2 * ((size_t)n + 1) + 2 * (size_t)cap_s + (size_t)cap_m;
   NTF_REQUIRE(out_words >= need, NTF_ERR_WORKSPACE, "pack_host_batch: block of %zu words, %zu needed", out_words, need);
   int32_t* sp = out;
@@ -166,7 +169,7 @@ extern "C" int ntf_pack_host_batch(const int32_t* rows, int n, const int32_t* s_
   sp[0] = 0; mp[0] = 0;
   for (int i = 0; i < n; ++i) {
     const int r = rows[i];
-    const int a = s_indptr[r], ls = s_indptr[r + 1] - a, b = m_indptr[r], lm = m_indptr[r + 1] - b;
+    const int a = s_indptr[r], ls = (i >= lo && i < hi) ? s_indptr[r + 1] - a : 0, b = m_indptr[r], lm = m_indptr[r + 1] - b;
     NTF_REQUIRE(ns + ls <= cap_s && nm + lm <= cap_m, NTF_ERR_BAD_ARG, "pack_host_batch: capacities (%d, %d) too small at row %d", cap_s, cap_m, i);
     memcpy(si + ns, s_indices + a, (size_t)ls * sizeof(int32_t));
     for (int k = 0; k < ls; ++k) sr[ns + k] = i;

@@ -225,62 +225,60 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
     }
   } else if (warp == WARP_MMA) {
     // =========================================== MMA issuer ===========================================
-    if (lane == 0) {
-      auto issue_fwd = [&](int it) {
-        const int sa = it % AST, s = it & 1;
-        const uint32_t pha = (it / AST) & 1, ph = (it >> 1) & 1;
-        mbar_wait(bar(BAR_A_FULL + sa), pha);
-        if (g.timing && blockIdx.x == 0) g.timing[it * 8 + 1] = clock64();
-        mbar_wait(bar(BAR_Z_EMPTY + s), ph ^ 1);
-        if (g.timing && blockIdx.x == 0) g.timing[it * 8 + 2] = clock64();
-        tc_fence_after();
+    // the whole warp runs this loop converged; one elected lane issues the MMAs and the commits (tc_common.cuh: elect_one)
+    const uint64_t d_w16_k = smem_desc(sbase + OFF_W16, 16, 1024);      // W16 as K-major operand (forward)
+    const uint64_t d_w16_mn = smem_desc(sbase + OFF_W16, CHUNK, 1024);  // W16 as MN-major operand (dA^T: M = hidden)
+    auto issue_fwd = [&](int it) {
+      const int sa = it % AST, s = it & 1;
+      const uint32_t pha = (it / AST) & 1, ph = (it >> 1) & 1;
+      mbar_wait(bar(BAR_A_FULL + sa), pha);
+      if (g.timing && blockIdx.x == 0 && lane == 0) g.timing[it * 8 + 1] = clock64();
+      mbar_wait(bar(BAR_Z_EMPTY + s), ph ^ 1);
+      if (g.timing && blockIdx.x == 0 && lane == 0) g.timing[it * 8 + 2] = clock64();
+      tc_fence_after();
+      const uint64_t d_a = smem_desc(sbase + OFF_A16 + sa * A16_BYTES, 16, 1024);
 #pragma unroll
-        for (int i = 0; i < HK / 16; ++i) {  // 8 k-steps of 16 halfs (32 bytes): chunk i/4, 32-byte slice i%4 of the 128-byte swizzle row
-          const uint64_t da = smem_desc(sbase + OFF_W16 + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
-          const uint64_t db = smem_desc(sbase + OFF_A16 + sa * A16_BYTES + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);
-          mma_f16(tmem + TM_Z + s * TB, da, db, IDESC_FWD, i > 0);
-        }
+      for (int i = 0; i < HK / 16; ++i) {  // 8 k-steps of 16 halfs (32 bytes): chunk i/4, 32-byte slice i%4 of the 128-byte swizzle row
+        const uint64_t koff = (uint64_t)(((i >> 2) * CHUNK + (i & 3) * 32) >> 4);
+        if (elect_one()) mma_f16(tmem + TM_Z + s * TB, d_w16_k + koff, d_a + koff, IDESC_FWD, i > 0);
+      }
+      if (elect_one()) {
         tc_commit(bar(BAR_Z_FULL + s));
-        if (g.timing && (g.exp & 4)) {  // diagnostic mode 4 serialises the pipeline: stamp the COMPLETION of the forward product
-          mbar_wait(bar(BAR_Z_FULL + s), ph);
-          if (blockIdx.x == 0) g.timing[it * 8 + 3] = clock64();
-        }
         if (!train) tc_commit(bar(BAR_A_EMPTY + sa));  // forward-only: the stage is free once the forward product has read it
-      };
-      mbar_wait(bar(BAR_W16), 0);
-      if (g.timing && blockIdx.x == 0) g.timing[15 * 8 + 2] = clock64();  // W image ready
-      if (MODE != 3 && ntiles > 0) issue_fwd(0);
-      for (int it = 0; it < ntiles; ++it) {
-        if (MODE != 3 && it + 1 < ntiles) issue_fwd(it + 1);  // keep the tensor pipe busy while the epilogue works on tile it
-        if (!train) continue;
-        const int sa = it % AST, s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        if (MODE == 3) mbar_wait(bar(BAR_A_FULL + sa), (it / AST) & 1);  // (no forward product waited for the activation tile)
-        mbar_wait(bar(BAR_DZ_FULL + s), ph);
-        tc_fence_after();
-        if (g.timing && blockIdx.x == 0) g.timing[it * 8 + 0] = clock64();  // backward products: issue starts
-        // dW[128 j x 128 k] += dz^T[j, n] . A16[n, k] : K = 128 teams = 8 steps of 16
+      }
+    };
+    mbar_wait(bar(BAR_W16), 0);
+    if (g.timing && blockIdx.x == 0 && lane == 0) g.timing[15 * 8 + 2] = clock64();  // W image ready
+    if (MODE != 3 && ntiles > 0) issue_fwd(0);
+    for (int it = 0; it < ntiles; ++it) {
+      if (MODE != 3 && it + 1 < ntiles) issue_fwd(it + 1);  // keep the tensor pipe busy while the epilogue works on tile it
+      if (!train) continue;
+      const int sa = it % AST, s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      if (MODE == 3) mbar_wait(bar(BAR_A_FULL + sa), (it / AST) & 1);  // (no forward product waited for the activation tile)
+      mbar_wait(bar(BAR_DZ_FULL + s), ph);
+      tc_fence_after();
+      if (g.timing && blockIdx.x == 0 && lane == 0) g.timing[it * 8 + 0] = clock64();  // backward products: issue starts
+      const uint64_t d_dz_k = smem_desc(sbase + OFF_DZ + s * DZ_BYTES, 16, 1024);       // dz^T as K-major operand (K = teams)
+      const uint64_t d_dz_mn = smem_desc(sbase + OFF_DZ + s * DZ_BYTES, CHUNK, 1024);   // dz as MN-major operand (N = teams)
+      const uint64_t d_a_mn = smem_desc(sbase + OFF_A16 + sa * A16_BYTES, CHUNK, 1024);  // A16 as MN-major operand (N = hidden)
+      // dW[128 j x 128 k] += dz^T[j, n] . A16[n, k] : K = 128 teams = 8 steps of 16
 #pragma unroll
-        for (int i = 0; i < TB / 16; ++i) {
-          const uint64_t da = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + (i >> 2) * CHUNK + (i & 3) * 32, 16, 1024);   // K-major, K = teams
-          const uint64_t db = smem_desc(sbase + OFF_A16 + sa * A16_BYTES + i * 2048, CHUNK, 1024);                     // MN-major, N = hidden
-          mma_f16(tmem + TM_DW, da, db, IDESC_DW, (it > 0 || i > 0));
-        }
-        // dA[128 n x 128 k] = dz[j, n]^T . W16[j, k] : K = 128 experts = 8 steps of 16
-        mbar_wait(bar(BAR_DA_EMPTY), (it & 1) ^ 1);
-        tc_fence_after();
-        if (g.timing && blockIdx.x == 0 && !(g.exp & 4)) g.timing[it * 8 + 7] = clock64();  // dW issued, dA accumulator free
+      for (int i = 0; i < TB / 16; ++i) {
+        const uint64_t koff = (uint64_t)(((i >> 2) * CHUNK + (i & 3) * 32) >> 4);
+        if (elect_one()) mma_f16(tmem + TM_DW, d_dz_k + koff, d_a_mn + (uint64_t)((i * 2048) >> 4), IDESC_DW, (it > 0 || i > 0));
+      }
+      // dA^T[128 k x 128 n] = W16[j, k]^T . dz[j, n] : K = 128 experts = 8 steps of 16; hidden on the TMEM lanes (see the dA warps)
+      mbar_wait(bar(BAR_DA_EMPTY), (it & 1) ^ 1);
+      tc_fence_after();
+      if (g.timing && blockIdx.x == 0 && lane == 0) g.timing[it * 8 + 7] = clock64();  // dW issued, dA accumulator free
 #pragma unroll
-        for (int i = 0; i < TE / 16; ++i) {
-          const uint64_t da = smem_desc(sbase + OFF_DZ + s * DZ_BYTES + i * 2048, CHUNK, 1024);                        // MN-major, M = teams
-          const uint64_t db = smem_desc(sbase + OFF_W16 + i * 2048, CHUNK, 1024);                                      // MN-major, N = hidden
-          mma_f16(tmem + TM_DA, da, db, IDESC_DA, i > 0);
-        }
+      for (int i = 0; i < TE / 16; ++i) {
+        const uint64_t koff = (uint64_t)((i * 2048) >> 4);
+        if (elect_one()) mma_f16(tmem + TM_DA, d_w16_mn + koff, d_dz_mn + koff, IDESC_DA, i > 0);
+      }
+      if (elect_one()) {
         tc_commit(bar(BAR_DA_FULL));
-        if (g.timing && (g.exp & 4)) {
-          mbar_wait(bar(BAR_DA_FULL), it & 1);
-          if (blockIdx.x == 0) g.timing[it * 8 + 7] = clock64();  // backward products complete
-        }
         tc_commit(bar(BAR_DZ_EMPTY + s));
         tc_commit(bar(BAR_A_EMPTY + sa));
         if (it == ntiles - 1) tc_commit(bar(BAR_DW_FULL));
@@ -613,39 +611,35 @@ __global__ void __launch_bounds__(NT, 1) out_tc_kernel(const __grid_constant__ C
       }
     }
   } else if (warp >= WARP_DA && warp < WARP_DA + 4) {
-    // ====== dA epilogue: thread = team.  TMEM -> regs -> swizzled fp32 chunks in shared memory -> TMA reduce-add into dA[B,128] ======
-    // (the sum over expert tiles = across CTAs happens in L2, issued by the TMA unit: no SM-side atomics; rows past B are clipped)
+    // ====== dA epilogue.  The product is taken TRANSPOSED (hidden unit on the TMEM lane, teams along the columns): a warp's 32 lanes hold 32
+    // consecutive hidden units of one team, so the tile is added into dA[B,128] by red.global.add.f32 straight from registers, 128
+    // contiguous bytes per instruction (round 1 staged 16 KB chunks for a TMA reduce-add through ONE buffer: 4600 cycles per tile, the
+    // tile period of the whole kernel; scripts/mb/mb_reduce.cu).  The sum over expert tiles (= across CTAs) happens in L2. ======
     if (train) {
-      const int r = threadIdx.x - WARP_DA * 32;  // 0..127 = TMEM lane = team of the tile
+      const int k = threadIdx.x - WARP_DA * 32;  // hidden unit = TMEM lane
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
       for (int it = 0; it < ntiles; ++it) {
         mbar_wait(bar(BAR_DA_FULL), it & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < HK / 32; ++c) {  // 32 hidden units = one 128-byte chunk row
+        for (int c = 0; c < TB / 32; ++c) {
           float v[32];
           tmem_ld32(tmem + lane_base + TM_DA + c * 32, v);
-          if (c == HK / 32 - 1) {
+          if (c == TB / 32 - 1) {
             tc_fence_before();
             mbar_arrive(bar(BAR_DA_EMPTY));
           }
-          if (r == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous reduce is done reading the buffer
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          uint8_t* row = sgen + OFF_DAST + r * 128;
+          const int team0 = (t_begin + it) * TB + c * 32;
+          float* dst = g.dA + (size_t)team0 * HK + k;
+          const int nrem = g.B - team0;
+          if (!(g.exp & 1)) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(row + ((q ^ (r & 7)) << 4)) = make_float4(v[4 * q] * g.scale, v[4 * q + 1] * g.scale, v[4 * q + 2] * g.scale, v[4 * q + 3] * g.scale);
-          fence_proxy_async();
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          if (r == 0 && !(g.exp & 1)) {
-            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
-                         ::"l"(reinterpret_cast<uint64_t>(&map_da)), "r"(c * 32), "r"((t_begin + it) * TB), "r"(sbase + OFF_DAST) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            for (int i = 0; i < 32; ++i)
+              if (i < nrem) atomicAdd(dst + (size_t)i * HK, v[i] * g.scale);
           }
         }
-        if (g.timing && blockIdx.x == 0 && r == 0 && !(g.exp & 4)) g.timing[it * 8 + 3] = clock64();  // dA tile staged / reduce issued
+        if (g.timing && blockIdx.x == 0 && k == 0) g.timing[it * 8 + 3] = clock64();  // dA tile added
       }
-      if (r == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
   tc_fence_before();

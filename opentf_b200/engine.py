@@ -149,12 +149,13 @@ class HostPacker:
         self.blocks = [torch.zeros(self.words, dtype=torch.int32).pin_memory() for _ in range(2)]
         self.k = 0
 
-    def pack(self, rows):
+    def pack(self, rows, lo=0, hi=None):
+        """[lo, hi): the rows of the global batch this rank trains on (skill CSR packed for them only; members for the whole batch)"""
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         assert len(rows) == self.n
         blk = self.blocks[self.k]; self.k ^= 1
         _lib.check(_lib.lib().ntf_pack_host_batch(rows.ctypes.data, self.n, self.sp.ctypes.data, self.si.ctypes.data, self.mp.ctypes.data, self.mi.ctypes.data,
-                                                  self.cap_s, self.cap_m, blk.data_ptr(), self.words), 'ntf_pack_host_batch')
+                                                  self.cap_s, self.cap_m, int(lo), self.n if hi is None else int(hi), blk.data_ptr(), self.words), 'ntf_pack_host_batch')
         return blk
 
 
