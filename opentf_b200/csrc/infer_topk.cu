@@ -7,12 +7,14 @@
 //
 //   pass 1   Z[128 teams x 128 experts] = A16 . W16^T per (batch tile, expert tile); every epilogue thread (team, block of 32
 //            consecutive experts) keeps only the block's MAXIMUM -> bm[B, E/32]   (4*E/32 bytes per team instead of 4*E)
-//   select   per team the K-th largest block maximum (blockmax_threshold_kernel: bisection on the ordered keys): value Tz, block bK.
-//            K blocks have a maximum >= Tz, so Tz is a lower bound of the K-th best logit, and everything that can be in the
-//            top K has  z > Tz  or  (z == Tz and its block <= bK)  -- at most 32*K elements, all inside those K blocks.
-//   pass 2   the same product again; elements passing that test are appended to the team's candidate list (global atomics on a
-//            per-team counter: a few dozen per team), everything else is dropped in registers.
-//   final    per team: sort the candidates by (z descending, expert id ascending), emit the first K as (probability, expert id).
+//   select   per team the K-th largest block maximum Tz under the order (value descending, block ascending) -- blockmax_threshold_kernel,
+//            an adaptive radix select -- and per block a bit (one of the K blocks at or above it?) and for those a byte, the slot 0..K-1.
+//            K blocks have a maximum >= Tz, so Tz is a lower bound of the K-th best logit and everything that can be in the top K
+//            has z >= Tz and lies inside those K blocks (an element equal to Tz in a later block loses the tie against the K-th block's).
+//   pass 2   the same product again; a thread whose block has a slot stores the block's 32 (logit, expert) composites at
+//            cand[team][slot][0..31] -- fixed positions, no atomics, no counters.  A warp none of whose 32 (team, block) pairs has a
+//            slot (the block bits sit in registers, 8 expert tiles at a time) does not even read its logits from TMEM.
+//   final    per team: the candidates >= Tz in rank order (z descending, expert id ascending) -> the first K as (probability, expert id).
 //
 // Recomputing the product is cheaper than writing and re-reading [B,E] (FlashAttention's trade): per team 2*2*h*E flops on the
 // tensor pipe against 8*E bytes of HBM traffic.  Exact: the result equals the K best of the full score row under the library's
@@ -20,10 +22,11 @@
 // logits are distinct where the probabilities are (equal probabilities of distinct logits -- sigmoid saturation -- are ranked
 // by logit: a permutation among exact score ties).
 //
-// Layout: CTA = (a PAIR of batch tiles of 128 teams, chunk of consecutive expert tiles); grid = pairs x chunks sized to one wave.
-//   warp 16     TMA: the two fp16 activation tiles once, then the fp16 W tiles of the chunk through a 3-stage ring
-//   warp 17     MMA issuer: per W tile two products (M = 128 teams, N = 128 experts, K = 128 hidden: 8 x kind::f16), 4 accumulator stages in TMEM
-//   warps 0-15  epilogue: thread = (team = TMEM lane, 32-expert column block): tcgen05.ld, + bias, max / threshold test
+// Layout: CTA = (NH = 4 batch tiles of 128 teams, chunk of consecutive expert tiles); grid = groups x chunks sized to one wave.
+//   warp 16       TMA: the fp16 activation tiles once, then the fp16 W tiles of the chunk through a 3-stage ring
+//   warps 17-18   MMA issuers: per W tile one product per batch tile (M = 128 teams, N = 128 experts, K = 128 hidden: 8 x kind::f16),
+//                 4 accumulators in TMEM
+//   warps 0-15    epilogue: thread = (team = TMEM lane, 32-expert column block): tcgen05.ld, + bias, block maximum / candidate store
 // W16 is an fp16 image of the layer's weight kept by the caller (ntf_to_half; rewritten when the parameters change).
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -40,16 +43,17 @@ constexpr uint32_t CHUNK = 128 * 128;        // one swizzle chunk: 128 rows x 12
 constexpr uint32_t TILE_BYTES = 2 * CHUNK;   // an fp16 [128 x 128] operand tile: 2 chunks (hidden 0-63 | 64-127)
 constexpr int W_STAGES = 3;
 constexpr int Z_STAGES = 4;
-constexpr int NH = 2;     // batch tiles per CTA: every W tile that comes in is multiplied with both (halves the W traffic out of L2, which bound the
-                          // one-tile version: 8 batch tiles x 10 MB per pass at ~4.4 TB/s = 18.6 us measured)
+constexpr int NH = 4;     // batch tiles per CTA: every W tile that comes in is multiplied with all of them.  The W traffic out of L2 bounds the
+                          // kernel otherwise: one tile per CTA = 8 x 11.5 MB per pass on the C2 shape (18.6 us measured), two = 46 MB (~12 us);
+                          // four fill the 512 TMEM columns (one accumulator each) and the shared memory (128 KB of A + 3 W stages)
 constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_W = OFF_A + NH * TILE_BYTES;
 constexpr uint32_t OFF_BAR = OFF_W + W_STAGES * TILE_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256;
-enum { BAR_A_FULL = 0, BAR_W_FULL = 1, BAR_W_EMPTY = 1 + W_STAGES, BAR_Z_FULL = 1 + 2 * W_STAGES, BAR_Z_EMPTY = 1 + 2 * W_STAGES + Z_STAGES,
-       NUM_BARS = 1 + 2 * W_STAGES + 2 * Z_STAGES };
+enum { BAR_A_FULL = 0, BAR_W_FULL = NH, BAR_W_EMPTY = NH + W_STAGES, BAR_Z_FULL = NH + 2 * W_STAGES, BAR_Z_EMPTY = NH + 2 * W_STAGES + Z_STAGES,
+       NUM_BARS = NH + 2 * W_STAGES + 2 * Z_STAGES };
 static_assert(NUM_BARS * 8 + 8 <= 256, "barrier block");
-constexpr int EPI_WARPS = 16, WARP_TMA = 16, WARP_MMA = 17, NT = 18 * 32;
+constexpr int EPI_WARPS = 16, WARP_TMA = 16, WARP_MMA = 17, N_MMA = 2, NT = (17 + N_MMA) * 32;  // warps 17, 18 issue the products of the even / odd batch tiles of the CTA
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr uint32_t IDESC = instr_desc(0, 0, 0, TT, TX);  // Z = A16(K-major) . W16(K-major)^T, fp16 operands, fp32 accumulate
 constexpr int BLK = 32;  // experts per block (= the 32 TMEM columns one epilogue thread reads)
@@ -66,11 +70,11 @@ struct ItArgs {
   int nbt, nct, nchunk;  // batch tiles, expert tiles, chunks of expert tiles
   int nblk;              // row pitch of bm = 4 * nct (blocks of 32 experts, the last tile padded)
   float* bm;             // pass 1 out: [B, nblk] block maxima (-inf for blocks past E)
-  float* thr_val;        // pass 2 in: [B] the K-th largest block maximum of the team (blockmax_threshold_kernel), and
-  int32_t* thr_blk;      //            [B] the block it belongs to under the rank order (value descending, block ascending)
-  unsigned long long* cand;  // pass 2 out: [B, cap] composites (ordered logit << 32 | ~expert)
-  int* cnt;                  // [B] candidates appended so far (zeroed by the caller)
-  int cap;
+  const uint32_t* bits;  // pass 2 in: [nwords, B] bit blk % 32 of word blk / 32 = the block is one of the team's K best blocks (blockmax_threshold_kernel), and
+  const uint8_t* slot;   //            [B, nblk] for those blocks: the slot 0..K-1 among them (the other bytes are not written; slot_blk[B, K] is the inverse)
+  int nwords;
+  float* cand;           // pass 2 out: [B, K, 32] the products a.w (no bias yet) of the team's K best blocks, slot by slot; every entry written
+  int timing_pass;
   long long* timing;         // debug (NTF_IT_TIMING): per CTA 256 slots: [0] start clock, [1] end clock; from 8, 4 per product q < 60: W tile landed (MMA warp),
                              // product issued, logits ready (epilogue thread 0), epilogue done
 };
@@ -90,11 +94,12 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
   const int nh = min(NH, g.nbt - bp * NH);  // batch tiles this CTA really has
   const int t0 = (int)((long long)chunk * g.nct / g.nchunk), t1 = (int)((long long)(chunk + 1) * g.nct / g.nchunk);
   const int ntiles = t1 - t0;
-  if (g.timing && threadIdx.x == 0) g.timing[256 * blockIdx.x] = clock64();
+  long long* const timing = g.timing_pass == PASS ? g.timing : nullptr;
+  if (timing && threadIdx.x == 0) timing[256 * blockIdx.x] = clock64();
 
   if (threadIdx.x == 0) {
-    mbar_init(bar(BAR_A_FULL), 1);
-    for (int s = 0; s < W_STAGES; ++s) { mbar_init(bar(BAR_W_FULL + s), 1); mbar_init(bar(BAR_W_EMPTY + s), 1); }
+    for (int hf = 0; hf < NH; ++hf) mbar_init(bar(BAR_A_FULL + hf), 1);
+    for (int s = 0; s < W_STAGES; ++s) { mbar_init(bar(BAR_W_FULL + s), 1); mbar_init(bar(BAR_W_EMPTY + s), min(nh, N_MMA)); }  // (one release per issuing warp)
     for (int s = 0; s < Z_STAGES; ++s) { mbar_init(bar(BAR_Z_FULL + s), 1); mbar_init(bar(BAR_Z_EMPTY + s), EPI_THREADS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -109,123 +114,164 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
 
   if (warp == WARP_TMA) {
     if (lane == 0) {
-      mbar_expect_tx(bar(BAR_A_FULL), nh * TILE_BYTES);
-      for (int hf = 0; hf < nh; ++hf)
-        for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A + hf * TILE_BYTES + c * CHUNK, &map_a, c * 64, (bp * NH + hf) * TT, bar(BAR_A_FULL));
-      for (int it = 0; it < ntiles; ++it) {
+      for (int hf = 0; hf < nh; ++hf) {  // the first product needs batch tile 0 and W tile 0 only: one barrier per batch tile, W tile 0 right behind the first
+        mbar_expect_tx(bar(BAR_A_FULL + hf), TILE_BYTES);
+        for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_A + hf * TILE_BYTES + c * CHUNK, &map_a, c * 64, (bp * NH + hf) * TT, bar(BAR_A_FULL + hf));
+        if (hf == 0 && ntiles > 0) {
+          mbar_expect_tx(bar(BAR_W_FULL), TILE_BYTES);
+          for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_W + c * CHUNK, &map_w, c * 64, t0 * TX, bar(BAR_W_FULL));
+        }
+      }
+      for (int it = 1; it < ntiles; ++it) {
         const int s = it % W_STAGES;
         mbar_wait(bar(BAR_W_EMPTY + s), ((it / W_STAGES) & 1) ^ 1);
         mbar_expect_tx(bar(BAR_W_FULL + s), TILE_BYTES);
         for (int c = 0; c < 2; ++c) tma_load_2d(sbase + OFF_W + s * TILE_BYTES + c * CHUNK, &map_w, c * 64, (t0 + it) * TX, bar(BAR_W_FULL + s));
       }
     }
-  } else if (warp == WARP_MMA) {
-    // the whole warp runs this loop converged; one elected lane issues the MMAs and the commits (tc_common.cuh: elect_one)
-    mbar_wait(bar(BAR_A_FULL), 0);
-    for (int it = 0; it < ntiles; ++it) {
-      const int s = it % W_STAGES;
-      mbar_wait(bar(BAR_W_FULL + s), (it / W_STAGES) & 1);
-      const uint64_t d_w = smem_desc(sbase + OFF_W + s * TILE_BYTES, 16, 1024);
-      for (int hf = 0; hf < nh; ++hf) {
-        const int q = it * nh + hf, zs = q % Z_STAGES;  // accumulator stages are handed out per product
-        if (g.timing && lane == 0 && q < 60) g.timing[256 * blockIdx.x + 8 + 4 * q] = clock64();
-        mbar_wait(bar(BAR_Z_EMPTY + zs), ((q / Z_STAGES) & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t d_a = smem_desc(sbase + OFF_A + hf * TILE_BYTES, 16, 1024);
+  } else if (warp >= WARP_MMA) {
+    // N_MMA issuing warps, warp m takes the batch tiles hf = m, m + N_MMA, ... of every W tile (a single warp sharing its scheduler with four
+    // epilogue warps fell behind the tensor pipe: scripts/topk_timing.py).  Each runs converged; one elected lane issues the MMAs and the commits.
+    const int m = warp - WARP_MMA;
+    if (m < nh) {
+      for (int it = 0; it < ntiles; ++it) {
+        const int s = it % W_STAGES;
+        mbar_wait(bar(BAR_W_FULL + s), (it / W_STAGES) & 1);
+        const uint64_t d_w = smem_desc(sbase + OFF_W + s * TILE_BYTES, 16, 1024);
+        for (int hf = m; hf < nh; hf += N_MMA) {
+          const int q = it * nh + hf, zs = q % Z_STAGES;  // accumulator stages are handed out per product (nh = 4: stage = batch tile)
+          if (it == 0) mbar_wait(bar(BAR_A_FULL + hf), 0);
+          if (timing && lane == 0 && q < 60) timing[256 * blockIdx.x + 8 + 4 * q] = clock64();
+          mbar_wait(bar(BAR_Z_EMPTY + zs), ((q / Z_STAGES) & 1) ^ 1);
+          tc_fence_after();
+          const uint64_t d_a = smem_desc(sbase + OFF_A + hf * TILE_BYTES, 16, 1024);
 #pragma unroll
-        for (int i = 0; i < HK / 16; ++i) {  // 8 k-steps of 16 halfs: chunk i/4, 32-byte slice i%4 of the 128-byte swizzle row
-          const uint64_t koff = (uint64_t)(((i >> 2) * CHUNK + (i & 3) * 32) >> 4);
-          if (elect_one()) mma_f16(tmem + zs * TX, d_a + koff, d_w + koff, IDESC, i > 0);
+          for (int i = 0; i < HK / 16; ++i) {  // 8 k-steps of 16 halfs: chunk i/4, 32-byte slice i%4 of the 128-byte swizzle row
+            const uint64_t koff = (uint64_t)(((i >> 2) * CHUNK + (i & 3) * 32) >> 4);
+            if (elect_one()) mma_f16(tmem + zs * TX, d_a + koff, d_w + koff, IDESC, i > 0);
+          }
+          if (elect_one()) tc_commit(bar(BAR_Z_FULL + zs));
+          if (timing && lane == 0 && q < 60) timing[256 * blockIdx.x + 8 + 4 * q + 1] = clock64();
         }
-        if (elect_one()) tc_commit(bar(BAR_Z_FULL + zs));
-        if (g.timing && lane == 0 && q < 60) g.timing[256 * blockIdx.x + 8 + 4 * q + 1] = clock64();
+        if (elect_one()) tc_commit(bar(BAR_W_EMPTY + s));
       }
-      if (elect_one()) tc_commit(bar(BAR_W_EMPTY + s));
     }
   } else {
     // ---- epilogue: thread = (team = TMEM lane, column block cb of 32 experts) ----
     const int qd = warp & 3, cb = warp >> 2;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
-    int team[NH];
-    bool team_ok[NH];
-    float Tz[NH];
-    int bK[NH];
-#pragma unroll
-    for (int hf = 0; hf < NH; ++hf) {
-      team[hf] = (bp * NH + hf) * TT + qd * 32 + lane;
-      team_ok[hf] = hf < nh && team[hf] < g.B;
-      Tz[hf] = 0.f; bK[hf] = 0;
-      if (PASS == 2 && team_ok[hf]) { Tz[hf] = __ldg(g.thr_val + team[hf]); bK[hf] = __ldg(g.thr_blk + team[hf]); }
-    }
+    const int team0 = bp * NH * TT + qd * 32 + lane;  // this thread's team of batch tile hf: team0 + hf * TT
     const float NEG_INF = __int_as_float(0xff800000);
+    uint32_t win[NH];  // pass 2: per batch tile the team's block bits of 8 expert tiles (bit 4 * (it % 8) + cb = this thread's block of tile it)
     for (int it = 0; it < ntiles; ++it) {
       const int e_base = (t0 + it) * TX + cb * BLK;  // first expert of this thread's block
       const int blk = (t0 + it) * 4 + cb;
-      // the block's biases (the same 32 addresses in every lane: broadcast loads); past E: -inf so that the column can never win
-      float bv[BLK];
-      if (e_base + BLK <= g.E) {
+      if (PASS == 2 && (it & 7) == 0) {  // (once per 8 expert tiles = 32 products)
+        const int bit0 = (t0 + it) * 4, wi = bit0 >> 5;
 #pragma unroll
-        for (int u = 0; u < BLK / 4; ++u) {
-          const float4 f = __ldg(reinterpret_cast<const float4*>(g.bias + e_base) + u);
-          bv[4 * u] = f.x; bv[4 * u + 1] = f.y; bv[4 * u + 2] = f.z; bv[4 * u + 3] = f.w;
+        for (int hf = 0; hf < NH; ++hf) {
+          const int team = team0 + hf * TT;
+          win[hf] = 0u;
+          if (hf < nh && team < g.B) {
+            const uint32_t* wp = g.bits + (size_t)wi * g.B + team;  // word-major: the 32 teams of a warp read 128 consecutive bytes
+            win[hf] = __funnelshift_r(__ldg(wp), wi + 1 < g.nwords ? __ldg(wp + g.B) : 0u, bit0 & 31);
+          }
+        }
+      }
+      float bv[BLK];       // pass 1: the block's biases (the same 32 addresses in every lane: broadcast loads); past E: -inf, the column can never win
+      uint32_t slotv[NH];  // pass 2: the slot of this thread's block per batch tile, fetched here, used 1..4 products later
+      if (PASS == 1) {
+        if (e_base + BLK <= g.E) {
+#pragma unroll
+          for (int u = 0; u < BLK / 4; ++u) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(g.bias + e_base) + u);
+            bv[4 * u] = f.x; bv[4 * u + 1] = f.y; bv[4 * u + 2] = f.z; bv[4 * u + 3] = f.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < BLK; ++i) bv[i] = (e_base + i < g.E) ? __ldg(g.bias + e_base + i) : NEG_INF;
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < BLK; ++i) bv[i] = (e_base + i < g.E) ? __ldg(g.bias + e_base + i) : NEG_INF;
+        for (int hf = 0; hf < NH; ++hf) {
+          slotv[hf] = 0u;
+          if ((win[hf] >> (4 * (it & 7) + cb)) & 1u) slotv[hf] = __ldg(g.slot + (size_t)(team0 + hf * TT) * g.nblk + blk);
+        }
       }
 #pragma unroll
       for (int hf = 0; hf < NH; ++hf) {
         if (hf >= nh) break;
         const int q = it * nh + hf, zs = q % Z_STAGES;
+        const int team = team0 + hf * TT;
+        const bool team_ok = team < g.B;
+        const bool mine = PASS == 2 && ((win[hf] >> (4 * (it & 7) + cb)) & 1u) != 0u;  // (0 for teams past B)
         mbar_wait(bar(BAR_Z_FULL + zs), (q / Z_STAGES) & 1);
-        if (g.timing && threadIdx.x == 0 && q < 60) g.timing[256 * blockIdx.x + 8 + 4 * q + 2] = clock64();
+        if (timing && threadIdx.x == 0 && q < 60) timing[256 * blockIdx.x + 8 + 4 * q + 2] = clock64();
+        // The TMEM read port (64 B per cycle: 1024 cycles for a product's 64 KB of fp32 logits against 512 of tensor time) paces pass 1.
+        // Pass 2 reads a warp's [32 teams x 32 experts] only when one of its 32 (team, block) pairs is among the K best: ~K/44 of the warps.
+        if (PASS == 2 && !__any_sync(0xffffffffu, mine)) {
+          mbar_arrive(bar(BAR_Z_EMPTY + zs));
+          continue;
+        }
         tc_fence_after();
         float z[BLK];
         tmem_ld32(tmem + lane_base + zs * TX + cb * BLK, z);
         tc_fence_before();
         mbar_arrive(bar(BAR_Z_EMPTY + zs));
-        float m = NEG_INF;
-#pragma unroll
-        for (int i = 0; i < BLK; ++i) { z[i] += bv[i]; m = fmaxf(m, z[i]); }
         if (PASS == 1) {
-          if (team_ok[hf]) g.bm[(size_t)team[hf] * g.nblk + blk] = m;
-        } else {
-          const float tz = Tz[hf];
-          const bool tie_ok = blk <= bK[hf];
-          if (team_ok[hf] && m >= tz && (m > tz || tie_ok)) {  // rare: K of the E/32 blocks of a team get here
+          float m = NEG_INF;
 #pragma unroll
-            for (int i = 0; i < BLK; ++i) {
-              const float v = z[i];
-              if (v > tz || (v == tz && tie_ok)) {
-                const int slot = atomicAdd(g.cnt + team[hf], 1);
-                if (slot < g.cap) g.cand[(size_t)team[hf] * g.cap + slot] = ((unsigned long long)ordered_key(v) << 32) | (uint32_t)(~(uint32_t)(e_base + i));
-              }
-            }
-          }
+          for (int i = 0; i < BLK; ++i) m = fmaxf(m, z[i] + bv[i]);
+          if (team_ok) g.bm[(size_t)team * g.nblk + blk] = m;
+        } else if (mine) {  // K of the E/32 blocks of a team: the block's 32 raw products, 128 contiguous bytes (the final kernel adds the biases)
+          float4* dst = reinterpret_cast<float4*>(g.cand + ((size_t)team * g.K + slotv[hf]) * BLK);
+#pragma unroll
+          for (int i = 0; i < BLK; i += 4) dst[i >> 2] = make_float4(z[i], z[i + 1], z[i + 2], z[i + 3]);
         }
-        if (g.timing && threadIdx.x == 0 && q < 60) g.timing[256 * blockIdx.x + 8 + 4 * q + 3] = clock64();
+        if (timing && threadIdx.x == 0 && q < 60) timing[256 * blockIdx.x + 8 + 4 * q + 3] = clock64();
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (g.timing && threadIdx.x == 0) g.timing[256 * blockIdx.x + 1] = clock64();
+  if (timing && threadIdx.x == 0) timing[256 * blockIdx.x + 1] = clock64();
   if (warp == WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
 }
 
-// per team: the candidates in rank order -> the first K as (probability, global expert id).  One CTA per team; bitonic sort in shared memory.
+// candidate i of team n: slot i / 32, expert slot_blk * 32 + i % 32; its logit = the stored product + the expert's bias (the same fp32 add as
+// pass 1's); the composite (ordered logit << 32 | ~expert) if the logit is >= the team's Tz and the expert exists, else 0 (= no candidate)
+__device__ __forceinline__ unsigned long long candidate(const float* __restrict__ cand, const int32_t* __restrict__ slot_blk, const float* __restrict__ bias, int n,
+                                                        int K, int E, uint32_t kz, int i) {
+  const int e = __ldg(slot_blk + (size_t)n * K + (i >> 5)) * BLK + (i & 31);
+  if (e >= E) return 0ull;
+  const uint32_t key = ordered_key(__ldg(cand + (size_t)n * K * BLK + i) + __ldg(bias + e));
+  return key >= kz ? ((unsigned long long)key << 32) | (uint32_t)(~(uint32_t)e) : 0ull;
+}
+
+// per team: the candidates >= Tz in rank order -> the first K as (probability, global expert id).  One CTA per team; the 32*K candidates of the
+// K blocks pass 2 stored are filtered into shared memory (a few per block survive), then a bitonic sort of the survivors.
 constexpr int FIN_THREADS = 128;
-__global__ void __launch_bounds__(FIN_THREADS) infer_topk_final_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cnt, int cap, int K,
-                                                                        int e_lo, float* __restrict__ vals, int32_t* __restrict__ idx) {
-  extern __shared__ unsigned long long sel[];
+__global__ void __launch_bounds__(FIN_THREADS) infer_topk_final_kernel(const float* __restrict__ cand, const int32_t* __restrict__ slot_blk,
+                                                                       const float* __restrict__ bias, const float* __restrict__ thr_val, int cap, int K, int E,
+                                                                       int e_lo, float* __restrict__ vals, int32_t* __restrict__ idx) {
+  extern __shared__ unsigned long long sel[];  // [npad(cap)]
+  __shared__ int nsel;
   const int n = blockIdx.x;
-  const int c = min(cnt[n], cap);
+  if (threadIdx.x == 0) nsel = 0;
+  __syncthreads();
+  const uint32_t kz = ordered_key(thr_val[n]);
+  for (int i = threadIdx.x; i < cap; i += FIN_THREADS) {
+    const unsigned long long x = candidate(cand, slot_blk, bias, n, K, E, kz, i);
+    if (x) sel[atomicAdd(&nsel, 1)] = x;
+  }
+  __syncthreads();
+  const int c = nsel;
   int npad = 32;
   while (npad < c) npad <<= 1;
-  for (int i = threadIdx.x; i < npad; i += FIN_THREADS) sel[i] = i < c ? cand[(size_t)n * cap + i] : 0ull;
+  for (int i = c + threadIdx.x; i < npad; i += FIN_THREADS) sel[i] = 0ull;
   __syncthreads();
   for (int k = 2; k <= npad; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -257,56 +303,171 @@ __global__ void __launch_bounds__(FIN_THREADS) infer_topk_final_kernel(const uns
   }
 }
 
-// per team (one CTA of 4 warps): Tz = the K-th largest of the row's block maxima and bK = the block that holds it under the rank order (value
-// descending, ties -> lower block first).  Bisection on the order-preserving integer image of the fp32 maxima: 32 rounds of "how many keys
-// >= candidate" (register-resident keys, PL per thread in contiguous chunks so that ties can be ranked by block id; one barrier per round).
+// per team (one CTA of 4 warps): Tz = the K-th largest of the row's block maxima under the order (value descending, block ascending), and for
+// every block whether it is one of the K at or above it (a bit, bits[blk / 32][team]) and, if so, its slot 0..K-1 (a byte, slot[team][blk];
+// slot_blk[team][slot] = the block).
+// Adaptive radix select on the order-preserving integer image of the maxima: the keys stay in registers (PL per thread); a round histograms
+// the ones inside the current range [lo, hi] into 256 equal bins of that range (shared-memory atomics -- the range starts at the row's
+// min..max, so the keys spread over the bins), every warp scans the bins from the top for the one that holds the wanted rank, and the
+// range shrinks to that bin.  As soon as the bin holds <= 128 keys, their (key, block) composites are gathered and ranked by counting; on
+// logits one round is the rule.  More than 128 EQUAL keys (a bin of width 1): the select restarts on the block numbers of those keys.
+// K <= 128 (ntf_infer_topk_supported): a slot fits a byte next to the 255 marker.
 template <int PL>
-__global__ void __launch_bounds__(128) blockmax_threshold_kernel(const float* __restrict__ bm, int nblk, int K, float* __restrict__ thr_val,
-                                                                 int32_t* __restrict__ thr_blk) {
-  __shared__ int cnt[2][4];
-  __shared__ int wsum[2][4];
+__global__ void __launch_bounds__(128) blockmax_threshold_kernel(const float* __restrict__ bm, int nblk, int nwords, int K, float* __restrict__ thr_val,
+                                                                 uint8_t* __restrict__ slot, uint32_t* __restrict__ bits, int32_t* __restrict__ slot_blk) {
+  __shared__ __align__(16) uint32_t hist[3][256];
+  __shared__ uint32_t red[2][4];
+  __shared__ unsigned long long list[128];
+  __shared__ unsigned long long kth;
+  __shared__ int nlist, nslot;
   const int team = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int per = (nblk + 127) / 128;  // <= PL (checked by the host)
   const float* row = bm + (size_t)team * nblk;
-  const int first = tid * per;
-  uint32_t key[PL];
+  uint32_t key[PL];  // 0 = no such block (< every real key)
+  uint32_t v[PL];    // what the select runs on: the key, later (ties) 4096 - block of the keys equal to Tz; 0 = not taking part
+  uint32_t lo = ~0u, hi = 0u;
 #pragma unroll
-  for (int i = 0; i < PL; ++i) key[i] = (i < per && first + i < nblk) ? ordered_key(__ldg(row + first + i)) : 0u;  // 0 < every real key
-  uint32_t T = 0u;
-#pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t cand = T | (1u << bit);
-    int c0 = 0, c1 = 0;
-#pragma unroll
-    for (int i = 0; i < PL; i += 2) { c0 += key[i] >= cand; if (i + 1 < PL) c1 += key[i + 1] >= cand; }
-    const int c = __reduce_add_sync(0xffffffffu, c0 + c1);
-    if (lane == 0) cnt[bit & 1][w] = c;
-    __syncthreads();  // (the buffer of round r is rewritten in round r+2, after everybody passed round r+1's barrier)
-    if (cnt[bit & 1][0] + cnt[bit & 1][1] + cnt[bit & 1][2] + cnt[bit & 1][3] >= K) T = cand;
+  for (int i = 0; i < PL; ++i) {
+    const int blk = i * 128 + tid;
+    key[i] = blk < nblk ? ordered_key(__ldg(row + blk)) : 0u;
+    v[i] = key[i];
+    if (blk < nblk) { lo = min(lo, key[i]); hi = max(hi, key[i]); }
   }
-  int gt = 0, eq = 0;
-#pragma unroll
-  for (int i = 0; i < PL; ++i) { gt += key[i] > T; eq += key[i] == T; }
-  const int gtw = __reduce_add_sync(0xffffffffu, gt);
-  int incl = eq;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 0) wsum[0][w] = gtw;
-  if (lane == 31) wsum[1][w] = incl;
+  for (int i = tid; i < 3 * 256; i += 128) (&hist[0][0])[i] = 0u;
+  if (tid == 0) { nlist = 0; nslot = 0; }
+  lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+  if (lane == 0) { red[0][w] = lo; red[1][w] = hi; }
   __syncthreads();
-  const int need = K - (wsum[0][0] + wsum[0][1] + wsum[0][2] + wsum[0][3]);  // the need-th block (in id order) whose maximum equals Tz is the K-th block
-  int before = incl - eq;
-  for (int q = 0; q < w; ++q) before += wsum[1][q];
-  if (before < need && need <= before + eq) {
-    int seen = before, blk = first;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { lo = min(lo, red[0][q]); hi = max(hi, red[1][q]); }
+  int need = K;        // the wanted element is the need-th largest of the v inside [lo, hi]
+  uint32_t tie_key = 0u;  // != 0: the select is on block numbers among the keys equal to this one
+#pragma unroll 1
+  for (int r = 0;; ++r) {
+    const uint32_t width = hi - lo;
+    const int shift = width < 256u ? 0 : 24 - __clz((int)width);  // (width >> shift) < 256
+    uint32_t* h = hist[r % 3];
+    uint32_t* hn = hist[(r + 1) % 3];  // last read in round r-2: every warp is past that scan (it passed round r-1's barrier)
+    hn[tid] = 0u; hn[tid + 128] = 0u;
 #pragma unroll
     for (int i = 0; i < PL; ++i)
-      if (key[i] == T && ++seen == need) blk = first + i;
-    thr_val[team] = key_to_float(T);
-    thr_blk[team] = blk;
+      if (v[i] >= lo && v[i] <= hi) atomicAdd(&h[(v[i] - lo) >> shift], 1u);
+    __syncthreads();
+    // every warp: lane l owns bins 8l..8l+7; suffix sums from the top bin down
+    const uint4 h0 = reinterpret_cast<const uint4*>(h)[2 * lane], h1 = reinterpret_cast<const uint4*>(h)[2 * lane + 1];
+    const int c[8] = {(int)h0.x, (int)h0.y, (int)h0.z, (int)h0.w, (int)h1.x, (int)h1.y, (int)h1.z, (int)h1.w};
+    const int mine = c[0] + c[1] + c[2] + c[3] + c[4] + c[5] + c[6] + c[7];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += t;
+    }
+    int above = incl - mine;  // elements in the bins of the higher lanes
+    const bool holds = above < need && need <= incl;
+    int bin = 0, cbin = 0;
+    if (holds) {
+#pragma unroll
+      for (int j = 7; j >= 0; --j) {
+        if (above < need && need <= above + c[j]) { bin = 8 * lane + j; cbin = c[j]; break; }
+        above += c[j];
+      }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, holds)) - 1;  // (exactly one lane: K <= the number of blocks)
+    bin = __shfl_sync(0xffffffffu, bin, src); cbin = __shfl_sync(0xffffffffu, cbin, src); above = __shfl_sync(0xffffffffu, above, src);
+    need -= above;
+    lo += (uint32_t)bin << shift;
+    hi = min(hi, lo + ((1u << shift) - 1u));
+    if (cbin <= 128) break;
+    if (shift == 0) {  // > 128 keys equal to lo: the need-th of them in block order, i.e. the need-th largest of 4096 - block
+      tie_key = lo;
+#pragma unroll
+      for (int i = 0; i < PL; ++i) v[i] = key[i] == tie_key ? (uint32_t)(4096 - (i * 128 + tid)) : 0u;
+      lo = 1u; hi = 4096u;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < PL; ++i)
+    if (v[i] >= lo && v[i] <= hi) list[atomicAdd(&nlist, 1)] = ((unsigned long long)key[i] << 12) | (unsigned)(4095 - (i * 128 + tid));
+  __syncthreads();
+  const int n = nlist;
+  if (tid < n) {
+    const unsigned long long x = list[tid];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += list[j] > x;
+    if (rank == need - 1) {
+      thr_val[team] = key_to_float((uint32_t)(x >> 12));
+      kth = x;
+    }
+  }
+  __syncthreads();
+  const unsigned long long x = kth;  // exactly K composites are >= it: they get the slots 0..K-1 (in any order)
+#pragma unroll
+  for (int i = 0; i < PL; ++i) {
+    const int blk = i * 128 + tid;
+    const bool in = blk < nblk && (((unsigned long long)key[i] << 12) | (unsigned)(4095 - blk)) >= x;
+    const uint32_t word = __ballot_sync(0xffffffffu, in);  // blocks 32 (4 i + w) .. + 31
+    if (lane == 0 && 4 * i + w < nwords) bits[(size_t)(4 * i + w) * gridDim.x + team] = word;  // [nwords][B]: pass 2 reads it by 32 teams
+    if (in) {
+      const int sl = atomicAdd(&nslot, 1);
+      slot[(size_t)team * nblk + blk] = (uint8_t)sl;
+      slot_blk[(size_t)team * K + sl] = blk;
+    }
+  }
+}
+
+// K <= 32: one WARP per team, no shared memory, no barriers.  The warp keeps the K best composites, rank r in lane r (topk.cu's small-K
+// list); the team's K candidate blocks are offered 32 candidates at a time, one above the current K-th is inserted by one shuffle-shift.
+__global__ void __launch_bounds__(128) infer_topk_final_warp_kernel(const float* __restrict__ cand, const int32_t* __restrict__ slot_blk, const float* __restrict__ bias,
+                                                                     const float* __restrict__ thr_val, int cap, int K, int E, int e_lo, int B,
+                                                                     float* __restrict__ vals, int32_t* __restrict__ idx) {
+  const int n = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (n >= B) return;
+  const uint32_t kz = ordered_key(thr_val[n]);
+  const int sb = lane < K ? __ldg(slot_blk + (size_t)n * K + lane) : 0;  // lane s: the block of slot s
+  unsigned long long mine = 0ull, kth = 0ull;  // (0 = empty: a real composite is never 0)
+  constexpr int G = 8;  // slots per group: their 2 G loads are in flight together (the kernel is a chain of memory latencies otherwise)
+  for (int s0 = 0; s0 < K; s0 += G) {
+    unsigned long long xs[G];
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int s = min(s0 + u, K - 1);
+      const int e = __shfl_sync(0xffffffffu, sb, s) * BLK + lane;
+      const float zz = __ldg(cand + ((size_t)n * K + s) * BLK + lane), bb = __ldg(bias + min(e, E - 1));
+      const uint32_t key = ordered_key(zz + bb);
+      xs[u] = (s0 + u < K && e < E && key >= kz) ? ((unsigned long long)key << 32) | (uint32_t)(~(uint32_t)e) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const unsigned long long x = xs[u];
+      unsigned hit = __ballot_sync(0xffffffffu, x > kth);
+      while (hit) {
+        const int L = __ffs(hit) - 1;
+        hit &= hit - 1;
+        const unsigned long long v = __shfl_sync(0xffffffffu, x, L);
+        if (v > kth) {  // (an earlier insert of this round may have raised the bar)
+          const unsigned long long up = __shfl_up_sync(0xffffffffu, mine, 1);
+          const unsigned long long prev = lane == 0 ? ~0ull : up;
+          if (v > mine) mine = v > prev ? prev : v;  // ranks below the insertion point shift down by one, the point takes v
+          if (lane >= K) mine = 0ull;
+          kth = __shfl_sync(0xffffffffu, mine, K - 1);
+        }
+      }
+    }
+  }
+  if (lane < K) {
+    constexpr float LOG2E = 1.4426950408889634f;
+    float p = 0.f;
+    int32_t e = -1;
+    if (mine) {
+      const float zz = key_to_float((uint32_t)(mine >> 32));
+      const float x = fmaxf(zz, NTF_LRELU_SLOPE * zz);           // the arithmetic of ntf_infer_scores' tensor-core epilogue (out_tc.cu, MODE 1)
+      const float ex = ex2_approx(fabsf(x) * -LOG2E);
+      const float r = rcp_approx(1.f + ex);
+      p = zz > 0.f ? r : ex * r;
+      e = e_lo + (int32_t)(~(uint32_t)mine);
+    }
+    vals[(size_t)n * K + lane] = p;
+    idx[(size_t)n * K + lane] = e;
   }
 }
 
@@ -314,17 +475,18 @@ __global__ void to_half_kernel(const float* __restrict__ x, size_t n, __half* __
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = __float2half_rn(x[i]);
 }
 
-struct ItWs { size_t a16, bm, tv, ti, cnt, cand, total; };
+struct ItWs { size_t a16, bm, tv, slot, bits, sblk, cand, total; };
 ItWs it_ws(int B, int h, int E, int K) {
   const size_t nblk = (size_t)cdiv(E, TX) * 4;
   ItWs w;
   w.a16 = 0;
   w.bm = w.a16 + align_up((size_t)B * h * sizeof(__half), 1024);
   w.tv = w.bm + align_up((size_t)B * nblk * sizeof(float), 1024);
-  w.ti = w.tv + align_up((size_t)B * sizeof(float), 1024);
-  w.cnt = w.ti + align_up((size_t)B * sizeof(int32_t), 1024);
-  w.cand = w.cnt + align_up((size_t)B * sizeof(int), 1024);
-  w.total = w.cand + align_up((size_t)B * (size_t)(BLK * K) * sizeof(unsigned long long), 1024);
+  w.slot = w.tv + align_up((size_t)B * sizeof(float), 1024);
+  w.bits = w.slot + align_up((size_t)B * nblk, 1024);
+  w.sblk = w.bits + align_up((size_t)B * cdiv((int)nblk, 32) * sizeof(uint32_t), 1024);
+  w.cand = w.sblk + align_up((size_t)B * K * sizeof(int32_t), 1024);
+  w.total = w.cand + align_up((size_t)B * (size_t)(BLK * K) * sizeof(float), 1024);
   return w;
 }
 }  // namespace
@@ -372,11 +534,14 @@ extern "C" int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_a
   g.nblk = g.nct * 4;
   g.bm = (float*)(ws + w.bm);
   float* tv = (float*)(ws + w.tv);
-  int32_t* ti = (int32_t*)(ws + w.ti);
-  g.thr_val = tv; g.thr_blk = ti;
-  g.cnt = (int*)(ws + w.cnt);
-  g.cand = (unsigned long long*)(ws + w.cand);
-  g.cap = BLK * a->K;
+  uint8_t* slot = (uint8_t*)(ws + w.slot);
+  uint32_t* bits = (uint32_t*)(ws + w.bits);
+  g.slot = slot; g.bits = bits; g.nwords = cdiv(g.nblk, 32);
+  g.cand = (float*)(ws + w.cand);
+  int32_t* sblk = (int32_t*)(ws + w.sblk);
+  const int cap = BLK * a->K;
+  const char* tp = getenv("NTF_IT_TIMING_PASS");
+  g.timing_pass = tp ? atoi(tp) : 2;
   const char* tim = getenv("NTF_IT_TIMING");
   g.timing = tim ? (long long*)(uintptr_t)strtoull(tim, nullptr, 0) : nullptr;
   CUtensorMap ma, mw;
@@ -390,22 +555,29 @@ extern "C" int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_a
     NTF_CUDA(cudaFuncSetAttribute(infer_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     attr_set[ctx->device & 63] = true;
   }
-  NTF_CUDA(cudaMemsetAsync(g.cnt, 0, (size_t)a->B * sizeof(int), st));
+  static const int stop_after = getenv("NTF_IT_STOP") ? atoi(getenv("NTF_IT_STOP")) : 0;  // debug: leave after stage 1..3 (scripts/topk_stages.sh times the prefixes)
   NTF_COUNT_LAUNCH; infer_topk_kernel<1><<<grid, NT, SMEM_BYTES, st>>>(ma, mw, g);
   NTF_LAUNCH_CHECK();
+  if (stop_after == 1) return NTF_OK;
   {
-    const int per = cdiv(g.nblk, 128);
+    const int per = cdiv(g.nblk, 128);  // <= 32: ntf_infer_topk_supported
     NTF_COUNT_LAUNCH;
-    if (per <= 4) blockmax_threshold_kernel<4><<<a->B, 128, 0, st>>>(g.bm, g.nblk, a->K, tv, ti);
-    else if (per <= 12) blockmax_threshold_kernel<12><<<a->B, 128, 0, st>>>(g.bm, g.nblk, a->K, tv, ti);
-    else blockmax_threshold_kernel<32><<<a->B, 128, 0, st>>>(g.bm, g.nblk, a->K, tv, ti);
+    if (per <= 4) blockmax_threshold_kernel<4><<<a->B, 128, 0, st>>>(g.bm, g.nblk, g.nwords, a->K, tv, slot, bits, sblk);
+    else if (per <= 12) blockmax_threshold_kernel<12><<<a->B, 128, 0, st>>>(g.bm, g.nblk, g.nwords, a->K, tv, slot, bits, sblk);
+    else blockmax_threshold_kernel<32><<<a->B, 128, 0, st>>>(g.bm, g.nblk, g.nwords, a->K, tv, slot, bits, sblk);
     NTF_LAUNCH_CHECK();
   }
+  if (stop_after == 2) return NTF_OK;
   NTF_COUNT_LAUNCH; infer_topk_kernel<2><<<grid, NT, SMEM_BYTES, st>>>(ma, mw, g);
   NTF_LAUNCH_CHECK();
-  int npad = 32;
-  while (npad < g.cap) npad <<= 1;
-  NTF_COUNT_LAUNCH; infer_topk_final_kernel<<<a->B, FIN_THREADS, (size_t)npad * 8, st>>>(g.cand, g.cnt, g.cap, a->K, a->e_lo, a->vals, a->idx);
+  if (stop_after == 3) return NTF_OK;
+  if (a->K <= 32) {
+    NTF_COUNT_LAUNCH; infer_topk_final_warp_kernel<<<cdiv(a->B, 4), 128, 0, st>>>(g.cand, sblk, a->b, tv, cap, a->K, a->E, a->e_lo, a->B, a->vals, a->idx);
+  } else {
+    int npad = 32;
+    while (npad < cap) npad <<= 1;
+    NTF_COUNT_LAUNCH; infer_topk_final_kernel<<<a->B, FIN_THREADS, (size_t)npad * 8, st>>>(g.cand, sblk, a->b, tv, cap, a->K, a->E, a->e_lo, a->vals, a->idx);
+  }
   NTF_LAUNCH_CHECK();
   return NTF_OK;
 }
