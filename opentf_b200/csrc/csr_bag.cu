@@ -7,6 +7,8 @@
 //   ntf_act_bwd       : dZ = dY*lrelu'(Y), db = colsum(dZ)
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // =========================================================================================================
@@ -205,6 +207,10 @@ __global__ void __launch_bounds__(256) csr_bag_fwd_kernel(int B, const int32_t* 
                                                           const int32_t* __restrict__ indices,
                                                           const float* __restrict__ W0T, const float* __restrict__ b0,
                                                           int h, float* __restrict__ A, __half* __restrict__ A16) {
+  // programmatic dependent launch (infer_topk.cu): the kernel chained behind this one may set itself up meanwhile; launched `chained`, this
+  // one starts while the kernel before it drains and waits here for its memory (no-ops in a plain launch)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < B; n += warps) {
@@ -254,9 +260,10 @@ __global__ void __launch_bounds__(256) csr_bag_fwd_kernel(int B, const int32_t* 
 }
 }  // namespace
 
-// A16 (nullable): also write the activations as fp16 [B,h] (operand of the tensor-core output layer)
+// A16 (nullable): also write the activations as fp16 [B,h] (operand of the tensor-core output layer); chained: launch with the programmatic
+// stream-serialization attribute (the test-time chain of infer_topk.cu, one call per batch back to back)
 int ntf_csr_bag_fwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices, const float* W0T,
-                         const float* b0, int S, int h, float* A, void* A16v) {
+                         const float* b0, int S, int h, float* A, void* A16v, bool chained) {
   __half* A16 = (__half*)A16v;
   NTF_REQUIRE(ctx && indptr && indices && W0T && b0 && A, NTF_ERR_BAD_ARG, "csr_bag_fwd: null pointer");
   NTF_REQUIRE(B >= 0 && S > 0 && h > 0, NTF_ERR_BAD_ARG, "csr_bag_fwd: B=%d S=%d h=%d", B, S, h);
@@ -264,15 +271,19 @@ int ntf_csr_bag_fwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* indpt
   const int blocks = min(cdiv(B, 8), ctx->sm_count * 8);
   const bool vec = (h % 4 == 0) && (((uintptr_t)W0T | (uintptr_t)b0 | (uintptr_t)A) % 16 == 0) && ((uintptr_t)A16 % 8 == 0);
   NTF_COUNT_LAUNCH;
-  if (vec) csr_bag_fwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(B, indptr, indices, W0T, b0, h, A, A16);
-  else csr_bag_fwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(B, indptr, indices, W0T, b0, h, A, A16);
-  NTF_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = blocks; cfg.blockDim = 256; cfg.stream = as_stream(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = chained ? 1 : 0;
+  NTF_CUDA(cudaLaunchKernelEx(&cfg, vec ? csr_bag_fwd_kernel<true> : csr_bag_fwd_kernel<false>, B, indptr, indices, W0T, b0, h, A, A16));
   return NTF_OK;
 }
 
 extern "C" int ntf_csr_bag_fwd(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices,
                                const float* W0T, const float* b0, int S, int h, float* A) {
-  return ntf_csr_bag_fwd_impl(ctx, stream, B, indptr, indices, W0T, b0, S, h, A, nullptr);
+  return ntf_csr_bag_fwd_impl(ctx, stream, B, indptr, indices, W0T, b0, S, h, A, nullptr, false);
 }
 
 // Bnn / Flipout input layer (bayesian-torch LinearFlipout on a multi-hot row):

@@ -58,6 +58,16 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr uint32_t IDESC = instr_desc(0, 0, 0, TT, TX);  // Z = A16(K-major) . W16(K-major)^T, fp16 operands, fp32 accumulate
 constexpr int BLK = 32;  // experts per block (= the 32 TMEM columns one epilogue thread reads)
 
+// Programmatic dependent launch: every kernel of the chain lets the next one start its CTAs (launch latency, barrier / TMEM set-up) while it is
+// still running, and itself touches global memory only after the kernel before it has completed and flushed (griddepcontrol.wait; without
+// the launch attribute both are no-ops).  The chain is transitive: a kernel that has completed has seen its predecessor complete.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t ordered_key(float f) {
   const uint32_t b = __float_as_uint(f);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -75,7 +85,7 @@ struct ItArgs {
   int nwords;
   float* cand;           // pass 2 out: [B, K, 32] the products a.w (no bias yet) of the team's K best blocks, slot by slot; every entry written
   int timing_pass;
-  long long* timing;         // debug (NTF_IT_TIMING): per CTA 256 slots: [0] start clock, [1] end clock; from 8, 4 per product q < 60: W tile landed (MMA warp),
+  long long* timing;         // debug (NTF_IT_TIMING): per CTA 256 slots: [0] start clock, [1] end clock, [2] [3] the same in globaltimer ns; from 8, 4 per product q < 60: W tile landed (MMA warp),
                              // product issued, logits ready (epilogue thread 0), epilogue done
 };
 
@@ -95,7 +105,7 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
   const int t0 = (int)((long long)chunk * g.nct / g.nchunk), t1 = (int)((long long)(chunk + 1) * g.nct / g.nchunk);
   const int ntiles = t1 - t0;
   long long* const timing = g.timing_pass == PASS ? g.timing : nullptr;
-  if (timing && threadIdx.x == 0) timing[256 * blockIdx.x] = clock64();
+  if (timing && threadIdx.x == 0) { timing[256 * blockIdx.x] = clock64(); timing[256 * blockIdx.x + 2] = (long long)globaltimer_ns(); }
 
   if (threadIdx.x == 0) {
     for (int hf = 0; hf < NH; ++hf) mbar_init(bar(BAR_A_FULL + hf), 1);
@@ -111,6 +121,8 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  griddep_launch();
+  griddep_wait();  // (everything above is set-up; the activations, the select's outputs and the workspace belong to the kernels before)
 
   if (warp == WARP_TMA) {
     if (lane == 0) {
@@ -234,22 +246,15 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (timing && threadIdx.x == 0) timing[256 * blockIdx.x + 1] = clock64();
+  if (timing && threadIdx.x == 0) { timing[256 * blockIdx.x + 1] = clock64(); timing[256 * blockIdx.x + 3] = (long long)globaltimer_ns(); }
   if (warp == WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
 }
 
-// candidate i of team n: slot i / 32, expert slot_blk * 32 + i % 32; its logit = the stored product + the expert's bias (the same fp32 add as
-// pass 1's); the composite (ordered logit << 32 | ~expert) if the logit is >= the team's Tz and the expert exists, else 0 (= no candidate)
-__device__ __forceinline__ unsigned long long candidate(const float* __restrict__ cand, const int32_t* __restrict__ slot_blk, const float* __restrict__ bias, int n,
-                                                        int K, int E, uint32_t kz, int i) {
-  const int e = __ldg(slot_blk + (size_t)n * K + (i >> 5)) * BLK + (i & 31);
-  if (e >= E) return 0ull;
-  const uint32_t key = ordered_key(__ldg(cand + (size_t)n * K * BLK + i) + __ldg(bias + e));
-  return key >= kz ? ((unsigned long long)key << 32) | (uint32_t)(~(uint32_t)e) : 0ull;
-}
+// Candidate i of a team: slot i / 32, expert slot_blk[slot] * 32 + i % 32; its logit = the stored product + the expert's bias (the same fp32 add
+// as pass 1's); it counts if the logit is >= the team's Tz and the expert exists; composite = ordered logit << 32 | ~expert (0 = none).
 
 // per team: the candidates >= Tz in rank order -> the first K as (probability, global expert id).  One CTA per team; the 32*K candidates of the
 // K blocks pass 2 stored are filtered into shared memory (a few per block survive), then a bitonic sort of the survivors.
@@ -259,13 +264,30 @@ __global__ void __launch_bounds__(FIN_THREADS) infer_topk_final_kernel(const flo
                                                                        int e_lo, float* __restrict__ vals, int32_t* __restrict__ idx) {
   extern __shared__ unsigned long long sel[];  // [npad(cap)]
   __shared__ int nsel;
+  __shared__ int sblk[128];  // K <= 128: the block of every slot
   const int n = blockIdx.x;
   if (threadIdx.x == 0) nsel = 0;
-  __syncthreads();
+  griddep_launch();
+  griddep_wait();
+  if (threadIdx.x < K) sblk[threadIdx.x] = __ldg(slot_blk + (size_t)n * K + threadIdx.x);
   const uint32_t kz = ordered_key(thr_val[n]);
-  for (int i = threadIdx.x; i < cap; i += FIN_THREADS) {
-    const unsigned long long x = candidate(cand, slot_blk, bias, n, K, E, kz, i);
-    if (x) sel[atomicAdd(&nsel, 1)] = x;
+  __syncthreads();
+  constexpr int U = 8;  // candidates per thread and round: their 2 U loads are in flight together (a chain of memory latencies otherwise)
+  for (int i0 = 0; i0 < cap; i0 += U * FIN_THREADS) {
+    float zz[U], bb[U];
+    int ee[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = min(i0 + u * FIN_THREADS + (int)threadIdx.x, cap - 1);
+      ee[u] = sblk[i >> 5] * BLK + (i & 31);
+      zz[u] = __ldg(cand + (size_t)n * cap + i);
+      bb[u] = __ldg(bias + min(ee[u], E - 1));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t key = ordered_key(zz[u] + bb[u]);
+      if (i0 + u * FIN_THREADS + (int)threadIdx.x < cap && ee[u] < E && key >= kz) sel[atomicAdd(&nsel, 1)] = ((unsigned long long)key << 32) | (uint32_t)(~(uint32_t)ee[u]);
+    }
   }
   __syncthreads();
   const int c = nsel;
@@ -322,6 +344,8 @@ __global__ void __launch_bounds__(128) blockmax_threshold_kernel(const float* __
   __shared__ int nlist, nslot;
   const int team = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const float* row = bm + (size_t)team * nblk;
+  griddep_launch();
+  griddep_wait();
   uint32_t key[PL];  // 0 = no such block (< every real key)
   uint32_t v[PL];    // what the select runs on: the key, later (ties) 4096 - block of the keys equal to Tz; 0 = not taking part
   uint32_t lo = ~0u, hi = 0u;
@@ -348,9 +372,12 @@ __global__ void __launch_bounds__(128) blockmax_threshold_kernel(const float* __
     uint32_t* h = hist[r % 3];
     uint32_t* hn = hist[(r + 1) % 3];  // last read in round r-2: every warp is past that scan (it passed round r-1's barrier)
     hn[tid] = 0u; hn[tid + 128] = 0u;
+    const uint32_t hbase = smem_u32(h);
 #pragma unroll
-    for (int i = 0; i < PL; ++i)
-      if (v[i] >= lo && v[i] <= hi) atomicAdd(&h[(v[i] - lo) >> shift], 1u);
+    for (int i = 0; i < PL; ++i) {  // (a predicated red.shared: no branch per key)
+      const uint32_t d = v[i] - lo;
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(hbase + ((d >> shift) << 2)), "r"(d), "r"(width) : "memory");
+    }
     __syncthreads();
     // every warp: lane l owns bins 8l..8l+7; suffix sums from the top bin down
     const uint4 h0 = reinterpret_cast<const uint4*>(h)[2 * lane], h1 = reinterpret_cast<const uint4*>(h)[2 * lane + 1];
@@ -387,7 +414,7 @@ __global__ void __launch_bounds__(128) blockmax_threshold_kernel(const float* __
   }
 #pragma unroll
   for (int i = 0; i < PL; ++i)
-    if (v[i] >= lo && v[i] <= hi) list[atomicAdd(&nlist, 1)] = ((unsigned long long)key[i] << 12) | (unsigned)(4095 - (i * 128 + tid));
+    if (v[i] - lo <= hi - lo) list[atomicAdd(&nlist, 1)] = ((unsigned long long)key[i] << 12) | (unsigned)(4095 - (i * 128 + tid));
   __syncthreads();
   const int n = nlist;
   if (tid < n) {
@@ -417,40 +444,41 @@ __global__ void __launch_bounds__(128) blockmax_threshold_kernel(const float* __
 
 // K <= 32: one WARP per team, no shared memory, no barriers.  The warp keeps the K best composites, rank r in lane r (topk.cu's small-K
 // list); the team's K candidate blocks are offered 32 candidates at a time, one above the current K-th is inserted by one shuffle-shift.
+template <int NG>
 __global__ void __launch_bounds__(128) infer_topk_final_warp_kernel(const float* __restrict__ cand, const int32_t* __restrict__ slot_blk, const float* __restrict__ bias,
                                                                      const float* __restrict__ thr_val, int cap, int K, int E, int e_lo, int B,
                                                                      float* __restrict__ vals, int32_t* __restrict__ idx) {
   const int n = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  griddep_launch();
+  griddep_wait();
   if (n >= B) return;
   const uint32_t kz = ordered_key(thr_val[n]);
   const int sb = lane < K ? __ldg(slot_blk + (size_t)n * K + lane) : 0;  // lane s: the block of slot s
   unsigned long long mine = 0ull, kth = 0ull;  // (0 = empty: a real composite is never 0)
-  constexpr int G = 8;  // slots per group: their 2 G loads are in flight together (the kernel is a chain of memory latencies otherwise)
-  for (int s0 = 0; s0 < K; s0 += G) {
-    unsigned long long xs[G];
+  // all 2 * 8 NG loads of the team's K <= 8 NG candidate blocks are issued before the first is used (the kernel is a chain of memory latencies otherwise)
+  unsigned long long xs[8 * NG];
 #pragma unroll
-    for (int u = 0; u < G; ++u) {
-      const int s = min(s0 + u, K - 1);
-      const int e = __shfl_sync(0xffffffffu, sb, s) * BLK + lane;
-      const float zz = __ldg(cand + ((size_t)n * K + s) * BLK + lane), bb = __ldg(bias + min(e, E - 1));
-      const uint32_t key = ordered_key(zz + bb);
-      xs[u] = (s0 + u < K && e < E && key >= kz) ? ((unsigned long long)key << 32) | (uint32_t)(~(uint32_t)e) : 0ull;
-    }
+  for (int u = 0; u < 8 * NG; ++u) {
+    const int s = min(u, K - 1);
+    const int e = __shfl_sync(0xffffffffu, sb, s) * BLK + lane;
+    const float zz = __ldg(cand + ((size_t)n * K + s) * BLK + lane), bb = __ldg(bias + min(e, E - 1));
+    const uint32_t key = ordered_key(zz + bb);
+    xs[u] = (u < K && e < E && key >= kz) ? ((unsigned long long)key << 32) | (uint32_t)(~(uint32_t)e) : 0ull;
+  }
 #pragma unroll
-    for (int u = 0; u < G; ++u) {
-      const unsigned long long x = xs[u];
-      unsigned hit = __ballot_sync(0xffffffffu, x > kth);
-      while (hit) {
-        const int L = __ffs(hit) - 1;
-        hit &= hit - 1;
-        const unsigned long long v = __shfl_sync(0xffffffffu, x, L);
-        if (v > kth) {  // (an earlier insert of this round may have raised the bar)
-          const unsigned long long up = __shfl_up_sync(0xffffffffu, mine, 1);
-          const unsigned long long prev = lane == 0 ? ~0ull : up;
-          if (v > mine) mine = v > prev ? prev : v;  // ranks below the insertion point shift down by one, the point takes v
-          if (lane >= K) mine = 0ull;
-          kth = __shfl_sync(0xffffffffu, mine, K - 1);
-        }
+  for (int u = 0; u < 8 * NG; ++u) {
+    const unsigned long long x = xs[u];
+    unsigned hit = __ballot_sync(0xffffffffu, x > kth);
+    while (hit) {
+      const int L = __ffs(hit) - 1;
+      hit &= hit - 1;
+      const unsigned long long v = __shfl_sync(0xffffffffu, x, L);
+      if (v > kth) {  // (an earlier insert of this round may have raised the bar)
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, mine, 1);
+        const unsigned long long prev = lane == 0 ? ~0ull : up;
+        if (v > mine) mine = v > prev ? prev : v;  // ranks below the insertion point shift down by one, the point takes v
+        if (lane >= K) mine = 0ull;
+        kth = __shfl_sync(0xffffffffu, mine, K - 1);
       }
     }
   }
@@ -473,6 +501,18 @@ __global__ void __launch_bounds__(128) infer_topk_final_warp_kernel(const float*
 
 __global__ void to_half_kernel(const float* __restrict__ x, size_t n, __half* __restrict__ y) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = __float2half_rn(x[i]);
+}
+
+// <<<>>> with the programmatic-stream-serialization attribute (see griddep_wait)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 struct ItWs { size_t a16, bm, tv, slot, bits, sblk, cand, total; };
@@ -556,27 +596,25 @@ extern "C" int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_a
     attr_set[ctx->device & 63] = true;
   }
   static const int stop_after = getenv("NTF_IT_STOP") ? atoi(getenv("NTF_IT_STOP")) : 0;  // debug: leave after stage 1..3 (scripts/topk_stages.sh times the prefixes)
-  NTF_COUNT_LAUNCH; infer_topk_kernel<1><<<grid, NT, SMEM_BYTES, st>>>(ma, mw, g);
-  NTF_LAUNCH_CHECK();
+  static const bool pdl = !getenv("NTF_IT_PDL") || atoi(getenv("NTF_IT_PDL")) != 0;
+  NTF_COUNT_LAUNCH; NTF_CUDA(launch_chained(infer_topk_kernel<1>, grid, NT, SMEM_BYTES, st, pdl, ma, mw, g));
   if (stop_after == 1) return NTF_OK;
   {
     const int per = cdiv(g.nblk, 128);  // <= 32: ntf_infer_topk_supported
     NTF_COUNT_LAUNCH;
-    if (per <= 4) blockmax_threshold_kernel<4><<<a->B, 128, 0, st>>>(g.bm, g.nblk, g.nwords, a->K, tv, slot, bits, sblk);
-    else if (per <= 12) blockmax_threshold_kernel<12><<<a->B, 128, 0, st>>>(g.bm, g.nblk, g.nwords, a->K, tv, slot, bits, sblk);
-    else blockmax_threshold_kernel<32><<<a->B, 128, 0, st>>>(g.bm, g.nblk, g.nwords, a->K, tv, slot, bits, sblk);
-    NTF_LAUNCH_CHECK();
+    auto* sel = per <= 4 ? blockmax_threshold_kernel<4> : per <= 12 ? blockmax_threshold_kernel<12> : blockmax_threshold_kernel<32>;
+    NTF_CUDA(launch_chained(sel, a->B, 128, 0, st, pdl, (const float*)g.bm, g.nblk, g.nwords, a->K, tv, slot, bits, sblk));
   }
   if (stop_after == 2) return NTF_OK;
-  NTF_COUNT_LAUNCH; infer_topk_kernel<2><<<grid, NT, SMEM_BYTES, st>>>(ma, mw, g);
-  NTF_LAUNCH_CHECK();
+  NTF_COUNT_LAUNCH; NTF_CUDA(launch_chained(infer_topk_kernel<2>, grid, NT, SMEM_BYTES, st, pdl, ma, mw, g));
   if (stop_after == 3) return NTF_OK;
   if (a->K <= 32) {
-    NTF_COUNT_LAUNCH; infer_topk_final_warp_kernel<<<cdiv(a->B, 4), 128, 0, st>>>(g.cand, sblk, a->b, tv, cap, a->K, a->E, a->e_lo, a->B, a->vals, a->idx);
+    auto* fin = a->K <= 8 ? infer_topk_final_warp_kernel<1> : a->K <= 16 ? infer_topk_final_warp_kernel<2> : a->K <= 24 ? infer_topk_final_warp_kernel<3> : infer_topk_final_warp_kernel<4>;
+    NTF_COUNT_LAUNCH; NTF_CUDA(launch_chained(fin, cdiv(a->B, 4), 128, 0, st, pdl, (const float*)g.cand, (const int32_t*)sblk, a->b, (const float*)tv, cap, a->K, a->E, a->e_lo, a->B, a->vals, a->idx));
   } else {
     int npad = 32;
     while (npad < cap) npad <<= 1;
-    NTF_COUNT_LAUNCH; infer_topk_final_kernel<<<a->B, FIN_THREADS, (size_t)npad * 8, st>>>(g.cand, sblk, a->b, tv, cap, a->K, a->E, a->e_lo, a->vals, a->idx);
+    NTF_COUNT_LAUNCH; NTF_CUDA(launch_chained(infer_topk_final_kernel, a->B, FIN_THREADS, (size_t)npad * 8, st, pdl, g.cand, sblk, a->b, tv, cap, a->K, a->E, a->e_lo, a->vals, a->idx));
   }
   NTF_LAUNCH_CHECK();
   return NTF_OK;

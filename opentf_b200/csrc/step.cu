@@ -18,7 +18,7 @@ int ntf_neg_sample_impl(ntf_ctx* ctx, void* stream, int nsd, uint64_t seed, uint
 int ntf_adam_step_impl(ntf_ctx* ctx, cudaStream_t st, float* p, const float* g, float* m, float* v, size_t n, double lr, double beta1,
                        double beta2, double eps, int64_t step, const ntf_dyn* dyn, void* shadow, size_t sh_off, size_t sh_n);
 int ntf_csr_bag_fwd_impl(ntf_ctx* ctx, void* stream, int B, const int32_t* indptr, const int32_t* indices, const float* W0T,
-                         const float* b0, int S, int h, float* A, void* A16);
+                         const float* b0, int S, int h, float* A, void* A16, bool chained);
 int ntf_csr_bag_bwd_fill_impl(ntf_ctx* ctx, cudaStream_t st, int B, const int32_t* indptr, const int32_t* indices, const int32_t* ent_row,
                               int row_base, int S, int h, void* workspace, size_t workspace_bytes, const uint32_t* ent_sign);
 int ntf_csr_bag_bwd_reduce_impl(ntf_ctx* ctx, cudaStream_t st, int B, const int32_t* indptr, const int32_t* indices, const int32_t* ent_row,
@@ -118,7 +118,7 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     // (one hidden layer + tensor-core output layer: the bag kernel also writes the fp16 operand copy the output layer reads)
     void* A16 = (tc && Lo == 1 && (h[0] % 8) == 0 && !a->x_dense) ? ws_main : nullptr;
     if (a->x_dense) STEP(ntf_dense_fwd(ctx, stream, a->x_dense, a->W[0], a->b[0], B, a->S, h[0], 1, a->act[0]));  // ntf.py:24: embedded skills
-    else STEP(ntf_csr_bag_fwd_impl(ctx, stream, B, a->s_indptr, a->s_indices, a->W[0], a->b[0], a->S, h[0], a->act[0], A16));
+    else STEP(ntf_csr_bag_fwd_impl(ctx, stream, B, a->s_indptr, a->s_indices, a->W[0], a->b[0], a->S, h[0], a->act[0], A16, false));
     for (int i = 1; i < Lo; ++i) STEP(ntf_dense_fwd(ctx, stream, a->act[i - 1], a->W[i], a->b[i], B, h[i - 1], h[i], 1, a->act[i]));
     // ---- output layer: forward + weighted BCE (+ backward): fnn.py:32-46,135,137 ----
     o.A = a->act[Lo - 1]; o.W = a->W[Lo]; o.b = a->b[Lo]; o.A16 = A16; o.W16 = a->W16;
@@ -255,7 +255,7 @@ extern "C" int ntf_fnn_infer_topk(ntf_ctx* ctx, void* stream, const ntf_fnn_infe
   // one hidden layer: the bag kernel writes the fp16 operand image the tensor-core product reads next to the fp32 activations
   void* A16 = (Lo == 1 && (h[0] % 8) == 0 && !a->x_dense) ? workspace : nullptr;
   if (a->x_dense) rc = ntf_dense_fwd(ctx, stream, a->x_dense, a->W[0], a->b[0], a->B, a->S, h[0], 1, a->act[0]);
-  else rc = ntf_csr_bag_fwd_impl(ctx, stream, a->B, a->s_indptr, a->s_indices, a->W[0], a->b[0], a->S, h[0], a->act[0], A16);
+  else rc = ntf_csr_bag_fwd_impl(ctx, stream, a->B, a->s_indptr, a->s_indices, a->W[0], a->b[0], a->S, h[0], a->act[0], A16, true);
   if (rc) return rc;
   for (int i = 1; i < Lo; ++i)
     if ((rc = ntf_dense_fwd(ctx, stream, a->act[i - 1], a->W[i], a->b[i], a->B, h[i - 1], h[i], 1, a->act[i]))) return rc;

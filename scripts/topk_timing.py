@@ -26,6 +26,9 @@ for tpass in (1, 2):
     c = raw[raw[:, 0] > 0]
     cyc = c[:, 1] - c[:, 0]
     print(f'pass {tpass}: {len(c)} CTAs; cycles per CTA: min {cyc.min()} median {int(np.median(cyc))} max {cyc.max()}')
+    g0, g1 = c[:, 2], c[:, 3]
+    print(f'  globaltimer: first CTA start -> last CTA end {(g1.max() - g0.min()) / 1e3:.2f} us; CTA starts spread over {(g0.max() - g0.min()) / 1e3:.2f} us; '
+          f'CTA ends spread over {(g1.max() - g1.min()) / 1e3:.2f} us; CTA lifetime median {np.median(g1 - g0) / 1e3:.2f} us max {(g1 - g0).max() / 1e3:.2f} us')
     for cta in (0, len(c) // 2):
         r = c[cta]; t0 = r[0]
         st = r[8:8 + 240].reshape(60, 4)
