@@ -363,6 +363,7 @@ def run_ours(args):
     sync()
     infer_value = reps * ib * (1 if shard else G) / (i0.elapsed_time(i1) * 1e-3)
 
+    E_local = eng.E  # (the engine is released before the secondary legs)
     extras = {}
     # secondary legs: on one GPU by default; under torchrun only when asked for (--extras) -- the headline line of a scaling run should not
     # depend on them (a leg that fails on one rank would leave the others waiting in a collective).  `--leg bnn` runs the Bnn leg alone at any N.
@@ -379,11 +380,12 @@ def run_ours(args):
         if not shard: leg('infer_topk_sweep', lambda: topk_sweep(args, tv, splits, dev, sync, G, lin_sd))
         leg('bnn_train', lambda: bnn_leg(args, dev, world, rank, sync, dist))
         leg('batch_sweep', lambda: batch_sweep(args, tv, splits, dev, world, rank, sync, dist))
+        if rank == 0: leg('staging', lambda: staging_leg(args, tv, splits, dev, sync, peaks()))
     if rank != 0:
         if world > 1: dist.destroy_process_group()
         return
     pk = peaks()
-    flops = 6.0 * 128 * eng.E * b  # K3 flops/team (Fnn train) = 6*h_L*E, per launch of b teams (sharded: this rank's experts)
+    flops = 6.0 * 128 * E_local * b  # K3 flops/team (Fnn train) = 6*h_L*E, per launch of b teams (sharded: this rank's experts)
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'out_tc2_traffic.json')
     if precision_used == 'tf32' and args.workload == 'dblp' and b == 1000 and os.path.exists(tpath):
@@ -509,6 +511,89 @@ def batch_sweep(args, tv, splits, dev, world, rank, sync, dist):
                     'precision': 'tf32' if eng.precision == _lib.NTF_TF32 else 'fp32', 'output_layer_tflops_if_alone': 6.0 * 128 * E * b / (ms / steps * 1e-3) / 1e12})
         del eng, sp
         torch.cuda.empty_cache()
+    return out
+
+
+def staging_leg(args, tv, splits, dev, sync, pk):
+    """SURVEY 8(f-4) on the bench workload's teamsvecs: member^T . skill (team.py:302-341, test teams skipped), the multi-hot rows from id lists
+    (team.py:148-173) and the skill-coverage loop (metric.py:44-73), device resident, CUDA events; beside each the reference's own CPU code path
+    (oracle/staging_oracle.py: scipy's product / the per-team loop) on a bounded sample on this host.  HBM/L2-bound integer work: algorithmic bytes
+    over time over the measured copy bandwidth."""
+    import time, numpy as np, scipy.sparse as sp_, torch
+    from opentf_b200 import ops
+    from oracle import staging_oracle as SO
+    M, S = sp_.csr_matrix(tv['member']), sp_.csr_matrix(tv['skill'])
+    M.sort_indices(); S.sort_indices()
+    T, E = M.shape; Sn = S.shape[1]
+    i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device=dev)
+    mp, mi, sp0, si = i32(M.indptr), i32(M.indices), i32(S.indptr), i32(S.indices)
+    flags = np.zeros(T, np.uint8); flags[np.asarray(splits['test'])] = 1
+    skip = torch.as_tensor(flags, device=dev)
+    ws = ops.Workspace(dev)
+
+    def timed(fn, reps):
+        for _ in range(2): r = fn()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps): r = fn()
+        e1.record()
+        sync()
+        return e0.elapsed_time(e1) / reps * 1e-3, r
+
+    out = {}
+    # --- member^T . skill
+    t, (cp, ci, cv) = timed(lambda: ops.cooccur(mp, mi, sp0, si, E, Sn, skip, ws), 5)
+    n_s = np.diff(S.indptr).astype(np.int64)
+    keep = flags == 0
+    pairs = int((np.diff(M.indptr).astype(np.int64) * n_s)[keep].sum())  # (team of expert, skill) visits
+    nnz_m = int(np.diff(M.indptr)[keep].sum())
+    nbytes = 16 * nnz_m + 2 * 2 * 4 * pairs + 8 * int(ci.numel())  # transpose (count + scatter: 8 B each per member entry), two sweeps x two passes over the pairs, the output
+    t0 = time.perf_counter()
+    sample = min(T, 20000)  # the scipy product is superlinear in nothing: a prefix of the teams, scaled by its own pair count
+    co_cpu = SO.cooccurrence(M[:sample], S[:sample], [r for r in np.asarray(splits['test']) if r < sample])
+    dt = time.perf_counter() - t0
+    pairs_cpu = int((np.diff(M.indptr).astype(np.int64) * n_s)[:sample][keep[:sample]].sum())
+    out['cooccurrence'] = {'what': f'member^T . skill [{E} x {Sn}] over {T} teams, {len(splits["test"])} test teams skipped', 'ms': t * 1e3, 'pairs': pairs, 'nnz': int(ci.numel()),
+                           'value': pairs / t, 'unit': '(expert, skill) pairs/s', 'algorithmic_bytes': nbytes, 'achieved_gbs': nbytes / t / 1e9, 'peak_gbs': pk['hbm_gbs'],
+                           'frac': nbytes / t / 1e9 / pk['hbm_gbs'], 'bound': 'hbm/l2 + shared-memory atomics',
+                           'cpu_baseline': {'value': pairs_cpu / dt, 'unit': '(expert, skill) pairs/s', 'cores': 1, 'kind': 'reference (team.py:325-335 verbatim: lil copies, scipy product)',
+                                            'sample': f'the first {sample} teams ({dt:.1f} s)'}}
+    # --- id lists -> multi-hot rows (both matrices of teamsvecs, the lists = the rows shuffled)
+    ids_m, ids_s = i32(M.indices[::-1].copy()), i32(S.indices[::-1].copy())
+    ptr_m, ptr_s = i32(M.indptr[-1] - M.indptr[::-1]), i32(S.indptr[-1] - S.indptr[::-1])  # (rows reversed, every row's ids descending)
+    t, _ = timed(lambda: (ops.csr_from_lists(ptr_m, ids_m, E, ws), ops.csr_from_lists(ptr_s, ids_s, Sn, ws)), 5)
+    n_ids = int(M.indices.shape[0] + S.indices.shape[0])
+    t0 = time.perf_counter()
+    sample = min(T, 2000)
+    SO.rows_from_lists(M.indptr[:sample + 1], M.indices, E); SO.rows_from_lists(S.indptr[:sample + 1], S.indices, Sn)
+    dt = time.perf_counter() - t0
+    out['rows_from_lists'] = {'what': f'skill and member id lists of {T} teams -> sorted duplicate-free CSR rows', 'ms': t * 1e3, 'value': T / t, 'unit': 'teams/s',
+                              'algorithmic_bytes': 16 * n_ids + 16 * T, 'achieved_gbs': (16 * n_ids + 16 * T) / t / 1e9, 'peak_gbs': pk['hbm_gbs'],
+                              'frac': (16 * n_ids + 16 * T) / t / 1e9 / pk['hbm_gbs'], 'bound': 'latency (a warp per team, 8 ids per row)',
+                              'cpu_baseline': {'value': sample / dt, 'unit': 'teams/s', 'cores': 1, 'kind': 'port (team.py:17-38,148-173: a dense one-hot row per team into a lil_matrix)',
+                                               'sample': f'{sample} teams ({dt:.1f} s)'}}
+    # --- skill coverage of the test teams' top-10 (random distinct scores stand in for the model's)
+    test = np.asarray(splits['test'])[:4096]
+    X = S[test]; X.sort_indices()
+    K = 10
+    idx = torch.stack([torch.randperm(E, device=dev)[:K] for _ in range(64)]).to(torch.int32).repeat((len(test) + 63) // 64, 1)[:len(test)].contiguous()
+    cov = torch.empty(len(test), 3, dtype=torch.float64, device=dev)
+    xp, xi = i32(X.indptr), i32(X.indices)
+    t, _ = timed(lambda: ops.skill_coverage(idx, xp, xi, cp, ci, [2, 5, 10], cov), 20)
+    co_host = sp_.csr_matrix((np.minimum(cv.cpu().numpy(), 255).astype(np.uint8), ci.cpu().numpy(), cp.cpu().numpy()), shape=(E, Sn))
+    sample = 200
+    Yd = np.zeros((sample, E), np.float32)
+    ih = idx[:sample].cpu().numpy()
+    for r in range(sample): Yd[r, ih[r]] = np.arange(K, 0, -1)
+    t0 = time.perf_counter()
+    want = SO.skill_coverage(X[:sample], Yd, co_host, '2,5,10')
+    dt = time.perf_counter() - t0
+    got = cov[:sample].cpu().numpy()
+    ok = all(np.array_equal(got[:, j], want[k]) for j, k in enumerate((2, 5, 10)))
+    out['skill_coverage'] = {'what': f'coverage@2,5,10 of {len(test)} test teams', 'ms': t * 1e3, 'value': len(test) / t, 'unit': 'teams/s', 'equals_cpu_sample': bool(ok),
+                             'bound': 'latency (binary searches in the co-occurrence rows)',
+                             'cpu_baseline': {'value': sample / dt, 'unit': 'teams/s', 'cores': 1, 'kind': 'port (metric.py:53-69 line by line)', 'sample': f'{sample} teams ({dt:.1f} s)'}}
     return out
 
 

@@ -267,6 +267,33 @@ int ntf_eval_ranked(ntf_ctx* ctx, void* stream, int n, int K, const int32_t* idx
                     const int32_t* m_indices, const int* ks, int nk, double* out);
 int ntf_axpy(ntf_ctx* ctx, void* stream, size_t n, float a, const float* x, float* y); /* y += a*x (MC mean, fnn.py:209) */
 
+/* ---- staging either side of the path: src/cmn/team.py:148-173, 318-341; src/evl/metric.py:44-73 ------------------
+ * ntf_csr_from_lists replaces Team.bucketing / get_one_hot (team.py:148-173: a dense one-hot row per team copied into a lil_matrix):
+ * ragged id lists (indptr[n+1], ids[n_ids] in ANY order, duplicates allowed, every id in [0, n_cols)) -> the sorted duplicate-free CSR
+ * rows of the multi-hot matrix.  dst_indices needs n_ids slots; *nnz (host) = entries kept.  Synchronises the stream.
+ * n_cols <= ~1.8 M (a bitmap of the columns has to fit the shared memory of an SM). */
+size_t ntf_csr_from_lists_workspace_bytes(int n, size_t n_ids);
+int ntf_csr_from_lists(ntf_ctx* ctx, void* stream, int n, size_t n_ids, const int32_t* indptr, const int32_t* ids, int n_cols,
+                       int32_t* dst_indptr, int32_t* dst_indices, int64_t* nnz, void* workspace, size_t workspace_bytes);
+/* replaces Team.gen_skill_coverage (team.py:318-341): member^T . skill as a sparse [E,S] matrix, value = number of (not skipped) teams
+ * in which expert e and skill s occur together (int32; the reference's uint8 arithmetic wraps at 256 -- the caller narrows).
+ * skip (nullable): uint8[T], 1 = leave the team out (team.py:327-332, test teams).  Two calls around the caller's allocation:
+ *   _count  transposes the member matrix into the workspace, writes co_indptr[E+1], returns the entry count in *nnz (host; synchronises)
+ *   _fill   writes co_indices (ascending per row) and co_values [nnz]; same workspace, untouched in between. */
+size_t ntf_cooccur_workspace_bytes(int E, size_t nnz_member);
+int ntf_cooccur_count(ntf_ctx* ctx, void* stream, int T, int E, int S, size_t nnz_member, const int32_t* m_indptr,
+                      const int32_t* m_indices, const int32_t* s_indptr, const int32_t* s_indices, const uint8_t* skip,
+                      int32_t* co_indptr, int64_t* nnz, void* workspace, size_t workspace_bytes);
+int ntf_cooccur_fill(ntf_ctx* ctx, void* stream, int T, int E, int S, size_t nnz_member, const int32_t* s_indptr,
+                     const int32_t* s_indices, const int32_t* co_indptr, int32_t* co_indices, int32_t* co_values, void* workspace,
+                     size_t workspace_bytes);
+/* replaces the per-team loop of calculate_skill_coverage (metric.py:53-69): out[t, j] = |skills(t) n U_{r < ks[j]} skills_of(idx[t, r])|
+ * / |skills(t)| (fp64; a team without skills gives nan like numpy's 0/0).  idx [n,K]: the team's experts in rank order (-1 = none);
+ * x_*: the teams' required skills (CSR rows, n+1 absolute offsets); co_*: the co-occurrence matrix's pattern, columns ascending,
+ * entries whose (narrowed) value is 0 removed by the caller; ks: HOST array of nk <= 8 cut-offs. */
+int ntf_skill_coverage(ntf_ctx* ctx, void* stream, int n, int K, const int32_t* idx, const int32_t* x_indptr, const int32_t* x_indices,
+                       const int32_t* co_indptr, const int32_t* co_indices, const int* ks, int nk, double* out);
+
 /* ---- Bnn / Flipout parameter pass (bayesian-torch 0.5.0 LinearFlipout + get_kl_loss; bnn.py:19-25, fnn.py:136) ---------
  * delta = softplus(rho)*eps ;  kl_out[0] += kl_scale * sum(-log sigma + (sigma^2 + mu^2)/2 - 1/2)   (kl_scale = 1/numel:
  * the reference takes a MEAN per tensor, prior N(0,1)) */

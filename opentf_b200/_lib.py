@@ -114,6 +114,12 @@ SIGNATURES = {
     'ntf_topk_merge': (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),
     'ntf_row_entropy': (i32, [vp, vp, vp, i32, i32, f32, i32, vp]),
     'ntf_eval_ranked': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(i32), i32, vp]),
+    'ntf_csr_from_lists_workspace_bytes': (sz, [i32, sz]),
+    'ntf_csr_from_lists': (i32, [vp, vp, i32, sz, vp, vp, i32, vp, vp, C.POINTER(C.c_int64), vp, sz]),
+    'ntf_cooccur_workspace_bytes': (sz, [i32, sz]),
+    'ntf_cooccur_count': (i32, [vp, vp, i32, i32, i32, sz, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int64), vp, sz]),
+    'ntf_cooccur_fill': (i32, [vp, vp, i32, i32, i32, sz, vp, vp, vp, vp, vp, vp, sz]),
+    'ntf_skill_coverage': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, C.POINTER(i32), i32, vp]),
     'ntf_axpy': (i32, [vp, vp, sz, f32, vp, vp]),
     'ntf_flipout_prepare_workspace_bytes': (sz, [vp]),
     'ntf_flipout_prepare': (i32, [vp, vp, vp, vp, vp, sz, f32, vp, vp, vp, sz]),

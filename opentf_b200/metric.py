@@ -142,21 +142,8 @@ def calculate_auc_roc(Y, Y_, curve=False):
     return auc, None
 
 
-def calculate_skill_coverage(X, Y_, expertskillvecs, per_instance=False, topks='2,5,10'):
-    """metric.py:44-73: fraction of a team's required skills held by the union of its top-k recommended experts."""
-    import pandas as pd
-    assert X.shape[0] == Y_.shape[0]
-    ks = [int(k) for k in topks.split(',')]
-    Xc, Sk = sp.csr_matrix(X), sp.csr_matrix(expertskillvecs)
-    teams = Y_.shape[0]
-    cov = {k: np.zeros(teams) for k in ks}
-    Yr = sp.csr_matrix(Y_) if sp.issparse(Y_) else None
-    for t in range(teams):
-        row = np.asarray(Yr.getrow(t).todense()).ravel() if Yr is not None else np.asarray(Y_[t])
-        ranked = np.argsort(row)[::-1]
-        need = Xc.indices[Xc.indptr[t]:Xc.indptr[t + 1]]
-        for k in ks:
-            have = np.unique(Sk[ranked[:k]].indices)
-            cov[k][t] = np.intersect1d(need, have).size / len(need)
-    df = pd.DataFrame({f'skill_coverage_{k}': cov[k] for k in ks})
-    return df, df.mean().to_frame('mean').rename_axis('metrics')
+def calculate_skill_coverage(X, Y_, expertskillvecs, per_instance=False, topks='2,5,10', device='cuda:0'):
+    """metric.py:44-73: fraction of a team's required skills held by the union of its top-k recommended experts.  The per-team loop runs on the
+    device (staging.calculate_skill_coverage -> ntf_skill_coverage); no host implementation in the product."""
+    from . import staging
+    return staging.calculate_skill_coverage(X, Y_, expertskillvecs, per_instance, topks, device)

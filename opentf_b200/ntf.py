@@ -69,11 +69,9 @@ class Ntf:
                     assert Y.shape == Y_.shape, f'Shape mismatch between truth Y {Y.shape} vs preds Y_ {Y_.shape}!'
                     df, df_mean = pd.DataFrame(), pd.DataFrame()
                     if trec:
-                        if str(self.device).startswith('cuda'):  # the per-team ranking loop runs on the GPU (ntf_eval_ranked); no fallback
-                            df, df_mean = metric.calculate_metrics_device(Y, Y_, g(evalcfg, 'topK'), g(evalcfg, 'per_instance'), trec,
-                                                                          device=util.first_device(self.device))
-                        else:
-                            df, df_mean = metric.calculate_metrics(Y, Y_, g(evalcfg, 'topK'), g(evalcfg, 'per_instance'), trec)
+                        # the per-team ranking loop runs on the GPU (ntf_eval_ranked); a non-CUDA device raises there: no host fallback
+                        df, df_mean = metric.calculate_metrics_device(Y, Y_, g(evalcfg, 'topK'), g(evalcfg, 'per_instance'), trec,
+                                                                      device=util.first_device(self.device))
                         if df is None: df = pd.DataFrame()
                     if (m := [m for m in other if 'aucroc' in m]):
                         aucroc, fpr_tpr = metric.calculate_auc_roc(Y, Y_, curve=(m[0] == 'aucroc+'))
@@ -85,7 +83,7 @@ class Ntf:
                         X = teamsvecs['skill'] if scipy.sparse.issparse(teamsvecs['skill']) else teamsvecs['original_skill']
                         X = X[splits['test']] if pred_set == 'test' else X[splits['folds'][foldidx][pred_set]]
                         df_skc, df_mean_skc = metric.calculate_skill_coverage(X, Y_, teamsvecs['skillcoverage'], g(evalcfg, 'per_instance'),
-                                                                              topks=m[0].replace('skill_coverage_', ''))
+                                                                              topks=m[0].replace('skill_coverage_', ''), device=util.first_device(self.device))
                         df = df_skc if df.empty else pd.concat([df.reset_index(drop=True), df_skc.reset_index(drop=True)], axis=1)
                         df_mean = df_mean_skc if df_mean.empty else pd.concat([df_mean, df_mean_skc], axis=0)
                     if g(evalcfg, 'per_instance'): df.to_csv(f'{predfile}.eval.instance.csv', float_format='%.5f', index=False)

@@ -227,6 +227,46 @@ def eval_ranked(idx, vals, m_indptr, m_indices, ks, out):
                                 _p(out, torch.float64)), 'ntf_eval_ranked')
 
 
+def csr_from_lists(indptr, ids, n_cols, ws):
+    """ragged id lists (device int32 indptr [n+1], ids) -> (dst_indptr [n+1], dst_indices [nnz]) sorted duplicate-free rows (ntf_csr_from_lists)"""
+    d = _dev(indptr)
+    n, n_ids = indptr.numel() - 1, ids.numel()
+    dst_ptr = torch.empty(n + 1, dtype=I32, device=indptr.device)
+    dst_idx = torch.empty(max(n_ids, 1), dtype=I32, device=indptr.device)
+    nnz = C.c_int64(0)
+    p, nb = ws.get(lib().ntf_csr_from_lists_workspace_bytes(n, n_ids))
+    check(lib().ntf_csr_from_lists(_lib.ctx(d), _stream(d), n, n_ids, _p(indptr, I32), _p(ids, I32) if n_ids else None, n_cols, _p(dst_ptr, I32), _p(dst_idx, I32),
+                                   C.byref(nnz), p, nb), 'ntf_csr_from_lists')
+    return dst_ptr, dst_idx[:nnz.value]
+
+
+def cooccur(m_indptr, m_indices, s_indptr, s_indices, E, S, skip, ws):
+    """member^T . skill on the device (ntf_cooccur_count + ntf_cooccur_fill): (co_indptr [E+1], co_indices, co_values) int32, columns ascending.
+    skip: uint8 [T] device tensor or None"""
+    d = _dev(m_indptr)
+    T, nnz_m = m_indptr.numel() - 1, m_indices.numel()
+    co_ptr = torch.empty(E + 1, dtype=I32, device=m_indptr.device)
+    nnz = C.c_int64(0)
+    p, nb = ws.get(lib().ntf_cooccur_workspace_bytes(E, nnz_m))
+    check(lib().ntf_cooccur_count(_lib.ctx(d), _stream(d), T, E, S, nnz_m, _p(m_indptr, I32), _p(m_indices, I32) if nnz_m else None, _p(s_indptr, I32), _p(s_indices, I32),
+                                  _p(skip, torch.uint8), _p(co_ptr, I32), C.byref(nnz), p, nb), 'ntf_cooccur_count')
+    co_idx = torch.empty(max(nnz.value, 1), dtype=I32, device=m_indptr.device)
+    co_val = torch.empty(max(nnz.value, 1), dtype=I32, device=m_indptr.device)
+    check(lib().ntf_cooccur_fill(_lib.ctx(d), _stream(d), T, E, S, nnz_m, _p(s_indptr, I32), _p(s_indices, I32), _p(co_ptr, I32), _p(co_idx, I32), _p(co_val, I32), p, nb),
+          'ntf_cooccur_fill')
+    return co_ptr, co_idx[:nnz.value], co_val[:nnz.value]
+
+
+def skill_coverage(idx, x_indptr, x_indices, co_indptr, co_indices, ks, out):
+    """out [n, len(ks)] fp64: covered fraction of every team's skills by its first k ranked experts (ntf_skill_coverage)"""
+    d = _dev(idx)
+    n, K = idx.shape
+    assert out.dtype == torch.float64 and tuple(out.shape) == (n, len(ks))
+    karr = (C.c_int * len(ks))(*[int(k) for k in ks])
+    check(lib().ntf_skill_coverage(_lib.ctx(d), _stream(d), n, K, _p(idx, I32), _p(x_indptr, I32), _p(x_indices, I32), _p(co_indptr, I32), _p(co_indices, I32), karr,
+                                   len(ks), _p(out, torch.float64)), 'ntf_skill_coverage')
+
+
 def axpy(n, a, x, y):
     d = _dev(x)
     check(lib().ntf_axpy(_lib.ctx(d), _stream(d), n, a, _p(x, F32), _p(y, F32)), 'ntf_axpy')

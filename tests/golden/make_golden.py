@@ -213,8 +213,46 @@ def record_tntf(key='gith', seed=0):
     print('tntf', key, {y: (int(out[f'{y}/f0/e']), float(out[f'{y}/f0/t_loss'])) for _, y in year_idx[:-1]})
 
 
+def record_staging(key):
+    """the UNMODIFIED Team.gen_skill_coverage (team.py:302-341, test teams skipped as main.py:98 does) and calculate_skill_coverage
+    (metric.py:44-73) on the committed toy teamsvecs; the predictions are seeded random scores (distinct per row: the ranking has no ties) and the
+    committed f0.test.pred of the reference's own fnn run where it exists"""
+    ref_shim._install_shims()
+    if ref_shim.REF_SRC not in sys.path: sys.path.insert(0, ref_shim.REF_SRC)
+    from cmn.team import Team
+    from evl import metric as refmetric
+    root, tv, sp_ = load_toy(key)
+    out = {}
+    co = Team.gen_skill_coverage(tv, tempfile.mkdtemp(), skipteams=sp_['test'])
+    co = co.tocsr(); co.sort_indices()
+    out['co/indptr'], out['co/indices'], out['co/data'] = co.indptr.astype(np.int64), co.indices.astype(np.int32), co.data.astype(np.int64)
+    out['co/dtype'] = np.array(str(co.dtype))
+    co_all = Team.gen_skill_coverage(tv, tempfile.mkdtemp(), skipteams=None).tocsr(); co_all.sort_indices()
+    out['co_all/indptr'], out['co_all/indices'], out['co_all/data'] = co_all.indptr.astype(np.int64), co_all.indices.astype(np.int32), co_all.data.astype(np.int64)
+    test = np.asarray(sp_['test'])
+    X = tv['skill'][test]
+    rng = np.random.default_rng(5)
+    Y_ = rng.permutation(len(test) * tv['member'].shape[1]).reshape(len(test), -1).astype(np.float32) / (len(test) * tv['member'].shape[1])
+    df, df_mean = refmetric.calculate_skill_coverage(X, Y_, co, per_instance=True, topks='2,5,10')
+    out['random/Y_'] = Y_
+    for c in df.columns: out[f'random/{c}'] = df[c].to_numpy(dtype=np.float64)
+    predfile = f'{root}/{RUN}/f0.test.pred'
+    if os.path.isfile(predfile):
+        _stub_omegaconf()
+        Yp = torch.load(predfile, map_location='cpu', weights_only=False)['y_pred']
+        Yp = Yp.to_dense().numpy() if Yp.is_sparse else Yp.numpy()
+        if all(len(np.unique(r)) == len(r) for r in Yp):  # (a dense, tie-free prediction: the ranking is unambiguous)
+            df, _ = refmetric.calculate_skill_coverage(X, Yp, co, per_instance=True, topks='2,5,10')
+            for c in df.columns: out[f'pred/{c}'] = df[c].to_numpy(dtype=np.float64)
+    np.savez_compressed(f'{HERE}/staging_{key}.npz', **out)
+    print('staging', key, 'co', co.shape, co.nnz, 'coverage means', {c: float(np.mean(out[f'random/{c}'])) for c in df.columns}, 'pred' if any(k.startswith('pred/') for k in out) else '')
+
+
 if __name__ == '__main__':
     assert ref_shim.available(), 'run this where /root/reference is mounted'
+    if sys.argv[1:] == ['staging']:
+        for key in TOYS: record_staging(key)
+        sys.exit(0)
     if sys.argv[1:] == ['tntf']:
         record_tntf()
         sys.exit(0)
@@ -236,3 +274,4 @@ if __name__ == '__main__':
     record_trajectory('unigram_b', key='imdb', tag='unigram_b_small', b=4, h=[16, 8], e=6)  # short last batches + 3 layers
     record_trajectory('unigram_b', key='gith', tag='dense16', dense_d=16, b=32, h=[24], e=8, lr=0.01)  # dense (embedded) skill input, several batches per epoch
     record_tntf()
+    for key in TOYS: record_staging(key)

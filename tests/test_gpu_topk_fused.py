@@ -90,6 +90,24 @@ def test_fused_topk_exact_ties_follow_the_lower_id_rule(ops, ws):
     assert (idx == np.arange(K)[None, :]).all() and (vals == P.cpu().numpy()[:, :K]).all() and abs(float(vals[0, 0]) - 0.5) < 1e-6
 
 
+def test_fused_topk_many_equal_block_maxima_restart_the_select_on_block_numbers(ops, ws):
+    """more than 128 blocks of a team with EQUAL maxima (an all-zero layer over 20000 experts, then a few experts raised above the plateau): the
+    select's tie path ranks the equal blocks by block number, so the winners after the raised experts are the lowest expert ids"""
+    B, h, E, K = 40, 128, 20000, 12
+    A = torch.randn(B, h, generator=torch.Generator().manual_seed(9)).abs().to(DEV)
+    Z, zb = torch.zeros(E, h, device=DEV), torch.zeros(E, device=DEV)
+    vals, idx = run_fused(ops, ws, A, Z, zb, K)
+    assert (idx == np.arange(K)[None, :]).all() and (np.abs(vals - 0.5) < 1e-6).all()
+    raised = [19999, 7, 12345, 4100, 4101]  # two of them in one block
+    zb[raised] = torch.tensor([3.0, 2.5, 2.0, 1.5, 1.0], device=DEV)
+    P = torch.empty(B, E, device=DEV)
+    ops.infer_scores(1, A, Z, zb, B, h, E, P, ws)
+    vals, idx = run_fused(ops, ws, A, Z, zb, K)
+    want = raised + [e for e in range(E) if e not in raised][:K - len(raised)]
+    assert (idx == np.asarray(want)[None, :]).all(), idx[0]
+    check_against_dense(P.cpu().numpy(), vals, idx, K)
+
+
 def test_fused_topk_of_an_expert_shard_reports_global_ids(ops, ws):
     torch.manual_seed(5)
     B, h, E, K, e_lo = 33, 128, 1000, 5, 7000
