@@ -330,10 +330,11 @@ def run_ours(args):
 
     # ---- end to end through the streaming entry point: host batches in, loss out ----
     # Every step: the global batch's rows are PACKED from the host teamsvecs CSR into a pinned block (ntf_pack_host_batch, the loader's work),
-    # copied to the device (one H2D transfer), stepped, and the loss is read back (D2H + sync).  Packing of batch i+1 runs on the host while the
-    # GPU works on batch i, as a loader thread would; all of it is inside the timed region.
+    # copied to the device (one H2D transfer), stepped, and the loss of every step is copied back and read by the host.  Packing and enqueueing of
+    # batch i+1 run on the host while the GPU works on batch i, as a loader thread would; all of it is inside the timed region.
     host = HostBatches(tv, train_rows, b, 0 if shard else rank, 1 if shard else G)
     for i in range(min(3, args.warmup)): host.step(eng, i)
+    host.run(eng, 3, 4)  # (both loss slots of the two-in-flight loop: their step graphs are captured here, not in the timed region)
     sync()
     w0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -356,7 +357,7 @@ def run_ours(args):
     for _ in range(3): eng.topk(test_sp, 0, ib, args.infer_k, scores, vals, idx)
     sync()
     i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
+    reps = 50
     i0.record()
     for r in range(reps): eng.topk(test_sp, (r * ib) % max(1, test_sp.n - ib + 1), ib, args.infer_k, scores, vals, idx)
     i1.record()
@@ -405,7 +406,7 @@ def run_ours(args):
            'data': 'synthetic', 'config': config_of(args, tv), 'clocks': clk.summary(),
            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': host.h2d_bytes, 'd2h_bytes_per_step': 4,
                    'api': 'HostPacker.pack (ntf_pack_host_batch: rows of the host teamsvecs CSR -> pinned block; batch i+1 packed while the GPU works on batch i) '
-                          '-> Engine.step_host: one H2D copy -> ntf_fnn_step (replayed as a CUDA graph) -> loss read back (D2H + sync); all inside the timed region'},
+                          '-> Engine.step_host: one H2D copy -> ntf_fnn_step (replayed as a CUDA graph) -> the loss of every step copied back and read by the host (two steps in flight: the host waits for loss i after it has enqueued step i+1); all inside the timed region'},
            'gpu_launches': launches, 'cuda_graphs': bool(graphs),
            'dp_exchange': None if G == 1 else {'peer': 'reduce-scatter + Adam + all-gather fused in one pass over peer memory inside ntf_fnn_step (csrc/peer.cu), 2 overlapped arena segments',
                                                'nccl': 'ncclAllReduce inside ntf_fnn_step: 2 overlapped arena segments, captured in the step graph'}.get(
@@ -710,16 +711,18 @@ class HostBatches:
         return eng.step_host(self.packer.pack(self._rows(i), *self._slice()), self.b * self.G, self.cap_s, self.cap_m, self.rank, self.G, lr=1e-3)
 
     def run(self, eng, first, steps):
-        """`steps` consecutive batches: pack(i+1) overlaps the GPU's work on batch i; the loss of every step is read back"""
+        """`steps` consecutive batches, every one packed from the host CSR, copied to the device and stepped, the loss of EVERY step read back.
+        Two steps are in flight: batch i+1 is packed and enqueued while the GPU works on batch i, then the host waits for loss i (its own
+        copy event, not the stream) -- the GPU never waits for the host as long as pack + enqueue take less than a step"""
         gB = self.b * self.G
         lo, hi = self._slice()
-        blk = self.packer.pack(self._rows(first), lo, hi)
+        eng.step_host(self.packer.pack(self._rows(first), lo, hi), gB, self.cap_s, self.cap_m, self.rank, self.G, lr=1e-3, sync=False, slot=0)
         loss = None
-        for i in range(steps):
-            eng.step_host(blk, gB, self.cap_s, self.cap_m, self.rank, self.G, lr=1e-3, sync=False)
-            if i + 1 < steps: blk = self.packer.pack(self._rows(first + i + 1), lo, hi)
-            loss = eng.step_host_loss()
-        return loss
+        for i in range(1, steps):
+            blk = self.packer.pack(self._rows(first + i), lo, hi)  # (block i % 2: the copy of batch i-2 out of it has completed -- loss i-2 was read)
+            eng.step_host(blk, gB, self.cap_s, self.cap_m, self.rank, self.G, lr=1e-3, sync=False, slot=i & 1)
+            loss = eng.step_host_loss((i - 1) & 1)
+        return eng.step_host_loss((steps - 1) & 1)
 
 
 if __name__ == '__main__':

@@ -63,6 +63,8 @@ struct Tc2Args {
   long long* timing;  // debug: per CTA TSLOTS slots: start ns, end ns, smid, start / end clock; from slot 8, 8 per tile n < 60: Z ready, tile done, drain start, drain end, bwd issue start / end, dA staged, dW products complete
   int nct, nbt;     // expert tiles, batch tiles
   unsigned* done;   // block counter of the correction pass that follows: cleared here (CTA 0), so that pass needs no launch of its own for it
+  int exp;          // debug (NTF_TC2_EXP, wrong results): 1 = the dA partial sums are read from TMEM but not added to global memory
+                    // (profiles/r02h_tc2_no_dA_atomics_experiment.txt: the kernel goes from 57.8 to 48.3 us)
   int split;        // 0: CTA c owns tiles [c*T/G, (c+1)*T/G) of the expert-major sequence; s > 0: expert tile c/s, batch part c%s of s
 };
 
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(NT, 1) out_tc2_kernel(const __grid_constant__ 
           const int nrem = g.B - team0;
           if (nrem >= 32) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(dst + (size_t)i * HK, v[i] * g.scale);
+            for (int i = 0; i < 32; ++i) if (!(g.exp & 1)) atomicAdd(dst + (size_t)i * HK, v[i] * g.scale);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
@@ -706,6 +708,7 @@ int ntf_out_train_tc2(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a
   g.Zdbg = dbg ? (float*)(uintptr_t)strtoull(dbg, nullptr, 0) : nullptr;
   const char* tim = getenv("NTF_TC_TIMING");
   g.timing = tim ? (long long*)(uintptr_t)strtoull(tim, nullptr, 0) : nullptr;
+  { static const int ex = getenv("NTF_TC2_EXP") ? atoi(getenv("NTF_TC2_EXP")) : 0; g.exp = ex; }
   int grid;
   tc2_plan(ctx, a->B, a->E, &g, &grid);
   NTF_REQUIRE(grid <= 1024, NTF_ERR_UNSUPPORTED, "out_train(tf32): %d CTAs", grid);

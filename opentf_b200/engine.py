@@ -842,10 +842,11 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ streaming entry point (host batches)
-    def step_host(self, packed, n, cap_s, cap_m, rank=0, G=1, lr=1e-3, train=True, sync=True):
+    def step_host(self, packed, n, cap_s, cap_m, rank=0, G=1, lr=1e-3, train=True, sync=True, slot=0):
         """one step on a batch the HOST holds (`pack_host_batch`: compact CSR of the global batch in one pinned block): one H2D copy,
-        this rank trains on its slice, and the loss comes back to the host (one sync) -- the per-step shape of the reference's loop
-        (fnn.py:118-140: H2D of the batch, .item())."""
+        this rank trains on its slice, and the loss comes back to the host -- the per-step shape of the reference's loop (fnn.py:118-140: H2D
+        of the batch, .item()).  sync=False: the loss is copied to a pinned host slot (`slot` 0/1) behind the step and an event marks it;
+        the caller reads it with step_host_loss(slot) -- after it has enqueued the NEXT step, so the GPU never waits for the host."""
         st = getattr(self, '_hstage', None)
         if st is None or st.buf.numel() < packed.numel():
             st = self._hstage = _HostStage(self.device, 2 * packed.numel() + 1024)
@@ -853,13 +854,19 @@ class Engine:
         st.buf[:packed.numel()].copy_(packed, non_blocking=True)
         b = -(-n // G)
         lo, hi = min(n, rank * b), min(n, (rank + 1) * b)
-        self.step(st, lo, hi - lo, train, lr=lr, loss_slot=0, loss_scale=1.0 / n, gbatch=(0, n))
-        if not sync: return None  # (the caller overlaps host work -- packing the next batch -- and reads the loss with step_host_loss)
-        return float(self.loss_buf[0].item())
+        self.step(st, lo, hi - lo, train, lr=lr, loss_slot=slot, loss_scale=1.0 / n, gbatch=(0, n))
+        if sync: return float(self.loss_buf[slot].item())
+        if getattr(self, '_hloss', None) is None:
+            self._hloss = torch.zeros(2, dtype=torch.float32).pin_memory()
+            self._hloss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self._hloss[slot:slot + 1].copy_(self.loss_buf[slot:slot + 1], non_blocking=True)
+        self._hloss_ev[slot].record(torch.cuda.current_stream(self.device))
+        return None
 
-    def step_host_loss(self):
-        """the loss of the last step_host(sync=False): the D2H read + sync of the streaming loop (fnn.py:140 `loss.item()`)"""
-        return float(self.loss_buf[0].item())
+    def step_host_loss(self, slot=0):
+        """the loss of the step_host(sync=False, slot=slot) enqueued last on that slot: waits for ITS copy only (fnn.py:140 `loss.item()`)"""
+        self._hloss_ev[slot].synchronize()
+        return float(self._hloss[slot])
 
     # ------------------------------------------------------------------ inference
     def scores(self, sp, b0, B, out):

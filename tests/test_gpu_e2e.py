@@ -198,6 +198,38 @@ def test_step_host_is_the_same_step_as_the_resident_path(toy):
     assert out[0][0][2] < out[0][0][0]
 
 
+def test_step_host_with_two_steps_in_flight_returns_every_loss(toy):
+    """the streaming loop of bench.py's end-to-end leg: step i+1 is enqueued before the host reads loss i (pinned slot + its own event);
+    losses and final parameters are those of the synchronous loop"""
+    from opentf_b200.engine import Engine, HostPacker, to_csr
+    skill, member, splits, _ = toy('gith')
+    train = np.asarray(splits['folds'][0]['train'])
+    n, steps = 16, 7
+    torch.manual_seed(0)
+    layers = O.init_params(skill.shape[1], [32], member.shape[1])
+    sd = {f'layers.{i}.{nm}': t for i, (W, b) in enumerate(layers) for nm, t in (('weight', W), ('bias', b))}
+    s_csr, m_csr = to_csr(skill), to_csr(member)
+    out = []
+    for mode in ('sync', 'pipelined'):
+        eng = Engine(skill.shape[1], [32], member.shape[1], 'cuda:0', precision='fp32', nsd='unigram_b', ns=5, seed=7, max_batch=n)
+        eng.stage(skill, member)
+        eng.load_state_dict(sd)
+        packer = HostPacker(s_csr, m_csr, n, 512, 512)
+        rows = lambda i: train[(i * n) % (len(train) - n):][:n]
+        losses = []
+        if mode == 'sync':
+            for i in range(steps): losses.append(eng.step_host(packer.pack(rows(i)), n, 512, 512, lr=1e-2))
+        else:
+            eng.step_host(packer.pack(rows(0)), n, 512, 512, lr=1e-2, sync=False, slot=0)
+            for i in range(1, steps):
+                eng.step_host(packer.pack(rows(i)), n, 512, 512, lr=1e-2, sync=False, slot=i & 1)
+                losses.append(eng.step_host_loss((i - 1) & 1))
+            losses.append(eng.step_host_loss((steps - 1) & 1))
+        out.append((np.asarray(losses, dtype=np.float32), eng.params.cpu().clone()))
+    assert np.array_equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert len(set(out[0][0].tolist())) == steps  # (seven different batches, seven different losses: no slot was read twice)
+
+
 # ---------------------------------------------------------------------------------------------- tNtf: year-by-year fine-tuning (SURVEY 8f-3)
 def test_tntf_chain_retraces_the_reference_run(toy, tmp_path):
     """opentf_b200.tntf.tNtf around opentf_b200.fnn.Fnn, free-running from seed 0 (nsd unset: nothing is drawn in bxe), against the run of
