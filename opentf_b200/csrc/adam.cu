@@ -28,7 +28,48 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) adam1(p[i], g[i], m[i], v[i], k);
 }
+
+// Layer 0's weight [S, h] row by row (a warp per row): the rows of the skills the batch holds (cnt[s] > 0) have a gradient; all the others have
+// g = 0 exactly, so their update (moments decay, the parameter follows its momentum) does not depend on the step's backward pass at all.
+// TOUCHED = false steps those rows (no gradient read) -- ntf_fnn_step runs it at the TOP of the step on a side stream, under the output
+// layer's kernel; TOUCHED = true steps the batch's rows after the backward pass, plus the contiguous tail [tail, tail + tail_n) (the
+// layer's bias).  Same adam1 as the flat kernel: the two passes together are bit-identical to one pass over the arena.
+template <bool TOUCHED>
+__global__ void __launch_bounds__(256) adam_rows_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int S, int h4,
+                                                        const uint32_t* __restrict__ cnt, AdamK k, const ntf_dyn* __restrict__ dyn, size_t tail, size_t tail_n) {
+  if (dyn) k = AdamK{dyn->one_minus_b1, dyn->b2, dyn->one_minus_b2, dyn->bc2_sqrt, dyn->eps, dyn->neg_step};
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < S; s += warps) {
+    if ((__ldg(cnt + s) != 0u) != TOUCHED) continue;
+    const size_t row = (size_t)s * h4;
+    for (int c = lane; c < h4; c += 32) {
+      float4 P = reinterpret_cast<float4*>(p)[row + c], M = reinterpret_cast<float4*>(m)[row + c], V = reinterpret_cast<float4*>(v)[row + c];
+      float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (TOUCHED) G = __ldg(reinterpret_cast<const float4*>(g) + row + c);
+      adam1(P.x, G.x, M.x, V.x, k); adam1(P.y, G.y, M.y, V.y, k); adam1(P.z, G.z, M.z, V.z, k); adam1(P.w, G.w, M.w, V.w, k);
+      reinterpret_cast<float4*>(p)[row + c] = P; reinterpret_cast<float4*>(m)[row + c] = M; reinterpret_cast<float4*>(v)[row + c] = V;
+    }
+  }
+  if (TOUCHED)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tail_n; i += (size_t)gridDim.x * blockDim.x) adam1(p[tail + i], g[tail + i], m[tail + i], v[tail + i], k);
+}
 }  // namespace
+
+// p, g, m, v: the [S, h] weight (h % 4 == 0, 16-byte aligned); tail / tail_n: floats relative to p stepped with the touched rows (touched = 1 only)
+int ntf_adam_rows_impl(ntf_ctx* ctx, cudaStream_t st, float* p, const float* g, float* m, float* v, int S, int h, const uint32_t* cnt, int touched, size_t tail,
+                       size_t tail_n, double lr, double beta1, double beta2, double eps, int64_t step, const ntf_dyn* dyn) {
+  NTF_REQUIRE(ctx && p && g && m && v && cnt, NTF_ERR_BAD_ARG, "adam_rows: null pointer");
+  NTF_REQUIRE(S > 0 && h > 0 && (h % 4) == 0 && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0), NTF_ERR_BAD_ARG, "adam_rows: S=%d h=%d or misaligned", S, h);
+  NTF_REQUIRE(dyn || step >= 1, NTF_ERR_BAD_ARG, "adam_rows: step=%lld (1-based)", (long long)step);
+  const AdamK k = adam_consts(lr, beta1, beta2, eps, step >= 1 ? step : 1);
+  const int blocks = min(cdiv(S, 8), ctx->sm_count * 16);
+  NTF_COUNT_LAUNCH;
+  if (touched) adam_rows_kernel<true><<<blocks, 256, 0, st>>>(p, g, m, v, S, h / 4, cnt, k, dyn, tail, tail_n);
+  else adam_rows_kernel<false><<<blocks, 256, 0, st>>>(p, g, m, v, S, h / 4, cnt, k, dyn, 0, 0);
+  NTF_LAUNCH_CHECK();
+  return NTF_OK;
+}
 
 // `dyn` (device, nullable): the constants come from the block ntf_dyn_update wrote for this step instead of the arguments
 int ntf_adam_step_impl(ntf_ctx* ctx, cudaStream_t st, float* p, const float* g, float* m, float* v, size_t n, double lr, double beta1,

@@ -63,6 +63,7 @@ extern "C" int ntf_create(int device, ntf_ctx** out) {
   for (int i = 0; i < 2 && es == cudaSuccess; ++i) es = cudaEventCreateWithFlags(&c->ev_ar[i], cudaEventDisableTiming);
   if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_bwd, cudaEventDisableTiming);
   if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_finish, cudaEventDisableTiming);
+  if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_adam_rows, cudaEventDisableTiming);
   cudaSetDevice(cur);
   if (es != cudaSuccess) {
     ntf_set_error("ntf_create: side streams / events: %s", cudaGetErrorString(es));
@@ -79,7 +80,7 @@ extern "C" int ntf_destroy(ntf_ctx* ctx) {
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_fork_opt); cudaEventDestroy(ctx->ev_join_opt);
     cudaEventDestroy(ctx->ev_hot_fork); cudaEventDestroy(ctx->ev_hot_join);
-    cudaStreamDestroy(ctx->comm_st); cudaEventDestroy(ctx->ev_ar[0]); cudaEventDestroy(ctx->ev_ar[1]); cudaEventDestroy(ctx->ev_bwd); cudaEventDestroy(ctx->ev_finish);
+    cudaStreamDestroy(ctx->comm_st); cudaEventDestroy(ctx->ev_ar[0]); cudaEventDestroy(ctx->ev_ar[1]); cudaEventDestroy(ctx->ev_bwd); cudaEventDestroy(ctx->ev_finish); cudaEventDestroy(ctx->ev_adam_rows);
   }
   delete ctx;
   return NTF_OK;

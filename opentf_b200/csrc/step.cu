@@ -29,6 +29,9 @@ int ntf_peer_exchange_adam_impl(ntf_ctx* ctx, cudaStream_t st, const ntf_peers* 
                                 double beta1, double beta2, double eps, int64_t step, const ntf_dyn* dyn, int channel);
 
 int ntf_peer_allreduce_impl(ntf_ctx* ctx, cudaStream_t st, const ntf_peers* pr, size_t n, float* dst, int channel);
+int ntf_adam_rows_impl(ntf_ctx* ctx, cudaStream_t st, float* p, const float* g, float* m, float* v, int S, int h, const uint32_t* cnt, int touched, size_t tail,
+                       size_t tail_n, double lr, double beta1, double beta2, double eps, int64_t step, const ntf_dyn* dyn);
+const uint32_t* ntf_csr_bag_bwd_counts(void* workspace, int S);
 
 static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 
@@ -73,6 +76,13 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
   bool finish_pending = false, finish_side = false;
   int rc;
 #define STEP(call) do { if ((rc = (call)) != NTF_OK) return rc; } while (0)
+  // layer 0's weight [S, h0] (CSR input, single rank, whole step in this call): its Adam pass is split by rows -- see ntf_adam_rows_impl.
+  // Under data parallelism the gradient of a row this rank's batch does not touch is not zero after the exchange: one flat pass there.
+  const size_t w0_off = (size_t)(a->W[0] - a->params), w0_n = (size_t)a->S * h[0];
+  const size_t last_off = (size_t)((a->gW[Lo] < a->gb[Lo] ? a->gW[Lo] : a->gb[Lo]) - a->grads);  // the last layer's segment starts here (arena order)
+  const bool rows_split = bwd_here && phase == 3 && a->run_adam && !a->x_dense && a->comm == nullptr && a->peers == nullptr && getenv("NTF_ADAM_ROWS_OFF") == nullptr &&
+                          a->W[0] >= a->params && (size_t)(a->gW[0] - a->grads) == w0_off && (w0_off % 4) == 0 && (h[0] % 4) == 0 && a->gW[Lo] >= a->grads &&
+                          w0_off + w0_n <= last_off && last_off <= a->n_params;
   // ---- fork: what needs the batch's CSR only ----
   if ((phase & 1) || bwd_here) NTF_CUDA(cudaEventRecord(ctx->ev_fork, st));
   const bool prep = bwd_here && tc2 && (phase & 1);
@@ -83,6 +93,13 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     // ... and every (team, skill) entry takes a slot of its skill (pass 1 of the input layer's backward)
     if (!a->x_dense) STEP(ntf_csr_bag_bwd_fill_impl(ctx, ctx->side[1], B, a->s_indptr, a->s_indices, a->s_ent_row, a->row_base, a->S, h[0], ws_bag, ws_bag_bytes, nullptr));
     NTF_CUDA(cudaEventRecord(ctx->ev_join[1], ctx->side[1]));
+    // ... and the optimiser steps the rows of layer 0's weight the batch does NOT touch (g = 0 there whatever the backward pass computes):
+    // ~3/4 of that weight's Adam traffic moves from the end of the critical path to here, under the output layer's kernel
+    if (rows_split) {
+      STEP(ntf_adam_rows_impl(ctx, ctx->side[1], a->params + w0_off, a->grads + w0_off, a->adam_m + w0_off, a->adam_v + w0_off, a->S, h[0],
+                              ntf_csr_bag_bwd_counts(ws_bag, a->S), 0, 0, 0, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn));
+      NTF_CUDA(cudaEventRecord(ctx->ev_adam_rows, ctx->side[1]));
+    }
   }
   if (phase & 1) {
     const bool tc = a->precision == NTF_TF32;
@@ -183,7 +200,7 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
       NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_ar[0], 0));
     } else
     NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork_opt, 0));
-    if (finish_pending) {
+    if (finish_pending) {  // (in front of the last layer's optimiser: measured better than a stream of its own, profiles/r02h_step_optimiser_ab.txt)
       STEP(ntf_out_train_finish(ctx, (void*)ctx->side[0], &o, ws_main, ws_main_bytes));
       NTF_CUDA(cudaEventRecord(ctx->ev_finish, ctx->side[0]));
       finish_pending = false; finish_side = true;
@@ -227,6 +244,17 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
   if (peers) {
     STEP(ntf_peer_exchange_adam_impl(ctx, st, a->peers, a->adam_m, a->adam_v, 0, opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn, 0));
     if (sh_main) STEP(ntf_to_half(ctx, stream, a->W[Lo], w_n, const_cast<void*>(a->W16)));
+  } else if (a->run_adam && rows_split) {
+    // [0, w0_off) flat | layer 0's weight: the batch's rows + the floats up to the next 4-float boundary group | [.., opt_split) flat
+    if (w0_off > 0) STEP(ntf_adam_step_impl(ctx, st, a->params, a->grads, a->adam_m, a->adam_v, w0_off, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn, nullptr, 0, 0));
+    const size_t rest = w0_off + w0_n;  // (a multiple of 4 floats: w0_off and h0 are)
+    const bool small_tail = !sh_main && opt_split - rest <= 65536;  // the layer's bias (+ padding): stepped by the rows kernel itself, no launch of its own
+    STEP(ntf_adam_rows_impl(ctx, st, a->params + w0_off, a->grads + w0_off, a->adam_m + w0_off, a->adam_v + w0_off, a->S, h[0], ntf_csr_bag_bwd_counts(ws_bag, a->S), 1,
+                            w0_n, small_tail ? opt_split - rest : 0, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn));
+    if (!small_tail && opt_split > rest)
+      STEP(ntf_adam_step_impl(ctx, st, a->params + rest, a->grads + rest, a->adam_m + rest, a->adam_v + rest, opt_split - rest, a->lr, a->beta1, a->beta2, a->eps, a->adam_t,
+                              a->dyn, sh_main ? const_cast<void*>(a->W16) : nullptr, sh_main ? w_off - rest : 0, sh_main ? w_n : 0));
+    NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_adam_rows, 0));  // the untouched rows' pass (side 1) belongs to this step
   } else if (a->run_adam)
     STEP(ntf_adam_step_impl(ctx, st, a->params, a->grads, a->adam_m, a->adam_v, opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn,
                             sh_main ? const_cast<void*>(a->W16) : nullptr, sh_main ? w_off : 0, sh_main ? w_n : 0));
