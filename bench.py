@@ -300,14 +300,13 @@ def run_ours(args):
         eng.graph_event_factory = None
     else:
         for _ in range(args.steps): new_pair()
-    for i in range(args.warmup): device_step(i)
-    sync()
-    _lib.lib().ntf_launch_count(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     clk = ClockSampler(local).__enter__()  # samples through both timed legs (device-resident and end-to-end)
-    time.sleep(0.3)
+    time.sleep(0.3)                        # (the sampler's first reading) ... then the warm-up steps, so that the timed ones do not start on an idle GPU
+    for i in range(args.warmup): device_step(i)
     sync()
+    _lib.lib().ntf_launch_count(1)
     w0 = time.time()
     ev0.record()
     h0 = time.perf_counter()
@@ -334,7 +333,7 @@ def run_ours(args):
     # batch i+1 run on the host while the GPU works on batch i, as a loader thread would; all of it is inside the timed region.
     host = HostBatches(tv, train_rows, b, 0 if shard else rank, 1 if shard else G)
     for i in range(min(3, args.warmup)): host.step(eng, i)
-    host.run(eng, 3, 4)  # (both loss slots of the two-in-flight loop: their step graphs are captured here, not in the timed region)
+    host.run(eng, 3, max(4, args.warmup))  # (both loss slots of the two-in-flight loop: their step graphs are captured here, not in the timed region)
     sync()
     w0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -406,7 +405,7 @@ def run_ours(args):
            'data': 'synthetic', 'config': config_of(args, tv), 'clocks': clk.summary(),
            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': host.h2d_bytes, 'd2h_bytes_per_step': 4,
                    'api': 'HostPacker.pack (ntf_pack_host_batch: rows of the host teamsvecs CSR -> pinned block; batch i+1 packed while the GPU works on batch i) '
-                          '-> Engine.step_host: one H2D copy -> ntf_fnn_step (replayed as a CUDA graph) -> the loss of every step copied back and read by the host (two steps in flight: the host waits for loss i after it has enqueued step i+1); all inside the timed region'},
+                          '-> Engine.step_host: one H2D copy -> ntf_fnn_step (replayed as a CUDA graph) -> the loss of every step copied back and read by the host (two steps in flight: the host packs and enqueues batch i+1 while the GPU works on batch i, then waits for loss i; the copies run on the copy stream of the library); all inside the timed region'},
            'gpu_launches': launches, 'cuda_graphs': bool(graphs),
            'dp_exchange': None if G == 1 else {'peer': 'reduce-scatter + Adam + all-gather fused in one pass over peer memory inside ntf_fnn_step (csrc/peer.cu), 2 overlapped arena segments',
                                                'nccl': 'ncclAllReduce inside ntf_fnn_step: 2 overlapped arena segments, captured in the step graph'}.get(
@@ -712,16 +711,16 @@ class HostBatches:
 
     def run(self, eng, first, steps):
         """`steps` consecutive batches, every one packed from the host CSR, copied to the device and stepped, the loss of EVERY step read back.
-        Two steps are in flight: batch i+1 is packed and enqueued while the GPU works on batch i, then the host waits for loss i (its own
-        copy event, not the stream) -- the GPU never waits for the host as long as pack + enqueue take less than a step"""
+        Two steps are in flight: while the GPU works on batch i the host packs and enqueues batch i+1 (its copy runs on the library's copy
+        stream), then waits for loss i (its own copy event, not the stream) -- the GPU never waits for the host as long as pack + enqueue take
+        less than a step"""
         gB = self.b * self.G
         lo, hi = self._slice()
         eng.step_host(self.packer.pack(self._rows(first), lo, hi), gB, self.cap_s, self.cap_m, self.rank, self.G, lr=1e-3, sync=False, slot=0)
-        loss = None
         for i in range(1, steps):
-            blk = self.packer.pack(self._rows(first + i), lo, hi)  # (block i % 2: the copy of batch i-2 out of it has completed -- loss i-2 was read)
+            blk = self.packer.pack(self._rows(first + i), lo, hi)  # (block i % 3: the copy of batch i-3 out of it completed long ago -- loss i-2 was read)
             eng.step_host(blk, gB, self.cap_s, self.cap_m, self.rank, self.G, lr=1e-3, sync=False, slot=i & 1)
-            loss = eng.step_host_loss((i - 1) & 1)
+            eng.step_host_loss((i - 1) & 1)
         return eng.step_host_loss((steps - 1) & 1)
 
 

@@ -208,6 +208,9 @@ typedef struct {
   int prepared;                /* != 0: the caller ran ntf_out_train_prepare for this call already (off the critical path) */
   int defer_finish;            /* != 0: leave the call's final reductions (loss_out; db_prev when fused) to ntf_out_train_finish, which the caller
                                   runs with the same args / workspace on any stream ordered after this call -- they gate nothing but the optimiser */
+  void* ev_after_dense;        /* NTF_TF32 Fnn, nullable: a cudaEvent_t recorded on `stream` between the dense tensor-core pass and the sparse correction
+                                  pass.  Behind it dW / db are final for every expert that is neither a member nor a sampled negative of a team of the
+                                  batch: ntf_fnn_step starts the optimiser on those rows there, next to the correction pass */
 } ntf_out_train_args;
 int ntf_out_train_finish(ntf_ctx* ctx, void* stream, const ntf_out_train_args* args, void* workspace, size_t workspace_bytes);
 /* NTF_TF32 Fnn: what ntf_out_train has to clear before its kernel -- dA and the dW/db rows of expert tiles that two CTAs share.  A caller
@@ -456,6 +459,17 @@ int ntf_fnn_infer_topk(ntf_ctx* ctx, void* stream, const ntf_fnn_infer_topk_args
  * is packed for them only (empty skill rows elsewhere), the member CSR for all n rows (unigram_b samples from the whole batch). */
 int ntf_pack_host_batch(const int32_t* rows, int n, const int32_t* s_indptr, const int32_t* s_indices, const int32_t* m_indptr,
                         const int32_t* m_indices, int cap_s, int cap_m, int lo, int hi, int32_t* out, size_t out_words);
+
+/* The copies of the streaming entry point (host batches in, a loss out per step: fnn.py:118-140) on the context's own copy streams (one per
+ * direction), so that batch i+1 goes up while step i computes and loss i comes down while step i+1 computes; `slot` (0/1, alternating)
+ * names the device block / the events.
+ *   _upload    upload stream: waits for the step that read this slot's block last (the _download call of two steps ago marks it), then
+ *              cudaMemcpyAsync(dst_dev <- src_pinned); `stream` then waits for the copy
+ *   _download  marks the end of the step on `stream`; the download stream waits for it, then copies *loss_dev to *loss_pinned
+ *   _wait      the host blocks until the download of `slot` has landed */
+int ntf_host_batch_upload(ntf_ctx* ctx, void* stream, int slot, void* dst_dev, const void* src_pinned, size_t bytes);
+int ntf_host_loss_download(ntf_ctx* ctx, void* stream, int slot, const float* loss_dev, float* loss_pinned);
+int ntf_host_loss_wait(ntf_ctx* ctx, int slot);
 
 /* out[i] = sum_k parts[k*part_stride + i] in a fixed order (deterministic split reductions) */
 int ntf_sum_parts(ntf_ctx* ctx, void* stream, const float* parts, int nparts, size_t n, size_t part_stride, float* out);

@@ -21,7 +21,7 @@ class OutTrainArgs(C.Structure):
     _fields_ = [('A', vp), ('W', vp), ('b', vp), ('special', vp), ('pitch_words', i32), ('m_indptr', vp), ('m_indices', vp),
                 ('B', i32), ('h', i32), ('E', i32), ('tpw', f32), ('tnw', f32), ('loss_scale', f32),
                 ('dW', vp), ('db', vp), ('dA', vp), ('loss_out', vp),
-                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp), ('e_lo', i32), ('A16', vp), ('W16', vp), ('neg', vp), ('ns', i32), ('act_prev', vp), ('dz_prev', vp), ('db_prev', vp), ('prepared', i32), ('defer_finish', i32)]
+                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp), ('e_lo', i32), ('A16', vp), ('W16', vp), ('neg', vp), ('ns', i32), ('act_prev', vp), ('dz_prev', vp), ('db_prev', vp), ('prepared', i32), ('defer_finish', i32), ('ev_after_dense', vp)]
 
 
 class InferTopkArgs(C.Structure):
@@ -114,6 +114,9 @@ SIGNATURES = {
     'ntf_topk_merge': (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),
     'ntf_row_entropy': (i32, [vp, vp, vp, i32, i32, f32, i32, vp]),
     'ntf_eval_ranked': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(i32), i32, vp]),
+    'ntf_host_batch_upload': (i32, [vp, vp, i32, vp, vp, sz]),
+    'ntf_host_loss_download': (i32, [vp, vp, i32, vp, vp]),
+    'ntf_host_loss_wait': (i32, [vp, i32]),
     'ntf_csr_from_lists_workspace_bytes': (sz, [i32, sz]),
     'ntf_csr_from_lists': (i32, [vp, vp, i32, sz, vp, vp, i32, vp, vp, C.POINTER(C.c_int64), vp, sz]),
     'ntf_cooccur_workspace_bytes': (sz, [i32, sz]),

@@ -64,6 +64,14 @@ extern "C" int ntf_create(int device, ntf_ctx** out) {
   if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_bwd, cudaEventDisableTiming);
   if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_finish, cudaEventDisableTiming);
   if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_adam_rows, cudaEventDisableTiming);
+  if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_dense, cudaEventDisableTiming);
+  if (es == cudaSuccess) es = cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking);
+  if (es == cudaSuccess) es = cudaStreamCreateWithFlags(&c->copy_dn, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && es == cudaSuccess; ++i) {
+    es = cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming);
+    if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_step[i], cudaEventDisableTiming);
+    if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_loss[i], cudaEventDisableTiming);
+  }
   cudaSetDevice(cur);
   if (es != cudaSuccess) {
     ntf_set_error("ntf_create: side streams / events: %s", cudaGetErrorString(es));
@@ -80,9 +88,35 @@ extern "C" int ntf_destroy(ntf_ctx* ctx) {
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_fork_opt); cudaEventDestroy(ctx->ev_join_opt);
     cudaEventDestroy(ctx->ev_hot_fork); cudaEventDestroy(ctx->ev_hot_join);
-    cudaStreamDestroy(ctx->comm_st); cudaEventDestroy(ctx->ev_ar[0]); cudaEventDestroy(ctx->ev_ar[1]); cudaEventDestroy(ctx->ev_bwd); cudaEventDestroy(ctx->ev_finish); cudaEventDestroy(ctx->ev_adam_rows);
+    cudaStreamDestroy(ctx->comm_st); cudaEventDestroy(ctx->ev_ar[0]); cudaEventDestroy(ctx->ev_ar[1]); cudaEventDestroy(ctx->ev_bwd); cudaEventDestroy(ctx->ev_finish); cudaEventDestroy(ctx->ev_adam_rows); cudaEventDestroy(ctx->ev_dense);
+    cudaStreamDestroy(ctx->copy_st); cudaStreamDestroy(ctx->copy_dn);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_up[i]); cudaEventDestroy(ctx->ev_step[i]); cudaEventDestroy(ctx->ev_loss[i]); }
   }
   delete ctx;
+  return NTF_OK;
+}
+
+extern "C" int ntf_host_batch_upload(ntf_ctx* ctx, void* stream, int slot, void* dst_dev, const void* src_pinned, size_t bytes) {
+  NTF_REQUIRE(ctx && dst_dev && src_pinned && (slot == 0 || slot == 1), NTF_ERR_BAD_ARG, "host_batch_upload: null pointer or slot %d", slot);
+  NTF_CUDA(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_step[slot], 0));  // the step that read this slot's device block last (two calls ago) must be through
+  NTF_CUDA(cudaMemcpyAsync(dst_dev, src_pinned, bytes, cudaMemcpyHostToDevice, ctx->copy_st));
+  NTF_CUDA(cudaEventRecord(ctx->ev_up[slot], ctx->copy_st));
+  NTF_CUDA(cudaStreamWaitEvent(as_stream(stream), ctx->ev_up[slot], 0));
+  return NTF_OK;
+}
+
+extern "C" int ntf_host_loss_download(ntf_ctx* ctx, void* stream, int slot, const float* loss_dev, float* loss_pinned) {
+  NTF_REQUIRE(ctx && loss_dev && loss_pinned && (slot == 0 || slot == 1), NTF_ERR_BAD_ARG, "host_loss_download: null pointer or slot %d", slot);
+  NTF_CUDA(cudaEventRecord(ctx->ev_step[slot], as_stream(stream)));
+  NTF_CUDA(cudaStreamWaitEvent(ctx->copy_dn, ctx->ev_step[slot], 0));
+  NTF_CUDA(cudaMemcpyAsync(loss_pinned, loss_dev, sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_dn));
+  NTF_CUDA(cudaEventRecord(ctx->ev_loss[slot], ctx->copy_dn));
+  return NTF_OK;
+}
+
+extern "C" int ntf_host_loss_wait(ntf_ctx* ctx, int slot) {
+  NTF_REQUIRE(ctx && (slot == 0 || slot == 1), NTF_ERR_BAD_ARG, "host_loss_wait: slot %d", slot);
+  NTF_CUDA(cudaEventSynchronize(ctx->ev_loss[slot]));
   return NTF_OK;
 }
 

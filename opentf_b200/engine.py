@@ -139,21 +139,22 @@ def pack_host_batch(s_ptr, s_idx, m_ptr, m_idx, cap_s=None, cap_m=None):
 
 
 class HostPacker:
-    """packs global batches of the HOST teamsvecs CSR into pinned blocks for `Engine.step_host` (ntf_pack_host_batch: a memcpy per row), two
-    blocks in rotation so that batch i+1 can be packed while batch i is on the GPU -- the loader side of the streaming entry point"""
+    """packs global batches of the HOST teamsvecs CSR into pinned blocks for `Engine.step_host` (ntf_pack_host_batch: a memcpy per row), three
+    blocks in rotation so that batch i+1 can be packed (on a loader thread: the call releases the GIL) while batch i is being copied and batch
+    i-1 is on the GPU -- the loader side of the streaming entry point"""
 
     def __init__(self, skill_csr, member_csr, n, cap_s, cap_m):
         (self.sp, self.si, _), (self.mp, self.mi, _) = skill_csr, member_csr  # to_csr() triples: int32 indptr, indices
         self.n, self.cap_s, self.cap_m = int(n), int(cap_s), int(cap_m)
         self.words = 2 * (self.n + 1) + 2 * self.cap_s + self.cap_m
-        self.blocks = [torch.zeros(self.words, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.blocks = [torch.zeros(self.words, dtype=torch.int32).pin_memory() for _ in range(3)]
         self.k = 0
 
     def pack(self, rows, lo=0, hi=None):
         """[lo, hi): the rows of the global batch this rank trains on (skill CSR packed for them only; members for the whole batch)"""
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         assert len(rows) == self.n
-        blk = self.blocks[self.k]; self.k ^= 1
+        blk = self.blocks[self.k]; self.k = (self.k + 1) % 3
         _lib.check(_lib.lib().ntf_pack_host_batch(rows.ctypes.data, self.n, self.sp.ctypes.data, self.si.ctypes.data, self.mp.ctypes.data, self.mi.ctypes.data,
                                                   self.cap_s, self.cap_m, int(lo), self.n if hi is None else int(hi), blk.data_ptr(), self.words), 'ntf_pack_host_batch')
         return blk
@@ -845,28 +846,38 @@ class Engine:
     def step_host(self, packed, n, cap_s, cap_m, rank=0, G=1, lr=1e-3, train=True, sync=True, slot=0):
         """one step on a batch the HOST holds (`pack_host_batch`: compact CSR of the global batch in one pinned block): one H2D copy,
         this rank trains on its slice, and the loss comes back to the host -- the per-step shape of the reference's loop (fnn.py:118-140: H2D
-        of the batch, .item()).  sync=False: the loss is copied to a pinned host slot (`slot` 0/1) behind the step and an event marks it;
-        the caller reads it with step_host_loss(slot) -- after it has enqueued the NEXT step, so the GPU never waits for the host."""
-        st = getattr(self, '_hstage', None)
-        if st is None or st.buf.numel() < packed.numel():
-            st = self._hstage = _HostStage(self.device, 2 * packed.numel() + 1024)
-        st.view(n, cap_s, cap_m)
-        st.buf[:packed.numel()].copy_(packed, non_blocking=True)
+        of the batch, .item()).
+        sync=False is the streaming form: `slot` (0/1, alternating) names a device staging block, a loss slot and a pinned host slot; the copies
+        run on a copy stream -- batch i+1 goes up while step i computes, loss i comes down while step i+1 computes -- and the caller reads the
+        loss with step_host_loss(slot) AFTER it has enqueued the next step, so the compute stream runs the steps back to back."""
         b = -(-n // G)
         lo, hi = min(n, rank * b), min(n, (rank + 1) * b)
+        if sync:
+            st = getattr(self, '_hstage', None)
+            if st is None or st.buf.numel() < packed.numel():
+                st = self._hstage = _HostStage(self.device, 2 * packed.numel() + 1024)
+            st.view(n, cap_s, cap_m)
+            st.buf[:packed.numel()].copy_(packed, non_blocking=True)
+            self.step(st, lo, hi - lo, train, lr=lr, loss_slot=slot, loss_scale=1.0 / n, gbatch=(0, n))
+            return float(self.loss_buf[slot].item())
+        hs = getattr(self, '_hstream', None)
+        if hs is None or hs['stage'][0].buf.numel() < packed.numel():
+            hs = self._hstream = {'stage': [_HostStage(self.device, 2 * packed.numel() + 1024) for _ in range(2)], 'shape': [None, None],
+                                  'loss': torch.zeros(2, dtype=torch.float32).pin_memory()}
+            hs['loss_np'] = hs['loss'].numpy()
+        st = hs['stage'][slot]
+        if hs['shape'][slot] != (n, cap_s, cap_m):
+            st.view(n, cap_s, cap_m); hs['shape'][slot] = (n, cap_s, cap_m)
+        L, stream = _lib.lib(), torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(L.ntf_host_batch_upload(self.h, stream, slot, st.buf.data_ptr(), packed.data_ptr(), packed.numel() * 4), 'ntf_host_batch_upload')
         self.step(st, lo, hi - lo, train, lr=lr, loss_slot=slot, loss_scale=1.0 / n, gbatch=(0, n))
-        if sync: return float(self.loss_buf[slot].item())
-        if getattr(self, '_hloss', None) is None:
-            self._hloss = torch.zeros(2, dtype=torch.float32).pin_memory()
-            self._hloss_ev = [torch.cuda.Event(), torch.cuda.Event()]
-        self._hloss[slot:slot + 1].copy_(self.loss_buf[slot:slot + 1], non_blocking=True)
-        self._hloss_ev[slot].record(torch.cuda.current_stream(self.device))
+        _lib.check(L.ntf_host_loss_download(self.h, stream, slot, self.loss_buf.data_ptr() + 4 * slot, hs['loss'].data_ptr() + 4 * slot), 'ntf_host_loss_download')
         return None
 
     def step_host_loss(self, slot=0):
         """the loss of the step_host(sync=False, slot=slot) enqueued last on that slot: waits for ITS copy only (fnn.py:140 `loss.item()`)"""
-        self._hloss_ev[slot].synchronize()
-        return float(self._hloss[slot])
+        _lib.check(_lib.lib().ntf_host_loss_wait(self.h, slot), 'ntf_host_loss_wait')
+        return float(self._hstream['loss_np'][slot])
 
     # ------------------------------------------------------------------ inference
     def scores(self, sp, b0, B, out):
