@@ -208,9 +208,6 @@ typedef struct {
   int prepared;                /* != 0: the caller ran ntf_out_train_prepare for this call already (off the critical path) */
   int defer_finish;            /* != 0: leave the call's final reductions (loss_out; db_prev when fused) to ntf_out_train_finish, which the caller
                                   runs with the same args / workspace on any stream ordered after this call -- they gate nothing but the optimiser */
-  void* ev_after_dense;        /* NTF_TF32 Fnn, nullable: a cudaEvent_t recorded on `stream` between the dense tensor-core pass and the sparse correction
-                                  pass.  Behind it dW / db are final for every expert that is neither a member nor a sampled negative of a team of the
-                                  batch: ntf_fnn_step starts the optimiser on those rows there, next to the correction pass */
 } ntf_out_train_args;
 int ntf_out_train_finish(ntf_ctx* ctx, void* stream, const ntf_out_train_args* args, void* workspace, size_t workspace_bytes);
 /* NTF_TF32 Fnn: what ntf_out_train has to clear before its kernel -- dA and the dW/db rows of expert tiles that two CTAs share.  A caller

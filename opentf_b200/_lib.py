@@ -21,7 +21,7 @@ class OutTrainArgs(C.Structure):
     _fields_ = [('A', vp), ('W', vp), ('b', vp), ('special', vp), ('pitch_words', i32), ('m_indptr', vp), ('m_indices', vp),
                 ('B', i32), ('h', i32), ('E', i32), ('tpw', f32), ('tnw', f32), ('loss_scale', f32),
                 ('dW', vp), ('db', vp), ('dA', vp), ('loss_out', vp),
-                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp), ('e_lo', i32), ('A16', vp), ('W16', vp), ('neg', vp), ('ns', i32), ('act_prev', vp), ('dz_prev', vp), ('db_prev', vp), ('prepared', i32), ('defer_finish', i32), ('ev_after_dense', vp)]
+                ('A_s', vp), ('W_delta', vp), ('b_delta', vp), ('sign_out', vp), ('dW_delta', vp), ('db_delta', vp), ('dA_s', vp), ('special_t', vp), ('member_t', vp), ('e_lo', i32), ('A16', vp), ('W16', vp), ('neg', vp), ('ns', i32), ('act_prev', vp), ('dz_prev', vp), ('db_prev', vp), ('prepared', i32), ('defer_finish', i32)]
 
 
 class InferTopkArgs(C.Structure):

@@ -28,59 +28,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) adam1(p[i], g[i], m[i], v[i], k);
 }
-
-// A weight [S, h] row by row (a warp per row), the rows split by a per-row mark cnt[s]; the two passes together are bit-identical to one flat
-// pass (same adam1), they only run at different times of ntf_fnn_step:
-//  * layer 0 (mark = the batch holds the skill; ZERO_G): the unmarked rows have g = 0 exactly, so their update (moments decay, the parameter
-//    follows its momentum) does not depend on the step's backward pass: stepped at the TOP of the step on a side stream, no gradient read;
-//    the batch's rows after the backward pass
-//  * the output layer (mark = the expert is a member or a sampled negative of a team of the batch, i.e. a row the correction pass adds to):
-//    the unmarked rows are final after the dense tensor-core pass and are stepped next to the correction pass; the marked ones after it
-// TOUCHED = true also steps the contiguous tail [tail, tail + tail_n) (the layer's bias); shadow (nullable): the weight's fp16 image.
-template <bool TOUCHED, bool ZERO_G>
-__global__ void __launch_bounds__(256) adam_rows_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int S, int h4,
-                                                        const uint32_t* __restrict__ cnt, AdamK k, const ntf_dyn* __restrict__ dyn, size_t tail, size_t tail_n,
-                                                        uint2* __restrict__ shadow) {
-  if (dyn) k = AdamK{dyn->one_minus_b1, dyn->b2, dyn->one_minus_b2, dyn->bc2_sqrt, dyn->eps, dyn->neg_step};
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < S; s += warps) {
-    if ((__ldg(cnt + s) != 0u) != TOUCHED) continue;
-    const size_t row = (size_t)s * h4;
-    for (int c = lane; c < h4; c += 32) {
-      float4 P = reinterpret_cast<float4*>(p)[row + c], M = reinterpret_cast<float4*>(m)[row + c], V = reinterpret_cast<float4*>(v)[row + c];
-      float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (TOUCHED || !ZERO_G) G = __ldg(reinterpret_cast<const float4*>(g) + row + c);
-      adam1(P.x, G.x, M.x, V.x, k); adam1(P.y, G.y, M.y, V.y, k); adam1(P.z, G.z, M.z, V.z, k); adam1(P.w, G.w, M.w, V.w, k);
-      reinterpret_cast<float4*>(p)[row + c] = P; reinterpret_cast<float4*>(m)[row + c] = M; reinterpret_cast<float4*>(v)[row + c] = V;
-      if (shadow) {  // the fp16 image of this weight (adam_kernel's `shadow`)
-        const __half2 lo = __floats2half2_rn(P.x, P.y), hi = __floats2half2_rn(P.z, P.w);
-        shadow[row + c] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
-      }
-    }
-  }
-  if (TOUCHED)
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tail_n; i += (size_t)gridDim.x * blockDim.x) adam1(p[tail + i], g[tail + i], m[tail + i], v[tail + i], k);
-}
 }  // namespace
-
-// p, g, m, v: the [S, h] weight (h % 4 == 0, 16-byte aligned); tail / tail_n: floats relative to p stepped with the touched rows (touched = 1 only);
-// zero_g: the untouched rows' gradient is known to be 0 and is not read; shadow (nullable): fp16 image [S, h] of the weight
-int ntf_adam_rows_impl(ntf_ctx* ctx, cudaStream_t st, float* p, const float* g, float* m, float* v, int S, int h, const uint32_t* cnt, int touched, size_t tail,
-                       size_t tail_n, double lr, double beta1, double beta2, double eps, int64_t step, const ntf_dyn* dyn, int zero_g, void* shadow) {
-  NTF_REQUIRE(ctx && p && g && m && v && cnt, NTF_ERR_BAD_ARG, "adam_rows: null pointer");
-  NTF_REQUIRE(S > 0 && h > 0 && (h % 4) == 0 && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0), NTF_ERR_BAD_ARG, "adam_rows: S=%d h=%d or misaligned", S, h);
-  NTF_REQUIRE(dyn || step >= 1, NTF_ERR_BAD_ARG, "adam_rows: step=%lld (1-based)", (long long)step);
-  const AdamK k = adam_consts(lr, beta1, beta2, eps, step >= 1 ? step : 1);
-  const int blocks = min(cdiv(S, 8), ctx->sm_count * 16);
-  NTF_COUNT_LAUNCH;
-  NTF_REQUIRE(!shadow || ((uintptr_t)shadow & 7) == 0, NTF_ERR_BAD_ARG, "adam_rows: misaligned fp16 image");
-  if (touched) adam_rows_kernel<true, false><<<blocks, 256, 0, st>>>(p, g, m, v, S, h / 4, cnt, k, dyn, tail, tail_n, (uint2*)shadow);
-  else if (zero_g) adam_rows_kernel<false, true><<<blocks, 256, 0, st>>>(p, g, m, v, S, h / 4, cnt, k, dyn, 0, 0, (uint2*)shadow);
-  else adam_rows_kernel<false, false><<<blocks, 256, 0, st>>>(p, g, m, v, S, h / 4, cnt, k, dyn, 0, 0, (uint2*)shadow);
-  NTF_LAUNCH_CHECK();
-  return NTF_OK;
-}
 
 // `dyn` (device, nullable): the constants come from the block ntf_dyn_update wrote for this step instead of the arguments
 int ntf_adam_step_impl(ntf_ctx* ctx, cudaStream_t st, float* p, const float* g, float* m, float* v, size_t n, double lr, double beta1,

@@ -63,8 +63,6 @@ extern "C" int ntf_create(int device, ntf_ctx** out) {
   for (int i = 0; i < 2 && es == cudaSuccess; ++i) es = cudaEventCreateWithFlags(&c->ev_ar[i], cudaEventDisableTiming);
   if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_bwd, cudaEventDisableTiming);
   if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_finish, cudaEventDisableTiming);
-  if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_adam_rows, cudaEventDisableTiming);
-  if (es == cudaSuccess) es = cudaEventCreateWithFlags(&c->ev_dense, cudaEventDisableTiming);
   if (es == cudaSuccess) es = cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking);
   if (es == cudaSuccess) es = cudaStreamCreateWithFlags(&c->copy_dn, cudaStreamNonBlocking);
   for (int i = 0; i < 2 && es == cudaSuccess; ++i) {
@@ -88,7 +86,7 @@ extern "C" int ntf_destroy(ntf_ctx* ctx) {
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_fork_opt); cudaEventDestroy(ctx->ev_join_opt);
     cudaEventDestroy(ctx->ev_hot_fork); cudaEventDestroy(ctx->ev_hot_join);
-    cudaStreamDestroy(ctx->comm_st); cudaEventDestroy(ctx->ev_ar[0]); cudaEventDestroy(ctx->ev_ar[1]); cudaEventDestroy(ctx->ev_bwd); cudaEventDestroy(ctx->ev_finish); cudaEventDestroy(ctx->ev_adam_rows); cudaEventDestroy(ctx->ev_dense);
+    cudaStreamDestroy(ctx->comm_st); cudaEventDestroy(ctx->ev_ar[0]); cudaEventDestroy(ctx->ev_ar[1]); cudaEventDestroy(ctx->ev_bwd); cudaEventDestroy(ctx->ev_finish);
     cudaStreamDestroy(ctx->copy_st); cudaStreamDestroy(ctx->copy_dn);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_up[i]); cudaEventDestroy(ctx->ev_step[i]); cudaEventDestroy(ctx->ev_loss[i]); }
   }

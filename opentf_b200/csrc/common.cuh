@@ -28,8 +28,6 @@ struct ntf_ctx {
   cudaEvent_t ev_ar[2], ev_bwd;
   cudaStream_t copy_st, copy_dn;  // the streaming entry point's copies, one stream per direction (ntf_host_batch_upload / ntf_host_loss_download)
   cudaEvent_t ev_up[2], ev_step[2], ev_loss[2];
-  cudaEvent_t ev_dense;      // between the output layer's dense pass and its correction pass (ntf_out_train_args.ev_after_dense)
-  cudaEvent_t ev_adam_rows;  // the optimiser pass over layer 0's rows the batch does not touch (side 1, started at the top of the step) is done
   cudaEvent_t ev_finish;  // the output layer's deferred reductions (loss, fused db) done on side[0]: the optimiser of the hidden layers' segment waits for it
 };
 

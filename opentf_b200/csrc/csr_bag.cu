@@ -574,9 +574,6 @@ static BagBwdWs bag_bwd_ws(void* workspace, int S) {
 }
 
 // pass 1 depends on the batch's CSR only (not on dZ): ntf_fnn_step runs it on a side stream while the output layer computes
-// entries per skill in the batch (after ntf_csr_bag_bwd_fill_impl on the same workspace): > 0 = the batch touches the skill's row of dW0T
-const uint32_t* ntf_csr_bag_bwd_counts(void* workspace, int S) { return bag_bwd_ws(workspace, S).cnt; }
-
 int ntf_csr_bag_bwd_fill_impl(ntf_ctx* ctx, cudaStream_t st, int B, const int32_t* indptr, const int32_t* indices, const int32_t* ent_row,
                               int row_base, int S, int h, void* workspace, size_t workspace_bytes, const uint32_t* ent_sign) {
   NTF_REQUIRE(ctx && indptr && indices && ent_row && workspace, NTF_ERR_BAD_ARG, "csr_bag_bwd: null pointer");

@@ -716,7 +716,6 @@ int ntf_out_train_tc2(ntf_ctx* ctx, cudaStream_t st, const ntf_out_train_args* a
   NTF_CUDA(cudaFuncSetAttribute(out_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   NTF_COUNT_LAUNCH; out_tc2_kernel<<<grid, NT, SMEM_BYTES, st>>>(mw, mh, mdw, g);
   NTF_LAUNCH_CHECK();
-  if (train && a->ev_after_dense) NTF_CUDA(cudaEventRecord((cudaEvent_t)a->ev_after_dense, st));  // (see ntf_out_train_args)
   FixArgs f{};
   f.A16 = A16; f.W16 = W16; f.bias = a->b; f.m_indptr = a->m_indptr; f.m_indices = a->m_indices; f.neg = a->neg; f.ns = a->neg ? a->ns : 0;
   f.B = a->B; f.E = a->E; f.e_lo = a->e_lo; f.tpw = a->tpw; f.tnw = a->tnw; f.scale = a->loss_scale;

@@ -29,33 +29,11 @@ int ntf_peer_exchange_adam_impl(ntf_ctx* ctx, cudaStream_t st, const ntf_peers* 
                                 double beta1, double beta2, double eps, int64_t step, const ntf_dyn* dyn, int channel);
 
 int ntf_peer_allreduce_impl(ntf_ctx* ctx, cudaStream_t st, const ntf_peers* pr, size_t n, float* dst, int channel);
-int ntf_adam_rows_impl(ntf_ctx* ctx, cudaStream_t st, float* p, const float* g, float* m, float* v, int S, int h, const uint32_t* cnt, int touched, size_t tail,
-                       size_t tail_n, double lr, double beta1, double beta2, double eps, int64_t step, const ntf_dyn* dyn, int zero_g, void* shadow);
-const uint32_t* ntf_csr_bag_bwd_counts(void* workspace, int S);
 
 static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 
 // workspace = [ input-layer backward (slots, lives from the fork to the end of the step) | everything that runs on the main stream ]
 static size_t bag_region(const ntf_fnn_step_args* a) { return a->x_dense ? 0 : align_up(ntf_csr_bag_bwd_workspace_bytes(a->S, a->hidden[0]), 256); }
-// [ ... | one mark per expert of this call's range: a member or a sampled negative of a team of the batch (the rows the correction pass adds to) | ... ]
-static size_t mark_region(const ntf_fnn_step_args* a) { return align_up((size_t)a->E * sizeof(uint32_t), 256); }
-
-namespace {
-// thread per team: marks[e - e_lo] = 1 for the team's members and its sampled negatives (the candidate set of out_fix_kernel, or a superset)
-__global__ void mark_experts_kernel(int B, const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_indices, const int32_t* __restrict__ neg, int ns, int e_lo,
-                                    int E, uint32_t* __restrict__ marks) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= B) return;
-  for (int p = m_indptr[n]; p < m_indptr[n + 1]; ++p) {
-    const int e = m_indices[p] - e_lo;
-    if (e >= 0 && e < E) marks[e] = 1u;
-  }
-  for (int q = 0; q < ns; ++q) {
-    const int e = neg[(size_t)n * ns + q] - e_lo;  // (-1 = no sample)
-    if (e >= 0 && e < E) marks[e] = 1u;
-  }
-}
-}  // namespace
 
 extern "C" size_t ntf_fnn_step_workspace_bytes(const ntf_ctx* ctx, const ntf_fnn_step_args* a) {
   if (!a || a->n_layers < 2 || a->n_layers > NTF_MAX_LAYERS) return 0;
@@ -65,7 +43,7 @@ extern "C" size_t ntf_fnn_step_workspace_bytes(const ntf_ctx* ctx, const ntf_fnn
   for (int i = 0; i < L - 1; ++i) w = max_sz(w, ntf_act_bwd_workspace_bytes(a->B, a->hidden[i]));
   for (int i = 1; i < L - 1; ++i) w = max_sz(w, ntf_dense_bwd_workspace_bytes(a->B, a->hidden[i - 1], a->hidden[i]));
   if (a->x_dense) w = max_sz(w, ntf_dense_bwd_workspace_bytes(a->B, a->S, a->hidden[0]));
-  return bag_region(a) + mark_region(a) + w;
+  return bag_region(a) + w;
 }
 
 extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args* a, void* workspace, size_t workspace_bytes) {
@@ -81,9 +59,8 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
   cudaStream_t st = as_stream(stream);
   void* ws_bag = workspace;
   const size_t ws_bag_bytes = bag_region(a);
-  uint32_t* marks = (uint32_t*)((char*)workspace + ws_bag_bytes);
-  void* ws_main = (char*)workspace + ws_bag_bytes + mark_region(a);
-  const size_t ws_main_bytes = workspace_bytes - ws_bag_bytes - mark_region(a);
+  void* ws_main = (char*)workspace + ws_bag_bytes;
+  const size_t ws_main_bytes = workspace_bytes - ws_bag_bytes;
   const bool bwd_here = a->train && (phase & 2);
   // tensor-core Fnn output layer = the persistent kernel + sparse correction pass of out_tc2.cu (NTF_TC_V1=1: round 1's kernel, bit planes)
   const bool tc2 = a->precision == NTF_TF32 && getenv("NTF_TC_V1") == nullptr;
@@ -93,16 +70,9 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
   const bool act_fused = tc2 && Lo == 1 && a->train && phase == 3 && !shard_x;
   ntf_out_train_args o;  // the output layer's call; its final reductions may run later, off the critical path (finish_pending)
   memset(&o, 0, sizeof(o));
-  bool finish_pending = false, finish_side = false, marks_ready = false;
+  bool finish_pending = false, finish_side = false;
   int rc;
 #define STEP(call) do { if ((rc = (call)) != NTF_OK) return rc; } while (0)
-  // layer 0's weight [S, h0] (CSR input, single rank, whole step in this call): its Adam pass is split by rows -- see ntf_adam_rows_impl.
-  // Under data parallelism the gradient of a row this rank's batch does not touch is not zero after the exchange: one flat pass there.
-  const size_t w0_off = (size_t)(a->W[0] - a->params), w0_n = (size_t)a->S * h[0];
-  const size_t last_off = (size_t)((a->gW[Lo] < a->gb[Lo] ? a->gW[Lo] : a->gb[Lo]) - a->grads);  // the last layer's segment starts here (arena order)
-  const bool rows_split = bwd_here && phase == 3 && a->run_adam && !a->x_dense && a->comm == nullptr && a->peers == nullptr && getenv("NTF_ADAM_ROWS_OFF") == nullptr &&
-                          a->W[0] >= a->params && (size_t)(a->gW[0] - a->grads) == w0_off && (w0_off % 4) == 0 && (h[0] % 4) == 0 && a->gW[Lo] >= a->grads &&
-                          w0_off + w0_n <= last_off && last_off <= a->n_params;
   // ---- fork: what needs the batch's CSR only ----
   if ((phase & 1) || bwd_here) NTF_CUDA(cudaEventRecord(ctx->ev_fork, st));
   const bool prep = bwd_here && tc2 && (phase & 1);
@@ -113,13 +83,6 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
     // ... and every (team, skill) entry takes a slot of its skill (pass 1 of the input layer's backward)
     if (!a->x_dense) STEP(ntf_csr_bag_bwd_fill_impl(ctx, ctx->side[1], B, a->s_indptr, a->s_indices, a->s_ent_row, a->row_base, a->S, h[0], ws_bag, ws_bag_bytes, nullptr));
     NTF_CUDA(cudaEventRecord(ctx->ev_join[1], ctx->side[1]));
-    // ... and the optimiser steps the rows of layer 0's weight the batch does NOT touch (g = 0 there whatever the backward pass computes):
-    // ~3/4 of that weight's Adam traffic moves from the end of the critical path to here, under the output layer's kernel
-    if (rows_split) {
-      STEP(ntf_adam_rows_impl(ctx, ctx->side[1], a->params + w0_off, a->grads + w0_off, a->adam_m + w0_off, a->adam_v + w0_off, a->S, h[0],
-                              ntf_csr_bag_bwd_counts(ws_bag, a->S), 0, 0, 0, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn, 1, nullptr));
-      NTF_CUDA(cudaEventRecord(ctx->ev_adam_rows, ctx->side[1]));
-    }
   }
   if (phase & 1) {
     const bool tc = a->precision == NTF_TF32;
@@ -143,13 +106,6 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
       // the one-hidden-layer CSR configuration: there nothing else touches the main part of the workspace while they are pending
       o.defer_finish = (bwd_here && a->run_adam && act_fused && !a->x_dense) ? 1 : 0;
       finish_pending = o.defer_finish != 0;
-      if (rows_split) {  // the optimiser of the output layer is split by rows too: mark the rows the correction pass will add to (side 0, behind the sampler)
-        NTF_CUDA(cudaMemsetAsync(marks, 0, (size_t)a->E * sizeof(uint32_t), ctx->side[0]));
-        NTF_COUNT_LAUNCH; mark_experts_kernel<<<cdiv(B, 128), 128, 0, ctx->side[0]>>>(B, a->m_indptr, a->m_indices, neg, neg ? ns : 0, a->e_lo, a->E, marks);
-        NTF_LAUNCH_CHECK();
-        o.ev_after_dense = ctx->ev_dense;
-        marks_ready = true;
-      }
     } else if (tc) {
       STEP(ntf_special_tiles(ctx, ctx->side[0], 1, B, a->m_indptr, a->m_indices, neg, ns, a->E, a->e_lo, a->special_t, a->member_t));
       o.special_t = a->special_t; o.member_t = a->member_t;
@@ -211,9 +167,6 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
   NTF_REQUIRE(!peers || (a->run_adam && phase == 3 && a->peers->params[a->peers->rank] == a->params && a->peers->grads[a->peers->rank] == a->grads),
               NTF_ERR_BAD_ARG, "fnn_step: peers needs run_adam, phase 3 and this rank's own arenas in the table");
   const bool dp = a->comm != nullptr && !peers;
-  // the last layer's segment is [its weight | its bias] and the weight's rows carry marks: its optimiser pass is split like layer 0's
-  const bool l1_split = marks_ready && opt_split < a->n_params && w_off == opt_split && (w_n % 4) == 0 && (h[Lo - 1] % 4) == 0 && w_off + w_n <= a->n_params &&
-                        (a->W16 == nullptr || shadow) && (size_t)(a->gW[Lo] - a->grads) == w_off && getenv("NTF_ADAM_L1_FLAT") == nullptr;
   NTF_REQUIRE(!dp || (a->allreduce && a->run_adam && phase == 3), NTF_ERR_BAD_ARG, "fnn_step: comm needs allreduce, run_adam and phase 3");
   const ntf_allreduce_fn allreduce = (ntf_allreduce_fn)a->allreduce;
 #define ALLREDUCE(ptr, count)                                                                                               \
@@ -228,15 +181,9 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
       ALLREDUCE(a->grads + opt_split, a->n_params - opt_split);
       NTF_CUDA(cudaEventRecord(ctx->ev_ar[0], ctx->comm_st));
       NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_ar[0], 0));
-    } else {
-      if (l1_split) {  // the rows of the last layer's weight the correction pass does not add to: final after the dense pass, stepped next to the correction pass
-        NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_dense, 0));
-        STEP(ntf_adam_rows_impl(ctx, ctx->side[0], a->params + w_off, a->grads + w_off, a->adam_m + w_off, a->adam_v + w_off, a->E, h[Lo - 1], marks, 0, 0, 0, a->lr, a->beta1,
-                                a->beta2, a->eps, a->adam_t, a->dyn, 0, const_cast<void*>(a->W16)));
-      }
-      NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork_opt, 0));
-    }
-    if (finish_pending) {  // (in front of the last layer's optimiser: measured better than a stream of its own, profiles/r02h_step_optimiser_ab.txt)
+    } else
+    NTF_CUDA(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork_opt, 0));
+    if (finish_pending) {
       STEP(ntf_out_train_finish(ctx, (void*)ctx->side[0], &o, ws_main, ws_main_bytes));
       NTF_CUDA(cudaEventRecord(ctx->ev_finish, ctx->side[0]));
       finish_pending = false; finish_side = true;
@@ -246,10 +193,7 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
       STEP(ntf_peer_exchange_adam_impl(ctx, ctx->side[0], a->peers, a->adam_m, a->adam_v, opt_split, a->n_params - opt_split, a->lr, a->beta1,
                                        a->beta2, a->eps, a->adam_t, a->dyn, 1));
       if (sh_here) STEP(ntf_to_half(ctx, (void*)ctx->side[0], a->W[Lo], w_n, const_cast<void*>(a->W16)));
-    } else if (l1_split)  // ... and the marked rows + the bias behind the correction pass
-      STEP(ntf_adam_rows_impl(ctx, ctx->side[0], a->params + w_off, a->grads + w_off, a->adam_m + w_off, a->adam_v + w_off, a->E, h[Lo - 1], marks, 1, w_n,
-                              a->n_params - (w_off + w_n), a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn, 0, const_cast<void*>(a->W16)));
-    else
+    } else
     STEP(ntf_adam_step_impl(ctx, ctx->side[0], a->params + opt_split, a->grads + opt_split, a->adam_m + opt_split, a->adam_v + opt_split,
                             a->n_params - opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn, sh_here ? const_cast<void*>(a->W16) : nullptr,
                             sh_here ? w_off - opt_split : 0, sh_here ? w_n : 0));
@@ -283,17 +227,6 @@ extern "C" int ntf_fnn_step(ntf_ctx* ctx, void* stream, const ntf_fnn_step_args*
   if (peers) {
     STEP(ntf_peer_exchange_adam_impl(ctx, st, a->peers, a->adam_m, a->adam_v, 0, opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn, 0));
     if (sh_main) STEP(ntf_to_half(ctx, stream, a->W[Lo], w_n, const_cast<void*>(a->W16)));
-  } else if (a->run_adam && rows_split) {
-    // [0, w0_off) flat | layer 0's weight: the batch's rows + the floats up to the next 4-float boundary group | [.., opt_split) flat
-    if (w0_off > 0) STEP(ntf_adam_step_impl(ctx, st, a->params, a->grads, a->adam_m, a->adam_v, w0_off, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn, nullptr, 0, 0));
-    const size_t rest = w0_off + w0_n;  // (a multiple of 4 floats: w0_off and h0 are)
-    const bool small_tail = !sh_main && opt_split - rest <= 65536;  // the layer's bias (+ padding): stepped by the rows kernel itself, no launch of its own
-    STEP(ntf_adam_rows_impl(ctx, st, a->params + w0_off, a->grads + w0_off, a->adam_m + w0_off, a->adam_v + w0_off, a->S, h[0], ntf_csr_bag_bwd_counts(ws_bag, a->S), 1,
-                            w0_n, small_tail ? opt_split - rest : 0, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn, 1, nullptr));
-    if (!small_tail && opt_split > rest)
-      STEP(ntf_adam_step_impl(ctx, st, a->params + rest, a->grads + rest, a->adam_m + rest, a->adam_v + rest, opt_split - rest, a->lr, a->beta1, a->beta2, a->eps, a->adam_t,
-                              a->dyn, sh_main ? const_cast<void*>(a->W16) : nullptr, sh_main ? w_off - rest : 0, sh_main ? w_n : 0));
-    NTF_CUDA(cudaStreamWaitEvent(st, ctx->ev_adam_rows, 0));  // the untouched rows' pass (side 1) belongs to this step
   } else if (a->run_adam)
     STEP(ntf_adam_step_impl(ctx, st, a->params, a->grads, a->adam_m, a->adam_v, opt_split, a->lr, a->beta1, a->beta2, a->eps, a->adam_t, a->dyn,
                             sh_main ? const_cast<void*>(a->W16) : nullptr, sh_main ? w_off : 0, sh_main ? w_n : 0));

@@ -453,6 +453,10 @@ class Engine:
         if dp: self.optimizer_step(lr)
         else: self.adam_t += 1
 
+    def clear_graphs(self):
+        """forget the captured step graphs (they are captured again on the next use)"""
+        self._graphs.clear()
+
     def attach_comm(self, comm=None):
         """data-parallel ranks: hand the library an NCCL communicator (nccl.Comm) so that ntf_fnn_step exchanges the gradients itself --
         two all-reduces on its own stream inside the (captured) step instead of torch.distributed calls between two halves of it."""

@@ -198,64 +198,6 @@ def test_step_host_is_the_same_step_as_the_resident_path(toy):
     assert out[0][0][2] < out[0][0][0]
 
 
-def test_adam_split_by_rows_is_bit_identical_to_the_flat_pass(toy):
-    """ntf_fnn_step steps the rows of layer 0's weight the batch does not touch early on a side stream and the batch's rows after the backward
-    pass (ntf_adam_rows_impl); NTF_ADAM_ROWS_OFF=1 is the single flat pass: parameters and Adam moments must agree bit for bit, with graphs and without"""
-    import os
-    from opentf_b200.engine import Engine
-    skill, member, splits, _ = toy('dblp')
-    rows = np.asarray(splits['folds'][0]['train'])
-    torch.manual_seed(0)
-    layers = O.init_params(skill.shape[1], [32], member.shape[1])
-    sd = {f'layers.{i}.{n}': t for i, (W, b) in enumerate(layers) for n, t in (('weight', W), ('bias', b))}
-    out = []
-    for off in (False, True):
-        if off: os.environ['NTF_ADAM_ROWS_OFF'] = '1'
-        try:
-            eng = Engine(skill.shape[1], [32], member.shape[1], 'cuda:0', precision='fp32', nsd='uniform', ns=3, seed=5, max_batch=8)
-            eng.stage(skill, member)
-            eng.load_state_dict(sd)
-            sp = eng.split(rows)
-            for i in range(6): eng.step(sp, (i % 2) * 8, 8 if i % 2 == 0 else min(8, sp.n - 8), True, lr=1e-2, loss_slot=i)
-            torch.cuda.synchronize()
-            out.append((eng.params.cpu().clone(), eng.adam_m.cpu().clone(), eng.adam_v.cpu().clone(), eng.loss_buf[:6].cpu().clone()))
-        finally:
-            os.environ.pop('NTF_ADAM_ROWS_OFF', None)
-    for a, b in zip(out[0], out[1]): assert torch.equal(a, b)
-
-
-def test_output_layer_adam_split_by_marked_rows_matches_the_flat_pass():
-    """tensor-core mode: the experts the correction pass does not add to are stepped right after the dense pass, the members / sampled negatives
-    after the correction pass (step.cu: l1_split).  Against NTF_ADAM_L1_FLAT=1 (one pass): parameters and moments agree to the run-to-run noise of
-    the mode's fp32 atomics, and the fp16 image of the weight is exactly the rounded weight after every arrangement"""
-    import os
-    from opentf_b200.engine import Engine
-    from test_gpu_kernels import rand_csr
-    rng = np.random.default_rng(21)
-    N, S, E, B = 64, 50, 1000, 32
-    skill, member = rand_csr(rng, N, S, 1, 6), rand_csr(rng, N, E, 1, 5)
-    torch.manual_seed(2)
-    layers = O.init_params(S, [128], E)
-    sd = {f'layers.{i}.{n}': t for i, (W, b) in enumerate(layers) for n, t in (('weight', W), ('bias', b))}
-    out = []
-    for flat in (False, True):
-        if flat: os.environ['NTF_ADAM_L1_FLAT'] = '1'
-        try:
-            eng = Engine(S, [128], E, 'cuda:0', precision='tf32', nsd='uniform', ns=4, seed=5, max_batch=B)
-            eng.stage(skill, member)
-            eng.load_state_dict(sd)
-            sp = eng.split(np.arange(N))
-            for i in range(5): eng.step(sp, (i % 2) * B, B, True, lr=1e-2, loss_slot=i)
-            torch.cuda.synchronize()
-            W = eng.view('layers.1.weight')
-            assert torch.equal(eng._w16.view(E, 128), W.to(torch.float16)), 'fp16 image out of step with the weight'
-            out.append((eng.params.cpu().clone(), eng.adam_m.cpu().clone(), eng.adam_v.cpu().clone(), eng.loss_buf[:5].cpu().clone()))
-        finally:
-            os.environ.pop('NTF_ADAM_L1_FLAT', None)
-    for a, b in zip(out[0], out[1]): assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item())
-    assert out[0][3][4] < out[0][3][0]
-
-
 def test_step_host_with_two_steps_in_flight_returns_every_loss(toy):
     """the streaming loop of bench.py's end-to-end leg: step i+1 is enqueued before the host reads loss i (pinned slot + its own event);
     losses and final parameters are those of the synchronous loop"""
