@@ -648,8 +648,8 @@ def kernel_rooflines(eng, sp, b, dev, sync, pk):
 
 def topk_sweep(args, tv, splits, dev, sync, G, lin_sd):
     """BASELINE configs[4]: top-K expert ranking over all experts, K x batch sweep (device resident; team-parallel: every rank ranks its own
-    batches, the aggregate is G x one rank's rate).  K <= 128 runs the fused kernel (the [B,E] scores never reach HBM), K = 1000 (the
-    reference's default testcfg.topK) the scores -> radix-select path.  Small batches are latency-bound (one library call per batch: ~6
+    batches, the aggregate is G x one rank's rate).  K <= 1024 with 32 K <= E runs the fused kernels (the [B,E] scores never reach HBM) -- that includes
+    K = 1000, the reference's default testcfg.topK; the `fused` flag of every row says which path ran.  Small batches are latency-bound (one library call per batch: ~6
     launches); the teams/s at batch >= 4096 is the throughput figure."""
     import torch
     from opentf_b200.engine import Engine

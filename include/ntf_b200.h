@@ -247,7 +247,7 @@ typedef struct ntf_infer_topk_args {
   float* vals;      /* [B,K] out: probabilities, rank order */
   int32_t* idx;     /* [B,K] out: expert ids */
 } ntf_infer_topk_args;
-int ntf_infer_topk_supported(int B, int h, int E, int K); /* h == 128, K <= 128, 32*K <= E <= 131072 */
+int ntf_infer_topk_supported(int B, int h, int E, int K); /* h == 128, K <= 1024, 32*K <= E <= 131072 */
 size_t ntf_infer_topk_workspace_bytes(int B, int h, int E, int K);
 int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_args* args, void* workspace, size_t workspace_bytes);
 /* y[i] = fp16(x[i]) round-to-nearest: the fp16 operand images the tensor-core kernels read (10-bit mantissa = TF32's) */

@@ -81,7 +81,7 @@ struct ItArgs {
   int nblk;              // row pitch of bm = 4 * nct (blocks of 32 experts, the last tile padded)
   float* bm;             // pass 1 out: [B, nblk] block maxima (-inf for blocks past E)
   const uint32_t* bits;  // pass 2 in: [nwords, B] bit blk % 32 of word blk / 32 = the block is one of the team's K best blocks (blockmax_threshold_kernel), and
-  const uint8_t* slot;   //            [B, nblk] for those blocks: the slot 0..K-1 among them (the other bytes are not written; slot_blk[B, K] is the inverse)
+  const uint16_t* slot;  //            [B, nblk] for those blocks: the slot 0..K-1 among them (the other entries are not written; slot_blk[B, K] is the inverse)
   int nwords;
   float* cand;           // pass 2 out: [B, K, 32] the products a.w (no bias yet) of the team's K best blocks, slot by slot; every entry written
   int timing_pass;
@@ -256,60 +256,152 @@ __global__ void __launch_bounds__(NT, 1) infer_topk_kernel(const __grid_constant
 // Candidate i of a team: slot i / 32, expert slot_blk[slot] * 32 + i % 32; its logit = the stored product + the expert's bias (the same fp32 add
 // as pass 1's); it counts if the logit is >= the team's Tz and the expert exists; composite = ordered logit << 32 | ~expert (0 = none).
 
-// per team: the candidates >= Tz in rank order -> the first K as (probability, global expert id).  One CTA per team; the 32*K candidates of the
-// K blocks pass 2 stored are filtered into shared memory (a few per block survive), then a bitonic sort of the survivors.
-constexpr int FIN_THREADS = 128;
+// per team (K > 32): the candidates >= Tz in rank order -> the first K as (probability, global expert id).  One CTA per team.  A warp takes a
+// slot (a block of 32 candidates) at a time; the survivors (a few per block) are appended to shared memory, one atomic per warp and slot.
+// `raise_bar`: an adaptive radix select over the UNIQUE composites -- 256-bin histograms of the current range, one sweep per round -- that
+// finds a bar with K <= #(composites >= bar) <= limit.  It is used twice: over the candidates in global memory when more than SEL_CAP
+// survive (K near 1000 on a flat score distribution, a plateau of equal scores: rare), and over the survivors in shared memory to cut them
+// down to the next power of two above K before the bitonic sort (sorting 2 048 survivors to emit 1 000 cost more than everything else).
+constexpr int FIN_THREADS = 256, SEL_CAP = 4096, KMAX = 1024;
 __global__ void __launch_bounds__(FIN_THREADS) infer_topk_final_kernel(const float* __restrict__ cand, const int32_t* __restrict__ slot_blk,
                                                                        const float* __restrict__ bias, const float* __restrict__ thr_val, int cap, int K, int E,
                                                                        int e_lo, float* __restrict__ vals, int32_t* __restrict__ idx) {
-  extern __shared__ unsigned long long sel[];  // [npad(cap)]
-  __shared__ int nsel;
-  __shared__ int sblk[128];  // K <= 128: the block of every slot
-  const int n = blockIdx.x;
-  if (threadIdx.x == 0) nsel = 0;
+  __shared__ unsigned long long sel[SEL_CAP];
+  __shared__ unsigned long long top[KMAX];
+  __shared__ int sblk[KMAX];  // the block of every slot
+  __shared__ uint32_t hist[256];
+  __shared__ unsigned long long bar_s;
+  __shared__ int nsel, need_s, done_s;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = FIN_THREADS / 32;
+  if (tid == 0) nsel = 0;
   griddep_launch();
   griddep_wait();
-  if (threadIdx.x < K) sblk[threadIdx.x] = __ldg(slot_blk + (size_t)n * K + threadIdx.x);
+  for (int i = tid; i < K; i += FIN_THREADS) sblk[i] = __ldg(slot_blk + (size_t)n * K + i);
   const uint32_t kz = ordered_key(thr_val[n]);
   __syncthreads();
-  constexpr int U = 8;  // candidates per thread and round: their 2 U loads are in flight together (a chain of memory latencies otherwise)
-  for (int i0 = 0; i0 < cap; i0 += U * FIN_THREADS) {
-    float zz[U], bb[U];
-    int ee[U];
+  // one sweep over the stored candidates: fn(composite), 0 for a candidate that does not count; a warp calls fn together (collectives allowed)
+  auto sweep_global = [&](auto fn) {
+    constexpr int U = 8;  // slots per warp and round: their 2 U loads are in flight together (a chain of memory latencies otherwise)
+    for (int s0 = warp; s0 < K; s0 += NW * U) {
+      float zz[U], bb[U];
+      int ee[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = min(i0 + u * FIN_THREADS + (int)threadIdx.x, cap - 1);
-      ee[u] = sblk[i >> 5] * BLK + (i & 31);
-      zz[u] = __ldg(cand + (size_t)n * cap + i);
-      bb[u] = __ldg(bias + min(ee[u], E - 1));
-    }
+      for (int u = 0; u < U; ++u) {
+        const int sv = min(s0 + u * NW, K - 1);
+        ee[u] = sblk[sv] * BLK + lane;
+        zz[u] = __ldg(cand + ((size_t)n * K + sv) * BLK + lane);
+        bb[u] = __ldg(bias + min(ee[u], E - 1));
+      }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t key = ordered_key(zz[u] + bb[u]);
-      if (i0 + u * FIN_THREADS + (int)threadIdx.x < cap && ee[u] < E && key >= kz) sel[atomicAdd(&nsel, 1)] = ((unsigned long long)key << 32) | (uint32_t)(~(uint32_t)ee[u]);
+      for (int u = 0; u < U; ++u) {
+        const uint32_t key = ordered_key(zz[u] + bb[u]);
+        fn((s0 + u * NW < K && ee[u] < E && key >= kz) ? ((unsigned long long)key << 32) | (uint32_t)(~(uint32_t)ee[u]) : 0ull);
+      }
     }
-  }
+  };
+  auto sweep_sel = [&](int c, auto fn) {  // the same over the survivors in shared memory
+    for (int i0 = 0; i0 < c; i0 += FIN_THREADS) fn(i0 + tid < c ? sel[i0 + tid] : 0ull);
+  };
+  // append the composites that pass `keep` to dst: one shared-memory atomic per warp and call
+  auto append = [&](unsigned long long* dst, int limit, unsigned long long x, bool keep) {
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m == 0u) return;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&nsel, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    const int pos = base + __popc(m & ((1u << lane) - 1u));
+    if (keep && pos < limit) dst[pos] = x;
+  };
+  // -> the largest bar found with K <= #(composites >= bar) <= limit (limit >= K; the composites are unique, so a bin of width 1 ends it)
+  auto raise_bar = [&](auto sweep, int limit) {
+    unsigned long long lo = (unsigned long long)kz << 32, hi = ~0ull;  // the K-th largest composite = the need-th largest inside [lo, hi]
+    int need = K;
+    for (;;) {
+      const unsigned long long width = hi - lo;
+      const int shift = width < 256ull ? 0 : 56 - __clzll((long long)width);  // (width >> shift) < 256
+      hist[tid] = 0u;  // (FIN_THREADS = 256 bins)
+      __syncthreads();
+      sweep([&](unsigned long long x) {
+        if (x != 0ull && x >= lo && x <= hi) atomicAdd(&hist[(int)((x - lo) >> shift)], 1u);
+      });
+      __syncthreads();
+      if (warp == 0) {  // from the top bin down to the one that holds the need-th largest: lane l owns bins 8l..8l+7, suffix sums over the lanes
+        int cb[8], mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { cb[j] = (int)hist[8 * lane + j]; mine += cb[j]; }
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_down_sync(0xffffffffu, incl, o);
+          if (lane + o < 32) incl += t;
+        }
+        int cum = incl - mine;  // composites in the bins of the higher lanes
+        const bool holds = (cum < need && need <= incl) || (lane == 0 && incl < need);  // (lane 0 takes it if the counts fell short: cannot happen)
+        if (holds) {
+          int d = 0;
+#pragma unroll
+          for (int j = 7; j >= 0; --j) {
+            if (need <= cum + cb[j] || j == 0) { d = j; break; }
+            cum += cb[j];
+          }
+          done_s = ((K - need) + cum + cb[d] <= limit) || shift == 0;  // (K - need composites lie above hi: all of them in the top K)
+          bar_s = lo + ((unsigned long long)(8 * lane + d) << shift); need_s = need - cum;
+        }
+      }
+      __syncthreads();
+      const unsigned long long blo = bar_s;
+      const bool done = done_s != 0;
+      const int nn = need_s;
+      __syncthreads();
+      if (done) return blo;
+      const unsigned long long t = blo + ((1ull << shift) - 1ull);
+      hi = t < hi ? t : hi; lo = blo; need = nn;
+    }
+  };
+  sweep_global([&](unsigned long long x) { append(sel, SEL_CAP, x, x != 0ull); });
   __syncthreads();
-  const int c = nsel;
+  int c = nsel;
+  if (c > SEL_CAP) {  // (block-uniform) rare
+    const unsigned long long bar = raise_bar(sweep_global, SEL_CAP);
+    if (tid == 0) nsel = 0;
+    __syncthreads();
+    sweep_global([&](unsigned long long x) { append(sel, SEL_CAP, x, x != 0ull && x >= bar); });
+    __syncthreads();
+    c = min(nsel, SEL_CAP);
+  }
+  int kpad = 32;
+  while (kpad < K) kpad <<= 1;
+  unsigned long long* srt = sel;
+  if (c > kpad) {  // more survivors than the sort needs: keep those at or above a bar with K <= count <= kpad
+    const unsigned long long bar = raise_bar([&](auto fn) { sweep_sel(c, fn); }, kpad);
+    if (tid == 0) nsel = 0;
+    __syncthreads();
+    sweep_sel(c, [&](unsigned long long x) { append(top, kpad, x, x != 0ull && x >= bar); });
+    __syncthreads();
+    c = min(nsel, kpad);
+    srt = top;
+  }
   int npad = 32;
   while (npad < c) npad <<= 1;
-  for (int i = c + threadIdx.x; i < npad; i += FIN_THREADS) sel[i] = 0ull;
+  for (int i = c + tid; i < npad; i += FIN_THREADS) srt[i] = 0ull;
   __syncthreads();
   for (int k = 2; k <= npad; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < npad; i += FIN_THREADS) {
+      for (int i = tid; i < npad; i += FIN_THREADS) {
         const int ixj = i ^ j;
         if (ixj > i) {
-          const unsigned long long x = sel[i], y = sel[ixj];
+          const unsigned long long x = srt[i], y = srt[ixj];
           const bool desc = (i & k) == 0;
-          if (desc ? (x < y) : (x > y)) { sel[i] = y; sel[ixj] = x; }
+          if (desc ? (x < y) : (x > y)) { srt[i] = y; srt[ixj] = x; }
         }
       }
       __syncthreads();
     }
   constexpr float LOG2E = 1.4426950408889634f;
-  for (int i = threadIdx.x; i < K; i += FIN_THREADS) {
-    const unsigned long long cmp = i < c ? sel[i] : 0ull;
+  for (int i = tid; i < K; i += FIN_THREADS) {
+    const unsigned long long cmp = i < c ? srt[i] : 0ull;
     float p = 0.f;
     int32_t e = -1;
     if (cmp) {
@@ -326,17 +418,17 @@ __global__ void __launch_bounds__(FIN_THREADS) infer_topk_final_kernel(const flo
 }
 
 // per team (one CTA of 4 warps): Tz = the K-th largest of the row's block maxima under the order (value descending, block ascending), and for
-// every block whether it is one of the K at or above it (a bit, bits[blk / 32][team]) and, if so, its slot 0..K-1 (a byte, slot[team][blk];
+// every block whether it is one of the K at or above it (a bit, bits[blk / 32][team]) and, if so, its slot 0..K-1 (16 bits, slot[team][blk];
 // slot_blk[team][slot] = the block).
 // Adaptive radix select on the order-preserving integer image of the maxima: the keys stay in registers (PL per thread); a round histograms
 // the ones inside the current range [lo, hi] into 256 equal bins of that range (shared-memory atomics -- the range starts at the row's
 // min..max, so the keys spread over the bins), every warp scans the bins from the top for the one that holds the wanted rank, and the
 // range shrinks to that bin.  As soon as the bin holds <= 128 keys, their (key, block) composites are gathered and ranked by counting; on
 // logits one round is the rule.  More than 128 EQUAL keys (a bin of width 1): the select restarts on the block numbers of those keys.
-// K <= 128 (ntf_infer_topk_supported): a slot fits a byte next to the 255 marker.
+// K <= 1024 (ntf_infer_topk_supported).
 template <int PL>
 __global__ void __launch_bounds__(128) blockmax_threshold_kernel(const float* __restrict__ bm, int nblk, int nwords, int K, float* __restrict__ thr_val,
-                                                                 uint8_t* __restrict__ slot, uint32_t* __restrict__ bits, int32_t* __restrict__ slot_blk) {
+                                                                 uint16_t* __restrict__ slot, uint32_t* __restrict__ bits, int32_t* __restrict__ slot_blk) {
   __shared__ __align__(16) uint32_t hist[3][256];
   __shared__ uint32_t red[2][4];
   __shared__ unsigned long long list[128];
@@ -436,7 +528,7 @@ __global__ void __launch_bounds__(128) blockmax_threshold_kernel(const float* __
     if (lane == 0 && 4 * i + w < nwords) bits[(size_t)(4 * i + w) * gridDim.x + team] = word;  // [nwords][B]: pass 2 reads it by 32 teams
     if (in) {
       const int sl = atomicAdd(&nslot, 1);
-      slot[(size_t)team * nblk + blk] = (uint8_t)sl;
+      slot[(size_t)team * nblk + blk] = (uint16_t)sl;
       slot_blk[(size_t)team * K + sl] = blk;
     }
   }
@@ -523,7 +615,7 @@ ItWs it_ws(int B, int h, int E, int K) {
   w.bm = w.a16 + align_up((size_t)B * h * sizeof(__half), 1024);
   w.tv = w.bm + align_up((size_t)B * nblk * sizeof(float), 1024);
   w.slot = w.tv + align_up((size_t)B * sizeof(float), 1024);
-  w.bits = w.slot + align_up((size_t)B * nblk, 1024);
+  w.bits = w.slot + align_up((size_t)B * nblk * sizeof(uint16_t), 1024);
   w.sblk = w.bits + align_up((size_t)B * cdiv((int)nblk, 32) * sizeof(uint32_t), 1024);
   w.cand = w.sblk + align_up((size_t)B * K * sizeof(int32_t), 1024);
   w.total = w.cand + align_up((size_t)B * (size_t)(BLK * K) * sizeof(float), 1024);
@@ -542,14 +634,14 @@ extern "C" int ntf_to_half(ntf_ctx* ctx, void* stream, const float* x, size_t n,
 
 // the fused path needs the tensor-core width, at least K blocks of 32 experts per team, and a candidate list that sorts in shared memory
 extern "C" int ntf_infer_topk_supported(int B, int h, int E, int K) {
-  return (h == HK && B >= 1 && K >= 1 && K <= 128 && (long long)K * BLK <= (long long)E && cdiv(cdiv(E, TX) * 4, 128) <= 32) ? 1 : 0;  // (E <= 131072 per shard)
+  return (h == HK && B >= 1 && K >= 1 && K <= KMAX && (long long)K * BLK <= (long long)E && cdiv(cdiv(E, TX) * 4, 128) <= 32) ? 1 : 0;  // (E <= 131072 per shard)
 }
 
 extern "C" size_t ntf_infer_topk_workspace_bytes(int B, int h, int E, int K) { return it_ws(B, h, E, K).total; }
 
 extern "C" int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_args* a, void* workspace, size_t workspace_bytes) {
   NTF_REQUIRE(ctx && a && a->W16 && a->b && a->vals && a->idx && (a->A || a->A16), NTF_ERR_BAD_ARG, "infer_topk: null pointer");
-  NTF_REQUIRE(ntf_infer_topk_supported(a->B, a->h, a->E, a->K), NTF_ERR_UNSUPPORTED, "infer_topk: B=%d h=%d E=%d K=%d (needs h=%d, K <= 128, 32*K <= E <= 131072)", a->B, a->h, a->E,
+  NTF_REQUIRE(ntf_infer_topk_supported(a->B, a->h, a->E, a->K), NTF_ERR_UNSUPPORTED, "infer_topk: B=%d h=%d E=%d K=%d (needs h=%d, K <= 1024, 32*K <= E <= 131072)", a->B, a->h, a->E,
               a->K, HK);
   const ItWs w = it_ws(a->B, a->h, a->E, a->K);
   NTF_REQUIRE(workspace && workspace_bytes >= w.total, NTF_ERR_WORKSPACE, "infer_topk: workspace too small");
@@ -574,7 +666,7 @@ extern "C" int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_a
   g.nblk = g.nct * 4;
   g.bm = (float*)(ws + w.bm);
   float* tv = (float*)(ws + w.tv);
-  uint8_t* slot = (uint8_t*)(ws + w.slot);
+  uint16_t* slot = (uint16_t*)(ws + w.slot);
   uint32_t* bits = (uint32_t*)(ws + w.bits);
   g.slot = slot; g.bits = bits; g.nwords = cdiv(g.nblk, 32);
   g.cand = (float*)(ws + w.cand);
@@ -612,9 +704,7 @@ extern "C" int ntf_infer_topk(ntf_ctx* ctx, void* stream, const ntf_infer_topk_a
     auto* fin = a->K <= 8 ? infer_topk_final_warp_kernel<1> : a->K <= 16 ? infer_topk_final_warp_kernel<2> : a->K <= 24 ? infer_topk_final_warp_kernel<3> : infer_topk_final_warp_kernel<4>;
     NTF_COUNT_LAUNCH; NTF_CUDA(launch_chained(fin, cdiv(a->B, 4), 128, 0, st, pdl, (const float*)g.cand, (const int32_t*)sblk, a->b, (const float*)tv, cap, a->K, a->E, a->e_lo, a->B, a->vals, a->idx));
   } else {
-    int npad = 32;
-    while (npad < cap) npad <<= 1;
-    NTF_COUNT_LAUNCH; NTF_CUDA(launch_chained(infer_topk_final_kernel, a->B, FIN_THREADS, (size_t)npad * 8, st, pdl, g.cand, sblk, a->b, tv, cap, a->K, a->E, a->e_lo, a->vals, a->idx));
+    NTF_COUNT_LAUNCH; NTF_CUDA(launch_chained(infer_topk_final_kernel, a->B, FIN_THREADS, 0, st, pdl, (const float*)g.cand, (const int32_t*)sblk, a->b, (const float*)tv, cap, a->K, a->E, a->e_lo, a->vals, a->idx));
   }
   NTF_LAUNCH_CHECK();
   return NTF_OK;

@@ -907,7 +907,7 @@ class Engine:
 
     def topk(self, sp, b0, B, K, scores_buf, vals, idx):
         """the K best experts per team in rank order; only [B,K] leaves the GPU (fnn.py:213-218 keeps [N,E] on the host).
-        Tensor-core mode with K <= 128 and 32*K <= E: hidden layers + output layer + sigmoid + selection in ONE library call
+        Tensor-core mode with K <= 1024 and 32*K <= E: hidden layers + output layer + sigmoid + selection in ONE library call
         (ntf_fnn_infer_topk), the [B,E] scores never reach HBM; otherwise scores -> ntf_topk_select."""
         if self.fused_topk_ok(B, K):
             if self.shard[1] == 1: return self._topk_one_call(sp, b0, B, K, vals, idx)

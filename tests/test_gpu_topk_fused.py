@@ -52,7 +52,7 @@ def check_against_dense(P, vals, idx, K, e_lo=0):
     return int(diff.sum())
 
 
-@pytest.mark.parametrize('B,E,K', [(1, 4096, 10), (37, 3001, 2), (130, 5000, 10), (256, 4224, 100), (1000, 40000, 10), (1000, 40000, 128), (300, 44774, 20), (129, 70, 2)])
+@pytest.mark.parametrize('B,E,K', [(1, 4096, 10), (37, 3001, 2), (130, 5000, 10), (256, 4224, 100), (1000, 40000, 10), (1000, 40000, 128), (300, 44774, 20), (129, 70, 2), (200, 40000, 1000), (64, 32768, 1024), (130, 9000, 250)])
 def test_fused_topk_matches_oracle_ranking_of_the_dense_scores(ops, ws, B, E, K):
     torch.manual_seed(B + E + K)
     h = 128
@@ -62,7 +62,7 @@ def test_fused_topk_matches_oracle_ranking_of_the_dense_scores(ops, ws, B, E, K)
     ops.infer_scores(1, A, W, b, B, h, E, P, ws)  # the unfused tensor-core path on the same operands
     vals, idx = run_fused(ops, ws, A, W, b, K)
     ndiff = check_against_dense(P.cpu().numpy(), vals, idx, K)
-    assert ndiff <= max(2, B * K // 200)  # rounding-collapsed ties are rare
+    assert ndiff <= max(2, B * K // (200 if K <= 128 else 100))  # rounding-collapsed ties are rare (less so deep down the ranking, where the scores crowd)
 
 
 def test_fused_topk_exact_ties_follow_the_lower_id_rule(ops, ws):
@@ -105,6 +105,24 @@ def test_fused_topk_many_equal_block_maxima_restart_the_select_on_block_numbers(
     vals, idx = run_fused(ops, ws, A, Z, zb, K)
     want = raised + [e for e in range(E) if e not in raised][:K - len(raised)]
     assert (idx == np.asarray(want)[None, :]).all(), idx[0]
+    check_against_dense(P.cpu().numpy(), vals, idx, K)
+
+
+def test_fused_topk_large_k_on_a_plateau_of_equal_scores_takes_the_refinement_path(ops, ws):
+    """K = 1000 with far more than 4096 candidates at or above the bar (every expert scores the same but for a few): the final kernel's radix
+    refinement over the unique (score, expert) composites must still return exactly the oracle's K, lowest expert ids first inside the plateau"""
+    B, h, E, K = 9, 128, 40000, 1000
+    A = torch.randn(B, h, generator=torch.Generator().manual_seed(4)).abs().to(DEV)
+    Z, zb = torch.zeros(E, h, device=DEV), torch.zeros(E, device=DEV)
+    raised = [39999, 3, 20000, 20001, 31]
+    zb[raised] = torch.tensor([2.0, 1.5, 1.0, 0.75, 0.5], device=DEV)
+    lowered = list(range(100, 164))  # a whole run of experts below the plateau: they must be skipped
+    zb[lowered] = -1.0
+    P = torch.empty(B, E, device=DEV)
+    ops.infer_scores(1, A, Z, zb, B, h, E, P, ws)
+    vals, idx = run_fused(ops, ws, A, Z, zb, K)
+    want = raised + [e for e in range(E) if e not in raised and e not in lowered][:K - len(raised)]
+    assert (idx == np.asarray(want)[None, :]).all(), (idx[0][:12], idx[0][-5:])
     check_against_dense(P.cpu().numpy(), vals, idx, K)
 
 
