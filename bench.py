@@ -564,7 +564,7 @@ def staging_leg(args, tv, splits, dev, sync, pk):
     out['cooccurrence'] = {'what': f'member^T . skill [{E} x {Sn}] over {T} teams, {len(splits["test"])} test teams skipped', 'ms': t * 1e3, 'pairs': pairs, 'nnz': int(ci.numel()),
                            'value': pairs / t, 'unit': '(expert, skill) pairs/s', 'algorithmic_bytes': nbytes, 'achieved_gbs': nbytes / t / 1e9, 'peak_gbs': pk['hbm_gbs'],
                            'frac': nbytes / t / 1e9 / pk['hbm_gbs'], 'bound': 'hbm/l2 + shared-memory atomics',
-                           'cpu_baseline': {'value': pairs_cpu / dt, 'unit': '(expert, skill) pairs/s', 'cores': 1, 'kind': 'reference (team.py:325-335 verbatim: lil copies, scipy product)',
+                           'cpu_baseline': {'value': pairs_cpu / dt, 'unit': '(expert, skill) pairs/s', 'cores': 1, 'kind': 'port (oracle/staging_oracle.py: the statements of team.py:325-335 -- lil copies, rows emptied, scipy product)',
                                             'sample': f'the first {sample} teams ({dt:.1f} s)'}}
     # --- id lists -> multi-hot rows (both matrices of teamsvecs, the lists = the rows shuffled)
     ids_m, ids_s = i32(M.indices[::-1].copy()), i32(S.indices[::-1].copy())

@@ -16,9 +16,9 @@ import scipy.sparse as sp
 def _dev(device):
     import torch
     from . import util
-    d = torch.device(util.first_device(device) if not isinstance(device, torch.device) else device)
-    if d.type != 'cuda': raise RuntimeError(f'opentf_b200.staging runs on a CUDA device only (got {device}); there is no host implementation in the product')
-    return d
+    if not str(device).startswith('cuda'): raise RuntimeError(f'opentf_b200.staging runs on a CUDA device only (got {device}); there is no host implementation in the product')
+    if not torch.cuda.is_available(): raise RuntimeError('opentf_b200.staging needs a CUDA device (none is visible); there is no host implementation in the product')
+    return torch.device(util.first_device(device) if not isinstance(device, torch.device) else device)
 
 
 def _i32(a, dev):

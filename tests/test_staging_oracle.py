@@ -73,3 +73,13 @@ def test_oracle_cooccurrence_wraps_like_the_reference_uint8_product():
     for t in range(300): m[t, 1] = 1; s[t, 2] = 1
     co = SO.cooccurrence(m, s)
     assert co.dtype == np.uint8 and co.nnz == 1 and co[1, 2] == 44
+
+
+def test_product_staging_has_no_host_path():
+    """opentf_b200.staging is the device implementation only: on a CPU device (or without a GPU) every entry point raises instead of computing"""
+    from opentf_b200 import staging
+    m, s = sp.csr_matrix(np.eye(3, dtype=np.uint8)), sp.csr_matrix(np.eye(3, dtype=np.uint8))
+    for call in (lambda: staging.csr_from_lists([0, 1], [0], 3, device='cpu'), lambda: staging.cooccurrence(m, s, device='cpu'),
+                 lambda: staging.calculate_skill_coverage(s, np.eye(3, dtype=np.float32), m, topks='1', device='cpu')):
+        with pytest.raises(RuntimeError, match='CUDA'):
+            call()
