@@ -148,3 +148,35 @@ def test_sampler_oracle_edge_cases():
     # fewer negatives than ns -> padded with -1
     out = SO.sample_row('uniform', 7, 0, 0, [0, 1, 2], 5, 4, None)
     assert sorted(out) == [-1, -1, 3, 4]
+
+
+def test_evaluate_hands_skill_coverage_to_the_device_function_and_writes_the_reference_csvs(toy, tmp_path, monkeypatch):
+    """Ntf.evaluate with metrics.other = ['skill_coverage_2,5,10'] (ntf.py:72-78): the wiring around opentf_b200.staging.calculate_skill_coverage --
+    which rows of the skill matrix, which prediction file, which co-occurrence matrix, the cut-offs, the device -- and the CSVs that come out.  The
+    device function itself is replaced by the oracle here (this test runs without a GPU; tests/test_gpu_staging.py checks the real one)."""
+    import pandas as pd
+    import scipy.sparse as sp
+    from oracle import staging_oracle as SO
+    from opentf_b200 import staging
+    from opentf_b200.ntf import Ntf
+    skill, member, splits, z = toy('dblp')
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'staging_dblp.npz'))
+    co = sp.csr_matrix((g['co/data'].astype(np.uint8), g['co/indices'], g['co/indptr']), shape=(member.shape[1], skill.shape[1]))
+    seen = {}
+
+    def fake(X, Y_, expertskillvecs, per_instance=False, topks='2,5,10', device='cuda:0'):
+        seen.update(n=X.shape[0], topks=topks, device=device, same_co=(expertskillvecs != co).nnz == 0)
+        cov = SO.skill_coverage(X, Y_, expertskillvecs, topks)
+        df = pd.DataFrame({f'skill_coverage_{k}': v for k, v in cov.items()})
+        return df, df.mean().to_frame('mean').rename_axis('metrics')
+    monkeypatch.setattr(staging, 'calculate_skill_coverage', fake)
+    m = Ntf(str(tmp_path), 'cuda:0', 0, {})
+    torch.save({'y_pred': torch.as_tensor(z['pred/f0']), 'uncertainty': None}, f'{m.output}/f0.test.pred')
+    tv = {'skill': skill.tolil(), 'member': member.tolil(), 'skillcoverage': co}
+    one_fold = {'test': splits['test'], 'folds': {0: splits['folds'][0]}}
+    m.evaluate(tv, one_fold, {'on_train': False, 'per_instance': True, 'per_epoch': False, 'topK': None, 'metrics': {'trec': [], 'other': ['skill_coverage_2,5,10']}})
+    assert seen == {'n': len(splits['test']), 'topks': '2,5,10', 'device': 'cuda:0', 'same_co': True}
+    inst = pd.read_csv(f'{m.output}/f0.test.pred.eval.instance.csv')
+    for k in (2, 5, 10): assert np.allclose(inst[f'skill_coverage_{k}'].to_numpy(), g[f'pred/skill_coverage_{k}'], atol=5e-6)  # (the reference's own frame, %.5f in the file)
+    mean = pd.read_csv(f'{m.output}/test.pred.eval.mean.csv', index_col=0)
+    assert abs(mean.loc['skill_coverage_10', 'mean'] - g['pred/skill_coverage_10'].mean()) < 1e-9
