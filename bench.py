@@ -405,6 +405,7 @@ def run_ours(args):
                             if pk['_source'] == 'measured' else 'fallback 1.59 PFLOP/s (B200_PROFILING.md)'),
             'frac_of_sustained_peak': flops / (k_ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
             'avg_launch_ms': k_ms, 'share_of_step': k_ms * args.steps / ms_k, 'ms_per_step_with_event_pairs': ms_k / args.steps,
+            'timed': 'a second pass of the same W + K steps with an event pair around the output-layer call inside every step graph (external event-record nodes); `value` is timed on graphs without them: nothing overlaps across such a node and the step is ~10 us slower with them',
             'note': 'persistent dense pass (out_tc2_kernel) + sparse correction pass (out_fix_kernel); h=128: per logit 768 tensor flops vs ~10 issue slots + 1.25 MUFU ops of epilogue: the epilogue binds before the tensor pipe (DESIGN.md 4.1)'}
     roof['frac'] = roof['achieved'] / roof['peak']
     out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': G, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
